@@ -1,0 +1,179 @@
+/* ptb200 — C ABI of the B200-native render hot path (drop-in for PathTracerWithCuda's
+ * Kernel/ path-trace loop).  Plain pointers and sizes only; no C++/torch types.
+ *
+ * Every entry point names the reference interface it replaces (paths are relative to
+ * /root/reference/gpu_path_tracer/).  The reference-side binding a maintainer would add is
+ * shown in INTEGRATION.md.
+ *
+ * Conventions: functions returning int return 0 on success, non-zero on failure with a
+ * message retrievable through ptb_last_error() (the reference itself only prints
+ * "[Error]..." / "[Cuda]Error..." and carries on — Others/utilities.hpp:10-18).  A renderer
+ * handle is bound to one CUDA device and is not re-entrant; all calls are synchronous unless
+ * stated otherwise (the reference returns after cudaDeviceSynchronize,
+ * Kernel/path_tracer_kernel.cu:779).  There is NO CPU fallback: without a CUDA device every
+ * compute entry point fails. */
+#ifndef PTB200_H
+#define PTB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct ptb_renderer ptb_renderer;
+
+/* Same 64-byte layout as the reference's `render_camera` (Core/camera.h:14-23): three float3,
+ * 4 bytes of padding (float2 is 8-byte aligned), resolution, fov in DEGREES, aperture, focal. */
+typedef struct ptb_camera
+{
+	float eye[3];
+	float view[3];
+	float up[3];
+	float _pad;
+	float resolution[2];
+	float fov[2];
+	float aperture_radius;
+	float focal_distance;
+} ptb_camera;
+
+/* Same 84-byte layout as the reference's `material` (Core/material.h:49-78). */
+typedef struct ptb_material
+{
+	float diffuse_color[3];
+	float emission_color[3];
+	float specular_color[3];
+	uint8_t is_transparent; uint8_t _pad[3];
+	float roughness;
+	float refraction_index;
+	float extinction_coefficient;
+	float absorption_coefficient[3];
+	float reduced_scattering_coefficient[3];
+	int32_t diffuse_texture_id;
+	int32_t specular_texture_id;
+} ptb_material;
+
+/* Counters of the last ptb_render* call (M1/M2 inputs). */
+typedef struct ptb_stats
+{
+	int64_t passes;            /* passes rendered by the call */
+	int64_t ray_segments;      /* sum over depth of live paths entering the extend stage */
+	int64_t kernel_launches;   /* CUDA kernels launched by the call */
+	double gpu_ms_total;       /* CUDA-event time of the whole call on the render stream */
+	double gpu_ms_extend;      /* CUDA-event time spent in the extend (closest-hit) kernel; 0 unless profiling enabled */
+	int64_t bvh_nodes;         /* wide-BVH node count of the loaded scene */
+	int64_t bvh_bytes;         /* bytes of node + triangle intersection data */
+	int64_t nodes_visited;     /* instrumented builds only (ptb_set_option "count_traversal" = 1) */
+	int64_t tris_tested;
+} ptb_stats;
+
+const char* ptb_last_error(void);
+int ptb_version(void);
+/* number of visible CUDA devices (0 = the library cannot render) */
+int ptb_device_count(void);
+
+/* ---- lifecycle -------------------------------------------------------------------------
+ * ptb_create        = config_parser::load_config + create_config_device_data
+ *                     (Core/config_parser.cpp:8-124,159-187) followed by path_tracer::init's
+ *                     buffer allocation (Core/path_tracer.cpp:18-38,
+ *                     Kernel/path_tracer_kernel.cu:782-796) and the default orbit camera of
+ *                     Main/window.cpp:356-360 / Core/camera.cpp:3-14.
+ * ptb_destroy       = path_tracer::~path_tracer (Core/path_tracer.cpp:3-16). */
+ptb_renderer* ptb_create(const char* config_json_path, int cuda_device);
+void ptb_destroy(ptb_renderer* r);
+
+/* scene_parser::set_scene_file_directory (Core/scene_parser.cpp:9-35): '\n'-separated list of
+ * "*.json" under scene_dir, sorted; returns the count or -1. */
+int ptb_list_scenes(const char* scene_dir, char* out, int cap);
+
+/* path_tracer::init_scene_device_data (Core/path_tracer.cpp:371-395): parse the scene JSON
+ * (Core/scene_parser.cpp:37-442), load OBJ groups (Core/triangle_mesh.cpp:8-213), upload and
+ * build the acceleration structure (triangle_mesh.cpp:498-655).  Paths inside the scene file
+ * are resolved against asset_root (the reference resolves them against its CWD); both '\\' and
+ * '/' separators are accepted.  Resets the accumulation like a scene switch does. */
+int ptb_load_scene(ptb_renderer* r, const char* scene_json_path, const char* asset_root);
+/* path_tracer::release_scene_device_data (Core/path_tracer.cpp:397-406) */
+int ptb_release_scene(ptb_renderer* r);
+
+/* view_camera::get_render_camera with the constructor defaults (Core/camera.cpp:3-14,80-98)
+ * for a given resolution; aperture/focal < 0 keep the defaults (0 and radius=14). */
+int ptb_default_camera(float width, float height, float aperture_radius, float focal_distance, ptb_camera* out);
+int ptb_set_camera(ptb_renderer* r, const ptb_camera* cam);
+int ptb_get_camera(ptb_renderer* r, ptb_camera* out);
+
+/* ---- rendering ---------------------------------------------------------------------------
+ * ptb_render(r, n)  = n consecutive path_tracer::render() calls (Core/path_tracer.cpp:40-99):
+ *                     pass_counter advances by n; pass k uses seed k
+ *                     (Kernel/path_tracer_kernel.cu:712) and adds clamp(L_k, 0, 2*MaxDepth) to
+ *                     the float accumulation image (:644-651).
+ * ptb_clear         = path_tracer::clear -> reset_image (Core/image.cpp:36-40).
+ * ptb_render_strided: multi-GPU sharding hook — renders passes first, first+stride, ... (n of
+ *                     them) into the local accumulation WITHOUT touching pass_counter's
+ *                     meaning for other ranks; see ptb_finalize. */
+int ptb_render(ptb_renderer* r, int n_passes);
+int ptb_render_strided(ptb_renderer* r, int first_pass, int stride, int n_passes);
+int ptb_clear(ptb_renderer* r);
+int ptb_pass_counter(ptb_renderer* r);
+int ptb_width(ptb_renderer* r);
+int ptb_height(ptb_renderer* r);
+
+/* image::pixels_device (float3 running sum, Core/image.h:16) and image::pixels_256_device
+ * (gamma-corrected 8-bit, Kernel/path_tracer_kernel.cu:653-680) copied to HOST buffers of
+ * width*height*3 elements. */
+int ptb_image_f32(ptb_renderer* r, float* out_rgb_sum, int* out_passes);
+int ptb_image_u8(ptb_renderer* r, uint8_t* out_rgb);
+/* un-clamped radiance of the most recent pass (the reference's accumulated_colors work buffer) */
+int ptb_last_pass_f32(ptb_renderer* r, float* out_rgb);
+
+/* Device pointer of the float3 accumulation image (3*width*height floats) so a caller can
+ * sum it across ranks with NCCL, then ptb_finalize(total_passes) runs the mean/gamma/8-bit
+ * step of pixel_256_transform_gamma_corrected_kernel (:653-680) on the reduced sum. */
+void* ptb_image_device_ptr(ptb_renderer* r);
+int ptb_finalize(ptb_renderer* r, int total_passes);
+/* enqueue work without the trailing synchronize / wait for it (benchmarks use CUDA events) */
+int ptb_render_async(ptb_renderer* r, int n_passes);
+int ptb_synchronize(ptb_renderer* r);
+void* ptb_stream(ptb_renderer* r);
+
+/* Closest hit of a caller-supplied ray batch (n rays x 6 floats: origin, direction), same
+ * acceptance rules as Kernel/path_tracer_kernel.cu:418-454.  out_prim: global triangle index
+ * >= 0, sphere s -> -(s+2), miss -> -1; out_t: hit distance (+inf on miss); out_bary may be
+ * NULL or n x 2 floats (t1, t2).  Host pointers. */
+int ptb_trace_batch(ptb_renderer* r, const float* rays6, int n, int32_t* out_prim, float* out_t, float* out_bary);
+/* same query answered by a brute-force scan over every primitive (test hook) */
+int ptb_trace_batch_bruteforce(ptb_renderer* r, const float* rays6, int n, int32_t* out_prim, float* out_t);
+/* rays the camera stage generates for pass `pass` (Kernel/path_tracer_kernel.cu:299-379): n = w*h x 6 floats */
+int ptb_generate_rays(ptb_renderer* r, int pass, float* out_rays6);
+
+int ptb_get_stats(ptb_renderer* r, ptb_stats* out);
+/* string options: "bvh_builder" = "gpu_lbvh" | "host_sah"; "passes_in_flight" = "1".."64";
+ * "profile_stages" = "0"|"1"; "count_traversal" = "0"|"1"; "sort_by_material" = "0"|"1". */
+int ptb_set_option(ptb_renderer* r, const char* key, const char* value);
+
+/* ---- loaded-scene introspection (flat host copies; used by the parity tests) ------------- */
+int ptb_scene_counts(ptb_renderer* r, int* n_triangles, int* n_materials, int* n_spheres, int* n_textures, int* cube_length, int* n_meshes);
+/* per triangle 24 floats: v0 v1 v2 n0 n1 n2 uv0 uv1 uv2 (Core/triangle.h:11-25) + material index */
+int ptb_scene_triangles(ptb_renderer* r, float* out24, int32_t* out_material);
+int ptb_scene_materials(ptb_renderer* r, ptb_material* out);
+/* per sphere: center[3], radius, then ptb_material (Core/sphere.h:11-16) = 100 bytes */
+int ptb_scene_spheres(ptb_renderer* r, void* out100);
+int ptb_scene_texture(ptb_renderer* r, int index, int* width, int* height, uint8_t* out_rgba /* may be NULL */);
+int ptb_scene_cubemap_face(ptb_renderer* r, int face, uint8_t* out_rgba);
+/* the parsed configuration as the reference's 96-byte `configuration` (Core/configuration.h:9-34) */
+int ptb_get_config(ptb_renderer* r, void* out96);
+
+/* ---- reference-signature compatibility entry (Core/path_tracer_kernel.h:18-54) -----------
+ * Declared with opaque pointers; the layouts are the reference's.  All
+ * scene pointers may be managed or device memory; render_camera is a host pointer. */
+void ptb_path_tracer_kernel(
+	int mesh_num, void** bvh_nodes_device, void* triangles_device, int triangle_num,
+	int sphere_num, void* spheres_device, int pixel_count,
+	float* image_pixels, uint8_t* image_pixels_256, int pass_counter,
+	const ptb_camera* render_camera, void* sky_cube_map_device,
+	void* mesh_textures_device, int texture_num, void* config_device);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PTB200_H */

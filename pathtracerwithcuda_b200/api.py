@@ -1,0 +1,361 @@
+"""ctypes binding of libptb200.so (the C ABI in include/ptb200.h) plus a host-side mirror of the
+reference's `path_tracer` class (Core/path_tracer.h:54-61: init / init_scene_device_data / render /
+clear / release_scene_device_data).
+
+There is no CPU or PyTorch fallback: if the CUDA library is missing the import of the binding fails,
+and every compute call fails on a host-only handle.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "libptb200.so")
+
+
+class PtbError(RuntimeError):
+    pass
+
+
+class Camera(ctypes.Structure):
+    """Reference `render_camera` layout (Core/camera.h:14-23), 64 bytes."""
+    _fields_ = [("eye", ctypes.c_float * 3), ("view", ctypes.c_float * 3), ("up", ctypes.c_float * 3), ("_pad", ctypes.c_float),
+                ("resolution", ctypes.c_float * 2), ("fov", ctypes.c_float * 2), ("aperture_radius", ctypes.c_float),
+                ("focal_distance", ctypes.c_float)]
+
+    def as_array(self):
+        return np.frombuffer(bytes(self), dtype=np.float32).copy()
+
+    @staticmethod
+    def from_array(a):
+        a = np.ascontiguousarray(a, np.float32)
+        assert a.size == 16
+        return Camera.from_buffer_copy(a.tobytes())
+
+
+class Stats(ctypes.Structure):
+    _fields_ = [("passes", ctypes.c_int64), ("ray_segments", ctypes.c_int64), ("kernel_launches", ctypes.c_int64),
+                ("gpu_ms_total", ctypes.c_double), ("gpu_ms_extend", ctypes.c_double), ("bvh_nodes", ctypes.c_int64),
+                ("bvh_bytes", ctypes.c_int64), ("nodes_visited", ctypes.c_int64), ("tris_tested", ctypes.c_int64)]
+
+
+MATERIAL_DTYPE = np.dtype([("diffuse_color", np.float32, 3), ("emission_color", np.float32, 3), ("specular_color", np.float32, 3),
+                           ("is_transparent", np.uint8), ("_pad", np.uint8, 3), ("roughness", np.float32),
+                           ("refraction_index", np.float32), ("extinction_coefficient", np.float32),
+                           ("absorption_coefficient", np.float32, 3), ("reduced_scattering_coefficient", np.float32, 3),
+                           ("diffuse_texture_id", np.int32), ("specular_texture_id", np.int32)])
+assert MATERIAL_DTYPE.itemsize == 84
+SPHERE_DTYPE = np.dtype([("center", np.float32, 3), ("radius", np.float32), ("mat", MATERIAL_DTYPE)])
+assert SPHERE_DTYPE.itemsize == 100
+CONFIG_DTYPE = np.dtype([("width", np.int32), ("height", np.int32), ("use_fullscreen", np.uint8), ("_p0", np.uint8, 3),
+                         ("block_size", np.int32), ("max_block_size", np.int32), ("max_tracer_depth", np.int32),
+                         ("vector_bias_length", np.float32), ("energy_exist_threshold", np.float32), ("sss_threshold", np.float32),
+                         ("use_sky_box", np.uint8), ("use_sky", np.uint8), ("use_bilinear", np.uint8), ("gamma_correction", np.uint8),
+                         ("use_anti_alias", np.uint8), ("_p1", np.uint8, 3), ("fov", np.float32),
+                         ("bvh_leaf_node_triangle_num", np.int32), ("bvh_bucket_max_divide_internal_num", np.int32),
+                         ("bvh_build_block_size", np.int32), ("bvh_build", np.int32), ("air_refraction_index", np.float32),
+                         ("air_absorption_coef", np.float32, 3), ("air_reduced_scattering_coef", np.float32, 3),
+                         ("cuda_acceleration", np.uint8), ("_p2", np.uint8, 3)])
+assert CONFIG_DTYPE.itemsize == 96
+
+_lib = None
+
+
+def load_library():
+    """Loads libptb200.so, building it first if the sources are newer. Fails loudly if impossible."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(_LIB_PATH):
+        from . import build as _build
+        _build.build()
+    L = ctypes.CDLL(_LIB_PATH)
+    vp, ci, cf, cp = ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_char_p
+    L.ptb_last_error.restype = cp
+    L.ptb_create.restype = vp
+    L.ptb_create.argtypes = [cp, ci]
+    L.ptb_destroy.argtypes = [vp]
+    L.ptb_list_scenes.argtypes = [cp, cp, ci]
+    L.ptb_load_scene.argtypes = [vp, cp, cp]
+    L.ptb_release_scene.argtypes = [vp]
+    L.ptb_default_camera.argtypes = [cf, cf, cf, cf, ctypes.POINTER(Camera)]
+    L.ptb_set_camera.argtypes = [vp, ctypes.POINTER(Camera)]
+    L.ptb_get_camera.argtypes = [vp, ctypes.POINTER(Camera)]
+    L.ptb_render.argtypes = [vp, ci]
+    L.ptb_render_async.argtypes = [vp, ci]
+    L.ptb_render_strided.argtypes = [vp, ci, ci, ci]
+    L.ptb_synchronize.argtypes = [vp]
+    L.ptb_stream.restype = vp
+    L.ptb_stream.argtypes = [vp]
+    L.ptb_clear.argtypes = [vp]
+    L.ptb_pass_counter.argtypes = [vp]
+    L.ptb_width.argtypes = [vp]
+    L.ptb_height.argtypes = [vp]
+    L.ptb_image_f32.argtypes = [vp, vp, ctypes.POINTER(ci)]
+    L.ptb_image_u8.argtypes = [vp, vp]
+    L.ptb_last_pass_f32.argtypes = [vp, vp]
+    L.ptb_image_device_ptr.restype = vp
+    L.ptb_image_device_ptr.argtypes = [vp]
+    L.ptb_finalize.argtypes = [vp, ci]
+    L.ptb_trace_batch.argtypes = [vp, vp, ci, vp, vp, vp]
+    L.ptb_trace_batch_bruteforce.argtypes = [vp, vp, ci, vp, vp]
+    L.ptb_generate_rays.argtypes = [vp, ci, vp]
+    L.ptb_get_stats.argtypes = [vp, ctypes.POINTER(Stats)]
+    L.ptb_set_option.argtypes = [vp, cp, cp]
+    L.ptb_scene_counts.argtypes = [vp] + [ctypes.POINTER(ci)] * 6
+    L.ptb_scene_triangles.argtypes = [vp, vp, vp]
+    L.ptb_scene_materials.argtypes = [vp, vp]
+    L.ptb_scene_spheres.argtypes = [vp, vp]
+    L.ptb_scene_texture.argtypes = [vp, ci, ctypes.POINTER(ci), ctypes.POINTER(ci), vp]
+    L.ptb_scene_cubemap_face.argtypes = [vp, ci, vp]
+    L.ptb_get_config.argtypes = [vp, vp]
+    _lib = L
+    return L
+
+
+def last_error():
+    return load_library().ptb_last_error().decode(errors="replace")
+
+
+def device_count():
+    return load_library().ptb_device_count()
+
+
+def default_camera(width, height, aperture_radius=-1.0, focal_distance=-1.0):
+    cam = Camera()
+    load_library().ptb_default_camera(float(width), float(height), float(aperture_radius), float(focal_distance), ctypes.byref(cam))
+    return cam
+
+
+def _ptr(a):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+class Renderer:
+    """Thin object wrapper over the ptb_* handle API."""
+
+    def __init__(self, config_json_path, device=0):
+        self.lib = load_library()
+        self.handle = self.lib.ptb_create(os.fsencode(config_json_path), int(device))
+        if not self.handle:
+            raise PtbError(last_error())
+        self.device = device
+        self.width = self.lib.ptb_width(self.handle)
+        self.height = self.lib.ptb_height(self.handle)
+
+    def close(self):
+        if self.handle:
+            self.lib.ptb_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            raise PtbError(last_error())
+
+    # -- scene ---------------------------------------------------------------------------------
+    def load_scene(self, scene_json_path, asset_root=""):
+        self._check(self.lib.ptb_load_scene(self.handle, os.fsencode(scene_json_path), os.fsencode(asset_root)))
+
+    def release_scene(self):
+        self._check(self.lib.ptb_release_scene(self.handle))
+
+    def set_option(self, key, value):
+        self._check(self.lib.ptb_set_option(self.handle, key.encode(), str(value).encode()))
+
+    def config(self):
+        out = np.zeros(1, CONFIG_DTYPE)
+        self._check(self.lib.ptb_get_config(self.handle, _ptr(out)))
+        return out[0]
+
+    def scene_counts(self):
+        vals = [ctypes.c_int() for _ in range(6)]
+        self._check(self.lib.ptb_scene_counts(self.handle, *[ctypes.byref(v) for v in vals]))
+        keys = ["triangles", "materials", "spheres", "textures", "cube_length", "meshes"]
+        return dict(zip(keys, [v.value for v in vals]))
+
+    def scene_triangles(self):
+        n = self.scene_counts()["triangles"]
+        tri = np.zeros((n, 24), np.float32)
+        mat = np.zeros(n, np.int32)
+        self._check(self.lib.ptb_scene_triangles(self.handle, _ptr(tri), _ptr(mat)))
+        return tri, mat
+
+    def scene_materials(self):
+        out = np.zeros(self.scene_counts()["materials"], MATERIAL_DTYPE)
+        if out.size:
+            self._check(self.lib.ptb_scene_materials(self.handle, _ptr(out)))
+        return out
+
+    def scene_spheres(self):
+        out = np.zeros(self.scene_counts()["spheres"], SPHERE_DTYPE)
+        if out.size:
+            self._check(self.lib.ptb_scene_spheres(self.handle, _ptr(out)))
+        return out
+
+    def scene_texture(self, index):
+        w, h = ctypes.c_int(), ctypes.c_int()
+        self._check(self.lib.ptb_scene_texture(self.handle, index, ctypes.byref(w), ctypes.byref(h), None))
+        out = np.zeros((h.value, w.value, 4), np.uint8)
+        self._check(self.lib.ptb_scene_texture(self.handle, index, ctypes.byref(w), ctypes.byref(h), _ptr(out)))
+        return out
+
+    def scene_cubemap(self):
+        n = self.scene_counts()["cube_length"]
+        out = np.zeros((6, n, n, 4), np.uint8)
+        for f in range(6):
+            self._check(self.lib.ptb_scene_cubemap_face(self.handle, f, _ptr(out[f])))
+        return out
+
+    # -- camera --------------------------------------------------------------------------------
+    def camera(self):
+        cam = Camera()
+        self._check(self.lib.ptb_get_camera(self.handle, ctypes.byref(cam)))
+        return cam
+
+    def set_camera(self, cam):
+        if not isinstance(cam, Camera):
+            cam = Camera.from_array(cam)
+        self._check(self.lib.ptb_set_camera(self.handle, ctypes.byref(cam)))
+
+    # -- rendering -----------------------------------------------------------------------------
+    def render(self, n_passes=1):
+        self._check(self.lib.ptb_render(self.handle, int(n_passes)))
+
+    def render_async(self, n_passes=1):
+        self._check(self.lib.ptb_render_async(self.handle, int(n_passes)))
+
+    def render_strided(self, first_pass, stride, n_passes):
+        self._check(self.lib.ptb_render_strided(self.handle, int(first_pass), int(stride), int(n_passes)))
+
+    def synchronize(self):
+        self._check(self.lib.ptb_synchronize(self.handle))
+
+    def stream(self):
+        return self.lib.ptb_stream(self.handle)
+
+    def clear(self):
+        self._check(self.lib.ptb_clear(self.handle))
+
+    def pass_counter(self):
+        return self.lib.ptb_pass_counter(self.handle)
+
+    def image_f32(self, out=None):
+        if out is None:
+            out = np.zeros((self.height, self.width, 3), np.float32)
+        passes = ctypes.c_int()
+        self._check(self.lib.ptb_image_f32(self.handle, _ptr(out), ctypes.byref(passes)))
+        return out
+
+    def image_u8(self, out=None):
+        if out is None:
+            out = np.zeros((self.height, self.width, 3), np.uint8)
+        self._check(self.lib.ptb_image_u8(self.handle, _ptr(out)))
+        return out
+
+    def last_pass_f32(self):
+        out = np.zeros((self.height, self.width, 3), np.float32)
+        self._check(self.lib.ptb_last_pass_f32(self.handle, _ptr(out)))
+        return out
+
+    def image_device_ptr(self):
+        return self.lib.ptb_image_device_ptr(self.handle)
+
+    def finalize(self, total_passes):
+        self._check(self.lib.ptb_finalize(self.handle, int(total_passes)))
+
+    def trace_batch(self, rays6, bruteforce=False, with_bary=False):
+        rays = np.ascontiguousarray(rays6, np.float32).reshape(-1, 6)
+        n = rays.shape[0]
+        prim = np.zeros(n, np.int32)
+        t = np.zeros(n, np.float32)
+        if bruteforce:
+            self._check(self.lib.ptb_trace_batch_bruteforce(self.handle, _ptr(rays), n, _ptr(prim), _ptr(t)))
+            return prim, t
+        bary = np.zeros((n, 2), np.float32) if with_bary else None
+        self._check(self.lib.ptb_trace_batch(self.handle, _ptr(rays), n, _ptr(prim), _ptr(t), _ptr(bary) if with_bary else None))
+        return (prim, t, bary) if with_bary else (prim, t)
+
+    def generate_rays(self, pass_index):
+        out = np.zeros((self.width * self.height, 6), np.float32)
+        self._check(self.lib.ptb_generate_rays(self.handle, int(pass_index), _ptr(out)))
+        return out
+
+    def stats(self):
+        s = Stats()
+        self._check(self.lib.ptb_get_stats(self.handle, ctypes.byref(s)))
+        return {k: getattr(s, k) for k, _ in Stats._fields_}
+
+
+class PathTracer:
+    """Mirror of the reference's `class path_tracer` (Core/path_tracer.h:31-61, path_tracer.cpp:18-106,371-406).
+
+    init(render_camera, config_path, scene_dir) -> list of scene files; init_scene_device_data(index) -> bool;
+    render() -> image dict or None when no scene is initiated; clear(); release_scene_device_data().
+    """
+
+    def __init__(self, device=0):
+        self._device = device
+        self._r = None
+        self._scene_files = []
+        self._asset_root = ""
+        self._is_initiated = False
+        self._render_camera = None
+
+    def init(self, render_camera, config_path, scene_file_directory, asset_root=None):
+        self._r = Renderer(config_path, self._device)
+        self._render_camera = render_camera
+        # the reference resolves paths against its CWD: "res\\scene" lives directly under it
+        self._asset_root = asset_root if asset_root is not None else os.getcwd()
+        buf = ctypes.create_string_buffer(1 << 16)
+        scene_dir = scene_file_directory.replace("\\", "/")
+        if not os.path.isabs(scene_dir):
+            scene_dir = os.path.join(self._asset_root, scene_dir)
+        n = self._r.lib.ptb_list_scenes(os.fsencode(scene_dir), buf, len(buf))
+        self._scene_files = [s for s in buf.value.decode().split("\n") if s] if n > 0 else []
+        if not self._scene_files:
+            print("[Warn]There exists no scene file!")
+        return list(self._scene_files)
+
+    def init_scene_device_data(self, index):
+        if self._r is None or index < 0 or index >= len(self._scene_files):
+            self._is_initiated = False
+            return False
+        try:
+            self._r.load_scene(self._scene_files[index], self._asset_root)
+        except PtbError as e:
+            print(str(e))
+            print("[Error]Load scene failed!")
+            self._is_initiated = False
+            return False
+        self._is_initiated = True
+        return True
+
+    def render(self):
+        if not self._is_initiated:
+            return None
+        if self._render_camera is not None:
+            self._r.set_camera(self._render_camera)
+        self._r.render(1)
+        return {"width": self._r.width, "height": self._r.height, "pixel_count": self._r.width * self._r.height,
+                "pass_counter": self._r.pass_counter(), "pixels": self._r.image_f32(), "pixels_256": self._r.image_u8()}
+
+    def clear(self):
+        if self._is_initiated:
+            self._r.clear()
+
+    def release_scene_device_data(self):
+        if not self._is_initiated:
+            return
+        self._r.release_scene()
+        self._is_initiated = False
+
+    @property
+    def renderer(self):
+        return self._r

@@ -1,0 +1,75 @@
+"""Builds pathtracerwithcuda_b200/libptb200.so IN-TREE for sm_100a (nvcc cross-compiles without a GPU).
+
+    python -m pathtracerwithcuda_b200.build [--force]
+
+Host sources are compiled with -ffp-contract=off: the scene front-end must reproduce the
+reference's un-fused IEEE binary32 transform arithmetic bit for bit (csrc/scene_io.cpp).
+"""
+import hashlib
+import os
+import subprocess
+import sys
+from concurrent.futures import ThreadPoolExecutor
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+OUT = os.path.join(HERE, "libptb200.so")
+OBJ = os.path.join(HERE, "build")
+
+HOST_SOURCES = ["scene_io.cpp", "bvh_host.cpp"]
+CUDA_SOURCES = ["render.cu"]
+NVCC_ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
+
+
+def _hash_sources():
+    h = hashlib.sha1()
+    for root in (CSRC, os.path.join(HERE, "..", "include")):
+        for fn in sorted(os.listdir(root)):
+            with open(os.path.join(root, fn), "rb") as f:
+                h.update(fn.encode() + f.read())
+    with open(__file__, "rb") as f:
+        h.update(f.read())
+    return h.hexdigest()
+
+
+def build(force=False, verbose=False):
+    os.makedirs(OBJ, exist_ok=True)
+    stamp = os.path.join(OBJ, "stamp")
+    digest = _hash_sources()
+    if not force and os.path.exists(OUT) and os.path.exists(stamp) and open(stamp).read() == digest:
+        return OUT
+    jobs = []
+    for src in HOST_SOURCES:
+        obj = os.path.join(OBJ, src + ".o")
+        jobs.append((obj, ["g++", "-std=c++17", "-O2", "-fPIC", "-ffp-contract=off", "-fopenmp", "-Wall",
+                           "-c", os.path.join(CSRC, src), "-o", obj]))
+    for src in CUDA_SOURCES:
+        obj = os.path.join(OBJ, src + ".o")
+        jobs.append((obj, ["nvcc", "-std=c++17", "-O3", "-lineinfo"] + NVCC_ARCH +
+                     ["-Xcompiler", "-fPIC,-fopenmp", "-Xptxas", "-v" if verbose else "-warn-spills",
+                      "-c", os.path.join(CSRC, src), "-o", obj]))
+
+    def run(job):
+        obj, cmd = job
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        return obj, cmd, r
+
+    objs = []
+    with ThreadPoolExecutor(max_workers=4) as ex:
+        for obj, cmd, r in ex.map(run, jobs):
+            if r.returncode != 0:
+                raise RuntimeError("build failed: %s\n%s\n%s" % (" ".join(cmd), r.stdout, r.stderr))
+            if verbose:
+                sys.stderr.write(r.stderr)
+            objs.append(obj)
+    link = ["nvcc", "-shared"] + NVCC_ARCH + ["-Xcompiler", "-fPIC,-fopenmp", "-o", OUT] + objs + ["-lgomp"]
+    r = subprocess.run(link, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("link failed:\n%s\n%s" % (r.stdout, r.stderr))
+    with open(stamp, "w") as f:
+        f.write(digest)
+    return OUT
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

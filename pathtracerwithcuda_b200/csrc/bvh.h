@@ -1,0 +1,55 @@
+// Acceleration-structure build for the ptb200 extend stage.
+//
+// Replaces the reference's per-mesh binary trees flattened to a skip-pointer array
+// (Bvh/bvh.cpp:185-330,667-780,862-1047; Kernel/bvh_morton_code_kernel.cu:298-346) with ONE tree
+// over all meshes' world-space triangles (global triangle indices, same numbering as the
+// reference's concatenated triangle array, triangle_mesh.cpp:498-540).
+#pragma once
+#include <cstdint>
+#include <vector>
+#include "scene.h"
+
+namespace ptb
+{
+
+struct Aabb
+{
+	float lo[3], hi[3];
+};
+
+// Binary tree in host memory; node 0 is the root. Leaves reference a range of `prim_order`.
+struct Bvh2Node
+{
+	Aabb box;
+	int left = -1, right = -1;   // inner node
+	int first = 0, count = 0;    // leaf if count > 0
+};
+
+struct Bvh2
+{
+	std::vector<Bvh2Node> nodes;
+	std::vector<int> prim_order; // permutation of triangle indices
+	float sah_cost = 0.0f;
+};
+
+// Top-down binned surface-area-heuristic build (host, multi-threaded).
+void build_bvh2_sah(const std::vector<Triangle>& tris, int max_leaf_size, Bvh2& out);
+
+// GPU layout #1: binary nodes holding BOTH children's boxes (64 bytes = 4 x 16-byte loads).
+//   n[0] = c0.lo.x c0.hi.x c0.lo.y c0.hi.y
+//   n[1] = c1.lo.x c1.hi.x c1.lo.y c1.hi.y
+//   n[2] = c0.lo.z c0.hi.z c1.lo.z c1.hi.z
+//   n[3] = child0, child1 (int bits), 0, 0    child >= 0: node index; child < 0: ~((first<<3)|(count-1))
+// Child boxes are padded outwards by a few ulps so a conservative traversal never culls a
+// triangle whose exact Moller-Trumbore distance rounds across its box face.
+struct GpuBvh2
+{
+	std::vector<float> nodes;    // 16 floats per node
+	std::vector<float> tris;     // 12 floats per triangle in leaf order: v0.xyz,id | e1.xyz,0 | e2.xyz,0
+	int root_is_leaf = 0;
+	int root_ref = 0;
+};
+
+void flatten_bvh2(const Bvh2& bvh, const std::vector<Triangle>& tris, GpuBvh2& out);
+
+} // namespace ptb

@@ -1,0 +1,68 @@
+// Kernel-side data layout of the ptb200 wavefront integrator (device buffers, all explicit
+// cudaMalloc — no managed memory, unlike the reference's cudaMallocManaged scene).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "pt_device.cuh"
+
+namespace ptb
+{
+
+// Material padded from the reference's 84 bytes to 6 x 16-byte loads.
+//  a = diffuse.xyz, roughness      b = emission.xyz, refraction_index   c = specular.xyz, extinction
+//  d = sigma_a.xyz, sigma_s'.x     e = sigma_s'.y, sigma_s'.z, transparent(bits), diffuse_tex(bits)
+//  f = specular_tex(bits), 0, 0, 0
+struct DeviceMaterial
+{
+	float4 a, b, c, d, e, f;
+};
+
+struct DeviceTexture
+{
+	const uint8_t* pixels;
+	int width, height;
+};
+
+struct DeviceScene
+{
+	const float4* bvh_nodes;      // 4 x float4 per binary node (bvh.h)
+	const float4* tri_isect;      // 3 x float4 per triangle, leaf order
+	const float4* tri_shade;      // 4 x float4 per triangle, by global triangle id:
+	                              //   n0.xyz n1.x | n1.yz n2.xy | n2.z uv0.xy uv1.x | uv1.y uv2.xy material(bits)
+	const DeviceMaterial* materials; // mesh materials, then one per sphere
+	const float4* spheres;        // center.xyz, radius
+	const DeviceTexture* textures;
+	int n_triangles;
+	int n_spheres;
+	int sphere_material_base;
+	int n_textures;
+	int root_ref;                 // node index (>= 0) or leaf ref (< 0)
+	ptbdev::SkyParams sky;
+};
+
+// Config values the kernels read (Core/configuration.h), passed by value in kernel params.
+struct DeviceConfig
+{
+	int max_depth;
+	float bias_length;
+	float energy_threshold;
+	float sss_threshold;
+	int use_bilinear;
+	int gamma_correction;
+	int use_anti_alias;
+	float air_n;
+	float3 air_sigma_a;
+	float3 air_sigma_s;
+};
+
+// SoA path state, indexed by path id = slot * pixel_count + pixel.
+struct PathState
+{
+	float4* ray_o;      // origin.xyz, (unused)
+	float4* ray_d;      // direction.xyz, (unused)
+	float4* throughput; // not-absorbed colour .xyz, medium material index (bits; -1 = air)
+	float4* radiance;   // accumulated colour .xyz of this pass
+	float4* hit;        // t, t1, t2, primitive (bits): >= 0 triangle, -(s+2) sphere s, -1 miss
+};
+
+} // namespace ptb

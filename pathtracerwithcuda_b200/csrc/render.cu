@@ -1,0 +1,1160 @@
+// ptb200 wavefront integrator: kernels, renderer state and the C ABI (include/ptb200.h).
+//
+// The reference runs, per pass, init -> generate -> { trace_ray_kernel ; thrust::remove_if +
+// host sync } x depth -> tonemap (Kernel/path_tracer_kernel.cu:706-779).  Here one batch of
+// `passes_in_flight` passes is traced as a single wavefront:
+//     k_generate -> { k_extend ; k_shade } x depth -> k_accumulate        (no host round trips)
+// with SoA path state, device-side queue counters, warp-ballot compaction into the next-depth
+// queue and per-(pass, pixel, depth) stateless RNG identical to the reference's, so every
+// sample's value is the one the reference computes for that (pass, pixel).
+#include <cuda_runtime.h>
+#include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/ptb200.h"
+#include "scene.h"
+#include "bvh.h"
+#include "kernels.cuh"
+
+using namespace ptbdev;
+
+namespace ptb
+{
+
+#define PTB_CUDA(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { \
+	set_error(std::string("[Cuda]Error in file '") + __FILE__ + "' in line " + std::to_string(__LINE__) + " : " + cudaGetErrorString(e_)); return 1; } } while (0)
+
+__device__ __forceinline__ int float_as_int_(float f) { return __float_as_int(f); }
+
+// ------------------------------------------------------------------------------------------
+// k_generate — init_data_kernel + generate_ray_kernel fused (path_tracer_kernel.cu:275-379)
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_generate(PathState st, int* __restrict__ queue, int* __restrict__ counts, int n_counts,
+	CameraParams cam, DeviceConfig cfg, int pixel_count, int n_slots, int first_pass, int pass_stride)
+{
+	const int total = pixel_count * n_slots;
+	int tid = blockIdx.x * blockDim.x + threadIdx.x;
+	if (tid < n_counts) counts[tid] = tid == 0 ? total : 0;
+	for (int id = tid; id < total; id += gridDim.x * blockDim.x)
+	{
+		int slot = id / pixel_count;
+		int pixel = id - slot * pixel_count;
+		int seed = first_pass + slot * pass_stride;
+		float3 o, d;
+		generate_camera_ray(cam, pixel, seed, cfg.use_anti_alias != 0, o, d);
+		st.ray_o[id] = make_float4(o.x, o.y, o.z, 0.0f);
+		st.ray_d[id] = make_float4(d.x, d.y, d.z, 0.0f);
+		st.throughput[id] = make_float4(1.0f, 1.0f, 1.0f, __int_as_float(-1));
+		st.radiance[id] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+		queue[id] = id;
+	}
+}
+
+// ------------------------------------------------------------------------------------------
+// k_extend — closest hit (path_tracer_kernel.cu:418-454 + intersect_triangle_mesh_bvh :85-161)
+// One conservative traversal over a single tree for all meshes; the accepted hit is decided by
+// the reference's own Moller-Trumbore / sphere arithmetic (pt_device.cuh).
+// ------------------------------------------------------------------------------------------
+#define PTB_STACK_SIZE 64
+#define PTB_SLACK_LO 0.9999995f
+#define PTB_SLACK_HI 1.0000005f
+
+struct HitRecord
+{
+	float t, t1, t2;
+	int prim;
+};
+
+template <bool COUNT>
+__device__ __forceinline__ HitRecord closest_hit(const DeviceScene& sc, float3 o, float3 d, unsigned& n_nodes, unsigned& n_tris)
+{
+	HitRecord best;
+	best.t = CUDART_INF_F; best.t1 = CUDART_INF_F; best.t2 = CUDART_INF_F; best.prim = -1;
+
+	// spheres first, in index order, strict '<' (path_tracer_kernel.cu:431-441)
+	for (int s = 0; s < sc.n_spheres; s++)
+	{
+		float4 sp = __ldg(&sc.spheres[s]);
+		float t;
+		if (intersect_sphere(make_float3(sp.x, sp.y, sp.z), sp.w, o, d, t) && t < best.t && t > 0.0f)
+		{
+			best.t = t;
+			best.prim = -(s + 2);
+		}
+	}
+	if (sc.n_triangles == 0) return best;
+
+	const float3 idir = make_float3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+	int stack[PTB_STACK_SIZE];
+	int sp = 0;
+	int node = sc.root_ref;
+	int best_tri = 0x7fffffff;
+
+	while (true)
+	{
+		while (node >= 0)
+		{
+			if (COUNT) n_nodes++;
+			const float4* np = sc.bvh_nodes + (size_t)node * 4;
+			float4 n0 = __ldg(np + 0), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3);
+			float c0x0 = (n0.x - o.x) * idir.x, c0x1 = (n0.y - o.x) * idir.x;
+			float c0y0 = (n0.z - o.y) * idir.y, c0y1 = (n0.w - o.y) * idir.y;
+			float c0z0 = (n2.x - o.z) * idir.z, c0z1 = (n2.y - o.z) * idir.z;
+			float c1x0 = (n1.x - o.x) * idir.x, c1x1 = (n1.y - o.x) * idir.x;
+			float c1y0 = (n1.z - o.y) * idir.y, c1y1 = (n1.w - o.y) * idir.y;
+			float c1z0 = (n2.z - o.z) * idir.z, c1z1 = (n2.w - o.z) * idir.z;
+			float tmin0 = fmaxf(fmaxf(fminf(c0x0, c0x1), fminf(c0y0, c0y1)), fmaxf(fminf(c0z0, c0z1), 0.0f));
+			float tmax0 = fminf(fminf(fmaxf(c0x0, c0x1), fmaxf(c0y0, c0y1)), fminf(fmaxf(c0z0, c0z1), best.t));
+			float tmin1 = fmaxf(fmaxf(fminf(c1x0, c1x1), fminf(c1y0, c1y1)), fmaxf(fminf(c1z0, c1z1), 0.0f));
+			float tmax1 = fminf(fminf(fmaxf(c1x0, c1x1), fmaxf(c1y0, c1y1)), fminf(fmaxf(c1z0, c1z1), best.t));
+			bool h0 = tmin0 * PTB_SLACK_LO <= tmax0 * PTB_SLACK_HI;
+			bool h1 = tmin1 * PTB_SLACK_LO <= tmax1 * PTB_SLACK_HI;
+			int child0 = __float_as_int(n3.x), child1 = __float_as_int(n3.y);
+			if (h0 && h1)
+			{
+				bool swap = tmin1 < tmin0;
+				int near_c = swap ? child1 : child0;
+				int far_c = swap ? child0 : child1;
+				if (sp < PTB_STACK_SIZE) stack[sp++] = far_c;
+				node = near_c;
+			}
+			else if (h0) node = child0;
+			else if (h1) node = child1;
+			else
+			{
+				if (sp == 0) return best;
+				node = stack[--sp];
+			}
+		}
+		// leaf: node = ~((first << 3) | (count - 1))
+		{
+			int ref = ~node;
+			int first = ref >> 3;
+			int count = (ref & 7) + 1;
+			for (int k = 0; k < count; k++)
+			{
+				if (COUNT) n_tris++;
+				const float4* tp = sc.tri_isect + (size_t)(first + k) * 3;
+				float4 a = __ldg(tp + 0), b = __ldg(tp + 1), c = __ldg(tp + 2);
+				float t, t1, t2;
+				if (intersect_triangle(make_float3(a.x, a.y, a.z), make_float3(b.x, b.y, b.z), make_float3(c.x, c.y, c.z), o, d, t, t1, t2) && t > 0.0f)
+				{
+					int id = __float_as_int(a.w);
+					// strict '<' like the reference; exact-t ties between triangles go to the lower
+					// global index (the reference's tie winner depends on its tree layout)
+					if (t < best.t || (t == best.t && best.prim >= 0 && id < best_tri))
+					{
+						best.t = t; best.t1 = t1; best.t2 = t2; best.prim = id; best_tri = id;
+					}
+				}
+			}
+			if (sp == 0) return best;
+			node = stack[--sp];
+		}
+	}
+}
+
+template <bool COUNT>
+__global__ void __launch_bounds__(128) k_extend(DeviceScene sc, PathState st, const int* __restrict__ queue, const int* __restrict__ count_ptr,
+	unsigned long long* __restrict__ counters)
+{
+	const int count = *count_ptr;
+	unsigned n_nodes = 0, n_tris = 0;
+	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x)
+	{
+		int id = queue[i];
+		float4 o4 = st.ray_o[id], d4 = st.ray_d[id];
+		HitRecord h = closest_hit<COUNT>(sc, make_float3(o4.x, o4.y, o4.z), make_float3(d4.x, d4.y, d4.z), n_nodes, n_tris);
+		st.hit[id] = make_float4(h.t, h.t1, h.t2, __int_as_float(h.prim));
+	}
+	if (COUNT)
+	{
+		for (int off = 16; off > 0; off >>= 1)
+		{
+			n_nodes += __shfl_down_sync(0xffffffffu, n_nodes, off);
+			n_tris += __shfl_down_sync(0xffffffffu, n_tris, off);
+		}
+		if ((threadIdx.x & 31) == 0)
+		{
+			atomicAdd(&counters[0], (unsigned long long)n_nodes);
+			atomicAdd(&counters[1], (unsigned long long)n_tris);
+		}
+	}
+}
+
+// brute-force closest hit over every primitive (test hook; same acceptance arithmetic)
+__global__ void k_bruteforce(DeviceScene sc, const float4* __restrict__ ray_o, const float4* __restrict__ ray_d, float4* __restrict__ hit, int n)
+{
+	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	float3 o = make_float3(ray_o[i].x, ray_o[i].y, ray_o[i].z), d = make_float3(ray_d[i].x, ray_d[i].y, ray_d[i].z);
+	float best_t = CUDART_INF_F, bt1 = CUDART_INF_F, bt2 = CUDART_INF_F;
+	int prim = -1;
+	for (int s = 0; s < sc.n_spheres; s++)
+	{
+		float4 sp = sc.spheres[s];
+		float t;
+		if (intersect_sphere(make_float3(sp.x, sp.y, sp.z), sp.w, o, d, t) && t < best_t && t > 0.0f) { best_t = t; prim = -(s + 2); }
+	}
+	for (int k = 0; k < sc.n_triangles; k++)
+	{
+		const float4* tp = sc.tri_isect + (size_t)k * 3;
+		float4 a = tp[0], b = tp[1], c = tp[2];
+		float t, t1, t2;
+		if (intersect_triangle(make_float3(a.x, a.y, a.z), make_float3(b.x, b.y, b.z), make_float3(c.x, c.y, c.z), o, d, t, t1, t2) && t > 0.0f)
+		{
+			int id = __float_as_int(a.w);
+			if (t < best_t || (t == best_t && prim >= 0 && id < prim)) { best_t = t; bt1 = t1; bt2 = t2; prim = id; }
+		}
+	}
+	hit[i] = make_float4(best_t, bt1, bt2, __int_as_float(prim));
+}
+
+// ------------------------------------------------------------------------------------------
+// k_shade — medium, material, Fresnel, branch, sky (path_tracer_kernel.cu:456-624)
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ float3 sample_texture(const DeviceTexture& tex, float2 uv, bool use_bilinear)
+{
+	float ux = uv.x - floorf(uv.x);
+	float uy = uv.y - floorf(uv.y);
+	return sample_image(tex.pixels, tex.width, tex.height, ux, 1.0f - uy, use_bilinear);
+}
+
+__global__ void __launch_bounds__(128) k_shade(DeviceScene sc, PathState st, DeviceConfig cfg, int depth, int pixel_count, int first_pass, int pass_stride,
+	const int* __restrict__ queue_in, const int* __restrict__ count_in, int* __restrict__ queue_out, int* __restrict__ count_out)
+{
+	const int count = *count_in;
+	const unsigned lane = threadIdx.x & 31;
+	// warp-uniform trip count so the ballots below are convergent
+	for (int base = (blockIdx.x * blockDim.x + threadIdx.x) - lane; base < count; base += gridDim.x * blockDim.x)
+	{
+		int i = base + lane;
+		bool valid = i < count;
+		bool alive = false;
+		int id = 0;
+		if (valid)
+		{
+			id = queue_in[i];
+			int slot = id / pixel_count;
+			int pixel_index = id - slot * pixel_count;
+			int seed = first_pass + slot * pass_stride;
+
+			float4 o4 = st.ray_o[id], d4 = st.ray_d[id], t4 = st.throughput[id], h4 = st.hit[id];
+			float3 ray_o = make_float3(o4.x, o4.y, o4.z);
+			float3 ray_d = make_float3(d4.x, d4.y, d4.z);
+			float3 not_absorbed = make_float3(t4.x, t4.y, t4.z);
+			int medium_index = __float_as_int(t4.w);
+			float min_t = h4.x, min_t1 = h4.y, min_t2 = h4.z;
+			int prim = __float_as_int(h4.w);
+
+			Rng rng;
+			rng.seed((uint32_t)(hash_ref(seed) * hash_ref(pixel_index) * hash_ref(depth)), 0.0f, 1.0f);
+
+			float3 sigma_a = cfg.air_sigma_a, sigma_s = cfg.air_sigma_s;
+			if (medium_index >= 0)
+			{
+				float4 md = __ldg(&sc.materials[medium_index].d), me = __ldg(&sc.materials[medium_index].e);
+				sigma_a = make_float3(md.x, md.y, md.z);
+				sigma_s = make_float3(md.w, me.x, me.y);
+			}
+
+			bool done = false;
+			alive = true;
+			if (sigma_s.x > 0.0f || length(sigma_a) > cfg.sss_threshold)
+			{
+				float rand = rng.next();
+				float scattering_distance = -__logf(rand) / sigma_s.x;
+				if (scattering_distance < min_t)
+				{
+					float rand1 = rng.next();
+					float rand2 = rng.next();
+					float3 next_o = ray_o + ray_d * scattering_distance;
+					float3 next_d = sample_on_sphere(rand1, rand2);
+					not_absorbed = not_absorbed * absorption_through_medium(sigma_a, scattering_distance);
+					st.ray_o[id] = make_float4(next_o.x, next_o.y, next_o.z, 0.0f);
+					st.ray_d[id] = make_float4(next_d.x, next_d.y, next_d.z, 0.0f);
+					st.throughput[id] = make_float4(not_absorbed.x, not_absorbed.y, not_absorbed.z, t4.w);
+					if (length(not_absorbed) <= cfg.energy_threshold) alive = false;
+					done = true;
+				}
+				else
+				{
+					not_absorbed = not_absorbed * absorption_through_medium(sigma_a, min_t);
+				}
+			}
+
+			if (!done)
+			{
+				if (prim != -1)
+				{
+					float3 diffuse_color, emission_color, specular_color, min_normal, min_point;
+					float roughness, mat_n, mat_k;
+					float2 uv0 = make_float2(0.0f, 0.0f), uv1 = uv0, uv2 = uv0;
+					bool is_transparent;
+					int material_index;
+					if (prim < -1)
+					{
+						int s = -(prim + 2);
+						material_index = sc.sphere_material_base + s;
+						float4 sp = __ldg(&sc.spheres[s]);
+						min_point = ray_o + ray_d * min_t;
+						min_normal = normalize(min_point - make_float3(sp.x, sp.y, sp.z));
+					}
+					else
+					{
+						const float4* sh = sc.tri_shade + (size_t)prim * 4;
+						float4 s0 = __ldg(sh + 0), s1 = __ldg(sh + 1), s2 = __ldg(sh + 2), s3 = __ldg(sh + 3);
+						material_index = __float_as_int(s3.w);
+						float3 normal0 = make_float3(s0.x, s0.y, s0.z), normal1 = make_float3(s0.w, s1.x, s1.y), normal2 = make_float3(s1.z, s1.w, s2.x);
+						min_normal = normal0 * (1.0f - min_t1 - min_t2) + normal1 * min_t1 + normal2 * min_t2;
+						min_point = ray_o + ray_d * min_t;
+						uv0 = make_float2(s2.y, s2.z); uv1 = make_float2(s2.w, s3.x); uv2 = make_float2(s3.y, s3.z);
+					}
+					const DeviceMaterial* mp = &sc.materials[material_index];
+					float4 ma = __ldg(&mp->a), mb = __ldg(&mp->b), mc = __ldg(&mp->c), me = __ldg(&mp->e), mf = __ldg(&mp->f);
+					diffuse_color = make_float3(ma.x, ma.y, ma.z);
+					emission_color = make_float3(mb.x, mb.y, mb.z);
+					specular_color = make_float3(mc.x, mc.y, mc.z);
+					is_transparent = __float_as_int(me.z) != 0;
+					if (prim >= 0)
+					{
+						int diffuse_tex = __float_as_int(me.w), specular_tex = __float_as_int(mf.x);
+						if (diffuse_tex != -1 || specular_tex != -1)
+						{
+							float2 uv = uv0 * (1.0f - min_t1 - min_t2) + uv1 * min_t1 + uv2 * min_t2;
+							if (diffuse_tex != -1) diffuse_color = diffuse_color * sample_texture(sc.textures[diffuse_tex], uv, cfg.use_bilinear != 0);
+							if (specular_tex != -1) specular_color = specular_color * sample_texture(sc.textures[specular_tex], uv, cfg.use_bilinear != 0);
+						}
+					}
+					roughness = ma.w; mat_n = mb.w; mat_k = mc.w;
+
+					float3 in_direction = ray_d;
+					float in_n = cfg.air_n, out_n = mat_n;
+					float out_k = mat_k;
+					int in_medium = -1, out_medium = material_index;
+
+					bool is_hit_on_back = dot(in_direction, min_normal) > 0;
+					if (is_hit_on_back)
+					{
+						min_normal = min_normal * -1.0f;
+						if (is_transparent)
+						{
+							float tn = in_n; in_n = out_n; out_n = tn;
+							int tm = in_medium; in_medium = out_medium; out_medium = tm;
+							out_k = 0.0f;
+						}
+					}
+
+					float3 reflection_direction = reflection(min_normal, in_direction);
+					float3 refraction_direction = refraction(min_normal, in_direction, in_n, out_n);
+					float3 bias_vector = cfg.bias_length * min_normal;
+					(void)reflection_direction;
+
+					float fresnel_reflection;
+					if (mat_k == 0 || is_transparent) fresnel_reflection = fresnel_dielectric(min_normal, in_direction, in_n, out_n, refraction_direction);
+					else fresnel_reflection = fresnel_conductor(min_normal, in_direction, out_n, out_k);
+
+					float rand = rng.next();
+					float3 next_o, next_d;
+					float medium_bits = t4.w;
+					if (rand < fresnel_reflection)
+					{
+						float rand1 = rng.next();
+						float rand2 = rng.next();
+						float remap_roughness = __powf(roughness, 1.85f) * 0.238f;
+						float3 micro_normal = sample_on_hemisphere_ggx_weight(min_normal, remap_roughness, rand1, rand2);
+						float3 micro_reflection_direction = reflection(micro_normal, in_direction);
+						float self_shadowing = ggx_shadowing_masking(remap_roughness, min_normal, micro_normal, ray_d) *
+							ggx_shadowing_masking(remap_roughness, min_normal, micro_normal, micro_reflection_direction);
+						next_o = min_point + bias_vector;
+						next_d = micro_reflection_direction;
+						not_absorbed = not_absorbed * (specular_color * self_shadowing);
+					}
+					else if (is_transparent)
+					{
+						next_o = min_point - bias_vector;
+						next_d = refraction_direction;
+						medium_bits = __int_as_float(out_medium);
+						not_absorbed = not_absorbed * __powf((out_n / in_n), 2.0f);
+					}
+					else
+					{
+						float4 r4 = st.radiance[id];
+						float3 add = not_absorbed * emission_color;
+						st.radiance[id] = make_float4(r4.x + add.x, r4.y + add.y, r4.z + add.z, 0.0f);
+						not_absorbed = not_absorbed * diffuse_color;
+						float rand1 = rng.next();
+						float rand2 = rng.next();
+						next_o = min_point + bias_vector;
+						next_d = sample_on_hemisphere_cosine_weight(min_normal, rand1, rand2);
+					}
+					st.ray_o[id] = make_float4(next_o.x, next_o.y, next_o.z, 0.0f);
+					st.ray_d[id] = make_float4(next_d.x, next_d.y, next_d.z, 0.0f);
+					st.throughput[id] = make_float4(not_absorbed.x, not_absorbed.y, not_absorbed.z, medium_bits);
+					if (length(not_absorbed) <= cfg.energy_threshold) alive = false;
+				}
+				else
+				{
+					float3 bg = background_color(sc.sky, ray_d);
+					float4 r4 = st.radiance[id];
+					float3 add = not_absorbed * bg;
+					st.radiance[id] = make_float4(r4.x + add.x, r4.y + add.y, r4.z + add.z, 0.0f);
+					alive = false;
+				}
+			}
+		}
+		// stream compaction of survivors: one atomic per warp (replaces thrust::remove_if + host sync)
+		unsigned mask = __ballot_sync(0xffffffffu, alive);
+		if (mask)
+		{
+			int pos = 0;
+			if (lane == 0) pos = atomicAdd(count_out, __popc(mask));
+			pos = __shfl_sync(0xffffffffu, pos, 0);
+			if (alive) queue_out[pos + __popc(mask & ((1u << lane) - 1u))] = id;
+		}
+	}
+}
+
+// ------------------------------------------------------------------------------------------
+// k_accumulate / k_tonemap — pixel_256_transform_gamma_corrected_kernel (:627-682) split in two
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_accumulate(const float4* __restrict__ radiance, float* __restrict__ image_sum, float* __restrict__ last_pass,
+	int pixel_count, int n_slots, float clamp_hi)
+{
+	int p = blockIdx.x * blockDim.x + threadIdx.x;
+	if (p >= pixel_count) return;
+	float sx = image_sum[p * 3 + 0], sy = image_sum[p * 3 + 1], sz = image_sum[p * 3 + 2];
+	float4 r = make_float4(0, 0, 0, 0);
+	for (int s = 0; s < n_slots; s++)
+	{
+		r = radiance[(size_t)s * pixel_count + p];
+		sx += clampf(r.x, 0.0f, clamp_hi);
+		sy += clampf(r.y, 0.0f, clamp_hi);
+		sz += clampf(r.z, 0.0f, clamp_hi);
+	}
+	image_sum[p * 3 + 0] = sx; image_sum[p * 3 + 1] = sy; image_sum[p * 3 + 2] = sz;
+	last_pass[p * 3 + 0] = r.x; last_pass[p * 3 + 1] = r.y; last_pass[p * 3 + 2] = r.z;
+}
+
+__global__ void __launch_bounds__(256) k_tonemap(const float* __restrict__ image_sum, uint8_t* __restrict__ image_u8, int pixel_count, int pass_counter, int gamma_correction)
+{
+	int p = blockIdx.x * blockDim.x + threadIdx.x;
+	if (p >= pixel_count) return;
+	float3 pixel = make_float3(image_sum[p * 3 + 0] / (float)pass_counter, image_sum[p * 3 + 1] / (float)pass_counter, image_sum[p * 3 + 2] / (float)pass_counter);
+	float x, y, z;
+	if (gamma_correction)
+	{
+		float inverse_gamma = 0.45454545f;
+		float cx = __expf(inverse_gamma * __logf(pixel.x));
+		float cy = __expf(inverse_gamma * __logf(pixel.y));
+		float cz = __expf(inverse_gamma * __logf(pixel.z));
+		x = clampf(cx * 255.0f, 0.0f, 255.0f);
+		y = clampf(cy * 255.0f, 0.0f, 255.0f);
+		z = clampf(cz * 255.0f, 0.0f, 255.0f);
+	}
+	else
+	{
+		x = clampf(pixel.x * 255.0f, 0.0f, 255.0f);
+		y = clampf(pixel.y * 255.0f, 0.0f, 255.0f);
+		z = clampf(pixel.z * 255.0f, 0.0f, 255.0f);
+	}
+	image_u8[p * 3 + 0] = (uint8_t)x;
+	image_u8[p * 3 + 1] = (uint8_t)y;
+	image_u8[p * 3 + 2] = (uint8_t)z;
+}
+
+__global__ void k_iota(int* q, int* count, int n)
+{
+	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i == 0) *count = n;
+	if (i < n) q[i] = i;
+}
+
+} // namespace ptb
+
+// ==========================================================================================
+// Renderer
+// ==========================================================================================
+
+using namespace ptb;
+
+struct ptb_renderer
+{
+	Config cfg;
+	int device = -1;
+	bool host_only = false;
+	bool scene_loaded = false;
+	HostScene scene;
+	ptb_camera cam;
+	int pass_counter = 0;
+
+	// options
+	int passes_in_flight = 4;
+	int profile_stages = 0;
+	int count_traversal = 0;
+	std::string bvh_builder = "host_sah";
+
+	cudaStream_t stream = nullptr;
+	int sm_count = 148;
+
+	// scene on device
+	DeviceScene dscene;
+	std::vector<void*> scene_allocs;
+	int64_t bvh_nodes = 0, bvh_bytes = 0;
+
+	// work buffers
+	int pixel_count = 0;
+	size_t capacity = 0;       // paths = pixel_count * passes_in_flight
+	PathState st;
+	int* queue[2] = { nullptr, nullptr };
+	int* counts = nullptr;     // max_depth + 2 ints
+	int* counts_host = nullptr; // pinned
+	unsigned long long* counters = nullptr;
+	float* image_sum = nullptr;
+	float* last_pass = nullptr;
+	uint8_t* image_u8 = nullptr;
+	cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+	std::vector<cudaEvent_t> stage_events;
+
+	ptb_stats stats;
+};
+
+namespace
+{
+
+int alloc_work_buffers(ptb_renderer* r)
+{
+	r->pixel_count = r->cfg.width * r->cfg.height;
+	r->capacity = (size_t)r->pixel_count * r->passes_in_flight;
+	PTB_CUDA(cudaMalloc(&r->st.ray_o, r->capacity * sizeof(float4)));
+	PTB_CUDA(cudaMalloc(&r->st.ray_d, r->capacity * sizeof(float4)));
+	PTB_CUDA(cudaMalloc(&r->st.throughput, r->capacity * sizeof(float4)));
+	PTB_CUDA(cudaMalloc(&r->st.radiance, r->capacity * sizeof(float4)));
+	PTB_CUDA(cudaMalloc(&r->st.hit, r->capacity * sizeof(float4)));
+	PTB_CUDA(cudaMalloc(&r->queue[0], r->capacity * sizeof(int)));
+	PTB_CUDA(cudaMalloc(&r->queue[1], r->capacity * sizeof(int)));
+	int n_counts = r->cfg.max_tracer_depth + 2;
+	PTB_CUDA(cudaMalloc(&r->counts, n_counts * sizeof(int)));
+	PTB_CUDA(cudaMallocHost(&r->counts_host, n_counts * sizeof(int)));
+	PTB_CUDA(cudaMalloc(&r->counters, 2 * sizeof(unsigned long long)));
+	PTB_CUDA(cudaMalloc(&r->image_sum, (size_t)r->pixel_count * 3 * sizeof(float)));
+	PTB_CUDA(cudaMalloc(&r->last_pass, (size_t)r->pixel_count * 3 * sizeof(float)));
+	PTB_CUDA(cudaMalloc(&r->image_u8, (size_t)r->pixel_count * 3));
+	PTB_CUDA(cudaMemsetAsync(r->image_sum, 0, (size_t)r->pixel_count * 3 * sizeof(float), r->stream));
+	PTB_CUDA(cudaMemsetAsync(r->last_pass, 0, (size_t)r->pixel_count * 3 * sizeof(float), r->stream));
+	PTB_CUDA(cudaMemsetAsync(r->image_u8, 0, (size_t)r->pixel_count * 3, r->stream));
+	PTB_CUDA(cudaMemsetAsync(r->counters, 0, 2 * sizeof(unsigned long long), r->stream));
+	PTB_CUDA(cudaStreamSynchronize(r->stream));
+	return 0;
+}
+
+void free_work_buffers(ptb_renderer* r)
+{
+	cudaFree(r->st.ray_o); cudaFree(r->st.ray_d); cudaFree(r->st.throughput); cudaFree(r->st.radiance); cudaFree(r->st.hit);
+	cudaFree(r->queue[0]); cudaFree(r->queue[1]); cudaFree(r->counts); cudaFree(r->counters);
+	if (r->counts_host) cudaFreeHost(r->counts_host);
+	cudaFree(r->image_sum); cudaFree(r->last_pass); cudaFree(r->image_u8);
+	r->st = PathState(); r->queue[0] = r->queue[1] = nullptr; r->counts = nullptr; r->counts_host = nullptr; r->counters = nullptr;
+	r->image_sum = nullptr; r->last_pass = nullptr; r->image_u8 = nullptr;
+}
+
+template <class T>
+int upload(ptb_renderer* r, const T* host, size_t count, const T** out)
+{
+	void* d = nullptr;
+	size_t bytes = std::max<size_t>(count * sizeof(T), 16);
+	PTB_CUDA(cudaMalloc(&d, bytes));
+	r->scene_allocs.push_back(d);
+	if (count) PTB_CUDA(cudaMemcpyAsync(d, host, count * sizeof(T), cudaMemcpyHostToDevice, r->stream));
+	*out = (const T*)d;
+	return 0;
+}
+
+void release_scene_device(ptb_renderer* r)
+{
+	for (void* p : r->scene_allocs) cudaFree(p);
+	r->scene_allocs.clear();
+	memset(&r->dscene, 0, sizeof(r->dscene));
+	r->bvh_nodes = r->bvh_bytes = 0;
+}
+
+DeviceMaterial pack_material(const ptb_material& m)
+{
+	DeviceMaterial d;
+	int transparent = m.is_transparent ? 1 : 0;
+	float tbits, dbits, sbits;
+	memcpy(&tbits, &transparent, 4); memcpy(&dbits, &m.diffuse_texture_id, 4); memcpy(&sbits, &m.specular_texture_id, 4);
+	d.a = make_float4(m.diffuse_color[0], m.diffuse_color[1], m.diffuse_color[2], m.roughness);
+	d.b = make_float4(m.emission_color[0], m.emission_color[1], m.emission_color[2], m.refraction_index);
+	d.c = make_float4(m.specular_color[0], m.specular_color[1], m.specular_color[2], m.extinction_coefficient);
+	d.d = make_float4(m.absorption_coefficient[0], m.absorption_coefficient[1], m.absorption_coefficient[2], m.reduced_scattering_coefficient[0]);
+	d.e = make_float4(m.reduced_scattering_coefficient[1], m.reduced_scattering_coefficient[2], tbits, dbits);
+	d.f = make_float4(sbits, 0.0f, 0.0f, 0.0f);
+	return d;
+}
+
+int upload_scene(ptb_renderer* r)
+{
+	release_scene_device(r);
+	const HostScene& s = r->scene;
+	DeviceScene& ds = r->dscene;
+	memset(&ds, 0, sizeof(ds));
+
+	// acceleration structure over all meshes' world-space triangles
+	Bvh2 bvh;
+	build_bvh2_sah(s.triangles, 4, bvh);
+	GpuBvh2 flat;
+	flatten_bvh2(bvh, s.triangles, flat);
+	if (upload(r, (const float4*)flat.nodes.data(), flat.nodes.size() / 4, &ds.bvh_nodes)) return 1;
+	if (upload(r, (const float4*)flat.tris.data(), flat.tris.size() / 4, &ds.tri_isect)) return 1;
+	ds.n_triangles = (int)s.triangles.size();
+	ds.root_ref = 0;
+	r->bvh_nodes = (int64_t)flat.nodes.size() / 16;
+	r->bvh_bytes = (int64_t)(flat.nodes.size() + flat.tris.size()) * 4;
+
+	// shading attributes by global triangle id
+	std::vector<float> shade((size_t)s.triangles.size() * 16);
+	for (size_t i = 0; i < s.triangles.size(); i++)
+	{
+		const Triangle& t = s.triangles[i];
+		float* d = &shade[i * 16];
+		d[0] = t.n0.x; d[1] = t.n0.y; d[2] = t.n0.z; d[3] = t.n1.x;
+		d[4] = t.n1.y; d[5] = t.n1.z; d[6] = t.n2.x; d[7] = t.n2.y;
+		d[8] = t.n2.z; d[9] = t.uv0.x; d[10] = t.uv0.y; d[11] = t.uv1.x;
+		d[12] = t.uv1.y; d[13] = t.uv2.x; d[14] = t.uv2.y;
+		memcpy(&d[15], &s.triangle_material[i], 4);
+	}
+	if (upload(r, (const float4*)shade.data(), shade.size() / 4, &ds.tri_shade)) return 1;
+
+	std::vector<DeviceMaterial> mats;
+	for (auto& m : s.materials) mats.push_back(pack_material(m));
+	ds.sphere_material_base = (int)mats.size();
+	std::vector<float4> spheres;
+	for (auto& sp : s.spheres)
+	{
+		mats.push_back(pack_material(sp.mat));
+		spheres.push_back(make_float4(sp.center.x, sp.center.y, sp.center.z, sp.radius));
+	}
+	if (upload(r, mats.data(), mats.size(), &ds.materials)) return 1;
+	if (upload(r, spheres.data(), spheres.size(), &ds.spheres)) return 1;
+	ds.n_spheres = (int)spheres.size();
+
+	std::vector<DeviceTexture> textures;
+	for (auto& t : s.textures)
+	{
+		DeviceTexture dt;
+		if (upload(r, t.rgba.data(), t.rgba.size(), &dt.pixels)) return 1;
+		dt.width = t.width; dt.height = t.height;
+		textures.push_back(dt);
+	}
+	if (upload(r, textures.data(), textures.size(), &ds.textures)) return 1;
+	ds.n_textures = (int)textures.size();
+
+	for (int f = 0; f < 6; f++)
+		if (upload(r, s.cube_faces[f].rgba.data(), s.cube_faces[f].rgba.size(), &ds.sky.faces[f])) return 1;
+	ds.sky.length = s.cube_length;
+	ds.sky.use_sky_box = r->cfg.use_sky_box ? 1 : 0;
+	ds.sky.use_sky = r->cfg.use_sky ? 1 : 0;
+	ds.sky.use_bilinear = r->cfg.use_bilinear ? 1 : 0;
+	PTB_CUDA(cudaStreamSynchronize(r->stream));
+	return 0;
+}
+
+DeviceConfig device_config(const ptb_renderer* r)
+{
+	DeviceConfig c;
+	c.max_depth = r->cfg.max_tracer_depth;
+	c.bias_length = r->cfg.vector_bias_length;
+	c.energy_threshold = r->cfg.energy_exist_threshold;
+	c.sss_threshold = r->cfg.sss_threshold;
+	c.use_bilinear = r->cfg.use_bilinear ? 1 : 0;
+	c.gamma_correction = r->cfg.gamma_correction ? 1 : 0;
+	c.use_anti_alias = r->cfg.use_anti_alias ? 1 : 0;
+	c.air_n = r->cfg.air_refraction_index;
+	c.air_sigma_a = make_float3(r->cfg.air_absorption_coef.x, r->cfg.air_absorption_coef.y, r->cfg.air_absorption_coef.z);
+	c.air_sigma_s = make_float3(r->cfg.air_reduced_scattering_coef.x, r->cfg.air_reduced_scattering_coef.y, r->cfg.air_reduced_scattering_coef.z);
+	return c;
+}
+
+CameraParams camera_params(const ptb_camera& c)
+{
+	CameraParams p;
+	p.eye = make_float3(c.eye[0], c.eye[1], c.eye[2]);
+	p.view = make_float3(c.view[0], c.view[1], c.view[2]);
+	p.up = make_float3(c.up[0], c.up[1], c.up[2]);
+	p.resolution = make_float2(c.resolution[0], c.resolution[1]);
+	p.fov = make_float2(c.fov[0], c.fov[1]);
+	p.aperture_radius = c.aperture_radius;
+	p.focal_distance = c.focal_distance;
+	return p;
+}
+
+int grid_for(const ptb_renderer* r, size_t items, int block, int blocks_per_sm)
+{
+	size_t need = (items + block - 1) / block;
+	size_t cap = (size_t)r->sm_count * blocks_per_sm;
+	return (int)std::max<size_t>(1, std::min(need, cap));
+}
+
+// enqueue one batch of n_slots passes: first, first+stride, ...
+int enqueue_batch(ptb_renderer* r, int first_pass, int stride, int n_slots)
+{
+	const int px = r->pixel_count;
+	const size_t total = (size_t)px * n_slots;
+	DeviceConfig dc = device_config(r);
+	CameraParams cp = camera_params(r->cam);
+	const int n_counts = r->cfg.max_tracer_depth + 2;
+	const bool prof = r->profile_stages != 0;
+	k_generate<<<grid_for(r, total, 256, 8), 256, 0, r->stream>>>(r->st, r->queue[0], r->counts, n_counts, cp, dc, px, n_slots, first_pass, stride);
+	r->stats.kernel_launches++;
+	for (int depth = 0; depth < r->cfg.max_tracer_depth; depth++)
+	{
+		int* qin = r->queue[depth & 1];
+		int* qout = r->queue[(depth + 1) & 1];
+		cudaEvent_t e0 = nullptr, e1 = nullptr;
+		if (prof)
+		{
+			cudaEventCreate(&e0); cudaEventCreate(&e1);
+			r->stage_events.push_back(e0); r->stage_events.push_back(e1);
+			cudaEventRecord(e0, r->stream);
+		}
+		if (r->count_traversal)
+			k_extend<true><<<grid_for(r, total, 128, 16), 128, 0, r->stream>>>(r->dscene, r->st, qin, r->counts + depth, r->counters);
+		else
+			k_extend<false><<<grid_for(r, total, 128, 16), 128, 0, r->stream>>>(r->dscene, r->st, qin, r->counts + depth, r->counters);
+		if (prof) cudaEventRecord(e1, r->stream);
+		k_shade<<<grid_for(r, total, 128, 16), 128, 0, r->stream>>>(r->dscene, r->st, dc, depth, px, first_pass, stride, qin, r->counts + depth, qout, r->counts + depth + 1);
+		r->stats.kernel_launches += 2;
+	}
+	k_accumulate<<<(px + 255) / 256, 256, 0, r->stream>>>(r->st.radiance, r->image_sum, r->last_pass, px, n_slots, (float)r->cfg.max_tracer_depth * 2.0f);
+	r->stats.kernel_launches++;
+	// ray-segment counters of this batch -> host (summed after the stream drains)
+	PTB_CUDA(cudaMemcpyAsync(r->counts_host, r->counts, n_counts * sizeof(int), cudaMemcpyDeviceToHost, r->stream));
+	PTB_CUDA(cudaGetLastError());
+	return 0;
+}
+
+int render_impl(ptb_renderer* r, int first_pass, int stride, int n_passes, bool advance_counter, bool synchronous)
+{
+	if (!r || r->host_only) { set_error("[Error]renderer has no CUDA device (host-only handle): rendering is unavailable, there is no CPU fallback"); return 1; }
+	if (!r->scene_loaded) { set_error("[Error]no scene loaded"); return 1; }
+	if (n_passes <= 0) return 0;
+	memset(&r->stats, 0, sizeof(r->stats));
+	r->stats.bvh_nodes = r->bvh_nodes; r->stats.bvh_bytes = r->bvh_bytes;
+	PTB_CUDA(cudaMemsetAsync(r->counters, 0, 2 * sizeof(unsigned long long), r->stream));
+	PTB_CUDA(cudaEventRecord(r->ev0, r->stream));
+	int done = 0;
+	const int n_counts = r->cfg.max_tracer_depth + 2;
+	while (done < n_passes)
+	{
+		int nb = std::min(r->passes_in_flight, n_passes - done);
+		if (enqueue_batch(r, first_pass + done * stride, stride, nb)) return 1;
+		done += nb;
+		if (synchronous)
+		{
+			// counts_host is reused per batch; drain before the next batch overwrites it
+			PTB_CUDA(cudaStreamSynchronize(r->stream));
+			for (int d = 0; d < n_counts - 1; d++) r->stats.ray_segments += r->counts_host[d];
+		}
+	}
+	if (advance_counter) r->pass_counter += n_passes;
+	int total_passes = advance_counter ? r->pass_counter : n_passes;
+	k_tonemap<<<(r->pixel_count + 255) / 256, 256, 0, r->stream>>>(r->image_sum, r->image_u8, r->pixel_count, std::max(total_passes, 1), r->cfg.gamma_correction ? 1 : 0);
+	r->stats.kernel_launches++;
+	PTB_CUDA(cudaEventRecord(r->ev1, r->stream));
+	r->stats.passes = n_passes;
+	if (synchronous)
+	{
+		PTB_CUDA(cudaStreamSynchronize(r->stream));
+		float ms = 0.0f;
+		cudaEventElapsedTime(&ms, r->ev0, r->ev1);
+		r->stats.gpu_ms_total = ms;
+		double ext = 0.0;
+		for (size_t i = 0; i + 1 < r->stage_events.size(); i += 2)
+		{
+			float m = 0.0f;
+			cudaEventElapsedTime(&m, r->stage_events[i], r->stage_events[i + 1]);
+			ext += m;
+		}
+		for (auto e : r->stage_events) cudaEventDestroy(e);
+		r->stage_events.clear();
+		r->stats.gpu_ms_extend = ext;
+		if (r->count_traversal)
+		{
+			unsigned long long c[2] = { 0, 0 };
+			cudaMemcpy(c, r->counters, sizeof(c), cudaMemcpyDeviceToHost);
+			r->stats.nodes_visited = (int64_t)c[0]; r->stats.tris_tested = (int64_t)c[1];
+		}
+	}
+	return 0;
+}
+
+// shared by ptb_trace_batch / ptb_trace_batch_bruteforce
+int trace_impl(ptb_renderer* r, const float* rays6, int n, int32_t* out_prim, float* out_t, float* out_bary, bool brute)
+{
+	if (!r || r->host_only) { set_error("[Error]renderer has no CUDA device (host-only handle): tracing is unavailable, there is no CPU fallback"); return 1; }
+	if (!r->scene_loaded) { set_error("[Error]no scene loaded"); return 1; }
+	if (n <= 0) return 0;
+	float4 *d_o = nullptr, *d_d = nullptr, *d_hit = nullptr;
+	int* d_q = nullptr; int* d_count = nullptr;
+	std::vector<float4> ho(n), hd(n);
+	for (int i = 0; i < n; i++)
+	{
+		ho[i] = make_float4(rays6[i * 6 + 0], rays6[i * 6 + 1], rays6[i * 6 + 2], 0.0f);
+		hd[i] = make_float4(rays6[i * 6 + 3], rays6[i * 6 + 4], rays6[i * 6 + 5], 0.0f);
+	}
+	PTB_CUDA(cudaMalloc(&d_o, (size_t)n * sizeof(float4)));
+	PTB_CUDA(cudaMalloc(&d_d, (size_t)n * sizeof(float4)));
+	PTB_CUDA(cudaMalloc(&d_hit, (size_t)n * sizeof(float4)));
+	PTB_CUDA(cudaMalloc(&d_q, (size_t)n * sizeof(int)));
+	PTB_CUDA(cudaMalloc(&d_count, sizeof(int)));
+	PTB_CUDA(cudaMemcpyAsync(d_o, ho.data(), (size_t)n * sizeof(float4), cudaMemcpyHostToDevice, r->stream));
+	PTB_CUDA(cudaMemcpyAsync(d_d, hd.data(), (size_t)n * sizeof(float4), cudaMemcpyHostToDevice, r->stream));
+	if (brute)
+	{
+		k_bruteforce<<<(n + 127) / 128, 128, 0, r->stream>>>(r->dscene, d_o, d_d, d_hit, n);
+	}
+	else
+	{
+		k_iota<<<(n + 255) / 256, 256, 0, r->stream>>>(d_q, d_count, n);
+		PathState st;
+		memset(&st, 0, sizeof(st));
+		st.ray_o = d_o; st.ray_d = d_d; st.hit = d_hit;
+		k_extend<false><<<grid_for(r, n, 128, 16), 128, 0, r->stream>>>(r->dscene, st, d_q, d_count, r->counters);
+	}
+	std::vector<float4> hh(n);
+	PTB_CUDA(cudaMemcpyAsync(hh.data(), d_hit, (size_t)n * sizeof(float4), cudaMemcpyDeviceToHost, r->stream));
+	PTB_CUDA(cudaStreamSynchronize(r->stream));
+	PTB_CUDA(cudaGetLastError());
+	for (int i = 0; i < n; i++)
+	{
+		int prim;
+		memcpy(&prim, &hh[i].w, 4);
+		out_prim[i] = prim;
+		if (out_t) out_t[i] = hh[i].x;
+		if (out_bary) { out_bary[i * 2] = hh[i].y; out_bary[i * 2 + 1] = hh[i].z; }
+	}
+	cudaFree(d_o); cudaFree(d_d); cudaFree(d_hit); cudaFree(d_q); cudaFree(d_count);
+	return 0;
+}
+
+} // namespace
+
+// ==========================================================================================
+// C ABI
+// ==========================================================================================
+
+extern "C"
+{
+
+const char* ptb_last_error(void) { return last_error().c_str(); }
+int ptb_version(void) { return 100; }
+
+int ptb_device_count(void)
+{
+	int n = 0;
+	if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+	return n;
+}
+
+ptb_renderer* ptb_create(const char* config_json_path, int cuda_device)
+{
+	ptb_renderer* r = new ptb_renderer();
+	memset(&r->stats, 0, sizeof(r->stats));
+	memset(&r->dscene, 0, sizeof(r->dscene));
+	memset(&r->st, 0, sizeof(r->st));
+	if (!config_json_path || !load_config(config_json_path, r->cfg)) { delete r; return nullptr; }
+	default_camera((float)r->cfg.width, (float)r->cfg.height, -1.0f, -1.0f, r->cam);
+	r->device = cuda_device;
+	if (cuda_device < 0)
+	{
+		// host-only handle: scene loading and introspection work, every compute entry point fails
+		r->host_only = true;
+		return r;
+	}
+	cudaError_t e = cudaSetDevice(cuda_device);
+	if (e != cudaSuccess)
+	{
+		set_error(std::string("[Cuda]cannot select device ") + std::to_string(cuda_device) + ": " + cudaGetErrorString(e) + " (there is no CPU fallback)");
+		cudaGetLastError();
+		delete r;
+		return nullptr;
+	}
+	cudaDeviceProp prop;
+	if (cudaGetDeviceProperties(&prop, cuda_device) == cudaSuccess) r->sm_count = prop.multiProcessorCount;
+	if (cudaStreamCreateWithFlags(&r->stream, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreate(&r->ev0) != cudaSuccess || cudaEventCreate(&r->ev1) != cudaSuccess)
+	{
+		set_error("[Cuda]cannot create stream/events");
+		delete r;
+		return nullptr;
+	}
+	if (alloc_work_buffers(r)) { free_work_buffers(r); delete r; return nullptr; }
+	return r;
+}
+
+void ptb_destroy(ptb_renderer* r)
+{
+	if (!r) return;
+	if (!r->host_only)
+	{
+		cudaSetDevice(r->device);
+		cudaStreamSynchronize(r->stream);
+		release_scene_device(r);
+		free_work_buffers(r);
+		if (r->ev0) cudaEventDestroy(r->ev0);
+		if (r->ev1) cudaEventDestroy(r->ev1);
+		if (r->stream) cudaStreamDestroy(r->stream);
+	}
+	delete r;
+}
+
+int ptb_list_scenes(const char* scene_dir, char* out, int cap)
+{
+	std::vector<std::string> files;
+	int n = list_scenes(scene_dir ? scene_dir : "", files);
+	if (n < 0) { set_error("[Warn]There exists no scene file!"); return -1; }
+	std::string all;
+	for (auto& f : files) { all += f; all += "\n"; }
+	if ((int)all.size() + 1 > cap) { set_error("[Error]ptb_list_scenes: buffer too small"); return -1; }
+	memcpy(out, all.c_str(), all.size() + 1);
+	return n;
+}
+
+int ptb_load_scene(ptb_renderer* r, const char* scene_json_path, const char* asset_root)
+{
+	if (!r) { set_error("[Error]null renderer"); return 1; }
+	ptb_release_scene(r);
+	if (!load_scene(scene_json_path ? scene_json_path : "", asset_root ? asset_root : "", r->scene))
+	{
+		r->scene = HostScene();
+		return 1;
+	}
+	if (!r->host_only)
+	{
+		cudaSetDevice(r->device);
+		if (upload_scene(r)) { release_scene_device(r); r->scene = HostScene(); return 1; }
+	}
+	r->scene_loaded = true;
+	return ptb_clear(r);
+}
+
+int ptb_release_scene(ptb_renderer* r)
+{
+	if (!r) return 1;
+	if (!r->host_only) { cudaSetDevice(r->device); cudaStreamSynchronize(r->stream); release_scene_device(r); }
+	r->scene = HostScene();
+	r->scene_loaded = false;
+	return 0;
+}
+
+int ptb_default_camera(float width, float height, float aperture_radius, float focal_distance, ptb_camera* out)
+{
+	if (!out) return 1;
+	default_camera(width, height, aperture_radius, focal_distance, *out);
+	return 0;
+}
+
+int ptb_set_camera(ptb_renderer* r, const ptb_camera* cam) { if (!r || !cam) return 1; r->cam = *cam; return 0; }
+int ptb_get_camera(ptb_renderer* r, ptb_camera* out) { if (!r || !out) return 1; *out = r->cam; return 0; }
+
+int ptb_render(ptb_renderer* r, int n_passes)
+{
+	if (!r) { set_error("[Error]null renderer"); return 1; }
+	return render_impl(r, r->pass_counter + 1, 1, n_passes, true, true);
+}
+
+int ptb_render_async(ptb_renderer* r, int n_passes)
+{
+	if (!r) { set_error("[Error]null renderer"); return 1; }
+	return render_impl(r, r->pass_counter + 1, 1, n_passes, true, false);
+}
+
+int ptb_render_strided(ptb_renderer* r, int first_pass, int stride, int n_passes)
+{
+	if (!r) { set_error("[Error]null renderer"); return 1; }
+	int rc = render_impl(r, first_pass, stride, n_passes, false, true);
+	if (rc == 0) r->pass_counter += n_passes;
+	return rc;
+}
+
+int ptb_synchronize(ptb_renderer* r)
+{
+	if (!r || r->host_only) return 1;
+	PTB_CUDA(cudaStreamSynchronize(r->stream));
+	return 0;
+}
+
+void* ptb_stream(ptb_renderer* r) { return r ? (void*)r->stream : nullptr; }
+
+int ptb_clear(ptb_renderer* r)
+{
+	if (!r) return 1;
+	r->pass_counter = 0;
+	if (r->host_only) return 0;
+	cudaSetDevice(r->device);
+	PTB_CUDA(cudaMemsetAsync(r->image_sum, 0, (size_t)r->pixel_count * 3 * sizeof(float), r->stream));
+	PTB_CUDA(cudaStreamSynchronize(r->stream));
+	return 0;
+}
+
+int ptb_pass_counter(ptb_renderer* r) { return r ? r->pass_counter : 0; }
+int ptb_width(ptb_renderer* r) { return r ? r->cfg.width : 0; }
+int ptb_height(ptb_renderer* r) { return r ? r->cfg.height : 0; }
+
+int ptb_image_f32(ptb_renderer* r, float* out_rgb_sum, int* out_passes)
+{
+	if (!r || r->host_only) { set_error("[Error]no CUDA device"); return 1; }
+	PTB_CUDA(cudaMemcpyAsync(out_rgb_sum, r->image_sum, (size_t)r->pixel_count * 3 * sizeof(float), cudaMemcpyDeviceToHost, r->stream));
+	PTB_CUDA(cudaStreamSynchronize(r->stream));
+	if (out_passes) *out_passes = r->pass_counter;
+	return 0;
+}
+
+int ptb_image_u8(ptb_renderer* r, uint8_t* out_rgb)
+{
+	if (!r || r->host_only) { set_error("[Error]no CUDA device"); return 1; }
+	PTB_CUDA(cudaMemcpyAsync(out_rgb, r->image_u8, (size_t)r->pixel_count * 3, cudaMemcpyDeviceToHost, r->stream));
+	PTB_CUDA(cudaStreamSynchronize(r->stream));
+	return 0;
+}
+
+int ptb_last_pass_f32(ptb_renderer* r, float* out_rgb)
+{
+	if (!r || r->host_only) { set_error("[Error]no CUDA device"); return 1; }
+	PTB_CUDA(cudaMemcpyAsync(out_rgb, r->last_pass, (size_t)r->pixel_count * 3 * sizeof(float), cudaMemcpyDeviceToHost, r->stream));
+	PTB_CUDA(cudaStreamSynchronize(r->stream));
+	return 0;
+}
+
+void* ptb_image_device_ptr(ptb_renderer* r) { return (r && !r->host_only) ? (void*)r->image_sum : nullptr; }
+
+int ptb_finalize(ptb_renderer* r, int total_passes)
+{
+	if (!r || r->host_only) { set_error("[Error]no CUDA device"); return 1; }
+	k_tonemap<<<(r->pixel_count + 255) / 256, 256, 0, r->stream>>>(r->image_sum, r->image_u8, r->pixel_count, std::max(total_passes, 1), r->cfg.gamma_correction ? 1 : 0);
+	PTB_CUDA(cudaStreamSynchronize(r->stream));
+	r->pass_counter = total_passes;
+	return 0;
+}
+
+int ptb_trace_batch(ptb_renderer* r, const float* rays6, int n, int32_t* out_prim, float* out_t, float* out_bary)
+{
+	return trace_impl(r, rays6, n, out_prim, out_t, out_bary, false);
+}
+
+int ptb_trace_batch_bruteforce(ptb_renderer* r, const float* rays6, int n, int32_t* out_prim, float* out_t)
+{
+	return trace_impl(r, rays6, n, out_prim, out_t, nullptr, true);
+}
+
+int ptb_generate_rays(ptb_renderer* r, int pass, float* out_rays6)
+{
+	if (!r || r->host_only) { set_error("[Error]no CUDA device"); return 1; }
+	const int px = r->pixel_count;
+	k_generate<<<grid_for(r, px, 256, 8), 256, 0, r->stream>>>(r->st, r->queue[0], r->counts, r->cfg.max_tracer_depth + 2, camera_params(r->cam), device_config(r), px, 1, pass, 1);
+	std::vector<float4> o(px), d(px);
+	PTB_CUDA(cudaMemcpyAsync(o.data(), r->st.ray_o, (size_t)px * sizeof(float4), cudaMemcpyDeviceToHost, r->stream));
+	PTB_CUDA(cudaMemcpyAsync(d.data(), r->st.ray_d, (size_t)px * sizeof(float4), cudaMemcpyDeviceToHost, r->stream));
+	PTB_CUDA(cudaStreamSynchronize(r->stream));
+	for (int i = 0; i < px; i++)
+	{
+		out_rays6[i * 6 + 0] = o[i].x; out_rays6[i * 6 + 1] = o[i].y; out_rays6[i * 6 + 2] = o[i].z;
+		out_rays6[i * 6 + 3] = d[i].x; out_rays6[i * 6 + 4] = d[i].y; out_rays6[i * 6 + 5] = d[i].z;
+	}
+	return 0;
+}
+
+int ptb_get_stats(ptb_renderer* r, ptb_stats* out) { if (!r || !out) return 1; *out = r->stats; return 0; }
+
+int ptb_set_option(ptb_renderer* r, const char* key, const char* value)
+{
+	if (!r || !key || !value) return 1;
+	std::string k = key, v = value;
+	if (k == "passes_in_flight")
+	{
+		int n = atoi(value);
+		if (n < 1 || n > 64) { set_error("[Error]passes_in_flight must be in 1..64"); return 1; }
+		if (n != r->passes_in_flight)
+		{
+			r->passes_in_flight = n;
+			if (!r->host_only)
+			{
+				cudaSetDevice(r->device);
+				cudaStreamSynchronize(r->stream);
+				free_work_buffers(r);
+				if (alloc_work_buffers(r)) return 1;
+				r->pass_counter = 0;
+			}
+		}
+		return 0;
+	}
+	if (k == "profile_stages") { r->profile_stages = atoi(value); return 0; }
+	if (k == "count_traversal") { r->count_traversal = atoi(value); return 0; }
+	if (k == "bvh_builder") { r->bvh_builder = v; return 0; }
+	set_error("[Error]unknown option " + k);
+	return 1;
+}
+
+int ptb_scene_counts(ptb_renderer* r, int* n_triangles, int* n_materials, int* n_spheres, int* n_textures, int* cube_length, int* n_meshes)
+{
+	if (!r || !r->scene_loaded) { set_error("[Error]no scene loaded"); return 1; }
+	if (n_triangles) *n_triangles = (int)r->scene.triangles.size();
+	if (n_materials) *n_materials = (int)r->scene.materials.size();
+	if (n_spheres) *n_spheres = (int)r->scene.spheres.size();
+	if (n_textures) *n_textures = (int)r->scene.textures.size();
+	if (cube_length) *cube_length = r->scene.cube_length;
+	if (n_meshes) *n_meshes = (int)r->scene.mesh_triangle_count.size();
+	return 0;
+}
+
+int ptb_scene_triangles(ptb_renderer* r, float* out24, int32_t* out_material)
+{
+	if (!r || !r->scene_loaded) { set_error("[Error]no scene loaded"); return 1; }
+	if (out24) memcpy(out24, r->scene.triangles.data(), r->scene.triangles.size() * sizeof(Triangle));
+	if (out_material) memcpy(out_material, r->scene.triangle_material.data(), r->scene.triangle_material.size() * sizeof(int32_t));
+	return 0;
+}
+
+int ptb_scene_materials(ptb_renderer* r, ptb_material* out)
+{
+	if (!r || !r->scene_loaded) { set_error("[Error]no scene loaded"); return 1; }
+	memcpy(out, r->scene.materials.data(), r->scene.materials.size() * sizeof(ptb_material));
+	return 0;
+}
+
+int ptb_scene_spheres(ptb_renderer* r, void* out100)
+{
+	if (!r || !r->scene_loaded) { set_error("[Error]no scene loaded"); return 1; }
+	memcpy(out100, r->scene.spheres.data(), r->scene.spheres.size() * sizeof(Sphere));
+	return 0;
+}
+
+int ptb_scene_texture(ptb_renderer* r, int index, int* width, int* height, uint8_t* out_rgba)
+{
+	if (!r || !r->scene_loaded || index < 0 || index >= (int)r->scene.textures.size()) { set_error("[Error]bad texture index"); return 1; }
+	const Texture& t = r->scene.textures[index];
+	if (width) *width = t.width;
+	if (height) *height = t.height;
+	if (out_rgba) memcpy(out_rgba, t.rgba.data(), t.rgba.size());
+	return 0;
+}
+
+int ptb_scene_cubemap_face(ptb_renderer* r, int face, uint8_t* out_rgba)
+{
+	if (!r || !r->scene_loaded || face < 0 || face > 5) { set_error("[Error]bad cube face"); return 1; }
+	memcpy(out_rgba, r->scene.cube_faces[face].rgba.data(), r->scene.cube_faces[face].rgba.size());
+	return 0;
+}
+
+int ptb_get_config(ptb_renderer* r, void* out96)
+{
+	if (!r || !out96) return 1;
+	memcpy(out96, &r->cfg, sizeof(Config));
+	return 0;
+}
+
+} // extern "C"

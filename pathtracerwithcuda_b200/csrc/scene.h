@@ -1,0 +1,93 @@
+// Host-side scene model of the ptb200 render path: what the reference keeps in
+// scene_parser / triangle_mesh / cube_map_loader / config_parser, flattened.
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+#include "../../include/ptb200.h"
+
+namespace ptb
+{
+
+struct Vec3 { float x, y, z; };
+struct Vec2 { float x, y; };
+
+// Field-for-field mirror of the reference `configuration` (Core/configuration.h:9-34, 96 bytes).
+struct Config
+{
+	int width;
+	int height;
+	bool use_fullscreen;
+	int block_size;
+	int max_block_size;
+	int max_tracer_depth;
+	float vector_bias_length;
+	float energy_exist_threshold;
+	float sss_threshold;
+	bool use_sky_box;
+	bool use_sky;
+	bool use_bilinear;
+	bool gamma_correction;
+	bool use_anti_alias;
+	float fov;
+	int bvh_leaf_node_triangle_num;
+	int bvh_bucket_max_divide_internal_num;
+	int bvh_build_block_size;
+	int bvh_build;                 // 0 NaiveCPU, 1 MortonCodeCPU, 2 MortonCodeCUDA (Bvh/bvh_build_config.h)
+	float air_refraction_index;
+	Vec3 air_absorption_coef;
+	Vec3 air_reduced_scattering_coef;
+	bool cuda_acceleration;
+};
+static_assert(sizeof(Config) == 96, "Config must match the reference configuration layout");
+static_assert(sizeof(ptb_material) == 84, "ptb_material must match the reference material layout");
+static_assert(sizeof(ptb_camera) == 64, "ptb_camera must match the reference render_camera layout");
+
+// One triangle as the reference stores it after upload (Core/triangle.h:11-25), minus the pointer.
+struct Triangle
+{
+	Vec3 v0, v1, v2;
+	Vec3 n0, n1, n2;
+	Vec2 uv0, uv1, uv2;
+};
+static_assert(sizeof(Triangle) == 96, "24 floats");
+
+struct Sphere
+{
+	Vec3 center;
+	float radius;
+	ptb_material mat;
+};
+static_assert(sizeof(Sphere) == 100, "Sphere must match the reference sphere layout");
+
+struct Texture
+{
+	int width = 0, height = 0;
+	std::vector<uint8_t> rgba;     // RGBA8, row 0 = top (Others/image_loader.cpp:31-95)
+};
+
+struct HostScene
+{
+	std::vector<Triangle> triangles;       // global order: meshes in JSON order, shapes, faces
+	std::vector<int32_t> triangle_material; // index into `materials`
+	std::vector<ptb_material> materials;    // per-mesh private copies, concatenated
+	std::vector<int> mesh_triangle_count;
+	std::vector<int> mesh_material_count;
+	std::vector<Sphere> spheres;
+	std::vector<Texture> textures;
+	Texture cube_faces[6];                  // +x -x +y -y +z -z
+	int cube_length = 0;
+};
+
+// Error text of the last failing loader call on this thread.
+std::string& last_error();
+void set_error(const std::string& msg);
+
+bool load_config(const std::string& path, Config& out);
+bool load_scene(const std::string& scene_json_path, const std::string& asset_root, HostScene& out);
+bool load_image_rgba8(const std::string& path, Texture& out);
+bool builtin_material(const std::string& name, ptb_material& out);
+void default_camera(float width, float height, float aperture, float focal, ptb_camera& out);
+int list_scenes(const std::string& dir, std::vector<std::string>& out);
+
+} // namespace ptb

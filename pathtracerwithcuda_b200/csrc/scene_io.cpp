@@ -1,0 +1,1152 @@
+// Scene front-end of the ptb200 render path: reads the reference's config JSON, scene JSON and
+// OBJ groups UNCHANGED and produces the flat HostScene the device side uploads.
+//
+// Behaviour follows (file:line under /root/reference/gpu_path_tracer/):
+//   config       Core/config_parser.cpp:8-124 (all 23 keys mandatory, every value a string)
+//   scene        Core/scene_parser.cpp:37-442 (Background/Texture/Material/Sphere/Mesh)
+//   OBJ          Core/triangle_mesh.cpp:8-213 over tinyobjloader 1.1.0 semantics
+//                (lib/tiny_obj_loader/tiny_obj_loader.h:498-611 number grammar, :747-800 index
+//                triples, :985-1175 ear clipping, :1660-1960 shape splitting)
+//   transforms   triangle_mesh.cpp:147-170,200-202,617-647 with glm 0.9.9's operation order
+//                (lib/glm/gtc/matrix_transform.inl:10-87, detail/func_matrix.inl:297-355,
+//                detail/type_mat4x4.inl:487-520) so world-space vertices are bit-identical
+//   materials    Core/material.cpp:12-580, scene_parser.cpp:675-708
+//   images       Others/image_loader.cpp:31-95 pixel contract (RGBA8, A=255, row 0 = top)
+// This file must be compiled WITHOUT floating-point contraction (-ffp-contract=off): the
+// reference's host code is plain IEEE binary32 with no fused multiply-adds.
+#include "scene.h"
+#include "json_min.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <fstream>
+#include <map>
+#include <sstream>
+#include <dirent.h>
+
+namespace ptb
+{
+
+std::string& last_error()
+{
+	static thread_local std::string e;
+	return e;
+}
+
+void set_error(const std::string& msg)
+{
+	last_error() = msg;
+}
+
+// ------------------------------------------------------------------------------------------
+// small helpers
+// ------------------------------------------------------------------------------------------
+
+static std::string normalize_separators(std::string p)
+{
+	for (auto& c : p) if (c == '\\') c = '/';
+	return p;
+}
+
+static std::string join_path(const std::string& root, const std::string& rel)
+{
+	std::string r = normalize_separators(rel);
+	if (root.empty() || (!r.empty() && r[0] == '/')) return r;
+	if (root.back() == '/') return root + r;
+	return root + "/" + r;
+}
+
+static bool read_text_file(const std::string& path, std::string& out)
+{
+	std::ifstream f(path, std::ios::in | std::ios::binary);
+	if (!f) return false;
+	std::ostringstream ss;
+	ss << f.rdbuf();
+	out = ss.str();
+	return true;
+}
+
+// `istringstream >> float` (config_parser.cpp:189-195): leading blanks skipped, 0 on failure.
+static float parse_float(const std::string& text)
+{
+	const char* s = text.c_str();
+	char* end = nullptr;
+	float v = strtof(s, &end);
+	return end == s ? 0.0f : v;
+}
+
+static int parse_int(const std::string& text)
+{
+	const char* s = text.c_str();
+	char* end = nullptr;
+	long v = strtol(s, &end, 10);
+	if (end == s) return 0;
+	if (v > 2147483647L) v = 2147483647L;
+	if (v < -2147483647L - 1) v = -2147483647L - 1;
+	return (int)v;
+}
+
+static bool parse_bool(const std::string& text)
+{
+	return text == "true";
+}
+
+static Vec3 parse_float3(const std::string& text)
+{
+	float v[3] = { 0.0f, 0.0f, 0.0f };
+	const char* s = text.c_str();
+	for (int k = 0; k < 3; k++)
+	{
+		char* end = nullptr;
+		float f = strtof(s, &end);
+		if (end == s) break;
+		v[k] = f;
+		s = end;
+	}
+	return Vec3{ v[0], v[1], v[2] };
+}
+
+static float clampf(float f, float a, float b)
+{
+	return fmaxf(a, fminf(f, b));
+}
+
+// ------------------------------------------------------------------------------------------
+// config
+// ------------------------------------------------------------------------------------------
+
+static bool get_string(const JValue& obj, const char* category, const char* key, std::string& out)
+{
+	const JValue& v = obj[key];
+	if (v.is_null())
+	{
+		set_error(std::string("[Error]") + category + " property <" + key + "> not defined!");
+		return false;
+	}
+	if (!v.is_string())
+	{
+		set_error(std::string("[Error]") + category + " property <" + key + "> must be a string");
+		return false;
+	}
+	out = v.str;
+	return true;
+}
+
+bool load_config(const std::string& path, Config& c)
+{
+	std::string text, err;
+	if (!read_text_file(normalize_separators(path), text)) { set_error("[Error]cannot open config file " + path); return false; }
+	JValue root;
+	if (!JParser(text).parse(root, err)) { set_error("[Error]config parse error: " + err); return false; }
+	if (!root.is_object()) { set_error("[Error]config must be a JSON object"); return false; }
+
+	static const char* keys[23] = {
+		"Height", "Width", "FullScreen", "BlockSize", "MaxBlockSize", "MaxDepth", "BiasLength", "EnergyThreshold",
+		"SSSThreshold", "Skybox", "BilinearSample", "Sky", "GammaCorrection", "AntiAlias", "FOV", "BvhLeafNodeTriangleNum",
+		"BvhBucketMaxDivideInternalNum", "BvhBuildBlockSize", "BvhBuildMethod", "AirRefractionIndex", "AirAbsorptionCoef",
+		"AirReducedScatteringCoef", "CUDAAcceleration" };
+	std::map<std::string, std::string> s;
+	for (const char* k : keys)
+	{
+		std::string v;
+		if (!get_string(root, "Config", k, v)) return false;
+		s[k] = v;
+	}
+
+	memset(&c, 0, sizeof(c));
+	c.height = parse_int(s["Height"]);
+	c.width = parse_int(s["Width"]);
+	c.use_fullscreen = parse_bool(s["FullScreen"]);
+	c.block_size = parse_int(s["BlockSize"]);
+	c.max_block_size = parse_int(s["MaxBlockSize"]);
+	c.max_tracer_depth = parse_int(s["MaxDepth"]);
+	c.vector_bias_length = parse_float(s["BiasLength"]);
+	c.energy_exist_threshold = parse_float(s["EnergyThreshold"]);
+	c.sss_threshold = parse_float(s["SSSThreshold"]);
+	c.use_sky_box = parse_bool(s["Skybox"]);
+	c.use_bilinear = parse_bool(s["BilinearSample"]);
+	c.use_sky = parse_bool(s["Sky"]);
+	c.gamma_correction = parse_bool(s["GammaCorrection"]);
+	c.use_anti_alias = parse_bool(s["AntiAlias"]);
+	// config_parser.cpp:111 parses FOV with parse_bool -> 0.0 or 1.0; rendering never reads it.
+	c.fov = parse_bool(s["FOV"]) ? 1.0f : 0.0f;
+	c.bvh_leaf_node_triangle_num = parse_int(s["BvhLeafNodeTriangleNum"]);
+	c.bvh_bucket_max_divide_internal_num = parse_int(s["BvhBucketMaxDivideInternalNum"]);
+	c.bvh_build_block_size = parse_int(s["BvhBuildBlockSize"]);
+	std::string method = s["BvhBuildMethod"];
+	std::transform(method.begin(), method.end(), method.begin(), [](unsigned char ch) { return (char)tolower(ch); });
+	c.bvh_build = method == "mortoncodecpu" ? 1 : (method == "mortoncodecuda" ? 2 : 0);
+	c.air_refraction_index = parse_float(s["AirRefractionIndex"]);
+	c.air_absorption_coef = parse_float3(s["AirAbsorptionCoef"]);
+	c.air_reduced_scattering_coef = parse_float3(s["AirReducedScatteringCoef"]);
+	c.cuda_acceleration = parse_bool(s["CUDAAcceleration"]);
+
+	if (c.width <= 0 || c.height <= 0) { set_error("[Error]config Width/Height must be positive"); return false; }
+	return true;
+}
+
+// ------------------------------------------------------------------------------------------
+// camera (Core/camera.cpp:3-14,56-60,80-98)
+// ------------------------------------------------------------------------------------------
+
+void default_camera(float width, float height, float aperture, float focal, ptb_camera& out)
+{
+	const float PI_F = 3.1415926535897f;
+	float yaw = 0.0f, pitch = 0.3f, radius = 14.0f;
+	float aperture_radius = 0.0f, focal_distance = radius;
+	float fov_x = 45.0f;
+	// set_fov: degrees_to_radians = d / 180 * PI; radians_to_degrees = r * 180 / PI (Math/basic_math.hpp:41-49)
+	float half = (fov_x / 180.0f * PI_F) * 0.5f;
+	float fov_y = (atanf(tanf(half) * (height / width)) * 2.0f) * 180.0f / PI_F;
+	if (focal >= 0.0f) focal_distance = fminf(fmaxf(focal, 0.0f), 2.0f * radius);
+	if (aperture >= 0.0f) aperture_radius = fminf(fmaxf(aperture, 0.0f), 1.0f);
+
+	float x = sinf(yaw) * cosf(pitch);
+	float y = sinf(pitch);
+	float z = cosf(yaw) * cosf(pitch);
+	memset(&out, 0, sizeof(out));
+	out.eye[0] = 0.0f + x * radius; out.eye[1] = 0.0f + y * radius; out.eye[2] = 0.0f + z * radius;
+	out.view[0] = -1.0f * x; out.view[1] = -1.0f * y; out.view[2] = -1.0f * z;
+	out.up[0] = 0.0f; out.up[1] = 1.0f; out.up[2] = 0.0f;
+	out.resolution[0] = width; out.resolution[1] = height;
+	out.fov[0] = fov_x; out.fov[1] = fov_y;
+	out.focal_distance = focal_distance;
+	out.aperture_radius = aperture_radius;
+}
+
+// ------------------------------------------------------------------------------------------
+// built-in materials (Core/material.cpp)
+// ------------------------------------------------------------------------------------------
+
+static ptb_material make_material(float dr, float dg, float db, float er, float eg, float eb, float sr, float sg, float sb,
+	bool transparent, float roughness, float n, float k, float ar, float ag, float ab, float s)
+{
+	ptb_material m;
+	memset(&m, 0, sizeof(m));
+	m.diffuse_color[0] = dr; m.diffuse_color[1] = dg; m.diffuse_color[2] = db;
+	m.emission_color[0] = er; m.emission_color[1] = eg; m.emission_color[2] = eb;
+	m.specular_color[0] = sr; m.specular_color[1] = sg; m.specular_color[2] = sb;
+	m.is_transparent = transparent ? 1 : 0;
+	m.roughness = roughness;
+	m.refraction_index = n;
+	m.extinction_coefficient = k;
+	m.absorption_coefficient[0] = ar; m.absorption_coefficient[1] = ag; m.absorption_coefficient[2] = ab;
+	m.reduced_scattering_coefficient[0] = s; m.reduced_scattering_coefficient[1] = s; m.reduced_scattering_coefficient[2] = s;
+	m.diffuse_texture_id = -1;
+	m.specular_texture_id = -1;
+	return m;
+}
+
+static ptb_material metal(float sr, float sg, float sb, float n, float k)
+{
+	return make_material(0, 0, 0, 0, 0, 0, sr, sg, sb, false, 0.3f, n, k, 0, 0, 0, 0);
+}
+
+static ptb_material opaque(float dr, float dg, float db, float spec)
+{
+	return make_material(dr, dg, db, 0, 0, 0, spec, spec, spec, false, 0.01f, 1.491f, 0, 0, 0, 0, 0);
+}
+
+static const std::map<std::string, ptb_material>& builtin_table()
+{
+	static const std::map<std::string, ptb_material> table = {
+		{ "titanium", metal(0.542f, 0.497f, 0.499f, 2.2670f, 3.0385f) },
+		{ "chromium", metal(0.549f, 0.556f, 0.554f, 2.3230f, 3.1350f) },
+		{ "iron", metal(0.562f, 0.556f, 0.578f, 2.5845f, 2.7670f) },
+		{ "nickel", metal(0.662f, 0.609f, 0.526f, 1.7290f, 2.9435f) },
+		{ "platinum", metal(0.673f, 0.637f, 0.585f, 1.3400f, 1.0300f) },
+		{ "copper", metal(0.955f, 0.638f, 0.538f, 1.2404f, 2.3929f) },
+		{ "palladium", metal(0.733f, 0.697f, 0.652f, 1.4080f, 3.2540f) },
+		{ "zinc", metal(0.664f, 0.824f, 0.850f, 0.67767f, 4.01220f) },
+		{ "gold", metal(1.022f, 0.782f, 0.344f, 0.89863f, 2.4584f) },
+		{ "aluminum", metal(0.913f, 0.922f, 0.924f, 0.63324f, 5.4544f) },
+		{ "silver", metal(0.972f, 0.960f, 0.915f, 0.04f, 2.6484f) },
+		{ "glass", make_material(1, 1, 1, 0, 0, 0, 0.045f, 0.045f, 0.045f, true, 0.1f, 1.5319f, 0, 0, 0, 0, 0) },
+		{ "green_glass", make_material(1, 1, 1, 0, 0, 0, 0.045f, 0.045f, 0.045f, true, 0.1f, 1.5319f, 0, 0.8f, 0.01f, 0.8f, 0) },
+		{ "diamond", make_material(1, 1, 1, 0, 0, 0, 1, 1, 1, true, 0.01f, 2.4392f, 0, 0, 0, 0, 0) },
+		{ "red", opaque(0.87f, 0.15f, 0.15f, 1.0f) },
+		{ "green", opaque(0.15f, 0.87f, 0.15f, 1.0f) },
+		{ "orange", opaque(0.93f, 0.33f, 0.04f, 1.0f) },
+		{ "purple", opaque(0.5f, 0.1f, 0.9f, 1.0f) },
+		{ "blue", opaque(0.4f, 0.6f, 0.8f, 1.0f) },
+		{ "wall_blue", opaque(0.4f, 0.6f, 0.8f, 0.0f) },
+		{ "wall_red", opaque(0.87f, 0.15f, 0.15f, 0.0f) },
+		{ "wall_green", opaque(0.15f, 0.87f, 0.15f, 0.0f) },
+		{ "wall_white", opaque(1.0f, 1.0f, 1.0f, 0.0f) },
+		{ "marble", make_material(0, 0, 0, 0, 0, 0, 1, 1, 1, true, 0.01f, 1.486f, 0, 0.6f, 0.6f, 0.6f, 8.0f) },
+		{ "something_blue", make_material(0, 0, 0, 0, 0, 0, 1, 1, 1, true, 0.01f, 1.333f, 0, 0.9f, 0.3f, 0.02f, 2.0f) },
+		{ "something_red", make_material(0, 0, 0, 0, 0, 0, 1, 1, 1, true, 0.01f, 1.35f, 0, 0.02f, 5.1f, 5.7f, 9.0f) },
+		{ "light", make_material(0, 0, 0, 13.0f, 13.0f, 11.0f, 0, 0, 0, false, 0.01f, 1.000293f, 0, 0, 0, 0, 0) },
+	};
+	return table;
+}
+
+bool builtin_material(const std::string& name, ptb_material& out)
+{
+	auto it = builtin_table().find(name);
+	if (it == builtin_table().end()) return false;
+	out = it->second;
+	return true;
+}
+
+// ------------------------------------------------------------------------------------------
+// images: RGBA8, A=255, row 0 = top
+// ------------------------------------------------------------------------------------------
+
+static bool read_binary_file(const std::string& path, std::vector<uint8_t>& out)
+{
+	FILE* fp = fopen(path.c_str(), "rb");
+	if (!fp) return false;
+	fseek(fp, 0, SEEK_END);
+	long n = ftell(fp);
+	fseek(fp, 0, SEEK_SET);
+	out.resize(n > 0 ? (size_t)n : 0);
+	size_t got = n > 0 ? fread(out.data(), 1, (size_t)n, fp) : 0;
+	fclose(fp);
+	return got == (size_t)(n > 0 ? n : 0);
+}
+
+static uint32_t le32(const uint8_t* p) { return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24); }
+static uint32_t le16(const uint8_t* p) { return (uint32_t)p[0] | ((uint32_t)p[1] << 8); }
+
+static bool decode_bmp(const std::vector<uint8_t>& f, Texture& out)
+{
+	if (f.size() < 54 || f[0] != 'B' || f[1] != 'M') return false;
+	uint32_t data_offset = le32(&f[10]);
+	int32_t w = (int32_t)le32(&f[18]);
+	int32_t h = (int32_t)le32(&f[22]);
+	uint32_t bits = le16(&f[28]);
+	uint32_t compression = le32(&f[30]);
+	if (w <= 0 || h == 0 || (bits != 24 && bits != 32) || (compression != 0 && compression != 3)) return false;
+	bool bottom_up = h > 0;
+	uint32_t rows = (uint32_t)(h > 0 ? h : -h);
+	uint32_t bpp = bits / 8;
+	size_t pitch = ((size_t)w * bpp + 3) & ~(size_t)3;
+	if (f.size() < data_offset + pitch * rows) return false;
+	out.width = w;
+	out.height = (int)rows;
+	out.rgba.resize((size_t)w * rows * 4);
+	for (uint32_t y = 0; y < rows; y++)
+	{
+		const uint8_t* src = &f[data_offset + (size_t)(bottom_up ? rows - 1 - y : y) * pitch];
+		uint8_t* dst = &out.rgba[(size_t)y * w * 4];
+		for (int32_t x = 0; x < w; x++)
+		{
+			dst[x * 4 + 0] = src[x * bpp + 2];
+			dst[x * 4 + 1] = src[x * bpp + 1];
+			dst[x * 4 + 2] = src[x * bpp + 0];
+			dst[x * 4 + 3] = 255;
+		}
+	}
+	return true;
+}
+
+// Uncompressed / RLE true-colour and greyscale TGA (types 2, 3, 10, 11).
+static bool decode_tga(const std::vector<uint8_t>& f, Texture& out)
+{
+	if (f.size() < 18) return false;
+	uint32_t id_len = f[0], cmap_type = f[1], type = f[2];
+	uint32_t w = le16(&f[12]), h = le16(&f[14]), bits = f[16], desc = f[17];
+	if (cmap_type != 0 || (type != 2 && type != 3 && type != 10 && type != 11) || w == 0 || h == 0) return false;
+	uint32_t bpp = bits / 8;
+	if (bpp != 1 && bpp != 3 && bpp != 4) return false;
+	size_t pos = 18 + id_len;
+	std::vector<uint8_t> px((size_t)w * h * bpp);
+	if (type == 2 || type == 3)
+	{
+		if (f.size() < pos + px.size()) return false;
+		memcpy(px.data(), &f[pos], px.size());
+	}
+	else
+	{
+		size_t o = 0;
+		while (o < px.size())
+		{
+			if (pos >= f.size()) return false;
+			uint8_t hd = f[pos++];
+			uint32_t count = (hd & 0x7F) + 1;
+			if (hd & 0x80)
+			{
+				if (pos + bpp > f.size()) return false;
+				for (uint32_t k = 0; k < count && o + bpp <= px.size(); k++) { memcpy(&px[o], &f[pos], bpp); o += bpp; }
+				pos += bpp;
+			}
+			else
+			{
+				size_t n = (size_t)count * bpp;
+				if (pos + n > f.size() || o + n > px.size()) return false;
+				memcpy(&px[o], &f[pos], n); o += n; pos += n;
+			}
+		}
+	}
+	bool top_down = (desc & 0x20) != 0;
+	bool right_left = (desc & 0x10) != 0;
+	out.width = (int)w; out.height = (int)h;
+	out.rgba.resize((size_t)w * h * 4);
+	for (uint32_t y = 0; y < h; y++)
+	{
+		const uint8_t* src = &px[(size_t)(top_down ? y : h - 1 - y) * w * bpp];
+		uint8_t* dst = &out.rgba[(size_t)y * w * 4];
+		for (uint32_t x = 0; x < w; x++)
+		{
+			const uint8_t* p = src + (size_t)(right_left ? w - 1 - x : x) * bpp;
+			if (bpp == 1) { dst[x * 4 + 0] = dst[x * 4 + 1] = dst[x * 4 + 2] = p[0]; }
+			else { dst[x * 4 + 0] = p[2]; dst[x * 4 + 1] = p[1]; dst[x * 4 + 2] = p[0]; }
+			dst[x * 4 + 3] = 255;
+		}
+	}
+	return true;
+}
+
+// "<file>.rgba8" side-car (u32 width, u32 height, RGBA8 top-down): how a caller hands over
+// formats this library does not decode itself (JPG, PNG); the reference used FreeImage for all.
+static bool decode_sidecar(const std::vector<uint8_t>& f, Texture& out)
+{
+	if (f.size() < 8) return false;
+	uint32_t w = le32(&f[0]), h = le32(&f[4]);
+	if (w == 0 || h == 0 || f.size() != 8 + (size_t)w * h * 4) return false;
+	out.width = (int)w; out.height = (int)h;
+	out.rgba.assign(f.begin() + 8, f.end());
+	for (size_t i = 3; i < out.rgba.size(); i += 4) out.rgba[i] = 255;
+	return true;
+}
+
+bool load_image_rgba8(const std::string& path_in, Texture& out)
+{
+	std::string path = normalize_separators(path_in);
+	std::vector<uint8_t> bytes;
+	if (read_binary_file(path + ".rgba8", bytes) && decode_sidecar(bytes, out)) return true;
+	if (!read_binary_file(path, bytes)) { set_error("[Error]Failed to load image file " + path); return false; }
+	if (decode_bmp(bytes, out)) return true;
+	std::string lower = path;
+	std::transform(lower.begin(), lower.end(), lower.begin(), [](unsigned char ch) { return (char)tolower(ch); });
+	if (lower.size() > 4 && lower.substr(lower.size() - 4) == ".tga" && decode_tga(bytes, out)) return true;
+	set_error("[Error]Unsupported image file format (provide a .rgba8 side-car): " + path);
+	return false;
+}
+
+// ------------------------------------------------------------------------------------------
+// glm-order float32 matrix helpers (column-major m[col][row])
+// ------------------------------------------------------------------------------------------
+
+struct V4 { float x, y, z, w; };
+struct M4 { V4 c[4]; };
+
+static inline V4 v4(float x, float y, float z, float w) { return V4{ x, y, z, w }; }
+static inline V4 mul(const V4& a, float s) { return V4{ a.x * s, a.y * s, a.z * s, a.w * s }; }
+static inline V4 mul(const V4& a, const V4& b) { return V4{ a.x * b.x, a.y * b.y, a.z * b.z, a.w * b.w }; }
+static inline V4 add(const V4& a, const V4& b) { return V4{ a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w }; }
+static inline V4 sub(const V4& a, const V4& b) { return V4{ a.x - b.x, a.y - b.y, a.z - b.z, a.w - b.w }; }
+static inline float& at(V4& v, int i) { return (&v.x)[i]; }
+static inline float at(const V4& v, int i) { return (&v.x)[i]; }
+
+static M4 identity()
+{
+	M4 m;
+	m.c[0] = v4(1, 0, 0, 0); m.c[1] = v4(0, 1, 0, 0); m.c[2] = v4(0, 0, 1, 0); m.c[3] = v4(0, 0, 0, 1);
+	return m;
+}
+
+// glm::rotate(m, angle, axis) — matrix_transform.inl:19-47. `axis` must be a unit basis vector here
+// (normalize() of a basis vector is exact), which is all triangle_mesh.cpp:148-150 passes.
+static M4 rotate(const M4& m, float angle, float ax, float ay, float az)
+{
+	float c = cosf(angle);
+	float s = sinf(angle);
+	float inv_len = 1.0f / sqrtf(ax * ax + ay * ay + az * az);
+	float axis[3] = { ax * inv_len, ay * inv_len, az * inv_len };
+	float temp[3] = { (1.0f - c) * axis[0], (1.0f - c) * axis[1], (1.0f - c) * axis[2] };
+	float R[3][3];
+	R[0][0] = c + temp[0] * axis[0];
+	R[0][1] = temp[0] * axis[1] + s * axis[2];
+	R[0][2] = temp[0] * axis[2] - s * axis[1];
+	R[1][0] = temp[1] * axis[0] - s * axis[2];
+	R[1][1] = c + temp[1] * axis[1];
+	R[1][2] = temp[1] * axis[2] + s * axis[0];
+	R[2][0] = temp[2] * axis[0] + s * axis[1];
+	R[2][1] = temp[2] * axis[1] - s * axis[0];
+	R[2][2] = c + temp[2] * axis[2];
+	M4 r;
+	r.c[0] = add(add(mul(m.c[0], R[0][0]), mul(m.c[1], R[0][1])), mul(m.c[2], R[0][2]));
+	r.c[1] = add(add(mul(m.c[0], R[1][0]), mul(m.c[1], R[1][1])), mul(m.c[2], R[1][2]));
+	r.c[2] = add(add(mul(m.c[0], R[2][0]), mul(m.c[1], R[2][1])), mul(m.c[2], R[2][2]));
+	r.c[3] = m.c[3];
+	return r;
+}
+
+static M4 translate(const M4& m, float x, float y, float z)
+{
+	M4 r = m;
+	r.c[3] = add(add(add(mul(m.c[0], x), mul(m.c[1], y)), mul(m.c[2], z)), m.c[3]);
+	return r;
+}
+
+static M4 scale(const M4& m, float x, float y, float z)
+{
+	M4 r;
+	r.c[0] = mul(m.c[0], x); r.c[1] = mul(m.c[1], y); r.c[2] = mul(m.c[2], z); r.c[3] = m.c[3];
+	return r;
+}
+
+static M4 transpose(const M4& m)
+{
+	M4 r;
+	for (int i = 0; i < 4; i++) for (int j = 0; j < 4; j++) at(r.c[i], j) = at(m.c[j], i);
+	return r;
+}
+
+// glm::inverse(mat4) — detail/func_matrix.inl:297-355
+static M4 inverse(const M4& mm)
+{
+	auto m = [&](int col, int row) { return at(mm.c[col], row); };
+	float Coef00 = m(2, 2) * m(3, 3) - m(3, 2) * m(2, 3);
+	float Coef02 = m(1, 2) * m(3, 3) - m(3, 2) * m(1, 3);
+	float Coef03 = m(1, 2) * m(2, 3) - m(2, 2) * m(1, 3);
+	float Coef04 = m(2, 1) * m(3, 3) - m(3, 1) * m(2, 3);
+	float Coef06 = m(1, 1) * m(3, 3) - m(3, 1) * m(1, 3);
+	float Coef07 = m(1, 1) * m(2, 3) - m(2, 1) * m(1, 3);
+	float Coef08 = m(2, 1) * m(3, 2) - m(3, 1) * m(2, 2);
+	float Coef10 = m(1, 1) * m(3, 2) - m(3, 1) * m(1, 2);
+	float Coef11 = m(1, 1) * m(2, 2) - m(2, 1) * m(1, 2);
+	float Coef12 = m(2, 0) * m(3, 3) - m(3, 0) * m(2, 3);
+	float Coef14 = m(1, 0) * m(3, 3) - m(3, 0) * m(1, 3);
+	float Coef15 = m(1, 0) * m(2, 3) - m(2, 0) * m(1, 3);
+	float Coef16 = m(2, 0) * m(3, 2) - m(3, 0) * m(2, 2);
+	float Coef18 = m(1, 0) * m(3, 2) - m(3, 0) * m(1, 2);
+	float Coef19 = m(1, 0) * m(2, 2) - m(2, 0) * m(1, 2);
+	float Coef20 = m(2, 0) * m(3, 1) - m(3, 0) * m(2, 1);
+	float Coef22 = m(1, 0) * m(3, 1) - m(3, 0) * m(1, 1);
+	float Coef23 = m(1, 0) * m(2, 1) - m(2, 0) * m(1, 1);
+
+	V4 Fac0 = v4(Coef00, Coef00, Coef02, Coef03);
+	V4 Fac1 = v4(Coef04, Coef04, Coef06, Coef07);
+	V4 Fac2 = v4(Coef08, Coef08, Coef10, Coef11);
+	V4 Fac3 = v4(Coef12, Coef12, Coef14, Coef15);
+	V4 Fac4 = v4(Coef16, Coef16, Coef18, Coef19);
+	V4 Fac5 = v4(Coef20, Coef20, Coef22, Coef23);
+
+	V4 Vec0 = v4(m(1, 0), m(0, 0), m(0, 0), m(0, 0));
+	V4 Vec1 = v4(m(1, 1), m(0, 1), m(0, 1), m(0, 1));
+	V4 Vec2 = v4(m(1, 2), m(0, 2), m(0, 2), m(0, 2));
+	V4 Vec3_ = v4(m(1, 3), m(0, 3), m(0, 3), m(0, 3));
+
+	V4 Inv0 = add(sub(mul(Vec1, Fac0), mul(Vec2, Fac1)), mul(Vec3_, Fac2));
+	V4 Inv1 = add(sub(mul(Vec0, Fac0), mul(Vec2, Fac3)), mul(Vec3_, Fac4));
+	V4 Inv2 = add(sub(mul(Vec0, Fac1), mul(Vec1, Fac3)), mul(Vec3_, Fac5));
+	V4 Inv3 = add(sub(mul(Vec0, Fac2), mul(Vec1, Fac4)), mul(Vec2, Fac5));
+
+	V4 SignA = v4(+1, -1, +1, -1);
+	V4 SignB = v4(-1, +1, -1, +1);
+	M4 Inverse;
+	Inverse.c[0] = mul(Inv0, SignA); Inverse.c[1] = mul(Inv1, SignB); Inverse.c[2] = mul(Inv2, SignA); Inverse.c[3] = mul(Inv3, SignB);
+
+	V4 Row0 = v4(Inverse.c[0].x, Inverse.c[1].x, Inverse.c[2].x, Inverse.c[3].x);
+	V4 Dot0 = mul(mm.c[0], Row0);
+	float Dot1 = (Dot0.x + Dot0.y) + (Dot0.z + Dot0.w);
+	float OneOverDeterminant = 1.0f / Dot1;
+	M4 r;
+	for (int i = 0; i < 4; i++) r.c[i] = mul(Inverse.c[i], OneOverDeterminant);
+	return r;
+}
+
+// mat4 * vec4 — detail/type_mat4x4.inl:507-518: (m0*v0 + m1*v1) + (m2*v2 + m3*v3)
+static V4 transform(const M4& m, const V4& v)
+{
+	V4 Add0 = add(mul(m.c[0], v.x), mul(m.c[1], v.y));
+	V4 Add1 = add(mul(m.c[2], v.z), mul(m.c[3], v.w));
+	return add(Add0, Add1);
+}
+
+// The reference normalises normals on the host with Math/cuda_math.hpp:1458-1462
+// (v * rsqrtf(dot(v,v))). Under nvcc's host pass rsqrtf is CUDA's host fallback,
+// (float)(1.0 / sqrt((double)x)); the parity baseline (oracle/_ref) is built that way.
+static Vec3 normalize_host(float x, float y, float z)
+{
+	float d = x * x + y * y + z * z;
+	float inv = (float)(1.0 / sqrt((double)d));
+	return Vec3{ x * inv, y * inv, z * inv };
+}
+
+// ------------------------------------------------------------------------------------------
+// OBJ (tinyobjloader 1.1.0 semantics)
+// ------------------------------------------------------------------------------------------
+
+namespace
+{
+
+struct ObjIndex { int v = -1, vt = -1, vn = -1; };
+
+struct ObjShape
+{
+	std::vector<ObjIndex> indices; // 3 per triangle
+};
+
+struct ObjData
+{
+	std::vector<float> v, vn, vt;
+	std::vector<ObjShape> shapes;
+};
+
+inline bool is_space(char c) { return c == ' ' || c == '\t'; }
+inline bool is_digit(char c) { return (unsigned)(c - '0') < 10u; }
+inline bool is_new_line(char c) { return c == '\r' || c == '\n' || c == '\0'; }
+
+// tiny_obj_loader.h:498-611 — hand-rolled decimal grammar accumulated in double.
+bool try_parse_double(const char* s, const char* s_end, double* result)
+{
+	if (s >= s_end) return false;
+	double mantissa = 0.0;
+	int exponent = 0;
+	char sign = '+', exp_sign = '+';
+	const char* curr = s;
+	int read = 0;
+	bool end_not_reached = false;
+
+	if (*curr == '+' || *curr == '-') { sign = *curr; curr++; }
+	else if (!is_digit(*curr)) return false;
+
+	end_not_reached = (curr != s_end);
+	while (end_not_reached && is_digit(*curr))
+	{
+		mantissa *= 10;
+		mantissa += (int)(*curr - 0x30);
+		curr++; read++;
+		end_not_reached = (curr != s_end);
+	}
+	if (read == 0) return false;
+	bool assemble = !end_not_reached;
+
+	if (!assemble)
+	{
+		if (*curr == '.')
+		{
+			curr++;
+			read = 1;
+			end_not_reached = (curr != s_end);
+			while (end_not_reached && is_digit(*curr))
+			{
+				static const double pow_lut[] = { 1.0, 0.1, 0.01, 0.001, 0.0001, 0.00001, 0.000001, 0.0000001 };
+				const int lut_entries = 8;
+				mantissa += (int)(*curr - 0x30) * (read < lut_entries ? pow_lut[read] : std::pow(10.0, -read));
+				read++; curr++;
+				end_not_reached = (curr != s_end);
+			}
+		}
+		else if (*curr == 'e' || *curr == 'E') { }
+		else assemble = true;
+	}
+
+	if (!assemble && end_not_reached && (*curr == 'e' || *curr == 'E'))
+	{
+		curr++;
+		end_not_reached = (curr != s_end);
+		if (end_not_reached && (*curr == '+' || *curr == '-')) { exp_sign = *curr; curr++; }
+		else if (is_digit(*curr)) { }
+		else return false;
+		read = 0;
+		end_not_reached = (curr != s_end);
+		while (end_not_reached && is_digit(*curr))
+		{
+			exponent *= 10;
+			exponent += (int)(*curr - 0x30);
+			curr++; read++;
+			end_not_reached = (curr != s_end);
+		}
+		exponent *= (exp_sign == '+' ? 1 : -1);
+		if (read == 0) return false;
+	}
+
+	*result = (sign == '+' ? 1 : -1) * (exponent ? std::ldexp(mantissa * std::pow(5.0, exponent), exponent) : mantissa);
+	return true;
+}
+
+float parse_real(const char** token, double default_value = 0.0)
+{
+	(*token) += strspn((*token), " \t");
+	const char* end = (*token) + strcspn((*token), " \t\r");
+	double val = default_value;
+	try_parse_double((*token), end, &val);
+	(*token) = end;
+	return (float)val;
+}
+
+bool fix_index(int idx, int n, int* ret)
+{
+	if (idx > 0) { *ret = idx - 1; return true; }
+	if (idx == 0) return false;
+	*ret = n + idx;
+	return true;
+}
+
+// tiny_obj_loader.h:747-800
+bool parse_triple(const char** token, int vsize, int vnsize, int vtsize, ObjIndex* ret)
+{
+	ObjIndex vi;
+	if (!fix_index(atoi(*token), vsize, &vi.v)) return false;
+	(*token) += strcspn((*token), "/ \t\r");
+	if ((*token)[0] != '/') { *ret = vi; return true; }
+	(*token)++;
+	if ((*token)[0] == '/')
+	{
+		(*token)++;
+		if (!fix_index(atoi(*token), vnsize, &vi.vn)) return false;
+		(*token) += strcspn((*token), "/ \t\r");
+		*ret = vi;
+		return true;
+	}
+	if (!fix_index(atoi(*token), vtsize, &vi.vt)) return false;
+	(*token) += strcspn((*token), "/ \t\r");
+	if ((*token)[0] != '/') { *ret = vi; return true; }
+	(*token)++;
+	if (!fix_index(atoi(*token), vnsize, &vi.vn)) return false;
+	(*token) += strcspn((*token), "/ \t\r");
+	*ret = vi;
+	return true;
+}
+
+int point_in_polygon(int nvert, const float* vertx, const float* verty, float testx, float testy)
+{
+	int c = 0;
+	for (int i = 0, j = nvert - 1; i < nvert; j = i++)
+	{
+		if (((verty[i] > testy) != (verty[j] > testy)) &&
+			(testx < (vertx[j] - vertx[i]) * (testy - verty[i]) / (verty[j] - verty[i]) + vertx[i]))
+			c = !c;
+	}
+	return c;
+}
+
+// tiny_obj_loader.h:985-1175 with triangulate=true: project on the dominant plane of the first
+// non-degenerate corner, then clip ears; a triangle passes through untouched.
+void emit_face(ObjShape& shape, const std::vector<ObjIndex>& face, const std::vector<float>& v)
+{
+	size_t npolys = face.size();
+	size_t axes[2] = { 1, 2 };
+	for (size_t k = 0; k < npolys; ++k)
+	{
+		size_t vi0 = (size_t)face[(k + 0) % npolys].v, vi1 = (size_t)face[(k + 1) % npolys].v, vi2 = (size_t)face[(k + 2) % npolys].v;
+		float e0x = v[vi1 * 3 + 0] - v[vi0 * 3 + 0], e0y = v[vi1 * 3 + 1] - v[vi0 * 3 + 1], e0z = v[vi1 * 3 + 2] - v[vi0 * 3 + 2];
+		float e1x = v[vi2 * 3 + 0] - v[vi1 * 3 + 0], e1y = v[vi2 * 3 + 1] - v[vi1 * 3 + 1], e1z = v[vi2 * 3 + 2] - v[vi1 * 3 + 2];
+		float cx = (float)fabs(e0y * e1z - e0z * e1y);
+		float cy = (float)fabs(e0z * e1x - e0x * e1z);
+		float cz = (float)fabs(e0x * e1y - e0y * e1x);
+		const float epsilon = 0.0001f;
+		if (cx > epsilon || cy > epsilon || cz > epsilon)
+		{
+			if (cx > cy && cx > cz) { }
+			else
+			{
+				axes[0] = 0;
+				if (cz > cx && cz > cy) axes[1] = 1;
+			}
+			break;
+		}
+	}
+
+	float area = 0;
+	for (size_t k = 0; k < npolys; ++k)
+	{
+		size_t vi0 = (size_t)face[(k + 0) % npolys].v, vi1 = (size_t)face[(k + 1) % npolys].v;
+		float v0x = v[vi0 * 3 + axes[0]], v0y = v[vi0 * 3 + axes[1]];
+		float v1x = v[vi1 * 3 + axes[0]], v1y = v[vi1 * 3 + axes[1]];
+		area += (v0x * v1y - v0y * v1x) * 0.5f;
+	}
+
+	int max_rounds = 10;
+	std::vector<ObjIndex> remaining = face;
+	size_t guess_vert = 0;
+	ObjIndex ind[3];
+	float vx[3], vy[3];
+	while (remaining.size() > 3 && max_rounds > 0)
+	{
+		npolys = remaining.size();
+		if (guess_vert >= npolys) { max_rounds -= 1; guess_vert -= npolys; }
+		for (size_t k = 0; k < 3; k++)
+		{
+			ind[k] = remaining[(guess_vert + k) % npolys];
+			size_t vi = (size_t)ind[k].v;
+			vx[k] = v[vi * 3 + axes[0]];
+			vy[k] = v[vi * 3 + axes[1]];
+		}
+		float e0x = vx[1] - vx[0], e0y = vy[1] - vy[0];
+		float e1x = vx[2] - vx[1], e1y = vy[2] - vy[1];
+		float cross = e0x * e1y - e0y * e1x;
+		if (cross * area < 0.0f) { guess_vert += 1; continue; }
+
+		bool overlap = false;
+		for (size_t other = 3; other < npolys; ++other)
+		{
+			size_t ovi = (size_t)remaining[(guess_vert + other) % npolys].v;
+			if (point_in_polygon(3, vx, vy, v[ovi * 3 + axes[0]], v[ovi * 3 + axes[1]])) { overlap = true; break; }
+		}
+		if (overlap) { guess_vert += 1; continue; }
+
+		shape.indices.push_back(ind[0]); shape.indices.push_back(ind[1]); shape.indices.push_back(ind[2]);
+
+		size_t removed = (guess_vert + 1) % npolys;
+		while (removed + 1 < npolys) { remaining[removed] = remaining[removed + 1]; removed += 1; }
+		remaining.pop_back();
+	}
+	if (remaining.size() == 3)
+	{
+		shape.indices.push_back(remaining[0]); shape.indices.push_back(remaining[1]); shape.indices.push_back(remaining[2]);
+	}
+}
+
+void flush_group(ObjShape& shape, std::vector<std::vector<ObjIndex>>& group, const std::vector<float>& v)
+{
+	for (auto& face : group) emit_face(shape, face, v);
+	group.clear();
+}
+
+bool parse_obj(const std::string& path, ObjData& out)
+{
+	std::string text;
+	if (!read_text_file(path, text)) { set_error("[Info]Load file " + path + " failed: Cannot open file"); return false; }
+	std::vector<std::vector<ObjIndex>> group;
+	ObjShape shape;
+	size_t pos = 0;
+	std::string line;
+	while (pos < text.size())
+	{
+		// safeGetline: lines end at \n, \r\n or a lone \r
+		size_t e = pos;
+		while (e < text.size() && text[e] != '\n' && text[e] != '\r') e++;
+		line.assign(text, pos, e - pos);
+		if (e < text.size() && text[e] == '\r' && e + 1 < text.size() && text[e + 1] == '\n') e++;
+		pos = e + 1;
+		if (line.empty()) continue;
+		const char* token = line.c_str();
+		token += strspn(token, " \t");
+		if (token[0] == '\0' || token[0] == '#') continue;
+
+		if (token[0] == 'v' && is_space(token[1]))
+		{
+			token += 2;
+			float x = parse_real(&token), y = parse_real(&token), z = parse_real(&token);
+			out.v.push_back(x); out.v.push_back(y); out.v.push_back(z);
+			continue;
+		}
+		if (token[0] == 'v' && token[1] == 'n' && is_space(token[2]))
+		{
+			token += 3;
+			float x = parse_real(&token), y = parse_real(&token), z = parse_real(&token);
+			out.vn.push_back(x); out.vn.push_back(y); out.vn.push_back(z);
+			continue;
+		}
+		if (token[0] == 'v' && token[1] == 't' && is_space(token[2]))
+		{
+			token += 3;
+			float x = parse_real(&token), y = parse_real(&token);
+			out.vt.push_back(x); out.vt.push_back(y);
+			continue;
+		}
+		if (token[0] == 'f' && is_space(token[1]))
+		{
+			token += 2;
+			token += strspn(token, " \t");
+			std::vector<ObjIndex> face;
+			while (!is_new_line(token[0]))
+			{
+				ObjIndex vi;
+				if (!parse_triple(&token, (int)(out.v.size() / 3), (int)(out.vn.size() / 3), (int)(out.vt.size() / 2), &vi))
+				{
+					set_error("[TinyObj]Failed parse `f' line(e.g. zero value for face index).");
+					return false;
+				}
+				face.push_back(vi);
+				token += strspn(token, " \t\r");
+			}
+			if (face.size() >= 3) group.push_back(face);
+			else if (!face.empty()) { set_error("[Error]" + path + " has a face with fewer than 3 vertices"); return false; }
+			continue;
+		}
+		// `usemtl`: no .mtl files ship, every name maps to material id -1, so the per-face material
+		// never changes and the statement is a no-op (tiny_obj_loader.h:1779-1803).
+		if (token[0] == 'g' && is_space(token[1]))
+		{
+			flush_group(shape, group, out.v);
+			if (!shape.indices.empty()) out.shapes.push_back(shape);
+			shape = ObjShape();
+			continue;
+		}
+		if (token[0] == 'o' && is_space(token[1]))
+		{
+			bool had_faces = !group.empty();
+			flush_group(shape, group, out.v);
+			if (had_faces) out.shapes.push_back(shape);
+			shape = ObjShape();
+			continue;
+		}
+	}
+	bool had_faces = !group.empty();
+	flush_group(shape, group, out.v);
+	if (had_faces || !shape.indices.empty()) out.shapes.push_back(shape);
+	return true;
+}
+
+} // namespace
+
+// triangle_mesh::load_obj + create_mesh_device_data for one mesh (triangle_mesh.cpp:8-213,558-655)
+static bool append_mesh(HostScene& scene, const std::string& path, const Vec3& position, const Vec3& scale_v, const Vec3& rotate_v,
+	std::vector<ptb_material> mats)
+{
+	if (mats.empty()) { set_error("[Error]Mesh has no material"); return false; }
+	ObjData obj;
+	if (!parse_obj(path, obj)) return false;
+	if (obj.vn.empty()) { set_error("[Error]Mesh does not have normal! (" + path + ")"); return false; }
+	const int mat_num = (int)mats.size();
+	const bool has_uv = !obj.vt.empty();
+
+	const float deg2rad = (float)0.01745329251994329576923690768489;
+	M4 rot = identity();
+	rot = rotate(rot, rotate_v.z * deg2rad, 0.0f, 0.0f, 1.0f);
+	rot = rotate(rot, rotate_v.y * deg2rad, 0.0f, 1.0f, 0.0f);
+	rot = rotate(rot, rotate_v.x * deg2rad, 1.0f, 0.0f, 0.0f);
+	M4 rot_it = transpose(inverse(rot));
+
+	M4 xf = identity();
+	xf = translate(xf, position.x, position.y, position.z);
+	xf = scale(xf, scale_v.x, scale_v.y, scale_v.z);
+	M4 xf_it = transpose(inverse(xf));
+
+	const int material_base = (int)scene.materials.size();
+	int mesh_triangles = 0;
+	const size_t nv = obj.v.size() / 3, nn = obj.vn.size() / 3, nt = obj.vt.size() / 2;
+	for (size_t si = 0; si < obj.shapes.size(); si++)
+	{
+		const ObjShape& sh = obj.shapes[si];
+		int mat_index = (int)si < mat_num ? (int)si : mat_num - 1;
+		for (size_t f = 0; f + 2 < sh.indices.size(); f += 3)
+		{
+			Triangle tri;
+			Vec3* vv[3] = { &tri.v0, &tri.v1, &tri.v2 };
+			Vec3* nn3[3] = { &tri.n0, &tri.n1, &tri.n2 };
+			Vec2* uu[3] = { &tri.uv0, &tri.uv1, &tri.uv2 };
+			for (int k = 0; k < 3; k++)
+			{
+				const ObjIndex& ix = sh.indices[f + k];
+				if (ix.v < 0 || (size_t)ix.v >= nv || ix.vn < 0 || (size_t)ix.vn >= nn || (has_uv && (ix.vt < 0 || (size_t)ix.vt >= nt)))
+				{
+					set_error("[Error]" + path + ": face index out of range / missing normal or texcoord index");
+					return false;
+				}
+				V4 p = transform(rot, v4(obj.v[ix.v * 3], obj.v[ix.v * 3 + 1], obj.v[ix.v * 3 + 2], 1.0f));
+				V4 n = transform(rot_it, v4(obj.vn[ix.vn * 3], obj.vn[ix.vn * 3 + 1], obj.vn[ix.vn * 3 + 2], 0.0f));
+				Vec3 n1 = normalize_host(n.x, n.y, n.z);
+				// upload step: world = T*S, normals through its inverse transpose, re-normalised
+				V4 pw = transform(xf, v4(p.x, p.y, p.z, 1.0f));
+				V4 nw = transform(xf_it, v4(n1.x, n1.y, n1.z, 0.0f));
+				*vv[k] = Vec3{ pw.x, pw.y, pw.z };
+				*nn3[k] = normalize_host(nw.x, nw.y, nw.z);
+				*uu[k] = has_uv ? Vec2{ obj.vt[ix.vt * 2], obj.vt[ix.vt * 2 + 1] } : Vec2{ 0.0f, 0.0f };
+			}
+			if (!has_uv) mats[mat_index].diffuse_texture_id = -1; // triangle_mesh.cpp:131-137
+			scene.triangles.push_back(tri);
+			scene.triangle_material.push_back(material_base + mat_index);
+			mesh_triangles++;
+		}
+	}
+	scene.materials.insert(scene.materials.end(), mats.begin(), mats.end());
+	scene.mesh_triangle_count.push_back(mesh_triangles);
+	scene.mesh_material_count.push_back(mat_num);
+	return true;
+}
+
+// ------------------------------------------------------------------------------------------
+// scene JSON
+// ------------------------------------------------------------------------------------------
+
+bool load_scene(const std::string& scene_json_path, const std::string& asset_root, HostScene& scene)
+{
+	scene = HostScene();
+	std::string text, err;
+	if (!read_text_file(normalize_separators(scene_json_path), text)) { set_error("[Error]cannot open scene file " + scene_json_path); return false; }
+	JValue root;
+	if (!JParser(text).parse(root, err)) { set_error("[Error]scene parse error: " + err); return false; }
+
+	std::map<std::string, ptb_material> materials = builtin_table();
+	std::vector<std::string> texture_paths;
+
+	// Background (scene_parser.cpp:80-110)
+	const JValue& background = root["Background"];
+	if (background.is_null()) { set_error("[Error]Background not defined!"); return false; }
+	if (background.is_array()) { set_error("[Error]Background can not be array!"); return false; }
+	std::string bg_name, bg_path, bg_format;
+	if (!get_string(background, "Background", "Name", bg_name)) return false;
+	if (!get_string(background, "Background", "Path", bg_path)) return false;
+	if (!get_string(background, "Background", "Format", bg_format)) return false;
+	static const char* face_names[6] = { "xpos", "xneg", "ypos", "yneg", "zpos", "zneg" };
+
+	// Texture (scene_parser.cpp:112-126)
+	const JValue& textures = root["Texture"];
+	if (!textures.is_null())
+	{
+		if (!textures.is_array()) { set_error("[Error]Texture must be array!"); return false; }
+		for (auto& t : textures.arr)
+		{
+			if (!t.is_string()) { set_error("[Error]Texture entries must be strings"); return false; }
+			texture_paths.push_back(t.str);
+		}
+	}
+
+	// Material (scene_parser.cpp:128-234)
+	const JValue& mats = root["Material"];
+	if (!mats.is_null())
+	{
+		if (!mats.is_array()) { set_error("[Error]Material must be array!"); return false; }
+		for (auto& m : mats.arr)
+		{
+			std::string name, diffuse, emission, specular, transparent, roughness, n, k, sa, ss;
+			if (!get_string(m, "Material", "Name", name) || !get_string(m, "Material", "Diffuse", diffuse) ||
+				!get_string(m, "Material", "Emission", emission) || !get_string(m, "Material", "Specular", specular) ||
+				!get_string(m, "Material", "Transparent", transparent) || !get_string(m, "Material", "Roughness", roughness) ||
+				!get_string(m, "Material", "RefractionIndex", n) || !get_string(m, "Material", "ExtinctionCoef", k) ||
+				!get_string(m, "Material", "AbsorptionCoef", sa) || !get_string(m, "Material", "ReducedScatteringCoef", ss))
+				return false;
+			ptb_material mat;
+			memset(&mat, 0, sizeof(mat));
+			Vec3 d = parse_float3(diffuse), e = parse_float3(emission), s = parse_float3(specular), a = parse_float3(sa), r = parse_float3(ss);
+			mat.diffuse_color[0] = d.x; mat.diffuse_color[1] = d.y; mat.diffuse_color[2] = d.z;
+			mat.emission_color[0] = e.x; mat.emission_color[1] = e.y; mat.emission_color[2] = e.z;
+			mat.specular_color[0] = s.x; mat.specular_color[1] = s.y; mat.specular_color[2] = s.z;
+			mat.is_transparent = parse_bool(transparent) ? 1 : 0;
+			mat.roughness = clampf(parse_float(roughness), 0.0f, 1.0f);
+			mat.refraction_index = parse_float(n);
+			mat.extinction_coefficient = parse_float(k);
+			mat.absorption_coefficient[0] = a.x; mat.absorption_coefficient[1] = a.y; mat.absorption_coefficient[2] = a.z;
+			mat.reduced_scattering_coefficient[0] = r.x; mat.reduced_scattering_coefficient[1] = r.y; mat.reduced_scattering_coefficient[2] = r.z;
+			mat.diffuse_texture_id = -1;
+			mat.specular_texture_id = -1;
+			const JValue* ids[2] = { &m["DiffuseTextureId"], &m["SpecularTextureId"] };
+			int32_t* dst[2] = { &mat.diffuse_texture_id, &mat.specular_texture_id };
+			for (int q = 0; q < 2; q++)
+			{
+				if (ids[q]->is_null()) continue;
+				if (!ids[q]->is_string()) { set_error("[Error]Materail <" + name + ">: texture id must be a string"); return false; }
+				int id = parse_int(ids[q]->str);
+				if (id != -1 && (id >= (int)texture_paths.size() || id < 0))
+				{
+					set_error("[Error]Materail <" + name + ">: Texture index out of range!");
+					return false;
+				}
+				*dst[q] = id;
+			}
+			if (mat.is_transparent && mat.extinction_coefficient > 0.0f)
+			{
+				set_error("[Error]Materail <" + name + ">: Extinction coefficient of transparent material should be zero!");
+				return false;
+			}
+			materials[name] = mat;
+		}
+	}
+
+	// Sphere (scene_parser.cpp:236-268)
+	std::vector<std::string> sphere_materials;
+	const JValue& spheres = root["Sphere"];
+	if (!spheres.is_null())
+	{
+		if (!spheres.is_array()) { set_error("[Error]Sphere must be array!"); return false; }
+		for (auto& s : spheres.arr)
+		{
+			std::string center, radius, material;
+			if (!get_string(s, "Sphere", "Center", center) || !get_string(s, "Sphere", "Radius", radius) || !get_string(s, "Sphere", "Material", material))
+				return false;
+			Sphere sp;
+			memset(&sp, 0, sizeof(sp));
+			sp.center = parse_float3(center);
+			sp.radius = clampf(parse_float(radius), 0.0f, INFINITY);
+			scene.spheres.push_back(sp);
+			sphere_materials.push_back(material);
+		}
+	}
+
+	// Mesh (scene_parser.cpp:270-322)
+	struct MeshDecl { std::string path; std::vector<std::string> mats; Vec3 position, scale, rotate; };
+	std::vector<MeshDecl> meshes;
+	const JValue& mesh_array = root["Mesh"];
+	if (!mesh_array.is_null())
+	{
+		if (!mesh_array.is_array()) { set_error("[Error]Mesh must be array!"); return false; }
+		for (auto& m : mesh_array.arr)
+		{
+			MeshDecl d;
+			std::string position, scale_s, rotate_s;
+			if (!get_string(m, "Mesh", "Path", d.path)) return false;
+			const JValue& mm = m["Material"];
+			if (mm.is_null()) { set_error("[Error]Mesh property <Material> not defined!"); return false; }
+			if (!get_string(m, "Mesh", "Position", position) || !get_string(m, "Mesh", "Scale", scale_s) || !get_string(m, "Mesh", "Rotate", rotate_s))
+				return false;
+			if (!mm.is_array()) { set_error("[Error]Material of mesh must be array!"); return false; }
+			for (auto& name : mm.arr)
+			{
+				if (!name.is_string()) { set_error("[Error]Material of mesh must be an array of strings"); return false; }
+				d.mats.push_back(name.str);
+			}
+			d.position = parse_float3(position);
+			Vec3 sc = parse_float3(scale_s);
+			d.scale = Vec3{ clampf(sc.x, 0.0f, INFINITY), clampf(sc.y, 0.0f, INFINITY), clampf(sc.z, 0.0f, INFINITY) };
+			d.rotate = parse_float3(rotate_s);
+			meshes.push_back(d);
+		}
+	}
+
+	// Step 2 (scene_parser.cpp:324-440): cube map, textures, material names, meshes, spheres
+	for (int f = 0; f < 6; f++)
+	{
+		std::string p = join_path(asset_root, bg_path + bg_name + "\\" + face_names[f] + "." + bg_format);
+		if (!load_image_rgba8(p, scene.cube_faces[f]))
+		{
+			set_error("[Error]Background load fail, please check the <Path> and <Name>! (" + p + ")");
+			return false;
+		}
+		const Texture& t = scene.cube_faces[f];
+		if (t.width != t.height || t.width != scene.cube_faces[0].width)
+		{
+			set_error("[Error]Background load fail: cube map faces must be square and equal (" + p + ")");
+			return false;
+		}
+	}
+	scene.cube_length = scene.cube_faces[0].width;
+
+	for (auto& tp : texture_paths)
+	{
+		Texture t;
+		if (!load_image_rgba8(join_path(asset_root, tp), t)) { set_error("[Error]Texture " + tp + " load fail."); return false; }
+		scene.textures.push_back(std::move(t));
+	}
+
+	bool missing = false;
+	std::string missing_names;
+	for (auto& n : sphere_materials) if (!materials.count(n)) { missing = true; missing_names += " <" + n + ">"; }
+	for (auto& m : meshes) for (auto& n : m.mats) if (!materials.count(n)) { missing = true; missing_names += " <" + n + ">"; }
+	if (missing) { set_error("[Error]Material" + missing_names + " not found!"); return false; }
+
+	for (auto& m : meshes)
+	{
+		std::vector<ptb_material> mesh_mats;
+		for (auto& n : m.mats) mesh_mats.push_back(materials[n]);
+		if (!append_mesh(scene, join_path(asset_root, m.path), m.position, m.scale, m.rotate, mesh_mats)) return false;
+	}
+	for (size_t i = 0; i < scene.spheres.size(); i++) scene.spheres[i].mat = materials[sphere_materials[i]];
+	return true;
+}
+
+int list_scenes(const std::string& dir_in, std::vector<std::string>& out)
+{
+	std::string dir = normalize_separators(dir_in);
+	DIR* d = opendir(dir.c_str());
+	if (!d) return -1;
+	while (dirent* e = readdir(d))
+	{
+		std::string n = e->d_name;
+		if (n.size() > 5 && n.substr(n.size() - 5) == ".json") out.push_back(join_path(dir, n));
+	}
+	closedir(d);
+	std::sort(out.begin(), out.end());
+	return (int)out.size();
+}
+
+} // namespace ptb
