@@ -1,0 +1,310 @@
+#!/usr/bin/env python3
+"""bench.py — headline benchmark of the ptb200 render hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload c2]
+
+metric  : path samples/sec in Mspp*px/s  (W*H*passes / seconds of the pass loop)
+workload: BASELINE.json configs[1] = 'c2' (procedural ~150k-triangle OBJ, silver conductor + red
+          dielectric blobs + emissive box + cube-map sky, 1920x1080, depth 8), synthetic/procedural
+          data generated on the box, seeds = pass indices.
+step    : PASSES_PER_STEP consecutive passes (1 spp each) of the hot path on one GPU.
+N > 1   : launched under torchrun, one process per GPU; rank r renders passes r+1, r+1+N, ...
+          (weak scaling: every rank does PASSES_PER_STEP passes per step); ONE NCCL sum-reduce of
+          the float accumulation buffer at the end of the timed region; value = samples of all
+          ranks / max-over-ranks device time.
+value   : device-timed (CUDA events on the library's render stream), scene resident in HBM.
+e2e     : same metric through the public C ABI with HOST buffers: each step sets the camera from
+          host memory (64 B), renders synchronously and copies the 8-bit image back to the host.
+--impl reference : the UNMODIFIED reference CUDA kernels rebuilt headless for sm_100a
+          (oracle/_ref/libptref.so) on the same scene/config; if that library is not on the box the
+          C oracle port on the host cores is timed instead.  Rank 0 only.
+"""
+import argparse
+import json
+import os
+import shutil
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+PASSES_PER_STEP = 8
+METRIC = "path samples/sec (Mspp*px/s), 1080p"
+UNIT = "Msamples/s"
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)), "measured"
+        except Exception:
+            pass
+    return {"hbm_gbs": 6650.0, "sm_max_mhz": 1965.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            time.sleep(0.15)
+            self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+                for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_scene(workload, root):
+    from pathtracerwithcuda_b200 import procedural as pr
+    from oracle import refharness as rh
+    w = pr.make_workload(root, workload)
+    rh.link_backslash_names(root)      # the reference opens '\\'-spelled paths; harmless for us
+    return w
+
+
+def cpu_baseline(w, root, budget_s=15.0):
+    """C oracle (OpenMP port of the same integrator) on a bounded sample of the SAME workload."""
+    from oracle import oracle as orc
+    import pathtracerwithcuda_b200 as ptb
+    host = ptb.Renderer(w["config"], device=-1)
+    host.load_scene(w["scene"], root)
+    S = orc.OracleScene.from_renderer(host)
+    px = S.width * S.height
+    n = min(px, 65536)
+    t0 = time.perf_counter()
+    S.render_pass(1, 0, n)                        # calibrate
+    dt = time.perf_counter() - t0
+    n2 = int(min(px, max(n, n * budget_s / max(dt, 1e-3))))
+    t0 = time.perf_counter()
+    _, seg = S.render_pass(2, 0, n2)
+    dt = time.perf_counter() - t0
+    return {"value": n2 / dt / 1e6, "unit": UNIT, "cores": orc.num_threads(), "kind": "port",
+            "sample": "pixels [0,%d) of pass 2 of workload %s (%dx%d, depth %d): %.1f s, %d ray segments" % (n2, w["name"], S.width, S.height, w["depth"], dt, seg)}
+
+
+def run_reference(args, w, root, rank, world):
+    """Reference arm: unmodified reference kernels (oracle/_ref) on the GPU, else the oracle port."""
+    if rank != 0:
+        return None
+    config = {"workload": w["name"], "resolution": [w["width"], w["height"]], "max_depth": w["depth"], "triangles": w["triangles"],
+              "passes_per_step": PASSES_PER_STEP}
+    ref_lib = os.path.join(ROOT, "oracle", "_ref", "libptref.so")
+    if os.path.exists(ref_lib):
+        from oracle import refharness as rh
+        ref = rh.RefLib(host_only=False)
+        ref.open(root, config_rel=w["config_rel"], scene=w["scene_name"])
+        ref.render(1)
+        ref.lib.ref_prefetch()
+        for _ in range(args.warmup):
+            ref.render(PASSES_PER_STEP)
+        secs = 0.0
+        for _ in range(args.steps):
+            secs += ref.render(PASSES_PER_STEP)       # synchronous: returns after cudaDeviceSynchronize
+        seg, trace_ms = ref.pass_instrumented(ref.lib.ref_pass_counter() + 1)
+        value = w["width"] * w["height"] * PASSES_PER_STEP * args.steps / secs / 1e6
+        line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": secs / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic", "config": dict(config, note="unmodified reference CUDA kernels rebuilt headless for sm_100a, managed memory prefetched"),
+                "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "reference",
+                                 "sample": "%d passes of %s through path_tracer_kernel() on the B200 (the reference has no CPU implementation of this path)" % (PASSES_PER_STEP * args.steps, w["name"])},
+                "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "reference_extra": {"ray_segments_per_pass": seg, "trace_ray_kernel_ms_per_pass": trace_ms, "Mrays_s_trace_kernel": seg / trace_ms / 1e3 if trace_ms else None}}
+        ref.close()
+        return line
+    cb = cpu_baseline(w, root, budget_s=20.0)
+    cb["kind"] = "port"
+    return {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": None, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": dict(config, note="oracle/_ref not on this box: C oracle port on the host cores"), "cpu_baseline": cb,
+            "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ptb200")
+    ap.add_argument("--workload", default="c2")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl != "reference" else max(args.warmup, 1)
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference" and rank != 0:
+        return 0
+    root = tempfile.mkdtemp(prefix="ptb_bench_%d_" % rank)
+    try:
+        w = make_scene(args.workload, root)
+        if args.impl == "reference":
+            print(json.dumps(run_reference(args, w, root, rank, world)))
+            return 0
+        return run_ptb200(args, w, root, rank, local_rank, world)
+    finally:
+        shutil.rmtree(root, ignore_errors=True)
+
+
+def run_ptb200(args, w, root, rank, local_rank, world):
+    import torch
+    import pathtracerwithcuda_b200 as ptb
+    from pathtracerwithcuda_b200.distributed import CudaBackend, ShardedRenderer
+
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    if ptb.device_count() == 0:
+        raise SystemExit("bench.py: no CUDA device — the ptb200 path has no CPU fallback")
+
+    r = ptb.Renderer(w["config"], device=local_rank)
+    r.set_option("passes_in_flight", PASSES_PER_STEP)
+    t0 = time.perf_counter()
+    r.load_scene(w["scene"], root)
+    load_s = time.perf_counter() - t0
+    if w["aperture"] >= 0 or w["focal"] >= 0:
+        r.set_camera(ptb.default_camera(w["width"], w["height"], w["aperture"], w["focal"]))
+    sr = ShardedRenderer(CudaBackend(r), rank, world, dist)
+    px = w["width"] * w["height"]
+    stream = torch.cuda.ExternalStream(r.stream(), device=torch.device("cuda", local_rank))
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- instrumented pass outside the timed region: mean nodes visited / triangles tested per segment
+    r.set_option("count_traversal", 1)
+    r.clear()
+    r.render_strided(rank + 1, world, PASSES_PER_STEP)
+    st = r.stats()
+    nodes_per_seg = st["nodes_visited"] / max(st["ray_segments"], 1)
+    tris_per_seg = st["tris_tested"] / max(st["ray_segments"], 1)
+    r.set_option("count_traversal", 0)
+
+    # ---- warm-up
+    sr.begin()
+    for _ in range(args.warmup):
+        sr.render_local(PASSES_PER_STEP)
+    sr.begin()
+
+    # ---- timed region: K steps, device-timed on the render stream, extend launches timed live
+    r.set_option("profile_stages", 1)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    segments = launches = 0
+    extend_ms = 0.0
+    for _ in range(args.steps):
+        sr.render_local(PASSES_PER_STEP)
+        s = r.stats()
+        segments += s["ray_segments"]; launches += s["kernel_launches"]; extend_ms += s["gpu_ms_extend"]
+    total_passes = sr.reduce()                      # one sum-reduce per image (no-op at N=1) + tonemap on rank 0
+    e1.record(stream)
+    barrier()
+    clocks = sampler.stop()
+    ms = e0.elapsed_time(e1)
+    r.set_option("profile_stages", 0)
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    seg_t = torch.tensor([float(segments), float(launches), extend_ms], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(seg_t, op=dist.ReduceOp.SUM)
+    ms_max = float(t.item())
+    value = px * PASSES_PER_STEP * args.steps * world / (ms_max / 1e3) / 1e6
+
+    # ---- e2e through the C ABI with host buffers (camera in, 8-bit image out), wall clock incl. copies
+    cam = r.camera()
+    u8 = np.zeros((w["height"], w["width"], 3), np.uint8)
+    sr.begin()
+    sr.render_local(PASSES_PER_STEP)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        r.set_camera(cam)                            # 64 B of host memory -> kernel parameters
+        sr.render_local(PASSES_PER_STEP)             # synchronous C-ABI call
+        r.image_u8(u8)                               # D2H of the displayed image (the reference's per-frame cudaMemcpy)
+    sr.reduce()
+    r.image_f32()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    te = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = px * PASSES_PER_STEP * args.steps * world / float(te.item()) / 1e6
+
+    if rank == 0:
+        peaks, peak_kind = measured_peaks()
+        seg_total, launches_total, extend_total = [float(x) for x in seg_t.tolist()]
+        n_extend = args.steps * w["depth"] * world       # one batch per step => `depth` extend launches per step per rank
+        # algorithmic bytes of the extend (closest-hit) kernel per ray segment, SURVEY.md §8d:
+        # queue id 4 + ray o,d 32 + nodes*64 + tris*48 + hit record 16
+        bytes_per_seg = 4 + 32 + nodes_per_seg * 64.0 + tris_per_seg * 48.0 + 16
+        seg_per_launch = seg_total / max(n_extend, 1)
+        avg_launch_ms = extend_total / max(n_extend, 1)
+        achieved = seg_per_launch * bytes_per_seg / (avg_launch_ms / 1e3) / 1e9 if avg_launch_ms > 0 else None
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic",
+                "config": {"workload": w["name"], "resolution": [w["width"], w["height"]], "max_depth": w["depth"], "triangles": w["triangles"],
+                           "passes_per_step": PASSES_PER_STEP, "passes_in_flight": PASSES_PER_STEP, "parallelism": "spp-sharded x%d" % world,
+                           "l2": "path state per step %.0f MB > L2 (126 MB); no explicit flush" % (px * PASSES_PER_STEP * 84 / 1e6),
+                           "scene_load_s": load_s},
+                "clocks": clocks, "gpu_launches": int(launches_total),
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 64, "d2h_bytes_per_step": int(u8.nbytes)},
+                "roofline": {"bound": "hbm", "kernel": "k_extend", "achieved": achieved, "peak": peaks.get("hbm_gbs"), "unit": "GB/s",
+                             "frac": (achieved / peaks["hbm_gbs"]) if achieved else None, "traffic": None, "peak_source": peak_kind,
+                             "bytes_per_segment": bytes_per_seg, "nodes_per_segment": nodes_per_seg, "tris_per_segment": tris_per_seg,
+                             "segments_per_launch": seg_per_launch, "avg_launch_ms": avg_launch_ms,
+                             "extend_share_of_step": extend_total / world / ms_max if ms_max else None,
+                             "Mrays_s_extend_per_gpu": seg_total / (extend_total / 1e3) / 1e6 if extend_total else None},
+                "ray_segments": int(seg_total), "total_passes": int(total_passes)}
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(w, root)
+        print(json.dumps(line))
+    r.close()
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

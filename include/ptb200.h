@@ -146,6 +146,11 @@ int ptb_trace_batch_bruteforce(ptb_renderer* r, const float* rays6, int n, int32
 /* rays the camera stage generates for pass `pass` (Kernel/path_tracer_kernel.cu:299-379): n = w*h x 6 floats */
 int ptb_generate_rays(ptb_renderer* r, int pass, float* out_rays6);
 
+/* Test hook: the live ray batch entering `depth` of pass `pass` (pixel ids ascending + 6 floats
+ * each) — what the reference holds in rays_device[energy_exist_pixels[i]] at that point of
+ * Kernel/path_tracer_kernel.cu:738-768.  Does not touch the image. Returns the count or -1. */
+int ptb_capture_rays(ptb_renderer* r, int pass, int depth, int32_t* out_pixels, float* out_rays6, int max_out);
+
 int ptb_get_stats(ptb_renderer* r, ptb_stats* out);
 /* string options: "bvh_builder" = "gpu_lbvh" | "host_sah"; "passes_in_flight" = "1".."64";
  * "profile_stages" = "0"|"1"; "count_traversal" = "0"|"1"; "sort_by_material" = "0"|"1". */
@@ -162,16 +167,6 @@ int ptb_scene_texture(ptb_renderer* r, int index, int* width, int* height, uint8
 int ptb_scene_cubemap_face(ptb_renderer* r, int face, uint8_t* out_rgba);
 /* the parsed configuration as the reference's 96-byte `configuration` (Core/configuration.h:9-34) */
 int ptb_get_config(ptb_renderer* r, void* out96);
-
-/* ---- reference-signature compatibility entry (Core/path_tracer_kernel.h:18-54) -----------
- * Declared with opaque pointers; the layouts are the reference's.  All
- * scene pointers may be managed or device memory; render_camera is a host pointer. */
-void ptb_path_tracer_kernel(
-	int mesh_num, void** bvh_nodes_device, void* triangles_device, int triangle_num,
-	int sphere_num, void* spheres_device, int pixel_count,
-	float* image_pixels, uint8_t* image_pixels_256, int pass_counter,
-	const ptb_camera* render_camera, void* sky_cube_map_device,
-	void* mesh_textures_device, int texture_num, void* config_device);
 
 #ifdef __cplusplus
 }

@@ -101,6 +101,7 @@ def load_library():
     L.ptb_trace_batch.argtypes = [vp, vp, ci, vp, vp, vp]
     L.ptb_trace_batch_bruteforce.argtypes = [vp, vp, ci, vp, vp]
     L.ptb_generate_rays.argtypes = [vp, ci, vp]
+    L.ptb_capture_rays.argtypes = [vp, ci, ci, vp, vp, ci]
     L.ptb_get_stats.argtypes = [vp, ctypes.POINTER(Stats)]
     L.ptb_set_option.argtypes = [vp, cp, cp]
     L.ptb_scene_counts.argtypes = [vp] + [ctypes.POINTER(ci)] * 6
@@ -286,6 +287,15 @@ class Renderer:
         out = np.zeros((self.width * self.height, 6), np.float32)
         self._check(self.lib.ptb_generate_rays(self.handle, int(pass_index), _ptr(out)))
         return out
+
+    def capture_rays(self, pass_index, depth):
+        n_max = self.width * self.height
+        pix = np.zeros(n_max, np.int32)
+        rays = np.zeros((n_max, 6), np.float32)
+        n = self.lib.ptb_capture_rays(self.handle, int(pass_index), int(depth), _ptr(pix), _ptr(rays), n_max)
+        if n < 0:
+            raise PtbError(last_error())
+        return pix[:n].copy(), rays[:n].copy()
 
     def stats(self):
         s = Stats()

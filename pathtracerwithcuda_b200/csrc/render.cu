@@ -1068,6 +1068,43 @@ int ptb_generate_rays(ptb_renderer* r, int pass, float* out_rays6)
 	return 0;
 }
 
+int ptb_capture_rays(ptb_renderer* r, int pass, int depth, int32_t* out_pixels, float* out_rays6, int max_out)
+{
+	if (!r || r->host_only) { set_error("[Error]no CUDA device"); return -1; }
+	if (!r->scene_loaded) { set_error("[Error]no scene loaded"); return -1; }
+	const int px = r->pixel_count;
+	DeviceConfig dc = device_config(r);
+	k_generate<<<grid_for(r, px, 256, 8), 256, 0, r->stream>>>(r->st, r->queue[0], r->counts, r->cfg.max_tracer_depth + 2, camera_params(r->cam), dc, px, 1, pass, 1);
+	int d = 0;
+	for (; d < depth && d < r->cfg.max_tracer_depth; d++)
+	{
+		k_extend<false><<<grid_for(r, px, 128, 16), 128, 0, r->stream>>>(r->dscene, r->st, r->queue[d & 1], r->counts + d, r->counters);
+		k_shade<<<grid_for(r, px, 128, 16), 128, 0, r->stream>>>(r->dscene, r->st, dc, d, px, pass, 1, r->queue[d & 1], r->counts + d, r->queue[(d + 1) & 1], r->counts + d + 1);
+	}
+	int count = 0;
+	if (cudaMemcpyAsync(&count, r->counts + d, sizeof(int), cudaMemcpyDeviceToHost, r->stream) != cudaSuccess || cudaStreamSynchronize(r->stream) != cudaSuccess)
+	{
+		set_error(std::string("[Cuda]") + cudaGetErrorString(cudaGetLastError()));
+		return -1;
+	}
+	std::vector<int> q(count);
+	std::vector<float4> o(px), dd(px);
+	cudaMemcpy(q.data(), r->queue[d & 1], (size_t)count * sizeof(int), cudaMemcpyDeviceToHost);
+	cudaMemcpy(o.data(), r->st.ray_o, (size_t)px * sizeof(float4), cudaMemcpyDeviceToHost);
+	cudaMemcpy(dd.data(), r->st.ray_d, (size_t)px * sizeof(float4), cudaMemcpyDeviceToHost);
+	// the wavefront's queue order is not the reference's stable order: report sorted by pixel
+	std::sort(q.begin(), q.end());
+	int n = std::min(count, max_out);
+	for (int i = 0; i < n; i++)
+	{
+		int id = q[i];
+		out_pixels[i] = id;
+		out_rays6[i * 6 + 0] = o[id].x; out_rays6[i * 6 + 1] = o[id].y; out_rays6[i * 6 + 2] = o[id].z;
+		out_rays6[i * 6 + 3] = dd[id].x; out_rays6[i * 6 + 4] = dd[id].y; out_rays6[i * 6 + 5] = dd[id].z;
+	}
+	return n;
+}
+
 int ptb_get_stats(ptb_renderer* r, ptb_stats* out) { if (!r || !out) return 1; *out = r->stats; return 0; }
 
 int ptb_set_option(ptb_renderer* r, const char* key, const char* value)
