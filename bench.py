@@ -125,12 +125,19 @@ def run_reference(args, w, root, rank, world):
         ref = rh.RefLib(host_only=False)
         ref.open(root, config_rel=w["config_rel"], scene=w["scene_name"])
         ref.render(1)
-        ref.lib.ref_prefetch()
+        # (a) as shipped: managed memory, pages migrate on demand (first timing)
+        shipped_s = ref.render(PASSES_PER_STEP)
+        # (b) steady state: everything prefetched to the GPU, config marked read-mostly — the most
+        #     favourable condition for the reference; THIS is the reported value
+        ref.prefetch()
         for _ in range(args.warmup):
             ref.render(PASSES_PER_STEP)
-        secs = 0.0
+        ref.prefetch()
+        secs, step_ms = 0.0, []
         for _ in range(args.steps):
-            secs += ref.render(PASSES_PER_STEP)       # synchronous: returns after cudaDeviceSynchronize
+            dt = ref.render(PASSES_PER_STEP)       # synchronous: returns after cudaDeviceSynchronize
+            secs += dt
+            step_ms.append(dt * 1e3)
         seg, trace_ms = ref.pass_instrumented(ref.lib.ref_pass_counter() + 1)
         value = w["width"] * w["height"] * PASSES_PER_STEP * args.steps / secs / 1e6
         line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
@@ -139,7 +146,8 @@ def run_reference(args, w, root, rank, world):
                 "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "reference",
                                  "sample": "%d passes of %s through path_tracer_kernel() on the B200 (the reference has no CPU implementation of this path)" % (PASSES_PER_STEP * args.steps, w["name"])},
                 "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-                "reference_extra": {"ray_segments_per_pass": seg, "trace_ray_kernel_ms_per_pass": trace_ms, "Mrays_s_trace_kernel": seg / trace_ms / 1e3 if trace_ms else None}}
+                "reference_extra": {"step_ms": step_ms, "as_shipped_unified_memory_Msamples_s": w["width"] * w["height"] * PASSES_PER_STEP / shipped_s / 1e6,
+                                    "ray_segments_per_pass": seg, "trace_ray_kernel_ms_per_pass": trace_ms, "Mrays_s_trace_kernel": seg / trace_ms / 1e3 if trace_ms else None}}
         ref.close()
         return line
     cb = cpu_baseline(w, root, budget_s=20.0)

@@ -244,32 +244,62 @@ long long ref_num_bvh_nodes()
 	return n;
 }
 
-/* move every managed scene/work buffer to the device so timing excludes UM page migration */
-int ref_prefetch()
+/* Move every managed scene / work buffer to the device so timing excludes unified-memory page
+ * migration (second timing).  The reference reads *config_device on the HOST every
+ * pass (path_tracer_kernel.cu:706), which bounces that page (and its small managed neighbours)
+ * between CPU and GPU; with advise != 0 the harness marks the config read-mostly so both sides
+ * keep a copy — the most favourable steady state for the reference, applied from OUTSIDE its
+ * sources. */
+static void prefetch_one(const void* p, size_t bytes, int dev)
+{
+	if (p && bytes) cudaMemPrefetchAsync(p, bytes, dev, 0);
+}
+
+int ref_prefetch(int advise)
 {
 	int dev = 0; cudaGetDevice(&dev);
-	cudaMemLocation loc; loc.type = cudaMemLocationTypeDevice; loc.id = dev;
-	(void)loc;
 	size_t px = g_image->pixel_count;
 	int ntri = ref_num_triangles();
-	cudaMemPrefetchAsync(g_scene->get_triangles_device_ptr(), (size_t)ntri * sizeof(triangle), dev, 0);
-	cudaMemPrefetchAsync(g_scene->m_triangle_mesh.m_mat_device, (size_t)ref_num_mesh_materials() * sizeof(material), dev, 0);
+	configuration* cfg = g_config->get_config_device_ptr();
+	if (advise) cudaMemAdvise(cfg, sizeof(configuration), cudaMemAdviseSetReadMostly, dev);
+	prefetch_one(cfg, sizeof(configuration), dev);
+	prefetch_one(g_scene->get_triangles_device_ptr(), (size_t)ntri * sizeof(triangle), dev);
+	prefetch_one(g_scene->m_triangle_mesh.m_mat_device, (size_t)ref_num_mesh_materials() * sizeof(material), dev);
+	int nmesh = g_scene->get_mesh_num();
 	bvh_node_device** init = g_scene->m_triangle_mesh.m_mesh_bvh_initial_device;
-	for (int m = 0; m < g_scene->get_mesh_num(); m++)
+	if (nmesh > 0)
 	{
-		int nn = init[m][0].next_node_index;
-		int* idx = nullptr;
-		for (int k = 0; k < nn && idx == nullptr; k++) if (init[m][k].is_leaf) idx = init[m][k].triangle_indices;
-		cudaMemPrefetchAsync(init[m], (size_t)nn * 2 * sizeof(bvh_node_device), dev, 0);
-		(void)idx;
+		std::vector<bvh_node_device*> roots(init, init + nmesh);   /* read the pointer arrays before moving them */
+		for (int m = 0; m < nmesh; m++)
+		{
+			int nn = roots[m][0].next_node_index;
+			int leaves = 0; int* slab = nullptr;
+			for (int k = 0; k < nn; k++) if (roots[m][k].is_leaf) { if (!slab) slab = roots[m][k].triangle_indices; leaves++; }
+			prefetch_one(slab, (size_t)leaves * cfg->bvh_leaf_node_triangle_num * sizeof(int), dev);
+			prefetch_one(roots[m], (size_t)nn * 2 * sizeof(bvh_node_device), dev);
+		}
+		prefetch_one(init, nmesh * sizeof(bvh_node_device*), dev);
+		prefetch_one(g_scene->m_triangle_mesh.m_mesh_bvh_transformed_device, nmesh * sizeof(bvh_node_device*), dev);
 	}
-	cudaMemPrefetchAsync(g_not_absorbed, px * sizeof(color), dev, 0);
-	cudaMemPrefetchAsync(g_accumulated, px * sizeof(color), dev, 0);
-	cudaMemPrefetchAsync(g_rays, px * sizeof(ray), dev, 0);
-	cudaMemPrefetchAsync(g_energy_exist, px * sizeof(int), dev, 0);
-	cudaMemPrefetchAsync(g_scatterings, px * sizeof(scattering), dev, 0);
-	cudaMemPrefetchAsync(g_image->pixels_device, px * sizeof(color), dev, 0);
-	cudaMemPrefetchAsync(g_image->pixels_256_device, px * sizeof(color256), dev, 0);
+	prefetch_one(g_scene->get_sphere_device_ptr(), (size_t)ref_num_spheres() * sizeof(sphere), dev);
+	texture_wrapper* tex = g_scene->get_mesh_texture_device_ptr();
+	for (int i = 0; i < g_scene->m_textures_num; i++) prefetch_one(tex[i].pixels, (size_t)tex[i].width * tex[i].height * 4, dev);
+	prefetch_one(tex, (size_t)g_scene->m_textures_num * sizeof(texture_wrapper), dev);
+	cube_map* cm = g_scene->get_cube_map_device_ptr();
+	if (cm)
+	{
+		size_t face = (size_t)cm->length * cm->length * 4;
+		uchar* faces[6] = { cm->m_x_positive_map, cm->m_x_negative_map, cm->m_y_positive_map, cm->m_y_negative_map, cm->m_z_positive_map, cm->m_z_negative_map };
+		for (int f = 0; f < 6; f++) prefetch_one(faces[f], face, dev);
+		prefetch_one(cm, sizeof(cube_map), dev);
+	}
+	prefetch_one(g_not_absorbed, px * sizeof(color), dev);
+	prefetch_one(g_accumulated, px * sizeof(color), dev);
+	prefetch_one(g_rays, px * sizeof(ray), dev);
+	prefetch_one(g_energy_exist, px * sizeof(int), dev);
+	prefetch_one(g_scatterings, px * sizeof(scattering), dev);
+	prefetch_one(g_image->pixels_device, px * sizeof(color), dev);
+	prefetch_one(g_image->pixels_256_device, px * sizeof(color256), dev);
 	return cudaDeviceSynchronize() != cudaSuccess;
 }
 

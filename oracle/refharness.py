@@ -166,6 +166,10 @@ class RefLib:
     def render(self, n):
         return self.lib.ref_render(int(n))
 
+    def prefetch(self, advise=True):
+        """Moves all managed buffers to the GPU (and marks the config read-mostly): steady-state timing."""
+        return self.lib.ref_prefetch(1 if advise else 0)
+
     def clear(self):
         self.lib.ref_clear()
 

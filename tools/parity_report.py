@@ -132,7 +132,7 @@ def run(scene, width, height, depth, spp, root=None, config_extra=None, camera=N
     if time_passes > 0:
         ref.clear(); mine.clear()
         ref.render(1); mine.render(1)  # warm-up
-        ref.lib.ref_prefetch()
+        ref.prefetch()
         t_ref = ref.render(time_passes)
         t0 = time.time()
         mine.render(time_passes)
