@@ -52,4 +52,26 @@ struct GpuBvh2
 
 void flatten_bvh2(const Bvh2& bvh, const std::vector<Triangle>& tris, GpuBvh2& out);
 
+// GPU layout #2 (default): compressed 8-wide BVH, 80-byte nodes = 5 x 16-byte loads, after
+// Ylitie, Karras & Laine 2017.  Child boxes are quantised to 8 bits per plane on a per-node grid
+// (origin p, per-axis power-of-two cell 2^e), rounded OUTWARDS, so the node array is ~1/4 the size
+// of the binary layout and far more of it stays in L1/L2.
+//   n[0] = p.x, p.y, p.z, {e.x, e.y, e.z, imask}                       imask bit s: slot s is an inner node
+//   n[1] = child_base (u32), tri_base (u32), meta[0..3], meta[4..7]     meta: inner 0b001xxxxx (x = 24 + slot),
+//                                                                              leaf  (unary count) << 5 | first tri offset
+//   n[2] = qlo.x[0..3], qlo.x[4..7], qhi.x[0..3], qhi.x[4..7]
+//   n[3] = same for y        n[4] = same for z
+// Inner children of a node are stored contiguously from child_base in slot order; the triangles of
+// its leaf children contiguously from tri_base (<= 24 per node, <= 3 per leaf slot).  Slots are
+// assigned so that visiting set bits of (hit mask) from the top, after XOR with the ray octant,
+// walks the children front to back.
+struct GpuBvh8
+{
+	std::vector<uint32_t> nodes; // 20 words per node
+	std::vector<float> tris;     // 12 floats per triangle: v0.xyz,id | e1.xyz,0 | e2.xyz,0
+	int max_depth = 0;
+};
+
+void build_bvh8(const Bvh2& bvh, const std::vector<Triangle>& tris, GpuBvh8& out);
+
 } // namespace ptb

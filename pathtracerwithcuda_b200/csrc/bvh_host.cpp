@@ -278,3 +278,213 @@ void flatten_bvh2(const Bvh2& bvh, const std::vector<Triangle>& tris, GpuBvh2& o
 }
 
 } // namespace ptb
+
+// ==========================================================================================
+// 8-wide compressed BVH
+// ==========================================================================================
+namespace ptb
+{
+
+namespace
+{
+
+struct WideChild
+{
+	int node2;      // index into Bvh2::nodes
+};
+
+struct WideBuilder
+{
+	const Bvh2& bvh;
+	const std::vector<Triangle>& tris;
+	GpuBvh8& out;
+	int max_depth = 0;
+
+	WideBuilder(const Bvh2& b, const std::vector<Triangle>& t, GpuBvh8& o) : bvh(b), tris(t), out(o) {}
+
+	// open the inner child with the largest surface area until 8 children (or only leaves remain)
+	void gather_children(int node2, std::vector<int>& children) const
+	{
+		children.clear();
+		const Bvh2Node& n = bvh.nodes[node2];
+		children.push_back(n.left);
+		children.push_back(n.right);
+		while (children.size() < 8)
+		{
+			int best = -1;
+			float best_area = -1.0f;
+			for (size_t i = 0; i < children.size(); i++)
+			{
+				const Bvh2Node& c = bvh.nodes[children[i]];
+				if (c.count > 0) continue;
+				float a = half_area(c.box);
+				if (a > best_area) { best_area = a; best = (int)i; }
+			}
+			if (best < 0) break;
+			int open = children[best];
+			children[best] = bvh.nodes[open].left;
+			children.push_back(bvh.nodes[open].right);
+		}
+	}
+
+	// greedy assignment of children to octant slots: slot s prefers the child lying furthest along
+	// (s&4 ? +x : -x, s&2 ? +y : -y, s&1 ? +z : -z) from the node centre
+	void assign_slots(const Aabb& parent, const std::vector<int>& children, int slot_child[8]) const
+	{
+		float pc[3];
+		for (int a = 0; a < 3; a++) pc[a] = 0.5f * (parent.lo[a] + parent.hi[a]);
+		float cost[8][8];
+		const int n = (int)children.size();
+		for (int c = 0; c < n; c++)
+		{
+			const Aabb& b = bvh.nodes[children[c]].box;
+			float d[3];
+			for (int a = 0; a < 3; a++) d[a] = 0.5f * (b.lo[a] + b.hi[a]) - pc[a];
+			for (int s = 0; s < 8; s++)
+				cost[c][s] = ((s & 4) ? d[0] : -d[0]) + ((s & 2) ? d[1] : -d[1]) + ((s & 1) ? d[2] : -d[2]);
+		}
+		bool child_done[8] = { false }, slot_done[8] = { false };
+		for (int s = 0; s < 8; s++) slot_child[s] = -1;
+		for (int k = 0; k < n; k++)
+		{
+			int bc = -1, bs = -1;
+			float best = -std::numeric_limits<float>::infinity();
+			for (int c = 0; c < n; c++)
+			{
+				if (child_done[c]) continue;
+				for (int s = 0; s < 8; s++)
+				{
+					if (slot_done[s]) continue;
+					if (cost[c][s] > best) { best = cost[c][s]; bc = c; bs = s; }
+				}
+			}
+			child_done[bc] = true; slot_done[bs] = true;
+			slot_child[bs] = children[bc];
+		}
+	}
+
+	void emit_triangle(int prim)
+	{
+		const Triangle& t = tris[prim];
+		size_t o = out.tris.size();
+		out.tris.resize(o + 12);
+		float* d = &out.tris[o];
+		d[0] = t.v0.x; d[1] = t.v0.y; d[2] = t.v0.z;
+		memcpy(&d[3], &prim, 4);
+		d[4] = t.v1.x - t.v0.x; d[5] = t.v1.y - t.v0.y; d[6] = t.v1.z - t.v0.z; d[7] = 0.0f;
+		d[8] = t.v2.x - t.v0.x; d[9] = t.v2.y - t.v0.y; d[10] = t.v2.z - t.v0.z; d[11] = 0.0f;
+	}
+
+	void build()
+	{
+		out.nodes.clear();
+		out.tris.clear();
+		out.tris.reserve(bvh.prim_order.size() * 12);
+		if (bvh.nodes.empty()) return;
+
+		struct Item { int node2; int index; int depth; bool root_leaf; };
+		std::vector<Item> queue;
+		out.nodes.resize(20, 0u);
+		queue.push_back({ 0, 0, 1, bvh.nodes[0].count > 0 });
+		std::vector<int> children;
+		size_t head = 0;
+		while (head < queue.size())
+		{
+			Item it = queue[head++];
+			max_depth = std::max(max_depth, it.depth);
+			const Aabb& box = bvh.nodes[it.node2].box;
+			int slot_child[8];
+			if (it.root_leaf)
+			{
+				for (int s = 0; s < 8; s++) slot_child[s] = -1;
+				slot_child[0] = it.node2;
+			}
+			else
+			{
+				gather_children(it.node2, children);
+				assign_slots(box, children, slot_child);
+			}
+
+			// quantisation grid of this node (boxes are padded outwards before quantising)
+			float p[3], scale[3];
+			uint32_t e[3];
+			for (int a = 0; a < 3; a++)
+			{
+				p[a] = pad_down(box.lo[a]);
+				float extent = pad_up(box.hi[a]) - p[a];
+				int ex = (int)std::ceil(std::log2(std::max(extent, 1e-30f) / 255.0f));
+				// make sure 255 cells really cover the extent after rounding
+				while (std::ldexp(255.0f, ex) < extent) ex++;
+				ex = std::max(-126, std::min(127, ex));
+				e[a] = (uint32_t)(ex + 127);
+				scale[a] = std::ldexp(1.0f, -ex);
+			}
+
+			uint32_t imask = 0;
+			int n_inner = 0;
+			for (int s = 0; s < 8; s++)
+				if (slot_child[s] >= 0 && bvh.nodes[slot_child[s]].count == 0) { imask |= 1u << s; n_inner++; }
+			uint32_t child_base = (uint32_t)(out.nodes.size() / 20);
+			out.nodes.resize(out.nodes.size() + (size_t)n_inner * 20, 0u);
+			uint32_t tri_base = (uint32_t)(out.tris.size() / 12);
+
+			uint8_t meta[8], qlo[3][8], qhi[3][8];
+			int inner_rank = 0, tri_offset = 0;
+			for (int s = 0; s < 8; s++)
+			{
+				meta[s] = 0;
+				for (int a = 0; a < 3; a++) { qlo[a][s] = 0; qhi[a][s] = 0; }
+				int c = slot_child[s];
+				if (c < 0) continue;
+				const Bvh2Node& cn = bvh.nodes[c];
+				for (int a = 0; a < 3; a++)
+				{
+					float lo = std::floor((pad_down(cn.box.lo[a]) - p[a]) * scale[a]);
+					float hi = std::ceil((pad_up(cn.box.hi[a]) - p[a]) * scale[a]);
+					qlo[a][s] = (uint8_t)std::max(0.0f, std::min(255.0f, lo));
+					qhi[a][s] = (uint8_t)std::max(0.0f, std::min(255.0f, hi));
+				}
+				if (cn.count == 0)
+				{
+					meta[s] = (uint8_t)((1u << 5) | (24u + (uint32_t)s));
+					queue.push_back({ c, (int)child_base + inner_rank, it.depth + 1, false });
+					inner_rank++;
+				}
+				else
+				{
+					int count = std::min(cn.count, 3);
+					uint32_t unary = count == 1 ? 1u : (count == 2 ? 3u : 7u);
+					meta[s] = (uint8_t)((unary << 5) | (uint32_t)tri_offset);
+					for (int k = 0; k < count; k++) emit_triangle(bvh.prim_order[cn.first + k]);
+					tri_offset += count;
+				}
+			}
+
+			uint32_t* d = &out.nodes[(size_t)it.index * 20];
+			memcpy(&d[0], &p[0], 4); memcpy(&d[1], &p[1], 4); memcpy(&d[2], &p[2], 4);
+			d[3] = e[0] | (e[1] << 8) | (e[2] << 16) | (imask << 24);
+			d[4] = child_base;
+			d[5] = tri_base;
+			d[6] = meta[0] | (meta[1] << 8) | (meta[2] << 16) | ((uint32_t)meta[3] << 24);
+			d[7] = meta[4] | (meta[5] << 8) | (meta[6] << 16) | ((uint32_t)meta[7] << 24);
+			for (int a = 0; a < 3; a++)
+			{
+				d[8 + a * 4 + 0] = qlo[a][0] | (qlo[a][1] << 8) | (qlo[a][2] << 16) | ((uint32_t)qlo[a][3] << 24);
+				d[8 + a * 4 + 1] = qlo[a][4] | (qlo[a][5] << 8) | (qlo[a][6] << 16) | ((uint32_t)qlo[a][7] << 24);
+				d[8 + a * 4 + 2] = qhi[a][0] | (qhi[a][1] << 8) | (qhi[a][2] << 16) | ((uint32_t)qhi[a][3] << 24);
+				d[8 + a * 4 + 3] = qhi[a][4] | (qhi[a][5] << 8) | (qhi[a][6] << 16) | ((uint32_t)qhi[a][7] << 24);
+			}
+		}
+		out.max_depth = max_depth;
+	}
+};
+
+} // namespace
+
+void build_bvh8(const Bvh2& bvh, const std::vector<Triangle>& tris, GpuBvh8& out)
+{
+	WideBuilder b(bvh, tris, out);
+	b.build();
+}
+
+} // namespace ptb

@@ -38,7 +38,8 @@ __global__ void __launch_bounds__(256) k_generate(PathState st, int* __restrict_
 {
 	const int total = pixel_count * n_slots;
 	int tid = blockIdx.x * blockDim.x + threadIdx.x;
-	if (tid < n_counts) counts[tid] = tid == 0 ? total : 0;
+	// counts[0..n_counts) = live paths per depth; counts[n_counts..2*n_counts) = per-depth work-fetch cursors of the persistent extend kernel
+	if (tid < 2 * n_counts) counts[tid] = tid == 0 ? total : 0;
 	for (int id = tid; id < total; id += gridDim.x * blockDim.x)
 	{
 		int slot = id / pixel_count;
@@ -60,6 +61,7 @@ __global__ void __launch_bounds__(256) k_generate(PathState st, int* __restrict_
 // the reference's own Moller-Trumbore / sphere arithmetic (pt_device.cuh).
 // ------------------------------------------------------------------------------------------
 #define PTB_STACK_SIZE 64
+#define PTB_STACK_SIZE8 32
 #define PTB_SLACK_LO 0.9999995f
 #define PTB_SLACK_HI 1.0000005f
 
@@ -158,7 +160,133 @@ __device__ __forceinline__ HitRecord closest_hit(const DeviceScene& sc, float3 o
 	}
 }
 
+// ---- compressed 8-wide traversal (layout in bvh.h; after Ylitie, Karras & Laine 2017) ----
+__device__ __forceinline__ unsigned sign_extend_s8x4(unsigned x)
+{
+	unsigned r;
+	asm("prmt.b32 %0, %1, 0x0, 0x0000BA98;" : "=r"(r) : "r"(x));
+	return r;
+}
+
+__device__ __forceinline__ unsigned extract_byte(unsigned x, unsigned i) { return (x >> (i * 8)) & 0xffu; }
+
 template <bool COUNT>
+__device__ __forceinline__ HitRecord closest_hit_bvh8(const DeviceScene& sc, float3 o, float3 d, unsigned& n_nodes, unsigned& n_tris)
+{
+	HitRecord best;
+	best.t = CUDART_INF_F; best.t1 = CUDART_INF_F; best.t2 = CUDART_INF_F; best.prim = -1;
+	for (int s = 0; s < sc.n_spheres; s++)
+	{
+		float4 sp = __ldg(&sc.spheres[s]);
+		float t;
+		if (intersect_sphere(make_float3(sp.x, sp.y, sp.z), sp.w, o, d, t) && t < best.t && t > 0.0f)
+		{
+			best.t = t;
+			best.prim = -(s + 2);
+		}
+	}
+	if (sc.n_triangles == 0) return best;
+
+	// box culling only: keep the reciprocal finite so 0 * inf never appears (the deciding
+	// triangle test below still sees the exact direction)
+	const float tiny = 1e-30f;
+	const float3 ds = make_float3(fabsf(d.x) < tiny ? copysignf(tiny, d.x) : d.x, fabsf(d.y) < tiny ? copysignf(tiny, d.y) : d.y,
+		fabsf(d.z) < tiny ? copysignf(tiny, d.z) : d.z);
+	const float3 idir = make_float3(1.0f / ds.x, 1.0f / ds.y, 1.0f / ds.z);
+	const unsigned oct_inv4 = (d.x < 0.0f ? 0u : 0x04040404u) | (d.y < 0.0f ? 0u : 0x02020202u) | (d.z < 0.0f ? 0u : 0x01010101u);
+
+	uint2 stack[PTB_STACK_SIZE8];
+	int sp = 0;
+	uint2 current = make_uint2(0u, 0x80000000u);
+	int best_tri = 0x7fffffff;
+
+	while (true)
+	{
+		uint2 tri_group;
+		if (current.y & 0xff000000u)
+		{
+			const unsigned hits_imask = current.y;
+			const unsigned child_index_offset = 31u - __clz(hits_imask);
+			const unsigned child_index_base = current.x;
+			current.y &= ~(1u << child_index_offset);
+			if (current.y & 0xff000000u) { if (sp < PTB_STACK_SIZE8) stack[sp++] = current; }
+			const unsigned slot_index = (child_index_offset - 24u) ^ (oct_inv4 & 0xffu);
+			const unsigned relative_index = __popc(hits_imask & ~(0xffffffffu << slot_index));
+			const unsigned node_index = child_index_base + relative_index;
+			if (COUNT) n_nodes++;
+
+			const float4* np = sc.bvh_nodes + (size_t)node_index * 5;
+			const float4 n0 = __ldg(np + 0), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3), n4 = __ldg(np + 4);
+			const unsigned e_imask = __float_as_uint(n0.w);
+			const float3 adir = make_float3(__uint_as_float(extract_byte(e_imask, 0) << 23) * idir.x, __uint_as_float(extract_byte(e_imask, 1) << 23) * idir.y,
+				__uint_as_float(extract_byte(e_imask, 2) << 23) * idir.z);
+			const float3 aorg = make_float3((n0.x - o.x) * idir.x, (n0.y - o.y) * idir.y, (n0.z - o.z) * idir.z);
+
+			unsigned hit_mask = 0;
+#pragma unroll
+			for (int half = 0; half < 2; half++)
+			{
+				const unsigned meta4 = __float_as_uint(half == 0 ? n1.z : n1.w);
+				const unsigned is_inner4 = (meta4 & (meta4 << 1)) & 0x10101010u;
+				const unsigned inner_mask4 = sign_extend_s8x4(is_inner4 << 3);
+				const unsigned bit_index4 = (meta4 ^ (oct_inv4 & inner_mask4)) & 0x1f1f1f1fu;
+				const unsigned child_bits4 = (meta4 >> 5) & 0x07070707u;
+				const unsigned qlox = __float_as_uint(half == 0 ? n2.x : n2.y), qhix = __float_as_uint(half == 0 ? n2.z : n2.w);
+				const unsigned qloy = __float_as_uint(half == 0 ? n3.x : n3.y), qhiy = __float_as_uint(half == 0 ? n3.z : n3.w);
+				const unsigned qloz = __float_as_uint(half == 0 ? n4.x : n4.y), qhiz = __float_as_uint(half == 0 ? n4.z : n4.w);
+				const unsigned x_min = d.x < 0.0f ? qhix : qlox, x_max = d.x < 0.0f ? qlox : qhix;
+				const unsigned y_min = d.y < 0.0f ? qhiy : qloy, y_max = d.y < 0.0f ? qloy : qhiy;
+				const unsigned z_min = d.z < 0.0f ? qhiz : qloz, z_max = d.z < 0.0f ? qloz : qhiz;
+#pragma unroll
+				for (int j = 0; j < 4; j++)
+				{
+					const float tx0 = fmaf((float)extract_byte(x_min, j), adir.x, aorg.x), tx1 = fmaf((float)extract_byte(x_max, j), adir.x, aorg.x);
+					const float ty0 = fmaf((float)extract_byte(y_min, j), adir.y, aorg.y), ty1 = fmaf((float)extract_byte(y_max, j), adir.y, aorg.y);
+					const float tz0 = fmaf((float)extract_byte(z_min, j), adir.z, aorg.z), tz1 = fmaf((float)extract_byte(z_max, j), adir.z, aorg.z);
+					const float tmin = fmaxf(fmaxf(tx0, ty0), fmaxf(tz0, 0.0f));
+					const float tmax = fminf(fminf(tx1, ty1), fminf(tz1, best.t));
+					if (tmin * PTB_SLACK_LO <= tmax * PTB_SLACK_HI)
+						hit_mask |= extract_byte(child_bits4, j) << extract_byte(bit_index4, j);
+				}
+			}
+			current.x = __float_as_uint(n1.x);
+			tri_group.x = __float_as_uint(n1.y);
+			current.y = (hit_mask & 0xff000000u) | (e_imask >> 24);
+			tri_group.y = hit_mask & 0x00ffffffu;
+		}
+		else
+		{
+			tri_group = current;
+			current = make_uint2(0u, 0u);
+		}
+
+		while (tri_group.y)
+		{
+			const unsigned k = 31u - __clz(tri_group.y);
+			tri_group.y &= ~(1u << k);
+			if (COUNT) n_tris++;
+			const float4* tp = sc.tri_isect + (size_t)(tri_group.x + k) * 3;
+			const float4 a = __ldg(tp + 0), b = __ldg(tp + 1), c = __ldg(tp + 2);
+			float t, t1, t2;
+			if (intersect_triangle(make_float3(a.x, a.y, a.z), make_float3(b.x, b.y, b.z), make_float3(c.x, c.y, c.z), o, d, t, t1, t2) && t > 0.0f)
+			{
+				const int id = __float_as_int(a.w);
+				if (t < best.t || (t == best.t && best.prim >= 0 && id < best_tri))
+				{
+					best.t = t; best.t1 = t1; best.t2 = t2; best.prim = id; best_tri = id;
+				}
+			}
+		}
+
+		if ((current.y & 0xff000000u) == 0u)
+		{
+			if (sp == 0) return best;
+			current = stack[--sp];
+		}
+	}
+}
+
+template <bool COUNT, bool WIDE>
 __global__ void __launch_bounds__(128) k_extend(DeviceScene sc, PathState st, const int* __restrict__ queue, const int* __restrict__ count_ptr,
 	unsigned long long* __restrict__ counters)
 {
@@ -168,7 +296,8 @@ __global__ void __launch_bounds__(128) k_extend(DeviceScene sc, PathState st, co
 	{
 		int id = queue[i];
 		float4 o4 = st.ray_o[id], d4 = st.ray_d[id];
-		HitRecord h = closest_hit<COUNT>(sc, make_float3(o4.x, o4.y, o4.z), make_float3(d4.x, d4.y, d4.z), n_nodes, n_tris);
+		HitRecord h = WIDE ? closest_hit_bvh8<COUNT>(sc, make_float3(o4.x, o4.y, o4.z), make_float3(d4.x, d4.y, d4.z), n_nodes, n_tris)
+		                   : closest_hit<COUNT>(sc, make_float3(o4.x, o4.y, o4.z), make_float3(d4.x, d4.y, d4.z), n_nodes, n_tris);
 		st.hit[id] = make_float4(h.t, h.t1, h.t2, __int_as_float(h.prim));
 	}
 	if (COUNT)
@@ -179,6 +308,179 @@ __global__ void __launch_bounds__(128) k_extend(DeviceScene sc, PathState st, co
 			n_tris += __shfl_down_sync(0xffffffffu, n_tris, off);
 		}
 		if ((threadIdx.x & 31) == 0)
+		{
+			atomicAdd(&counters[0], (unsigned long long)n_nodes);
+			atomicAdd(&counters[1], (unsigned long long)n_tris);
+		}
+	}
+}
+
+// ------------------------------------------------------------------------------------------
+// k_extend_persistent — the production closest-hit kernel.
+// ncu on the one-ray-per-thread kernels above showed them ISSUE-bound (65-70% issue slots busy)
+// with only 8-18 of 32 lanes active per instruction: rays of one warp need very different numbers
+// of node visits and the finished lanes idle.  Here warps are persistent: a lane whose ray
+// terminates fetches the next queue entry (one atomicAdd per warp per refill) as soon as fewer than
+// PTB_REFILL_THRESHOLD lanes are still traversing, so the 32 lanes stay populated.
+// Binary tree, both child boxes per 64-byte node; slab distances as one FMA per plane
+// (plane * (1/d) - o/d) with an absolute + relative safety margin so culling stays conservative.
+// ------------------------------------------------------------------------------------------
+#define PTB_DONE ((int)0x80000000)
+#define PTB_REFILL_MIN 8      // refill when at least this many lanes are idle
+#define PTB_LEAF_MIN 10       // run a leaf phase when at least this many lanes wait at a leaf
+
+template <bool COUNT>
+__global__ void __launch_bounds__(128, 4) k_extend_persistent(DeviceScene sc, PathState st, const int* __restrict__ queue, const int* __restrict__ count_ptr,
+	int* __restrict__ work_counter, unsigned long long* __restrict__ counters)
+{
+	const int count = *count_ptr;
+	const unsigned lane = threadIdx.x & 31u;
+	const unsigned lane_lt = (1u << lane) - 1u;
+	const unsigned FULL = 0xffffffffu;
+	unsigned n_nodes = 0, n_tris = 0;
+
+	int id = -1;                 // path id this lane is tracing; -1 = idle
+	bool exhausted = false;      // warp-uniform: the queue has been handed out completely
+	float3 o = make_float3(0, 0, 0), d = o, idir = o, noidir = o;
+	float margin2 = 0.0f;
+	HitRecord best;
+	best.t = CUDART_INF_F; best.t1 = 0.0f; best.t2 = 0.0f; best.prim = -1;
+	int best_tri = 0x7fffffff;
+	int stack[PTB_STACK_SIZE];
+	int sp = 0;
+	int node = PTB_DONE;         // >= 0 inner node, PTB_DONE = nothing left, other negative = leaf reference
+
+	// Every iteration starts with full-mask votes, so all 32 lanes are converged when a phase
+	// begins; a phase is executed by the lanes in that state, the others are predicated off.
+	while (true)
+	{
+		const bool has_ray = id >= 0;
+		const unsigned m_idle = __ballot_sync(FULL, !has_ray);
+		const unsigned m_node = __ballot_sync(FULL, has_ray && node >= 0);
+		const unsigned m_leaf = __ballot_sync(FULL, has_ray && node < 0 && node != PTB_DONE);
+		const unsigned m_done = __ballot_sync(FULL, has_ray && node == PTB_DONE);
+
+		if (m_done != 0u)
+		{
+			// ---- retire finished rays
+			if (has_ray && node == PTB_DONE)
+			{
+				st.hit[id] = make_float4(best.t, best.t1, best.t2, __int_as_float(best.prim));
+				id = -1;
+			}
+			continue;
+		}
+		if (m_idle != 0u && !exhausted && (__popc(m_idle) >= PTB_REFILL_MIN || (m_node | m_leaf) == 0u))
+		{
+			// ---- refill idle lanes from the queue: one atomic per warp
+			const int n = __popc(m_idle);
+			int base = 0;
+			if (lane == 0) base = atomicAdd(work_counter, n);
+			base = __shfl_sync(FULL, base, 0);
+			if (base + n >= count) exhausted = true;
+			if (!has_ray)
+			{
+				const int i = base + __popc(m_idle & lane_lt);
+				if (i < count)
+				{
+					id = queue[i];
+					const float4 o4 = st.ray_o[id], d4 = st.ray_d[id];
+					o = make_float3(o4.x, o4.y, o4.z);
+					d = make_float3(d4.x, d4.y, d4.z);
+					best.t = CUDART_INF_F; best.t1 = CUDART_INF_F; best.t2 = CUDART_INF_F; best.prim = -1;
+					best_tri = 0x7fffffff;
+					for (int s = 0; s < sc.n_spheres; s++)
+					{
+						const float4 sph = __ldg(&sc.spheres[s]);
+						float t;
+						if (intersect_sphere(make_float3(sph.x, sph.y, sph.z), sph.w, o, d, t) && t < best.t && t > 0.0f)
+						{
+							best.t = t;
+							best.prim = -(s + 2);
+						}
+					}
+					// box culling only: finite reciprocal so 0 * inf never appears
+					const float tiny = 1e-30f;
+					const float3 ds = make_float3(fabsf(d.x) < tiny ? copysignf(tiny, d.x) : d.x, fabsf(d.y) < tiny ? copysignf(tiny, d.y) : d.y,
+						fabsf(d.z) < tiny ? copysignf(tiny, d.z) : d.z);
+					idir = make_float3(1.0f / ds.x, 1.0f / ds.y, 1.0f / ds.z);
+					noidir = make_float3(-o.x * idir.x, -o.y * idir.y, -o.z * idir.z);
+					// |error| of fma(plane, idir, -o*idir) <= 2^-23 * (|o*idir| + |t|): absolute part here, relative part in the slack factors
+					margin2 = 4.8e-7f * fmaxf(fmaxf(fabsf(noidir.x), fabsf(noidir.y)), fabsf(noidir.z));
+					sp = 0;
+					node = sc.n_triangles > 0 ? sc.root_ref : PTB_DONE;
+				}
+			}
+			continue;
+		}
+		if ((m_node | m_leaf) == 0u) break;   // nothing in flight and nothing left to fetch
+
+		if (m_leaf != 0u && (__popc(m_leaf) >= PTB_LEAF_MIN || m_node == 0u))
+		{
+			// ---- leaf phase: node = ~((first << 3) | (count - 1))
+			if (has_ray && node < 0 && node != PTB_DONE)
+			{
+				const int ref = ~node;
+				const int first = ref >> 3;
+				const int cnt = (ref & 7) + 1;
+				for (int k = 0; k < cnt; k++)
+				{
+					if (COUNT) n_tris++;
+					const float4* tp = sc.tri_isect + (size_t)(first + k) * 3;
+					const float4 a = __ldg(tp + 0), b = __ldg(tp + 1), c = __ldg(tp + 2);
+					float t, t1, t2;
+					if (intersect_triangle(make_float3(a.x, a.y, a.z), make_float3(b.x, b.y, b.z), make_float3(c.x, c.y, c.z), o, d, t, t1, t2) && t > 0.0f)
+					{
+						const int tid = __float_as_int(a.w);
+						if (t < best.t || (t == best.t && best.prim >= 0 && tid < best_tri))
+						{
+							best.t = t; best.t1 = t1; best.t2 = t2; best.prim = tid; best_tri = tid;
+						}
+					}
+				}
+				node = sp > 0 ? stack[--sp] : PTB_DONE;
+			}
+			continue;
+		}
+
+		// ---- node phase (one step for every lane sitting at an inner node)
+		if (has_ray && node >= 0)
+		{
+			if (COUNT) n_nodes++;
+			const float4* np = sc.bvh_nodes + (size_t)node * 4;
+			const float4 n0 = __ldg(np + 0), n1 = __ldg(np + 1), n2 = __ldg(np + 2);
+			const float2 n3 = __ldg(reinterpret_cast<const float2*>(np + 3));
+			const float c0x0 = fmaf(n0.x, idir.x, noidir.x), c0x1 = fmaf(n0.y, idir.x, noidir.x);
+			const float c0y0 = fmaf(n0.z, idir.y, noidir.y), c0y1 = fmaf(n0.w, idir.y, noidir.y);
+			const float c0z0 = fmaf(n2.x, idir.z, noidir.z), c0z1 = fmaf(n2.y, idir.z, noidir.z);
+			const float c1x0 = fmaf(n1.x, idir.x, noidir.x), c1x1 = fmaf(n1.y, idir.x, noidir.x);
+			const float c1y0 = fmaf(n1.z, idir.y, noidir.y), c1y1 = fmaf(n1.w, idir.y, noidir.y);
+			const float c1z0 = fmaf(n2.z, idir.z, noidir.z), c1z1 = fmaf(n2.w, idir.z, noidir.z);
+			const float tmin0 = fmaxf(fmaxf(fminf(c0x0, c0x1), fminf(c0y0, c0y1)), fmaxf(fminf(c0z0, c0z1), 0.0f));
+			const float tmax0 = fminf(fminf(fmaxf(c0x0, c0x1), fmaxf(c0y0, c0y1)), fminf(fmaxf(c0z0, c0z1), best.t));
+			const float tmin1 = fmaxf(fmaxf(fminf(c1x0, c1x1), fminf(c1y0, c1y1)), fmaxf(fminf(c1z0, c1z1), 0.0f));
+			const float tmax1 = fminf(fminf(fmaxf(c1x0, c1x1), fmaxf(c1y0, c1y1)), fminf(fmaxf(c1z0, c1z1), best.t));
+			const bool h0 = fmaf(tmin0, PTB_SLACK_LO, -margin2) <= tmax0 * PTB_SLACK_HI;
+			const bool h1 = fmaf(tmin1, PTB_SLACK_LO, -margin2) <= tmax1 * PTB_SLACK_HI;
+			const int child0 = __float_as_int(n3.x), child1 = __float_as_int(n3.y);
+			const bool both = h0 && h1;
+			const bool swap = tmin1 < tmin0;
+			const int near_c = swap ? child1 : child0;
+			const int far_c = swap ? child0 : child1;
+			int next = both ? near_c : (h0 ? child0 : (h1 ? child1 : PTB_DONE));
+			if (both) stack[sp++] = far_c;
+			else if (!(h0 || h1) && sp > 0) next = stack[--sp];
+			node = next;
+		}
+	}
+	if (COUNT)
+	{
+		for (int off = 16; off > 0; off >>= 1)
+		{
+			n_nodes += __shfl_down_sync(FULL, n_nodes, off);
+			n_tris += __shfl_down_sync(FULL, n_tris, off);
+		}
+		if (lane == 0)
 		{
 			atomicAdd(&counters[0], (unsigned long long)n_nodes);
 			atomicAdd(&counters[1], (unsigned long long)n_tris);
@@ -497,6 +799,9 @@ struct ptb_renderer
 	int profile_stages = 0;
 	int count_traversal = 0;
 	std::string bvh_builder = "host_sah";
+	int bvh_layout = 2;
+	int extend_persistent = 1;
+	int persistent_grid = 148 * 4;
 
 	cudaStream_t stream = nullptr;
 	int sm_count = 148;
@@ -538,7 +843,7 @@ int alloc_work_buffers(ptb_renderer* r)
 	PTB_CUDA(cudaMalloc(&r->queue[0], r->capacity * sizeof(int)));
 	PTB_CUDA(cudaMalloc(&r->queue[1], r->capacity * sizeof(int)));
 	int n_counts = r->cfg.max_tracer_depth + 2;
-	PTB_CUDA(cudaMalloc(&r->counts, n_counts * sizeof(int)));
+	PTB_CUDA(cudaMalloc(&r->counts, 2 * n_counts * sizeof(int)));
 	PTB_CUDA(cudaMallocHost(&r->counts_host, n_counts * sizeof(int)));
 	PTB_CUDA(cudaMalloc(&r->counters, 2 * sizeof(unsigned long long)));
 	PTB_CUDA(cudaMalloc(&r->image_sum, (size_t)r->pixel_count * 3 * sizeof(float)));
@@ -606,15 +911,30 @@ int upload_scene(ptb_renderer* r)
 
 	// acceleration structure over all meshes' world-space triangles
 	Bvh2 bvh;
-	build_bvh2_sah(s.triangles, 4, bvh);
-	GpuBvh2 flat;
-	flatten_bvh2(bvh, s.triangles, flat);
-	if (upload(r, (const float4*)flat.nodes.data(), flat.nodes.size() / 4, &ds.bvh_nodes)) return 1;
-	if (upload(r, (const float4*)flat.tris.data(), flat.tris.size() / 4, &ds.tri_isect)) return 1;
+	if (r->bvh_layout == 8)
+	{
+		build_bvh2_sah(s.triangles, 3, bvh);   // <= 3 triangles per leaf slot of a wide node
+		GpuBvh8 wide;
+		build_bvh8(bvh, s.triangles, wide);
+		if (wide.max_depth > PTB_STACK_SIZE8) { set_error("[Error]BVH8 too deep for the traversal stack"); return 1; }
+		if (upload(r, (const float4*)wide.nodes.data(), wide.nodes.size() / 4, &ds.bvh_nodes)) return 1;
+		if (upload(r, (const float4*)wide.tris.data(), wide.tris.size() / 4, &ds.tri_isect)) return 1;
+		r->bvh_nodes = (int64_t)wide.nodes.size() / 20;
+		r->bvh_bytes = (int64_t)(wide.nodes.size() + wide.tris.size()) * 4;
+	}
+	else
+	{
+		build_bvh2_sah(s.triangles, 4, bvh);
+		GpuBvh2 flat;
+		flatten_bvh2(bvh, s.triangles, flat);
+		if (upload(r, (const float4*)flat.nodes.data(), flat.nodes.size() / 4, &ds.bvh_nodes)) return 1;
+		if (upload(r, (const float4*)flat.tris.data(), flat.tris.size() / 4, &ds.tri_isect)) return 1;
+		r->bvh_nodes = (int64_t)flat.nodes.size() / 16;
+		r->bvh_bytes = (int64_t)(flat.nodes.size() + flat.tris.size()) * 4;
+	}
+	ds.bvh_layout = r->bvh_layout;
 	ds.n_triangles = (int)s.triangles.size();
 	ds.root_ref = 0;
-	r->bvh_nodes = (int64_t)flat.nodes.size() / 16;
-	r->bvh_bytes = (int64_t)(flat.nodes.size() + flat.tris.size()) * 4;
 
 	// shading attributes by global triangle id
 	std::vector<float> shade((size_t)s.triangles.size() * 16);
@@ -700,6 +1020,30 @@ int grid_for(const ptb_renderer* r, size_t items, int block, int blocks_per_sm)
 	return (int)std::max<size_t>(1, std::min(need, cap));
 }
 
+void launch_extend(ptb_renderer* r, size_t items, const PathState& st, const int* queue, const int* count_ptr, int* work_counter)
+{
+	bool wide = r->dscene.bvh_layout == 8;
+	if (!wide && r->extend_persistent)
+	{
+		// persistent warps: one resident wave, sized from the occupancy the kernel actually gets
+		int grid = std::max(1, std::min(r->persistent_grid, (int)((items + 127) / 128)));
+		if (r->count_traversal) k_extend_persistent<true><<<grid, 128, 0, r->stream>>>(r->dscene, st, queue, count_ptr, work_counter, r->counters);
+		else k_extend_persistent<false><<<grid, 128, 0, r->stream>>>(r->dscene, st, queue, count_ptr, work_counter, r->counters);
+		return;
+	}
+	int grid = grid_for(r, items, 128, 16);
+	if (r->count_traversal)
+	{
+		if (wide) k_extend<true, true><<<grid, 128, 0, r->stream>>>(r->dscene, st, queue, count_ptr, r->counters);
+		else k_extend<true, false><<<grid, 128, 0, r->stream>>>(r->dscene, st, queue, count_ptr, r->counters);
+	}
+	else
+	{
+		if (wide) k_extend<false, true><<<grid, 128, 0, r->stream>>>(r->dscene, st, queue, count_ptr, r->counters);
+		else k_extend<false, false><<<grid, 128, 0, r->stream>>>(r->dscene, st, queue, count_ptr, r->counters);
+	}
+}
+
 // enqueue one batch of n_slots passes: first, first+stride, ...
 int enqueue_batch(ptb_renderer* r, int first_pass, int stride, int n_slots)
 {
@@ -722,10 +1066,7 @@ int enqueue_batch(ptb_renderer* r, int first_pass, int stride, int n_slots)
 			r->stage_events.push_back(e0); r->stage_events.push_back(e1);
 			cudaEventRecord(e0, r->stream);
 		}
-		if (r->count_traversal)
-			k_extend<true><<<grid_for(r, total, 128, 16), 128, 0, r->stream>>>(r->dscene, r->st, qin, r->counts + depth, r->counters);
-		else
-			k_extend<false><<<grid_for(r, total, 128, 16), 128, 0, r->stream>>>(r->dscene, r->st, qin, r->counts + depth, r->counters);
+		launch_extend(r, total, r->st, qin, r->counts + depth, r->counts + n_counts + depth);
 		if (prof) cudaEventRecord(e1, r->stream);
 		k_shade<<<grid_for(r, total, 128, 16), 128, 0, r->stream>>>(r->dscene, r->st, dc, depth, px, first_pass, stride, qin, r->counts + depth, qout, r->counts + depth + 1);
 		r->stats.kernel_launches += 2;
@@ -811,7 +1152,8 @@ int trace_impl(ptb_renderer* r, const float* rays6, int n, int32_t* out_prim, fl
 	PTB_CUDA(cudaMalloc(&d_d, (size_t)n * sizeof(float4)));
 	PTB_CUDA(cudaMalloc(&d_hit, (size_t)n * sizeof(float4)));
 	PTB_CUDA(cudaMalloc(&d_q, (size_t)n * sizeof(int)));
-	PTB_CUDA(cudaMalloc(&d_count, sizeof(int)));
+	PTB_CUDA(cudaMalloc(&d_count, 2 * sizeof(int)));
+	PTB_CUDA(cudaMemsetAsync(d_count, 0, 2 * sizeof(int), r->stream));
 	PTB_CUDA(cudaMemcpyAsync(d_o, ho.data(), (size_t)n * sizeof(float4), cudaMemcpyHostToDevice, r->stream));
 	PTB_CUDA(cudaMemcpyAsync(d_d, hd.data(), (size_t)n * sizeof(float4), cudaMemcpyHostToDevice, r->stream));
 	if (brute)
@@ -824,7 +1166,7 @@ int trace_impl(ptb_renderer* r, const float* rays6, int n, int32_t* out_prim, fl
 		PathState st;
 		memset(&st, 0, sizeof(st));
 		st.ray_o = d_o; st.ray_d = d_d; st.hit = d_hit;
-		k_extend<false><<<grid_for(r, n, 128, 16), 128, 0, r->stream>>>(r->dscene, st, d_q, d_count, r->counters);
+		launch_extend(r, n, st, d_q, d_count, d_count + 1);
 	}
 	std::vector<float4> hh(n);
 	PTB_CUDA(cudaMemcpyAsync(hh.data(), d_hit, (size_t)n * sizeof(float4), cudaMemcpyDeviceToHost, r->stream));
@@ -891,6 +1233,11 @@ ptb_renderer* ptb_create(const char* config_json_path, int cuda_device)
 		set_error("[Cuda]cannot create stream/events");
 		delete r;
 		return nullptr;
+	}
+	{
+		int per_sm = 0;
+		if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_extend_persistent<false>, 128, 0) == cudaSuccess && per_sm > 0)
+			r->persistent_grid = r->sm_count * per_sm;
 	}
 	if (alloc_work_buffers(r)) { free_work_buffers(r); delete r; return nullptr; }
 	return r;
@@ -1078,7 +1425,7 @@ int ptb_capture_rays(ptb_renderer* r, int pass, int depth, int32_t* out_pixels, 
 	int d = 0;
 	for (; d < depth && d < r->cfg.max_tracer_depth; d++)
 	{
-		k_extend<false><<<grid_for(r, px, 128, 16), 128, 0, r->stream>>>(r->dscene, r->st, r->queue[d & 1], r->counts + d, r->counters);
+		launch_extend(r, px, r->st, r->queue[d & 1], r->counts + d, r->counts + (r->cfg.max_tracer_depth + 2) + d);
 		k_shade<<<grid_for(r, px, 128, 16), 128, 0, r->stream>>>(r->dscene, r->st, dc, d, px, pass, 1, r->queue[d & 1], r->counts + d, r->queue[(d + 1) & 1], r->counts + d + 1);
 	}
 	int count = 0;
@@ -1132,6 +1479,14 @@ int ptb_set_option(ptb_renderer* r, const char* key, const char* value)
 	if (k == "profile_stages") { r->profile_stages = atoi(value); return 0; }
 	if (k == "count_traversal") { r->count_traversal = atoi(value); return 0; }
 	if (k == "bvh_builder") { r->bvh_builder = v; return 0; }
+	if (k == "extend_persistent") { r->extend_persistent = atoi(value); return 0; }
+	if (k == "bvh_layout")
+	{
+		int n = atoi(value);
+		if (n != 2 && n != 8) { set_error("[Error]bvh_layout must be 2 or 8"); return 1; }
+		r->bvh_layout = n;   // takes effect at the next ptb_load_scene
+		return 0;
+	}
 	set_error("[Error]unknown option " + k);
 	return 1;
 }

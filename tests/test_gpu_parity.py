@@ -211,3 +211,25 @@ def test_full_size_properties(workload_root):
     u8 = r.image_u8()
     expect = np.clip(np.exp(0.45454545 * np.log(np.maximum(a / 4, 1e-30))) * 255, 0, 255).astype(np.uint8)
     assert np.abs(u8.astype(int) - expect.astype(int)).max() <= 1
+
+
+def test_bvh_layouts_agree(workload_root):
+    """binary (layout 2) and compressed 8-wide (layout 8) traversals must return identical hits:
+    the winner is decided by the same Moller-Trumbore arithmetic, the tree only culls."""
+    root, w = workload_root("c2", width=320, height=180, tri_scale=0.2)
+    res = {}
+    for layout in (2, 8):
+        r = gpu_renderer(w, root, bvh_layout=layout, count_traversal=1)
+        rays = np.concatenate([r.generate_rays(1), r.capture_rays(1, 2)[1], r.capture_rays(2, 4)[1]], 0)
+        prim, t, bary = r.trace_batch(rays, with_bary=True)
+        r.render(2)
+        st = r.stats()
+        assert st["nodes_visited"] > 0 and st["tris_tested"] > 0
+        res[layout] = (prim, t, bary, r.image_f32().copy(), st)
+        r.close()
+    assert np.array_equal(res[2][0], res[8][0])
+    assert np.array_equal(res[2][1].view(np.uint32), res[8][1].view(np.uint32))
+    assert np.array_equal(res[2][2].view(np.uint32), res[8][2].view(np.uint32))
+    assert np.array_equal(res[2][3].view(np.uint32), res[8][3].view(np.uint32))
+    # the wide tree visits far fewer nodes per ray
+    assert res[8][4]["nodes_visited"] < 0.6 * res[2][4]["nodes_visited"]
