@@ -139,14 +139,22 @@ def run_reference(args, w, root, rank, world):
             secs += dt
             step_ms.append(dt * 1e3)
         seg, trace_ms = ref.pass_instrumented(ref.lib.ref_pass_counter() + 1)
-        value = w["width"] * w["height"] * PASSES_PER_STEP * args.steps / secs / 1e6
+        # The reference's steps show multi-x outliers on this platform (cudaMallocManaged buffers +
+        # a cudaMalloc/cudaFree pair inside thrust::remove_if every bounce).  To keep the ratio the
+        # driver computes CONSERVATIVE for us, `value` is taken from the MEDIAN step, not the mean;
+        # the mean and the best step are reported next to it.
+        px_step = w["width"] * w["height"] * PASSES_PER_STEP
+        median_ms = float(np.median(step_ms))
+        value = px_step / (median_ms / 1e3) / 1e6
+        mean_value = px_step * args.steps / secs / 1e6
         line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": secs / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                "ms_per_step": median_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
                 "data": "synthetic", "config": dict(config, note="unmodified reference CUDA kernels rebuilt headless for sm_100a, managed memory prefetched"),
                 "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "reference",
                                  "sample": "%d passes of %s through path_tracer_kernel() on the B200 (the reference has no CPU implementation of this path)" % (PASSES_PER_STEP * args.steps, w["name"])},
                 "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-                "reference_extra": {"step_ms": step_ms, "as_shipped_unified_memory_Msamples_s": w["width"] * w["height"] * PASSES_PER_STEP / shipped_s / 1e6,
+                "reference_extra": {"value_basis": "median step", "mean_step_Msamples_s": mean_value, "best_step_Msamples_s": px_step / (min(step_ms) / 1e3) / 1e6,
+                                    "ms_per_step_mean": secs / args.steps * 1e3, "step_ms": step_ms, "as_shipped_unified_memory_Msamples_s": w["width"] * w["height"] * PASSES_PER_STEP / shipped_s / 1e6,
                                     "ray_segments_per_pass": seg, "trace_ray_kernel_ms_per_pass": trace_ms, "Mrays_s_trace_kernel": seg / trace_ms / 1e3 if trace_ms else None}}
         ref.close()
         return line

@@ -11,7 +11,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_LIB_PATH = os.path.join(_HERE, "libptb200.so")
+# PTB200_LIB selects an experimental build variant of the same library (tools/ only)
+_LIB_PATH = os.environ.get("PTB200_LIB") or os.path.join(_HERE, "libptb200.so")
 
 
 class PtbError(RuntimeError):

@@ -32,7 +32,13 @@ def _hash_sources():
     return h.hexdigest()
 
 
-def build(force=False, verbose=False):
+def build(force=False, verbose=False, extra_nvcc=None, out=None):
+    """extra_nvcc / out: build an experimental variant (e.g. ["-DPTB_PERSISTENT_MIN_BLOCKS=12"]) next to the default library."""
+    global OUT, OBJ
+    if out:
+        OUT = out
+        OBJ = os.path.join(HERE, "build", os.path.basename(out) + ".d")
+        force = True
     os.makedirs(OBJ, exist_ok=True)
     stamp = os.path.join(OBJ, "stamp")
     digest = _hash_sources()
@@ -46,7 +52,7 @@ def build(force=False, verbose=False):
     for src in CUDA_SOURCES:
         obj = os.path.join(OBJ, src + ".o")
         jobs.append((obj, ["nvcc", "-std=c++17", "-O3", "-lineinfo"] + NVCC_ARCH +
-                     ["-Xcompiler", "-fPIC,-fopenmp", "-Xptxas", "-v" if verbose else "-warn-spills",
+                     (extra_nvcc or []) + ["-Xcompiler", "-fPIC,-fopenmp", "-Xptxas", "-v" if verbose else "-warn-spills",
                       "-c", os.path.join(CSRC, src), "-o", obj]))
 
     def run(job):
@@ -72,4 +78,6 @@ def build(force=False, verbose=False):
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    extra = [a for a in sys.argv[1:] if a.startswith("-D")]
+    out = [a.split("=", 1)[1] for a in sys.argv[1:] if a.startswith("--out=")]
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, extra_nvcc=extra or None, out=out[0] if out else None))

@@ -326,12 +326,13 @@ __global__ void __launch_bounds__(128) k_extend(DeviceScene sc, PathState st, co
 // (plane * (1/d) - o/d) with an absolute + relative safety margin so culling stays conservative.
 // ------------------------------------------------------------------------------------------
 #define PTB_DONE ((int)0x80000000)
-#define PTB_REFILL_MIN 8      // refill when at least this many lanes are idle
-#define PTB_LEAF_MIN 10       // run a leaf phase when at least this many lanes wait at a leaf
+#ifndef PTB_PERSISTENT_MIN_BLOCKS
+#define PTB_PERSISTENT_MIN_BLOCKS 8
+#endif
 
 template <bool COUNT>
-__global__ void __launch_bounds__(128, 4) k_extend_persistent(DeviceScene sc, PathState st, const int* __restrict__ queue, const int* __restrict__ count_ptr,
-	int* __restrict__ work_counter, unsigned long long* __restrict__ counters)
+__global__ void __launch_bounds__(128, PTB_PERSISTENT_MIN_BLOCKS) k_extend_persistent(DeviceScene sc, PathState st, const int* __restrict__ queue, const int* __restrict__ count_ptr,
+	int* __restrict__ work_counter, unsigned long long* __restrict__ counters, int refill_min, int leaf_min, int node_reps)
 {
 	const int count = *count_ptr;
 	const unsigned lane = threadIdx.x & 31u;
@@ -354,23 +355,18 @@ __global__ void __launch_bounds__(128, 4) k_extend_persistent(DeviceScene sc, Pa
 	// begins; a phase is executed by the lanes in that state, the others are predicated off.
 	while (true)
 	{
+		// retire finished rays (no vote needed: a plain predicated store)
+		if (id >= 0 && node == PTB_DONE)
+		{
+			st.hit[id] = make_float4(best.t, best.t1, best.t2, __int_as_float(best.prim));
+			id = -1;
+		}
 		const bool has_ray = id >= 0;
 		const unsigned m_idle = __ballot_sync(FULL, !has_ray);
 		const unsigned m_node = __ballot_sync(FULL, has_ray && node >= 0);
-		const unsigned m_leaf = __ballot_sync(FULL, has_ray && node < 0 && node != PTB_DONE);
-		const unsigned m_done = __ballot_sync(FULL, has_ray && node == PTB_DONE);
+		const unsigned m_leaf = __ballot_sync(FULL, has_ray && node < 0);
 
-		if (m_done != 0u)
-		{
-			// ---- retire finished rays
-			if (has_ray && node == PTB_DONE)
-			{
-				st.hit[id] = make_float4(best.t, best.t1, best.t2, __int_as_float(best.prim));
-				id = -1;
-			}
-			continue;
-		}
-		if (m_idle != 0u && !exhausted && (__popc(m_idle) >= PTB_REFILL_MIN || (m_node | m_leaf) == 0u))
+		if (m_idle != 0u && !exhausted && (__popc(m_idle) >= refill_min || (m_node | m_leaf) == 0u))
 		{
 			// ---- refill idle lanes from the queue: one atomic per warp
 			const int n = __popc(m_idle);
@@ -415,10 +411,10 @@ __global__ void __launch_bounds__(128, 4) k_extend_persistent(DeviceScene sc, Pa
 		}
 		if ((m_node | m_leaf) == 0u) break;   // nothing in flight and nothing left to fetch
 
-		if (m_leaf != 0u && (__popc(m_leaf) >= PTB_LEAF_MIN || m_node == 0u))
+		if (m_leaf != 0u && (__popc(m_leaf) >= leaf_min || m_node == 0u))
 		{
 			// ---- leaf phase: node = ~((first << 3) | (count - 1))
-			if (has_ray && node < 0 && node != PTB_DONE)
+			if (has_ray && node < 0)
 			{
 				const int ref = ~node;
 				const int first = ref >> 3;
@@ -443,8 +439,9 @@ __global__ void __launch_bounds__(128, 4) k_extend_persistent(DeviceScene sc, Pa
 			continue;
 		}
 
-		// ---- node phase (one step for every lane sitting at an inner node)
-		if (has_ray && node >= 0)
+		// ---- node phase (node_reps steps for every lane sitting at an inner node)
+		for (int rep = 0; rep < node_reps; rep++)
+		if (id >= 0 && node >= 0)
 		{
 			if (COUNT) n_nodes++;
 			const float4* np = sc.bvh_nodes + (size_t)node * 4;
@@ -802,6 +799,7 @@ struct ptb_renderer
 	int bvh_layout = 2;
 	int extend_persistent = 1;
 	int persistent_grid = 148 * 4;
+	int tune_refill = 12, tune_leaf = 8, tune_reps = 3;
 
 	cudaStream_t stream = nullptr;
 	int sm_count = 148;
@@ -1027,8 +1025,8 @@ void launch_extend(ptb_renderer* r, size_t items, const PathState& st, const int
 	{
 		// persistent warps: one resident wave, sized from the occupancy the kernel actually gets
 		int grid = std::max(1, std::min(r->persistent_grid, (int)((items + 127) / 128)));
-		if (r->count_traversal) k_extend_persistent<true><<<grid, 128, 0, r->stream>>>(r->dscene, st, queue, count_ptr, work_counter, r->counters);
-		else k_extend_persistent<false><<<grid, 128, 0, r->stream>>>(r->dscene, st, queue, count_ptr, work_counter, r->counters);
+		if (r->count_traversal) k_extend_persistent<true><<<grid, 128, 0, r->stream>>>(r->dscene, st, queue, count_ptr, work_counter, r->counters, r->tune_refill, r->tune_leaf, r->tune_reps);
+		else k_extend_persistent<false><<<grid, 128, 0, r->stream>>>(r->dscene, st, queue, count_ptr, work_counter, r->counters, r->tune_refill, r->tune_leaf, r->tune_reps);
 		return;
 	}
 	int grid = grid_for(r, items, 128, 16);
@@ -1480,6 +1478,10 @@ int ptb_set_option(ptb_renderer* r, const char* key, const char* value)
 	if (k == "count_traversal") { r->count_traversal = atoi(value); return 0; }
 	if (k == "bvh_builder") { r->bvh_builder = v; return 0; }
 	if (k == "extend_persistent") { r->extend_persistent = atoi(value); return 0; }
+	if (k == "tune_refill") { r->tune_refill = atoi(value); return 0; }
+	if (k == "tune_leaf") { r->tune_leaf = atoi(value); return 0; }
+	if (k == "tune_reps") { r->tune_reps = atoi(value); return 0; }
+	if (k == "persistent_grid") { r->persistent_grid = atoi(value); return 0; }
 	if (k == "bvh_layout")
 	{
 		int n = atoi(value);

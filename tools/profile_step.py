@@ -18,6 +18,9 @@ r = ptb.Renderer(w["config"], device=0)
 r.set_option("passes_in_flight", passes)
 r.set_option("bvh_layout", layout)
 r.set_option("extend_persistent", persistent)
+for kv in sys.argv[5:]:
+    k, v = kv.split("=")
+    r.set_option(k, v)
 r.load_scene(w["scene"], root)
 if w["aperture"] >= 0:
     r.set_camera(ptb.default_camera(w["width"], w["height"], w["aperture"], w["focal"]))
