@@ -34,7 +34,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-PASSES_PER_STEP = 8
+PASSES_PER_STEP = 16
 METRIC = "path samples/sec (Mspp*px/s), 1080p"
 UNIT = "Msamples/s"
 
