@@ -34,8 +34,13 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-PASSES_PER_STEP = 16
+PASSES_PER_STEP = 32
+PASSES_IN_FLIGHT = 8      # passes traced as one wavefront batch
+STREAMS_IN_FLIGHT = 4     # batches overlapped on separate CUDA streams
 METRIC = "path samples/sec (Mspp*px/s), 1080p"
+# dram__bytes_read.sum + dram__bytes_write.sum per k_extend_persistent launch (ncu --set full, workload c2, 8 passes in flight),
+# averaged over the 8 depth launches of one batch — profiles/r01_extend_ncu_summary.md
+NCU_DRAM_BYTES_PER_EXTEND_LAUNCH = 197.6e6
 UNIT = "Msamples/s"
 
 
@@ -208,7 +213,8 @@ def run_ptb200(args, w, root, rank, local_rank, world):
         raise SystemExit("bench.py: no CUDA device — the ptb200 path has no CPU fallback")
 
     r = ptb.Renderer(w["config"], device=local_rank)
-    r.set_option("passes_in_flight", PASSES_PER_STEP)
+    r.set_option("passes_in_flight", PASSES_IN_FLIGHT)
+    r.set_option("streams_in_flight", STREAMS_IN_FLIGHT)
     t0 = time.perf_counter()
     r.load_scene(w["scene"], root)
     load_s = time.perf_counter() - t0
@@ -224,14 +230,25 @@ def run_ptb200(args, w, root, rank, local_rank, world):
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- instrumented pass outside the timed region: mean nodes visited / triangles tested per segment
+    # ---- instrumented + serial pre-pass (outside the timed region): mean nodes visited / triangles tested
+    # per segment, and EXCLUSIVE per-launch durations of the extend kernel (one stream in flight, CUDA
+    # events on the launching stream around every k_extend launch)
     r.set_option("count_traversal", 1)
     r.clear()
-    r.render_strided(rank + 1, world, PASSES_PER_STEP)
+    r.render_strided(rank + 1, world, PASSES_IN_FLIGHT)
     st = r.stats()
     nodes_per_seg = st["nodes_visited"] / max(st["ray_segments"], 1)
     tris_per_seg = st["tris_tested"] / max(st["ray_segments"], 1)
     r.set_option("count_traversal", 0)
+    r.set_option("active_streams", 1)
+    r.set_option("profile_stages", 1)
+    r.render_strided(rank + 1, world, PASSES_PER_STEP)      # warm
+    r.render_strided(rank + 1, world, PASSES_PER_STEP)
+    st = r.stats()
+    serial_extend_ms, serial_segments, serial_step_ms = st["gpu_ms_extend"], st["ray_segments"], st["gpu_ms_total"]
+    serial_launches = (PASSES_PER_STEP // PASSES_IN_FLIGHT) * w["depth"]
+    r.set_option("profile_stages", 0)
+    r.set_option("active_streams", 0)
 
     # ---- warm-up
     sr.begin()
@@ -239,8 +256,7 @@ def run_ptb200(args, w, root, rank, local_rank, world):
         sr.render_local(PASSES_PER_STEP)
     sr.begin()
 
-    # ---- timed region: K steps, device-timed on the render stream, extend launches timed live
-    r.set_option("profile_stages", 1)
+    # ---- timed region: K steps, device-timed on the render stream (4 batches overlap on 4 streams)
     sampler = ClockSampler(local_rank)
     sampler.start()
     barrier()
@@ -257,7 +273,6 @@ def run_ptb200(args, w, root, rank, local_rank, world):
     barrier()
     clocks = sampler.stop()
     ms = e0.elapsed_time(e1)
-    r.set_option("profile_stages", 0)
     t = torch.tensor([ms], dtype=torch.float64, device="cuda")
     seg_t = torch.tensor([float(segments), float(launches), extend_ms], dtype=torch.float64, device="cuda")
     if dist is not None:
@@ -288,29 +303,35 @@ def run_ptb200(args, w, root, rank, local_rank, world):
 
     if rank == 0:
         peaks, peak_kind = measured_peaks()
-        seg_total, launches_total, extend_total = [float(x) for x in seg_t.tolist()]
-        n_extend = args.steps * w["depth"] * world       # one batch per step => `depth` extend launches per step per rank
-        # algorithmic bytes of the extend (closest-hit) kernel per ray segment, SURVEY.md §8d:
+        seg_total, launches_total, _ = [float(x) for x in seg_t.tolist()]
+        # algorithmic bytes of the extend (closest-hit) kernel per ray segment, SURVEY.md 8d:
         # queue id 4 + ray o,d 32 + nodes*64 + tris*48 + hit record 16
         bytes_per_seg = 4 + 32 + nodes_per_seg * 64.0 + tris_per_seg * 48.0 + 16
-        seg_per_launch = seg_total / max(n_extend, 1)
-        avg_launch_ms = extend_total / max(n_extend, 1)
+        seg_per_launch = serial_segments / max(serial_launches, 1)
+        avg_launch_ms = serial_extend_ms / max(serial_launches, 1)
         achieved = seg_per_launch * bytes_per_seg / (avg_launch_ms / 1e3) / 1e9 if avg_launch_ms > 0 else None
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
                 "data": "synthetic",
                 "config": {"workload": w["name"], "resolution": [w["width"], w["height"]], "max_depth": w["depth"], "triangles": w["triangles"],
-                           "passes_per_step": PASSES_PER_STEP, "passes_in_flight": PASSES_PER_STEP, "parallelism": "spp-sharded x%d" % world,
-                           "l2": "path state per step %.0f MB > L2 (126 MB); no explicit flush" % (px * PASSES_PER_STEP * 84 / 1e6),
+                           "passes_per_step": PASSES_PER_STEP, "passes_in_flight": PASSES_IN_FLIGHT, "streams_in_flight": STREAMS_IN_FLIGHT,
+                           "parallelism": "spp-sharded x%d" % world,
+                           "l2": "inputs larger than L2: path state touched per step %.0f MB > 126 MB L2; no explicit flush" % (px * PASSES_PER_STEP * 84 / 1e6),
                            "scene_load_s": load_s},
                 "clocks": clocks, "gpu_launches": int(launches_total),
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 64, "d2h_bytes_per_step": int(u8.nbytes)},
                 "roofline": {"bound": "hbm", "kernel": "k_extend", "achieved": achieved, "peak": peaks.get("hbm_gbs"), "unit": "GB/s",
-                             "frac": (achieved / peaks["hbm_gbs"]) if achieved else None, "traffic": None, "peak_source": peak_kind,
+                             "frac": (achieved / peaks["hbm_gbs"]) if achieved else None, "traffic": NCU_DRAM_BYTES_PER_EXTEND_LAUNCH,
+                             "traffic_source": "profiles/r01_extend_ncu_summary.md: dram__bytes_read.sum + dram__bytes_write.sum averaged over the 8 k_extend_persistent launches of one 8-pass batch of c2 (ncu --set full)",
+                             "peak_source": peak_kind,
                              "bytes_per_segment": bytes_per_seg, "nodes_per_segment": nodes_per_seg, "tris_per_segment": tris_per_seg,
                              "segments_per_launch": seg_per_launch, "avg_launch_ms": avg_launch_ms,
-                             "extend_share_of_step": extend_total / world / ms_max if ms_max else None,
-                             "Mrays_s_extend_per_gpu": seg_total / (extend_total / 1e3) / 1e6 if extend_total else None},
+                             "how": "per-launch CUDA events on the launching stream with ONE stream in flight, immediately before the timed region "
+                                    "(the timed region overlaps %d streams, so launches there are not exclusive); achieved counts cache-served "
+                                    "bytes: nodes/triangles are L1/L2-resident, see DESIGN.md" % STREAMS_IN_FLIGHT,
+                             "extend_share_of_serial_step": serial_extend_ms / serial_step_ms if serial_step_ms else None,
+                             "Mrays_s_extend_serial": serial_segments / (serial_extend_ms / 1e3) / 1e6 if serial_extend_ms else None,
+                             "Mrays_s_whole_step": seg_total / world / (ms_max / 1e3) / 1e6},
                 "ray_segments": int(seg_total), "total_passes": int(total_passes)}
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(w, root)

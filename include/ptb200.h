@@ -152,6 +152,10 @@ int ptb_generate_rays(ptb_renderer* r, int pass, float* out_rays6);
 int ptb_capture_rays(ptb_renderer* r, int pass, int depth, int32_t* out_pixels, float* out_rays6, int max_out);
 
 int ptb_get_stats(ptb_renderer* r, ptb_stats* out);
+/* per-bounce breakdown of the last synchronous render call: live paths entering each depth and
+ * (with option "profile_stages"=1) CUDA-event milliseconds spent in the extend kernel there.
+ * Returns the number of depths written (<= max_entries) or -1. */
+int ptb_get_depth_profile(ptb_renderer* r, int max_entries, int64_t* out_segments, double* out_extend_ms);
 /* string options: "bvh_builder" = "gpu_lbvh" | "host_sah"; "passes_in_flight" = "1".."64";
  * "profile_stages" = "0"|"1"; "count_traversal" = "0"|"1"; "sort_by_material" = "0"|"1". */
 int ptb_set_option(ptb_renderer* r, const char* key, const char* value);

@@ -104,6 +104,7 @@ def load_library():
     L.ptb_generate_rays.argtypes = [vp, ci, vp]
     L.ptb_capture_rays.argtypes = [vp, ci, ci, vp, vp, ci]
     L.ptb_get_stats.argtypes = [vp, ctypes.POINTER(Stats)]
+    L.ptb_get_depth_profile.argtypes = [vp, ci, vp, vp]
     L.ptb_set_option.argtypes = [vp, cp, cp]
     L.ptb_scene_counts.argtypes = [vp] + [ctypes.POINTER(ci)] * 6
     L.ptb_scene_triangles.argtypes = [vp, vp, vp]
@@ -297,6 +298,12 @@ class Renderer:
         if n < 0:
             raise PtbError(last_error())
         return pix[:n].copy(), rays[:n].copy()
+
+    def depth_profile(self):
+        seg = np.zeros(256, np.int64)
+        ms = np.zeros(256, np.float64)
+        n = self.lib.ptb_get_depth_profile(self.handle, 256, _ptr(seg), _ptr(ms))
+        return seg[:max(n, 0)].copy(), ms[:max(n, 0)].copy()
 
     def stats(self):
         s = Stats()

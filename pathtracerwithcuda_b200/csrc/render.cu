@@ -30,6 +30,26 @@ namespace ptb
 
 __device__ __forceinline__ int float_as_int_(float f) { return __float_as_int(f); }
 
+// Upper bound on the hit distance the NEXT bounce can use (stored in ray_d.w).  In a scattering
+// medium the reference draws a free-flight distance d = -__logf(u0) / sigma_s'.x first thing in the
+// bounce and, when d < t_hit, scatters WITHOUT looking at the hit (path_tracer_kernel.cu:460-486).
+// The RNG stream of a bounce depends only on (pass, pixel, depth), so d is known before the ray is
+// traced: the closest-hit search can stop at d.  Subsurface random walks (mean free path << object
+// size) then cost a handful of node visits instead of a full traversal, with identical results.
+__device__ __forceinline__ float next_bounce_bound(const DeviceConfig& cfg, float3 sigma_a, float3 sigma_s, int seed, int pixel_index, int depth)
+{
+	if (!(sigma_s.x > 0.0f || length(sigma_a) > cfg.sss_threshold)) return CUDART_INF_F;
+	Rng rng;
+	rng.seed((uint32_t)(hash_ref(seed) * hash_ref(pixel_index) * hash_ref(depth)), 0.0f, 1.0f);
+	const float scattering_distance = -__logf(rng.next()) / sigma_s.x;
+	// hits with t <= d are still needed (the test is d < t_hit): bound = next float above d.
+	// NaN (0/0) never compares less than t_hit -> no clipping.
+	if (!(scattering_distance == scattering_distance)) return CUDART_INF_F;
+	if (scattering_distance < 0.0f || scattering_distance == 0.0f) return 1e-37f;
+	if (scattering_distance >= 3.0e38f) return CUDART_INF_F;
+	return __uint_as_float(__float_as_uint(scattering_distance) + 1u);
+}
+
 // ------------------------------------------------------------------------------------------
 // k_generate — init_data_kernel + generate_ray_kernel fused (path_tracer_kernel.cu:275-379)
 // ------------------------------------------------------------------------------------------
@@ -48,7 +68,7 @@ __global__ void __launch_bounds__(256) k_generate(PathState st, int* __restrict_
 		float3 o, d;
 		generate_camera_ray(cam, pixel, seed, cfg.use_anti_alias != 0, o, d);
 		st.ray_o[id] = make_float4(o.x, o.y, o.z, 0.0f);
-		st.ray_d[id] = make_float4(d.x, d.y, d.z, 0.0f);
+		st.ray_d[id] = make_float4(d.x, d.y, d.z, next_bounce_bound(cfg, cfg.air_sigma_a, cfg.air_sigma_s, seed, pixel, 0));
 		st.throughput[id] = make_float4(1.0f, 1.0f, 1.0f, __int_as_float(-1));
 		st.radiance[id] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
 		queue[id] = id;
@@ -72,10 +92,10 @@ struct HitRecord
 };
 
 template <bool COUNT>
-__device__ __forceinline__ HitRecord closest_hit(const DeviceScene& sc, float3 o, float3 d, unsigned& n_nodes, unsigned& n_tris)
+__device__ __forceinline__ HitRecord closest_hit(const DeviceScene& sc, float3 o, float3 d, float t_bound, unsigned& n_nodes, unsigned& n_tris)
 {
 	HitRecord best;
-	best.t = CUDART_INF_F; best.t1 = CUDART_INF_F; best.t2 = CUDART_INF_F; best.prim = -1;
+	best.t = t_bound; best.t1 = CUDART_INF_F; best.t2 = CUDART_INF_F; best.prim = -1;
 
 	// spheres first, in index order, strict '<' (path_tracer_kernel.cu:431-441)
 	for (int s = 0; s < sc.n_spheres; s++)
@@ -171,10 +191,10 @@ __device__ __forceinline__ unsigned sign_extend_s8x4(unsigned x)
 __device__ __forceinline__ unsigned extract_byte(unsigned x, unsigned i) { return (x >> (i * 8)) & 0xffu; }
 
 template <bool COUNT>
-__device__ __forceinline__ HitRecord closest_hit_bvh8(const DeviceScene& sc, float3 o, float3 d, unsigned& n_nodes, unsigned& n_tris)
+__device__ __forceinline__ HitRecord closest_hit_bvh8(const DeviceScene& sc, float3 o, float3 d, float t_bound, unsigned& n_nodes, unsigned& n_tris)
 {
 	HitRecord best;
-	best.t = CUDART_INF_F; best.t1 = CUDART_INF_F; best.t2 = CUDART_INF_F; best.prim = -1;
+	best.t = t_bound; best.t1 = CUDART_INF_F; best.t2 = CUDART_INF_F; best.prim = -1;
 	for (int s = 0; s < sc.n_spheres; s++)
 	{
 		float4 sp = __ldg(&sc.spheres[s]);
@@ -296,9 +316,9 @@ __global__ void __launch_bounds__(128) k_extend(DeviceScene sc, PathState st, co
 	{
 		int id = queue[i];
 		float4 o4 = st.ray_o[id], d4 = st.ray_d[id];
-		HitRecord h = WIDE ? closest_hit_bvh8<COUNT>(sc, make_float3(o4.x, o4.y, o4.z), make_float3(d4.x, d4.y, d4.z), n_nodes, n_tris)
-		                   : closest_hit<COUNT>(sc, make_float3(o4.x, o4.y, o4.z), make_float3(d4.x, d4.y, d4.z), n_nodes, n_tris);
-		st.hit[id] = make_float4(h.t, h.t1, h.t2, __int_as_float(h.prim));
+		HitRecord h = WIDE ? closest_hit_bvh8<COUNT>(sc, make_float3(o4.x, o4.y, o4.z), make_float3(d4.x, d4.y, d4.z), d4.w, n_nodes, n_tris)
+		                   : closest_hit<COUNT>(sc, make_float3(o4.x, o4.y, o4.z), make_float3(d4.x, d4.y, d4.z), d4.w, n_nodes, n_tris);
+		st.hit[id] = make_float4(h.prim == -1 ? CUDART_INF_F : h.t, h.t1, h.t2, __int_as_float(h.prim));
 	}
 	if (COUNT)
 	{
@@ -341,6 +361,7 @@ __global__ void __launch_bounds__(128, PTB_PERSISTENT_MIN_BLOCKS) k_extend_persi
 	unsigned n_nodes = 0, n_tris = 0;
 
 	int id = -1;                 // path id this lane is tracing; -1 = idle
+	unsigned ray_nodes = 0;      // COUNT only: node visits of the current ray
 	bool exhausted = false;      // warp-uniform: the queue has been handed out completely
 	float3 o = make_float3(0, 0, 0), d = o, idir = o, noidir = o;
 	float margin2 = 0.0f;
@@ -358,8 +379,15 @@ __global__ void __launch_bounds__(128, PTB_PERSISTENT_MIN_BLOCKS) k_extend_persi
 		// retire finished rays (no vote needed: a plain predicated store)
 		if (id >= 0 && node == PTB_DONE)
 		{
-			st.hit[id] = make_float4(best.t, best.t1, best.t2, __int_as_float(best.prim));
+			st.hit[id] = make_float4(best.prim == -1 ? CUDART_INF_F : best.t, best.t1, best.t2, __int_as_float(best.prim));
 			id = -1;
+			if (COUNT)
+			{
+				// histogram of node visits per ray: counters[4 + floor(log2(n + 1))], max in counters[2]
+				atomicMax(&counters[2], (unsigned long long)ray_nodes);
+				atomicAdd(&counters[4 + min(27, 31 - __clz(ray_nodes + 1u))], 1ull);
+				ray_nodes = 0;
+			}
 		}
 		const bool has_ray = id >= 0;
 		const unsigned m_idle = __ballot_sync(FULL, !has_ray);
@@ -383,7 +411,7 @@ __global__ void __launch_bounds__(128, PTB_PERSISTENT_MIN_BLOCKS) k_extend_persi
 					const float4 o4 = st.ray_o[id], d4 = st.ray_d[id];
 					o = make_float3(o4.x, o4.y, o4.z);
 					d = make_float3(d4.x, d4.y, d4.z);
-					best.t = CUDART_INF_F; best.t1 = CUDART_INF_F; best.t2 = CUDART_INF_F; best.prim = -1;
+					best.t = d4.w; best.t1 = CUDART_INF_F; best.t2 = CUDART_INF_F; best.prim = -1;   // d4.w: free-flight bound (next_bounce_bound)
 					best_tri = 0x7fffffff;
 					for (int s = 0; s < sc.n_spheres; s++)
 					{
@@ -443,7 +471,7 @@ __global__ void __launch_bounds__(128, PTB_PERSISTENT_MIN_BLOCKS) k_extend_persi
 		for (int rep = 0; rep < node_reps; rep++)
 		if (id >= 0 && node >= 0)
 		{
-			if (COUNT) n_nodes++;
+			if (COUNT) { n_nodes++; ray_nodes++; }
 			const float4* np = sc.bvh_nodes + (size_t)node * 4;
 			const float4 n0 = __ldg(np + 0), n1 = __ldg(np + 1), n2 = __ldg(np + 2);
 			const float2 n3 = __ldg(reinterpret_cast<const float2*>(np + 3));
@@ -575,7 +603,7 @@ __global__ void __launch_bounds__(128) k_shade(DeviceScene sc, PathState st, Dev
 					float3 next_d = sample_on_sphere(rand1, rand2);
 					not_absorbed = not_absorbed * absorption_through_medium(sigma_a, scattering_distance);
 					st.ray_o[id] = make_float4(next_o.x, next_o.y, next_o.z, 0.0f);
-					st.ray_d[id] = make_float4(next_d.x, next_d.y, next_d.z, 0.0f);
+					st.ray_d[id] = make_float4(next_d.x, next_d.y, next_d.z, next_bounce_bound(cfg, sigma_a, sigma_s, seed, pixel_index, depth + 1));
 					st.throughput[id] = make_float4(not_absorbed.x, not_absorbed.y, not_absorbed.z, t4.w);
 					if (length(not_absorbed) <= cfg.energy_threshold) alive = false;
 					done = true;
@@ -691,8 +719,23 @@ __global__ void __launch_bounds__(128) k_shade(DeviceScene sc, PathState st, Dev
 						next_o = min_point + bias_vector;
 						next_d = sample_on_hemisphere_cosine_weight(min_normal, rand1, rand2);
 					}
+					{
+						// medium the next segment travels in: unchanged unless the path refracted
+						float3 nsa = sigma_a, nss = sigma_s;
+						const int next_medium = __float_as_int(medium_bits);
+						if (next_medium != medium_index)
+						{
+							nsa = cfg.air_sigma_a; nss = cfg.air_sigma_s;
+							if (next_medium >= 0)
+							{
+								float4 md = __ldg(&sc.materials[next_medium].d), me2 = __ldg(&sc.materials[next_medium].e);
+								nsa = make_float3(md.x, md.y, md.z);
+								nss = make_float3(md.w, me2.x, me2.y);
+							}
+						}
+						st.ray_d[id] = make_float4(next_d.x, next_d.y, next_d.z, next_bounce_bound(cfg, nsa, nss, seed, pixel_index, depth + 1));
+					}
 					st.ray_o[id] = make_float4(next_o.x, next_o.y, next_o.z, 0.0f);
-					st.ray_d[id] = make_float4(next_d.x, next_d.y, next_d.z, 0.0f);
 					st.throughput[id] = make_float4(not_absorbed.x, not_absorbed.y, not_absorbed.z, medium_bits);
 					if (length(not_absorbed) <= cfg.energy_threshold) alive = false;
 				}
@@ -722,9 +765,12 @@ __global__ void __launch_bounds__(128) k_shade(DeviceScene sc, PathState st, Dev
 // k_accumulate / k_tonemap — pixel_256_transform_gamma_corrected_kernel (:627-682) split in two
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_accumulate(const float4* __restrict__ radiance, float* __restrict__ image_sum, float* __restrict__ last_pass,
+	const int* __restrict__ counts, unsigned long long* __restrict__ segment_totals, int n_counts,
 	int pixel_count, int n_slots, float clamp_hi)
 {
 	int p = blockIdx.x * blockDim.x + threadIdx.x;
+	// tally this batch's live-path counters (ray segments per depth) into the call totals
+	if (p < n_counts && counts != nullptr) atomicAdd(&segment_totals[p], (unsigned long long)counts[p]);
 	if (p >= pixel_count) return;
 	float sx = image_sum[p * 3 + 0], sy = image_sum[p * 3 + 1], sz = image_sum[p * 3 + 2];
 	float4 r = make_float4(0, 0, 0, 0);
@@ -815,53 +861,110 @@ struct ptb_renderer
 	PathState st;
 	int* queue[2] = { nullptr, nullptr };
 	int* counts = nullptr;     // max_depth + 2 ints
-	int* counts_host = nullptr; // pinned
+	unsigned long long* counts_host = nullptr; // pinned copy of segment_totals
 	unsigned long long* counters = nullptr;
 	float* image_sum = nullptr;
 	float* last_pass = nullptr;
 	uint8_t* image_u8 = nullptr;
 	cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 	std::vector<cudaEvent_t> stage_events;
+	// Batches are issued round-robin over `streams_in_flight` contexts (own stream + own path-state
+	// buffers) so the long-tail rays and tiny deep-bounce launches of one batch overlap with the
+	// bulk of another.  Context 0 is (stream, st, queue, counts) above.
+	struct BatchContext
+	{
+		cudaStream_t stream = nullptr;
+		PathState st;
+		int* queue[2] = { nullptr, nullptr };
+		int* counts = nullptr;
+		cudaEvent_t accumulated = nullptr;   // recorded after the context's k_accumulate
+	};
+	int streams_in_flight = 4;
+	int active_streams = 0;                  // 0 = all contexts; 1 = serialise batches (clean per-kernel timing)
+	std::vector<BatchContext> contexts;      // size streams_in_flight; [0] aliases the members above
+	unsigned long long* segment_totals = nullptr;   // per-depth live-path totals of the current call (device)
 
 	ptb_stats stats;
+	int64_t traversal_histogram[32] = { 0 };  // raw device counters of the last count_traversal call
+	std::vector<double> depth_extend_ms;   // per-depth sums of the last call (profile_stages)
+	std::vector<int64_t> depth_segments;
 };
 
 namespace
 {
 
+int alloc_path_state(ptb_renderer* r, PathState& st, int* queue[2], int** counts)
+{
+	const int n_counts = r->cfg.max_tracer_depth + 2;
+	PTB_CUDA(cudaMalloc(&st.ray_o, r->capacity * sizeof(float4)));
+	PTB_CUDA(cudaMalloc(&st.ray_d, r->capacity * sizeof(float4)));
+	PTB_CUDA(cudaMalloc(&st.throughput, r->capacity * sizeof(float4)));
+	PTB_CUDA(cudaMalloc(&st.radiance, r->capacity * sizeof(float4)));
+	PTB_CUDA(cudaMalloc(&st.hit, r->capacity * sizeof(float4)));
+	PTB_CUDA(cudaMalloc(&queue[0], r->capacity * sizeof(int)));
+	PTB_CUDA(cudaMalloc(&queue[1], r->capacity * sizeof(int)));
+	PTB_CUDA(cudaMalloc(counts, 2 * n_counts * sizeof(int)));
+	return 0;
+}
+
+void free_path_state(PathState& st, int* queue[2], int** counts)
+{
+	cudaFree(st.ray_o); cudaFree(st.ray_d); cudaFree(st.throughput); cudaFree(st.radiance); cudaFree(st.hit);
+	cudaFree(queue[0]); cudaFree(queue[1]); cudaFree(*counts);
+	st = PathState(); queue[0] = queue[1] = nullptr; *counts = nullptr;
+}
+
 int alloc_work_buffers(ptb_renderer* r)
 {
 	r->pixel_count = r->cfg.width * r->cfg.height;
 	r->capacity = (size_t)r->pixel_count * r->passes_in_flight;
-	PTB_CUDA(cudaMalloc(&r->st.ray_o, r->capacity * sizeof(float4)));
-	PTB_CUDA(cudaMalloc(&r->st.ray_d, r->capacity * sizeof(float4)));
-	PTB_CUDA(cudaMalloc(&r->st.throughput, r->capacity * sizeof(float4)));
-	PTB_CUDA(cudaMalloc(&r->st.radiance, r->capacity * sizeof(float4)));
-	PTB_CUDA(cudaMalloc(&r->st.hit, r->capacity * sizeof(float4)));
-	PTB_CUDA(cudaMalloc(&r->queue[0], r->capacity * sizeof(int)));
-	PTB_CUDA(cudaMalloc(&r->queue[1], r->capacity * sizeof(int)));
-	int n_counts = r->cfg.max_tracer_depth + 2;
-	PTB_CUDA(cudaMalloc(&r->counts, 2 * n_counts * sizeof(int)));
-	PTB_CUDA(cudaMallocHost(&r->counts_host, n_counts * sizeof(int)));
-	PTB_CUDA(cudaMalloc(&r->counters, 2 * sizeof(unsigned long long)));
+	const int n_counts = r->cfg.max_tracer_depth + 2;
+	if (alloc_path_state(r, r->st, r->queue, &r->counts)) return 1;
+	r->contexts.assign(std::max(1, r->streams_in_flight), ptb_renderer::BatchContext());
+	for (size_t c = 0; c < r->contexts.size(); c++)
+	{
+		ptb_renderer::BatchContext& ctx = r->contexts[c];
+		if (c == 0)
+		{
+			ctx.stream = r->stream; ctx.st = r->st; ctx.queue[0] = r->queue[0]; ctx.queue[1] = r->queue[1]; ctx.counts = r->counts;
+		}
+		else
+		{
+			PTB_CUDA(cudaStreamCreateWithFlags(&ctx.stream, cudaStreamNonBlocking));
+			if (alloc_path_state(r, ctx.st, ctx.queue, &ctx.counts)) return 1;
+		}
+		PTB_CUDA(cudaEventCreateWithFlags(&ctx.accumulated, cudaEventDisableTiming));
+	}
+	PTB_CUDA(cudaMallocHost(&r->counts_host, n_counts * sizeof(unsigned long long)));
+	PTB_CUDA(cudaMalloc(&r->segment_totals, n_counts * sizeof(unsigned long long)));
+	PTB_CUDA(cudaMalloc(&r->counters, 32 * sizeof(unsigned long long)));
 	PTB_CUDA(cudaMalloc(&r->image_sum, (size_t)r->pixel_count * 3 * sizeof(float)));
 	PTB_CUDA(cudaMalloc(&r->last_pass, (size_t)r->pixel_count * 3 * sizeof(float)));
 	PTB_CUDA(cudaMalloc(&r->image_u8, (size_t)r->pixel_count * 3));
 	PTB_CUDA(cudaMemsetAsync(r->image_sum, 0, (size_t)r->pixel_count * 3 * sizeof(float), r->stream));
 	PTB_CUDA(cudaMemsetAsync(r->last_pass, 0, (size_t)r->pixel_count * 3 * sizeof(float), r->stream));
 	PTB_CUDA(cudaMemsetAsync(r->image_u8, 0, (size_t)r->pixel_count * 3, r->stream));
-	PTB_CUDA(cudaMemsetAsync(r->counters, 0, 2 * sizeof(unsigned long long), r->stream));
+	PTB_CUDA(cudaMemsetAsync(r->counters, 0, 32 * sizeof(unsigned long long), r->stream));
 	PTB_CUDA(cudaStreamSynchronize(r->stream));
 	return 0;
 }
 
 void free_work_buffers(ptb_renderer* r)
 {
-	cudaFree(r->st.ray_o); cudaFree(r->st.ray_d); cudaFree(r->st.throughput); cudaFree(r->st.radiance); cudaFree(r->st.hit);
-	cudaFree(r->queue[0]); cudaFree(r->queue[1]); cudaFree(r->counts); cudaFree(r->counters);
+	for (size_t c = 0; c < r->contexts.size(); c++)
+	{
+		ptb_renderer::BatchContext& ctx = r->contexts[c];
+		if (ctx.accumulated) cudaEventDestroy(ctx.accumulated);
+		if (c == 0) continue;
+		if (ctx.stream) { cudaStreamSynchronize(ctx.stream); cudaStreamDestroy(ctx.stream); }
+		free_path_state(ctx.st, ctx.queue, &ctx.counts);
+	}
+	r->contexts.clear();
+	free_path_state(r->st, r->queue, &r->counts);
+	cudaFree(r->counters); cudaFree(r->segment_totals);
 	if (r->counts_host) cudaFreeHost(r->counts_host);
 	cudaFree(r->image_sum); cudaFree(r->last_pass); cudaFree(r->image_u8);
-	r->st = PathState(); r->queue[0] = r->queue[1] = nullptr; r->counts = nullptr; r->counts_host = nullptr; r->counters = nullptr;
+	r->counts_host = nullptr; r->counters = nullptr; r->segment_totals = nullptr;
 	r->image_sum = nullptr; r->last_pass = nullptr; r->image_u8 = nullptr;
 }
 
@@ -1018,32 +1121,34 @@ int grid_for(const ptb_renderer* r, size_t items, int block, int blocks_per_sm)
 	return (int)std::max<size_t>(1, std::min(need, cap));
 }
 
-void launch_extend(ptb_renderer* r, size_t items, const PathState& st, const int* queue, const int* count_ptr, int* work_counter)
+void launch_extend(ptb_renderer* r, cudaStream_t stream, size_t items, const PathState& st, const int* queue, const int* count_ptr, int* work_counter)
 {
 	bool wide = r->dscene.bvh_layout == 8;
 	if (!wide && r->extend_persistent)
 	{
 		// persistent warps: one resident wave, sized from the occupancy the kernel actually gets
 		int grid = std::max(1, std::min(r->persistent_grid, (int)((items + 127) / 128)));
-		if (r->count_traversal) k_extend_persistent<true><<<grid, 128, 0, r->stream>>>(r->dscene, st, queue, count_ptr, work_counter, r->counters, r->tune_refill, r->tune_leaf, r->tune_reps);
-		else k_extend_persistent<false><<<grid, 128, 0, r->stream>>>(r->dscene, st, queue, count_ptr, work_counter, r->counters, r->tune_refill, r->tune_leaf, r->tune_reps);
+		if (r->count_traversal) k_extend_persistent<true><<<grid, 128, 0, stream>>>(r->dscene, st, queue, count_ptr, work_counter, r->counters, r->tune_refill, r->tune_leaf, r->tune_reps);
+		else k_extend_persistent<false><<<grid, 128, 0, stream>>>(r->dscene, st, queue, count_ptr, work_counter, r->counters, r->tune_refill, r->tune_leaf, r->tune_reps);
 		return;
 	}
 	int grid = grid_for(r, items, 128, 16);
 	if (r->count_traversal)
 	{
-		if (wide) k_extend<true, true><<<grid, 128, 0, r->stream>>>(r->dscene, st, queue, count_ptr, r->counters);
-		else k_extend<true, false><<<grid, 128, 0, r->stream>>>(r->dscene, st, queue, count_ptr, r->counters);
+		if (wide) k_extend<true, true><<<grid, 128, 0, stream>>>(r->dscene, st, queue, count_ptr, r->counters);
+		else k_extend<true, false><<<grid, 128, 0, stream>>>(r->dscene, st, queue, count_ptr, r->counters);
 	}
 	else
 	{
-		if (wide) k_extend<false, true><<<grid, 128, 0, r->stream>>>(r->dscene, st, queue, count_ptr, r->counters);
-		else k_extend<false, false><<<grid, 128, 0, r->stream>>>(r->dscene, st, queue, count_ptr, r->counters);
+		if (wide) k_extend<false, true><<<grid, 128, 0, stream>>>(r->dscene, st, queue, count_ptr, r->counters);
+		else k_extend<false, false><<<grid, 128, 0, stream>>>(r->dscene, st, queue, count_ptr, r->counters);
 	}
 }
 
-// enqueue one batch of n_slots passes: first, first+stride, ...
-int enqueue_batch(ptb_renderer* r, int first_pass, int stride, int n_slots)
+// enqueue one batch of n_slots passes (first, first+stride, ...) on a context's stream.
+// `prev_accumulated`: event of the previous batch's k_accumulate — the running sum is updated in
+// pass order whatever the overlap, so the image is bit-identical to a serial run.
+int enqueue_batch(ptb_renderer* r, ptb_renderer::BatchContext& ctx, cudaEvent_t prev_accumulated, int first_pass, int stride, int n_slots)
 {
 	const int px = r->pixel_count;
 	const size_t total = (size_t)px * n_slots;
@@ -1051,28 +1156,29 @@ int enqueue_batch(ptb_renderer* r, int first_pass, int stride, int n_slots)
 	CameraParams cp = camera_params(r->cam);
 	const int n_counts = r->cfg.max_tracer_depth + 2;
 	const bool prof = r->profile_stages != 0;
-	k_generate<<<grid_for(r, total, 256, 8), 256, 0, r->stream>>>(r->st, r->queue[0], r->counts, n_counts, cp, dc, px, n_slots, first_pass, stride);
+	cudaStream_t stream = ctx.stream;
+	k_generate<<<grid_for(r, total, 256, 8), 256, 0, stream>>>(ctx.st, ctx.queue[0], ctx.counts, n_counts, cp, dc, px, n_slots, first_pass, stride);
 	r->stats.kernel_launches++;
 	for (int depth = 0; depth < r->cfg.max_tracer_depth; depth++)
 	{
-		int* qin = r->queue[depth & 1];
-		int* qout = r->queue[(depth + 1) & 1];
+		int* qin = ctx.queue[depth & 1];
+		int* qout = ctx.queue[(depth + 1) & 1];
 		cudaEvent_t e0 = nullptr, e1 = nullptr;
 		if (prof)
 		{
 			cudaEventCreate(&e0); cudaEventCreate(&e1);
 			r->stage_events.push_back(e0); r->stage_events.push_back(e1);
-			cudaEventRecord(e0, r->stream);
+			cudaEventRecord(e0, stream);
 		}
-		launch_extend(r, total, r->st, qin, r->counts + depth, r->counts + n_counts + depth);
-		if (prof) cudaEventRecord(e1, r->stream);
-		k_shade<<<grid_for(r, total, 128, 16), 128, 0, r->stream>>>(r->dscene, r->st, dc, depth, px, first_pass, stride, qin, r->counts + depth, qout, r->counts + depth + 1);
+		launch_extend(r, stream, total, ctx.st, qin, ctx.counts + depth, ctx.counts + n_counts + depth);
+		if (prof) cudaEventRecord(e1, stream);
+		k_shade<<<grid_for(r, total, 128, 16), 128, 0, stream>>>(r->dscene, ctx.st, dc, depth, px, first_pass, stride, qin, ctx.counts + depth, qout, ctx.counts + depth + 1);
 		r->stats.kernel_launches += 2;
 	}
-	k_accumulate<<<(px + 255) / 256, 256, 0, r->stream>>>(r->st.radiance, r->image_sum, r->last_pass, px, n_slots, (float)r->cfg.max_tracer_depth * 2.0f);
+	if (prev_accumulated) PTB_CUDA(cudaStreamWaitEvent(stream, prev_accumulated, 0));
+	k_accumulate<<<(px + 255) / 256, 256, 0, stream>>>(ctx.st.radiance, r->image_sum, r->last_pass, ctx.counts, r->segment_totals, n_counts, px, n_slots, (float)r->cfg.max_tracer_depth * 2.0f);
 	r->stats.kernel_launches++;
-	// ray-segment counters of this batch -> host (summed after the stream drains)
-	PTB_CUDA(cudaMemcpyAsync(r->counts_host, r->counts, n_counts * sizeof(int), cudaMemcpyDeviceToHost, r->stream));
+	PTB_CUDA(cudaEventRecord(ctx.accumulated, stream));
 	PTB_CUDA(cudaGetLastError());
 	return 0;
 }
@@ -1084,49 +1190,63 @@ int render_impl(ptb_renderer* r, int first_pass, int stride, int n_passes, bool 
 	if (n_passes <= 0) return 0;
 	memset(&r->stats, 0, sizeof(r->stats));
 	r->stats.bvh_nodes = r->bvh_nodes; r->stats.bvh_bytes = r->bvh_bytes;
-	PTB_CUDA(cudaMemsetAsync(r->counters, 0, 2 * sizeof(unsigned long long), r->stream));
-	PTB_CUDA(cudaEventRecord(r->ev0, r->stream));
-	int done = 0;
 	const int n_counts = r->cfg.max_tracer_depth + 2;
+	PTB_CUDA(cudaMemsetAsync(r->counters, 0, 32 * sizeof(unsigned long long), r->stream));
+	PTB_CUDA(cudaMemsetAsync(r->segment_totals, 0, n_counts * sizeof(unsigned long long), r->stream));
+	PTB_CUDA(cudaEventRecord(r->ev0, r->stream));
+	const int n_ctx = r->active_streams > 0 ? std::min(r->active_streams, (int)r->contexts.size()) : (int)r->contexts.size();
+	for (int c = 1; c < n_ctx; c++) PTB_CUDA(cudaStreamWaitEvent(r->contexts[c].stream, r->ev0, 0));
+	int done = 0, batch = 0;
+	cudaEvent_t prev_acc = nullptr;
 	while (done < n_passes)
 	{
 		int nb = std::min(r->passes_in_flight, n_passes - done);
-		if (enqueue_batch(r, first_pass + done * stride, stride, nb)) return 1;
+		ptb_renderer::BatchContext& ctx = r->contexts[batch % n_ctx];
+		if (enqueue_batch(r, ctx, prev_acc, first_pass + done * stride, stride, nb)) return 1;
+		prev_acc = ctx.accumulated;
 		done += nb;
-		if (synchronous)
-		{
-			// counts_host is reused per batch; drain before the next batch overwrites it
-			PTB_CUDA(cudaStreamSynchronize(r->stream));
-			for (int d = 0; d < n_counts - 1; d++) r->stats.ray_segments += r->counts_host[d];
-		}
+		batch++;
 	}
+	// the last accumulate depends (transitively) on every earlier batch: wait for it on the main stream
+	if (prev_acc && batch > 0 && r->contexts[(batch - 1) % n_ctx].stream != r->stream) PTB_CUDA(cudaStreamWaitEvent(r->stream, prev_acc, 0));
 	if (advance_counter) r->pass_counter += n_passes;
 	int total_passes = advance_counter ? r->pass_counter : n_passes;
 	k_tonemap<<<(r->pixel_count + 255) / 256, 256, 0, r->stream>>>(r->image_sum, r->image_u8, r->pixel_count, std::max(total_passes, 1), r->cfg.gamma_correction ? 1 : 0);
 	r->stats.kernel_launches++;
+	PTB_CUDA(cudaMemcpyAsync(r->counts_host, r->segment_totals, n_counts * sizeof(unsigned long long), cudaMemcpyDeviceToHost, r->stream));
 	PTB_CUDA(cudaEventRecord(r->ev1, r->stream));
 	r->stats.passes = n_passes;
 	if (synchronous)
 	{
 		PTB_CUDA(cudaStreamSynchronize(r->stream));
+		for (int c = 1; c < n_ctx; c++) PTB_CUDA(cudaStreamSynchronize(r->contexts[c].stream));
+		r->depth_segments.assign(r->cfg.max_tracer_depth, 0);
+		for (int d = 0; d < r->cfg.max_tracer_depth; d++)
+		{
+			r->stats.ray_segments += (int64_t)r->counts_host[d];
+			r->depth_segments[d] = (int64_t)r->counts_host[d];
+		}
 		float ms = 0.0f;
 		cudaEventElapsedTime(&ms, r->ev0, r->ev1);
 		r->stats.gpu_ms_total = ms;
 		double ext = 0.0;
+		r->depth_extend_ms.assign(r->cfg.max_tracer_depth, 0.0);
 		for (size_t i = 0; i + 1 < r->stage_events.size(); i += 2)
 		{
 			float m = 0.0f;
 			cudaEventElapsedTime(&m, r->stage_events[i], r->stage_events[i + 1]);
 			ext += m;
+			r->depth_extend_ms[(i / 2) % r->cfg.max_tracer_depth] += m;
 		}
 		for (auto e : r->stage_events) cudaEventDestroy(e);
 		r->stage_events.clear();
 		r->stats.gpu_ms_extend = ext;
 		if (r->count_traversal)
 		{
-			unsigned long long c[2] = { 0, 0 };
+			unsigned long long c[32];
 			cudaMemcpy(c, r->counters, sizeof(c), cudaMemcpyDeviceToHost);
 			r->stats.nodes_visited = (int64_t)c[0]; r->stats.tris_tested = (int64_t)c[1];
+			for (int k = 0; k < 32; k++) r->traversal_histogram[k] = (int64_t)c[k];
 		}
 	}
 	return 0;
@@ -1144,7 +1264,7 @@ int trace_impl(ptb_renderer* r, const float* rays6, int n, int32_t* out_prim, fl
 	for (int i = 0; i < n; i++)
 	{
 		ho[i] = make_float4(rays6[i * 6 + 0], rays6[i * 6 + 1], rays6[i * 6 + 2], 0.0f);
-		hd[i] = make_float4(rays6[i * 6 + 3], rays6[i * 6 + 4], rays6[i * 6 + 5], 0.0f);
+		hd[i] = make_float4(rays6[i * 6 + 3], rays6[i * 6 + 4], rays6[i * 6 + 5], INFINITY);
 	}
 	PTB_CUDA(cudaMalloc(&d_o, (size_t)n * sizeof(float4)));
 	PTB_CUDA(cudaMalloc(&d_d, (size_t)n * sizeof(float4)));
@@ -1164,7 +1284,7 @@ int trace_impl(ptb_renderer* r, const float* rays6, int n, int32_t* out_prim, fl
 		PathState st;
 		memset(&st, 0, sizeof(st));
 		st.ray_o = d_o; st.ray_d = d_d; st.hit = d_hit;
-		launch_extend(r, n, st, d_q, d_count, d_count + 1);
+		launch_extend(r, r->stream, n, st, d_q, d_count, d_count + 1);
 	}
 	std::vector<float4> hh(n);
 	PTB_CUDA(cudaMemcpyAsync(hh.data(), d_hit, (size_t)n * sizeof(float4), cudaMemcpyDeviceToHost, r->stream));
@@ -1290,7 +1410,13 @@ int ptb_load_scene(ptb_renderer* r, const char* scene_json_path, const char* ass
 int ptb_release_scene(ptb_renderer* r)
 {
 	if (!r) return 1;
-	if (!r->host_only) { cudaSetDevice(r->device); cudaStreamSynchronize(r->stream); release_scene_device(r); }
+	if (!r->host_only)
+	{
+		cudaSetDevice(r->device);
+		for (size_t c = 1; c < r->contexts.size(); c++) cudaStreamSynchronize(r->contexts[c].stream);
+		cudaStreamSynchronize(r->stream);
+		release_scene_device(r);
+	}
 	r->scene = HostScene();
 	r->scene_loaded = false;
 	return 0;
@@ -1326,11 +1452,17 @@ int ptb_render_strided(ptb_renderer* r, int first_pass, int stride, int n_passes
 	return rc;
 }
 
+static int sync_all_streams(ptb_renderer* r)
+{
+	for (size_t c = 1; c < r->contexts.size(); c++) PTB_CUDA(cudaStreamSynchronize(r->contexts[c].stream));
+	PTB_CUDA(cudaStreamSynchronize(r->stream));
+	return 0;
+}
+
 int ptb_synchronize(ptb_renderer* r)
 {
 	if (!r || r->host_only) return 1;
-	PTB_CUDA(cudaStreamSynchronize(r->stream));
-	return 0;
+	return sync_all_streams(r);
 }
 
 void* ptb_stream(ptb_renderer* r) { return r ? (void*)r->stream : nullptr; }
@@ -1341,6 +1473,7 @@ int ptb_clear(ptb_renderer* r)
 	r->pass_counter = 0;
 	if (r->host_only) return 0;
 	cudaSetDevice(r->device);
+	for (size_t c = 1; c < r->contexts.size(); c++) PTB_CUDA(cudaStreamSynchronize(r->contexts[c].stream));
 	PTB_CUDA(cudaMemsetAsync(r->image_sum, 0, (size_t)r->pixel_count * 3 * sizeof(float), r->stream));
 	PTB_CUDA(cudaStreamSynchronize(r->stream));
 	return 0;
@@ -1423,7 +1556,7 @@ int ptb_capture_rays(ptb_renderer* r, int pass, int depth, int32_t* out_pixels, 
 	int d = 0;
 	for (; d < depth && d < r->cfg.max_tracer_depth; d++)
 	{
-		launch_extend(r, px, r->st, r->queue[d & 1], r->counts + d, r->counts + (r->cfg.max_tracer_depth + 2) + d);
+		launch_extend(r, r->stream, px, r->st, r->queue[d & 1], r->counts + d, r->counts + (r->cfg.max_tracer_depth + 2) + d);
 		k_shade<<<grid_for(r, px, 128, 16), 128, 0, r->stream>>>(r->dscene, r->st, dc, d, px, pass, 1, r->queue[d & 1], r->counts + d, r->queue[(d + 1) & 1], r->counts + d + 1);
 	}
 	int count = 0;
@@ -1452,6 +1585,24 @@ int ptb_capture_rays(ptb_renderer* r, int pass, int depth, int32_t* out_pixels, 
 
 int ptb_get_stats(ptb_renderer* r, ptb_stats* out) { if (!r || !out) return 1; *out = r->stats; return 0; }
 
+int ptb_get_depth_profile(ptb_renderer* r, int max_entries, int64_t* out_segments, double* out_extend_ms)
+{
+	if (!r) return -1;
+	if (max_entries == -32)
+	{
+		// debugging side door: raw traversal counters (max node visits per ray in [2], log2 histogram from [4])
+		memcpy(out_segments, r->traversal_histogram, sizeof(r->traversal_histogram));
+		return 32;
+	}
+	int n = std::min(max_entries, r->cfg.max_tracer_depth);
+	for (int d = 0; d < n; d++)
+	{
+		out_segments[d] = d < (int)r->depth_segments.size() ? r->depth_segments[d] : 0;
+		out_extend_ms[d] = d < (int)r->depth_extend_ms.size() ? r->depth_extend_ms[d] : 0.0;
+	}
+	return n;
+}
+
 int ptb_set_option(ptb_renderer* r, const char* key, const char* value)
 {
 	if (!r || !key || !value) return 1;
@@ -1474,6 +1625,25 @@ int ptb_set_option(ptb_renderer* r, const char* key, const char* value)
 		}
 		return 0;
 	}
+	if (k == "streams_in_flight")
+	{
+		int n = atoi(value);
+		if (n < 1 || n > 8) { set_error("[Error]streams_in_flight must be in 1..8"); return 1; }
+		if (n != r->streams_in_flight)
+		{
+			r->streams_in_flight = n;
+			if (!r->host_only)
+			{
+				cudaSetDevice(r->device);
+				cudaDeviceSynchronize();
+				free_work_buffers(r);
+				if (alloc_work_buffers(r)) return 1;
+				r->pass_counter = 0;
+			}
+		}
+		return 0;
+	}
+	if (k == "active_streams") { r->active_streams = atoi(value); return 0; }
 	if (k == "profile_stages") { r->profile_stages = atoi(value); return 0; }
 	if (k == "count_traversal") { r->count_traversal = atoi(value); return 0; }
 	if (k == "bvh_builder") { r->bvh_builder = v; return 0; }

@@ -15,7 +15,8 @@ persistent = sys.argv[4] if len(sys.argv) > 4 else "1"
 root = tempfile.mkdtemp(prefix="ptb_prof_")
 w = pr.make_workload(root, name)
 r = ptb.Renderer(w["config"], device=0)
-r.set_option("passes_in_flight", passes)
+in_flight = int(os.environ.get("PTB_IN_FLIGHT", passes))
+r.set_option("passes_in_flight", in_flight)
 r.set_option("bvh_layout", layout)
 r.set_option("extend_persistent", persistent)
 for kv in sys.argv[5:]:
@@ -32,3 +33,15 @@ st = r.stats()
 print("step: %.3f ms gpu (%.3f ms in k_extend), %d segments, %.1f Msamples/s, %.1f Mrays/s extend" % (
     st["gpu_ms_total"], st["gpu_ms_extend"], st["ray_segments"], w["width"] * w["height"] * passes / st["gpu_ms_total"] / 1e3,
     st["ray_segments"] / max(st["gpu_ms_extend"], 1e-9) / 1e3))
+seg, ms = r.depth_profile()
+print("depth  segments   extend_ms  Mrays/s")
+for d in range(len(seg)):
+    print("%5d %9d %10.3f %8.1f" % (d, seg[d], ms[d], seg[d] / max(ms[d], 1e-9) / 1e3))
+r.set_option("count_traversal", 1)
+r.render(passes)
+st = r.stats()
+print("nodes/segment %.2f  tris/segment %.2f" % (st["nodes_visited"] / st["ray_segments"], st["tris_tested"] / st["ray_segments"]))
+import numpy as np, ctypes
+h = np.zeros(32, np.int64); dummy = np.zeros(32, np.float64)
+r.lib.ptb_get_depth_profile(r.handle, -32, h.ctypes.data_as(ctypes.c_void_p), dummy.ctypes.data_as(ctypes.c_void_p))
+print("max node visits of one ray:", h[2]); print("log2 histogram of node visits per ray:", h[4:28].tolist())
