@@ -206,6 +206,9 @@ def run_ptb200(args, w, root, rank, local_rank, world):
 
     dist = None
     if world > 1:
+        # keep stdout to the one JSON line: NCCL prints its version banner there at NCCL_DEBUG=VERSION
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
         import torch.distributed as dist
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))

@@ -172,6 +172,29 @@ int ptb_scene_cubemap_face(ptb_renderer* r, int face, uint8_t* out_rgba);
 /* the parsed configuration as the reference's 96-byte `configuration` (Core/configuration.h:9-34) */
 int ptb_get_config(ptb_renderer* r, void* out96);
 
+/* ---- reference-signature compatibility entries --------------------------------------------
+ * The three extern "C" symbols Core/path_tracer.cpp links against (Core/path_tracer_kernel.h:18-54;
+ * Kernel/path_tracer_kernel.cu:685,782,798), with the reference's own argument lists and struct
+ * layouts, so its host code can call this library unchanged: the AoS managed
+ * buffers (triangle 104 B, bvh_node_device 56 B, sphere 100 B, material 84 B, cube_map 56 B,
+ * texture_wrapper 16 B, configuration 96 B) are ingested and cached, the pass with seed
+ * `pass_counter` is traced by the wavefront kernels, and image_pixels (float3 running sum, "=" on pass
+ * 1, "+=" otherwise), image_pixels_256 and accumulated_colors are written like
+ * pixel_256_transform_gamma_corrected_kernel does.  Synchronous; logs in the reference's
+ * "[Cuda]Error ..." format and returns on failure.  Declared with opaque pointers here. */
+#ifndef PTB200_BUILDING_LIBRARY
+void path_tracer_kernel(
+	int mesh_num, void** bvh_nodes_device, void* triangles_device, int sphere_num, void* spheres_device,
+	int pixel_count, float* image_pixels, uint8_t* image_pixels_256, int pass_counter,
+	const ptb_camera* render_camera_device, void* sky_cube_map_device,
+	float* not_absorbed_colors_device, float* accumulated_colors_device, void* rays_device,
+	int* energy_exist_pixels_device, void* scatterings_device, void* mesh_textures_device, void* config_device);
+void path_tracer_kernel_memory_allocate(float** not_absorbed_colors_device, float** accumulated_colors_device, void** rays_device,
+	int** energy_exist_pixels_device, void** scatterings_device, int pixel_count);
+void path_tracer_kernel_memory_free(float* not_absorbed_colors_device, float* accumulated_colors_device, void* rays_device,
+	int* energy_exist_pixels_device, void* scatterings_device);
+#endif
+
 #ifdef __cplusplus
 }
 #endif

@@ -171,6 +171,33 @@ double ref_render(int n_passes)
 	return std::chrono::duration<double>(t1 - t0).count();
 }
 
+/* the 18 arguments the reference hands to path_tracer_kernel (Core/path_tracer.cpp:48-67), as raw
+ * pointers/ints, so a test can call ANOTHER implementation of the same symbol on the reference's own
+ * managed scene buffers.  out[] order = argument order; ints are stored as intptr_t. */
+void ref_kernel_args(void** out18)
+{
+	out18[0] = (void*)(intptr_t)g_scene->get_mesh_num();
+	out18[1] = (void*)g_scene->get_bvh_node_device_ptr();
+	out18[2] = (void*)g_scene->get_triangles_device_ptr();
+	out18[3] = (void*)(intptr_t)g_scene->get_sphere_num();
+	out18[4] = (void*)g_scene->get_sphere_device_ptr();
+	out18[5] = (void*)(intptr_t)g_image->pixel_count;
+	out18[6] = (void*)g_image->pixels_device;
+	out18[7] = (void*)g_image->pixels_256_device;
+	out18[8] = (void*)(intptr_t)g_image->pass_counter;
+	out18[9] = (void*)g_render_cam;
+	out18[10] = (void*)g_scene->get_cube_map_device_ptr();
+	out18[11] = (void*)g_not_absorbed;
+	out18[12] = (void*)g_accumulated;
+	out18[13] = (void*)g_rays;
+	out18[14] = (void*)g_energy_exist;
+	out18[15] = (void*)g_scatterings;
+	out18[16] = (void*)g_scene->get_mesh_texture_device_ptr();
+	out18[17] = (void*)g_config->get_config_device_ptr();
+}
+
+void ref_set_pass_counter(int v) { if (g_image) g_image->pass_counter = v; }
+
 int ref_image_f32(float* out_rgb_sum)
 {
 	cudaDeviceSynchronize();

@@ -15,6 +15,7 @@
 #include <string>
 #include <vector>
 
+#define PTB200_BUILDING_LIBRARY 1
 #include "../../include/ptb200.h"
 #include "scene.h"
 #include "bvh.h"
@@ -1722,3 +1723,5 @@ int ptb_get_config(ptb_renderer* r, void* out96)
 }
 
 } // extern "C"
+
+#include "compat.inc"

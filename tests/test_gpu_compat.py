@@ -1,0 +1,67 @@
+"""Drop-in proof for the reference-signature entry: the UNMODIFIED reference host code (its own
+scene_parser / triangle_mesh / BVH build / image / config_parser, via oracle/_ref/libptref.so) builds
+its managed AoS scene, and `path_tracer_kernel` of libptb200.so is called with exactly the 18
+arguments Core/path_tracer.cpp:48-67 passes.  The image it leaves in the reference's own buffers
+must match what the reference's kernel leaves there."""
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF_LIB = os.path.join(REPO, "oracle", "_ref", "libptref.so")
+
+WORKER = r'''
+import ctypes, json, os, sys, tempfile
+import numpy as np
+sys.path.insert(0, %(repo)r)
+from oracle import refharness as rh
+from pathtracerwithcuda_b200 import procedural as pr, api
+name, passes = sys.argv[1], int(sys.argv[2])
+root = tempfile.mkdtemp(prefix="ptb_compat_")
+w = pr.make_workload(root, name, width=96, height=72)
+rh.link_backslash_names(root)
+ref = rh.RefLib(host_only=False)
+ref.open(root, config_rel=w["config_rel"], scene=w["scene_name"])
+ref.set_camera(ref.default_camera(w["width"], w["height"], w["aperture"], w["focal"]))
+ref.clear(); ref.render(passes)
+a_sum, a_u8, a_last = ref.image_f32().copy(), ref.image_u8().copy(), ref.last_pass_f32().copy()
+args = (ctypes.c_void_p * 18)()
+ref.lib.ref_kernel_args(args)
+L = api.load_library()
+vp, ci = ctypes.c_void_p, ctypes.c_int
+L.path_tracer_kernel.argtypes = [ci, vp, vp, ci, vp, ci, vp, vp, ci, vp, vp, vp, vp, vp, vp, vp, vp, vp]
+L.path_tracer_kernel.restype = None
+iv = lambda k: int(args[k] or 0)
+ref.clear()
+for p in range(1, passes + 1):
+    L.path_tracer_kernel(iv(0), args[1], args[2], iv(3), args[4], iv(5), args[6], args[7], p, args[9], args[10], args[11], args[12],
+                         args[13], args[14], args[15], args[16], args[17])
+b_sum, b_u8, b_last = ref.image_f32().copy(), ref.image_u8().copy(), ref.last_pass_f32().copy()
+rel = np.abs(a_sum.astype(np.float64) - b_sum) / np.maximum(np.abs(a_sum), 1e-3)
+rel_last = np.abs(a_last.astype(np.float64) - b_last) / np.maximum(np.abs(a_last), 1e-3)
+# second round: edit a material in place like the reference UI does, restart accumulation
+print(json.dumps({"outliers": float((rel > 1e-3).mean()), "p999": float(np.quantile(rel, 0.999)), "bit_equal": float((a_sum == b_sum).mean()),
+                  "u8_max": int(np.abs(a_u8.astype(int) - b_u8.astype(int)).max()), "last_outliers": float((rel_last > 1e-3).mean()),
+                  "mean": float(b_sum.mean())}))
+'''
+
+
+@pytest.mark.skipif(not os.path.exists(REF_LIB), reason="oracle/_ref/libptref.so not present on this box")
+@pytest.mark.parametrize("name", ["mix", "c1"])
+def test_reference_host_code_drives_our_kernel_symbol(name):
+    script = tempfile.mktemp(suffix=".py")
+    with open(script, "w") as f:
+        f.write(WORKER % {"repo": REPO})
+    out = subprocess.run([sys.executable, script, name, "3"], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr[-3000:]
+    rep = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][-1])
+    assert rep["mean"] > 0
+    assert rep["outliers"] <= 2e-4 and rep["p999"] <= 1e-3 and rep["last_outliers"] <= 2e-4, rep
+    assert rep["u8_max"] <= 1 and rep["bit_equal"] >= 0.98, rep

@@ -123,6 +123,9 @@ def run(scene, width, height, depth, spp, root=None, config_extra=None, camera=N
     ri = ref.image_f32()
     mi = mine.image_f32()
     report["image_sum"] = image_stats(ri, mi)
+    mean_ref, mean_new = ri.astype(np.float64) / spp, mi.astype(np.float64) / spp
+    report["mean_image_rmse"] = float(np.sqrt(np.mean((mean_ref - mean_new) ** 2)))
+    report["mean_image_rel_rmse"] = float(report["mean_image_rmse"] / max(np.sqrt(np.mean(mean_ref ** 2)), 1e-30))
     report["last_pass"] = image_stats(ref.last_pass_f32(), mine.last_pass_f32())
     r8, m8 = ref.image_u8().astype(np.int32), mine.image_u8().astype(np.int32)
     report["image_u8_max_abs_diff"] = int(np.abs(r8 - m8).max())
