@@ -156,7 +156,16 @@ int ptb_get_stats(ptb_renderer* r, ptb_stats* out);
  * (with option "profile_stages"=1) CUDA-event milliseconds spent in the extend kernel there.
  * Returns the number of depths written (<= max_entries) or -1. */
 int ptb_get_depth_profile(ptb_renderer* r, int max_entries, int64_t* out_segments, double* out_extend_ms);
-/* string options: "bvh_builder" = "gpu_lbvh" | "host_sah"; "passes_in_flight" = "1".."64";
+/* Acceleration structure of the loaded scene (replaces the BVH producers Bvh/bvh.cpp:185-219,667-780,
+ * 862-1047 + Kernel/bvh_morton_code_kernel.cu:298-346): facts about the last build and a structural
+ * check of the DEVICE arrays (binary layout).  out_i[8]: node records, reachable inner nodes, leaves,
+ * depth, valid (every triangle in exactly one leaf, vertices inside the leaf box, child boxes inside the
+ * parent's), built on the GPU (1/0), level-synchronous rounds, sub-trees finished in shared memory.
+ * out_d[4]: builder milliseconds (CUDA events for the GPU builder), SAH cost, whole scene upload ms,
+ * violations found.  ptb_bvh_leaf_labels: per triangle the smallest triangle id sharing its leaf. */
+int ptb_bvh_info(ptb_renderer* r, int64_t* out_i, double* out_d);
+int ptb_bvh_leaf_labels(ptb_renderer* r, int32_t* out_label);
+/* string options: "bvh_builder" = "gpu_sah" (default) | "host_sah"; "passes_in_flight" = "1".."64";
  * "profile_stages" = "0"|"1"; "count_traversal" = "0"|"1"; "sort_by_material" = "0"|"1". */
 int ptb_set_option(ptb_renderer* r, const char* key, const char* value);
 

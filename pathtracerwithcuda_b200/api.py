@@ -106,6 +106,8 @@ def load_library():
     L.ptb_get_stats.argtypes = [vp, ctypes.POINTER(Stats)]
     L.ptb_get_depth_profile.argtypes = [vp, ci, vp, vp]
     L.ptb_set_option.argtypes = [vp, cp, cp]
+    L.ptb_bvh_info.argtypes = [vp, vp, vp]
+    L.ptb_bvh_leaf_labels.argtypes = [vp, vp]
     L.ptb_scene_counts.argtypes = [vp] + [ctypes.POINTER(ci)] * 6
     L.ptb_scene_triangles.argtypes = [vp, vp, vp]
     L.ptb_scene_materials.argtypes = [vp, vp]
@@ -304,6 +306,19 @@ class Renderer:
         ms = np.zeros(256, np.float64)
         n = self.lib.ptb_get_depth_profile(self.handle, 256, _ptr(seg), _ptr(ms))
         return seg[:max(n, 0)].copy(), ms[:max(n, 0)].copy()
+
+    def bvh_info(self):
+        oi = np.zeros(8, np.int64)
+        od = np.zeros(4, np.float64)
+        self._check(self.lib.ptb_bvh_info(self.handle, _ptr(oi), _ptr(od)))
+        return {"node_records": int(oi[0]), "inner_nodes": int(oi[1]), "leaves": int(oi[2]), "depth": int(oi[3]), "valid": bool(oi[4]),
+                "built_on_gpu": bool(oi[5]), "levels": int(oi[6]), "small_subtrees": int(oi[7]), "build_ms": float(od[0]),
+                "sah_cost": float(od[1]), "upload_ms": float(od[2]), "violations": int(od[3])}
+
+    def bvh_leaf_labels(self):
+        out = np.zeros(self.scene_counts()["triangles"], np.int32)
+        self._check(self.lib.ptb_bvh_leaf_labels(self.handle, _ptr(out)))
+        return out
 
     def stats(self):
         s = Stats()

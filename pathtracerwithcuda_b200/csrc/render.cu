@@ -11,6 +11,7 @@
 #include <algorithm>
 #include <chrono>
 #include <cstdio>
+#include <cmath>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -19,6 +20,7 @@
 #include "../../include/ptb200.h"
 #include "scene.h"
 #include "bvh.h"
+#include "bvh_gpu.h"
 #include "kernels.cuh"
 
 using namespace ptbdev;
@@ -842,8 +844,12 @@ struct ptb_renderer
 	int passes_in_flight = 4;
 	int profile_stages = 0;
 	int count_traversal = 0;
-	std::string bvh_builder = "host_sah";
+	std::string bvh_builder = "gpu_sah";   // "gpu_sah" (csrc/bvh_build.cu) | "host_sah" (csrc/bvh_host.cpp)
 	int bvh_layout = 2;
+	// facts about the last acceleration-structure build (ptb_bvh_info)
+	int bvh_built_on_gpu = 0, bvh_levels = 0, bvh_small_tasks = 0, bvh_max_depth = 0;
+	double bvh_build_ms = 0.0, scene_upload_ms = 0.0;
+	std::string bvh_note;
 	int extend_persistent = 1;
 	int persistent_grid = 148 * 4;
 	int tune_refill = 12, tune_leaf = 8, tune_reps = 3;
@@ -1004,6 +1010,63 @@ DeviceMaterial pack_material(const ptb_material& m)
 	return d;
 }
 
+// Host copy of a device-built binary tree in the Bvh2 form build_bvh8 consumes (the wide layout's
+// collapse + quantisation still runs on the host).  Node boxes are the padded child boxes stored in
+// the parents; the root's box is the union of its children.
+int download_bvh2(const GpuBuildOutput& gb, Bvh2& out)
+{
+	std::vector<float> nodes((size_t)gb.n_nodes * 16);
+	out.prim_order.resize(gb.n_prims);
+	PTB_CUDA(cudaMemcpy(nodes.data(), gb.nodes, nodes.size() * sizeof(float), cudaMemcpyDeviceToHost));
+	PTB_CUDA(cudaMemcpy(out.prim_order.data(), gb.prim_order, (size_t)gb.n_prims * sizeof(int), cudaMemcpyDeviceToHost));
+	out.nodes.clear();
+	out.nodes.reserve((size_t)gb.n_prims);
+	struct Item { int dev_ref; int host_index; };
+	std::vector<Item> stack;
+	out.nodes.emplace_back();
+	for (int a = 0; a < 3; a++) { out.nodes[0].box.lo[a] = INFINITY; out.nodes[0].box.hi[a] = -INFINITY; }
+	stack.push_back({ 0, 0 });
+	bool root = true;
+	while (!stack.empty())
+	{
+		Item it = stack.back();
+		stack.pop_back();
+		if (it.dev_ref < 0)
+		{
+			int ref = ~it.dev_ref;
+			out.nodes[it.host_index].first = ref >> 3;
+			out.nodes[it.host_index].count = (ref & 7) + 1;
+			continue;
+		}
+		const float* d = &nodes[(size_t)it.dev_ref * 16];
+		Aabb cb[2];
+		cb[0].lo[0] = d[0]; cb[0].hi[0] = d[1]; cb[0].lo[1] = d[2]; cb[0].hi[1] = d[3]; cb[0].lo[2] = d[8]; cb[0].hi[2] = d[9];
+		cb[1].lo[0] = d[4]; cb[1].hi[0] = d[5]; cb[1].lo[1] = d[6]; cb[1].hi[1] = d[7]; cb[1].lo[2] = d[10]; cb[1].hi[2] = d[11];
+		int refs[2];
+		memcpy(refs, &d[12], 8);
+		const bool second_empty = cb[1].lo[0] > cb[1].hi[0];
+		if (root && second_empty)
+		{
+			// single-leaf tree (wrapper node): the Bvh2 root is that leaf
+			out.nodes[0].box = cb[0];
+			stack.push_back({ refs[0], 0 });
+			root = false;
+			continue;
+		}
+		const int l = (int)out.nodes.size();
+		out.nodes.emplace_back();
+		out.nodes.emplace_back();
+		out.nodes[l].box = cb[0]; out.nodes[l + 1].box = cb[1];
+		out.nodes[it.host_index].left = l; out.nodes[it.host_index].right = l + 1; out.nodes[it.host_index].count = 0;
+		if (root)
+			for (int a = 0; a < 3; a++) { out.nodes[0].box.lo[a] = std::min(cb[0].lo[a], cb[1].lo[a]); out.nodes[0].box.hi[a] = std::max(cb[0].hi[a], cb[1].hi[a]); }
+		root = false;
+		stack.push_back({ refs[1], l + 1 });
+		stack.push_back({ refs[0], l });
+	}
+	return 0;
+}
+
 int upload_scene(ptb_renderer* r)
 {
 	release_scene_device(r);
@@ -1011,11 +1074,66 @@ int upload_scene(ptb_renderer* r)
 	DeviceScene& ds = r->dscene;
 	memset(&ds, 0, sizeof(ds));
 
+	// raw triangles + material indices on the device: the builder, the leaf-order emitter and the
+	// shading-attribute packer all read them there
+	const auto t_upload0 = std::chrono::steady_clock::now();
+	const int n_tris = (int)s.triangles.size();
+	const float* d_tris24 = nullptr;
+	const int* d_material = nullptr;
+	if (upload(r, (const float*)s.triangles.data(), (size_t)n_tris * 24, &d_tris24)) return 1;
+	if (upload(r, s.triangle_material.data(), (size_t)n_tris, &d_material)) return 1;
+	r->bvh_built_on_gpu = 0; r->bvh_levels = 0; r->bvh_small_tasks = 0; r->bvh_max_depth = 0; r->bvh_build_ms = 0.0; r->bvh_note.clear();
+
 	// acceleration structure over all meshes' world-space triangles
+	const int max_leaf = r->bvh_layout == 8 ? 3 : 4;   // <= 3 triangles per leaf slot of a wide node
 	Bvh2 bvh;
+	bool have_device_bvh2 = false;
+	if (r->bvh_builder != "host_sah" && n_tris > 0)
+	{
+		GpuBuildOutput gb;
+		std::string why;
+		if (build_bvh2_gpu(d_tris24, n_tris, max_leaf, r->stream, gb, why) == 0)
+		{
+			r->bvh_built_on_gpu = 1; r->bvh_levels = gb.levels; r->bvh_small_tasks = gb.small_tasks; r->bvh_max_depth = gb.max_depth; r->bvh_build_ms = gb.build_ms;
+			if (gb.max_depth >= PTB_STACK_SIZE)
+			{
+				cudaFree(gb.nodes); cudaFree(gb.tri_isect); cudaFree(gb.prim_order);
+				set_error("[Error]BVH too deep for the traversal stack");
+				return 1;
+			}
+			if (r->bvh_layout == 8)
+			{
+				// wide layout: the binary tree comes from the device, the 8-wide collapse + quantisation runs on the host
+				int rc = download_bvh2(gb, bvh);
+				cudaFree(gb.nodes); cudaFree(gb.tri_isect); cudaFree(gb.prim_order);
+				if (rc) return 1;
+			}
+			else
+			{
+				r->scene_allocs.push_back(gb.nodes); r->scene_allocs.push_back(gb.tri_isect);
+				cudaFree(gb.prim_order);
+				ds.bvh_nodes = gb.nodes; ds.tri_isect = gb.tri_isect;
+				r->bvh_nodes = gb.n_nodes;
+				r->bvh_bytes = (int64_t)gb.n_nodes * 64 + (int64_t)n_tris * 48;
+				have_device_bvh2 = true;
+			}
+		}
+		else
+		{
+			// adversarial input (capacity) or out of memory: say so and use the host builder
+			r->bvh_note = why;
+			fprintf(stderr, "[Warn]GPU BVH build failed (%s); using the host SAH builder\n", why.c_str());
+			cudaGetLastError();
+		}
+	}
+	if (!have_device_bvh2 && !(r->bvh_built_on_gpu && r->bvh_layout == 8))
+	{
+		const auto t0 = std::chrono::steady_clock::now();
+		build_bvh2_sah(s.triangles, max_leaf, bvh);
+		r->bvh_build_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+	}
 	if (r->bvh_layout == 8)
 	{
-		build_bvh2_sah(s.triangles, 3, bvh);   // <= 3 triangles per leaf slot of a wide node
 		GpuBvh8 wide;
 		build_bvh8(bvh, s.triangles, wide);
 		if (wide.max_depth > PTB_STACK_SIZE8) { set_error("[Error]BVH8 too deep for the traversal stack"); return 1; }
@@ -1024,9 +1142,8 @@ int upload_scene(ptb_renderer* r)
 		r->bvh_nodes = (int64_t)wide.nodes.size() / 20;
 		r->bvh_bytes = (int64_t)(wide.nodes.size() + wide.tris.size()) * 4;
 	}
-	else
+	else if (!have_device_bvh2)
 	{
-		build_bvh2_sah(s.triangles, 4, bvh);
 		GpuBvh2 flat;
 		flatten_bvh2(bvh, s.triangles, flat);
 		if (upload(r, (const float4*)flat.nodes.data(), flat.nodes.size() / 4, &ds.bvh_nodes)) return 1;
@@ -1035,22 +1152,17 @@ int upload_scene(ptb_renderer* r)
 		r->bvh_bytes = (int64_t)(flat.nodes.size() + flat.tris.size()) * 4;
 	}
 	ds.bvh_layout = r->bvh_layout;
-	ds.n_triangles = (int)s.triangles.size();
+	ds.n_triangles = n_tris;
 	ds.root_ref = 0;
 
-	// shading attributes by global triangle id
-	std::vector<float> shade((size_t)s.triangles.size() * 16);
-	for (size_t i = 0; i < s.triangles.size(); i++)
+	// shading attributes by global triangle id, packed on the device
 	{
-		const Triangle& t = s.triangles[i];
-		float* d = &shade[i * 16];
-		d[0] = t.n0.x; d[1] = t.n0.y; d[2] = t.n0.z; d[3] = t.n1.x;
-		d[4] = t.n1.y; d[5] = t.n1.z; d[6] = t.n2.x; d[7] = t.n2.y;
-		d[8] = t.n2.z; d[9] = t.uv0.x; d[10] = t.uv0.y; d[11] = t.uv1.x;
-		d[12] = t.uv1.y; d[13] = t.uv2.x; d[14] = t.uv2.y;
-		memcpy(&d[15], &s.triangle_material[i], 4);
+		float4* d_shade = nullptr;
+		PTB_CUDA(cudaMalloc(&d_shade, std::max<size_t>((size_t)n_tris * 64, 16)));
+		r->scene_allocs.push_back(d_shade);
+		pack_tri_shade_gpu(d_tris24, d_material, n_tris, d_shade, r->stream);
+		ds.tri_shade = d_shade;
 	}
-	if (upload(r, (const float4*)shade.data(), shade.size() / 4, &ds.tri_shade)) return 1;
 
 	std::vector<DeviceMaterial> mats;
 	for (auto& m : s.materials) mats.push_back(pack_material(m));
@@ -1083,6 +1195,8 @@ int upload_scene(ptb_renderer* r)
 	ds.sky.use_sky = r->cfg.use_sky ? 1 : 0;
 	ds.sky.use_bilinear = r->cfg.use_bilinear ? 1 : 0;
 	PTB_CUDA(cudaStreamSynchronize(r->stream));
+	PTB_CUDA(cudaGetLastError());
+	r->scene_upload_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_upload0).count();
 	return 0;
 }
 
@@ -1604,6 +1718,130 @@ int ptb_get_depth_profile(ptb_renderer* r, int max_entries, int64_t* out_segment
 	return n;
 }
 
+// ---- acceleration-structure introspection (test / diagnostic hooks; binary layout only) ----
+// Walks a host copy of the DEVICE arrays the traversal kernels read, so it validates what was actually
+// built whichever builder produced it.
+int ptb_bvh_info(ptb_renderer* r, int64_t* out_i, double* out_d)
+{
+	if (!r || r->host_only) { set_error("[Error]no CUDA device"); return 1; }
+	if (!r->scene_loaded) { set_error("[Error]no scene loaded"); return 1; }
+	if (r->dscene.bvh_layout != 2) { set_error("[Error]ptb_bvh_info: binary layout only"); return 1; }
+	cudaSetDevice(r->device);
+	const int n = r->dscene.n_triangles;
+	const int64_t n_nodes = r->bvh_nodes;
+	std::vector<float> nodes((size_t)n_nodes * 16), tris((size_t)n * 12);
+	if (n_nodes) PTB_CUDA(cudaMemcpy(nodes.data(), r->dscene.bvh_nodes, nodes.size() * sizeof(float), cudaMemcpyDeviceToHost));
+	if (n) PTB_CUDA(cudaMemcpy(tris.data(), r->dscene.tri_isect, tris.size() * sizeof(float), cudaMemcpyDeviceToHost));
+	std::vector<int> seen(n, 0);
+	int64_t inner = 0, leaves = 0, max_depth = 0, bad = 0;
+	double cost = 0.0, root_area = 0.0;
+	auto area = [](const float* lo, const float* hi) { double dx = (double)hi[0] - lo[0], dy = (double)hi[1] - lo[1], dz = (double)hi[2] - lo[2]; return (dx < 0 || dy < 0 || dz < 0) ? 0.0 : dx * dy + dy * dz + dz * dx; };
+	struct Item { int ref; int depth; float lo[3], hi[3]; };
+	std::vector<Item> stack;
+	if (n > 0 && n_nodes > 0)
+	{
+		Item root; root.ref = r->dscene.root_ref; root.depth = 0;
+		const float* d = &nodes[(size_t)root.ref * 16];
+		root.lo[0] = std::min(d[0], d[4]); root.hi[0] = std::max(d[1], d[5]);
+		root.lo[1] = std::min(d[2], d[6]); root.hi[1] = std::max(d[3], d[7]);
+		root.lo[2] = std::min(d[8], d[10]); root.hi[2] = std::max(d[9], d[11]);
+		if (d[4] > d[5]) { root.lo[0] = d[0]; root.hi[0] = d[1]; root.lo[1] = d[2]; root.hi[1] = d[3]; root.lo[2] = d[8]; root.hi[2] = d[9]; }
+		root_area = area(root.lo, root.hi);
+		stack.push_back(root);
+	}
+	while (!stack.empty())
+	{
+		Item it = stack.back();
+		stack.pop_back();
+		max_depth = std::max<int64_t>(max_depth, it.depth);
+		if (it.ref < 0)
+		{
+			const int ref = ~it.ref, first = ref >> 3, cnt = (ref & 7) + 1;
+			leaves++;
+			cost += (root_area > 0 ? area(it.lo, it.hi) / root_area : 0.0) * 1.5 * cnt;
+			for (int k = 0; k < cnt; k++)
+			{
+				if (first + k >= n) { bad++; continue; }
+				const float* t = &tris[(size_t)(first + k) * 12];
+				int id; memcpy(&id, &t[3], 4);
+				if (id < 0 || id >= n) { bad++; continue; }
+				seen[id]++;
+				// the three vertices must lie inside the (padded) leaf box
+				for (int v = 0; v < 3; v++)
+					for (int a = 0; a < 3; a++)
+					{
+						float x = t[a] + (v == 1 ? t[4 + a] : (v == 2 ? t[8 + a] : 0.0f));
+						float slack = 1e-5f * (std::fabs(x) + std::fabs(t[a])) + 1e-30f;   // v0 + e1 re-rounds
+						if (!(x >= it.lo[a] - slack && x <= it.hi[a] + slack)) bad++;
+					}
+			}
+			continue;
+		}
+		if (it.ref >= n_nodes || it.depth > 4096) { bad++; continue; }
+		inner++;
+		cost += root_area > 0 ? area(it.lo, it.hi) / root_area : 0.0;
+		const float* d = &nodes[(size_t)it.ref * 16];
+		int refs[2]; memcpy(refs, &d[12], 8);
+		Item c0, c1;
+		c0.ref = refs[0]; c1.ref = refs[1]; c0.depth = c1.depth = it.depth + 1;
+		c0.lo[0] = d[0]; c0.hi[0] = d[1]; c0.lo[1] = d[2]; c0.hi[1] = d[3]; c0.lo[2] = d[8]; c0.hi[2] = d[9];
+		c1.lo[0] = d[4]; c1.hi[0] = d[5]; c1.lo[1] = d[6]; c1.hi[1] = d[7]; c1.lo[2] = d[10]; c1.hi[2] = d[11];
+		const bool c1_empty = c1.lo[0] > c1.hi[0];
+		for (int a = 0; a < 3; a++)
+		{
+			if (c0.lo[a] < it.lo[a] || c0.hi[a] > it.hi[a]) bad++;
+			if (!c1_empty && (c1.lo[a] < it.lo[a] || c1.hi[a] > it.hi[a])) bad++;
+		}
+		if (!c1_empty) stack.push_back(c1);
+		stack.push_back(c0);
+	}
+	for (int i = 0; i < n; i++) if (seen[i] != 1) bad++;
+	if (out_i)
+	{
+		out_i[0] = n_nodes; out_i[1] = inner; out_i[2] = leaves; out_i[3] = max_depth; out_i[4] = bad == 0 ? 1 : 0;
+		out_i[5] = r->bvh_built_on_gpu; out_i[6] = r->bvh_levels; out_i[7] = r->bvh_small_tasks;
+	}
+	if (out_d) { out_d[0] = r->bvh_build_ms; out_d[1] = cost; out_d[2] = r->scene_upload_ms; out_d[3] = (double)bad; }
+	return 0;
+}
+
+// label[t] = smallest triangle id sharing t's leaf: two builds have the same leaf partition iff the labels agree
+int ptb_bvh_leaf_labels(ptb_renderer* r, int32_t* out_label)
+{
+	if (!r || r->host_only) { set_error("[Error]no CUDA device"); return 1; }
+	if (!r->scene_loaded) { set_error("[Error]no scene loaded"); return 1; }
+	if (r->dscene.bvh_layout != 2) { set_error("[Error]ptb_bvh_leaf_labels: binary layout only"); return 1; }
+	cudaSetDevice(r->device);
+	const int n = r->dscene.n_triangles;
+	const int64_t n_nodes = r->bvh_nodes;
+	std::vector<float> nodes((size_t)n_nodes * 16), tris((size_t)n * 12);
+	if (n_nodes) PTB_CUDA(cudaMemcpy(nodes.data(), r->dscene.bvh_nodes, nodes.size() * sizeof(float), cudaMemcpyDeviceToHost));
+	if (n) PTB_CUDA(cudaMemcpy(tris.data(), r->dscene.tri_isect, tris.size() * sizeof(float), cudaMemcpyDeviceToHost));
+	for (int i = 0; i < n; i++) out_label[i] = -1;
+	std::vector<int> stack;
+	if (n > 0 && n_nodes > 0) stack.push_back(r->dscene.root_ref);
+	size_t guard = 0;
+	while (!stack.empty() && guard++ < (size_t)4 * n + 16)
+	{
+		int ref = stack.back();
+		stack.pop_back();
+		if (ref < 0)
+		{
+			const int lr = ~ref, first = lr >> 3, cnt = (lr & 7) + 1;
+			int lo = 0x7fffffff;
+			for (int k = 0; k < cnt && first + k < n; k++) { int id; memcpy(&id, &tris[(size_t)(first + k) * 12 + 3], 4); lo = std::min(lo, id); }
+			for (int k = 0; k < cnt && first + k < n; k++) { int id; memcpy(&id, &tris[(size_t)(first + k) * 12 + 3], 4); if (id >= 0 && id < n) out_label[id] = lo; }
+			continue;
+		}
+		if (ref >= n_nodes) continue;
+		const float* d = &nodes[(size_t)ref * 16];
+		int refs[2]; memcpy(refs, &d[12], 8);
+		if (!(d[4] > d[5])) stack.push_back(refs[1]);
+		stack.push_back(refs[0]);
+	}
+	return 0;
+}
+
 int ptb_set_option(ptb_renderer* r, const char* key, const char* value)
 {
 	if (!r || !key || !value) return 1;
@@ -1647,7 +1885,12 @@ int ptb_set_option(ptb_renderer* r, const char* key, const char* value)
 	if (k == "active_streams") { r->active_streams = atoi(value); return 0; }
 	if (k == "profile_stages") { r->profile_stages = atoi(value); return 0; }
 	if (k == "count_traversal") { r->count_traversal = atoi(value); return 0; }
-	if (k == "bvh_builder") { r->bvh_builder = v; return 0; }
+	if (k == "bvh_builder")
+	{
+		if (v != "gpu_sah" && v != "host_sah") { set_error("[Error]bvh_builder must be gpu_sah or host_sah"); return 1; }
+		r->bvh_builder = v;   // takes effect at the next ptb_load_scene
+		return 0;
+	}
 	if (k == "extend_persistent") { r->extend_persistent = atoi(value); return 0; }
 	if (k == "tune_refill") { r->tune_refill = atoi(value); return 0; }
 	if (k == "tune_leaf") { r->tune_leaf = atoi(value); return 0; }
