@@ -108,6 +108,7 @@ def load_library():
     L.ptb_set_option.argtypes = [vp, cp, cp]
     L.ptb_bvh_info.argtypes = [vp, vp, vp]
     L.ptb_bvh_leaf_labels.argtypes = [vp, vp]
+    L.ptb_bvh_download.argtypes = [vp, vp, vp]
     L.ptb_scene_counts.argtypes = [vp] + [ctypes.POINTER(ci)] * 6
     L.ptb_scene_triangles.argtypes = [vp, vp, vp]
     L.ptb_scene_materials.argtypes = [vp, vp]
@@ -314,6 +315,12 @@ class Renderer:
         return {"node_records": int(oi[0]), "inner_nodes": int(oi[1]), "leaves": int(oi[2]), "depth": int(oi[3]), "valid": bool(oi[4]),
                 "built_on_gpu": bool(oi[5]), "levels": int(oi[6]), "small_subtrees": int(oi[7]), "build_ms": float(od[0]),
                 "sah_cost": float(od[1]), "upload_ms": float(od[2]), "violations": int(od[3])}
+
+    def bvh_download(self):
+        nodes = np.zeros((self.bvh_info()["node_records"], 16), np.float32)
+        order = np.zeros(self.scene_counts()["triangles"], np.int32)
+        self._check(self.lib.ptb_bvh_download(self.handle, _ptr(nodes), _ptr(order)))
+        return nodes, order
 
     def bvh_leaf_labels(self):
         out = np.zeros(self.scene_counts()["triangles"], np.int32)

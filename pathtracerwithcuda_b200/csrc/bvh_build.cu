@@ -156,18 +156,22 @@ __device__ Choice warp_choose(const int* bins, int count, const float* blo, cons
 	for (int i = 0; i < 12; i++) { ch.l[i] = 0.0f; ch.r[i] = 0.0f; }
 	if (count <= 1) return ch;
 
-	const int a = min(lane / 15, 2), b = lane - (lane / 15) * 15;
+	// 45 candidate planes over 32 lanes: lane evaluates candidates `lane` and `lane + 32`, keeping its better one
 	float L[12], R[12];
-#pragma unroll
-	for (int i = 0; i < 3; i++)
-	{
-		L[i] = R[i] = L[6 + i] = R[6 + i] = CUDART_INF_F;
-		L[3 + i] = R[3 + i] = L[9 + i] = R[9 + i] = -CUDART_INF_F;
-	}
-	int cl = 0, cr = 0;
+	int cl = 0, cr = 0, cand_best = lane;
 	float cost = CUDART_INF_F;
-	if (lane < 45 && __fsub_rn(chi[a], clo[a]) > 0.0f)
+	for (int cand = lane; cand < 45; cand += 32)
 	{
+		const int a = cand / 15, b = cand - a * 15;
+		if (!(__fsub_rn(chi[a], clo[a]) > 0.0f)) continue;
+		float l[12], r[12];
+#pragma unroll
+		for (int i = 0; i < 3; i++)
+		{
+			l[i] = r[i] = l[6 + i] = r[6 + i] = CUDART_INF_F;
+			l[3 + i] = r[3 + i] = l[9 + i] = r[9 + i] = -CUDART_INF_F;
+		}
+		int nl = 0, nr = 0;
 		for (int k = 0; k < kBins; k++)
 		{
 			const int* p = bins + (a * kBins + k) * kBinWords;
@@ -175,29 +179,39 @@ __device__ Choice warp_choose(const int* bins, int count, const float* blo, cons
 			if (c == 0) continue;
 			if (k <= b)
 			{
-				cl += c;
+				nl += c;
 #pragma unroll
 				for (int i = 0; i < 3; i++)
 				{
-					L[i] = fminf(L[i], dec(p[1 + i])); L[3 + i] = fmaxf(L[3 + i], dec(p[4 + i]));
-					L[6 + i] = fminf(L[6 + i], dec(p[7 + i])); L[9 + i] = fmaxf(L[9 + i], dec(p[10 + i]));
+					l[i] = fminf(l[i], dec(p[1 + i])); l[3 + i] = fmaxf(l[3 + i], dec(p[4 + i]));
+					l[6 + i] = fminf(l[6 + i], dec(p[7 + i])); l[9 + i] = fmaxf(l[9 + i], dec(p[10 + i]));
 				}
 			}
 			else
 			{
-				cr += c;
+				nr += c;
 #pragma unroll
 				for (int i = 0; i < 3; i++)
 				{
-					R[i] = fminf(R[i], dec(p[1 + i])); R[3 + i] = fmaxf(R[3 + i], dec(p[4 + i]));
-					R[6 + i] = fminf(R[6 + i], dec(p[7 + i])); R[9 + i] = fmaxf(R[9 + i], dec(p[10 + i]));
+					r[i] = fminf(r[i], dec(p[1 + i])); r[3 + i] = fmaxf(r[3 + i], dec(p[4 + i]));
+					r[6 + i] = fminf(r[6 + i], dec(p[7 + i])); r[9 + i] = fmaxf(r[9 + i], dec(p[10 + i]));
 				}
 			}
 		}
-		if (cl > 0 && cr > 0) cost = __fadd_rn(__fmul_rn(area_half(L, L + 3), (float)cl), __fmul_rn(area_half(R, R + 3), (float)cr));
+		if (nl > 0 && nr > 0)
+		{
+			const float c = __fadd_rn(__fmul_rn(area_half(l, l + 3), (float)nl), __fmul_rn(area_half(r, r + 3), (float)nr));
+			if (c < cost)   // strict: the lower candidate index wins ties, like the host's sweep order
+			{
+				cost = c; cand_best = cand; cl = nl; cr = nr;
+#pragma unroll
+				for (int i = 0; i < 12; i++) { L[i] = l[i]; R[i] = r[i]; }
+			}
+		}
 	}
+	(void)cr;
 	float best = cost;
-	int who = lane;
+	int who = cand_best;
 	for (int off = 16; off > 0; off >>= 1)
 	{
 		const float oc = __shfl_down_sync(FULL, best, off);
@@ -205,7 +219,7 @@ __device__ Choice warp_choose(const int* bins, int count, const float* blo, cons
 		if (oc < best || (oc == best && ow < who)) { best = oc; who = ow; }
 	}
 	best = __shfl_sync(FULL, best, 0);
-	who = __shfl_sync(FULL, who, 0);
+	who = __shfl_sync(FULL, who, 0);   // winning candidate index (axis * 15 + bin); it lives in lane who & 31
 	const bool have = best < CUDART_INF_F;
 
 	const float parent_area = area_half(blo, bhi);
@@ -220,9 +234,9 @@ __device__ Choice warp_choose(const int* bins, int count, const float* blo, cons
 	if (kind == KIND_SAH)
 	{
 		ch.axis = who / 15; ch.bin = who - (who / 15) * 15;
-		ch.nl = __shfl_sync(FULL, cl, who);
+		ch.nl = __shfl_sync(FULL, cl, who & 31);
 #pragma unroll
-		for (int i = 0; i < 12; i++) { ch.l[i] = __shfl_sync(FULL, L[i], who); ch.r[i] = __shfl_sync(FULL, R[i], who); }
+		for (int i = 0; i < 12; i++) { ch.l[i] = __shfl_sync(FULL, L[i], who & 31); ch.r[i] = __shfl_sync(FULL, R[i], who & 31); }
 	}
 	else if (kind == KIND_MEDIAN)
 	{

@@ -1842,6 +1842,24 @@ int ptb_bvh_leaf_labels(ptb_renderer* r, int32_t* out_label)
 	return 0;
 }
 
+// raw copy of the device arrays (binary layout): 16 floats per node record, triangle id per leaf slot
+int ptb_bvh_download(ptb_renderer* r, float* out_nodes16, int32_t* out_leaf_order)
+{
+	if (!r || r->host_only) { set_error("[Error]no CUDA device"); return 1; }
+	if (!r->scene_loaded) { set_error("[Error]no scene loaded"); return 1; }
+	if (r->dscene.bvh_layout != 2) { set_error("[Error]ptb_bvh_download: binary layout only"); return 1; }
+	cudaSetDevice(r->device);
+	const int n = r->dscene.n_triangles;
+	if (out_nodes16 && r->bvh_nodes) PTB_CUDA(cudaMemcpy(out_nodes16, r->dscene.bvh_nodes, (size_t)r->bvh_nodes * 64, cudaMemcpyDeviceToHost));
+	if (out_leaf_order && n)
+	{
+		std::vector<float> tris((size_t)n * 12);
+		PTB_CUDA(cudaMemcpy(tris.data(), r->dscene.tri_isect, tris.size() * sizeof(float), cudaMemcpyDeviceToHost));
+		for (int i = 0; i < n; i++) memcpy(&out_leaf_order[i], &tris[(size_t)i * 12 + 3], 4);
+	}
+	return 0;
+}
+
 int ptb_set_option(ptb_renderer* r, const char* key, const char* value)
 {
 	if (!r || !key || !value) return 1;
