@@ -33,7 +33,7 @@ struct Bvh2
 };
 
 // Top-down binned surface-area-heuristic build (host, multi-threaded).
-void build_bvh2_sah(const std::vector<Triangle>& tris, int max_leaf_size, Bvh2& out);
+void build_bvh2_sah(const std::vector<Triangle>& tris, int max_leaf_size, Bvh2& out, float intersect_cost = 1.5f);
 
 // GPU layout #1: binary nodes holding BOTH children's boxes (64 bytes = 4 x 16-byte loads).
 //   n[0] = c0.lo.x c0.hi.x c0.lo.y c0.hi.y

@@ -35,7 +35,6 @@ constexpr int kItems = kChunk / kThreads;
 constexpr int kSmallThreads = 128;
 constexpr int kDepthLimit = 40;                         // below this depth splits fall back to halving by index (stack bound)
 constexpr int kPool = 32;                               // node indices a phase-2 block reserves per atomic
-constexpr float kIntersectCost = 1.5f;                  // bvh_host.cpp: kTraversalCost 1, kIntersectCost 1.5
 
 enum { KIND_LEAF = 0, KIND_SAH = 1, KIND_MEDIAN = 2 };
 
@@ -87,6 +86,7 @@ struct BuildArgs
 	float4* nodes;
 	Counters* counters;
 	int n, max_leaf;
+	float intersect_cost;          // SAH: cost of one triangle test relative to one node visit (bvh_host.cpp: 1.5)
 	int cap_tasks, cap_small, cap_chunks, cap_nodes;
 };
 
@@ -146,7 +146,7 @@ __device__ __forceinline__ void bins_add(int* bins, const float* lo, const float
 
 // One warp evaluates the 3 x 15 candidate planes of a node from its bins and decides leaf / split.
 // Mirrors Builder::build in bvh_host.cpp (first minimum in axis-major, bin-minor order wins).
-__device__ Choice warp_choose(const int* bins, int count, const float* blo, const float* bhi, const float* clo, const float* chi, int depth, int max_leaf)
+__device__ Choice warp_choose(const int* bins, int count, const float* blo, const float* bhi, const float* clo, const float* chi, int depth, int max_leaf, float kIntersectCost)
 {
 	const unsigned FULL = 0xffffffffu;
 	const int lane = threadIdx.x & 31;
@@ -416,7 +416,7 @@ __global__ void __launch_bounds__(128) k_split(BuildArgs A, const BuildTask* __r
 	if (ti >= n_tasks) return;
 	const BuildTask* t = tasks + ti;
 	const int count = t->end - t->begin;
-	const Choice ch = warp_choose(A.bins + (size_t)ti * kTaskBinWords, count, t->blo, t->bhi, t->clo, t->chi, t->depth, A.max_leaf);
+	const Choice ch = warp_choose(A.bins + (size_t)ti * kTaskBinWords, count, t->blo, t->bhi, t->clo, t->chi, t->depth, A.max_leaf, A.intersect_cost);
 	// count > kSmall > max_leaf: never a leaf here
 	int node = 0;
 	if (lane == 0)
@@ -616,7 +616,7 @@ __global__ void __launch_bounds__(kSmallThreads) k_build_small(BuildArgs A, int 
 			__syncthreads();
 			if (warp == 0)
 			{
-				const Choice ch = warp_choose(s_bins, count, s_cur.blo, s_cur.bhi, s_cur.clo, s_cur.chi, s_cur.depth, A.max_leaf);
+				const Choice ch = warp_choose(s_bins, count, s_cur.blo, s_cur.bhi, s_cur.clo, s_cur.chi, s_cur.depth, A.max_leaf, A.intersect_cost);
 				if (lane == 0)
 				{
 					s_kind = ch.kind;
@@ -778,7 +778,7 @@ void pack_tri_shade_gpu(const float* d_tris24, const int* d_material, int n, flo
 	k_pack_shade<<<std::min((n + kThreads - 1) / kThreads, 148 * 8), kThreads, 0, stream>>>(d_tris24, d_material, d_out, n);
 }
 
-int build_bvh2_gpu(const float* d_tris24, int n, int max_leaf_size, cudaStream_t stream, GpuBuildOutput& out, std::string& err)
+int build_bvh2_gpu(const float* d_tris24, int n, int max_leaf_size, float intersect_cost, cudaStream_t stream, GpuBuildOutput& out, std::string& err)
 {
 	out = GpuBuildOutput();
 	if (n <= 0) { err = "build_bvh2_gpu: no triangles"; return 1; }
@@ -789,6 +789,7 @@ int build_bvh2_gpu(const float* d_tris24, int n, int max_leaf_size, cudaStream_t
 	A.tris24 = d_tris24;
 	A.n = n;
 	A.max_leaf = std::max(1, std::min(max_leaf_size, 8));
+	A.intersect_cost = intersect_cost;
 	A.cap_tasks = n / kSmall + 4;
 	A.cap_small = std::max(4096, n / 64);
 	A.cap_chunks = n / kChunk + A.cap_tasks + 4;

@@ -30,7 +30,7 @@ struct GpuBuildOutput
 // d_tris24: n triangles x 24 floats on the DEVICE (v0 v1 v2 n0 n1 n2 uv0 uv1 uv2 — scene.h Triangle).
 // Returns 0 on success; on failure `err` says why (capacity overflow on adversarial input, CUDA error)
 // and the caller falls back to / reports the host builder.
-int build_bvh2_gpu(const float* d_tris24, int n, int max_leaf_size, cudaStream_t stream, GpuBuildOutput& out, std::string& err);
+int build_bvh2_gpu(const float* d_tris24, int n, int max_leaf_size, float intersect_cost, cudaStream_t stream, GpuBuildOutput& out, std::string& err);
 
 // packs the shading attributes (DeviceScene::tri_shade: 4 x float4 per triangle by global id) on the device
 void pack_tri_shade_gpu(const float* d_tris24, const int* d_material, int n, float4* d_out, cudaStream_t stream);

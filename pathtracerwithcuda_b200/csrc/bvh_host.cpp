@@ -14,7 +14,6 @@ namespace
 
 const int kBins = 16;
 const float kTraversalCost = 1.0f;
-const float kIntersectCost = 1.5f;
 
 inline void box_reset(Aabb& b)
 {
@@ -45,6 +44,7 @@ struct Builder
 	std::vector<PrimRef> prims;
 	std::vector<Bvh2Node>* nodes;
 	int max_leaf;
+	float kIntersectCost = 1.5f;
 
 	// builds the subtree for prims[first, first+count) into node `node_index`
 	void build(int node_index, int first, int count)
@@ -154,8 +154,9 @@ struct Builder
 
 } // namespace
 
-void build_bvh2_sah(const std::vector<Triangle>& tris, int max_leaf_size, Bvh2& out)
+void build_bvh2_sah(const std::vector<Triangle>& tris, int max_leaf_size, Bvh2& out, float intersect_cost)
 {
+	const float kIntersectCost = intersect_cost;
 	out.nodes.clear();
 	out.prim_order.clear();
 	const int n = (int)tris.size();
@@ -163,6 +164,7 @@ void build_bvh2_sah(const std::vector<Triangle>& tris, int max_leaf_size, Bvh2& 
 	Builder b;
 	b.nodes = &out.nodes;
 	b.max_leaf = std::max(1, std::min(max_leaf_size, 8));
+	b.kIntersectCost = intersect_cost;
 	b.prims.resize(n);
 	for (int i = 0; i < n; i++)
 	{

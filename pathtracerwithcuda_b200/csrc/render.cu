@@ -57,16 +57,25 @@ __device__ __forceinline__ float next_bounce_bound(const DeviceConfig& cfg, floa
 // k_generate — init_data_kernel + generate_ray_kernel fused (path_tracer_kernel.cu:275-379)
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_generate(PathState st, int* __restrict__ queue, int* __restrict__ counts, int n_counts,
-	CameraParams cam, DeviceConfig cfg, int pixel_count, int n_slots, int first_pass, int pass_stride)
+	CameraParams cam, DeviceConfig cfg, int pixel_count, int n_slots, int first_pass, int pass_stride, int tiles_x)
 {
 	const int total = pixel_count * n_slots;
 	int tid = blockIdx.x * blockDim.x + threadIdx.x;
 	// counts[0..n_counts) = live paths per depth; counts[n_counts..2*n_counts) = per-depth work-fetch cursors of the persistent extend kernel
 	if (tid < 2 * n_counts) counts[tid] = tid == 0 ? total : 0;
-	for (int id = tid; id < total; id += gridDim.x * blockDim.x)
+	for (int i = tid; i < total; i += gridDim.x * blockDim.x)
 	{
-		int slot = id / pixel_count;
-		int pixel = id - slot * pixel_count;
+		int slot = i / pixel_count;
+		int pixel = i - slot * pixel_count;
+		if (tiles_x > 0)
+		{
+			// queue position -> pixel in 8x4 tiles: the 32 rays of a warp cover a compact screen patch, so
+			// they visit nearly the same nodes (higher L1 hit rate, lanes finish together)
+			const int tile = pixel >> 5, within = pixel & 31;
+			const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
+			pixel = (ty * 4 + (within >> 3)) * (tiles_x * 8) + tx * 8 + (within & 7);
+		}
+		const int id = slot * pixel_count + pixel;
 		int seed = first_pass + slot * pass_stride;
 		float3 o, d;
 		generate_camera_ray(cam, pixel, seed, cfg.use_anti_alias != 0, o, d);
@@ -74,7 +83,7 @@ __global__ void __launch_bounds__(256) k_generate(PathState st, int* __restrict_
 		st.ray_d[id] = make_float4(d.x, d.y, d.z, next_bounce_bound(cfg, cfg.air_sigma_a, cfg.air_sigma_s, seed, pixel, 0));
 		st.throughput[id] = make_float4(1.0f, 1.0f, 1.0f, __int_as_float(-1));
 		st.radiance[id] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-		queue[id] = id;
+		queue[i] = id;
 	}
 }
 
@@ -349,6 +358,22 @@ __global__ void __launch_bounds__(128) k_extend(DeviceScene sc, PathState st, co
 // (plane * (1/d) - o/d) with an absolute + relative safety margin so culling stays conservative.
 // ------------------------------------------------------------------------------------------
 #define PTB_DONE ((int)0x80000000)
+
+// one 64-byte binary node: two 256-bit loads (sm_100 LDG.E.ENL2.256) instead of 3 x 128-bit + 1 x 64-bit.
+// (Routing the node fetches through the TEX data pipe was measured 2-7 % slower: profiles/r01_experiments.md.)
+__device__ __forceinline__ void load_node(const float4* np, float4& n0, float4& n1, float4& n2, float2& n3)
+{
+#ifndef PTB_NODE_LDG128
+	float z, w;
+	asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+		: "=f"(n0.x), "=f"(n0.y), "=f"(n0.z), "=f"(n0.w), "=f"(n1.x), "=f"(n1.y), "=f"(n1.z), "=f"(n1.w) : "l"(np));
+	asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+		: "=f"(n2.x), "=f"(n2.y), "=f"(n2.z), "=f"(n2.w), "=f"(n3.x), "=f"(n3.y), "=f"(z), "=f"(w) : "l"(np + 2));
+#else
+	n0 = __ldg(np + 0); n1 = __ldg(np + 1); n2 = __ldg(np + 2);
+	n3 = __ldg(reinterpret_cast<const float2*>(np + 3));
+#endif
+}
 #ifndef PTB_PERSISTENT_MIN_BLOCKS
 #define PTB_PERSISTENT_MIN_BLOCKS 8
 #endif
@@ -476,8 +501,9 @@ __global__ void __launch_bounds__(128, PTB_PERSISTENT_MIN_BLOCKS) k_extend_persi
 		{
 			if (COUNT) { n_nodes++; ray_nodes++; }
 			const float4* np = sc.bvh_nodes + (size_t)node * 4;
-			const float4 n0 = __ldg(np + 0), n1 = __ldg(np + 1), n2 = __ldg(np + 2);
-			const float2 n3 = __ldg(reinterpret_cast<const float2*>(np + 3));
+			float4 n0, n1, n2;
+			float2 n3;
+			load_node(np, n0, n1, n2, n3);
 			const float c0x0 = fmaf(n0.x, idir.x, noidir.x), c0x1 = fmaf(n0.y, idir.x, noidir.x);
 			const float c0y0 = fmaf(n0.z, idir.y, noidir.y), c0y1 = fmaf(n0.w, idir.y, noidir.y);
 			const float c0z0 = fmaf(n2.x, idir.z, noidir.z), c0z1 = fmaf(n2.y, idir.z, noidir.z);
@@ -488,8 +514,9 @@ __global__ void __launch_bounds__(128, PTB_PERSISTENT_MIN_BLOCKS) k_extend_persi
 			const float tmax0 = fminf(fminf(fmaxf(c0x0, c0x1), fmaxf(c0y0, c0y1)), fminf(fmaxf(c0z0, c0z1), best.t));
 			const float tmin1 = fmaxf(fmaxf(fminf(c1x0, c1x1), fminf(c1y0, c1y1)), fmaxf(fminf(c1z0, c1z1), 0.0f));
 			const float tmax1 = fminf(fminf(fmaxf(c1x0, c1x1), fmaxf(c1y0, c1y1)), fminf(fmaxf(c1z0, c1z1), best.t));
-			const bool h0 = fmaf(tmin0, PTB_SLACK_LO, -margin2) <= tmax0 * PTB_SLACK_HI;
-			const bool h1 = fmaf(tmin1, PTB_SLACK_LO, -margin2) <= tmax1 * PTB_SLACK_HI;
+			// conservative overlap test tmin * LO - margin <= tmax * HI, divided through by HI (one FMA per box)
+			const bool h0 = fmaf(tmin0, PTB_SLACK_LO / PTB_SLACK_HI, -margin2) <= tmax0;
+			const bool h1 = fmaf(tmin1, PTB_SLACK_LO / PTB_SLACK_HI, -margin2) <= tmax1;
 			const int child0 = __float_as_int(n3.x), child1 = __float_as_int(n3.y);
 			const bool both = h0 && h1;
 			const bool swap = tmin1 < tmin0;
@@ -554,21 +581,55 @@ __device__ __forceinline__ float3 sample_texture(const DeviceTexture& tex, float
 	return sample_image(tex.pixels, tex.width, tex.height, ux, 1.0f - uy, use_bilinear);
 }
 
+// SORT: the 128 queue entries a block handles per iteration are first reordered in shared memory by
+// (miss | sphere | triangle material), so warps shade runs of one material ("shade-by-material"): the
+// material fetch, texture sampling and the conductor / dielectric Fresnel paths stop diverging inside a
+// warp.  The stochastic reflect / refract / diffuse choice still diverges — it is decided inside.
+template <bool SORT>
 __global__ void __launch_bounds__(128) k_shade(DeviceScene sc, PathState st, DeviceConfig cfg, int depth, int pixel_count, int first_pass, int pass_stride,
 	const int* __restrict__ queue_in, const int* __restrict__ count_in, int* __restrict__ queue_out, int* __restrict__ count_out)
 {
+	__shared__ int s_ids[SORT ? 128 : 1];
+	__shared__ int s_hist[SORT ? 16 : 1];
 	const int count = *count_in;
 	const unsigned lane = threadIdx.x & 31;
-	// warp-uniform trip count so the ballots below are convergent
-	for (int base = (blockIdx.x * blockDim.x + threadIdx.x) - lane; base < count; base += gridDim.x * blockDim.x)
+	// block-uniform trip count (barriers in the SORT path), hence warp-uniform: the ballots below are convergent
+	for (int block_base = blockIdx.x * blockDim.x; block_base < count; block_base += gridDim.x * blockDim.x)
 	{
-		int i = base + lane;
+		int i = block_base + threadIdx.x;
 		bool valid = i < count;
 		bool alive = false;
 		int id = 0;
+		if (SORT)
+		{
+			int key = 15;
+			if (threadIdx.x < 16) s_hist[threadIdx.x] = 0;
+			__syncthreads();
+			if (valid)
+			{
+				id = queue_in[i];
+				const int prim = __float_as_int(st.hit[id].w);
+				key = prim == -1 ? 0 : (prim < -1 ? 1 : 2 + min(__float_as_int(__ldg(&sc.tri_shade[(size_t)prim * 4 + 3]).w), 12));
+			}
+			// counting sort over 16 keys: rank inside the key by warp-aggregated atomics
+			const unsigned peers = __match_any_sync(0xffffffffu, key);
+			const int leader = __ffs(peers) - 1;
+			int base_in_key = 0;
+			if ((int)lane == leader) base_in_key = atomicAdd(&s_hist[key], __popc(peers));
+			base_in_key = __shfl_sync(0xffffffffu, base_in_key, leader) + __popc(peers & ((1u << lane) - 1u));
+			__syncthreads();
+			int before = 0;
+			for (int k = 0; k < key; k++) before += s_hist[k];
+			s_ids[before + base_in_key] = valid ? id : -1;
+			__syncthreads();
+			id = s_ids[threadIdx.x];
+			valid = id >= 0;
+			if (!valid) id = 0;
+			__syncthreads();
+		}
+		else if (valid) id = queue_in[i];
 		if (valid)
 		{
-			id = queue_in[i];
 			int slot = id / pixel_count;
 			int pixel_index = id - slot * pixel_count;
 			int seed = first_pass + slot * pass_stride;
@@ -846,6 +907,10 @@ struct ptb_renderer
 	int count_traversal = 0;
 	std::string bvh_builder = "gpu_sah";   // "gpu_sah" (csrc/bvh_build.cu) | "host_sah" (csrc/bvh_host.cpp)
 	int bvh_layout = 2;
+	int bvh_max_leaf = 8;                  // binary layout; the wide layout holds <= 3 per leaf slot
+	float bvh_intersect_cost = 0.8f;       // SAH cost of a triangle test relative to a node visit (measured optimum on c2, profiles/r01_experiments.md)
+	int sort_by_material = 0;              // block-local material sort in k_shade (measured: profiles/r01_experiments.md)
+	int tile_order = 1;                    // camera rays enter the first queue in 8x4 pixel tiles
 	// facts about the last acceleration-structure build (ptb_bvh_info)
 	int bvh_built_on_gpu = 0, bvh_levels = 0, bvh_small_tasks = 0, bvh_max_depth = 0;
 	double bvh_build_ms = 0.0, scene_upload_ms = 0.0;
@@ -1085,14 +1150,14 @@ int upload_scene(ptb_renderer* r)
 	r->bvh_built_on_gpu = 0; r->bvh_levels = 0; r->bvh_small_tasks = 0; r->bvh_max_depth = 0; r->bvh_build_ms = 0.0; r->bvh_note.clear();
 
 	// acceleration structure over all meshes' world-space triangles
-	const int max_leaf = r->bvh_layout == 8 ? 3 : 4;   // <= 3 triangles per leaf slot of a wide node
+	const int max_leaf = r->bvh_layout == 8 ? 3 : r->bvh_max_leaf;   // <= 3 triangles per leaf slot of a wide node
 	Bvh2 bvh;
 	bool have_device_bvh2 = false;
 	if (r->bvh_builder != "host_sah" && n_tris > 0)
 	{
 		GpuBuildOutput gb;
 		std::string why;
-		if (build_bvh2_gpu(d_tris24, n_tris, max_leaf, r->stream, gb, why) == 0)
+		if (build_bvh2_gpu(d_tris24, n_tris, max_leaf, r->bvh_intersect_cost, r->stream, gb, why) == 0)
 		{
 			r->bvh_built_on_gpu = 1; r->bvh_levels = gb.levels; r->bvh_small_tasks = gb.small_tasks; r->bvh_max_depth = gb.max_depth; r->bvh_build_ms = gb.build_ms;
 			if (gb.max_depth >= PTB_STACK_SIZE)
@@ -1129,7 +1194,7 @@ int upload_scene(ptb_renderer* r)
 	if (!have_device_bvh2 && !(r->bvh_built_on_gpu && r->bvh_layout == 8))
 	{
 		const auto t0 = std::chrono::steady_clock::now();
-		build_bvh2_sah(s.triangles, max_leaf, bvh);
+		build_bvh2_sah(s.triangles, max_leaf, bvh, r->bvh_intersect_cost);
 		r->bvh_build_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
 	}
 	if (r->bvh_layout == 8)
@@ -1272,7 +1337,8 @@ int enqueue_batch(ptb_renderer* r, ptb_renderer::BatchContext& ctx, cudaEvent_t 
 	const int n_counts = r->cfg.max_tracer_depth + 2;
 	const bool prof = r->profile_stages != 0;
 	cudaStream_t stream = ctx.stream;
-	k_generate<<<grid_for(r, total, 256, 8), 256, 0, stream>>>(ctx.st, ctx.queue[0], ctx.counts, n_counts, cp, dc, px, n_slots, first_pass, stride);
+	const int tiles_x = (r->tile_order && r->cfg.width % 8 == 0 && r->cfg.height % 4 == 0) ? r->cfg.width / 8 : 0;
+	k_generate<<<grid_for(r, total, 256, 8), 256, 0, stream>>>(ctx.st, ctx.queue[0], ctx.counts, n_counts, cp, dc, px, n_slots, first_pass, stride, tiles_x);
 	r->stats.kernel_launches++;
 	for (int depth = 0; depth < r->cfg.max_tracer_depth; depth++)
 	{
@@ -1287,7 +1353,8 @@ int enqueue_batch(ptb_renderer* r, ptb_renderer::BatchContext& ctx, cudaEvent_t 
 		}
 		launch_extend(r, stream, total, ctx.st, qin, ctx.counts + depth, ctx.counts + n_counts + depth);
 		if (prof) cudaEventRecord(e1, stream);
-		k_shade<<<grid_for(r, total, 128, 16), 128, 0, stream>>>(r->dscene, ctx.st, dc, depth, px, first_pass, stride, qin, ctx.counts + depth, qout, ctx.counts + depth + 1);
+		if (r->sort_by_material) k_shade<true><<<grid_for(r, total, 128, 16), 128, 0, stream>>>(r->dscene, ctx.st, dc, depth, px, first_pass, stride, qin, ctx.counts + depth, qout, ctx.counts + depth + 1);
+		else k_shade<false><<<grid_for(r, total, 128, 16), 128, 0, stream>>>(r->dscene, ctx.st, dc, depth, px, first_pass, stride, qin, ctx.counts + depth, qout, ctx.counts + depth + 1);
 		r->stats.kernel_launches += 2;
 	}
 	if (prev_accumulated) PTB_CUDA(cudaStreamWaitEvent(stream, prev_accumulated, 0));
@@ -1648,7 +1715,7 @@ int ptb_generate_rays(ptb_renderer* r, int pass, float* out_rays6)
 {
 	if (!r || r->host_only) { set_error("[Error]no CUDA device"); return 1; }
 	const int px = r->pixel_count;
-	k_generate<<<grid_for(r, px, 256, 8), 256, 0, r->stream>>>(r->st, r->queue[0], r->counts, r->cfg.max_tracer_depth + 2, camera_params(r->cam), device_config(r), px, 1, pass, 1);
+	k_generate<<<grid_for(r, px, 256, 8), 256, 0, r->stream>>>(r->st, r->queue[0], r->counts, r->cfg.max_tracer_depth + 2, camera_params(r->cam), device_config(r), px, 1, pass, 1, 0);
 	std::vector<float4> o(px), d(px);
 	PTB_CUDA(cudaMemcpyAsync(o.data(), r->st.ray_o, (size_t)px * sizeof(float4), cudaMemcpyDeviceToHost, r->stream));
 	PTB_CUDA(cudaMemcpyAsync(d.data(), r->st.ray_d, (size_t)px * sizeof(float4), cudaMemcpyDeviceToHost, r->stream));
@@ -1667,12 +1734,12 @@ int ptb_capture_rays(ptb_renderer* r, int pass, int depth, int32_t* out_pixels, 
 	if (!r->scene_loaded) { set_error("[Error]no scene loaded"); return -1; }
 	const int px = r->pixel_count;
 	DeviceConfig dc = device_config(r);
-	k_generate<<<grid_for(r, px, 256, 8), 256, 0, r->stream>>>(r->st, r->queue[0], r->counts, r->cfg.max_tracer_depth + 2, camera_params(r->cam), dc, px, 1, pass, 1);
+	k_generate<<<grid_for(r, px, 256, 8), 256, 0, r->stream>>>(r->st, r->queue[0], r->counts, r->cfg.max_tracer_depth + 2, camera_params(r->cam), dc, px, 1, pass, 1, 0);
 	int d = 0;
 	for (; d < depth && d < r->cfg.max_tracer_depth; d++)
 	{
 		launch_extend(r, r->stream, px, r->st, r->queue[d & 1], r->counts + d, r->counts + (r->cfg.max_tracer_depth + 2) + d);
-		k_shade<<<grid_for(r, px, 128, 16), 128, 0, r->stream>>>(r->dscene, r->st, dc, d, px, pass, 1, r->queue[d & 1], r->counts + d, r->queue[(d + 1) & 1], r->counts + d + 1);
+		k_shade<false><<<grid_for(r, px, 128, 16), 128, 0, r->stream>>>(r->dscene, r->st, dc, d, px, pass, 1, r->queue[d & 1], r->counts + d, r->queue[(d + 1) & 1], r->counts + d + 1);
 	}
 	int count = 0;
 	if (cudaMemcpyAsync(&count, r->counts + d, sizeof(int), cudaMemcpyDeviceToHost, r->stream) != cudaSuccess || cudaStreamSynchronize(r->stream) != cudaSuccess)
@@ -1909,6 +1976,10 @@ int ptb_set_option(ptb_renderer* r, const char* key, const char* value)
 		r->bvh_builder = v;   // takes effect at the next ptb_load_scene
 		return 0;
 	}
+	if (k == "bvh_max_leaf") { int n = atoi(value); if (n < 1 || n > 8) { set_error("[Error]bvh_max_leaf must be in 1..8"); return 1; } r->bvh_max_leaf = n; return 0; }
+	if (k == "bvh_intersect_cost") { float c = (float)atof(value); if (!(c > 0.0f)) { set_error("[Error]bvh_intersect_cost must be > 0"); return 1; } r->bvh_intersect_cost = c; return 0; }
+	if (k == "tile_order") { r->tile_order = atoi(value); return 0; }
+	if (k == "sort_by_material") { r->sort_by_material = atoi(value); return 0; }
 	if (k == "extend_persistent") { r->extend_persistent = atoi(value); return 0; }
 	if (k == "tune_refill") { r->tune_refill = atoi(value); return 0; }
 	if (k == "tune_leaf") { r->tune_leaf = atoi(value); return 0; }

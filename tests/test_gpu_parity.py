@@ -233,3 +233,20 @@ def test_bvh_layouts_agree(workload_root):
     assert np.array_equal(res[2][3].view(np.uint32), res[8][3].view(np.uint32))
     # the wide tree visits far fewer nodes per ray
     assert res[8][4]["nodes_visited"] < 0.6 * res[2][4]["nodes_visited"]
+
+
+def test_scheduling_options_do_not_change_the_image(workload_root):
+    """Queue order (8x4 pixel tiles), the block-local material sort of k_shade and the number of overlapped
+    streams only reorder independent paths: the accumulated image must be bit-identical."""
+    root, w = workload_root("mix", width=96, height=72)
+    ref = None
+    for opts in (dict(), dict(tile_order=0), dict(sort_by_material=1), dict(sort_by_material=1, tile_order=0, streams_in_flight=1),
+                 dict(extend_persistent=0), dict(bvh_max_leaf=2, bvh_intersect_cost=1.5)):
+        r = gpu_renderer(w, root, **opts)
+        r.set_camera(ptb.default_camera(w["width"], w["height"], w["aperture"], w["focal"]))
+        r.render(5)
+        img = r.image_f32().copy()
+        r.close()
+        if ref is None:
+            ref = img
+        assert np.array_equal(ref.view(np.uint32), img.view(np.uint32)), opts
