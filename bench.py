@@ -205,10 +205,14 @@ def run_ptb200(args, w, root, rank, local_rank, world):
     from pathtracerwithcuda_b200.distributed import CudaBackend, ShardedRenderer
 
     dist = None
+    saved_stdout_fd = None
     if world > 1:
-        # keep stdout to the one JSON line: NCCL prints its version banner there at NCCL_DEBUG=VERSION
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"
+        # keep stdout to the one JSON line: NCCL writes its version banner / debug lines to stdout (at any
+        # NCCL_DEBUG level >= VERSION, when the communicator is created lazily by the first collective), so
+        # file descriptor 1 points at stderr until the result line is printed
+        sys.stdout.flush()
+        saved_stdout_fd = os.dup(1)
+        os.dup2(2, 1)
         import torch.distributed as dist
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
@@ -338,7 +342,13 @@ def run_ptb200(args, w, root, rank, local_rank, world):
                 "ray_segments": int(seg_total), "total_passes": int(total_passes)}
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(w, root)
+        if saved_stdout_fd is not None:
+            sys.stdout.flush()
+            os.dup2(saved_stdout_fd, 1)
         print(json.dumps(line))
+        sys.stdout.flush()
+        if saved_stdout_fd is not None:
+            os.dup2(2, 1)
     r.close()
     if dist is not None:
         dist.barrier()
