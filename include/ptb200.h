@@ -171,6 +171,21 @@ int ptb_bvh_download(ptb_renderer* r, float* out_nodes16, int32_t* out_leaf_orde
  * "profile_stages" = "0"|"1"; "count_traversal" = "0"|"1"; "sort_by_material" = "0"|"1". */
 int ptb_set_option(ptb_renderer* r, const char* key, const char* value);
 
+/* ---- live scene edits -----------------------------------------------------------------------
+ * What path_tracer::render_ui does between passes (Core/path_tracer.cpp:109-369) through
+ * scene_parser::set_sphere_device / set_mesh_material_device / set_mesh_transform_device /
+ * set_mesh_rotate + apply_mesh_rotate (Core/scene_parser.cpp:645-673, Core/triangle_mesh.cpp:252-426),
+ * followed by clear().  Same arithmetic as the reference (world = T*S * rotated-local, normals through the
+ * inverse transpose, re-normalised); the acceleration structure is REBUILT on the device instead of
+ * re-transforming stale boxes (Bvh/bvh.cpp:332-356).  sphere100: center[3], radius, ptb_material.
+ * ptb_set_mesh_material ignores a list whose length differs from the mesh's material count, like the
+ * reference.  The scale is clamped to >= 1e-6 like the UI does.  Every edit resets the accumulation. */
+int ptb_set_sphere(ptb_renderer* r, int index, const void* sphere100);
+int ptb_set_mesh_material(ptb_renderer* r, int mesh, const ptb_material* mats, int n);
+int ptb_set_mesh_transform(ptb_renderer* r, int mesh, const float* position3, const float* scale3);
+int ptb_apply_mesh_rotate(ptb_renderer* r, int mesh, const float* rotate_degrees3);
+int ptb_get_mesh_placement(ptb_renderer* r, int mesh, float* out_position3, float* out_scale3, float* out_rotate3, int* out_first_triangle, int* out_triangle_count, int* out_first_material, int* out_material_count);
+
 /* ---- loaded-scene introspection (flat host copies; used by the parity tests) ------------- */
 int ptb_scene_counts(ptb_renderer* r, int* n_triangles, int* n_materials, int* n_spheres, int* n_textures, int* cube_length, int* n_meshes);
 /* per triangle 24 floats: v0 v1 v2 n0 n1 n2 uv0 uv1 uv2 (Core/triangle.h:11-25) + material index */

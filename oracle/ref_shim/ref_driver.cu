@@ -254,6 +254,63 @@ int ref_get_spheres(void* out100)
 	return 0;
 }
 
+/* ---- live scene edits, driven the way path_tracer::render_ui does (Core/path_tracer.cpp:109-369):
+ * scene_parser::set_sphere_device / set_mesh_material_device / set_mesh_transform_device (with the
+ * builder's own bvh update function and the UI's scale clamp) / set_mesh_rotate + apply_mesh_rotate,
+ * each followed by reset_image like path_tracer::clear(). */
+int ref_set_sphere(int index, const void* sphere100)
+{
+	if (!g_scene || index < 0 || index >= g_scene->get_sphere_num()) return 1;
+	cudaDeviceSynchronize();
+	sphere s;
+	memcpy(&s, sphere100, sizeof(sphere));
+	g_scene->set_sphere_device(index, s);
+	if (g_image) reset_image(g_image);
+	return 0;
+}
+
+int ref_set_mesh_materials(int index, const void* mats84, int n)
+{
+	if (!g_scene || index < 0 || index >= g_scene->get_mesh_num()) return 1;
+	cudaDeviceSynchronize();
+	std::vector<material> mats(n);
+	memcpy(mats.data(), mats84, (size_t)n * sizeof(material));
+	g_scene->set_mesh_material_device(index, mats);
+	if (g_image) reset_image(g_image);
+	return 0;
+}
+
+int ref_set_mesh_transform(int index, const float* position3, const float* scale3)
+{
+	if (!g_scene || index < 0 || index >= g_scene->get_mesh_num()) return 1;
+	cudaDeviceSynchronize();
+	bvh_build_method build_method = g_config->get_config_device_ptr()->bvh_build;
+	std::function<void(const glm::mat4&, const glm::mat4&, bvh_node_device*, bvh_node_device*)> bvh_update_function = auto_bvh_update(build_method);
+	float3 position = make_float3(position3[0], position3[1], position3[2]);
+	float3 scale = make_float3(scale3[0], scale3[1], scale3[2]);
+	g_scene->set_mesh_transform_device(index, position,
+		clamp(scale, make_float3(0.000001f, 0.000001f, 0.000001f), make_float3(INFINITY, INFINITY, INFINITY)), bvh_update_function);
+	if (g_image) reset_image(g_image);
+	return 0;
+}
+
+int ref_apply_mesh_rotate(int index, const float* rotate3)
+{
+	if (!g_scene || index < 0 || index >= g_scene->get_mesh_num()) return 1;
+	cudaDeviceSynchronize();
+	g_scene->set_mesh_rotate(index, make_float3(rotate3[0], rotate3[1], rotate3[2]));
+	g_scene->apply_mesh_rotate(index);
+	if (g_image) reset_image(g_image);
+	return 0;
+}
+
+int ref_mesh_material_counts(int* out)
+{
+	if (!g_scene) return 1;
+	for (int i = 0; i < g_scene->get_mesh_num(); i++) out[i] = g_scene->m_triangle_mesh.m_mesh_material_num[i];
+	return 0;
+}
+
 int ref_struct_sizes(int* out8)
 {
 	out8[0] = sizeof(ray); out8[1] = sizeof(material); out8[2] = sizeof(sphere); out8[3] = sizeof(triangle);

@@ -210,6 +210,34 @@ class RefLib:
             self.lib.ref_get_spheres(out.ctypes.data_as(ctypes.c_void_p))
         return out
 
+    # -- live edits, as path_tracer::render_ui issues them (Core/path_tracer.cpp:109-369) -------
+    def set_sphere(self, index, sphere100):
+        a = np.ascontiguousarray(sphere100)
+        assert a.nbytes == 100
+        if self.lib.ref_set_sphere(int(index), a.ctypes.data_as(ctypes.c_void_p)) != 0:
+            raise RuntimeError("ref_set_sphere failed")
+
+    def set_mesh_materials(self, mesh, mats84):
+        a = np.ascontiguousarray(mats84)
+        assert a.nbytes % 84 == 0
+        if self.lib.ref_set_mesh_materials(int(mesh), a.ctypes.data_as(ctypes.c_void_p), a.nbytes // 84) != 0:
+            raise RuntimeError("ref_set_mesh_materials failed")
+
+    def set_mesh_transform(self, mesh, position, scale):
+        p, s = np.ascontiguousarray(position, np.float32), np.ascontiguousarray(scale, np.float32)
+        if self.lib.ref_set_mesh_transform(int(mesh), p.ctypes.data_as(ctypes.c_void_p), s.ctypes.data_as(ctypes.c_void_p)) != 0:
+            raise RuntimeError("ref_set_mesh_transform failed")
+
+    def apply_mesh_rotate(self, mesh, rotate_degrees):
+        a = np.ascontiguousarray(rotate_degrees, np.float32)
+        if self.lib.ref_apply_mesh_rotate(int(mesh), a.ctypes.data_as(ctypes.c_void_p)) != 0:
+            raise RuntimeError("ref_apply_mesh_rotate failed")
+
+    def mesh_material_counts(self):
+        out = np.zeros(self.lib.ref_num_meshes(), np.int32)
+        self.lib.ref_mesh_material_counts(out.ctypes.data_as(ctypes.c_void_p))
+        return out.tolist()
+
     def trace_batch(self, rays6):
         rays = np.ascontiguousarray(rays6, np.float32).reshape(-1, 6)
         n = rays.shape[0]

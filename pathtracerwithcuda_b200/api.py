@@ -106,6 +106,11 @@ def load_library():
     L.ptb_get_stats.argtypes = [vp, ctypes.POINTER(Stats)]
     L.ptb_get_depth_profile.argtypes = [vp, ci, vp, vp]
     L.ptb_set_option.argtypes = [vp, cp, cp]
+    L.ptb_set_sphere.argtypes = [vp, ci, vp]
+    L.ptb_set_mesh_material.argtypes = [vp, ci, vp, ci]
+    L.ptb_set_mesh_transform.argtypes = [vp, ci, vp, vp]
+    L.ptb_apply_mesh_rotate.argtypes = [vp, ci, vp]
+    L.ptb_get_mesh_placement.argtypes = [vp, ci, vp, vp, vp] + [ctypes.POINTER(ci)] * 4
     L.ptb_bvh_info.argtypes = [vp, vp, vp]
     L.ptb_bvh_leaf_labels.argtypes = [vp, vp]
     L.ptb_bvh_download.argtypes = [vp, vp, vp]
@@ -218,6 +223,34 @@ class Renderer:
         for f in range(6):
             self._check(self.lib.ptb_scene_cubemap_face(self.handle, f, _ptr(out[f])))
         return out
+
+    # -- live edits (Core/path_tracer.cpp:109-369) ----------------------------------------------
+    def set_sphere(self, index, sphere):
+        a = np.ascontiguousarray(np.asarray(sphere, SPHERE_DTYPE).reshape(1))
+        self._check(self.lib.ptb_set_sphere(self.handle, int(index), _ptr(a)))
+
+    def set_mesh_material(self, mesh, mats):
+        a = np.ascontiguousarray(np.asarray(mats, MATERIAL_DTYPE).reshape(-1))
+        self._check(self.lib.ptb_set_mesh_material(self.handle, int(mesh), _ptr(a), int(a.size)))
+
+    def set_mesh_transform(self, mesh, position, scale):
+        p, s = np.ascontiguousarray(position, np.float32), np.ascontiguousarray(scale, np.float32)
+        self._check(self.lib.ptb_set_mesh_transform(self.handle, int(mesh), _ptr(p), _ptr(s)))
+
+    def apply_mesh_rotate(self, mesh, rotate_degrees):
+        a = np.ascontiguousarray(rotate_degrees, np.float32)
+        self._check(self.lib.ptb_apply_mesh_rotate(self.handle, int(mesh), _ptr(a)))
+
+    def mesh_placement(self, mesh):
+        p, s, ro = np.zeros(3, np.float32), np.zeros(3, np.float32), np.zeros(3, np.float32)
+        first, count, mfirst, mcount = ctypes.c_int(), ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+        self._check(self.lib.ptb_get_mesh_placement(self.handle, int(mesh), _ptr(p), _ptr(s), _ptr(ro), ctypes.byref(first), ctypes.byref(count),
+                                                    ctypes.byref(mfirst), ctypes.byref(mcount)))
+        return {"position": p, "scale": s, "rotate": ro, "first_triangle": first.value, "triangle_count": count.value,
+                "first_material": mfirst.value, "material_count": mcount.value}
+
+    def mesh_material_counts(self):
+        return [self.mesh_placement(i)["material_count"] for i in range(self.scene_counts()["meshes"])]
 
     # -- camera --------------------------------------------------------------------------------
     def camera(self):

@@ -924,7 +924,9 @@ struct ptb_renderer
 
 	// scene on device
 	DeviceScene dscene;
-	std::vector<void*> scene_allocs;
+	std::vector<void*> scene_allocs;      // textures, cube map
+	std::vector<void*> geometry_allocs;   // triangles, BVH, shading attributes (rebuilt by mesh edits)
+	std::vector<void*> material_allocs;   // materials + spheres (rewritten by material / sphere edits)
 	int64_t bvh_nodes = 0, bvh_bytes = 0;
 
 	// work buffers
@@ -1041,12 +1043,12 @@ void free_work_buffers(ptb_renderer* r)
 }
 
 template <class T>
-int upload(ptb_renderer* r, const T* host, size_t count, const T** out)
+int upload(ptb_renderer* r, const T* host, size_t count, const T** out, std::vector<void*>* group = nullptr)
 {
 	void* d = nullptr;
 	size_t bytes = std::max<size_t>(count * sizeof(T), 16);
 	PTB_CUDA(cudaMalloc(&d, bytes));
-	r->scene_allocs.push_back(d);
+	(group ? *group : r->scene_allocs).push_back(d);
 	if (count) PTB_CUDA(cudaMemcpyAsync(d, host, count * sizeof(T), cudaMemcpyHostToDevice, r->stream));
 	*out = (const T*)d;
 	return 0;
@@ -1055,7 +1057,9 @@ int upload(ptb_renderer* r, const T* host, size_t count, const T** out)
 void release_scene_device(ptb_renderer* r)
 {
 	for (void* p : r->scene_allocs) cudaFree(p);
-	r->scene_allocs.clear();
+	for (void* p : r->geometry_allocs) cudaFree(p);
+	for (void* p : r->material_allocs) cudaFree(p);
+	r->scene_allocs.clear(); r->geometry_allocs.clear(); r->material_allocs.clear();
 	memset(&r->dscene, 0, sizeof(r->dscene));
 	r->bvh_nodes = r->bvh_bytes = 0;
 }
@@ -1132,21 +1136,25 @@ int download_bvh2(const GpuBuildOutput& gb, Bvh2& out)
 	return 0;
 }
 
-int upload_scene(ptb_renderer* r)
+// triangles, acceleration structure and shading attributes (re-run by mesh edits: the BVH is REBUILT on the
+// device — 5-65 ms for 0.15-5 M triangles — where the reference only re-transforms the old boxes,
+// Bvh/bvh.cpp:332-356)
+int upload_geometry(ptb_renderer* r)
 {
-	release_scene_device(r);
+	for (void* p : r->geometry_allocs) cudaFree(p);
+	r->geometry_allocs.clear();
 	const HostScene& s = r->scene;
 	DeviceScene& ds = r->dscene;
-	memset(&ds, 0, sizeof(ds));
+	ds.bvh_nodes = nullptr; ds.tri_isect = nullptr; ds.tri_shade = nullptr;
+	std::vector<void*>* G = &r->geometry_allocs;
 
 	// raw triangles + material indices on the device: the builder, the leaf-order emitter and the
 	// shading-attribute packer all read them there
-	const auto t_upload0 = std::chrono::steady_clock::now();
 	const int n_tris = (int)s.triangles.size();
 	const float* d_tris24 = nullptr;
 	const int* d_material = nullptr;
-	if (upload(r, (const float*)s.triangles.data(), (size_t)n_tris * 24, &d_tris24)) return 1;
-	if (upload(r, s.triangle_material.data(), (size_t)n_tris, &d_material)) return 1;
+	if (upload(r, (const float*)s.triangles.data(), (size_t)n_tris * 24, &d_tris24, G)) return 1;
+	if (upload(r, s.triangle_material.data(), (size_t)n_tris, &d_material, G)) return 1;
 	r->bvh_built_on_gpu = 0; r->bvh_levels = 0; r->bvh_small_tasks = 0; r->bvh_max_depth = 0; r->bvh_build_ms = 0.0; r->bvh_note.clear();
 
 	// acceleration structure over all meshes' world-space triangles
@@ -1175,7 +1183,7 @@ int upload_scene(ptb_renderer* r)
 			}
 			else
 			{
-				r->scene_allocs.push_back(gb.nodes); r->scene_allocs.push_back(gb.tri_isect);
+				G->push_back(gb.nodes); G->push_back(gb.tri_isect);
 				cudaFree(gb.prim_order);
 				ds.bvh_nodes = gb.nodes; ds.tri_isect = gb.tri_isect;
 				r->bvh_nodes = gb.n_nodes;
@@ -1202,8 +1210,8 @@ int upload_scene(ptb_renderer* r)
 		GpuBvh8 wide;
 		build_bvh8(bvh, s.triangles, wide);
 		if (wide.max_depth > PTB_STACK_SIZE8) { set_error("[Error]BVH8 too deep for the traversal stack"); return 1; }
-		if (upload(r, (const float4*)wide.nodes.data(), wide.nodes.size() / 4, &ds.bvh_nodes)) return 1;
-		if (upload(r, (const float4*)wide.tris.data(), wide.tris.size() / 4, &ds.tri_isect)) return 1;
+		if (upload(r, (const float4*)wide.nodes.data(), wide.nodes.size() / 4, &ds.bvh_nodes, G)) return 1;
+		if (upload(r, (const float4*)wide.tris.data(), wide.tris.size() / 4, &ds.tri_isect, G)) return 1;
 		r->bvh_nodes = (int64_t)wide.nodes.size() / 20;
 		r->bvh_bytes = (int64_t)(wide.nodes.size() + wide.tris.size()) * 4;
 	}
@@ -1211,8 +1219,8 @@ int upload_scene(ptb_renderer* r)
 	{
 		GpuBvh2 flat;
 		flatten_bvh2(bvh, s.triangles, flat);
-		if (upload(r, (const float4*)flat.nodes.data(), flat.nodes.size() / 4, &ds.bvh_nodes)) return 1;
-		if (upload(r, (const float4*)flat.tris.data(), flat.tris.size() / 4, &ds.tri_isect)) return 1;
+		if (upload(r, (const float4*)flat.nodes.data(), flat.nodes.size() / 4, &ds.bvh_nodes, G)) return 1;
+		if (upload(r, (const float4*)flat.tris.data(), flat.tris.size() / 4, &ds.tri_isect, G)) return 1;
 		r->bvh_nodes = (int64_t)flat.nodes.size() / 16;
 		r->bvh_bytes = (int64_t)(flat.nodes.size() + flat.tris.size()) * 4;
 	}
@@ -1224,11 +1232,22 @@ int upload_scene(ptb_renderer* r)
 	{
 		float4* d_shade = nullptr;
 		PTB_CUDA(cudaMalloc(&d_shade, std::max<size_t>((size_t)n_tris * 64, 16)));
-		r->scene_allocs.push_back(d_shade);
+		G->push_back(d_shade);
 		pack_tri_shade_gpu(d_tris24, d_material, n_tris, d_shade, r->stream);
 		ds.tri_shade = d_shade;
 	}
+	PTB_CUDA(cudaStreamSynchronize(r->stream));
+	PTB_CUDA(cudaGetLastError());
+	return 0;
+}
 
+// mesh materials followed by one material per sphere, and the sphere array (re-run by material / sphere edits)
+int upload_materials(ptb_renderer* r)
+{
+	for (void* p : r->material_allocs) cudaFree(p);
+	r->material_allocs.clear();
+	const HostScene& s = r->scene;
+	DeviceScene& ds = r->dscene;
 	std::vector<DeviceMaterial> mats;
 	for (auto& m : s.materials) mats.push_back(pack_material(m));
 	ds.sphere_material_base = (int)mats.size();
@@ -1238,9 +1257,22 @@ int upload_scene(ptb_renderer* r)
 		mats.push_back(pack_material(sp.mat));
 		spheres.push_back(make_float4(sp.center.x, sp.center.y, sp.center.z, sp.radius));
 	}
-	if (upload(r, mats.data(), mats.size(), &ds.materials)) return 1;
-	if (upload(r, spheres.data(), spheres.size(), &ds.spheres)) return 1;
+	if (upload(r, mats.data(), mats.size(), &ds.materials, &r->material_allocs)) return 1;
+	if (upload(r, spheres.data(), spheres.size(), &ds.spheres, &r->material_allocs)) return 1;
 	ds.n_spheres = (int)spheres.size();
+	PTB_CUDA(cudaStreamSynchronize(r->stream));
+	return 0;
+}
+
+int upload_scene(ptb_renderer* r)
+{
+	release_scene_device(r);
+	const HostScene& s = r->scene;
+	DeviceScene& ds = r->dscene;
+	memset(&ds, 0, sizeof(ds));
+	const auto t_upload0 = std::chrono::steady_clock::now();
+	if (upload_geometry(r)) return 1;
+	if (upload_materials(r)) return 1;
 
 	std::vector<DeviceTexture> textures;
 	for (auto& t : s.textures)
@@ -1658,6 +1690,74 @@ int ptb_clear(ptb_renderer* r)
 	for (size_t c = 1; c < r->contexts.size(); c++) PTB_CUDA(cudaStreamSynchronize(r->contexts[c].stream));
 	PTB_CUDA(cudaMemsetAsync(r->image_sum, 0, (size_t)r->pixel_count * 3 * sizeof(float), r->stream));
 	PTB_CUDA(cudaStreamSynchronize(r->stream));
+	return 0;
+}
+
+// ---- live scene edits (the reference mutates managed scene memory between passes,
+// Core/path_tracer.cpp:109-369).  Each edit resets the accumulation like path_tracer::render_ui -> clear().
+static int edit_prologue(ptb_renderer* r)
+{
+	if (!r) { set_error("[Error]null renderer"); return 1; }
+	if (!r->scene_loaded) { set_error("[Error]no scene loaded"); return 1; }
+	if (!r->host_only)
+	{
+		cudaSetDevice(r->device);
+		if (sync_all_streams(r)) return 1;
+	}
+	return 0;
+}
+
+int ptb_set_sphere(ptb_renderer* r, int index, const void* sphere100)
+{
+	if (edit_prologue(r)) return 1;
+	if (index < 0 || index >= (int)r->scene.spheres.size() || !sphere100) { set_error("[Error]sphere index out of range"); return 1; }
+	memcpy(&r->scene.spheres[index], sphere100, sizeof(Sphere));
+	if (!r->host_only && upload_materials(r)) return 1;
+	return ptb_clear(r);
+}
+
+int ptb_set_mesh_material(ptb_renderer* r, int mesh, const ptb_material* mats, int n)
+{
+	if (edit_prologue(r)) return 1;
+	if (mesh < 0 || mesh >= (int)r->scene.meshes.size() || !mats) { set_error("[Error]mesh index out of range"); return 1; }
+	const MeshInfo& m = r->scene.meshes[mesh];
+	if (n != m.material_count) return 0;   // triangle_mesh::set_material_device ignores a list of the wrong length (triangle_mesh.cpp:254-257)
+	for (int i = 0; i < n; i++) r->scene.materials[m.first_material + i] = mats[i];
+	if (!r->host_only && upload_materials(r)) return 1;
+	return ptb_clear(r);
+}
+
+int ptb_set_mesh_transform(ptb_renderer* r, int mesh, const float* position3, const float* scale3)
+{
+	if (edit_prologue(r)) return 1;
+	if (!position3 || !scale3) { set_error("[Error]null argument"); return 1; }
+	// the UI clamps the scale to >= 1e-6 before the call (Core/path_tracer.cpp:346-351)
+	Vec3 sc{ std::max(scale3[0], 0.000001f), std::max(scale3[1], 0.000001f), std::max(scale3[2], 0.000001f) };
+	if (!set_mesh_transform(r->scene, mesh, Vec3{ position3[0], position3[1], position3[2] }, sc)) return 1;
+	if (!r->host_only && upload_geometry(r)) return 1;
+	return ptb_clear(r);
+}
+
+int ptb_apply_mesh_rotate(ptb_renderer* r, int mesh, const float* rotate3)
+{
+	if (edit_prologue(r)) return 1;
+	if (!rotate3) { set_error("[Error]null argument"); return 1; }
+	if (!apply_mesh_rotate(r->scene, mesh, Vec3{ rotate3[0], rotate3[1], rotate3[2] })) return 1;
+	if (!r->host_only && upload_geometry(r)) return 1;
+	return ptb_clear(r);
+}
+
+int ptb_get_mesh_placement(ptb_renderer* r, int mesh, float* out_position3, float* out_scale3, float* out_rotate3, int* out_first_triangle, int* out_triangle_count, int* out_first_material, int* out_material_count)
+{
+	if (!r || !r->scene_loaded || mesh < 0 || mesh >= (int)r->scene.meshes.size()) { set_error("[Error]mesh index out of range"); return 1; }
+	const MeshInfo& m = r->scene.meshes[mesh];
+	if (out_position3) { out_position3[0] = m.position.x; out_position3[1] = m.position.y; out_position3[2] = m.position.z; }
+	if (out_scale3) { out_scale3[0] = m.scale.x; out_scale3[1] = m.scale.y; out_scale3[2] = m.scale.z; }
+	if (out_rotate3) { out_rotate3[0] = m.rotate_applied.x; out_rotate3[1] = m.rotate_applied.y; out_rotate3[2] = m.rotate_applied.z; }
+	if (out_first_triangle) *out_first_triangle = m.first_triangle;
+	if (out_triangle_count) *out_triangle_count = m.triangle_count;
+	if (out_first_material) *out_first_material = m.first_material;
+	if (out_material_count) *out_material_count = m.material_count;
 	return 0;
 }
 

@@ -66,9 +66,20 @@ struct Texture
 	std::vector<uint8_t> rgba;     // RGBA8, row 0 = top (Others/image_loader.cpp:31-95)
 };
 
+// Per-mesh placement state the reference keeps for live edits (triangle_mesh.h: m_mesh_position,
+// m_mesh_scale, m_mesh_rotate, m_mesh_rotate_applied, m_mesh_triangles_num, m_mesh_material_num).
+struct MeshInfo
+{
+	int first_triangle = 0, triangle_count = 0;
+	int first_material = 0, material_count = 0;
+	Vec3 position{ 0, 0, 0 }, scale{ 1, 1, 1 }, rotate{ 0, 0, 0 }, rotate_applied{ 0, 0, 0 };
+};
+
 struct HostScene
 {
 	std::vector<Triangle> triangles;       // global order: meshes in JSON order, shapes, faces
+	std::vector<Triangle> local_triangles; // the reference's m_triangles: rotation applied, translate/scale not (triangle_mesh.cpp:150-185)
+	std::vector<MeshInfo> meshes;
 	std::vector<int32_t> triangle_material; // index into `materials`
 	std::vector<ptb_material> materials;    // per-mesh private copies, concatenated
 	std::vector<int> mesh_triangle_count;
@@ -86,6 +97,10 @@ void set_error(const std::string& msg);
 bool load_config(const std::string& path, Config& out);
 bool load_scene(const std::string& scene_json_path, const std::string& asset_root, HostScene& out);
 bool load_image_rgba8(const std::string& path, Texture& out);
+// live edits with the reference's arithmetic: triangle_mesh::set_transform_device (triangle_mesh.cpp:271-328)
+// and set_rotate + apply_rotate (:330-426).  They rewrite `triangles` (and `local_triangles`) of one mesh.
+bool set_mesh_transform(HostScene& scene, int mesh, const Vec3& position, const Vec3& scale);
+bool apply_mesh_rotate(HostScene& scene, int mesh, const Vec3& rotate);
 bool builtin_material(const std::string& name, ptb_material& out);
 void default_camera(float width, float height, float aperture, float focal, ptb_camera& out);
 int list_scenes(const std::string& dir, std::vector<std::string>& out);

@@ -913,6 +913,7 @@ static bool append_mesh(HostScene& scene, const std::string& path, const Vec3& p
 	M4 xf_it = transpose(inverse(xf));
 
 	const int material_base = (int)scene.materials.size();
+	const int triangle_base = (int)scene.triangles.size();
 	int mesh_triangles = 0;
 	const size_t nv = obj.v.size() / 3, nn = obj.vn.size() / 3, nt = obj.vt.size() / 2;
 	for (size_t si = 0; si < obj.shapes.size(); si++)
@@ -921,10 +922,13 @@ static bool append_mesh(HostScene& scene, const std::string& path, const Vec3& p
 		int mat_index = (int)si < mat_num ? (int)si : mat_num - 1;
 		for (size_t f = 0; f + 2 < sh.indices.size(); f += 3)
 		{
-			Triangle tri;
+			Triangle tri, local;
 			Vec3* vv[3] = { &tri.v0, &tri.v1, &tri.v2 };
 			Vec3* nn3[3] = { &tri.n0, &tri.n1, &tri.n2 };
 			Vec2* uu[3] = { &tri.uv0, &tri.uv1, &tri.uv2 };
+			Vec3* lv[3] = { &local.v0, &local.v1, &local.v2 };
+			Vec3* ln[3] = { &local.n0, &local.n1, &local.n2 };
+			Vec2* lu[3] = { &local.uv0, &local.uv1, &local.uv2 };
 			for (int k = 0; k < 3; k++)
 			{
 				const ObjIndex& ix = sh.indices[f + k];
@@ -942,9 +946,11 @@ static bool append_mesh(HostScene& scene, const std::string& path, const Vec3& p
 				*vv[k] = Vec3{ pw.x, pw.y, pw.z };
 				*nn3[k] = normalize_host(nw.x, nw.y, nw.z);
 				*uu[k] = has_uv ? Vec2{ obj.vt[ix.vt * 2], obj.vt[ix.vt * 2 + 1] } : Vec2{ 0.0f, 0.0f };
+				*lv[k] = Vec3{ p.x, p.y, p.z }; *ln[k] = n1; *lu[k] = *uu[k];
 			}
 			if (!has_uv) mats[mat_index].diffuse_texture_id = -1; // triangle_mesh.cpp:131-137
 			scene.triangles.push_back(tri);
+			scene.local_triangles.push_back(local);
 			scene.triangle_material.push_back(material_base + mat_index);
 			mesh_triangles++;
 		}
@@ -952,6 +958,90 @@ static bool append_mesh(HostScene& scene, const std::string& path, const Vec3& p
 	scene.materials.insert(scene.materials.end(), mats.begin(), mats.end());
 	scene.mesh_triangle_count.push_back(mesh_triangles);
 	scene.mesh_material_count.push_back(mat_num);
+	MeshInfo info;
+	info.first_triangle = triangle_base; info.triangle_count = mesh_triangles;
+	info.first_material = material_base; info.material_count = mat_num;
+	info.position = position; info.scale = scale_v; info.rotate = rotate_v; info.rotate_applied = rotate_v;
+	scene.meshes.push_back(info);
+	return true;
+}
+
+// world = (T * S) * local, normals through the inverse transpose, re-normalised — the upload step of
+// triangle_mesh::create_mesh_device_data and the loop of set_transform_device (triangle_mesh.cpp:294-325)
+static void place_mesh(HostScene& scene, const MeshInfo& m)
+{
+	M4 xf = identity();
+	xf = translate(xf, m.position.x, m.position.y, m.position.z);
+	xf = scale(xf, m.scale.x, m.scale.y, m.scale.z);
+	M4 xf_it = transpose(inverse(xf));
+	for (int i = m.first_triangle; i < m.first_triangle + m.triangle_count; i++)
+	{
+		const Triangle& l = scene.local_triangles[i];
+		Triangle& t = scene.triangles[i];
+		const Vec3* lv[3] = { &l.v0, &l.v1, &l.v2 };
+		const Vec3* ln[3] = { &l.n0, &l.n1, &l.n2 };
+		Vec3* tv[3] = { &t.v0, &t.v1, &t.v2 };
+		Vec3* tn[3] = { &t.n0, &t.n1, &t.n2 };
+		for (int k = 0; k < 3; k++)
+		{
+			V4 pw = transform(xf, v4(lv[k]->x, lv[k]->y, lv[k]->z, 1.0f));
+			V4 nw = transform(xf_it, v4(ln[k]->x, ln[k]->y, ln[k]->z, 0.0f));
+			*tv[k] = Vec3{ pw.x, pw.y, pw.z };
+			*tn[k] = normalize_host(nw.x, nw.y, nw.z);
+		}
+	}
+}
+
+bool set_mesh_transform(HostScene& scene, int mesh, const Vec3& position, const Vec3& scale_v)
+{
+	if (mesh < 0 || mesh >= (int)scene.meshes.size()) { set_error("[Error]mesh index out of range"); return false; }
+	MeshInfo& m = scene.meshes[mesh];
+	m.position = position;
+	m.scale = scale_v;
+	place_mesh(scene, m);
+	return true;
+}
+
+bool apply_mesh_rotate(HostScene& scene, int mesh, const Vec3& rotate_v)
+{
+	if (mesh < 0 || mesh >= (int)scene.meshes.size()) { set_error("[Error]mesh index out of range"); return false; }
+	MeshInfo& m = scene.meshes[mesh];
+	m.rotate = rotate_v;
+	// the rotation still to apply, about z, then y, then x (triangle_mesh.cpp:364-368)
+	const float deg2rad = (float)0.01745329251994329576923690768489;
+	M4 rot = identity();
+	rot = rotate(rot, (m.rotate.z - m.rotate_applied.z) * deg2rad, 0.0f, 0.0f, 1.0f);
+	rot = rotate(rot, (m.rotate.y - m.rotate_applied.y) * deg2rad, 0.0f, 1.0f, 0.0f);
+	rot = rotate(rot, (m.rotate.x - m.rotate_applied.x) * deg2rad, 1.0f, 0.0f, 0.0f);
+	M4 rot_it = transpose(inverse(rot));
+	M4 xf = identity();
+	xf = translate(xf, m.position.x, m.position.y, m.position.z);
+	xf = scale(xf, m.scale.x, m.scale.y, m.scale.z);
+	M4 xf_it = transpose(inverse(xf));
+	for (int i = m.first_triangle; i < m.first_triangle + m.triangle_count; i++)
+	{
+		Triangle& l = scene.local_triangles[i];
+		Triangle& t = scene.triangles[i];
+		Vec3* lv[3] = { &l.v0, &l.v1, &l.v2 };
+		Vec3* ln[3] = { &l.n0, &l.n1, &l.n2 };
+		Vec3* tv[3] = { &t.v0, &t.v1, &t.v2 };
+		Vec3* tn[3] = { &t.n0, &t.n1, &t.n2 };
+		for (int k = 0; k < 3; k++)
+		{
+			V4 p = transform(rot, v4(lv[k]->x, lv[k]->y, lv[k]->z, 1.0f));
+			V4 n = transform(rot_it, v4(ln[k]->x, ln[k]->y, ln[k]->z, 0.0f));
+			*lv[k] = Vec3{ p.x, p.y, p.z };
+			*ln[k] = normalize_host(n.x, n.y, n.z);
+			// apply_rotate carries the rotated vec4s straight into the world transform: the world normal is
+			// normalize(xf_it * (rot_it * n)) WITHOUT the intermediate normalisation the stored local normal gets
+			// (triangle_mesh.cpp:370-408), unlike set_transform_device which starts from the stored one
+			V4 pw = transform(xf, p);
+			V4 nw = transform(xf_it, n);
+			*tv[k] = Vec3{ pw.x, pw.y, pw.z };
+			*tn[k] = normalize_host(nw.x, nw.y, nw.z);
+		}
+	}
+	m.rotate_applied = m.rotate;
 	return true;
 }
 

@@ -165,6 +165,56 @@ def host_kats(ref):
     return out
 
 
+# one edit of every kind the reference UI can issue, in an order that makes them interact
+# (rotate after a non-uniform scale, a second transform after the rotation was applied)
+EDIT_SCRIPT = [
+    ("transform", (1, [-1.0, 0.45, 0.3], [1.2, 1.9, 1.4])),
+    ("rotate", (1, [40.0, -25.0, 10.0])),
+    ("transform", (2, [2.1, -0.2, 0.6], [0.9, 0.9, 1.7])),
+    ("rotate", (2, [0.0, 90.0, -33.0])),
+    ("transform", (1, [-1.6, 0.1, -0.4], [1.0, 1.0, 1.0])),
+    ("sphere", (1, [2.5, 0.3, 1.2], 0.65, dict(diffuse_color=[0.2, 0.9, 0.4], roughness=0.35, is_transparent=0, extinction_coefficient=2.5))),
+    ("material", (1, 2, dict(diffuse_color=[0.1, 0.2, 0.9], specular_color=[0.9, 0.8, 0.7], roughness=0.6, refraction_index=1.7))),
+    ("transform", (0, [0.2, 4.2, 0.1], [1.0, 0.000000001, 2.0])),     # scale below the UI clamp
+]
+
+
+def apply_edit(target, op, args, spheres=None, mesh_materials=None, material_counts=None):
+    """Runs one EDIT_SCRIPT step on `target`: a RefLib (reference) or a pathtracerwithcuda_b200.Renderer."""
+    from pathtracerwithcuda_b200.api import MATERIAL_DTYPE, SPHERE_DTYPE
+    is_ref = hasattr(target, "set_mesh_materials")
+
+    def structured(a, dt):
+        return np.ascontiguousarray(a).view(np.uint8).reshape(-1).view(dt).copy()
+    if op == "transform":
+        target.set_mesh_transform(args[0], args[1], args[2])
+    elif op == "rotate":
+        target.apply_mesh_rotate(args[0], args[1])
+    elif op == "sphere":
+        index, center, radius, changes = args
+        sp = structured(target.spheres() if is_ref else target.scene_spheres(), SPHERE_DTYPE)
+        one = sp[index:index + 1].copy()
+        one["center"][0] = center
+        one["radius"][0] = radius
+        for k, v in changes.items():
+            one["mat"][k][0] = v
+        target.set_sphere(index, one)
+    elif op == "material":
+        mesh, which, changes = args
+        mats = structured(target.mesh_materials() if is_ref else target.scene_materials(), MATERIAL_DTYPE)
+        counts = target.mesh_material_counts()
+        first = int(sum(counts[:mesh]))
+        mine = mats[first:first + counts[mesh]].copy()
+        for k, v in changes.items():
+            mine[k][which] = v
+        if is_ref:
+            target.set_mesh_materials(mesh, mine)
+        else:
+            target.set_mesh_material(mesh, mine)
+    else:
+        raise ValueError(op)
+
+
 def do_host(out_dir):
     ref = rh.RefLib(host_only=True)
     kats = host_kats(ref)
@@ -180,6 +230,18 @@ def do_host(out_dir):
         np.savez_compressed(os.path.join(out_dir, "scene_%s.npz" % name), triangles=tri.view(np.uint32), triangle_material=mat,
                             materials=ref.mesh_materials(), spheres=ref.spheres(), camera=ref.camera().view(np.uint32))
         if name == "mix":
+            # live edits through the reference's own setters (scene_parser.cpp:645-673): the world-space result
+            # after each step of EDIT_SCRIPT is a fixture for the product's ptb_set_* / ptb_apply_* entry points
+            steps = {}
+            for k, (op, args) in enumerate(EDIT_SCRIPT):
+                apply_edit(ref, op, args)
+                tri_e, _ = ref.triangles()
+                steps["step%d_triangles" % k] = tri_e.view(np.uint32)
+                steps["step%d_materials" % k] = ref.mesh_materials()
+                steps["step%d_spheres" % k] = ref.spheres()
+            np.savez_compressed(os.path.join(out_dir, "scene_mix_edits.npz"), **steps)
+            ref.close()
+            ref.open(root, config_rel=w["config_rel"], scene=w["scene_name"])
             # the awkward-OBJ scene reuses this root (it needs the 64^2 cube map the mix workload wrote)
             sys.path.insert(0, HERE)
             import objedge

@@ -56,7 +56,7 @@ def image_stats(a, b, floor=1e-3):
 
 
 def run(scene, width, height, depth, spp, root=None, config_extra=None, camera=None, time_passes=0, ids_depths=(0, 1, 2), keep=False,
-        workload=None, tri_scale=1.0, options=None):
+        workload=None, tri_scale=1.0, options=None, edits=False):
     """scene: name of a reference scene JSON (staged copy of res/scene), or workload: a procedural one."""
     root = root or tempfile.mkdtemp(prefix="ptb_scratch_")
     cfg_rel = "res/configuration/parity.json"
@@ -86,6 +86,14 @@ def run(scene, width, height, depth, spp, root=None, config_extra=None, camera=N
     if camera is not None:
         ref.set_camera(camera)
         mine.set_camera(camera)
+    if edits:
+        # the same live-edit script on both sides (reference setters vs ptb_set_* / ptb_apply_*), then compare as usual
+        sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+        import make_golden as mg
+        for op, a in mg.EDIT_SCRIPT:
+            mg.apply_edit(ref, op, a)
+            mg.apply_edit(mine, op, a)
+        report["edits"] = len(mg.EDIT_SCRIPT)
 
     # scene arrays
     rt, rm = ref.triangles()
@@ -166,11 +174,12 @@ def main():
     ap.add_argument("--spp", type=int, default=4)
     ap.add_argument("--time-passes", type=int, default=0)
     ap.add_argument("--out", default="")
+    ap.add_argument("--edits", action="store_true", help="apply tests/golden/make_golden.py EDIT_SCRIPT to both sides first")
     args = ap.parse_args()
     opts = {"passes_in_flight": args.passes_in_flight} if args.passes_in_flight else None
     if args.workload:
         rep = run(None, args.width, args.height, args.depth, args.spp, time_passes=args.time_passes, workload=args.workload,
-                  tri_scale=args.tri_scale, options=opts)
+                  tri_scale=args.tri_scale, options=opts, edits=args.edits)
     else:
         rep = run(args.scene, args.width or 128, args.height or 128, args.depth or 5, args.spp, time_passes=args.time_passes, options=opts)
     txt = json.dumps(rep, indent=1)
