@@ -171,6 +171,22 @@ int ptb_bvh_download(ptb_renderer* r, float* out_nodes16, int32_t* out_leaf_orde
  * "profile_stages" = "0"|"1"; "count_traversal" = "0"|"1"; "sort_by_material" = "0"|"1". */
 int ptb_set_option(ptb_renderer* r, const char* key, const char* value);
 
+/* ---- output side -----------------------------------------------------------------------------
+ * ptb_save_png        = screenshot() of Main/window.cpp:712-740 (lodepng::encode of the displayed RGBA8 image),
+ *                       without the GL read-back: the 8-bit image of pixel_256_transform_gamma_corrected_kernel.
+ * ptb_save_pfm        = the float mean image (accumulation / pass_counter) as a little-endian colour PFM.
+ * ptb_save_checkpoint / ptb_load_checkpoint = the reference `image` state that defines a render in progress
+ *                       (Core/image.h:10-23: pixels + pass_counter) with a CRC, so a render continues with pass
+ *                       pass_counter+1 after a restart and produces the SAME image as an uninterrupted run; loading
+ *                       fails if resolution or MaxDepth differ.  restore_camera != 0 also restores the camera.
+ * ptb_write_png_rgb8 / ptb_write_pfm: the same writers on caller-supplied HOST buffers (row 0 = top). */
+int ptb_save_png(ptb_renderer* r, const char* path);
+int ptb_save_pfm(ptb_renderer* r, const char* path);
+int ptb_save_checkpoint(ptb_renderer* r, const char* path);
+int ptb_load_checkpoint(ptb_renderer* r, const char* path, int restore_camera);
+int ptb_write_png_rgb8(const char* path, const uint8_t* rgb, int width, int height);
+int ptb_write_pfm(const char* path, const float* rgb, int width, int height, float scale);
+
 /* ---- live scene edits -----------------------------------------------------------------------
  * What path_tracer::render_ui does between passes (Core/path_tracer.cpp:109-369) through
  * scene_parser::set_sphere_device / set_mesh_material_device / set_mesh_transform_device /

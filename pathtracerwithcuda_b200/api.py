@@ -106,6 +106,12 @@ def load_library():
     L.ptb_get_stats.argtypes = [vp, ctypes.POINTER(Stats)]
     L.ptb_get_depth_profile.argtypes = [vp, ci, vp, vp]
     L.ptb_set_option.argtypes = [vp, cp, cp]
+    L.ptb_save_png.argtypes = [vp, cp]
+    L.ptb_save_pfm.argtypes = [vp, cp]
+    L.ptb_save_checkpoint.argtypes = [vp, cp]
+    L.ptb_load_checkpoint.argtypes = [vp, cp, ci]
+    L.ptb_write_png_rgb8.argtypes = [cp, vp, ci, ci]
+    L.ptb_write_pfm.argtypes = [cp, vp, ci, ci, cf]
     L.ptb_set_sphere.argtypes = [vp, ci, vp]
     L.ptb_set_mesh_material.argtypes = [vp, ci, vp, ci]
     L.ptb_set_mesh_transform.argtypes = [vp, ci, vp, vp]
@@ -141,6 +147,18 @@ def default_camera(width, height, aperture_radius=-1.0, focal_distance=-1.0):
 
 def _ptr(a):
     return a.ctypes.data_as(ctypes.c_void_p)
+
+
+def write_png(path, rgb_u8):
+    a = np.ascontiguousarray(rgb_u8, np.uint8)
+    if load_library().ptb_write_png_rgb8(os.fsencode(path), _ptr(a), a.shape[1], a.shape[0]) != 0:
+        raise PtbError(last_error())
+
+
+def write_pfm(path, rgb_f32, scale=1.0):
+    a = np.ascontiguousarray(rgb_f32, np.float32)
+    if load_library().ptb_write_pfm(os.fsencode(path), _ptr(a), a.shape[1], a.shape[0], float(scale)) != 0:
+        raise PtbError(last_error())
 
 
 class Renderer:
@@ -223,6 +241,19 @@ class Renderer:
         for f in range(6):
             self._check(self.lib.ptb_scene_cubemap_face(self.handle, f, _ptr(out[f])))
         return out
+
+    # -- output side (Main/window.cpp:712-740) ---------------------------------------------------
+    def save_png(self, path):
+        self._check(self.lib.ptb_save_png(self.handle, os.fsencode(path)))
+
+    def save_pfm(self, path):
+        self._check(self.lib.ptb_save_pfm(self.handle, os.fsencode(path)))
+
+    def save_checkpoint(self, path):
+        self._check(self.lib.ptb_save_checkpoint(self.handle, os.fsencode(path)))
+
+    def load_checkpoint(self, path, restore_camera=True):
+        self._check(self.lib.ptb_load_checkpoint(self.handle, os.fsencode(path), 1 if restore_camera else 0))
 
     # -- live edits (Core/path_tracer.cpp:109-369) ----------------------------------------------
     def set_sphere(self, index, sphere):

@@ -21,6 +21,7 @@
 #include "scene.h"
 #include "bvh.h"
 #include "bvh_gpu.h"
+#include "image_out.h"
 #include "kernels.cuh"
 
 using namespace ptbdev;
@@ -1759,6 +1760,74 @@ int ptb_get_mesh_placement(ptb_renderer* r, int mesh, float* out_position3, floa
 	if (out_first_material) *out_first_material = m.first_material;
 	if (out_material_count) *out_material_count = m.material_count;
 	return 0;
+}
+
+// ---- output side ----------------------------------------------------------------
+int ptb_write_png_rgb8(const char* path, const uint8_t* rgb, int width, int height)
+{
+	std::string err;
+	if (!path || !write_png_rgb8(path, rgb, width, height, err)) { set_error(err.empty() ? "[Error]null path" : err); return 1; }
+	return 0;
+}
+
+int ptb_write_pfm(const char* path, const float* rgb, int width, int height, float scale)
+{
+	std::string err;
+	if (!path || !write_pfm_rgb(path, rgb, width, height, scale, err)) { set_error(err.empty() ? "[Error]null path" : err); return 1; }
+	return 0;
+}
+
+int ptb_save_png(ptb_renderer* r, const char* path)
+{
+	if (!r || r->host_only) { set_error("[Error]no CUDA device"); return 1; }
+	std::vector<uint8_t> u8((size_t)r->pixel_count * 3);
+	if (ptb_image_u8(r, u8.data())) return 1;
+	return ptb_write_png_rgb8(path, u8.data(), r->cfg.width, r->cfg.height);
+}
+
+int ptb_save_pfm(ptb_renderer* r, const char* path)
+{
+	if (!r || r->host_only) { set_error("[Error]no CUDA device"); return 1; }
+	std::vector<float> sum((size_t)r->pixel_count * 3);
+	int passes = 0;
+	if (ptb_image_f32(r, sum.data(), &passes)) return 1;
+	return ptb_write_pfm(path, sum.data(), r->cfg.width, r->cfg.height, passes > 0 ? 1.0f / (float)passes : 1.0f);
+}
+
+int ptb_save_checkpoint(ptb_renderer* r, const char* path)
+{
+	if (!r || r->host_only) { set_error("[Error]no CUDA device"); return 1; }
+	if (!path) { set_error("[Error]null path"); return 1; }
+	std::vector<float> sum((size_t)r->pixel_count * 3);
+	int passes = 0;
+	if (sync_all_streams(r) || ptb_image_f32(r, sum.data(), &passes)) return 1;
+	CheckpointHeader h;
+	h.width = r->cfg.width; h.height = r->cfg.height; h.pass_counter = r->pass_counter; h.max_depth = r->cfg.max_tracer_depth;
+	memcpy(h.camera, &r->cam, sizeof(h.camera));
+	std::string err;
+	if (!write_checkpoint(path, h, sum.data(), err)) { set_error(err); return 1; }
+	return 0;
+}
+
+int ptb_load_checkpoint(ptb_renderer* r, const char* path, int restore_camera)
+{
+	if (!r || r->host_only) { set_error("[Error]no CUDA device"); return 1; }
+	if (!path) { set_error("[Error]null path"); return 1; }
+	CheckpointHeader h;
+	std::vector<float> sum;
+	std::string err;
+	if (!read_checkpoint(path, h, sum, err)) { set_error(err); return 1; }
+	if (h.width != r->cfg.width || h.height != r->cfg.height) { set_error("[Error]checkpoint: resolution differs from the renderer's configuration"); return 1; }
+	if (h.max_depth != r->cfg.max_tracer_depth) { set_error("[Error]checkpoint: MaxDepth differs from the renderer's configuration"); return 1; }
+	cudaSetDevice(r->device);
+	if (sync_all_streams(r)) return 1;
+	PTB_CUDA(cudaMemcpyAsync(r->image_sum, sum.data(), sum.size() * sizeof(float), cudaMemcpyHostToDevice, r->stream));
+	PTB_CUDA(cudaStreamSynchronize(r->stream));
+	r->pass_counter = h.pass_counter;
+	if (restore_camera) memcpy(&r->cam, h.camera, sizeof(h.camera));
+	const int rc = ptb_finalize(r, std::max(h.pass_counter, 1));   // refresh the 8-bit image from the restored sum
+	r->pass_counter = h.pass_counter;
+	return rc;
 }
 
 int ptb_pass_counter(ptb_renderer* r) { return r ? r->pass_counter : 0; }
