@@ -127,6 +127,7 @@ def load_library():
     L.ptb_scene_texture.argtypes = [vp, ci, ctypes.POINTER(ci), ctypes.POINTER(ci), vp]
     L.ptb_scene_cubemap_face.argtypes = [vp, ci, vp]
     L.ptb_get_config.argtypes = [vp, vp]
+    L.ptb_decode_image.argtypes = [cp, ctypes.POINTER(ci), ctypes.POINTER(ci), vp]
     _lib = L
     return L
 
@@ -147,6 +148,18 @@ def default_camera(width, height, aperture_radius=-1.0, focal_distance=-1.0):
 
 def _ptr(a):
     return a.ctypes.data_as(ctypes.c_void_p)
+
+
+def decode_image(path):
+    """RGBA8 (H, W, 4) the scene front-end decodes from an image file (Others/image_loader.cpp:31-95)."""
+    L = load_library()
+    w, h = ctypes.c_int(), ctypes.c_int()
+    if L.ptb_decode_image(os.fsencode(path), ctypes.byref(w), ctypes.byref(h), None) != 0:
+        raise PtbError(last_error())
+    out = np.zeros((h.value, w.value, 4), np.uint8)
+    if L.ptb_decode_image(os.fsencode(path), ctypes.byref(w), ctypes.byref(h), _ptr(out)) != 0:
+        raise PtbError(last_error())
+    return out
 
 
 def write_png(path, rgb_u8):

@@ -2209,6 +2209,17 @@ int ptb_scene_texture(ptb_renderer* r, int index, int* width, int* height, uint8
 	return 0;
 }
 
+// image_loader::load_image (Others/image_loader.cpp:31-95) on one file: RGBA8, row 0 = top, alpha 255
+int ptb_decode_image(const char* path, int* width, int* height, uint8_t* out_rgba)
+{
+	Texture t;
+	if (!path || !load_image_rgba8(path, t)) return 1;
+	if (width) *width = t.width;
+	if (height) *height = t.height;
+	if (out_rgba) memcpy(out_rgba, t.rgba.data(), t.rgba.size());
+	return 0;
+}
+
 int ptb_scene_cubemap_face(ptb_renderer* r, int face, uint8_t* out_rgba)
 {
 	if (!r || !r->scene_loaded || face < 0 || face > 5) { set_error("[Error]bad cube face"); return 1; }

@@ -402,6 +402,247 @@ static bool decode_tga(const std::vector<uint8_t>& f, Texture& out)
 
 // "<file>.rgba8" side-car (u32 width, u32 height, RGBA8 top-down): how a caller hands over
 // formats this library does not decode itself (JPG, PNG); the reference used FreeImage for all.
+// ------------------------------------------------------------------------------------------
+// PNG (FreeImage_Load + FreeImage_ConvertTo24Bits of Others/image_loader.cpp:31-95): own inflate + unfilter.
+// Lossless, so parity with the reference's decode is exact by construction: 8-bit RGB as stored, alpha
+// dropped, grey replicated, palette expanded, 16-bit samples reduced to their high byte; output alpha = 255.
+// ------------------------------------------------------------------------------------------
+namespace
+{
+
+struct BitReader
+{
+	const uint8_t* p; size_t n, pos; uint32_t buf; int cnt;
+	BitReader(const uint8_t* d, size_t len) : p(d), n(len), pos(0), buf(0), cnt(0) {}
+	bool need(int k) { while (cnt < k) { if (pos >= n) return false; buf |= (uint32_t)p[pos++] << cnt; cnt += 8; } return true; }
+	bool bits(int k, uint32_t& v) { if (k == 0) { v = 0; return true; } if (!need(k)) return false; v = buf & ((1u << k) - 1u); buf >>= k; cnt -= k; return true; }
+	void align() { buf = 0; cnt = 0; }
+};
+
+struct Huffman
+{
+	uint16_t count[16], symbol[288];
+	bool build(const uint8_t* lengths, int n)
+	{
+		memset(count, 0, sizeof(count));
+		for (int i = 0; i < n; i++) count[lengths[i]]++;
+		uint16_t offs[16];
+		offs[1] = 0;
+		for (int l = 1; l < 15; l++) offs[l + 1] = offs[l] + count[l];
+		for (int i = 0; i < n; i++) if (lengths[i]) symbol[offs[lengths[i]]++] = (uint16_t)i;
+		int left = 1;
+		for (int l = 1; l <= 15; l++) { left <<= 1; left -= count[l]; if (left < 0) return false; }
+		return true;
+	}
+	int decode(BitReader& br) const
+	{
+		int code = 0, first = 0, index = 0;
+		for (int l = 1; l <= 15; l++)
+		{
+			uint32_t b;
+			if (!br.bits(1, b)) return -1;
+			code |= (int)b;
+			int c = count[l];
+			if (code - c < first) return symbol[index + (code - first)];
+			index += c; first += c; first <<= 1; code <<= 1;
+		}
+		return -1;
+	}
+};
+
+bool inflate_zlib(const std::vector<uint8_t>& z, std::vector<uint8_t>& out, size_t expect)
+{
+	if (z.size() < 6 || (z[0] & 0x0f) != 8 || ((z[0] << 8) | z[1]) % 31 != 0 || (z[1] & 0x20)) return false;
+	static const uint16_t len_base[29] = { 3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 15, 17, 19, 23, 27, 31, 35, 43, 51, 59, 67, 83, 99, 115, 131, 163, 195, 227, 258 };
+	static const uint8_t len_extra[29] = { 0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 5, 5, 5, 5, 0 };
+	static const uint16_t dist_base[30] = { 1, 2, 3, 4, 5, 7, 9, 13, 17, 25, 33, 49, 65, 97, 129, 193, 257, 385, 513, 769, 1025, 1537, 2049, 3073, 4097, 6145, 8193, 12289, 16385, 24577 };
+	static const uint8_t dist_extra[30] = { 0, 0, 0, 0, 1, 1, 2, 2, 3, 3, 4, 4, 5, 5, 6, 6, 7, 7, 8, 8, 9, 9, 10, 10, 11, 11, 12, 12, 13, 13 };
+	static const uint8_t order[19] = { 16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15 };
+	BitReader br(z.data() + 2, z.size() - 2);
+	out.clear();
+	out.reserve(expect);
+	uint32_t last = 0;
+	do
+	{
+		uint32_t type;
+		if (!br.bits(1, last) || !br.bits(2, type)) return false;
+		if (type == 0)
+		{
+			br.align();
+			if (br.pos + 4 > br.n) return false;
+			uint32_t len = br.p[br.pos] | (br.p[br.pos + 1] << 8), nlen = br.p[br.pos + 2] | (br.p[br.pos + 3] << 8);
+			br.pos += 4;
+			if ((len ^ 0xffffu) != nlen || br.pos + len > br.n) return false;
+			out.insert(out.end(), br.p + br.pos, br.p + br.pos + len);
+			br.pos += len;
+			continue;
+		}
+		if (type == 3) return false;
+		Huffman lit, dist;
+		uint8_t lengths[320];
+		if (type == 1)
+		{
+			int i = 0;
+			for (; i < 144; i++) lengths[i] = 8;
+			for (; i < 256; i++) lengths[i] = 9;
+			for (; i < 280; i++) lengths[i] = 7;
+			for (; i < 288; i++) lengths[i] = 8;
+			lit.build(lengths, 288);
+			for (i = 0; i < 30; i++) lengths[i] = 5;
+			dist.build(lengths, 30);
+		}
+		else
+		{
+			uint32_t hlit, hdist, hclen;
+			if (!br.bits(5, hlit) || !br.bits(5, hdist) || !br.bits(4, hclen)) return false;
+			hlit += 257; hdist += 1; hclen += 4;
+			if (hlit > 286 || hdist > 30) return false;
+			uint8_t cl[19] = { 0 };
+			for (uint32_t i = 0; i < hclen; i++) { uint32_t v; if (!br.bits(3, v)) return false; cl[order[i]] = (uint8_t)v; }
+			Huffman clh;
+			if (!clh.build(cl, 19)) return false;
+			uint32_t idx = 0;
+			while (idx < hlit + hdist)
+			{
+				int sym = clh.decode(br);
+				if (sym < 0) return false;
+				if (sym < 16) lengths[idx++] = (uint8_t)sym;
+				else
+				{
+					uint32_t rep, prev = 0;
+					if (sym == 16) { if (idx == 0) return false; prev = lengths[idx - 1]; if (!br.bits(2, rep)) return false; rep += 3; }
+					else if (sym == 17) { if (!br.bits(3, rep)) return false; rep += 3; }
+					else { if (!br.bits(7, rep)) return false; rep += 11; }
+					if (idx + rep > hlit + hdist) return false;
+					while (rep--) lengths[idx++] = (uint8_t)prev;
+				}
+			}
+			if (lengths[256] == 0) return false;
+			if (!lit.build(lengths, (int)hlit)) return false;
+			dist.build(lengths + hlit, (int)hdist);   // an incomplete distance code is legal (single code)
+		}
+		while (true)
+		{
+			int sym = lit.decode(br);
+			if (sym < 0) return false;
+			if (sym < 256) { out.push_back((uint8_t)sym); continue; }
+			if (sym == 256) break;
+			sym -= 257;
+			if (sym >= 29) return false;
+			uint32_t eb;
+			if (!br.bits(len_extra[sym], eb)) return false;
+			size_t len = len_base[sym] + eb;
+			int ds = dist.decode(br);
+			if (ds < 0 || ds >= 30) return false;
+			if (!br.bits(dist_extra[ds], eb)) return false;
+			size_t d = dist_base[ds] + eb;
+			if (d > out.size()) return false;
+			size_t from = out.size() - d;
+			for (size_t k = 0; k < len; k++) out.push_back(out[from + k]);
+		}
+	} while (!last);
+	return true;
+}
+
+uint32_t be32(const uint8_t* p) { return ((uint32_t)p[0] << 24) | ((uint32_t)p[1] << 16) | ((uint32_t)p[2] << 8) | (uint32_t)p[3]; }
+
+} // namespace
+
+static bool decode_png(const std::vector<uint8_t>& f, Texture& out)
+{
+	static const uint8_t sig[8] = { 0x89, 'P', 'N', 'G', 0x0d, 0x0a, 0x1a, 0x0a };
+	if (f.size() < 33 || memcmp(f.data(), sig, 8) != 0) return false;
+	uint32_t w = 0, h = 0;
+	int depth = 0, ctype = 0, interlace = 0;
+	std::vector<uint8_t> idat, palette;
+	size_t pos = 8;
+	bool have_ihdr = false, done = false;
+	while (!done && pos + 12 <= f.size())
+	{
+		uint32_t n = be32(&f[pos]);
+		const uint8_t* type = &f[pos + 4];
+		if (pos + 12 + (size_t)n > f.size()) return false;
+		const uint8_t* body = &f[pos + 8];
+		if (!memcmp(type, "IHDR", 4))
+		{
+			if (n != 13) return false;
+			w = be32(body); h = be32(body + 4); depth = body[8]; ctype = body[9]; interlace = body[12];
+			if (body[10] != 0 || body[11] != 0) return false;
+			have_ihdr = true;
+		}
+		else if (!memcmp(type, "PLTE", 4)) palette.assign(body, body + n);
+		else if (!memcmp(type, "IDAT", 4)) idat.insert(idat.end(), body, body + n);
+		else if (!memcmp(type, "IEND", 4)) done = true;
+		pos += 12 + (size_t)n;
+	}
+	if (!have_ihdr || w == 0 || h == 0 || w > 65536 || h > 65536 || interlace != 0) return false;   // Adam7 files need a side-car
+	int channels = ctype == 0 ? 1 : ctype == 2 ? 3 : ctype == 3 ? 1 : ctype == 4 ? 2 : ctype == 6 ? 4 : 0;
+	if (channels == 0) return false;
+	if (!(depth == 8 || depth == 16 || (depth < 8 && (ctype == 0 || ctype == 3) && (depth == 1 || depth == 2 || depth == 4)))) return false;
+	if (ctype == 3 && (depth > 8 || palette.empty())) return false;
+	const size_t bits_pp = (size_t)channels * depth;
+	const size_t row_bytes = (w * bits_pp + 7) / 8;
+	const size_t bpp = bits_pp >= 8 ? bits_pp / 8 : 1;
+	std::vector<uint8_t> raw;
+	if (!inflate_zlib(idat, raw, (row_bytes + 1) * h) || raw.size() < (row_bytes + 1) * h) return false;
+	// unfilter in place
+	std::vector<uint8_t> prev(row_bytes, 0);
+	out.width = (int)w; out.height = (int)h;
+	out.rgba.assign((size_t)w * h * 4, 255);
+	for (uint32_t y = 0; y < h; y++)
+	{
+		uint8_t* row = &raw[(row_bytes + 1) * y + 1];
+		const int filter = raw[(row_bytes + 1) * y];
+		for (size_t i = 0; i < row_bytes; i++)
+		{
+			const int a = i >= bpp ? row[i - bpp] : 0, b = prev[i], c = i >= bpp ? prev[i - bpp] : 0;
+			int x = row[i];
+			switch (filter)
+			{
+			case 0: break;
+			case 1: x += a; break;
+			case 2: x += b; break;
+			case 3: x += (a + b) >> 1; break;
+			case 4: { int p = a + b - c, pa = abs(p - a), pb = abs(p - b), pc = abs(p - c); x += (pa <= pb && pa <= pc) ? a : (pb <= pc ? b : c); break; }
+			default: return false;
+			}
+			row[i] = (uint8_t)x;
+		}
+		memcpy(prev.data(), row, row_bytes);
+		uint8_t* dst = &out.rgba[(size_t)y * w * 4];
+		for (uint32_t x = 0; x < w; x++)
+		{
+			uint8_t r, g, b;
+			if (depth < 8)
+			{
+				const size_t bit = (size_t)x * depth;
+				const int v = (row[bit >> 3] >> (8 - depth - (bit & 7))) & ((1 << depth) - 1);
+				if (ctype == 3)
+				{
+					if ((size_t)v * 3 + 2 >= palette.size()) { r = g = b = 0; }
+					else { r = palette[v * 3]; g = palette[v * 3 + 1]; b = palette[v * 3 + 2]; }
+				}
+				else r = g = b = (uint8_t)(v * 255 / ((1 << depth) - 1));
+			}
+			else
+			{
+				const size_t step = depth / 8;
+				const uint8_t* px = row + (size_t)x * channels * step;
+				if (ctype == 3)
+				{
+					const int v = px[0];
+					if ((size_t)v * 3 + 2 >= palette.size()) { r = g = b = 0; }
+					else { r = palette[v * 3]; g = palette[v * 3 + 1]; b = palette[v * 3 + 2]; }
+				}
+				else if (channels <= 2) r = g = b = px[0];
+				else { r = px[0]; g = px[step]; b = px[2 * step]; }
+			}
+			dst[x * 4] = r; dst[x * 4 + 1] = g; dst[x * 4 + 2] = b;
+		}
+	}
+	return true;
+}
+
 static bool decode_sidecar(const std::vector<uint8_t>& f, Texture& out)
 {
 	if (f.size() < 8) return false;
@@ -420,6 +661,7 @@ bool load_image_rgba8(const std::string& path_in, Texture& out)
 	if (read_binary_file(path + ".rgba8", bytes) && decode_sidecar(bytes, out)) return true;
 	if (!read_binary_file(path, bytes)) { set_error("[Error]Failed to load image file " + path); return false; }
 	if (decode_bmp(bytes, out)) return true;
+	if (decode_png(bytes, out)) return true;
 	std::string lower = path;
 	std::transform(lower.begin(), lower.end(), lower.begin(), [](unsigned char ch) { return (char)tolower(ch); });
 	if (lower.size() > 4 && lower.substr(lower.size() - 4) == ".tga" && decode_tga(bytes, out)) return true;

@@ -59,3 +59,90 @@ def test_pfm(tmp_path):
 def test_writer_errors(tmp_path):
     with pytest.raises(ptb.PtbError):
         ptb.write_png(str(tmp_path / "no_such_dir" / "a.png"), np.zeros((2, 2, 3), np.uint8))
+
+
+# ---- native PNG decode of the scene front-end (Others/image_loader.cpp:31-95: FreeImage_Load + ConvertTo24Bits) ----
+def _png_bytes(w, h, depth, ctype, rows, palette=None, level=6):
+    def chunk(t, b):
+        return struct.pack(">I", len(b)) + t + b + struct.pack(">I", zlib.crc32(t + b) & 0xFFFFFFFF)
+    raw = b"".join(bytes([f]) + bytes(r) for f, r in rows)
+    out = b"\x89PNG\r\n\x1a\n" + chunk(b"IHDR", struct.pack(">IIBBBBB", w, h, depth, ctype, 0, 0, 0))
+    if palette is not None:
+        out += chunk(b"PLTE", bytes(palette))
+    co = zlib.compress(raw, level)
+    half = len(co) // 2
+    return out + chunk(b"IDAT", co[:half]) + chunk(b"IDAT", co[half:]) + chunk(b"IEND", b"")
+
+
+def test_png_decode_matches_pil(tmp_path):
+    Image = pytest.importorskip("PIL.Image")
+    rng = np.random.default_rng(4)
+    smooth = (np.add.outer(np.arange(67), np.arange(45)) * 3 % 256).astype(np.uint8)
+    cases = {"rgb": rng.integers(0, 256, (37, 53, 3), dtype=np.uint8), "rgba": rng.integers(0, 256, (20, 31, 4), dtype=np.uint8),
+             "grey": smooth, "smooth_rgb": np.stack([smooth, smooth.T[:45, :45].repeat(2, 0)[:67, :45], 255 - smooth], -1),
+             "big": rng.integers(0, 4, (300, 400, 3), dtype=np.uint8) * 60}
+    for name, a in cases.items():
+        for level in (0, 1, 9):
+            p = str(tmp_path / ("%s_%d.png" % (name, level)))
+            Image.fromarray(a).save(p, compress_level=level)
+            want = np.asarray(Image.open(p).convert("RGB"))
+            got = ptb.decode_image(p)
+            assert got.shape == want.shape[:2] + (4,), name
+            assert np.array_equal(got[..., :3], want), (name, level)
+            assert np.all(got[..., 3] == 255)
+    # palette image
+    pal = Image.fromarray(cases["rgb"]).quantize(17)
+    p = str(tmp_path / "pal.png")
+    pal.save(p)
+    assert np.array_equal(ptb.decode_image(p)[..., :3], np.asarray(Image.open(p).convert("RGB")))
+    # our own writer's files decode too
+    p = str(tmp_path / "own.png")
+    ptb.write_png(p, cases["rgb"])
+    assert np.array_equal(ptb.decode_image(p)[..., :3], cases["rgb"])
+
+
+def test_png_decode_filters_depths_and_errors(tmp_path):
+    rng = np.random.default_rng(5)
+    w, h = 19, 11
+    img = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+    # every filter type, applied by hand
+    rows, prev = [], np.zeros(w * 3, np.int32)
+    for y in range(h):
+        cur = img[y].reshape(-1).astype(np.int32)
+        f = y % 5
+        left = np.concatenate([np.zeros(3, np.int32), cur[:-3]])
+        upleft = np.concatenate([np.zeros(3, np.int32), prev[:-3]])
+        if f == 0:
+            enc = cur
+        elif f == 1:
+            enc = cur - left
+        elif f == 2:
+            enc = cur - prev
+        elif f == 3:
+            enc = cur - ((left + prev) >> 1)
+        else:
+            p = left + prev - upleft
+            pa, pb, pc = np.abs(p - left), np.abs(p - prev), np.abs(p - upleft)
+            pred = np.where((pa <= pb) & (pa <= pc), left, np.where(pb <= pc, prev, upleft))
+            enc = cur - pred
+        rows.append((f, (enc & 255).astype(np.uint8)))
+        prev = cur
+    p = str(tmp_path / "filters.png")
+    open(p, "wb").write(_png_bytes(w, h, 8, 2, rows))
+    assert np.array_equal(ptb.decode_image(p)[..., :3], img)
+    # 16-bit grey -> high byte; 4-bit grey -> scaled; grey + alpha -> alpha dropped
+    g16 = rng.integers(0, 65536, (h, w), dtype=np.uint16)
+    open(p, "wb").write(_png_bytes(w, h, 16, 0, [(0, g16[y].astype(">u2").tobytes()) for y in range(h)]))
+    assert np.array_equal(ptb.decode_image(p)[..., 0], (g16 >> 8).astype(np.uint8))
+    g4 = rng.integers(0, 16, (h, 20), dtype=np.uint8)
+    open(p, "wb").write(_png_bytes(20, h, 4, 0, [(0, ((g4[y, 0::2] << 4) | g4[y, 1::2]).astype(np.uint8)) for y in range(h)]))
+    assert np.array_equal(ptb.decode_image(p)[..., 1], g4 * 17)
+    ga = rng.integers(0, 256, (h, w, 2), dtype=np.uint8)
+    open(p, "wb").write(_png_bytes(w, h, 8, 4, [(0, ga[y].reshape(-1)) for y in range(h)]))
+    assert np.array_equal(ptb.decode_image(p)[..., 2], ga[..., 0])
+    # corrupt stream / truncated file: loud failure, no crash
+    good = _png_bytes(w, h, 8, 2, rows)
+    for bad in (good[:60], good[:40] + bytes([good[40] ^ 0xFF]) + good[41:], b"\x89PNG\r\n\x1a\n" + b"\0" * 40):
+        open(p, "wb").write(bad)
+        with pytest.raises(ptb.PtbError):
+            ptb.decode_image(p)
