@@ -1,11 +1,12 @@
 // GPU binned-SAH BVH builder (see bvh_gpu.h).
 //
 // Top-down, 16 bins per axis, same split rule and float arithmetic as bvh_host.cpp:
-//   phase 1 (large nodes, > kSmall triangles): level-synchronous.  Every level runs
+//   phase 1 (large nodes, > kSmall = 128 triangles): level-synchronous.  Every level runs
 //       k_plan (chunk list) -> k_init_bins -> k_bin (shared-memory bins per 2048-triangle chunk, flushed
 //       with global atomics) -> k_split (one warp per node: SAH sweep over 45 candidate planes, writes
 //       the 64-byte traversal node, emits child tasks, scans the chunks' left counts) -> k_partition
 //       (stable out-of-place partition of the triangle-id array, ping-pong buffers);
+//       kSmall = 128 / 64 threads measured best: c2 2.3 ms, c4 7.8 ms (1024 / 128: 9.1 and 16.4 ms — too few, too long blocks)
 //   phase 2 (sub-trees of <= kSmall triangles): ONE thread block finishes the whole sub-tree in shared
 //       memory (ids, boxes, bins, an explicit stack; smaller child first so the stack stays <= log2 n),
 //       blocks pull sub-trees from a queue with an atomic cursor.
@@ -28,11 +29,17 @@ namespace
 constexpr int kBins = 16;
 constexpr int kBinWords = 13;                           // count | box lo xyz | box hi xyz | centroid lo xyz | centroid hi xyz
 constexpr int kTaskBinWords = 3 * kBins * kBinWords;    // 624 words per node
-constexpr int kSmall = 1024;                            // sub-trees of <= kSmall triangles are finished by one block
+#ifndef PTB_BUILD_SMALL
+#define PTB_BUILD_SMALL 128
+#endif
+#ifndef PTB_BUILD_SMALL_THREADS
+#define PTB_BUILD_SMALL_THREADS 64
+#endif
+constexpr int kSmall = PTB_BUILD_SMALL;                  // sub-trees of <= kSmall triangles are finished by one block
 constexpr int kChunk = 2048;                            // triangles per block-chunk in phase 1
 constexpr int kThreads = 256;
 constexpr int kItems = kChunk / kThreads;
-constexpr int kSmallThreads = 128;
+constexpr int kSmallThreads = PTB_BUILD_SMALL_THREADS;
 constexpr int kDepthLimit = 40;                         // below this depth splits fall back to halving by index (stack bound)
 constexpr int kPool = 32;                               // node indices a phase-2 block reserves per atomic
 
@@ -791,7 +798,7 @@ int build_bvh2_gpu(const float* d_tris24, int n, int max_leaf_size, float inters
 	A.max_leaf = std::max(1, std::min(max_leaf_size, 8));
 	A.intersect_cost = intersect_cost;
 	A.cap_tasks = n / kSmall + 4;
-	A.cap_small = std::max(4096, n / 64);
+	A.cap_small = 4096 + n / (kSmall >= 512 ? 64 : 8);
 	A.cap_chunks = n / kChunk + A.cap_tasks + 4;
 	A.cap_nodes = n + 65536;   // inner nodes <= n - 1, plus the unused tail of each block's last pool (<= 31 x blocks)
 
@@ -835,7 +842,7 @@ int build_bvh2_gpu(const float* d_tris24, int n, int max_leaf_size, float inters
 		if (level > 96) { cudaEventDestroy(e0); cudaEventDestroy(e1); err = "build_bvh2_gpu: too many levels"; return 1; }
 	}
 	if (root_small) hc.n_small = 1;
-	k_build_small<<<std::max(1, std::min(hc.n_small, 148 * 5)), kSmallThreads, 0, stream>>>(A, hc.n_small);
+	k_build_small<<<std::max(1, std::min(hc.n_small, 148 * (kSmall >= 512 ? 5 : 16))), kSmallThreads, 0, stream>>>(A, hc.n_small);
 	k_emit_tris<<<std::min((n + kThreads - 1) / kThreads, wide_grid), kThreads, 0, stream>>>(d_tris24, A.idx_final, tri_isect, n);
 	cudaEventRecord(e1, stream);
 	cudaError_t e = cudaMemcpyAsync(&hc, A.counters, sizeof(Counters), cudaMemcpyDeviceToHost, stream);

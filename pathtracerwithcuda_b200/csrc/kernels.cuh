@@ -38,6 +38,12 @@ struct DeviceScene
 	int sphere_material_base;
 	int n_textures;
 	int root_ref;                 // node index (>= 0) or leaf ref (< 0)
+	// next-event estimation (estimator "nee", off by default): emissive, non-transparent triangles
+	const float* tris24;          // raw triangles by global id (v0 v1 v2 ...), 24 floats each
+	const int* light_tri;         // global triangle id of light k
+	const float* light_cdf;       // cumulative area of lights 0..k, normalised to 1
+	int n_lights;
+	float light_area;             // total emissive area
 	ptbdev::SkyParams sky;
 };
 
@@ -59,11 +65,16 @@ struct DeviceConfig
 // SoA path state, indexed by path id = slot * pixel_count + pixel.
 struct PathState
 {
-	float4* ray_o;      // origin.xyz, (unused)
+	float4* ray_o;      // origin.xyz, 1.0f when this bounce estimated direct light by NEE (the next hit must not add emission)
 	float4* ray_d;      // direction.xyz, (unused)
 	float4* throughput; // not-absorbed colour .xyz, medium material index (bits; -1 = air)
 	float4* radiance;   // accumulated colour .xyz of this pass
 	float4* hit;        // t, t1, t2, primitive (bits): >= 0 triangle, -(s+2) sphere s, -1 miss
+	// estimator "nee" only (nullptr otherwise): one pending shadow ray per path
+	float4* shadow_o;   // origin.xyz, t_max
+	float4* shadow_d;   // direction.xyz
+	float4* shadow_c;   // radiance to add when the segment is unoccluded
+	int* shadow_queue;  // path ids with a pending shadow ray at the current depth
 };
 
 } // namespace ptb

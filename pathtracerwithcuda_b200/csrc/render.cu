@@ -62,8 +62,9 @@ __global__ void __launch_bounds__(256) k_generate(PathState st, int* __restrict_
 {
 	const int total = pixel_count * n_slots;
 	int tid = blockIdx.x * blockDim.x + threadIdx.x;
-	// counts[0..n_counts) = live paths per depth; counts[n_counts..2*n_counts) = per-depth work-fetch cursors of the persistent extend kernel
-	if (tid < 2 * n_counts) counts[tid] = tid == 0 ? total : 0;
+	// counts[0..n_counts) = live paths per depth; counts[n_counts..2*n_counts) = per-depth work-fetch cursors of the persistent
+	// extend kernel; counts[2*n_counts..3*n_counts) = shadow rays per depth (estimator "nee")
+	if (tid < 3 * n_counts) counts[tid] = tid == 0 ? total : 0;
 	for (int i = tid; i < total; i += gridDim.x * blockDim.x)
 	{
 		int slot = i / pixel_count;
@@ -586,9 +587,14 @@ __device__ __forceinline__ float3 sample_texture(const DeviceTexture& tex, float
 // (miss | sphere | triangle material), so warps shade runs of one material ("shade-by-material"): the
 // material fetch, texture sampling and the conductor / dielectric Fresnel paths stop diverging inside a
 // warp.  The stochastic reflect / refract / diffuse choice still diverges — it is decided inside.
-template <bool SORT>
+// NEE (estimator "nee", SURVEY.md 8f rank 4 — NOT the reference's estimator, off by default): at a diffuse bounce the
+// direct light of the emissive triangles is estimated by one area sample + shadow ray (k_shadow), and the
+// continuing path does not add the emission of an emissive triangle it hits next.  Expected value as in the
+// reference: the reference picks emission up with probability (1 - F) at the light (Fresnel branch first,
+// path_tracer_kernel.cu:529-616), so the light sample carries that factor; same bounce limit and energy cut.
+template <bool SORT, bool NEE>
 __global__ void __launch_bounds__(128) k_shade(DeviceScene sc, PathState st, DeviceConfig cfg, int depth, int pixel_count, int first_pass, int pass_stride,
-	const int* __restrict__ queue_in, const int* __restrict__ count_in, int* __restrict__ queue_out, int* __restrict__ count_out)
+	const int* __restrict__ queue_in, const int* __restrict__ count_in, int* __restrict__ queue_out, int* __restrict__ count_out, int* __restrict__ shadow_count)
 {
 	__shared__ int s_ids[SORT ? 128 : 1];
 	__shared__ int s_hist[SORT ? 16 : 1];
@@ -600,6 +606,7 @@ __global__ void __launch_bounds__(128) k_shade(DeviceScene sc, PathState st, Dev
 		int i = block_base + threadIdx.x;
 		bool valid = i < count;
 		bool alive = false;
+		bool want_shadow = false;
 		int id = 0;
 		if (SORT)
 		{
@@ -753,6 +760,8 @@ __global__ void __launch_bounds__(128) k_shade(DeviceScene sc, PathState st, Dev
 					float rand = rng.next();
 					float3 next_o, next_d;
 					float medium_bits = t4.w;
+					bool nee_candidate = false;
+					float nee_flag = 0.0f;
 					if (rand < fresnel_reflection)
 					{
 						float rand1 = rng.next();
@@ -775,18 +784,24 @@ __global__ void __launch_bounds__(128) k_shade(DeviceScene sc, PathState st, Dev
 					}
 					else
 					{
-						float4 r4 = st.radiance[id];
-						float3 add = not_absorbed * emission_color;
-						st.radiance[id] = make_float4(r4.x + add.x, r4.y + add.y, r4.z + add.z, 0.0f);
+						// NEE: an emissive triangle reached straight after a bounce that sampled the lights is already counted
+						const bool counted_by_nee = NEE && o4.w != 0.0f && prim >= 0 && (emission_color.x != 0.0f || emission_color.y != 0.0f || emission_color.z != 0.0f);
+						if (!counted_by_nee)
+						{
+							float4 r4 = st.radiance[id];
+							float3 add = not_absorbed * emission_color;
+							st.radiance[id] = make_float4(r4.x + add.x, r4.y + add.y, r4.z + add.z, 0.0f);
+						}
 						not_absorbed = not_absorbed * diffuse_color;
 						float rand1 = rng.next();
 						float rand2 = rng.next();
 						next_o = min_point + bias_vector;
 						next_d = sample_on_hemisphere_cosine_weight(min_normal, rand1, rand2);
+						nee_candidate = true;
 					}
+					float3 nsa = sigma_a, nss = sigma_s;
 					{
 						// medium the next segment travels in: unchanged unless the path refracted
-						float3 nsa = sigma_a, nss = sigma_s;
 						const int next_medium = __float_as_int(medium_bits);
 						if (next_medium != medium_index)
 						{
@@ -800,9 +815,56 @@ __global__ void __launch_bounds__(128) k_shade(DeviceScene sc, PathState st, Dev
 						}
 						st.ray_d[id] = make_float4(next_d.x, next_d.y, next_d.z, next_bounce_bound(cfg, nsa, nss, seed, pixel_index, depth + 1));
 					}
-					st.ray_o[id] = make_float4(next_o.x, next_o.y, next_o.z, 0.0f);
-					st.throughput[id] = make_float4(not_absorbed.x, not_absorbed.y, not_absorbed.z, medium_bits);
 					if (length(not_absorbed) <= cfg.energy_threshold) alive = false;
+					if (NEE && nee_candidate && alive && depth + 1 < cfg.max_depth && sc.n_lights > 0 && !(nss.x > 0.0f || length(nsa) > cfg.sss_threshold))
+					{
+						nee_flag = 1.0f;
+						// own random stream: the path itself is the one the reference estimator follows
+						Rng lrng;
+						lrng.seed((uint32_t)(hash_ref(seed) * hash_ref(pixel_index) * hash_ref(depth)) ^ 0x68bc21ebu, 0.0f, 1.0f);
+						const float u0 = lrng.next(), u1 = lrng.next(), u2 = lrng.next();
+						int lo = 0, hi = sc.n_lights - 1;
+						while (lo < hi) { const int mid = (lo + hi) >> 1; if (__ldg(&sc.light_cdf[mid]) < u0) lo = mid + 1; else hi = mid; }
+						const int lt = __ldg(&sc.light_tri[lo]);
+						const float* tv = sc.tris24 + (size_t)lt * 24;
+						const float3 lv0 = make_float3(__ldg(tv + 0), __ldg(tv + 1), __ldg(tv + 2));
+						const float3 lv1 = make_float3(__ldg(tv + 3), __ldg(tv + 4), __ldg(tv + 5));
+						const float3 lv2 = make_float3(__ldg(tv + 6), __ldg(tv + 7), __ldg(tv + 8));
+						const float su = sqrtf(u1);
+						const float b0 = 1.0f - su, b1 = su * (1.0f - u2), b2 = su * u2;
+						const float3 y = lv0 * b0 + lv1 * b1 + lv2 * b2;
+						const float3 to = y - next_o;
+						const float r2 = dot(to, to);
+						const float rr = sqrtf(r2);
+						const float3 wi = to * (1.0f / rr);
+						const float cos_x = dot(normalize(min_normal), wi);
+						const float3 ng = cross(lv1 - lv0, lv2 - lv0);
+						const float ng_len = length(ng);
+						const float cos_l = fabsf(dot(ng, wi)) / ng_len;
+						if (cos_x > 0.0f && cos_l > 0.0f && rr > 0.0f && ng_len > 0.0f)
+						{
+							const float4* lsh = sc.tri_shade + (size_t)lt * 4;
+							const float4 l0 = __ldg(lsh + 0), l1 = __ldg(lsh + 1), l2 = __ldg(lsh + 2), l3 = __ldg(lsh + 3);
+							float3 ln = make_float3(l0.x, l0.y, l0.z) * b0 + make_float3(l0.w, l1.x, l1.y) * b1 + make_float3(l1.z, l1.w, l2.x) * b2;
+							if (dot(wi, ln) > 0) ln = ln * -1.0f;
+							const DeviceMaterial* lm = &sc.materials[__float_as_int(l3.w)];
+							const float4 lmb = __ldg(&lm->b), lmc = __ldg(&lm->c);
+							const float3 refr = refraction(ln, wi, cfg.air_n, lmb.w);
+							const float fl = lmc.w == 0 ? fresnel_dielectric(ln, wi, cfg.air_n, lmb.w, refr) : fresnel_conductor(ln, wi, lmb.w, lmc.w);
+							const float keep = fminf(fmaxf(1.0f - fl, 0.0f), 1.0f);      // probability of the emission branch at the light
+							const float w = keep * cos_x * cos_l * sc.light_area / (3.14159265358979f * r2);
+							const float3 c = not_absorbed * make_float3(lmb.x, lmb.y, lmb.z) * w;
+							if (c.x > 0.0f || c.y > 0.0f || c.z > 0.0f)
+							{
+								st.shadow_o[id] = make_float4(next_o.x, next_o.y, next_o.z, rr * 0.9999f);
+								st.shadow_d[id] = make_float4(wi.x, wi.y, wi.z, 0.0f);
+								st.shadow_c[id] = make_float4(c.x, c.y, c.z, 0.0f);
+								want_shadow = true;
+							}
+						}
+					}
+					st.ray_o[id] = make_float4(next_o.x, next_o.y, next_o.z, nee_flag);
+					st.throughput[id] = make_float4(not_absorbed.x, not_absorbed.y, not_absorbed.z, medium_bits);
 				}
 				else
 				{
@@ -822,6 +884,99 @@ __global__ void __launch_bounds__(128) k_shade(DeviceScene sc, PathState st, Dev
 			if (lane == 0) pos = atomicAdd(count_out, __popc(mask));
 			pos = __shfl_sync(0xffffffffu, pos, 0);
 			if (alive) queue_out[pos + __popc(mask & ((1u << lane) - 1u))] = id;
+		}
+		if (NEE)
+		{
+			const unsigned smask = __ballot_sync(0xffffffffu, want_shadow);
+			if (smask)
+			{
+				int pos = 0;
+				if (lane == 0) pos = atomicAdd(shadow_count, __popc(smask));
+				pos = __shfl_sync(0xffffffffu, pos, 0);
+				if (want_shadow) st.shadow_queue[pos + __popc(smask & ((1u << lane) - 1u))] = id;
+			}
+		}
+	}
+}
+
+// ------------------------------------------------------------------------------------------
+// k_shadow — visibility of the NEE light samples (any hit strictly before the light point)
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_shadow(DeviceScene sc, PathState st, const int* __restrict__ count_ptr)
+{
+	const int count = *count_ptr;
+	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x)
+	{
+		const int id = st.shadow_queue[i];
+		const float4 o4 = st.shadow_o[id], d4 = st.shadow_d[id];
+		const float3 o = make_float3(o4.x, o4.y, o4.z), d = make_float3(d4.x, d4.y, d4.z);
+		const float t_max = o4.w;
+		bool blocked = false;
+		for (int s = 0; s < sc.n_spheres && !blocked; s++)
+		{
+			const float4 sp = __ldg(&sc.spheres[s]);
+			float t;
+			if (intersect_sphere(make_float3(sp.x, sp.y, sp.z), sp.w, o, d, t) && t > 0.0f && t < t_max) blocked = true;
+		}
+		if (!blocked && sc.n_triangles > 0)
+		{
+			const float tiny = 1e-30f;
+			const float3 ds = make_float3(fabsf(d.x) < tiny ? copysignf(tiny, d.x) : d.x, fabsf(d.y) < tiny ? copysignf(tiny, d.y) : d.y,
+				fabsf(d.z) < tiny ? copysignf(tiny, d.z) : d.z);
+			const float3 idir = make_float3(1.0f / ds.x, 1.0f / ds.y, 1.0f / ds.z);
+			const float3 noidir = make_float3(-o.x * idir.x, -o.y * idir.y, -o.z * idir.z);
+			const float margin2 = 4.8e-7f * fmaxf(fmaxf(fabsf(noidir.x), fabsf(noidir.y)), fabsf(noidir.z));
+			int stack[PTB_STACK_SIZE];
+			int sp = 0;
+			int node = sc.root_ref;
+			while (!blocked)
+			{
+				if (node >= 0)
+				{
+					const float4* np = sc.bvh_nodes + (size_t)node * 4;
+					float4 n0, n1, n2;
+					float2 n3;
+					load_node(np, n0, n1, n2, n3);
+					const float c0x0 = fmaf(n0.x, idir.x, noidir.x), c0x1 = fmaf(n0.y, idir.x, noidir.x);
+					const float c0y0 = fmaf(n0.z, idir.y, noidir.y), c0y1 = fmaf(n0.w, idir.y, noidir.y);
+					const float c0z0 = fmaf(n2.x, idir.z, noidir.z), c0z1 = fmaf(n2.y, idir.z, noidir.z);
+					const float c1x0 = fmaf(n1.x, idir.x, noidir.x), c1x1 = fmaf(n1.y, idir.x, noidir.x);
+					const float c1y0 = fmaf(n1.z, idir.y, noidir.y), c1y1 = fmaf(n1.w, idir.y, noidir.y);
+					const float c1z0 = fmaf(n2.z, idir.z, noidir.z), c1z1 = fmaf(n2.w, idir.z, noidir.z);
+					const float tmin0 = fmaxf(fmaxf(fminf(c0x0, c0x1), fminf(c0y0, c0y1)), fmaxf(fminf(c0z0, c0z1), 0.0f));
+					const float tmax0 = fminf(fminf(fmaxf(c0x0, c0x1), fmaxf(c0y0, c0y1)), fminf(fmaxf(c0z0, c0z1), t_max));
+					const float tmin1 = fmaxf(fmaxf(fminf(c1x0, c1x1), fminf(c1y0, c1y1)), fmaxf(fminf(c1z0, c1z1), 0.0f));
+					const float tmax1 = fminf(fminf(fmaxf(c1x0, c1x1), fmaxf(c1y0, c1y1)), fminf(fmaxf(c1z0, c1z1), t_max));
+					const bool h0 = fmaf(tmin0, PTB_SLACK_LO / PTB_SLACK_HI, -margin2) <= tmax0;
+					const bool h1 = fmaf(tmin1, PTB_SLACK_LO / PTB_SLACK_HI, -margin2) <= tmax1;
+					const int child0 = __float_as_int(n3.x), child1 = __float_as_int(n3.y);
+					if (h0 && h1) { if (sp < PTB_STACK_SIZE) stack[sp++] = child1; node = child0; }
+					else if (h0) node = child0;
+					else if (h1) node = child1;
+					else { if (sp == 0) break; node = stack[--sp]; }
+				}
+				else
+				{
+					const int ref = ~node;
+					const int first = ref >> 3, cnt = (ref & 7) + 1;
+					for (int k = 0; k < cnt && !blocked; k++)
+					{
+						const float4* tp = sc.tri_isect + (size_t)(first + k) * 3;
+						const float4 a = __ldg(tp + 0), b = __ldg(tp + 1), c = __ldg(tp + 2);
+						float t, t1, t2;
+						if (intersect_triangle(make_float3(a.x, a.y, a.z), make_float3(b.x, b.y, b.z), make_float3(c.x, c.y, c.z), o, d, t, t1, t2) && t > 0.0f && t < t_max)
+							blocked = true;
+					}
+					if (blocked || sp == 0) break;
+					node = stack[--sp];
+				}
+			}
+		}
+		if (!blocked)
+		{
+			const float4 c = st.shadow_c[id];
+			float4 r4 = st.radiance[id];
+			st.radiance[id] = make_float4(r4.x + c.x, r4.y + c.y, r4.z + c.z, 0.0f);
 		}
 	}
 }
@@ -910,6 +1065,8 @@ struct ptb_renderer
 	int bvh_layout = 2;
 	int bvh_max_leaf = 8;                  // binary layout; the wide layout holds <= 3 per leaf slot
 	float bvh_intersect_cost = 0.8f;       // SAH cost of a triangle test relative to a node visit (measured optimum on c2, profiles/r01_experiments.md)
+	float pass_clamp = -1.0f;              // < 0: the reference's per-pass clamp 2 * MaxDepth (path_tracer_kernel.cu:644-651)
+	int nee = 0;                           // estimator: 0 = the reference's (default, parity mode), 1 = next-event estimation
 	int sort_by_material = 0;              // block-local material sort in k_shade (measured: profiles/r01_experiments.md)
 	int tile_order = 1;                    // camera rays enter the first queue in 8x4 pixel tiles
 	// facts about the last acceleration-structure build (ptb_bvh_info)
@@ -928,6 +1085,7 @@ struct ptb_renderer
 	std::vector<void*> scene_allocs;      // textures, cube map
 	std::vector<void*> geometry_allocs;   // triangles, BVH, shading attributes (rebuilt by mesh edits)
 	std::vector<void*> material_allocs;   // materials + spheres (rewritten by material / sphere edits)
+	std::vector<void*> light_allocs;      // emissive-triangle list of the "nee" estimator
 	int64_t bvh_nodes = 0, bvh_bytes = 0;
 
 	// work buffers
@@ -978,13 +1136,21 @@ int alloc_path_state(ptb_renderer* r, PathState& st, int* queue[2], int** counts
 	PTB_CUDA(cudaMalloc(&st.hit, r->capacity * sizeof(float4)));
 	PTB_CUDA(cudaMalloc(&queue[0], r->capacity * sizeof(int)));
 	PTB_CUDA(cudaMalloc(&queue[1], r->capacity * sizeof(int)));
-	PTB_CUDA(cudaMalloc(counts, 2 * n_counts * sizeof(int)));
+	PTB_CUDA(cudaMalloc(counts, 3 * n_counts * sizeof(int)));
+	if (r->nee)
+	{
+		PTB_CUDA(cudaMalloc(&st.shadow_o, r->capacity * sizeof(float4)));
+		PTB_CUDA(cudaMalloc(&st.shadow_d, r->capacity * sizeof(float4)));
+		PTB_CUDA(cudaMalloc(&st.shadow_c, r->capacity * sizeof(float4)));
+		PTB_CUDA(cudaMalloc(&st.shadow_queue, r->capacity * sizeof(int)));
+	}
 	return 0;
 }
 
 void free_path_state(PathState& st, int* queue[2], int** counts)
 {
 	cudaFree(st.ray_o); cudaFree(st.ray_d); cudaFree(st.throughput); cudaFree(st.radiance); cudaFree(st.hit);
+	cudaFree(st.shadow_o); cudaFree(st.shadow_d); cudaFree(st.shadow_c); cudaFree(st.shadow_queue);
 	cudaFree(queue[0]); cudaFree(queue[1]); cudaFree(*counts);
 	st = PathState(); queue[0] = queue[1] = nullptr; *counts = nullptr;
 }
@@ -1060,7 +1226,8 @@ void release_scene_device(ptb_renderer* r)
 	for (void* p : r->scene_allocs) cudaFree(p);
 	for (void* p : r->geometry_allocs) cudaFree(p);
 	for (void* p : r->material_allocs) cudaFree(p);
-	r->scene_allocs.clear(); r->geometry_allocs.clear(); r->material_allocs.clear();
+	for (void* p : r->light_allocs) cudaFree(p);
+	r->scene_allocs.clear(); r->geometry_allocs.clear(); r->material_allocs.clear(); r->light_allocs.clear();
 	memset(&r->dscene, 0, sizeof(r->dscene));
 	r->bvh_nodes = r->bvh_bytes = 0;
 }
@@ -1156,6 +1323,7 @@ int upload_geometry(ptb_renderer* r)
 	const int* d_material = nullptr;
 	if (upload(r, (const float*)s.triangles.data(), (size_t)n_tris * 24, &d_tris24, G)) return 1;
 	if (upload(r, s.triangle_material.data(), (size_t)n_tris, &d_material, G)) return 1;
+	ds.tris24 = d_tris24;
 	r->bvh_built_on_gpu = 0; r->bvh_levels = 0; r->bvh_small_tasks = 0; r->bvh_max_depth = 0; r->bvh_build_ms = 0.0; r->bvh_note.clear();
 
 	// acceleration structure over all meshes' world-space triangles
@@ -1242,6 +1410,41 @@ int upload_geometry(ptb_renderer* r)
 	return 0;
 }
 
+// emissive, non-transparent triangles with their area CDF (estimator "nee"); depends on geometry AND materials
+int upload_lights(ptb_renderer* r)
+{
+	for (void* p : r->light_allocs) cudaFree(p);
+	r->light_allocs.clear();
+	const HostScene& s = r->scene;
+	DeviceScene& ds = r->dscene;
+	std::vector<int> ids;
+	std::vector<double> area;
+	double total = 0.0;
+	for (size_t i = 0; i < s.triangles.size(); i++)
+	{
+		const ptb_material& m = s.materials[s.triangle_material[i]];
+		// a transparent emitter never reaches the emission branch in the reference (path_tracer_kernel.cu:573-616)
+		if (m.is_transparent || !(m.emission_color[0] > 0.0f || m.emission_color[1] > 0.0f || m.emission_color[2] > 0.0f)) continue;
+		const Triangle& t = s.triangles[i];
+		const double e1[3] = { (double)t.v1.x - t.v0.x, (double)t.v1.y - t.v0.y, (double)t.v1.z - t.v0.z };
+		const double e2[3] = { (double)t.v2.x - t.v0.x, (double)t.v2.y - t.v0.y, (double)t.v2.z - t.v0.z };
+		const double cx = e1[1] * e2[2] - e1[2] * e2[1], cy = e1[2] * e2[0] - e1[0] * e2[2], cz = e1[0] * e2[1] - e1[1] * e2[0];
+		const double a = 0.5 * std::sqrt(cx * cx + cy * cy + cz * cz);
+		if (!(a > 0.0)) continue;
+		ids.push_back((int)i); area.push_back(a); total += a;
+	}
+	std::vector<float> cdf(ids.size());
+	double run = 0.0;
+	for (size_t k = 0; k < ids.size(); k++) { run += area[k]; cdf[k] = (float)(run / total); }
+	if (!cdf.empty()) cdf.back() = 1.0f;
+	if (upload(r, ids.data(), ids.size(), &ds.light_tri, &r->light_allocs)) return 1;
+	if (upload(r, cdf.data(), cdf.size(), &ds.light_cdf, &r->light_allocs)) return 1;
+	ds.n_lights = (int)ids.size();
+	ds.light_area = (float)total;
+	PTB_CUDA(cudaStreamSynchronize(r->stream));
+	return 0;
+}
+
 // mesh materials followed by one material per sphere, and the sphere array (re-run by material / sphere edits)
 int upload_materials(ptb_renderer* r)
 {
@@ -1274,6 +1477,7 @@ int upload_scene(ptb_renderer* r)
 	const auto t_upload0 = std::chrono::steady_clock::now();
 	if (upload_geometry(r)) return 1;
 	if (upload_materials(r)) return 1;
+	if (upload_lights(r)) return 1;
 
 	std::vector<DeviceTexture> textures;
 	for (auto& t : s.textures)
@@ -1386,12 +1590,24 @@ int enqueue_batch(ptb_renderer* r, ptb_renderer::BatchContext& ctx, cudaEvent_t 
 		}
 		launch_extend(r, stream, total, ctx.st, qin, ctx.counts + depth, ctx.counts + n_counts + depth);
 		if (prof) cudaEventRecord(e1, stream);
-		if (r->sort_by_material) k_shade<true><<<grid_for(r, total, 128, 16), 128, 0, stream>>>(r->dscene, ctx.st, dc, depth, px, first_pass, stride, qin, ctx.counts + depth, qout, ctx.counts + depth + 1);
-		else k_shade<false><<<grid_for(r, total, 128, 16), 128, 0, stream>>>(r->dscene, ctx.st, dc, depth, px, first_pass, stride, qin, ctx.counts + depth, qout, ctx.counts + depth + 1);
+		int* shadow_count = ctx.counts + 2 * n_counts + depth;
+		const int sgrid = grid_for(r, total, 128, 16);
+		if (r->nee)
+		{
+			if (r->sort_by_material) k_shade<true, true><<<sgrid, 128, 0, stream>>>(r->dscene, ctx.st, dc, depth, px, first_pass, stride, qin, ctx.counts + depth, qout, ctx.counts + depth + 1, shadow_count);
+			else k_shade<false, true><<<sgrid, 128, 0, stream>>>(r->dscene, ctx.st, dc, depth, px, first_pass, stride, qin, ctx.counts + depth, qout, ctx.counts + depth + 1, shadow_count);
+			if (depth + 1 < r->cfg.max_tracer_depth)
+			{
+				k_shadow<<<sgrid, 128, 0, stream>>>(r->dscene, ctx.st, shadow_count);
+				r->stats.kernel_launches++;
+			}
+		}
+		else if (r->sort_by_material) k_shade<true, false><<<sgrid, 128, 0, stream>>>(r->dscene, ctx.st, dc, depth, px, first_pass, stride, qin, ctx.counts + depth, qout, ctx.counts + depth + 1, shadow_count);
+		else k_shade<false, false><<<sgrid, 128, 0, stream>>>(r->dscene, ctx.st, dc, depth, px, first_pass, stride, qin, ctx.counts + depth, qout, ctx.counts + depth + 1, shadow_count);
 		r->stats.kernel_launches += 2;
 	}
 	if (prev_accumulated) PTB_CUDA(cudaStreamWaitEvent(stream, prev_accumulated, 0));
-	k_accumulate<<<(px + 255) / 256, 256, 0, stream>>>(ctx.st.radiance, r->image_sum, r->last_pass, ctx.counts, r->segment_totals, n_counts, px, n_slots, (float)r->cfg.max_tracer_depth * 2.0f);
+	k_accumulate<<<(px + 255) / 256, 256, 0, stream>>>(ctx.st.radiance, r->image_sum, r->last_pass, ctx.counts, r->segment_totals, n_counts, px, n_slots, r->pass_clamp >= 0.0f ? r->pass_clamp : (float)r->cfg.max_tracer_depth * 2.0f);
 	r->stats.kernel_launches++;
 	PTB_CUDA(cudaEventRecord(ctx.accumulated, stream));
 	PTB_CUDA(cudaGetLastError());
@@ -1713,7 +1929,7 @@ int ptb_set_sphere(ptb_renderer* r, int index, const void* sphere100)
 	if (edit_prologue(r)) return 1;
 	if (index < 0 || index >= (int)r->scene.spheres.size() || !sphere100) { set_error("[Error]sphere index out of range"); return 1; }
 	memcpy(&r->scene.spheres[index], sphere100, sizeof(Sphere));
-	if (!r->host_only && upload_materials(r)) return 1;
+	if (!r->host_only && (upload_materials(r) || upload_lights(r))) return 1;
 	return ptb_clear(r);
 }
 
@@ -1724,7 +1940,7 @@ int ptb_set_mesh_material(ptb_renderer* r, int mesh, const ptb_material* mats, i
 	const MeshInfo& m = r->scene.meshes[mesh];
 	if (n != m.material_count) return 0;   // triangle_mesh::set_material_device ignores a list of the wrong length (triangle_mesh.cpp:254-257)
 	for (int i = 0; i < n; i++) r->scene.materials[m.first_material + i] = mats[i];
-	if (!r->host_only && upload_materials(r)) return 1;
+	if (!r->host_only && (upload_materials(r) || upload_lights(r))) return 1;
 	return ptb_clear(r);
 }
 
@@ -1735,7 +1951,7 @@ int ptb_set_mesh_transform(ptb_renderer* r, int mesh, const float* position3, co
 	// the UI clamps the scale to >= 1e-6 before the call (Core/path_tracer.cpp:346-351)
 	Vec3 sc{ std::max(scale3[0], 0.000001f), std::max(scale3[1], 0.000001f), std::max(scale3[2], 0.000001f) };
 	if (!set_mesh_transform(r->scene, mesh, Vec3{ position3[0], position3[1], position3[2] }, sc)) return 1;
-	if (!r->host_only && upload_geometry(r)) return 1;
+	if (!r->host_only && (upload_geometry(r) || upload_lights(r))) return 1;
 	return ptb_clear(r);
 }
 
@@ -1744,7 +1960,7 @@ int ptb_apply_mesh_rotate(ptb_renderer* r, int mesh, const float* rotate3)
 	if (edit_prologue(r)) return 1;
 	if (!rotate3) { set_error("[Error]null argument"); return 1; }
 	if (!apply_mesh_rotate(r->scene, mesh, Vec3{ rotate3[0], rotate3[1], rotate3[2] })) return 1;
-	if (!r->host_only && upload_geometry(r)) return 1;
+	if (!r->host_only && (upload_geometry(r) || upload_lights(r))) return 1;
 	return ptb_clear(r);
 }
 
@@ -1908,7 +2124,7 @@ int ptb_capture_rays(ptb_renderer* r, int pass, int depth, int32_t* out_pixels, 
 	for (; d < depth && d < r->cfg.max_tracer_depth; d++)
 	{
 		launch_extend(r, r->stream, px, r->st, r->queue[d & 1], r->counts + d, r->counts + (r->cfg.max_tracer_depth + 2) + d);
-		k_shade<false><<<grid_for(r, px, 128, 16), 128, 0, r->stream>>>(r->dscene, r->st, dc, d, px, pass, 1, r->queue[d & 1], r->counts + d, r->queue[(d + 1) & 1], r->counts + d + 1);
+		k_shade<false, false><<<grid_for(r, px, 128, 16), 128, 0, r->stream>>>(r->dscene, r->st, dc, d, px, pass, 1, r->queue[d & 1], r->counts + d, r->queue[(d + 1) & 1], r->counts + d + 1, nullptr);
 	}
 	int count = 0;
 	if (cudaMemcpyAsync(&count, r->counts + d, sizeof(int), cudaMemcpyDeviceToHost, r->stream) != cudaSuccess || cudaStreamSynchronize(r->stream) != cudaSuccess)
@@ -2149,6 +2365,25 @@ int ptb_set_option(ptb_renderer* r, const char* key, const char* value)
 	if (k == "bvh_intersect_cost") { float c = (float)atof(value); if (!(c > 0.0f)) { set_error("[Error]bvh_intersect_cost must be > 0"); return 1; } r->bvh_intersect_cost = c; return 0; }
 	if (k == "tile_order") { r->tile_order = atoi(value); return 0; }
 	if (k == "sort_by_material") { r->sort_by_material = atoi(value); return 0; }
+	if (k == "pass_clamp") { r->pass_clamp = (float)atof(value); return 0; }   // diagnostic: per-pass clamp of the accumulation (default: the reference's)
+	if (k == "estimator")
+	{
+		if (v != "reference" && v != "nee") { set_error("[Error]estimator must be reference or nee"); return 1; }
+		const int want = v == "nee" ? 1 : 0;
+		if (want != r->nee)
+		{
+			r->nee = want;
+			if (!r->host_only)
+			{
+				cudaSetDevice(r->device);
+				cudaDeviceSynchronize();
+				free_work_buffers(r);
+				if (alloc_work_buffers(r)) return 1;
+				r->pass_counter = 0;
+			}
+		}
+		return 0;
+	}
 	if (k == "extend_persistent") { r->extend_persistent = atoi(value); return 0; }
 	if (k == "tune_refill") { r->tune_refill = atoi(value); return 0; }
 	if (k == "tune_leaf") { r->tune_leaf = atoi(value); return 0; }
