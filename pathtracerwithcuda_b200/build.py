@@ -78,6 +78,11 @@ def build(force=False, verbose=False, extra_nvcc=None, out=None):
 
 
 if __name__ == "__main__":
-    extra = [a for a in sys.argv[1:] if a.startswith("-D")]
+    extra = []
+    for a in sys.argv[1:]:
+        if a.startswith("-D"):
+            extra.append(a)
+        elif a.startswith("--nvcc="):      # e.g. --nvcc=-Xptxas,-fmad=false  ->  -Xptxas -fmad=false
+            extra += a.split("=", 1)[1].split(",")
     out = [a.split("=", 1)[1] for a in sys.argv[1:] if a.startswith("--out=")]
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, extra_nvcc=extra or None, out=out[0] if out else None))

@@ -83,7 +83,6 @@ __global__ void __launch_bounds__(256) k_generate(PathState st, int* __restrict_
 		generate_camera_ray(cam, pixel, seed, cfg.use_anti_alias != 0, o, d);
 		st.ray_o[id] = make_float4(o.x, o.y, o.z, 0.0f);
 		st.ray_d[id] = make_float4(d.x, d.y, d.z, next_bounce_bound(cfg, cfg.air_sigma_a, cfg.air_sigma_s, seed, pixel, 0));
-		st.throughput[id] = make_float4(1.0f, 1.0f, 1.0f, __int_as_float(-1));
 		st.radiance[id] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
 		queue[i] = id;
 	}
@@ -592,10 +591,15 @@ __device__ __forceinline__ float3 sample_texture(const DeviceTexture& tex, float
 // continuing path does not add the emission of an emissive triangle it hits next.  Expected value as in the
 // reference: the reference picks emission up with probability (1 - F) at the light (Fresnel branch first,
 // path_tracer_kernel.cu:529-616), so the light sample carries that factor; same bounce limit and energy cut.
+#ifndef PTB_SHADE_MIN_BLOCKS
+#define PTB_SHADE_MIN_BLOCKS 10   // 48 registers: measured optimum (profiles/r01_experiments.md); the kernel is latency / HBM bound, occupancy pays
+#endif
 template <bool SORT, bool NEE>
-__global__ void __launch_bounds__(128) k_shade(DeviceScene sc, PathState st, DeviceConfig cfg, int depth, int pixel_count, int first_pass, int pass_stride,
-	const int* __restrict__ queue_in, const int* __restrict__ count_in, int* __restrict__ queue_out, int* __restrict__ count_out, int* __restrict__ shadow_count)
+__global__ void __launch_bounds__(128, PTB_SHADE_MIN_BLOCKS) k_shade(DeviceScene sc, PathState st, DeviceConfig cfg, int depth, int pixel_count, int first_pass, int pass_stride,
+	const int* __restrict__ queue_in, const int* __restrict__ count_in, int* __restrict__ queue_out, int* __restrict__ count_out, int* __restrict__ shadow_count,
+	int octant_order)
 {
+	__shared__ int s_oct[10];
 	__shared__ int s_ids[SORT ? 128 : 1];
 	__shared__ int s_hist[SORT ? 16 : 1];
 	const int count = *count_in;
@@ -607,6 +611,7 @@ __global__ void __launch_bounds__(128) k_shade(DeviceScene sc, PathState st, Dev
 		bool valid = i < count;
 		bool alive = false;
 		bool want_shadow = false;
+		int oct_key = 0;
 		int id = 0;
 		if (SORT)
 		{
@@ -642,7 +647,10 @@ __global__ void __launch_bounds__(128) k_shade(DeviceScene sc, PathState st, Dev
 			int pixel_index = id - slot * pixel_count;
 			int seed = first_pass + slot * pass_stride;
 
-			float4 o4 = st.ray_o[id], d4 = st.ray_d[id], t4 = st.throughput[id], h4 = st.hit[id];
+			// at depth 0 the throughput is (1, 1, 1) in air by construction (init_data_kernel :275-297): k_generate does not
+			// write it and it is not read here
+			float4 o4 = st.ray_o[id], d4 = st.ray_d[id], h4 = st.hit[id];
+			float4 t4 = depth == 0 ? make_float4(1.0f, 1.0f, 1.0f, __int_as_float(-1)) : st.throughput[id];
 			float3 ray_o = make_float3(o4.x, o4.y, o4.z);
 			float3 ray_d = make_float3(d4.x, d4.y, d4.z);
 			float3 not_absorbed = make_float3(t4.x, t4.y, t4.z);
@@ -676,6 +684,7 @@ __global__ void __launch_bounds__(128) k_shade(DeviceScene sc, PathState st, Dev
 					not_absorbed = not_absorbed * absorption_through_medium(sigma_a, scattering_distance);
 					st.ray_o[id] = make_float4(next_o.x, next_o.y, next_o.z, 0.0f);
 					st.ray_d[id] = make_float4(next_d.x, next_d.y, next_d.z, next_bounce_bound(cfg, sigma_a, sigma_s, seed, pixel_index, depth + 1));
+					oct_key = (next_d.x < 0.0f ? 4 : 0) | (next_d.y < 0.0f ? 2 : 0) | (next_d.z < 0.0f ? 1 : 0);
 					st.throughput[id] = make_float4(not_absorbed.x, not_absorbed.y, not_absorbed.z, t4.w);
 					if (length(not_absorbed) <= cfg.energy_threshold) alive = false;
 					done = true;
@@ -788,9 +797,14 @@ __global__ void __launch_bounds__(128) k_shade(DeviceScene sc, PathState st, Dev
 						const bool counted_by_nee = NEE && o4.w != 0.0f && prim >= 0 && (emission_color.x != 0.0f || emission_color.y != 0.0f || emission_color.z != 0.0f);
 						if (!counted_by_nee)
 						{
-							float4 r4 = st.radiance[id];
-							float3 add = not_absorbed * emission_color;
-							st.radiance[id] = make_float4(r4.x + add.x, r4.y + add.y, r4.z + add.z, 0.0f);
+							// accumulated += not_absorbed * emission (:608-609); adding an exact zero changes nothing, so the
+							// read-modify-write is skipped for non-emissive hits (a NaN / inf product still goes through)
+							const float3 add = not_absorbed * emission_color;
+							if (!(add.x == 0.0f && add.y == 0.0f && add.z == 0.0f))
+							{
+								const float4 r4 = st.radiance[id];
+								st.radiance[id] = make_float4(r4.x + add.x, r4.y + add.y, r4.z + add.z, 0.0f);
+							}
 						}
 						not_absorbed = not_absorbed * diffuse_color;
 						float rand1 = rng.next();
@@ -814,6 +828,7 @@ __global__ void __launch_bounds__(128) k_shade(DeviceScene sc, PathState st, Dev
 							}
 						}
 						st.ray_d[id] = make_float4(next_d.x, next_d.y, next_d.z, next_bounce_bound(cfg, nsa, nss, seed, pixel_index, depth + 1));
+						oct_key = (next_d.x < 0.0f ? 4 : 0) | (next_d.y < 0.0f ? 2 : 0) | (next_d.z < 0.0f ? 1 : 0);
 					}
 					if (length(not_absorbed) <= cfg.energy_threshold) alive = false;
 					if (NEE && nee_candidate && alive && depth + 1 < cfg.max_depth && sc.n_lights > 0 && !(nss.x > 0.0f || length(nsa) > cfg.sss_threshold))
@@ -876,6 +891,36 @@ __global__ void __launch_bounds__(128) k_shade(DeviceScene sc, PathState st, Dev
 				}
 			}
 		}
+		if (octant_order)
+		{
+			// block-level compaction grouped by the direction octant of the next ray: the 32 rays an extend warp
+			// fetches together then descend the tree in the same child order
+			if (threadIdx.x < 10) s_oct[threadIdx.x] = 0;
+			__syncthreads();
+			const int key = alive ? oct_key : 8;
+			const unsigned peers = __match_any_sync(0xffffffffu, key);
+			const int leader = __ffs(peers) - 1;
+			int in_key = 0;
+			if ((int)lane == leader && alive) in_key = atomicAdd(&s_oct[key], __popc(peers));
+			in_key = __shfl_sync(0xffffffffu, in_key, leader) + __popc(peers & ((1u << lane) - 1u));
+			__syncthreads();
+			if (threadIdx.x == 0)
+			{
+				int total = 0;
+				for (int k = 0; k < 8; k++) total += s_oct[k];
+				s_oct[9] = total ? atomicAdd(count_out, total) : 0;
+			}
+			__syncthreads();
+			if (alive)
+			{
+				int before = s_oct[9];
+				for (int k = 0; k < key; k++) before += s_oct[k];
+				queue_out[before + in_key] = id;
+			}
+			__syncthreads();
+		}
+		else
+		{
 		// stream compaction of survivors: one atomic per warp (replaces thrust::remove_if + host sync)
 		unsigned mask = __ballot_sync(0xffffffffu, alive);
 		if (mask)
@@ -884,6 +929,7 @@ __global__ void __launch_bounds__(128) k_shade(DeviceScene sc, PathState st, Dev
 			if (lane == 0) pos = atomicAdd(count_out, __popc(mask));
 			pos = __shfl_sync(0xffffffffu, pos, 0);
 			if (alive) queue_out[pos + __popc(mask & ((1u << lane) - 1u))] = id;
+		}
 		}
 		if (NEE)
 		{
@@ -1068,6 +1114,7 @@ struct ptb_renderer
 	float pass_clamp = -1.0f;              // < 0: the reference's per-pass clamp 2 * MaxDepth (path_tracer_kernel.cu:644-651)
 	int nee = 0;                           // estimator: 0 = the reference's (default, parity mode), 1 = next-event estimation
 	int sort_by_material = 0;              // block-local material sort in k_shade (measured: profiles/r01_experiments.md)
+	int octant_order = 0;                  // next-depth queue grouped by ray-direction octant per block (measured: profiles/r01_experiments.md)
 	int tile_order = 1;                    // camera rays enter the first queue in 8x4 pixel tiles
 	// facts about the last acceleration-structure build (ptb_bvh_info)
 	int bvh_built_on_gpu = 0, bvh_levels = 0, bvh_small_tasks = 0, bvh_max_depth = 0;
@@ -1594,16 +1641,16 @@ int enqueue_batch(ptb_renderer* r, ptb_renderer::BatchContext& ctx, cudaEvent_t 
 		const int sgrid = grid_for(r, total, 128, 16);
 		if (r->nee)
 		{
-			if (r->sort_by_material) k_shade<true, true><<<sgrid, 128, 0, stream>>>(r->dscene, ctx.st, dc, depth, px, first_pass, stride, qin, ctx.counts + depth, qout, ctx.counts + depth + 1, shadow_count);
-			else k_shade<false, true><<<sgrid, 128, 0, stream>>>(r->dscene, ctx.st, dc, depth, px, first_pass, stride, qin, ctx.counts + depth, qout, ctx.counts + depth + 1, shadow_count);
+			if (r->sort_by_material) k_shade<true, true><<<sgrid, 128, 0, stream>>>(r->dscene, ctx.st, dc, depth, px, first_pass, stride, qin, ctx.counts + depth, qout, ctx.counts + depth + 1, shadow_count, r->octant_order);
+			else k_shade<false, true><<<sgrid, 128, 0, stream>>>(r->dscene, ctx.st, dc, depth, px, first_pass, stride, qin, ctx.counts + depth, qout, ctx.counts + depth + 1, shadow_count, r->octant_order);
 			if (depth + 1 < r->cfg.max_tracer_depth)
 			{
 				k_shadow<<<sgrid, 128, 0, stream>>>(r->dscene, ctx.st, shadow_count);
 				r->stats.kernel_launches++;
 			}
 		}
-		else if (r->sort_by_material) k_shade<true, false><<<sgrid, 128, 0, stream>>>(r->dscene, ctx.st, dc, depth, px, first_pass, stride, qin, ctx.counts + depth, qout, ctx.counts + depth + 1, shadow_count);
-		else k_shade<false, false><<<sgrid, 128, 0, stream>>>(r->dscene, ctx.st, dc, depth, px, first_pass, stride, qin, ctx.counts + depth, qout, ctx.counts + depth + 1, shadow_count);
+		else if (r->sort_by_material) k_shade<true, false><<<sgrid, 128, 0, stream>>>(r->dscene, ctx.st, dc, depth, px, first_pass, stride, qin, ctx.counts + depth, qout, ctx.counts + depth + 1, shadow_count, r->octant_order);
+		else k_shade<false, false><<<sgrid, 128, 0, stream>>>(r->dscene, ctx.st, dc, depth, px, first_pass, stride, qin, ctx.counts + depth, qout, ctx.counts + depth + 1, shadow_count, r->octant_order);
 		r->stats.kernel_launches += 2;
 	}
 	if (prev_accumulated) PTB_CUDA(cudaStreamWaitEvent(stream, prev_accumulated, 0));
@@ -2124,7 +2171,7 @@ int ptb_capture_rays(ptb_renderer* r, int pass, int depth, int32_t* out_pixels, 
 	for (; d < depth && d < r->cfg.max_tracer_depth; d++)
 	{
 		launch_extend(r, r->stream, px, r->st, r->queue[d & 1], r->counts + d, r->counts + (r->cfg.max_tracer_depth + 2) + d);
-		k_shade<false, false><<<grid_for(r, px, 128, 16), 128, 0, r->stream>>>(r->dscene, r->st, dc, d, px, pass, 1, r->queue[d & 1], r->counts + d, r->queue[(d + 1) & 1], r->counts + d + 1, nullptr);
+		k_shade<false, false><<<grid_for(r, px, 128, 16), 128, 0, r->stream>>>(r->dscene, r->st, dc, d, px, pass, 1, r->queue[d & 1], r->counts + d, r->queue[(d + 1) & 1], r->counts + d + 1, nullptr, 0);
 	}
 	int count = 0;
 	if (cudaMemcpyAsync(&count, r->counts + d, sizeof(int), cudaMemcpyDeviceToHost, r->stream) != cudaSuccess || cudaStreamSynchronize(r->stream) != cudaSuccess)
@@ -2364,6 +2411,7 @@ int ptb_set_option(ptb_renderer* r, const char* key, const char* value)
 	if (k == "bvh_max_leaf") { int n = atoi(value); if (n < 1 || n > 8) { set_error("[Error]bvh_max_leaf must be in 1..8"); return 1; } r->bvh_max_leaf = n; return 0; }
 	if (k == "bvh_intersect_cost") { float c = (float)atof(value); if (!(c > 0.0f)) { set_error("[Error]bvh_intersect_cost must be > 0"); return 1; } r->bvh_intersect_cost = c; return 0; }
 	if (k == "tile_order") { r->tile_order = atoi(value); return 0; }
+	if (k == "octant_order") { r->octant_order = atoi(value); return 0; }
 	if (k == "sort_by_material") { r->sort_by_material = atoi(value); return 0; }
 	if (k == "pass_clamp") { r->pass_clamp = (float)atof(value); return 0; }   // diagnostic: per-pass clamp of the accumulation (default: the reference's)
 	if (k == "estimator")
