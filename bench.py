@@ -192,7 +192,17 @@ def main():
     try:
         w = make_scene(args.workload, root)
         if args.impl == "reference":
-            print(json.dumps(run_reference(args, w, root, rank, world)))
+            # the reference prints its "[Info]..." progress lines with printf/cout: keep stdout to the ONE JSON line
+            sys.stdout.flush()
+            saved = os.dup(1)
+            os.dup2(2, 1)
+            try:
+                line = run_reference(args, w, root, rank, world)
+            finally:
+                sys.stdout.flush()
+                os.dup2(saved, 1)
+            print(json.dumps(line))
+            sys.stdout.flush()
             return 0
         return run_ptb200(args, w, root, rank, local_rank, world)
     finally:
