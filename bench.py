@@ -256,6 +256,7 @@ def run_ptb200(args, w, root, rank, local_rank, world):
     st = r.stats()
     nodes_per_seg = st["nodes_visited"] / max(st["ray_segments"], 1)
     tris_per_seg = st["tris_tested"] / max(st["ray_segments"], 1)
+    wide_per_seg = st["wide_nodes_visited"] / max(st["ray_segments"], 1)
     r.set_option("count_traversal", 0)
     r.set_option("active_streams", 1)
     r.set_option("profile_stages", 1)
@@ -322,8 +323,8 @@ def run_ptb200(args, w, root, rank, local_rank, world):
         peaks, peak_kind = measured_peaks()
         seg_total, launches_total, _ = [float(x) for x in seg_t.tolist()]
         # algorithmic bytes of the extend (closest-hit) kernel per ray segment, SURVEY.md 8d:
-        # queue id 4 + ray o,d 32 + nodes*64 + tris*48 + hit record 16
-        bytes_per_seg = 4 + 32 + nodes_per_seg * 64.0 + tris_per_seg * 48.0 + 16
+        # queue id 4 + ray o,d 32 + binary nodes*64 + wide nodes*80 + tris*48 + hit record 16
+        bytes_per_seg = 4 + 32 + nodes_per_seg * 64.0 + wide_per_seg * 80.0 + tris_per_seg * 48.0 + 16
         seg_per_launch = serial_segments / max(serial_launches, 1)
         avg_launch_ms = serial_extend_ms / max(serial_launches, 1)
         achieved = seg_per_launch * bytes_per_seg / (avg_launch_ms / 1e3) / 1e9 if avg_launch_ms > 0 else None
@@ -341,7 +342,7 @@ def run_ptb200(args, w, root, rank, local_rank, world):
                              "frac": (achieved / peaks["hbm_gbs"]) if achieved else None, "traffic": NCU_DRAM_BYTES_PER_EXTEND_LAUNCH,
                              "traffic_source": "profiles/r01b_extend_shade_ncu_summary.md: dram__bytes_read.sum + dram__bytes_write.sum averaged over the 8 k_extend_persistent launches of one 8-pass batch of c2 (ncu --set full)",
                              "peak_source": peak_kind,
-                             "bytes_per_segment": bytes_per_seg, "nodes_per_segment": nodes_per_seg, "tris_per_segment": tris_per_seg,
+                             "bytes_per_segment": bytes_per_seg, "nodes_per_segment": nodes_per_seg, "wide_nodes_per_segment": wide_per_seg, "tris_per_segment": tris_per_seg,
                              "segments_per_launch": seg_per_launch, "avg_launch_ms": avg_launch_ms,
                              "how": "per-launch CUDA events on the launching stream with ONE stream in flight, immediately before the timed region "
                                     "(the timed region overlaps %d streams, so launches there are not exclusive); achieved counts cache-served "

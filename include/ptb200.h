@@ -66,6 +66,7 @@ typedef struct ptb_stats
 	int64_t bvh_bytes;         /* bytes of node + triangle intersection data */
 	int64_t nodes_visited;     /* instrumented builds only (ptb_set_option "count_traversal" = 1) */
 	int64_t tris_tested;
+	int64_t wide_nodes_visited; /* 80-byte compressed 8-wide nodes visited (layout 8 / hybrid bounce rays); nodes_visited counts 64-byte binary nodes */
 } ptb_stats;
 
 const char* ptb_last_error(void);

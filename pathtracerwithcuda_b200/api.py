@@ -38,7 +38,8 @@ class Camera(ctypes.Structure):
 class Stats(ctypes.Structure):
     _fields_ = [("passes", ctypes.c_int64), ("ray_segments", ctypes.c_int64), ("kernel_launches", ctypes.c_int64),
                 ("gpu_ms_total", ctypes.c_double), ("gpu_ms_extend", ctypes.c_double), ("bvh_nodes", ctypes.c_int64),
-                ("bvh_bytes", ctypes.c_int64), ("nodes_visited", ctypes.c_int64), ("tris_tested", ctypes.c_int64)]
+                ("bvh_bytes", ctypes.c_int64), ("nodes_visited", ctypes.c_int64), ("tris_tested", ctypes.c_int64),
+                ("wide_nodes_visited", ctypes.c_int64)]
 
 
 MATERIAL_DTYPE = np.dtype([("diffuse_color", np.float32, 3), ("emission_color", np.float32, 3), ("specular_color", np.float32, 3),

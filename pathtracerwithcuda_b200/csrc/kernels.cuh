@@ -28,6 +28,8 @@ struct DeviceScene
 	const float4* bvh_nodes;      // layout 2: 4 x float4 per binary node; layout 8: 5 x float4 per compressed wide node (bvh.h)
 	const float4* tri_isect;      // 3 x float4 per triangle, leaf order
 	int bvh_layout;               // 2 or 8
+	const float4* bvh8_nodes;     // hybrid mode: a second, compressed 8-wide tree over the same triangles (bounce rays), else nullptr
+	const float4* tri_isect8;     // its triangles in ITS leaf order
 	const float4* tri_shade;      // 4 x float4 per triangle, by global triangle id:
 	                              //   n0.xyz n1.x | n1.yz n2.xy | n2.z uv0.xy uv1.x | uv1.y uv2.xy material(bits)
 	const DeviceMaterial* materials; // mesh materials, then one per sphere

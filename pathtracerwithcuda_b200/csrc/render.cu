@@ -408,7 +408,11 @@ __global__ void __launch_bounds__(128, PTB_PERSISTENT_MIN_BLOCKS) k_extend_persi
 		// retire finished rays (no vote needed: a plain predicated store)
 		if (id >= 0 && node == PTB_DONE)
 		{
+#ifndef PTB_NO_STREAMING_HINTS
+			__stcs(&st.hit[id], make_float4(best.prim == -1 ? CUDART_INF_F : best.t, best.t1, best.t2, __int_as_float(best.prim)));
+#else
 			st.hit[id] = make_float4(best.prim == -1 ? CUDART_INF_F : best.t, best.t1, best.t2, __int_as_float(best.prim));
+#endif
 			id = -1;
 			if (COUNT)
 			{
@@ -436,8 +440,13 @@ __global__ void __launch_bounds__(128, PTB_PERSISTENT_MIN_BLOCKS) k_extend_persi
 				const int i = base + __popc(m_idle & lane_lt);
 				if (i < count)
 				{
+#ifndef PTB_NO_STREAMING_HINTS   // ray records are read once: keep them from displacing tree nodes in L1 (+0.5 %)
+					id = __ldcs(&queue[i]);
+					const float4 o4 = __ldcs(&st.ray_o[id]), d4 = __ldcs(&st.ray_d[id]);
+#else
 					id = queue[i];
 					const float4 o4 = st.ray_o[id], d4 = st.ray_d[id];
+#endif
 					o = make_float3(o4.x, o4.y, o4.z);
 					d = make_float3(d4.x, d4.y, d4.z);
 					best.t = d4.w; best.t1 = CUDART_INF_F; best.t2 = CUDART_INF_F; best.prim = -1;   // d4.w: free-flight bound (next_bounce_bound)
@@ -539,6 +548,187 @@ __global__ void __launch_bounds__(128, PTB_PERSISTENT_MIN_BLOCKS) k_extend_persi
 		if (lane == 0)
 		{
 			atomicAdd(&counters[0], (unsigned long long)n_nodes);
+			atomicAdd(&counters[1], (unsigned long long)n_tris);
+		}
+	}
+}
+
+// ------------------------------------------------------------------------------------------
+// k_extend_persistent8 — the same persistent, warp-voting scheme over the compressed 8-wide layout
+// (bvh.h layout #2).  Lane state: `current` = a group of not-yet-visited inner children of one wide node
+// (child base + hit bits), `tri_group` = leaf triangles still to test; stack entries are node groups.
+// Phases: refill | wide-node step (one child popped, 8 quantised boxes decoded and tested) | triangle step.
+// ------------------------------------------------------------------------------------------
+template <bool COUNT>
+__global__ void __launch_bounds__(128, PTB_PERSISTENT_MIN_BLOCKS) k_extend_persistent8(DeviceScene sc, PathState st, const int* __restrict__ queue, const int* __restrict__ count_ptr,
+	int* __restrict__ work_counter, unsigned long long* __restrict__ counters, int refill_min, int leaf_min)
+{
+	const int count = *count_ptr;
+	const unsigned lane = threadIdx.x & 31u;
+	const unsigned lane_lt = (1u << lane) - 1u;
+	const unsigned FULL = 0xffffffffu;
+	unsigned n_nodes = 0, n_tris = 0;
+
+	int id = -1;
+	bool exhausted = false;
+	float3 o = make_float3(0, 0, 0), d = o, idir = o;
+	unsigned oct_inv4 = 0;
+	HitRecord best;
+	best.t = CUDART_INF_F; best.t1 = 0.0f; best.t2 = 0.0f; best.prim = -1;
+	int best_tri = 0x7fffffff;
+	uint2 stack[PTB_STACK_SIZE8];
+	int sp = 0;
+	uint2 current = make_uint2(0u, 0u), tri_group = make_uint2(0u, 0u);
+
+	while (true)
+	{
+		// bookkeeping without votes: pop a node group when the lane ran dry, retire when nothing is left
+		if (id >= 0 && (current.y & 0xff000000u) == 0u && tri_group.y == 0u)
+		{
+			if (sp > 0) current = stack[--sp];
+			else
+			{
+				__stcs(&st.hit[id], make_float4(best.prim == -1 ? CUDART_INF_F : best.t, best.t1, best.t2, __int_as_float(best.prim)));
+				id = -1;
+			}
+		}
+		const bool has_ray = id >= 0;
+		const bool at_tri = has_ray && tri_group.y != 0u;
+		const bool at_node = has_ray && !at_tri && (current.y & 0xff000000u) != 0u;
+		const unsigned m_idle = __ballot_sync(FULL, !has_ray);
+		const unsigned m_node = __ballot_sync(FULL, at_node);
+		const unsigned m_tri = __ballot_sync(FULL, at_tri);
+
+		if (m_idle != 0u && !exhausted && (__popc(m_idle) >= refill_min || (m_node | m_tri) == 0u))
+		{
+			const int n = __popc(m_idle);
+			int base = 0;
+			if (lane == 0) base = atomicAdd(work_counter, n);
+			base = __shfl_sync(FULL, base, 0);
+			if (base + n >= count) exhausted = true;
+			if (!has_ray)
+			{
+				const int i = base + __popc(m_idle & lane_lt);
+				if (i < count)
+				{
+					id = __ldcs(&queue[i]);
+					const float4 o4 = __ldcs(&st.ray_o[id]), d4 = __ldcs(&st.ray_d[id]);
+					o = make_float3(o4.x, o4.y, o4.z);
+					d = make_float3(d4.x, d4.y, d4.z);
+					best.t = d4.w; best.t1 = CUDART_INF_F; best.t2 = CUDART_INF_F; best.prim = -1;
+					best_tri = 0x7fffffff;
+					for (int s = 0; s < sc.n_spheres; s++)
+					{
+						const float4 sph = __ldg(&sc.spheres[s]);
+						float t;
+						if (intersect_sphere(make_float3(sph.x, sph.y, sph.z), sph.w, o, d, t) && t < best.t && t > 0.0f)
+						{
+							best.t = t;
+							best.prim = -(s + 2);
+						}
+					}
+					const float tiny = 1e-30f;
+					const float3 ds = make_float3(fabsf(d.x) < tiny ? copysignf(tiny, d.x) : d.x, fabsf(d.y) < tiny ? copysignf(tiny, d.y) : d.y,
+						fabsf(d.z) < tiny ? copysignf(tiny, d.z) : d.z);
+					idir = make_float3(1.0f / ds.x, 1.0f / ds.y, 1.0f / ds.z);
+					oct_inv4 = (d.x < 0.0f ? 0u : 0x04040404u) | (d.y < 0.0f ? 0u : 0x02020202u) | (d.z < 0.0f ? 0u : 0x01010101u);
+					sp = 0;
+					tri_group = make_uint2(0u, 0u);
+					current = sc.n_triangles > 0 ? make_uint2(0u, 0x80000000u) : make_uint2(0u, 0u);
+				}
+			}
+			continue;
+		}
+		if ((m_node | m_tri) == 0u) break;
+
+		if (m_tri != 0u && (__popc(m_tri) >= leaf_min || m_node == 0u))
+		{
+			// ---- triangle phase
+			if (at_tri)
+			{
+				while (tri_group.y)
+				{
+					const unsigned k = 31u - __clz(tri_group.y);
+					tri_group.y &= ~(1u << k);
+					if (COUNT) n_tris++;
+					const float4* tp = sc.tri_isect + (size_t)(tri_group.x + k) * 3;
+					const float4 a = __ldg(tp + 0), b = __ldg(tp + 1), c = __ldg(tp + 2);
+					float t, t1, t2;
+					if (intersect_triangle(make_float3(a.x, a.y, a.z), make_float3(b.x, b.y, b.z), make_float3(c.x, c.y, c.z), o, d, t, t1, t2) && t > 0.0f)
+					{
+						const int tid = __float_as_int(a.w);
+						if (t < best.t || (t == best.t && best.prim >= 0 && tid < best_tri))
+						{
+							best.t = t; best.t1 = t1; best.t2 = t2; best.prim = tid; best_tri = tid;
+						}
+					}
+				}
+			}
+			continue;
+		}
+
+		// ---- wide-node phase
+		if (at_node)
+		{
+			const unsigned hits_imask = current.y;
+			const unsigned child_index_offset = 31u - __clz(hits_imask);
+			const unsigned child_index_base = current.x;
+			current.y &= ~(1u << child_index_offset);
+			if (current.y & 0xff000000u) { if (sp < PTB_STACK_SIZE8) stack[sp++] = current; }
+			const unsigned slot_index = (child_index_offset - 24u) ^ (oct_inv4 & 0xffu);
+			const unsigned relative_index = __popc(hits_imask & ~(0xffffffffu << slot_index));
+			const unsigned node_index = child_index_base + relative_index;
+			if (COUNT) n_nodes++;
+
+			const float4* np = sc.bvh_nodes + (size_t)node_index * 5;
+			const float4 n0 = __ldg(np + 0), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3), n4 = __ldg(np + 4);
+			const unsigned e_imask = __float_as_uint(n0.w);
+			const float3 adir = make_float3(__uint_as_float(extract_byte(e_imask, 0) << 23) * idir.x, __uint_as_float(extract_byte(e_imask, 1) << 23) * idir.y,
+				__uint_as_float(extract_byte(e_imask, 2) << 23) * idir.z);
+			const float3 aorg = make_float3((n0.x - o.x) * idir.x, (n0.y - o.y) * idir.y, (n0.z - o.z) * idir.z);
+			unsigned hit_mask = 0;
+#pragma unroll
+			for (int half = 0; half < 2; half++)
+			{
+				const unsigned meta4 = __float_as_uint(half == 0 ? n1.z : n1.w);
+				const unsigned is_inner4 = (meta4 & (meta4 << 1)) & 0x10101010u;
+				const unsigned inner_mask4 = sign_extend_s8x4(is_inner4 << 3);
+				const unsigned bit_index4 = (meta4 ^ (oct_inv4 & inner_mask4)) & 0x1f1f1f1fu;
+				const unsigned child_bits4 = (meta4 >> 5) & 0x07070707u;
+				const unsigned qlox = __float_as_uint(half == 0 ? n2.x : n2.y), qhix = __float_as_uint(half == 0 ? n2.z : n2.w);
+				const unsigned qloy = __float_as_uint(half == 0 ? n3.x : n3.y), qhiy = __float_as_uint(half == 0 ? n3.z : n3.w);
+				const unsigned qloz = __float_as_uint(half == 0 ? n4.x : n4.y), qhiz = __float_as_uint(half == 0 ? n4.z : n4.w);
+				const unsigned x_min = d.x < 0.0f ? qhix : qlox, x_max = d.x < 0.0f ? qlox : qhix;
+				const unsigned y_min = d.y < 0.0f ? qhiy : qloy, y_max = d.y < 0.0f ? qloy : qhiy;
+				const unsigned z_min = d.z < 0.0f ? qhiz : qloz, z_max = d.z < 0.0f ? qloz : qhiz;
+#pragma unroll
+				for (int j = 0; j < 4; j++)
+				{
+					const float tx0 = fmaf((float)extract_byte(x_min, j), adir.x, aorg.x), tx1 = fmaf((float)extract_byte(x_max, j), adir.x, aorg.x);
+					const float ty0 = fmaf((float)extract_byte(y_min, j), adir.y, aorg.y), ty1 = fmaf((float)extract_byte(y_max, j), adir.y, aorg.y);
+					const float tz0 = fmaf((float)extract_byte(z_min, j), adir.z, aorg.z), tz1 = fmaf((float)extract_byte(z_max, j), adir.z, aorg.z);
+					const float tmin = fmaxf(fmaxf(tx0, ty0), fmaxf(tz0, 0.0f));
+					const float tmax = fminf(fminf(tx1, ty1), fminf(tz1, best.t));
+					if (tmin * PTB_SLACK_LO <= tmax * PTB_SLACK_HI)
+						hit_mask |= extract_byte(child_bits4, j) << extract_byte(bit_index4, j);
+				}
+			}
+			current.x = __float_as_uint(n1.x);
+			tri_group.x = __float_as_uint(n1.y);
+			current.y = (hit_mask & 0xff000000u) | (e_imask >> 24);
+			tri_group.y = hit_mask & 0x00ffffffu;
+		}
+	}
+	if (COUNT)
+	{
+		for (int off = 16; off > 0; off >>= 1)
+		{
+			n_nodes += __shfl_down_sync(FULL, n_nodes, off);
+			n_tris += __shfl_down_sync(FULL, n_tris, off);
+		}
+		if (lane == 0)
+		{
+			atomicAdd(&counters[3], (unsigned long long)n_nodes);   // wide-node visits are tallied apart from binary-node visits
 			atomicAdd(&counters[1], (unsigned long long)n_tris);
 		}
 	}
@@ -1109,6 +1299,9 @@ struct ptb_renderer
 	int count_traversal = 0;
 	std::string bvh_builder = "gpu_sah";   // "gpu_sah" (csrc/bvh_build.cu) | "host_sah" (csrc/bvh_host.cpp)
 	int bvh_layout = 2;
+	int bvh_hybrid = 1;                    // layout 2 only: also build the compressed 8-wide tree and trace depth >= hybrid_from_depth with it
+	int hybrid_from_depth = 2;             // measured: c2 -0.4 %, c3 +1.2 %, c4 +8.4 % against binary-only (from depth 1: c2 -2.8 %)
+	int64_t bvh8_nodes = 0;
 	int bvh_max_leaf = 8;                  // binary layout; the wide layout holds <= 3 per leaf slot
 	float bvh_intersect_cost = 0.8f;       // SAH cost of a triangle test relative to a node visit (measured optimum on c2, profiles/r01_experiments.md)
 	float pass_clamp = -1.0f;              // < 0: the reference's per-pass clamp 2 * MaxDepth (path_tracer_kernel.cu:644-651)
@@ -1122,6 +1315,7 @@ struct ptb_renderer
 	std::string bvh_note;
 	int extend_persistent = 1;
 	int persistent_grid = 148 * 4;
+	int persistent_grid8 = 148 * 4;
 	int tune_refill = 12, tune_leaf = 8, tune_reps = 3;
 
 	cudaStream_t stream = nullptr;
@@ -1443,6 +1637,37 @@ int upload_geometry(ptb_renderer* r)
 	ds.bvh_layout = r->bvh_layout;
 	ds.n_triangles = n_tris;
 	ds.root_ref = 0;
+	ds.bvh8_nodes = nullptr; ds.tri_isect8 = nullptr;
+	r->bvh8_nodes = 0;
+	if (r->bvh_layout == 2 && r->bvh_hybrid && n_tris > 0)
+	{
+		// Hybrid: coherent camera rays are issue-bound and fastest on the binary tree; bounce rays are bound by L1
+		// wavefronts and fastest on the compressed wide tree, which moves half the bytes per ray (measured on c2:
+		// depth 0 8.2 vs 10.8 ms, depth 1 10.3 vs 8.7 ms per 32 passes; profiles/r01_experiments.md).  Both trees
+		// return the same hits (conservative culling, the winner is decided by the same triangle arithmetic).
+		Bvh2 tree3;
+		GpuBuildOutput gb;
+		std::string why;
+		bool have = false;
+		if (r->bvh_builder != "host_sah" && build_bvh2_gpu(d_tris24, n_tris, 3, r->bvh_intersect_cost, r->stream, gb, why) == 0)
+		{
+			const int rc = download_bvh2(gb, tree3);
+			cudaFree(gb.nodes); cudaFree(gb.tri_isect); cudaFree(gb.prim_order);
+			if (rc) return 1;
+			r->bvh_build_ms += gb.build_ms;
+			have = true;
+		}
+		if (!have) { cudaGetLastError(); build_bvh2_sah(s.triangles, 3, tree3, r->bvh_intersect_cost); }
+		GpuBvh8 wide;
+		build_bvh8(tree3, s.triangles, wide);
+		if (wide.max_depth <= PTB_STACK_SIZE8)
+		{
+			if (upload(r, (const float4*)wide.nodes.data(), wide.nodes.size() / 4, &ds.bvh8_nodes, G)) return 1;
+			if (upload(r, (const float4*)wide.tris.data(), wide.tris.size() / 4, &ds.tri_isect8, G)) return 1;
+			r->bvh8_nodes = (int64_t)wide.nodes.size() / 20;
+			r->bvh_bytes += (int64_t)(wide.nodes.size() + wide.tris.size()) * 4;
+		}
+	}
 
 	// shading attributes by global triangle id, packed on the device
 	{
@@ -1585,9 +1810,26 @@ int grid_for(const ptb_renderer* r, size_t items, int block, int blocks_per_sm)
 	return (int)std::max<size_t>(1, std::min(need, cap));
 }
 
-void launch_extend(ptb_renderer* r, cudaStream_t stream, size_t items, const PathState& st, const int* queue, const int* count_ptr, int* work_counter)
+void launch_extend(ptb_renderer* r, cudaStream_t stream, size_t items, const PathState& st, const int* queue, const int* count_ptr, int* work_counter, int depth = 0)
 {
 	bool wide = r->dscene.bvh_layout == 8;
+	if (r->dscene.bvh_layout == 2 && r->dscene.bvh8_nodes && r->extend_persistent && depth >= r->hybrid_from_depth)
+	{
+		// hybrid: bounce rays over the compressed wide tree
+		DeviceScene sc8 = r->dscene;
+		sc8.bvh_nodes = r->dscene.bvh8_nodes; sc8.tri_isect = r->dscene.tri_isect8; sc8.bvh_layout = 8;
+		int grid = std::max(1, std::min(r->persistent_grid8, (int)((items + 127) / 128)));
+		if (r->count_traversal) k_extend_persistent8<true><<<grid, 128, 0, stream>>>(sc8, st, queue, count_ptr, work_counter, r->counters, r->tune_refill, r->tune_leaf);
+		else k_extend_persistent8<false><<<grid, 128, 0, stream>>>(sc8, st, queue, count_ptr, work_counter, r->counters, r->tune_refill, r->tune_leaf);
+		return;
+	}
+	if (wide && r->extend_persistent)
+	{
+		int grid = std::max(1, std::min(r->persistent_grid8, (int)((items + 127) / 128)));
+		if (r->count_traversal) k_extend_persistent8<true><<<grid, 128, 0, stream>>>(r->dscene, st, queue, count_ptr, work_counter, r->counters, r->tune_refill, r->tune_leaf);
+		else k_extend_persistent8<false><<<grid, 128, 0, stream>>>(r->dscene, st, queue, count_ptr, work_counter, r->counters, r->tune_refill, r->tune_leaf);
+		return;
+	}
 	if (!wide && r->extend_persistent)
 	{
 		// persistent warps: one resident wave, sized from the occupancy the kernel actually gets
@@ -1635,7 +1877,7 @@ int enqueue_batch(ptb_renderer* r, ptb_renderer::BatchContext& ctx, cudaEvent_t 
 			r->stage_events.push_back(e0); r->stage_events.push_back(e1);
 			cudaEventRecord(e0, stream);
 		}
-		launch_extend(r, stream, total, ctx.st, qin, ctx.counts + depth, ctx.counts + n_counts + depth);
+		launch_extend(r, stream, total, ctx.st, qin, ctx.counts + depth, ctx.counts + n_counts + depth, depth);
 		if (prof) cudaEventRecord(e1, stream);
 		int* shadow_count = ctx.counts + 2 * n_counts + depth;
 		const int sgrid = grid_for(r, total, 128, 16);
@@ -1723,7 +1965,7 @@ int render_impl(ptb_renderer* r, int first_pass, int stride, int n_passes, bool 
 		{
 			unsigned long long c[32];
 			cudaMemcpy(c, r->counters, sizeof(c), cudaMemcpyDeviceToHost);
-			r->stats.nodes_visited = (int64_t)c[0]; r->stats.tris_tested = (int64_t)c[1];
+			r->stats.nodes_visited = (int64_t)c[0]; r->stats.tris_tested = (int64_t)c[1]; r->stats.wide_nodes_visited = (int64_t)c[3];
 			for (int k = 0; k < 32; k++) r->traversal_histogram[k] = (int64_t)c[k];
 		}
 	}
@@ -1834,6 +2076,8 @@ ptb_renderer* ptb_create(const char* config_json_path, int cuda_device)
 		int per_sm = 0;
 		if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_extend_persistent<false>, 128, 0) == cudaSuccess && per_sm > 0)
 			r->persistent_grid = r->sm_count * per_sm;
+		if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_extend_persistent8<false>, 128, 0) == cudaSuccess && per_sm > 0)
+			r->persistent_grid8 = r->sm_count * per_sm;
 	}
 	if (alloc_work_buffers(r)) { free_work_buffers(r); delete r; return nullptr; }
 	return r;
@@ -2170,7 +2414,7 @@ int ptb_capture_rays(ptb_renderer* r, int pass, int depth, int32_t* out_pixels, 
 	int d = 0;
 	for (; d < depth && d < r->cfg.max_tracer_depth; d++)
 	{
-		launch_extend(r, r->stream, px, r->st, r->queue[d & 1], r->counts + d, r->counts + (r->cfg.max_tracer_depth + 2) + d);
+		launch_extend(r, r->stream, px, r->st, r->queue[d & 1], r->counts + d, r->counts + (r->cfg.max_tracer_depth + 2) + d, d);
 		k_shade<false, false><<<grid_for(r, px, 128, 16), 128, 0, r->stream>>>(r->dscene, r->st, dc, d, px, pass, 1, r->queue[d & 1], r->counts + d, r->queue[(d + 1) & 1], r->counts + d + 1, nullptr, 0);
 	}
 	int count = 0;
@@ -2437,6 +2681,8 @@ int ptb_set_option(ptb_renderer* r, const char* key, const char* value)
 	if (k == "tune_leaf") { r->tune_leaf = atoi(value); return 0; }
 	if (k == "tune_reps") { r->tune_reps = atoi(value); return 0; }
 	if (k == "persistent_grid") { r->persistent_grid = atoi(value); return 0; }
+	if (k == "bvh_hybrid") { r->bvh_hybrid = atoi(value); return 0; }             // takes effect at the next ptb_load_scene
+	if (k == "hybrid_from_depth") { r->hybrid_from_depth = atoi(value); return 0; }
 	if (k == "bvh_layout")
 	{
 		int n = atoi(value);

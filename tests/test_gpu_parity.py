@@ -224,7 +224,8 @@ def test_bvh_layouts_agree(workload_root):
         prim, t, bary = r.trace_batch(rays, with_bary=True)
         r.render(2)
         st = r.stats()
-        assert st["nodes_visited"] > 0 and st["tris_tested"] > 0
+        st["all_nodes"] = st["nodes_visited"] + st["wide_nodes_visited"]      # 64-byte binary + 80-byte wide node visits
+        assert st["all_nodes"] > 0 and st["tris_tested"] > 0
         res[layout] = (prim, t, bary, r.image_f32().copy(), st)
         r.close()
     assert np.array_equal(res[2][0], res[8][0])
@@ -232,7 +233,8 @@ def test_bvh_layouts_agree(workload_root):
     assert np.array_equal(res[2][2].view(np.uint32), res[8][2].view(np.uint32))
     assert np.array_equal(res[2][3].view(np.uint32), res[8][3].view(np.uint32))
     # the wide tree visits far fewer nodes per ray
-    assert res[8][4]["nodes_visited"] < 0.6 * res[2][4]["nodes_visited"]
+    assert res[8][4]["all_nodes"] < 0.6 * res[2][4]["all_nodes"]
+    assert res[8][4]["nodes_visited"] == 0 and res[2][4]["wide_nodes_visited"] > 0      # layout 2 is hybrid: deep bounces use the wide tree
 
 
 def test_scheduling_options_do_not_change_the_image(workload_root):
@@ -241,7 +243,8 @@ def test_scheduling_options_do_not_change_the_image(workload_root):
     root, w = workload_root("mix", width=96, height=72)
     ref = None
     for opts in (dict(), dict(tile_order=0), dict(sort_by_material=1), dict(sort_by_material=1, tile_order=0, streams_in_flight=1),
-                 dict(extend_persistent=0), dict(bvh_max_leaf=2, bvh_intersect_cost=1.5)):
+                 dict(extend_persistent=0), dict(bvh_max_leaf=2, bvh_intersect_cost=1.5), dict(bvh_hybrid=0), dict(hybrid_from_depth=0),
+                 dict(bvh_layout=8), dict(octant_order=1)):
         r = gpu_renderer(w, root, **opts)
         r.set_camera(ptb.default_camera(w["width"], w["height"], w["aperture"], w["focal"]))
         r.render(5)

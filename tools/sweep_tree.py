@@ -22,7 +22,10 @@ for cfg in configs:
     r.load_scene(w["scene"], root)
     if w["aperture"] >= 0:
         r.set_camera(ptb.default_camera(w["width"], w["height"], w["aperture"], w["focal"]))
-    info = r.bvh_info()
+    try:
+        info = r.bvh_info()
+    except ptb.PtbError:
+        info = {"sah_cost": float("nan"), "leaves": 0, "build_ms": float("nan")}
     r.render(32)
     r.set_option("active_streams", 1); r.set_option("profile_stages", 1)
     best = None
@@ -39,5 +42,5 @@ for cfg in configs:
     st = r.stats()
     print("%-46s serial: extend %.2f step %.2f ms | overlapped step %.2f ms (%.0f Msamples/s) | d0 %.2f d1 %.2f d2 %.2f | nodes %.1f tris %.2f | sah %.2f leaves %d build %.1f ms"
           % (cfg or "(default)", best[0], best[1], over, w["width"] * w["height"] * 32 / over / 1e3, ms[0], ms[1], ms[2],
-             st["nodes_visited"] / st["ray_segments"], st["tris_tested"] / st["ray_segments"], info["sah_cost"], info["leaves"], info["build_ms"]), flush=True)
+             (st["nodes_visited"] + st["wide_nodes_visited"]) / st["ray_segments"], st["tris_tested"] / st["ray_segments"], info["sah_cost"], info["leaves"], info["build_ms"]), flush=True)
     r.close()
