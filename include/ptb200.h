@@ -159,9 +159,10 @@ int ptb_get_stats(ptb_renderer* r, ptb_stats* out);
 int ptb_get_depth_profile(ptb_renderer* r, int max_entries, int64_t* out_segments, double* out_extend_ms);
 /* Acceleration structure of the loaded scene (replaces the BVH producers Bvh/bvh.cpp:185-219,667-780,
  * 862-1047 + Kernel/bvh_morton_code_kernel.cu:298-346): facts about the last build and a structural
- * check of the DEVICE arrays (binary layout).  out_i[8]: node records, reachable inner nodes, leaves,
+ * check of the DEVICE arrays (binary layout).  out_i[10]: node records, reachable inner nodes, leaves,
  * depth, valid (every triangle in exactly one leaf, vertices inside the leaf box, child boxes inside the
- * parent's), built on the GPU (1/0), level-synchronous rounds, sub-trees finished in shared memory.
+ * parent's), built on the GPU (1/0), level-synchronous rounds, sub-trees finished in shared memory, compressed 8-wide
+ * nodes of the hybrid bounce-ray tree, wide tree collapsed on the GPU (1/0).
  * out_d[4]: builder milliseconds (CUDA events for the GPU builder), SAH cost, whole scene upload ms,
  * violations found.  ptb_bvh_leaf_labels: per triangle the smallest triangle id sharing its leaf. */
 int ptb_bvh_info(ptb_renderer* r, int64_t* out_i, double* out_d);

@@ -387,12 +387,13 @@ class Renderer:
         return seg[:max(n, 0)].copy(), ms[:max(n, 0)].copy()
 
     def bvh_info(self):
-        oi = np.zeros(8, np.int64)
+        oi = np.zeros(10, np.int64)
         od = np.zeros(4, np.float64)
         self._check(self.lib.ptb_bvh_info(self.handle, _ptr(oi), _ptr(od)))
         return {"node_records": int(oi[0]), "inner_nodes": int(oi[1]), "leaves": int(oi[2]), "depth": int(oi[3]), "valid": bool(oi[4]),
                 "built_on_gpu": bool(oi[5]), "levels": int(oi[6]), "small_subtrees": int(oi[7]), "build_ms": float(od[0]),
-                "sah_cost": float(od[1]), "upload_ms": float(od[2]), "violations": int(od[3])}
+                "sah_cost": float(od[1]), "upload_ms": float(od[2]), "violations": int(od[3]),
+                "wide_nodes": int(oi[8]), "wide_collapsed_on_gpu": bool(oi[9])}
 
     def bvh_download(self):
         nodes = np.zeros((self.bvh_info()["node_records"], 16), np.float32)

@@ -17,6 +17,7 @@
 #include <math_constants.h>
 
 #include <algorithm>
+#include <cstdint>
 #include <cstdio>
 #include <vector>
 
@@ -761,6 +762,209 @@ __global__ void __launch_bounds__(kThreads) k_pack_shade(const float* __restrict
 	}
 }
 
+// ------------------------------------------------------------------------------------------
+// Collapse of the binary tree into the compressed 8-wide layout (bvh.h layout #2) on the device.
+// Same rules as the host WideBuilder (bvh_host.cpp): open the inner child with the largest surface area until 8
+// children, greedy octant-slot assignment, per-node power-of-two quantisation grid rounded outwards, inner
+// children contiguous from child_base, leaf triangles (<= 3 per slot) contiguous from tri_base.
+// One thread per wide node, one launch per level of the wide tree (breadth first).
+// ------------------------------------------------------------------------------------------
+struct WideItem
+{
+	int ref2;        // binary node this wide node is made from
+	int wide;        // index of the wide node to write
+	float lo[3], hi[3];
+};
+
+struct WideCounters
+{
+	int n_out, n_nodes, n_tris, max_depth, overflow;
+};
+
+__device__ __forceinline__ void read_binary_children(const float4* nodes2, int ref2, float (&blo)[2][3], float (&bhi)[2][3], int (&refs)[2])
+{
+	const float4* n = nodes2 + (size_t)ref2 * 4;
+	const float4 n0 = n[0], n1 = n[1], n2 = n[2], n3 = n[3];
+	blo[0][0] = n0.x; bhi[0][0] = n0.y; blo[0][1] = n0.z; bhi[0][1] = n0.w; blo[0][2] = n2.x; bhi[0][2] = n2.y;
+	blo[1][0] = n1.x; bhi[1][0] = n1.y; blo[1][1] = n1.z; bhi[1][1] = n1.w; blo[1][2] = n2.z; bhi[1][2] = n2.w;
+	refs[0] = __float_as_int(n3.x); refs[1] = __float_as_int(n3.y);
+}
+
+__global__ void __launch_bounds__(128) k_collapse8(const float4* __restrict__ nodes2, const int* __restrict__ prim_order, const float* __restrict__ tris24,
+	const WideItem* __restrict__ items_in, int n_in, WideItem* __restrict__ items_out, WideCounters* __restrict__ wc,
+	uint32_t* __restrict__ nodes8, float* __restrict__ tris8, int cap_nodes, int cap_tris, int depth)
+{
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n_in) return;
+	const WideItem it = items_in[i];
+	int ref[8];
+	float clo[8][3], chi[8][3];
+	int n = 0;
+	{
+		float blo[2][3], bhi[2][3];
+		int refs[2];
+		read_binary_children(nodes2, it.ref2, blo, bhi, refs);
+		for (int k = 0; k < 2; k++)
+		{
+			if (blo[k][0] > bhi[k][0]) continue;    // the empty second child of a single-leaf tree
+			ref[n] = refs[k];
+			for (int a = 0; a < 3; a++) { clo[n][a] = blo[k][a]; chi[n][a] = bhi[k][a]; }
+			n++;
+		}
+	}
+	while (n < 8)
+	{
+		int best = -1;
+		float best_area = -1.0f;
+		for (int c = 0; c < n; c++)
+		{
+			if (ref[c] < 0) continue;
+			const float a = area_half(clo[c], chi[c]);
+			if (a > best_area) { best_area = a; best = c; }
+		}
+		if (best < 0) break;
+		float blo[2][3], bhi[2][3];
+		int refs[2];
+		read_binary_children(nodes2, ref[best], blo, bhi, refs);
+		ref[best] = refs[0];
+		ref[n] = refs[1];
+		for (int a = 0; a < 3; a++) { clo[best][a] = blo[0][a]; chi[best][a] = bhi[0][a]; clo[n][a] = blo[1][a]; chi[n][a] = bhi[1][a]; }
+		n++;
+	}
+
+	// greedy octant slots: slot s prefers the child lying furthest along (s&4 ? +x : -x, s&2 ? +y : -y, s&1 ? +z : -z)
+	int slot_child[8];
+	{
+		float dcen[8][3];
+		for (int c = 0; c < n; c++)
+			for (int a = 0; a < 3; a++) dcen[c][a] = 0.5f * (clo[c][a] + chi[c][a]) - 0.5f * (it.lo[a] + it.hi[a]);
+		unsigned child_done = 0, slot_done = 0;
+		for (int s = 0; s < 8; s++) slot_child[s] = -1;
+		for (int k = 0; k < n; k++)
+		{
+			int bc = -1, bs = -1;
+			float bestv = -CUDART_INF_F;
+			for (int c = 0; c < n; c++)
+			{
+				if (child_done & (1u << c)) continue;
+				for (int s = 0; s < 8; s++)
+				{
+					if (slot_done & (1u << s)) continue;
+					const float v = ((s & 4) ? dcen[c][0] : -dcen[c][0]) + ((s & 2) ? dcen[c][1] : -dcen[c][1]) + ((s & 1) ? dcen[c][2] : -dcen[c][2]);
+					if (v > bestv || bc < 0) { bestv = v; bc = c; bs = s; }
+				}
+			}
+			child_done |= 1u << bc; slot_done |= 1u << bs;
+			slot_child[bs] = bc;
+		}
+	}
+
+	// quantisation grid of this node
+	float p[3], scale[3];
+	uint32_t e[3];
+	for (int a = 0; a < 3; a++)
+	{
+		p[a] = pad_down(it.lo[a]);
+		const float extent = __fsub_rn(pad_up(it.hi[a]), p[a]);
+		int e2;
+		const float m = frexpf(fmaxf(extent, 1e-30f) / 255.0f, &e2);   // m in [0.5, 1)
+		int ex = m > 0.5f ? e2 : e2 - 1;
+		while (ldexpf(255.0f, ex) < extent) ex++;
+		ex = max(-126, min(127, ex));
+		e[a] = (uint32_t)(ex + 127);
+		scale[a] = ldexpf(1.0f, -ex);
+	}
+
+	uint32_t imask = 0;
+	int n_inner = 0, n_leaf_tris = 0;
+	for (int s = 0; s < 8; s++)
+	{
+		const int c = slot_child[s];
+		if (c < 0) continue;
+		if (ref[c] >= 0) { imask |= 1u << s; n_inner++; }
+		else n_leaf_tris += min(((~ref[c]) & 7) + 1, 3);
+	}
+	int child_base = n_inner ? atomicAdd(&wc->n_nodes, n_inner) : 0;
+	int tri_base = n_leaf_tris ? atomicAdd(&wc->n_tris, n_leaf_tris) : 0;
+	int out_base = n_inner ? atomicAdd(&wc->n_out, n_inner) : 0;
+	if (child_base + n_inner > cap_nodes || tri_base + n_leaf_tris > cap_tris) { wc->overflow = 1; return; }
+	if (n_inner) atomicMax(&wc->max_depth, depth + 1);
+
+	uint32_t meta[8], qlo[3][8], qhi[3][8];
+	int inner_rank = 0, tri_offset = 0;
+	for (int s = 0; s < 8; s++)
+	{
+		meta[s] = 0;
+		for (int a = 0; a < 3; a++) { qlo[a][s] = 0; qhi[a][s] = 0; }
+		const int c = slot_child[s];
+		if (c < 0) continue;
+		for (int a = 0; a < 3; a++)
+		{
+			const float lo = floorf(__fmul_rn(__fsub_rn(pad_down(clo[c][a]), p[a]), scale[a]));
+			const float hi = ceilf(__fmul_rn(__fsub_rn(pad_up(chi[c][a]), p[a]), scale[a]));
+			qlo[a][s] = (uint32_t)fmaxf(0.0f, fminf(255.0f, lo));
+			qhi[a][s] = (uint32_t)fmaxf(0.0f, fminf(255.0f, hi));
+		}
+		if (ref[c] >= 0)
+		{
+			meta[s] = (1u << 5) | (24u + (uint32_t)s);
+			WideItem o;
+			o.ref2 = ref[c]; o.wide = child_base + inner_rank;
+			for (int a = 0; a < 3; a++) { o.lo[a] = clo[c][a]; o.hi[a] = chi[c][a]; }
+			items_out[out_base + inner_rank] = o;
+			inner_rank++;
+		}
+		else
+		{
+			const int lr = ~ref[c], first = lr >> 3, count = min((lr & 7) + 1, 3);
+			const uint32_t unary = count == 1 ? 1u : (count == 2 ? 3u : 7u);
+			meta[s] = (unary << 5) | (uint32_t)tri_offset;
+			for (int k = 0; k < count; k++)
+			{
+				const int id = prim_order[first + k];
+				const float* t = tris24 + (size_t)id * 24;
+				float* d = tris8 + (size_t)(tri_base + tri_offset + k) * 12;
+				const float v0x = t[0], v0y = t[1], v0z = t[2];
+				d[0] = v0x; d[1] = v0y; d[2] = v0z; d[3] = __int_as_float(id);
+				d[4] = __fsub_rn(t[3], v0x); d[5] = __fsub_rn(t[4], v0y); d[6] = __fsub_rn(t[5], v0z); d[7] = 0.0f;
+				d[8] = __fsub_rn(t[6], v0x); d[9] = __fsub_rn(t[7], v0y); d[10] = __fsub_rn(t[8], v0z); d[11] = 0.0f;
+			}
+			tri_offset += count;
+		}
+	}
+	uint32_t* d = nodes8 + (size_t)it.wide * 20;
+	d[0] = __float_as_uint(p[0]); d[1] = __float_as_uint(p[1]); d[2] = __float_as_uint(p[2]);
+	d[3] = e[0] | (e[1] << 8) | (e[2] << 16) | (imask << 24);
+	d[4] = (uint32_t)child_base;
+	d[5] = (uint32_t)tri_base;
+	d[6] = meta[0] | (meta[1] << 8) | (meta[2] << 16) | (meta[3] << 24);
+	d[7] = meta[4] | (meta[5] << 8) | (meta[6] << 16) | (meta[7] << 24);
+	for (int a = 0; a < 3; a++)
+	{
+		d[8 + a * 4 + 0] = qlo[a][0] | (qlo[a][1] << 8) | (qlo[a][2] << 16) | (qlo[a][3] << 24);
+		d[8 + a * 4 + 1] = qlo[a][4] | (qlo[a][5] << 8) | (qlo[a][6] << 16) | (qlo[a][7] << 24);
+		d[8 + a * 4 + 2] = qhi[a][0] | (qhi[a][1] << 8) | (qhi[a][2] << 16) | (qhi[a][3] << 24);
+		d[8 + a * 4 + 3] = qhi[a][4] | (qhi[a][5] << 8) | (qhi[a][6] << 16) | (qhi[a][7] << 24);
+	}
+}
+
+__global__ void k_collapse8_root(const float4* __restrict__ nodes2, WideItem* items, WideCounters* wc)
+{
+	float blo[2][3], bhi[2][3];
+	int refs[2];
+	read_binary_children(nodes2, 0, blo, bhi, refs);
+	WideItem it;
+	it.ref2 = 0; it.wide = 0;
+	const bool second_empty = blo[1][0] > bhi[1][0];
+	for (int a = 0; a < 3; a++)
+	{
+		it.lo[a] = second_empty ? blo[0][a] : fminf(blo[0][a], blo[1][a]);
+		it.hi[a] = second_empty ? bhi[0][a] : fmaxf(bhi[0][a], bhi[1][a]);
+	}
+	items[0] = it;
+	wc->n_out = 0; wc->n_nodes = 1; wc->n_tris = 0; wc->max_depth = 1; wc->overflow = 0;
+}
+
 struct DeviceBuffers
 {
 	std::vector<void*> ptrs;
@@ -858,6 +1062,57 @@ int build_bvh2_gpu(const float* d_tris24, int n, int max_leaf_size, float inters
 	results.release(A.nodes); results.release(tri_isect); results.release(A.idx_final);
 	out.n_nodes = hc.n_nodes; out.n_prims = n; out.max_depth = hc.max_depth; out.levels = level; out.small_tasks = hc.n_small; out.build_ms = ms;
 	if (hc.root_ref != 0) { err = "build_bvh2_gpu: internal error (root is not node 0)"; cudaFree(out.nodes); cudaFree(out.tri_isect); cudaFree(out.prim_order); out = GpuBuildOutput(); return 1; }
+	return 0;
+}
+
+int collapse_bvh8_gpu(const GpuBuildOutput& tree, const float* d_tris24, cudaStream_t stream, GpuWideOutput& out, std::string& err)
+{
+	out = GpuWideOutput();
+	const int n = tree.n_prims;
+	if (n <= 0 || tree.n_nodes <= 0) { err = "collapse_bvh8_gpu: empty tree"; return 1; }
+	const int cap_nodes = tree.n_nodes + 1, cap_tris = n;
+	DeviceBuffers scratch, results;
+	WideItem* items[2] = { nullptr, nullptr };
+	WideCounters* wc = nullptr;
+	uint32_t* nodes8 = nullptr;
+	float* tris8 = nullptr;
+	if (!scratch.alloc(&items[0], cap_nodes) || !scratch.alloc(&items[1], cap_nodes) || !scratch.alloc(&wc, 1) ||
+		!results.alloc(&nodes8, (size_t)cap_nodes * 20) || !results.alloc(&tris8, (size_t)cap_tris * 12))
+	{
+		cudaGetLastError();
+		err = "[Cuda]collapse_bvh8_gpu: out of device memory";
+		return 1;
+	}
+	cudaEvent_t e0, e1;
+	cudaEventCreate(&e0); cudaEventCreate(&e1);
+	cudaEventRecord(e0, stream);
+	k_collapse8_root<<<1, 1, 0, stream>>>(tree.nodes, items[0], wc);
+	WideCounters hc;
+	int n_cur = 1, level = 0;
+	cudaError_t e = cudaSuccess;
+	while (n_cur > 0 && e == cudaSuccess)
+	{
+		k_collapse8<<<(n_cur + 127) / 128, 128, 0, stream>>>(tree.nodes, tree.prim_order, d_tris24, items[level & 1], n_cur, items[(level + 1) & 1], wc,
+			nodes8, tris8, cap_nodes, cap_tris, level + 1);
+		e = cudaMemcpyAsync(&hc, wc, sizeof(hc), cudaMemcpyDeviceToHost, stream);
+		if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+		if (e != cudaSuccess || hc.overflow) break;
+		n_cur = hc.n_out;
+		level++;
+		if (n_cur > 0) e = cudaMemsetAsync(&wc->n_out, 0, sizeof(int), stream);
+		if (level > 128) break;
+	}
+	cudaEventRecord(e1, stream);
+	if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+	if (e == cudaSuccess) e = cudaGetLastError();
+	float ms = 0.0f;
+	if (e == cudaSuccess) cudaEventElapsedTime(&ms, e0, e1);
+	cudaEventDestroy(e0); cudaEventDestroy(e1);
+	if (e != cudaSuccess) { err = std::string("[Cuda]collapse_bvh8_gpu: ") + cudaGetErrorString(e); return 1; }
+	if (hc.overflow || level > 128) { err = "collapse_bvh8_gpu: capacity exceeded"; return 1; }
+	out.nodes = reinterpret_cast<float4*>(nodes8); out.tris = reinterpret_cast<float4*>(tris8);
+	results.release(nodes8); results.release(tris8);
+	out.n_nodes = hc.n_nodes; out.n_tris = hc.n_tris; out.max_depth = hc.max_depth; out.levels = level; out.collapse_ms = ms;
 	return 0;
 }
 

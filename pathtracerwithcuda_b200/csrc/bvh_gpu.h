@@ -32,6 +32,20 @@ struct GpuBuildOutput
 // and the caller falls back to / reports the host builder.
 int build_bvh2_gpu(const float* d_tris24, int n, int max_leaf_size, float intersect_cost, cudaStream_t stream, GpuBuildOutput& out, std::string& err);
 
+struct GpuWideOutput
+{
+	float4* nodes = nullptr;      // cudaMalloc'ed, 5 x float4 per compressed 8-wide node (bvh.h layout #2; caller frees)
+	float4* tris = nullptr;       // cudaMalloc'ed, 3 x float4 per triangle in the wide tree's leaf order (caller frees)
+	int n_nodes = 0, n_tris = 0;
+	int max_depth = 0;            // depth of the wide tree (traversal stack bound)
+	int levels = 0;
+	float collapse_ms = 0.0f;
+};
+
+// Collapses a binary tree built by build_bvh2_gpu (max_leaf_size <= 3) into the compressed 8-wide layout ON THE DEVICE
+// (same rules as the host build_bvh8 in bvh_host.cpp).
+int collapse_bvh8_gpu(const GpuBuildOutput& tree, const float* d_tris24, cudaStream_t stream, GpuWideOutput& out, std::string& err);
+
 // packs the shading attributes (DeviceScene::tri_shade: 4 x float4 per triangle by global id) on the device
 void pack_tri_shade_gpu(const float* d_tris24, const int* d_material, int n, float4* d_out, cudaStream_t stream);
 

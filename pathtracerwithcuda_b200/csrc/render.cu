@@ -1310,6 +1310,8 @@ struct ptb_renderer
 	int octant_order = 0;                  // next-depth queue grouped by ray-direction octant per block (measured: profiles/r01_experiments.md)
 	int tile_order = 1;                    // camera rays enter the first queue in 8x4 pixel tiles
 	// facts about the last acceleration-structure build (ptb_bvh_info)
+	int bvh_collapsed_on_gpu = 0;
+	std::string bvh_collapse = "gpu";      // "gpu" (csrc/bvh_build.cu: k_collapse8) | "host" (csrc/bvh_host.cpp: build_bvh8)
 	int bvh_built_on_gpu = 0, bvh_levels = 0, bvh_small_tasks = 0, bvh_max_depth = 0;
 	double bvh_build_ms = 0.0, scene_upload_ms = 0.0;
 	std::string bvh_note;
@@ -1570,7 +1572,8 @@ int upload_geometry(ptb_renderer* r)
 	// acceleration structure over all meshes' world-space triangles
 	const int max_leaf = r->bvh_layout == 8 ? 3 : r->bvh_max_leaf;   // <= 3 triangles per leaf slot of a wide node
 	Bvh2 bvh;
-	bool have_device_bvh2 = false;
+	bool have_device_bvh2 = false, have_device_bvh8 = false;
+	r->bvh_collapsed_on_gpu = 0;
 	if (r->bvh_builder != "host_sah" && n_tris > 0)
 	{
 		GpuBuildOutput gb;
@@ -1586,10 +1589,28 @@ int upload_geometry(ptb_renderer* r)
 			}
 			if (r->bvh_layout == 8)
 			{
-				// wide layout: the binary tree comes from the device, the 8-wide collapse + quantisation runs on the host
-				int rc = download_bvh2(gb, bvh);
-				cudaFree(gb.nodes); cudaFree(gb.tri_isect); cudaFree(gb.prim_order);
-				if (rc) return 1;
+				// wide layout: the binary tree and its 8-wide collapse + quantisation both come from the device
+				GpuWideOutput gw;
+				std::string why8;
+				if (r->bvh_collapse != "host" && collapse_bvh8_gpu(gb, d_tris24, r->stream, gw, why8) == 0)
+				{
+					cudaFree(gb.nodes); cudaFree(gb.tri_isect); cudaFree(gb.prim_order);
+					if (gw.max_depth > PTB_STACK_SIZE8) { cudaFree(gw.nodes); cudaFree(gw.tris); set_error("[Error]BVH8 too deep for the traversal stack"); return 1; }
+					G->push_back(gw.nodes); G->push_back(gw.tris);
+					ds.bvh_nodes = gw.nodes; ds.tri_isect = gw.tris;
+					r->bvh_nodes = gw.n_nodes;
+					r->bvh_bytes = (int64_t)gw.n_nodes * 80 + (int64_t)gw.n_tris * 48;
+					r->bvh_build_ms += gw.collapse_ms;
+					r->bvh_collapsed_on_gpu = 1;
+					have_device_bvh8 = true;
+				}
+				else
+				{
+					cudaGetLastError();
+					int rc = download_bvh2(gb, bvh);
+					cudaFree(gb.nodes); cudaFree(gb.tri_isect); cudaFree(gb.prim_order);
+					if (rc) return 1;
+				}
 			}
 			else
 			{
@@ -1615,7 +1636,7 @@ int upload_geometry(ptb_renderer* r)
 		build_bvh2_sah(s.triangles, max_leaf, bvh, r->bvh_intersect_cost);
 		r->bvh_build_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
 	}
-	if (r->bvh_layout == 8)
+	if (r->bvh_layout == 8 && !have_device_bvh8)
 	{
 		GpuBvh8 wide;
 		build_bvh8(bvh, s.triangles, wide);
@@ -1625,7 +1646,7 @@ int upload_geometry(ptb_renderer* r)
 		r->bvh_nodes = (int64_t)wide.nodes.size() / 20;
 		r->bvh_bytes = (int64_t)(wide.nodes.size() + wide.tris.size()) * 4;
 	}
-	else if (!have_device_bvh2)
+	else if (r->bvh_layout != 8 && !have_device_bvh2)
 	{
 		GpuBvh2 flat;
 		flatten_bvh2(bvh, s.triangles, flat);
@@ -1648,24 +1669,47 @@ int upload_geometry(ptb_renderer* r)
 		Bvh2 tree3;
 		GpuBuildOutput gb;
 		std::string why;
-		bool have = false;
+		bool have_tree = false, done = false;
 		if (r->bvh_builder != "host_sah" && build_bvh2_gpu(d_tris24, n_tris, 3, r->bvh_intersect_cost, r->stream, gb, why) == 0)
 		{
-			const int rc = download_bvh2(gb, tree3);
-			cudaFree(gb.nodes); cudaFree(gb.tri_isect); cudaFree(gb.prim_order);
-			if (rc) return 1;
 			r->bvh_build_ms += gb.build_ms;
-			have = true;
+			// collapse + quantisation on the device; the host collapse (bvh_host.cpp) stays as fallback and cross-check
+			GpuWideOutput gw;
+			if (r->bvh_collapse != "host" && collapse_bvh8_gpu(gb, d_tris24, r->stream, gw, why) == 0)
+			{
+				if (gw.max_depth <= PTB_STACK_SIZE8)
+				{
+					G->push_back(gw.nodes); G->push_back(gw.tris);
+					ds.bvh8_nodes = gw.nodes; ds.tri_isect8 = gw.tris;
+					r->bvh8_nodes = gw.n_nodes;
+					r->bvh_bytes += (int64_t)gw.n_nodes * 80 + (int64_t)gw.n_tris * 48;
+					r->bvh_build_ms += gw.collapse_ms;
+					r->bvh_collapsed_on_gpu = 1;
+				}
+				else { cudaFree(gw.nodes); cudaFree(gw.tris); }
+				done = true;
+			}
+			else
+			{
+				cudaGetLastError();
+				const int rc = download_bvh2(gb, tree3);
+				if (rc) { cudaFree(gb.nodes); cudaFree(gb.tri_isect); cudaFree(gb.prim_order); return 1; }
+				have_tree = true;
+			}
+			cudaFree(gb.nodes); cudaFree(gb.tri_isect); cudaFree(gb.prim_order);
 		}
-		if (!have) { cudaGetLastError(); build_bvh2_sah(s.triangles, 3, tree3, r->bvh_intersect_cost); }
-		GpuBvh8 wide;
-		build_bvh8(tree3, s.triangles, wide);
-		if (wide.max_depth <= PTB_STACK_SIZE8)
+		if (!done)
 		{
-			if (upload(r, (const float4*)wide.nodes.data(), wide.nodes.size() / 4, &ds.bvh8_nodes, G)) return 1;
-			if (upload(r, (const float4*)wide.tris.data(), wide.tris.size() / 4, &ds.tri_isect8, G)) return 1;
-			r->bvh8_nodes = (int64_t)wide.nodes.size() / 20;
-			r->bvh_bytes += (int64_t)(wide.nodes.size() + wide.tris.size()) * 4;
+			if (!have_tree) { cudaGetLastError(); build_bvh2_sah(s.triangles, 3, tree3, r->bvh_intersect_cost); }
+			GpuBvh8 wide;
+			build_bvh8(tree3, s.triangles, wide);
+			if (wide.max_depth <= PTB_STACK_SIZE8)
+			{
+				if (upload(r, (const float4*)wide.nodes.data(), wide.nodes.size() / 4, &ds.bvh8_nodes, G)) return 1;
+				if (upload(r, (const float4*)wide.tris.data(), wide.tris.size() / 4, &ds.tri_isect8, G)) return 1;
+				r->bvh8_nodes = (int64_t)wide.nodes.size() / 20;
+				r->bvh_bytes += (int64_t)(wide.nodes.size() + wide.tris.size()) * 4;
+			}
 		}
 	}
 
@@ -2543,6 +2587,7 @@ int ptb_bvh_info(ptb_renderer* r, int64_t* out_i, double* out_d)
 	{
 		out_i[0] = n_nodes; out_i[1] = inner; out_i[2] = leaves; out_i[3] = max_depth; out_i[4] = bad == 0 ? 1 : 0;
 		out_i[5] = r->bvh_built_on_gpu; out_i[6] = r->bvh_levels; out_i[7] = r->bvh_small_tasks;
+		out_i[8] = r->bvh8_nodes; out_i[9] = r->bvh_collapsed_on_gpu;
 	}
 	if (out_d) { out_d[0] = r->bvh_build_ms; out_d[1] = cost; out_d[2] = r->scene_upload_ms; out_d[3] = (double)bad; }
 	return 0;
@@ -2681,6 +2726,7 @@ int ptb_set_option(ptb_renderer* r, const char* key, const char* value)
 	if (k == "tune_leaf") { r->tune_leaf = atoi(value); return 0; }
 	if (k == "tune_reps") { r->tune_reps = atoi(value); return 0; }
 	if (k == "persistent_grid") { r->persistent_grid = atoi(value); return 0; }
+	if (k == "bvh_collapse") { if (v != "gpu" && v != "host") { set_error("[Error]bvh_collapse must be gpu or host"); return 1; } r->bvh_collapse = v; return 0; }
 	if (k == "bvh_hybrid") { r->bvh_hybrid = atoi(value); return 0; }             // takes effect at the next ptb_load_scene
 	if (k == "hybrid_from_depth") { r->hybrid_from_depth = atoi(value); return 0; }
 	if (k == "bvh_layout")

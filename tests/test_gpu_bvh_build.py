@@ -80,14 +80,31 @@ def test_images_do_not_depend_on_the_builder(workload_root):
     assert np.array_equal(imgs[0].view(np.uint32), imgs[2].view(np.uint32))
 
 
-def test_wide_layout_from_the_gpu_tree(workload_root):
-    root, w = workload_root("mix", width=96, height=72)
-    r8 = load(w, root, "gpu_sah", bvh_layout=8)
-    r2 = load(w, root, "gpu_sah")
-    rays = random_rays(8000, 11)
-    p8, t8 = r8.trace_batch(rays)
+@pytest.mark.parametrize("name,kw", [("mix", dict(width=96, height=72)), ("c2", dict(width=160, height=90))])
+def test_wide_layout_from_the_gpu_tree(workload_root, name, kw):
+    """Compressed 8-wide tree: collapsed + quantised on the device (k_collapse8) or on the host (build_bvh8) from the same
+    device-built binary tree — both must return exactly the binary tree's hits; so must the hybrid's bounce-ray tree."""
+    root, w = workload_root(name, **kw)
+    r2 = load(w, root, "gpu_sah", bvh_hybrid=0)
+    rays = random_rays(12000, 11)
     p2, t2 = r2.trace_batch(rays)
-    assert np.array_equal(p8, p2) and np.array_equal(t8.view(np.uint32), t2.view(np.uint32))
+    for opts in (dict(bvh_layout=8), dict(bvh_layout=8, bvh_collapse="host"), dict(bvh_layout=8, extend_persistent=0)):
+        r8 = load(w, root, "gpu_sah", **opts)
+        p8, t8 = r8.trace_batch(rays)
+        assert np.array_equal(p8, p2) and np.array_equal(t8.view(np.uint32), t2.view(np.uint32)), opts
+    # hybrid: deep bounces go through the wide tree; images equal the binary-only renderer's
+    cam = ptb.default_camera(w["width"], w["height"], w["aperture"], w["focal"])
+    imgs = []
+    for opts in (dict(bvh_hybrid=0), dict(), dict(bvh_collapse="host"), dict(hybrid_from_depth=0)):
+        r = load(w, root, "gpu_sah", **opts)
+        r.set_camera(cam)
+        r.render(3)
+        imgs.append(r.image_f32().copy())
+        if opts.get("bvh_hybrid", 1):
+            info = r.bvh_info()
+            assert info["wide_nodes"] > 0 and info["wide_collapsed_on_gpu"] == (opts.get("bvh_collapse") != "host")
+    for im in imgs[1:]:
+        assert np.array_equal(imgs[0].view(np.uint32), im.view(np.uint32))
 
 
 def _write_scene(root, name, verts, faces):
