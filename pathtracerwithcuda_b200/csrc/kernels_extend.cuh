@@ -1,0 +1,688 @@
+// ptb200 wavefront integrator, stage 2: closest hit.  One-ray-per-thread kernels over both tree layouts (test / comparison),
+// the production persistent warp-voting kernels (binary tree: k_extend_persistent, compressed 8-wide tree: k_extend_persistent8)
+// and the exhaustive-scan test hook.  Included by render.cu only.
+#pragma once
+#include <cuda_runtime.h>
+#include <math_constants.h>
+#include "kernels.cuh"
+
+namespace ptb
+{
+
+using namespace ptbdev;
+
+// ------------------------------------------------------------------------------------------
+// k_extend — closest hit (path_tracer_kernel.cu:418-454 + intersect_triangle_mesh_bvh :85-161)
+// One conservative traversal over a single tree for all meshes; the accepted hit is decided by
+// the reference's own Moller-Trumbore / sphere arithmetic (pt_device.cuh).
+// ------------------------------------------------------------------------------------------
+#define PTB_STACK_SIZE 64
+#define PTB_STACK_SIZE8 32
+#define PTB_SLACK_LO 0.9999995f
+#define PTB_SLACK_HI 1.0000005f
+
+struct HitRecord
+{
+	float t, t1, t2;
+	int prim;
+};
+
+template <bool COUNT>
+__device__ __forceinline__ HitRecord closest_hit(const DeviceScene& sc, float3 o, float3 d, float t_bound, unsigned& n_nodes, unsigned& n_tris)
+{
+	HitRecord best;
+	best.t = t_bound; best.t1 = CUDART_INF_F; best.t2 = CUDART_INF_F; best.prim = -1;
+
+	// spheres first, in index order, strict '<' (path_tracer_kernel.cu:431-441)
+	for (int s = 0; s < sc.n_spheres; s++)
+	{
+		float4 sp = __ldg(&sc.spheres[s]);
+		float t;
+		if (intersect_sphere(make_float3(sp.x, sp.y, sp.z), sp.w, o, d, t) && t < best.t && t > 0.0f)
+		{
+			best.t = t;
+			best.prim = -(s + 2);
+		}
+	}
+	if (sc.n_triangles == 0) return best;
+
+	const float3 idir = make_float3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+	int stack[PTB_STACK_SIZE];
+	int sp = 0;
+	int node = sc.root_ref;
+	int best_tri = 0x7fffffff;
+
+	while (true)
+	{
+		while (node >= 0)
+		{
+			if (COUNT) n_nodes++;
+			const float4* np = sc.bvh_nodes + (size_t)node * 4;
+			float4 n0 = __ldg(np + 0), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3);
+			float c0x0 = (n0.x - o.x) * idir.x, c0x1 = (n0.y - o.x) * idir.x;
+			float c0y0 = (n0.z - o.y) * idir.y, c0y1 = (n0.w - o.y) * idir.y;
+			float c0z0 = (n2.x - o.z) * idir.z, c0z1 = (n2.y - o.z) * idir.z;
+			float c1x0 = (n1.x - o.x) * idir.x, c1x1 = (n1.y - o.x) * idir.x;
+			float c1y0 = (n1.z - o.y) * idir.y, c1y1 = (n1.w - o.y) * idir.y;
+			float c1z0 = (n2.z - o.z) * idir.z, c1z1 = (n2.w - o.z) * idir.z;
+			float tmin0 = fmaxf(fmaxf(fminf(c0x0, c0x1), fminf(c0y0, c0y1)), fmaxf(fminf(c0z0, c0z1), 0.0f));
+			float tmax0 = fminf(fminf(fmaxf(c0x0, c0x1), fmaxf(c0y0, c0y1)), fminf(fmaxf(c0z0, c0z1), best.t));
+			float tmin1 = fmaxf(fmaxf(fminf(c1x0, c1x1), fminf(c1y0, c1y1)), fmaxf(fminf(c1z0, c1z1), 0.0f));
+			float tmax1 = fminf(fminf(fmaxf(c1x0, c1x1), fmaxf(c1y0, c1y1)), fminf(fmaxf(c1z0, c1z1), best.t));
+			bool h0 = tmin0 * PTB_SLACK_LO <= tmax0 * PTB_SLACK_HI;
+			bool h1 = tmin1 * PTB_SLACK_LO <= tmax1 * PTB_SLACK_HI;
+			int child0 = __float_as_int(n3.x), child1 = __float_as_int(n3.y);
+			if (h0 && h1)
+			{
+				bool swap = tmin1 < tmin0;
+				int near_c = swap ? child1 : child0;
+				int far_c = swap ? child0 : child1;
+				if (sp < PTB_STACK_SIZE) stack[sp++] = far_c;
+				node = near_c;
+			}
+			else if (h0) node = child0;
+			else if (h1) node = child1;
+			else
+			{
+				if (sp == 0) return best;
+				node = stack[--sp];
+			}
+		}
+		// leaf: node = ~((first << 3) | (count - 1))
+		{
+			int ref = ~node;
+			int first = ref >> 3;
+			int count = (ref & 7) + 1;
+			for (int k = 0; k < count; k++)
+			{
+				if (COUNT) n_tris++;
+				const float4* tp = sc.tri_isect + (size_t)(first + k) * 3;
+				float4 a = __ldg(tp + 0), b = __ldg(tp + 1), c = __ldg(tp + 2);
+				float t, t1, t2;
+				if (intersect_triangle(make_float3(a.x, a.y, a.z), make_float3(b.x, b.y, b.z), make_float3(c.x, c.y, c.z), o, d, t, t1, t2) && t > 0.0f)
+				{
+					int id = __float_as_int(a.w);
+					// strict '<' like the reference; exact-t ties between triangles go to the lower
+					// global index (the reference's tie winner depends on its tree layout)
+					if (t < best.t || (t == best.t && best.prim >= 0 && id < best_tri))
+					{
+						best.t = t; best.t1 = t1; best.t2 = t2; best.prim = id; best_tri = id;
+					}
+				}
+			}
+			if (sp == 0) return best;
+			node = stack[--sp];
+		}
+	}
+}
+
+// ---- compressed 8-wide traversal (layout in bvh.h; after Ylitie, Karras & Laine 2017) ----
+__device__ __forceinline__ unsigned sign_extend_s8x4(unsigned x)
+{
+	unsigned r;
+	asm("prmt.b32 %0, %1, 0x0, 0x0000BA98;" : "=r"(r) : "r"(x));
+	return r;
+}
+
+__device__ __forceinline__ unsigned extract_byte(unsigned x, unsigned i) { return (x >> (i * 8)) & 0xffu; }
+
+template <bool COUNT>
+__device__ __forceinline__ HitRecord closest_hit_bvh8(const DeviceScene& sc, float3 o, float3 d, float t_bound, unsigned& n_nodes, unsigned& n_tris)
+{
+	HitRecord best;
+	best.t = t_bound; best.t1 = CUDART_INF_F; best.t2 = CUDART_INF_F; best.prim = -1;
+	for (int s = 0; s < sc.n_spheres; s++)
+	{
+		float4 sp = __ldg(&sc.spheres[s]);
+		float t;
+		if (intersect_sphere(make_float3(sp.x, sp.y, sp.z), sp.w, o, d, t) && t < best.t && t > 0.0f)
+		{
+			best.t = t;
+			best.prim = -(s + 2);
+		}
+	}
+	if (sc.n_triangles == 0) return best;
+
+	// box culling only: keep the reciprocal finite so 0 * inf never appears (the deciding
+	// triangle test below still sees the exact direction)
+	const float tiny = 1e-30f;
+	const float3 ds = make_float3(fabsf(d.x) < tiny ? copysignf(tiny, d.x) : d.x, fabsf(d.y) < tiny ? copysignf(tiny, d.y) : d.y,
+		fabsf(d.z) < tiny ? copysignf(tiny, d.z) : d.z);
+	const float3 idir = make_float3(1.0f / ds.x, 1.0f / ds.y, 1.0f / ds.z);
+	const unsigned oct_inv4 = (d.x < 0.0f ? 0u : 0x04040404u) | (d.y < 0.0f ? 0u : 0x02020202u) | (d.z < 0.0f ? 0u : 0x01010101u);
+
+	uint2 stack[PTB_STACK_SIZE8];
+	int sp = 0;
+	uint2 current = make_uint2(0u, 0x80000000u);
+	int best_tri = 0x7fffffff;
+
+	while (true)
+	{
+		uint2 tri_group;
+		if (current.y & 0xff000000u)
+		{
+			const unsigned hits_imask = current.y;
+			const unsigned child_index_offset = 31u - __clz(hits_imask);
+			const unsigned child_index_base = current.x;
+			current.y &= ~(1u << child_index_offset);
+			if (current.y & 0xff000000u) { if (sp < PTB_STACK_SIZE8) stack[sp++] = current; }
+			const unsigned slot_index = (child_index_offset - 24u) ^ (oct_inv4 & 0xffu);
+			const unsigned relative_index = __popc(hits_imask & ~(0xffffffffu << slot_index));
+			const unsigned node_index = child_index_base + relative_index;
+			if (COUNT) n_nodes++;
+
+			const float4* np = sc.bvh_nodes + (size_t)node_index * 5;
+			const float4 n0 = __ldg(np + 0), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3), n4 = __ldg(np + 4);
+			const unsigned e_imask = __float_as_uint(n0.w);
+			const float3 adir = make_float3(__uint_as_float(extract_byte(e_imask, 0) << 23) * idir.x, __uint_as_float(extract_byte(e_imask, 1) << 23) * idir.y,
+				__uint_as_float(extract_byte(e_imask, 2) << 23) * idir.z);
+			const float3 aorg = make_float3((n0.x - o.x) * idir.x, (n0.y - o.y) * idir.y, (n0.z - o.z) * idir.z);
+
+			unsigned hit_mask = 0;
+#pragma unroll
+			for (int half = 0; half < 2; half++)
+			{
+				const unsigned meta4 = __float_as_uint(half == 0 ? n1.z : n1.w);
+				const unsigned is_inner4 = (meta4 & (meta4 << 1)) & 0x10101010u;
+				const unsigned inner_mask4 = sign_extend_s8x4(is_inner4 << 3);
+				const unsigned bit_index4 = (meta4 ^ (oct_inv4 & inner_mask4)) & 0x1f1f1f1fu;
+				const unsigned child_bits4 = (meta4 >> 5) & 0x07070707u;
+				const unsigned qlox = __float_as_uint(half == 0 ? n2.x : n2.y), qhix = __float_as_uint(half == 0 ? n2.z : n2.w);
+				const unsigned qloy = __float_as_uint(half == 0 ? n3.x : n3.y), qhiy = __float_as_uint(half == 0 ? n3.z : n3.w);
+				const unsigned qloz = __float_as_uint(half == 0 ? n4.x : n4.y), qhiz = __float_as_uint(half == 0 ? n4.z : n4.w);
+				const unsigned x_min = d.x < 0.0f ? qhix : qlox, x_max = d.x < 0.0f ? qlox : qhix;
+				const unsigned y_min = d.y < 0.0f ? qhiy : qloy, y_max = d.y < 0.0f ? qloy : qhiy;
+				const unsigned z_min = d.z < 0.0f ? qhiz : qloz, z_max = d.z < 0.0f ? qloz : qhiz;
+#pragma unroll
+				for (int j = 0; j < 4; j++)
+				{
+					const float tx0 = fmaf((float)extract_byte(x_min, j), adir.x, aorg.x), tx1 = fmaf((float)extract_byte(x_max, j), adir.x, aorg.x);
+					const float ty0 = fmaf((float)extract_byte(y_min, j), adir.y, aorg.y), ty1 = fmaf((float)extract_byte(y_max, j), adir.y, aorg.y);
+					const float tz0 = fmaf((float)extract_byte(z_min, j), adir.z, aorg.z), tz1 = fmaf((float)extract_byte(z_max, j), adir.z, aorg.z);
+					const float tmin = fmaxf(fmaxf(tx0, ty0), fmaxf(tz0, 0.0f));
+					const float tmax = fminf(fminf(tx1, ty1), fminf(tz1, best.t));
+					if (tmin * PTB_SLACK_LO <= tmax * PTB_SLACK_HI)
+						hit_mask |= extract_byte(child_bits4, j) << extract_byte(bit_index4, j);
+				}
+			}
+			current.x = __float_as_uint(n1.x);
+			tri_group.x = __float_as_uint(n1.y);
+			current.y = (hit_mask & 0xff000000u) | (e_imask >> 24);
+			tri_group.y = hit_mask & 0x00ffffffu;
+		}
+		else
+		{
+			tri_group = current;
+			current = make_uint2(0u, 0u);
+		}
+
+		while (tri_group.y)
+		{
+			const unsigned k = 31u - __clz(tri_group.y);
+			tri_group.y &= ~(1u << k);
+			if (COUNT) n_tris++;
+			const float4* tp = sc.tri_isect + (size_t)(tri_group.x + k) * 3;
+			const float4 a = __ldg(tp + 0), b = __ldg(tp + 1), c = __ldg(tp + 2);
+			float t, t1, t2;
+			if (intersect_triangle(make_float3(a.x, a.y, a.z), make_float3(b.x, b.y, b.z), make_float3(c.x, c.y, c.z), o, d, t, t1, t2) && t > 0.0f)
+			{
+				const int id = __float_as_int(a.w);
+				if (t < best.t || (t == best.t && best.prim >= 0 && id < best_tri))
+				{
+					best.t = t; best.t1 = t1; best.t2 = t2; best.prim = id; best_tri = id;
+				}
+			}
+		}
+
+		if ((current.y & 0xff000000u) == 0u)
+		{
+			if (sp == 0) return best;
+			current = stack[--sp];
+		}
+	}
+}
+
+template <bool COUNT, bool WIDE>
+__global__ void __launch_bounds__(128) k_extend(DeviceScene sc, PathState st, const int* __restrict__ queue, const int* __restrict__ count_ptr,
+	unsigned long long* __restrict__ counters)
+{
+	const int count = *count_ptr;
+	unsigned n_nodes = 0, n_tris = 0;
+	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x)
+	{
+		int id = queue[i];
+		float4 o4 = st.ray_o[id], d4 = st.ray_d[id];
+		HitRecord h = WIDE ? closest_hit_bvh8<COUNT>(sc, make_float3(o4.x, o4.y, o4.z), make_float3(d4.x, d4.y, d4.z), d4.w, n_nodes, n_tris)
+		                   : closest_hit<COUNT>(sc, make_float3(o4.x, o4.y, o4.z), make_float3(d4.x, d4.y, d4.z), d4.w, n_nodes, n_tris);
+		st.hit[id] = make_float4(h.prim == -1 ? CUDART_INF_F : h.t, h.t1, h.t2, __int_as_float(h.prim));
+	}
+	if (COUNT)
+	{
+		for (int off = 16; off > 0; off >>= 1)
+		{
+			n_nodes += __shfl_down_sync(0xffffffffu, n_nodes, off);
+			n_tris += __shfl_down_sync(0xffffffffu, n_tris, off);
+		}
+		if ((threadIdx.x & 31) == 0)
+		{
+			atomicAdd(&counters[0], (unsigned long long)n_nodes);
+			atomicAdd(&counters[1], (unsigned long long)n_tris);
+		}
+	}
+}
+
+// ------------------------------------------------------------------------------------------
+// k_extend_persistent — the production closest-hit kernel.
+// ncu on the one-ray-per-thread kernels above showed them ISSUE-bound (65-70% issue slots busy)
+// with only 8-18 of 32 lanes active per instruction: rays of one warp need very different numbers
+// of node visits and the finished lanes idle.  Here warps are persistent: a lane whose ray
+// terminates fetches the next queue entry (one atomicAdd per warp per refill) as soon as fewer than
+// PTB_REFILL_THRESHOLD lanes are still traversing, so the 32 lanes stay populated.
+// Binary tree, both child boxes per 64-byte node; slab distances as one FMA per plane
+// (plane * (1/d) - o/d) with an absolute + relative safety margin so culling stays conservative.
+// ------------------------------------------------------------------------------------------
+#define PTB_DONE ((int)0x80000000)
+
+// one 64-byte binary node: two 256-bit loads (sm_100 LDG.E.ENL2.256) instead of 3 x 128-bit + 1 x 64-bit.
+// (Routing the node fetches through the TEX data pipe was measured 2-7 % slower: profiles/r01_experiments.md.)
+__device__ __forceinline__ void load_node(const float4* np, float4& n0, float4& n1, float4& n2, float2& n3)
+{
+#ifndef PTB_NODE_LDG128
+	float z, w;
+	asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+		: "=f"(n0.x), "=f"(n0.y), "=f"(n0.z), "=f"(n0.w), "=f"(n1.x), "=f"(n1.y), "=f"(n1.z), "=f"(n1.w) : "l"(np));
+	asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+		: "=f"(n2.x), "=f"(n2.y), "=f"(n2.z), "=f"(n2.w), "=f"(n3.x), "=f"(n3.y), "=f"(z), "=f"(w) : "l"(np + 2));
+#else
+	n0 = __ldg(np + 0); n1 = __ldg(np + 1); n2 = __ldg(np + 2);
+	n3 = __ldg(reinterpret_cast<const float2*>(np + 3));
+#endif
+}
+#ifndef PTB_PERSISTENT_MIN_BLOCKS
+#define PTB_PERSISTENT_MIN_BLOCKS 8
+#endif
+
+template <bool COUNT>
+__global__ void __launch_bounds__(128, PTB_PERSISTENT_MIN_BLOCKS) k_extend_persistent(DeviceScene sc, PathState st, const int* __restrict__ queue, const int* __restrict__ count_ptr,
+	int* __restrict__ work_counter, unsigned long long* __restrict__ counters, int refill_min, int leaf_min, int node_reps)
+{
+	const int count = *count_ptr;
+	const unsigned lane = threadIdx.x & 31u;
+	const unsigned lane_lt = (1u << lane) - 1u;
+	const unsigned FULL = 0xffffffffu;
+	unsigned n_nodes = 0, n_tris = 0;
+
+	int id = -1;                 // path id this lane is tracing; -1 = idle
+	unsigned ray_nodes = 0;      // COUNT only: node visits of the current ray
+	bool exhausted = false;      // warp-uniform: the queue has been handed out completely
+	float3 o = make_float3(0, 0, 0), d = o, idir = o, noidir = o;
+	float margin2 = 0.0f;
+	HitRecord best;
+	best.t = CUDART_INF_F; best.t1 = 0.0f; best.t2 = 0.0f; best.prim = -1;
+	int best_tri = 0x7fffffff;
+	int stack[PTB_STACK_SIZE];
+	int sp = 0;
+	int node = PTB_DONE;         // >= 0 inner node, PTB_DONE = nothing left, other negative = leaf reference
+
+	// Every iteration starts with full-mask votes, so all 32 lanes are converged when a phase
+	// begins; a phase is executed by the lanes in that state, the others are predicated off.
+	while (true)
+	{
+		// retire finished rays (no vote needed: a plain predicated store)
+		if (id >= 0 && node == PTB_DONE)
+		{
+#ifndef PTB_NO_STREAMING_HINTS
+			__stcs(&st.hit[id], make_float4(best.prim == -1 ? CUDART_INF_F : best.t, best.t1, best.t2, __int_as_float(best.prim)));
+#else
+			st.hit[id] = make_float4(best.prim == -1 ? CUDART_INF_F : best.t, best.t1, best.t2, __int_as_float(best.prim));
+#endif
+			id = -1;
+			if (COUNT)
+			{
+				// histogram of node visits per ray: counters[4 + floor(log2(n + 1))], max in counters[2]
+				atomicMax(&counters[2], (unsigned long long)ray_nodes);
+				atomicAdd(&counters[4 + min(27, 31 - __clz(ray_nodes + 1u))], 1ull);
+				ray_nodes = 0;
+			}
+		}
+		const bool has_ray = id >= 0;
+		const unsigned m_idle = __ballot_sync(FULL, !has_ray);
+		const unsigned m_node = __ballot_sync(FULL, has_ray && node >= 0);
+		const unsigned m_leaf = __ballot_sync(FULL, has_ray && node < 0);
+
+		if (m_idle != 0u && !exhausted && (__popc(m_idle) >= refill_min || (m_node | m_leaf) == 0u))
+		{
+			// ---- refill idle lanes from the queue: one atomic per warp
+			const int n = __popc(m_idle);
+			int base = 0;
+			if (lane == 0) base = atomicAdd(work_counter, n);
+			base = __shfl_sync(FULL, base, 0);
+			if (base + n >= count) exhausted = true;
+			if (!has_ray)
+			{
+				const int i = base + __popc(m_idle & lane_lt);
+				if (i < count)
+				{
+#ifndef PTB_NO_STREAMING_HINTS   // ray records are read once: keep them from displacing tree nodes in L1 (+0.5 %)
+					id = __ldcs(&queue[i]);
+					const float4 o4 = __ldcs(&st.ray_o[id]), d4 = __ldcs(&st.ray_d[id]);
+#else
+					id = queue[i];
+					const float4 o4 = st.ray_o[id], d4 = st.ray_d[id];
+#endif
+					o = make_float3(o4.x, o4.y, o4.z);
+					d = make_float3(d4.x, d4.y, d4.z);
+					best.t = d4.w; best.t1 = CUDART_INF_F; best.t2 = CUDART_INF_F; best.prim = -1;   // d4.w: free-flight bound (next_bounce_bound)
+					best_tri = 0x7fffffff;
+					for (int s = 0; s < sc.n_spheres; s++)
+					{
+						const float4 sph = __ldg(&sc.spheres[s]);
+						float t;
+						if (intersect_sphere(make_float3(sph.x, sph.y, sph.z), sph.w, o, d, t) && t < best.t && t > 0.0f)
+						{
+							best.t = t;
+							best.prim = -(s + 2);
+						}
+					}
+					// box culling only: finite reciprocal so 0 * inf never appears
+					const float tiny = 1e-30f;
+					const float3 ds = make_float3(fabsf(d.x) < tiny ? copysignf(tiny, d.x) : d.x, fabsf(d.y) < tiny ? copysignf(tiny, d.y) : d.y,
+						fabsf(d.z) < tiny ? copysignf(tiny, d.z) : d.z);
+					idir = make_float3(1.0f / ds.x, 1.0f / ds.y, 1.0f / ds.z);
+					noidir = make_float3(-o.x * idir.x, -o.y * idir.y, -o.z * idir.z);
+					// |error| of fma(plane, idir, -o*idir) <= 2^-23 * (|o*idir| + |t|): absolute part here, relative part in the slack factors
+					margin2 = 4.8e-7f * fmaxf(fmaxf(fabsf(noidir.x), fabsf(noidir.y)), fabsf(noidir.z));
+					sp = 0;
+					node = sc.n_triangles > 0 ? sc.root_ref : PTB_DONE;
+				}
+			}
+			continue;
+		}
+		if ((m_node | m_leaf) == 0u) break;   // nothing in flight and nothing left to fetch
+
+		if (m_leaf != 0u && (__popc(m_leaf) >= leaf_min || m_node == 0u))
+		{
+			// ---- leaf phase: node = ~((first << 3) | (count - 1))
+			if (has_ray && node < 0)
+			{
+				const int ref = ~node;
+				const int first = ref >> 3;
+				const int cnt = (ref & 7) + 1;
+				for (int k = 0; k < cnt; k++)
+				{
+					if (COUNT) n_tris++;
+					const float4* tp = sc.tri_isect + (size_t)(first + k) * 3;
+					const float4 a = __ldg(tp + 0), b = __ldg(tp + 1), c = __ldg(tp + 2);
+					float t, t1, t2;
+					if (intersect_triangle(make_float3(a.x, a.y, a.z), make_float3(b.x, b.y, b.z), make_float3(c.x, c.y, c.z), o, d, t, t1, t2) && t > 0.0f)
+					{
+						const int tid = __float_as_int(a.w);
+						if (t < best.t || (t == best.t && best.prim >= 0 && tid < best_tri))
+						{
+							best.t = t; best.t1 = t1; best.t2 = t2; best.prim = tid; best_tri = tid;
+						}
+					}
+				}
+				node = sp > 0 ? stack[--sp] : PTB_DONE;
+			}
+			continue;
+		}
+
+		// ---- node phase (node_reps steps for every lane sitting at an inner node)
+		for (int rep = 0; rep < node_reps; rep++)
+		if (id >= 0 && node >= 0)
+		{
+			if (COUNT) { n_nodes++; ray_nodes++; }
+			const float4* np = sc.bvh_nodes + (size_t)node * 4;
+			float4 n0, n1, n2;
+			float2 n3;
+			load_node(np, n0, n1, n2, n3);
+			const float c0x0 = fmaf(n0.x, idir.x, noidir.x), c0x1 = fmaf(n0.y, idir.x, noidir.x);
+			const float c0y0 = fmaf(n0.z, idir.y, noidir.y), c0y1 = fmaf(n0.w, idir.y, noidir.y);
+			const float c0z0 = fmaf(n2.x, idir.z, noidir.z), c0z1 = fmaf(n2.y, idir.z, noidir.z);
+			const float c1x0 = fmaf(n1.x, idir.x, noidir.x), c1x1 = fmaf(n1.y, idir.x, noidir.x);
+			const float c1y0 = fmaf(n1.z, idir.y, noidir.y), c1y1 = fmaf(n1.w, idir.y, noidir.y);
+			const float c1z0 = fmaf(n2.z, idir.z, noidir.z), c1z1 = fmaf(n2.w, idir.z, noidir.z);
+			const float tmin0 = fmaxf(fmaxf(fminf(c0x0, c0x1), fminf(c0y0, c0y1)), fmaxf(fminf(c0z0, c0z1), 0.0f));
+			const float tmax0 = fminf(fminf(fmaxf(c0x0, c0x1), fmaxf(c0y0, c0y1)), fminf(fmaxf(c0z0, c0z1), best.t));
+			const float tmin1 = fmaxf(fmaxf(fminf(c1x0, c1x1), fminf(c1y0, c1y1)), fmaxf(fminf(c1z0, c1z1), 0.0f));
+			const float tmax1 = fminf(fminf(fmaxf(c1x0, c1x1), fmaxf(c1y0, c1y1)), fminf(fmaxf(c1z0, c1z1), best.t));
+			// conservative overlap test tmin * LO - margin <= tmax * HI, divided through by HI (one FMA per box)
+			const bool h0 = fmaf(tmin0, PTB_SLACK_LO / PTB_SLACK_HI, -margin2) <= tmax0;
+			const bool h1 = fmaf(tmin1, PTB_SLACK_LO / PTB_SLACK_HI, -margin2) <= tmax1;
+			const int child0 = __float_as_int(n3.x), child1 = __float_as_int(n3.y);
+			const bool both = h0 && h1;
+			const bool swap = tmin1 < tmin0;
+			const int near_c = swap ? child1 : child0;
+			const int far_c = swap ? child0 : child1;
+			int next = both ? near_c : (h0 ? child0 : (h1 ? child1 : PTB_DONE));
+			if (both) stack[sp++] = far_c;
+			else if (!(h0 || h1) && sp > 0) next = stack[--sp];
+			node = next;
+		}
+	}
+	if (COUNT)
+	{
+		for (int off = 16; off > 0; off >>= 1)
+		{
+			n_nodes += __shfl_down_sync(FULL, n_nodes, off);
+			n_tris += __shfl_down_sync(FULL, n_tris, off);
+		}
+		if (lane == 0)
+		{
+			atomicAdd(&counters[0], (unsigned long long)n_nodes);
+			atomicAdd(&counters[1], (unsigned long long)n_tris);
+		}
+	}
+}
+
+// ------------------------------------------------------------------------------------------
+// k_extend_persistent8 — the same persistent, warp-voting scheme over the compressed 8-wide layout
+// (bvh.h layout #2).  Lane state: `current` = a group of not-yet-visited inner children of one wide node
+// (child base + hit bits), `tri_group` = leaf triangles still to test; stack entries are node groups.
+// Phases: refill | wide-node step (one child popped, 8 quantised boxes decoded and tested) | triangle step.
+// ------------------------------------------------------------------------------------------
+template <bool COUNT>
+__global__ void __launch_bounds__(128, PTB_PERSISTENT_MIN_BLOCKS) k_extend_persistent8(DeviceScene sc, PathState st, const int* __restrict__ queue, const int* __restrict__ count_ptr,
+	int* __restrict__ work_counter, unsigned long long* __restrict__ counters, int refill_min, int leaf_min)
+{
+	const int count = *count_ptr;
+	const unsigned lane = threadIdx.x & 31u;
+	const unsigned lane_lt = (1u << lane) - 1u;
+	const unsigned FULL = 0xffffffffu;
+	unsigned n_nodes = 0, n_tris = 0;
+
+	int id = -1;
+	bool exhausted = false;
+	float3 o = make_float3(0, 0, 0), d = o, idir = o;
+	unsigned oct_inv4 = 0;
+	HitRecord best;
+	best.t = CUDART_INF_F; best.t1 = 0.0f; best.t2 = 0.0f; best.prim = -1;
+	int best_tri = 0x7fffffff;
+	uint2 stack[PTB_STACK_SIZE8];
+	int sp = 0;
+	uint2 current = make_uint2(0u, 0u), tri_group = make_uint2(0u, 0u);
+
+	while (true)
+	{
+		// bookkeeping without votes: pop a node group when the lane ran dry, retire when nothing is left
+		if (id >= 0 && (current.y & 0xff000000u) == 0u && tri_group.y == 0u)
+		{
+			if (sp > 0) current = stack[--sp];
+			else
+			{
+				__stcs(&st.hit[id], make_float4(best.prim == -1 ? CUDART_INF_F : best.t, best.t1, best.t2, __int_as_float(best.prim)));
+				id = -1;
+			}
+		}
+		const bool has_ray = id >= 0;
+		const bool at_tri = has_ray && tri_group.y != 0u;
+		const bool at_node = has_ray && !at_tri && (current.y & 0xff000000u) != 0u;
+		const unsigned m_idle = __ballot_sync(FULL, !has_ray);
+		const unsigned m_node = __ballot_sync(FULL, at_node);
+		const unsigned m_tri = __ballot_sync(FULL, at_tri);
+
+		if (m_idle != 0u && !exhausted && (__popc(m_idle) >= refill_min || (m_node | m_tri) == 0u))
+		{
+			const int n = __popc(m_idle);
+			int base = 0;
+			if (lane == 0) base = atomicAdd(work_counter, n);
+			base = __shfl_sync(FULL, base, 0);
+			if (base + n >= count) exhausted = true;
+			if (!has_ray)
+			{
+				const int i = base + __popc(m_idle & lane_lt);
+				if (i < count)
+				{
+					id = __ldcs(&queue[i]);
+					const float4 o4 = __ldcs(&st.ray_o[id]), d4 = __ldcs(&st.ray_d[id]);
+					o = make_float3(o4.x, o4.y, o4.z);
+					d = make_float3(d4.x, d4.y, d4.z);
+					best.t = d4.w; best.t1 = CUDART_INF_F; best.t2 = CUDART_INF_F; best.prim = -1;
+					best_tri = 0x7fffffff;
+					for (int s = 0; s < sc.n_spheres; s++)
+					{
+						const float4 sph = __ldg(&sc.spheres[s]);
+						float t;
+						if (intersect_sphere(make_float3(sph.x, sph.y, sph.z), sph.w, o, d, t) && t < best.t && t > 0.0f)
+						{
+							best.t = t;
+							best.prim = -(s + 2);
+						}
+					}
+					const float tiny = 1e-30f;
+					const float3 ds = make_float3(fabsf(d.x) < tiny ? copysignf(tiny, d.x) : d.x, fabsf(d.y) < tiny ? copysignf(tiny, d.y) : d.y,
+						fabsf(d.z) < tiny ? copysignf(tiny, d.z) : d.z);
+					idir = make_float3(1.0f / ds.x, 1.0f / ds.y, 1.0f / ds.z);
+					oct_inv4 = (d.x < 0.0f ? 0u : 0x04040404u) | (d.y < 0.0f ? 0u : 0x02020202u) | (d.z < 0.0f ? 0u : 0x01010101u);
+					sp = 0;
+					tri_group = make_uint2(0u, 0u);
+					current = sc.n_triangles > 0 ? make_uint2(0u, 0x80000000u) : make_uint2(0u, 0u);
+				}
+			}
+			continue;
+		}
+		if ((m_node | m_tri) == 0u) break;
+
+		if (m_tri != 0u && (__popc(m_tri) >= leaf_min || m_node == 0u))
+		{
+			// ---- triangle phase
+			if (at_tri)
+			{
+				while (tri_group.y)
+				{
+					const unsigned k = 31u - __clz(tri_group.y);
+					tri_group.y &= ~(1u << k);
+					if (COUNT) n_tris++;
+					const float4* tp = sc.tri_isect + (size_t)(tri_group.x + k) * 3;
+					const float4 a = __ldg(tp + 0), b = __ldg(tp + 1), c = __ldg(tp + 2);
+					float t, t1, t2;
+					if (intersect_triangle(make_float3(a.x, a.y, a.z), make_float3(b.x, b.y, b.z), make_float3(c.x, c.y, c.z), o, d, t, t1, t2) && t > 0.0f)
+					{
+						const int tid = __float_as_int(a.w);
+						if (t < best.t || (t == best.t && best.prim >= 0 && tid < best_tri))
+						{
+							best.t = t; best.t1 = t1; best.t2 = t2; best.prim = tid; best_tri = tid;
+						}
+					}
+				}
+			}
+			continue;
+		}
+
+		// ---- wide-node phase
+		if (at_node)
+		{
+			const unsigned hits_imask = current.y;
+			const unsigned child_index_offset = 31u - __clz(hits_imask);
+			const unsigned child_index_base = current.x;
+			current.y &= ~(1u << child_index_offset);
+			if (current.y & 0xff000000u) { if (sp < PTB_STACK_SIZE8) stack[sp++] = current; }
+			const unsigned slot_index = (child_index_offset - 24u) ^ (oct_inv4 & 0xffu);
+			const unsigned relative_index = __popc(hits_imask & ~(0xffffffffu << slot_index));
+			const unsigned node_index = child_index_base + relative_index;
+			if (COUNT) n_nodes++;
+
+			const float4* np = sc.bvh_nodes + (size_t)node_index * 5;
+			const float4 n0 = __ldg(np + 0), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3), n4 = __ldg(np + 4);
+			const unsigned e_imask = __float_as_uint(n0.w);
+			const float3 adir = make_float3(__uint_as_float(extract_byte(e_imask, 0) << 23) * idir.x, __uint_as_float(extract_byte(e_imask, 1) << 23) * idir.y,
+				__uint_as_float(extract_byte(e_imask, 2) << 23) * idir.z);
+			const float3 aorg = make_float3((n0.x - o.x) * idir.x, (n0.y - o.y) * idir.y, (n0.z - o.z) * idir.z);
+			unsigned hit_mask = 0;
+#pragma unroll
+			for (int half = 0; half < 2; half++)
+			{
+				const unsigned meta4 = __float_as_uint(half == 0 ? n1.z : n1.w);
+				const unsigned is_inner4 = (meta4 & (meta4 << 1)) & 0x10101010u;
+				const unsigned inner_mask4 = sign_extend_s8x4(is_inner4 << 3);
+				const unsigned bit_index4 = (meta4 ^ (oct_inv4 & inner_mask4)) & 0x1f1f1f1fu;
+				const unsigned child_bits4 = (meta4 >> 5) & 0x07070707u;
+				const unsigned qlox = __float_as_uint(half == 0 ? n2.x : n2.y), qhix = __float_as_uint(half == 0 ? n2.z : n2.w);
+				const unsigned qloy = __float_as_uint(half == 0 ? n3.x : n3.y), qhiy = __float_as_uint(half == 0 ? n3.z : n3.w);
+				const unsigned qloz = __float_as_uint(half == 0 ? n4.x : n4.y), qhiz = __float_as_uint(half == 0 ? n4.z : n4.w);
+				const unsigned x_min = d.x < 0.0f ? qhix : qlox, x_max = d.x < 0.0f ? qlox : qhix;
+				const unsigned y_min = d.y < 0.0f ? qhiy : qloy, y_max = d.y < 0.0f ? qloy : qhiy;
+				const unsigned z_min = d.z < 0.0f ? qhiz : qloz, z_max = d.z < 0.0f ? qloz : qhiz;
+#pragma unroll
+				for (int j = 0; j < 4; j++)
+				{
+					const float tx0 = fmaf((float)extract_byte(x_min, j), adir.x, aorg.x), tx1 = fmaf((float)extract_byte(x_max, j), adir.x, aorg.x);
+					const float ty0 = fmaf((float)extract_byte(y_min, j), adir.y, aorg.y), ty1 = fmaf((float)extract_byte(y_max, j), adir.y, aorg.y);
+					const float tz0 = fmaf((float)extract_byte(z_min, j), adir.z, aorg.z), tz1 = fmaf((float)extract_byte(z_max, j), adir.z, aorg.z);
+					const float tmin = fmaxf(fmaxf(tx0, ty0), fmaxf(tz0, 0.0f));
+					const float tmax = fminf(fminf(tx1, ty1), fminf(tz1, best.t));
+					if (tmin * PTB_SLACK_LO <= tmax * PTB_SLACK_HI)
+						hit_mask |= extract_byte(child_bits4, j) << extract_byte(bit_index4, j);
+				}
+			}
+			current.x = __float_as_uint(n1.x);
+			tri_group.x = __float_as_uint(n1.y);
+			current.y = (hit_mask & 0xff000000u) | (e_imask >> 24);
+			tri_group.y = hit_mask & 0x00ffffffu;
+		}
+	}
+	if (COUNT)
+	{
+		for (int off = 16; off > 0; off >>= 1)
+		{
+			n_nodes += __shfl_down_sync(FULL, n_nodes, off);
+			n_tris += __shfl_down_sync(FULL, n_tris, off);
+		}
+		if (lane == 0)
+		{
+			atomicAdd(&counters[3], (unsigned long long)n_nodes);   // wide-node visits are tallied apart from binary-node visits
+			atomicAdd(&counters[1], (unsigned long long)n_tris);
+		}
+	}
+}
+
+// brute-force closest hit over every primitive (test hook; same acceptance arithmetic)
+__global__ void k_bruteforce(DeviceScene sc, const float4* __restrict__ ray_o, const float4* __restrict__ ray_d, float4* __restrict__ hit, int n)
+{
+	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	float3 o = make_float3(ray_o[i].x, ray_o[i].y, ray_o[i].z), d = make_float3(ray_d[i].x, ray_d[i].y, ray_d[i].z);
+	float best_t = CUDART_INF_F, bt1 = CUDART_INF_F, bt2 = CUDART_INF_F;
+	int prim = -1;
+	for (int s = 0; s < sc.n_spheres; s++)
+	{
+		float4 sp = sc.spheres[s];
+		float t;
+		if (intersect_sphere(make_float3(sp.x, sp.y, sp.z), sp.w, o, d, t) && t < best_t && t > 0.0f) { best_t = t; prim = -(s + 2); }
+	}
+	for (int k = 0; k < sc.n_triangles; k++)
+	{
+		const float4* tp = sc.tri_isect + (size_t)k * 3;
+		float4 a = tp[0], b = tp[1], c = tp[2];
+		float t, t1, t2;
+		if (intersect_triangle(make_float3(a.x, a.y, a.z), make_float3(b.x, b.y, b.z), make_float3(c.x, c.y, c.z), o, d, t, t1, t2) && t > 0.0f)
+		{
+			int id = __float_as_int(a.w);
+			if (t < best_t || (t == best_t && prim >= 0 && id < prim)) { best_t = t; bt1 = t1; bt2 = t2; prim = id; }
+		}
+	}
+	hit[i] = make_float4(best_t, bt1, bt2, __int_as_float(prim));
+}
+
+} // namespace ptb

@@ -1,0 +1,69 @@
+// ptb200 wavefront integrator, stage 1: k_generate (camera rays + path-state reset) and the free-flight bound shared with k_shade.
+// Included by render.cu only (one translation unit).
+#pragma once
+#include <cuda_runtime.h>
+#include <math_constants.h>
+#include "kernels.cuh"
+
+namespace ptb
+{
+
+using namespace ptbdev;
+
+__device__ __forceinline__ int float_as_int_(float f) { return __float_as_int(f); }
+
+// Upper bound on the hit distance the NEXT bounce can use (stored in ray_d.w).  In a scattering
+// medium the reference draws a free-flight distance d = -__logf(u0) / sigma_s'.x first thing in the
+// bounce and, when d < t_hit, scatters WITHOUT looking at the hit (path_tracer_kernel.cu:460-486).
+// The RNG stream of a bounce depends only on (pass, pixel, depth), so d is known before the ray is
+// traced: the closest-hit search can stop at d.  Subsurface random walks (mean free path << object
+// size) then cost a handful of node visits instead of a full traversal, with identical results.
+__device__ __forceinline__ float next_bounce_bound(const DeviceConfig& cfg, float3 sigma_a, float3 sigma_s, int seed, int pixel_index, int depth)
+{
+	if (!(sigma_s.x > 0.0f || length(sigma_a) > cfg.sss_threshold)) return CUDART_INF_F;
+	Rng rng;
+	rng.seed((uint32_t)(hash_ref(seed) * hash_ref(pixel_index) * hash_ref(depth)), 0.0f, 1.0f);
+	const float scattering_distance = -__logf(rng.next()) / sigma_s.x;
+	// hits with t <= d are still needed (the test is d < t_hit): bound = next float above d.
+	// NaN (0/0) never compares less than t_hit -> no clipping.
+	if (!(scattering_distance == scattering_distance)) return CUDART_INF_F;
+	if (scattering_distance < 0.0f || scattering_distance == 0.0f) return 1e-37f;
+	if (scattering_distance >= 3.0e38f) return CUDART_INF_F;
+	return __uint_as_float(__float_as_uint(scattering_distance) + 1u);
+}
+
+// ------------------------------------------------------------------------------------------
+// k_generate — init_data_kernel + generate_ray_kernel fused (path_tracer_kernel.cu:275-379)
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_generate(PathState st, int* __restrict__ queue, int* __restrict__ counts, int n_counts,
+	CameraParams cam, DeviceConfig cfg, int pixel_count, int n_slots, int first_pass, int pass_stride, int tiles_x)
+{
+	const int total = pixel_count * n_slots;
+	int tid = blockIdx.x * blockDim.x + threadIdx.x;
+	// counts[0..n_counts) = live paths per depth; counts[n_counts..2*n_counts) = per-depth work-fetch cursors of the persistent
+	// extend kernel; counts[2*n_counts..3*n_counts) = shadow rays per depth (estimator "nee")
+	if (tid < 3 * n_counts) counts[tid] = tid == 0 ? total : 0;
+	for (int i = tid; i < total; i += gridDim.x * blockDim.x)
+	{
+		int slot = i / pixel_count;
+		int pixel = i - slot * pixel_count;
+		if (tiles_x > 0)
+		{
+			// queue position -> pixel in 8x4 tiles: the 32 rays of a warp cover a compact screen patch, so
+			// they visit nearly the same nodes (higher L1 hit rate, lanes finish together)
+			const int tile = pixel >> 5, within = pixel & 31;
+			const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
+			pixel = (ty * 4 + (within >> 3)) * (tiles_x * 8) + tx * 8 + (within & 7);
+		}
+		const int id = slot * pixel_count + pixel;
+		int seed = first_pass + slot * pass_stride;
+		float3 o, d;
+		generate_camera_ray(cam, pixel, seed, cfg.use_anti_alias != 0, o, d);
+		st.ray_o[id] = make_float4(o.x, o.y, o.z, 0.0f);
+		st.ray_d[id] = make_float4(d.x, d.y, d.z, next_bounce_bound(cfg, cfg.air_sigma_a, cfg.air_sigma_s, seed, pixel, 0));
+		st.radiance[id] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+		queue[i] = id;
+	}
+}
+
+} // namespace ptb
