@@ -713,6 +713,7 @@ int render_impl(ptb_renderer* r, int first_pass, int stride, int n_passes, bool 
 	if (!r || r->host_only) { set_error("[Error]renderer has no CUDA device (host-only handle): rendering is unavailable, there is no CPU fallback"); return 1; }
 	if (!r->scene_loaded) { set_error("[Error]no scene loaded"); return 1; }
 	if (n_passes <= 0) return 0;
+	if (r->nee && r->dscene.bvh_layout != 2) { set_error("[Error]estimator nee needs the binary tree (bvh_layout 2): its shadow stage traverses it"); return 1; }
 	memset(&r->stats, 0, sizeof(r->stats));
 	r->stats.bvh_nodes = r->bvh_nodes; r->stats.bvh_bytes = r->bvh_bytes;
 	const int n_counts = r->cfg.max_tracer_depth + 2;
