@@ -34,8 +34,8 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-PASSES_PER_STEP = 32
-PASSES_IN_FLIGHT = 8      # passes traced as one wavefront batch
+PASSES_PER_STEP = 64
+PASSES_IN_FLIGHT = 16     # passes traced as one wavefront batch (tools/sweep_batching.py: 16 x 4 streams +1.4 % over 8 x 4 at 11.7 GB of path state)
 STREAMS_IN_FLIGHT = 4     # batches overlapped on separate CUDA streams
 METRIC = "path samples/sec (Mspp*px/s), 1080p"
 # dram__bytes_read.sum + dram__bytes_write.sum per k_extend_persistent launch (ncu --set full, workload c2, 8 passes in flight),
