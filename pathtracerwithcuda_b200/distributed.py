@@ -50,6 +50,12 @@ class CudaBackend:
     def synchronize(self):
         self.r.synchronize()
 
+    def after_collective(self):
+        """torch.distributed's NCCL ops run on torch's own stream and only order themselves against torch's CURRENT stream;
+        the renderer works on its own stream, so the host waits here until the collective has written the buffer."""
+        import torch
+        torch.cuda.current_stream(torch.device("cuda", self.r.device)).synchronize()
+
     def finalize(self, total_passes):
         self.r.finalize(total_passes)
 
@@ -94,6 +100,9 @@ class ShardedRenderer:
             t = self.backend.accumulation_tensor()
             self.backend.synchronize()
             self.dist.reduce(t, dst=0, op=self.dist.ReduceOp.SUM)
+            after = getattr(self.backend, "after_collective", None)
+            if after is not None:
+                after()            # the reduced sum must be in place before finalize / clear touch the buffer on another stream
         if self.rank == 0:
             self.backend.finalize(total_passes)
         return total_passes
