@@ -169,6 +169,9 @@ int ptb_bvh_info(ptb_renderer* r, int64_t* out_i, double* out_d);
 int ptb_bvh_leaf_labels(ptb_renderer* r, int32_t* out_label);
 /* raw host copy of the device arrays: out_i[0] node records x 16 floats (bvh.h layout #1), and the triangle id per leaf slot */
 int ptb_bvh_download(ptb_renderer* r, float* out_nodes16, int32_t* out_leaf_order);
+/* with option "count_traversal" = 1: out25[0] = most node visits of one ray in the last render, out25[1 + k] = rays with
+ * floor(log2(visits + 1)) == k (binary-tree kernel) */
+int ptb_get_traversal_histogram(ptb_renderer* r, int64_t* out25);
 /* string options: "bvh_builder" = "gpu_sah" (default) | "host_sah"; "passes_in_flight" = "1".."64";
  * "profile_stages" = "0"|"1"; "count_traversal" = "0"|"1"; "sort_by_material" = "0"|"1". */
 int ptb_set_option(ptb_renderer* r, const char* key, const char* value);

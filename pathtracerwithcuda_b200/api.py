@@ -107,6 +107,7 @@ def load_library():
     L.ptb_get_stats.argtypes = [vp, ctypes.POINTER(Stats)]
     L.ptb_get_depth_profile.argtypes = [vp, ci, vp, vp]
     L.ptb_set_option.argtypes = [vp, cp, cp]
+    L.ptb_get_traversal_histogram.argtypes = [vp, vp]
     L.ptb_save_png.argtypes = [vp, cp]
     L.ptb_save_pfm.argtypes = [vp, cp]
     L.ptb_save_checkpoint.argtypes = [vp, cp]
@@ -405,6 +406,11 @@ class Renderer:
         out = np.zeros(self.scene_counts()["triangles"], np.int32)
         self._check(self.lib.ptb_bvh_leaf_labels(self.handle, _ptr(out)))
         return out
+
+    def traversal_histogram(self):
+        out = np.zeros(25, np.int64)
+        self._check(self.lib.ptb_get_traversal_histogram(self.handle, _ptr(out)))
+        return int(out[0]), out[1:].copy()
 
     def stats(self):
         s = Stats()

@@ -10,8 +10,6 @@ namespace ptb
 
 using namespace ptbdev;
 
-__device__ __forceinline__ int float_as_int_(float f) { return __float_as_int(f); }
-
 // Upper bound on the hit distance the NEXT bounce can use (stored in ray_d.w).  In a scattering
 // medium the reference draws a free-flight distance d = -__logf(u0) / sigma_s'.x first thing in the
 // bounce and, when d < t_hit, scatters WITHOUT looking at the hit (path_tracer_kernel.cu:460-486).

@@ -1252,12 +1252,6 @@ int ptb_get_stats(ptb_renderer* r, ptb_stats* out) { if (!r || !out) return 1; *
 int ptb_get_depth_profile(ptb_renderer* r, int max_entries, int64_t* out_segments, double* out_extend_ms)
 {
 	if (!r) return -1;
-	if (max_entries == -32)
-	{
-		// debugging side door: raw traversal counters (max node visits per ray in [2], log2 histogram from [4])
-		memcpy(out_segments, r->traversal_histogram, sizeof(r->traversal_histogram));
-		return 32;
-	}
 	int n = std::min(max_entries, r->cfg.max_tracer_depth);
 	for (int d = 0; d < n; d++)
 	{
@@ -1407,6 +1401,16 @@ int ptb_bvh_download(ptb_renderer* r, float* out_nodes16, int32_t* out_leaf_orde
 		PTB_CUDA(cudaMemcpy(tris.data(), r->dscene.tri_isect, tris.size() * sizeof(float), cudaMemcpyDeviceToHost));
 		for (int i = 0; i < n; i++) memcpy(&out_leaf_order[i], &tris[(size_t)i * 12 + 3], 4);
 	}
+	return 0;
+}
+
+// node visits per ray of the last count_traversal render (binary-tree kernel): out[0] = most visits of one ray,
+// out[1 + k] = rays with floor(log2(visits + 1)) == k, k < 24
+int ptb_get_traversal_histogram(ptb_renderer* r, int64_t* out25)
+{
+	if (!r || !out25) return 1;
+	out25[0] = r->traversal_histogram[2];
+	for (int k = 0; k < 24; k++) out25[1 + k] = r->traversal_histogram[4 + k];
 	return 0;
 }
 

@@ -41,7 +41,5 @@ r.set_option("count_traversal", 1)
 r.render(passes)
 st = r.stats()
 print("nodes/segment %.2f  tris/segment %.2f" % ((st["nodes_visited"] + st["wide_nodes_visited"]) / st["ray_segments"], st["tris_tested"] / st["ray_segments"]))
-import numpy as np, ctypes
-h = np.zeros(32, np.int64); dummy = np.zeros(32, np.float64)
-r.lib.ptb_get_depth_profile(r.handle, -32, h.ctypes.data_as(ctypes.c_void_p), dummy.ctypes.data_as(ctypes.c_void_p))
-print("max node visits of one ray:", h[2]); print("log2 histogram of node visits per ray:", h[4:28].tolist())
+mx, hist = r.traversal_histogram()
+print("max node visits of one ray:", mx); print("log2 histogram of node visits per ray:", hist.tolist())
