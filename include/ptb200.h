@@ -218,8 +218,9 @@ int ptb_scene_texture(ptb_renderer* r, int index, int* width, int* height, uint8
 int ptb_scene_cubemap_face(ptb_renderer* r, int face, uint8_t* out_rgba);
 /* image_loader::load_image (Others/image_loader.cpp:31-95: FreeImage_Load + ConvertTo24Bits, alpha forced to 255,
  * row 0 = top) on one file.  Decoded natively: BMP (24/32-bit), TGA, PNG (non-interlaced; grey / RGB / palette /
- * alpha dropped / 16-bit reduced to the high byte); JPG and other formats through a "<file>.rgba8" side-car
- * (u32 width, u32 height, RGBA8).  out_rgba may be NULL to query the size. */
+ * alpha dropped / 16-bit reduced to the high byte), baseline JPEG (1 or 3 components, 4:4:4 / 4:2:2 / 4:2:0; == libjpeg-turbo);
+ * a "<file>.rgba8" side-car (u32 width, u32 height, RGBA8) takes precedence when present and serves every other format.
+ * out_rgba may be NULL to query the size. */
 int ptb_decode_image(const char* path, int* width, int* height, uint8_t* out_rgba);
 /* the parsed configuration as the reference's 96-byte `configuration` (Core/configuration.h:9-34) */
 int ptb_get_config(ptb_renderer* r, void* out96);

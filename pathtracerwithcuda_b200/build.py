@@ -16,7 +16,7 @@ CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libptb200.so")
 OBJ = os.path.join(HERE, "build")
 
-HOST_SOURCES = ["scene_io.cpp", "bvh_host.cpp", "image_out.cpp"]
+HOST_SOURCES = ["scene_io.cpp", "bvh_host.cpp", "image_out.cpp", "jpeg_decode.cpp"]
 CUDA_SOURCES = ["render.cu", "bvh_build.cu"]
 NVCC_ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 

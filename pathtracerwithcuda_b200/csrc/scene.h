@@ -97,6 +97,8 @@ void set_error(const std::string& msg);
 bool load_config(const std::string& path, Config& out);
 bool load_scene(const std::string& scene_json_path, const std::string& asset_root, HostScene& out);
 bool load_image_rgba8(const std::string& path, Texture& out);
+// baseline JPEG (csrc/jpeg_decode.cpp); false for progressive / arithmetic / CMYK / corrupt files
+bool decode_jpeg(const std::vector<uint8_t>& file, Texture& out);
 // live edits with the reference's arithmetic: triangle_mesh::set_transform_device (triangle_mesh.cpp:271-328)
 // and set_rotate + apply_rotate (:330-426).  They rewrite `triangles` (and `local_triangles`) of one mesh.
 bool set_mesh_transform(HostScene& scene, int mesh, const Vec3& position, const Vec3& scale);

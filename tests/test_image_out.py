@@ -146,3 +146,65 @@ def test_png_decode_filters_depths_and_errors(tmp_path):
         open(p, "wb").write(bad)
         with pytest.raises(ptb.PtbError):
             ptb.decode_image(p)
+
+
+# ---- native baseline JPEG decode (csrc/jpeg_decode.cpp): == libjpeg-turbo's default decode (PIL) bit for bit ----
+def _test_image(h, w, seed):
+    rng = np.random.default_rng(seed)
+    yy, xx = np.mgrid[0:h, 0:w]
+    img = np.stack([(xx * 1.3 + yy * 0.4) % 256, (yy * 2.1 + 30 * np.sin(xx / 9.0)) % 256, (xx * yy / 50.0) % 256], -1).astype(np.uint8)
+    img[h // 4:h // 2, w // 4:w // 2] = rng.integers(0, 256, (h // 2 - h // 4, w // 2 - w // 4, 3))
+    return img
+
+
+@pytest.mark.parametrize("shape", [(203, 157), (16, 16), (8, 8), (1, 1), (3, 2), (17, 33), (64, 250)])
+def test_jpeg_decode_matches_pil(tmp_path, shape):
+    Image = pytest.importorskip("PIL.Image")
+    img = _test_image(shape[0], shape[1], shape[0] + shape[1])
+    for sub in (0, 1, 2):                       # 4:4:4, 4:2:2, 4:2:0
+        for kw in (dict(quality=30), dict(quality=75), dict(quality=95, optimize=True), dict(quality=60, restart_marker_blocks=3)):
+            p = str(tmp_path / ("j_%d_%d.jpg" % (sub, kw["quality"])))
+            try:
+                Image.fromarray(img).save(p, subsampling=sub, **kw)
+            except TypeError:
+                continue                        # older Pillow without restart_marker_blocks
+            want = np.asarray(Image.open(p).convert("RGB"))
+            got = ptb.decode_image(p)
+            assert got.shape == want.shape[:2] + (4,)
+            assert np.array_equal(got[..., :3], want), (shape, sub, kw)
+            assert np.all(got[..., 3] == 255)
+    p = str(tmp_path / "grey.jpg")
+    Image.fromarray(img[..., 1]).save(p, quality=85)
+    assert np.array_equal(ptb.decode_image(p)[..., :3], np.asarray(Image.open(p).convert("RGB")))
+
+
+def test_jpeg_progressive_needs_a_sidecar_and_corrupt_files_fail(tmp_path):
+    Image = pytest.importorskip("PIL.Image")
+    img = _test_image(40, 56, 3)
+    p = str(tmp_path / "prog.jpg")
+    Image.fromarray(img).save(p, quality=80, progressive=True)
+    with pytest.raises(ptb.PtbError):
+        ptb.decode_image(p)                     # progressive scans are not decoded natively
+    with open(p + ".rgba8", "wb") as f:         # ... the documented side-car is picked up instead
+        rgba = np.concatenate([img, np.full(img.shape[:2] + (1,), 255, np.uint8)], 2)
+        f.write(struct.pack("<II", img.shape[1], img.shape[0]) + rgba.tobytes())
+    assert np.array_equal(ptb.decode_image(p)[..., :3], img)
+    q = str(tmp_path / "base.jpg")
+    Image.fromarray(img).save(q, quality=80)
+    data = open(q, "rb").read()
+    for bad in (data[:200], data[:2] + b"\xff\xc0\x00\x05abc", b"\xff\xd8\xff\xd9"):
+        open(q, "wb").write(bad)
+        with pytest.raises(ptb.PtbError):
+            ptb.decode_image(q)
+
+
+def test_reference_cube_maps_decode_like_pil():
+    """The reference's own JPEG assets (two 2048^2 4:2:0 cube maps) — only where its checkout exists (this container)."""
+    import glob
+    Image = pytest.importorskip("PIL.Image")
+    files = sorted(glob.glob("/root/reference/gpu_path_tracer/res/texture/*/*.jpg"))
+    if not files:
+        pytest.skip("reference checkout not present")
+    for f in files[:4]:
+        want = np.asarray(Image.open(f).convert("RGB"))
+        assert np.array_equal(ptb.decode_image(f)[..., :3], want), f
