@@ -79,7 +79,10 @@ struct ptb_renderer
 	int extend_persistent = 1;
 	int persistent_grid = 148 * 4;
 	int persistent_grid8 = 148 * 4;
-	int tune_refill = 12, tune_leaf = 8, tune_reps = 3;
+	// voting thresholds of the persistent kernels (tools/sweep_tune.py, profiles/r01_experiments.md): refill when >= N lanes are idle,
+	// run a leaf / triangle phase when >= N lanes wait for one, node steps per node phase
+	int tune_refill = 20, tune_leaf = 6, tune_reps = 6;   // binary-tree kernel (camera rays + first bounce)
+	int tune_refill8 = 12, tune_leaf8 = 6;                 // wide-tree kernel (deep bounces)
 
 	cudaStream_t stream = nullptr;
 	int sm_count = 148;
@@ -624,15 +627,15 @@ void launch_extend(ptb_renderer* r, cudaStream_t stream, size_t items, const Pat
 		DeviceScene sc8 = r->dscene;
 		sc8.bvh_nodes = r->dscene.bvh8_nodes; sc8.tri_isect = r->dscene.tri_isect8; sc8.bvh_layout = 8;
 		int grid = std::max(1, std::min(r->persistent_grid8, (int)((items + 127) / 128)));
-		if (r->count_traversal) k_extend_persistent8<true><<<grid, 128, 0, stream>>>(sc8, st, queue, count_ptr, work_counter, r->counters, r->tune_refill, r->tune_leaf);
-		else k_extend_persistent8<false><<<grid, 128, 0, stream>>>(sc8, st, queue, count_ptr, work_counter, r->counters, r->tune_refill, r->tune_leaf);
+		if (r->count_traversal) k_extend_persistent8<true><<<grid, 128, 0, stream>>>(sc8, st, queue, count_ptr, work_counter, r->counters, r->tune_refill8, r->tune_leaf8);
+		else k_extend_persistent8<false><<<grid, 128, 0, stream>>>(sc8, st, queue, count_ptr, work_counter, r->counters, r->tune_refill8, r->tune_leaf8);
 		return;
 	}
 	if (wide && r->extend_persistent)
 	{
 		int grid = std::max(1, std::min(r->persistent_grid8, (int)((items + 127) / 128)));
-		if (r->count_traversal) k_extend_persistent8<true><<<grid, 128, 0, stream>>>(r->dscene, st, queue, count_ptr, work_counter, r->counters, r->tune_refill, r->tune_leaf);
-		else k_extend_persistent8<false><<<grid, 128, 0, stream>>>(r->dscene, st, queue, count_ptr, work_counter, r->counters, r->tune_refill, r->tune_leaf);
+		if (r->count_traversal) k_extend_persistent8<true><<<grid, 128, 0, stream>>>(r->dscene, st, queue, count_ptr, work_counter, r->counters, r->tune_refill8, r->tune_leaf8);
+		else k_extend_persistent8<false><<<grid, 128, 0, stream>>>(r->dscene, st, queue, count_ptr, work_counter, r->counters, r->tune_refill8, r->tune_leaf8);
 		return;
 	}
 	if (!wide && r->extend_persistent)
@@ -1491,6 +1494,8 @@ int ptb_set_option(ptb_renderer* r, const char* key, const char* value)
 	if (k == "tune_refill") { r->tune_refill = atoi(value); return 0; }
 	if (k == "tune_leaf") { r->tune_leaf = atoi(value); return 0; }
 	if (k == "tune_reps") { r->tune_reps = atoi(value); return 0; }
+	if (k == "tune_refill8") { r->tune_refill8 = atoi(value); return 0; }
+	if (k == "tune_leaf8") { r->tune_leaf8 = atoi(value); return 0; }
 	if (k == "persistent_grid") { r->persistent_grid = atoi(value); return 0; }
 	if (k == "bvh_collapse") { if (v != "gpu" && v != "host") { set_error("[Error]bvh_collapse must be gpu or host"); return 1; } r->bvh_collapse = v; return 0; }
 	if (k == "bvh_hybrid") { r->bvh_hybrid = atoi(value); return 0; }             // takes effect at the next ptb_load_scene

@@ -15,7 +15,10 @@ if w["aperture"] >= 0:
     r.set_camera(ptb.default_camera(w["width"], w["height"], w["aperture"], w["focal"]))
 r.render(64)
 res = []
-for refill, leaf, reps in itertools.product([8, 12, 16, 20], [4, 8, 12, 16], [2, 3, 4]):
+grid = [int(x) for x in sys.argv[2].split(",")] if len(sys.argv) > 2 else [8, 12, 16, 20]
+leafs = [int(x) for x in sys.argv[3].split(",")] if len(sys.argv) > 3 else [4, 8, 12, 16]
+repss = [int(x) for x in sys.argv[4].split(",")] if len(sys.argv) > 4 else [2, 3, 4]
+for refill, leaf, reps in itertools.product(grid, leafs, repss):
     r.set_option("tune_refill", refill); r.set_option("tune_leaf", leaf); r.set_option("tune_reps", reps)
     best = min((r.render(64), r.stats()["gpu_ms_total"])[1] for _ in range(3))
     res.append((best, refill, leaf, reps))
