@@ -302,7 +302,7 @@ __device__ __forceinline__ void load_node(const float4* np, float4& n0, float4& 
 #define PTB_PERSISTENT_MIN_BLOCKS 8
 #endif
 
-template <bool COUNT>
+template <bool COUNT, int REPS>
 __global__ void __launch_bounds__(128, PTB_PERSISTENT_MIN_BLOCKS) k_extend_persistent(DeviceScene sc, PathState st, const int* __restrict__ queue, const int* __restrict__ count_ptr,
 	int* __restrict__ work_counter, unsigned long long* __restrict__ counters, int refill_min, int leaf_min, int node_reps)
 {
@@ -429,7 +429,9 @@ __global__ void __launch_bounds__(128, PTB_PERSISTENT_MIN_BLOCKS) k_extend_persi
 		}
 
 		// ---- node phase (node_reps steps for every lane sitting at an inner node)
-		for (int rep = 0; rep < node_reps; rep++)
+		// REPS > 0: the shipped count, unrolled at compile time; REPS == 0: runtime count (tuning sweeps)
+#pragma unroll
+		for (int rep = 0; rep < (REPS > 0 ? REPS : node_reps); rep++)
 		if (id >= 0 && node >= 0)
 		{
 			if (COUNT) { n_nodes++; ray_nodes++; }

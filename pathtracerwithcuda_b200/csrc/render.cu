@@ -44,6 +44,8 @@ namespace ptb
 
 using namespace ptb;
 
+#define PTB_NODE_REPS 6
+
 struct ptb_renderer
 {
 	Config cfg;
@@ -82,6 +84,7 @@ struct ptb_renderer
 	// voting thresholds of the persistent kernels (tools/sweep_tune.py, profiles/r01_experiments.md): refill when >= N lanes are idle,
 	// run a leaf / triangle phase when >= N lanes wait for one, node steps per node phase
 	int tune_refill = 20, tune_leaf = 6, tune_reps = 6;   // binary-tree kernel (camera rays + first bounce)
+	int unroll_reps = 1;
 	int tune_refill8 = 12, tune_leaf8 = 6;                 // wide-tree kernel (deep bounces)
 
 	cudaStream_t stream = nullptr;
@@ -642,8 +645,9 @@ void launch_extend(ptb_renderer* r, cudaStream_t stream, size_t items, const Pat
 	{
 		// persistent warps: one resident wave, sized from the occupancy the kernel actually gets
 		int grid = std::max(1, std::min(r->persistent_grid, (int)((items + 127) / 128)));
-		if (r->count_traversal) k_extend_persistent<true><<<grid, 128, 0, stream>>>(r->dscene, st, queue, count_ptr, work_counter, r->counters, r->tune_refill, r->tune_leaf, r->tune_reps);
-		else k_extend_persistent<false><<<grid, 128, 0, stream>>>(r->dscene, st, queue, count_ptr, work_counter, r->counters, r->tune_refill, r->tune_leaf, r->tune_reps);
+		if (r->count_traversal) k_extend_persistent<true, 0><<<grid, 128, 0, stream>>>(r->dscene, st, queue, count_ptr, work_counter, r->counters, r->tune_refill, r->tune_leaf, r->tune_reps);
+		else if (r->tune_reps == PTB_NODE_REPS && r->unroll_reps) k_extend_persistent<false, PTB_NODE_REPS><<<grid, 128, 0, stream>>>(r->dscene, st, queue, count_ptr, work_counter, r->counters, r->tune_refill, r->tune_leaf, r->tune_reps);
+		else k_extend_persistent<false, 0><<<grid, 128, 0, stream>>>(r->dscene, st, queue, count_ptr, work_counter, r->counters, r->tune_refill, r->tune_leaf, r->tune_reps);
 		return;
 	}
 	int grid = grid_for(r, items, 128, 16);
@@ -883,7 +887,7 @@ ptb_renderer* ptb_create(const char* config_json_path, int cuda_device)
 	}
 	{
 		int per_sm = 0;
-		if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_extend_persistent<false>, 128, 0) == cudaSuccess && per_sm > 0)
+		if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_extend_persistent<false, 0>, 128, 0) == cudaSuccess && per_sm > 0)
 			r->persistent_grid = r->sm_count * per_sm;
 		if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_extend_persistent8<false>, 128, 0) == cudaSuccess && per_sm > 0)
 			r->persistent_grid8 = r->sm_count * per_sm;
@@ -1494,6 +1498,7 @@ int ptb_set_option(ptb_renderer* r, const char* key, const char* value)
 	if (k == "tune_refill") { r->tune_refill = atoi(value); return 0; }
 	if (k == "tune_leaf") { r->tune_leaf = atoi(value); return 0; }
 	if (k == "tune_reps") { r->tune_reps = atoi(value); return 0; }
+	if (k == "unroll_reps") { r->unroll_reps = atoi(value); return 0; }
 	if (k == "tune_refill8") { r->tune_refill8 = atoi(value); return 0; }
 	if (k == "tune_leaf8") { r->tune_leaf8 = atoi(value); return 0; }
 	if (k == "persistent_grid") { r->persistent_grid = atoi(value); return 0; }
