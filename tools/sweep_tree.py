@@ -14,8 +14,8 @@ root = tempfile.mkdtemp(prefix="ptb_sweep_")
 w = pr.make_workload(root, name)
 for cfg in configs:
     r = ptb.Renderer(w["config"], device=0)
-    r.set_option("passes_in_flight", 8)
-    r.set_option("streams_in_flight", 4)
+    r.set_option("passes_in_flight", int(os.environ.get("PIF", 8)))
+    r.set_option("streams_in_flight", int(os.environ.get("STREAMS", 4)))
     for kv in [c for c in cfg.split(",") if c]:
         k, v = kv.split("=")
         r.set_option(k, v)
