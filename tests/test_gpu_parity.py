@@ -253,3 +253,23 @@ def test_scheduling_options_do_not_change_the_image(workload_root):
         if ref is None:
             ref = img
         assert np.array_equal(ref.view(np.uint32), img.view(np.uint32)), opts
+
+
+@pytest.mark.skipif(not os.path.exists(REF_LIB), reason="oracle/_ref/libptref.so not present on this box")
+@pytest.mark.parametrize("scene", ["cornell_box_simple", "tex_cube", "vanille", "subsurface_scattering_s"])
+def test_live_reference_on_its_own_scene_files(scene):
+    """The reference's OWN res/scene files (staged copy, read unchanged by both sides): spheres + cornell.obj, a PNG-textured cube,
+    a 25 k-triangle TGA-textured mesh, a 120 k-triangle subsurface mesh."""
+    out = tempfile.mktemp(suffix=".json")
+    tool = os.path.join(REPO, "tools", "parity_report.py")
+    subprocess.run([sys.executable, tool, "--scene", scene, "--width", "160", "--height", "90", "--depth", "8", "--spp", "2", "--out", out],
+                   check=True, capture_output=True)
+    rep = json.load(open(out))
+    assert rep["triangles_bit_equal"] and rep["camera_rays_bit_equal"]
+    for d, c in rep["prim_ids"].items():
+        assert c["other"] == 0 and c["near_tie_1e-5"] == 0, (d, c)
+        assert c["mismatch"] == c["exact_t_ties"] + c["reference_missed_hit"]
+        assert c["t_bit_equal_on_same_prim"] == 1.0 and c["bvh_vs_bruteforce_mismatch"] == 0
+    for key in ("image_sum", "last_pass"):
+        assert rep[key]["outlier_frac_1e-3"] <= 2e-4 and rep[key]["p999_rel"] <= 1e-3, rep[key]
+    assert rep["image_u8_max_abs_diff"] <= 1
