@@ -308,7 +308,7 @@ def run_ptb200(args, w, root, rank, local_rank, world):
 
     # ---- e2e through the C ABI with host buffers (camera in, 8-bit image out), wall clock incl. copies
     cam = r.camera()
-    u8 = np.zeros((w["height"], w["width"], 3), np.uint8)
+    u8 = torch.empty((w["height"], w["width"], 3), dtype=torch.uint8, pin_memory=True).numpy()   # pinned host buffer for the per-step image read-back
     sr.begin()
     sr.render_local(PASSES_PER_STEP)
     barrier()

@@ -1,0 +1,29 @@
+#!/usr/bin/env python3
+"""Small end-to-end run for compute-sanitizer (memcheck): GPU build + collapse, render (binary + wide kernels), edits, NEE."""
+import os, sys, tempfile
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+import numpy as np
+import pathtracerwithcuda_b200 as ptb
+from pathtracerwithcuda_b200 import procedural as pr
+import make_golden as mg
+root = tempfile.mkdtemp(prefix="ptb_san_")
+for name, kw in (("mix", dict(width=96, height=72)), ("c2", dict(width=64, height=36, tri_scale=0.2))):
+    w = pr.make_workload(root, name, **kw)
+    for opts in (dict(), dict(bvh_layout=8), dict(estimator="nee"), dict(sort_by_material=1, octant_order=1, extend_persistent=0)):
+        r = ptb.Renderer(w["config"], device=0)
+        for k, v in opts.items():
+            r.set_option(k, v)
+        r.load_scene(w["scene"], root)
+        r.render(3)
+        rays = r.generate_rays(1)[::5]
+        p, t = r.trace_batch(rays)
+        if name == "mix" and not opts:
+            for op, a in mg.EDIT_SCRIPT:
+                mg.apply_edit(r, op, a)
+            r.render(2)
+            print("bvh after edits", r.bvh_info()["valid"])
+        print(name, opts, float(r.image_f32().mean()), int((p >= 0).sum()), flush=True)
+        r.close()
+print("done")
