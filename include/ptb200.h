@@ -205,6 +205,9 @@ int ptb_set_sphere(ptb_renderer* r, int index, const void* sphere100);
 int ptb_set_mesh_material(ptb_renderer* r, int mesh, const ptb_material* mats, int n);
 int ptb_set_mesh_transform(ptb_renderer* r, int mesh, const float* position3, const float* scale3);
 int ptb_apply_mesh_rotate(ptb_renderer* r, int mesh, const float* rotate_degrees3);
+/* live config toggles: the reference's UI edits the managed `configuration` (Core/configuration.h:9-34) between passes and clears;
+ * config96 = that 96-byte struct (ptb_get_config returns the current one).  Width / Height / MaxDepth may not change. */
+int ptb_set_config(ptb_renderer* r, const void* config96);
 int ptb_get_mesh_placement(ptb_renderer* r, int mesh, float* out_position3, float* out_scale3, float* out_rotate3, int* out_first_triangle, int* out_triangle_count, int* out_first_material, int* out_material_count);
 
 /* ---- loaded-scene introspection (flat host copies; used by the parity tests) ------------- */

@@ -129,6 +129,7 @@ def load_library():
     L.ptb_scene_texture.argtypes = [vp, ci, ctypes.POINTER(ci), ctypes.POINTER(ci), vp]
     L.ptb_scene_cubemap_face.argtypes = [vp, ci, vp]
     L.ptb_get_config.argtypes = [vp, vp]
+    L.ptb_set_config.argtypes = [vp, vp]
     L.ptb_decode_image.argtypes = [cp, ctypes.POINTER(ci), ctypes.POINTER(ci), vp]
     _lib = L
     return L
@@ -217,6 +218,10 @@ class Renderer:
         out = np.zeros(1, CONFIG_DTYPE)
         self._check(self.lib.ptb_get_config(self.handle, _ptr(out)))
         return out[0]
+
+    def set_config(self, config):
+        a = np.ascontiguousarray(np.asarray(config, CONFIG_DTYPE).reshape(1))
+        self._check(self.lib.ptb_set_config(self.handle, _ptr(a)))
 
     def scene_counts(self):
         vals = [ctypes.c_int() for _ in range(6)]

@@ -1150,6 +1150,31 @@ int ptb_load_checkpoint(ptb_renderer* r, const char* path, int restore_camera)
 	return rc;
 }
 
+// Live config toggles: the reference's UI writes into the managed `configuration` between passes
+// (Main/window.cpp; fields of Core/configuration.h:9-34 read by the kernels every pass) and restarts the accumulation.
+// Everything the path reads per pass can change; the image size and MaxDepth size the work buffers and need a new handle.
+int ptb_set_config(ptb_renderer* r, const void* config96)
+{
+	if (!r || !config96) { set_error("[Error]null argument"); return 1; }
+	Config c;
+	memcpy(&c, config96, sizeof(Config));
+	if (c.width != r->cfg.width || c.height != r->cfg.height || c.max_tracer_depth != r->cfg.max_tracer_depth)
+	{
+		set_error("[Error]ptb_set_config: Width / Height / MaxDepth size the work buffers; create a new renderer for them");
+		return 1;
+	}
+	if (!r->host_only)
+	{
+		cudaSetDevice(r->device);
+		if (sync_all_streams(r)) return 1;
+	}
+	r->cfg = c;
+	r->dscene.sky.use_sky_box = c.use_sky_box ? 1 : 0;
+	r->dscene.sky.use_sky = c.use_sky ? 1 : 0;
+	r->dscene.sky.use_bilinear = c.use_bilinear ? 1 : 0;
+	return ptb_clear(r);
+}
+
 int ptb_pass_counter(ptb_renderer* r) { return r ? r->pass_counter : 0; }
 int ptb_width(ptb_renderer* r) { return r ? r->cfg.width : 0; }
 int ptb_height(ptb_renderer* r) { return r ? r->cfg.height : 0; }

@@ -85,3 +85,49 @@ def test_edits_vs_live_reference(mode):
         for key in ("image_sum", "last_pass"):
             assert rep[key]["outlier_frac_1e-3"] <= 5e-4 and rep[key]["p999_rel"] <= 2e-3, rep[key]
         assert rep["image_u8_max_abs_diff"] <= 1
+
+
+def test_live_config_toggles(workload_root, tmp_path):
+    """ptb_set_config: the per-pass switches of the reference `configuration` (sky box / sky / bilinear / gamma / anti-alias /
+    thresholds / bias / air medium) take effect on the next pass and restart the accumulation; the image equals a fresh
+    renderer created with that configuration."""
+    from pathtracerwithcuda_b200 import procedural as pr
+    root, w = workload_root("mix", width=96, height=72)
+    cam = ptb.default_camera(w["width"], w["height"], w["aperture"], w["focal"])
+    r = ptb.Renderer(w["config"], device=0)
+    r.load_scene(w["scene"], root)
+    r.set_camera(cam)
+    r.render(2)
+    base = r.image_f32().copy()
+    cfg = r.config().copy()
+    variants = [dict(use_sky_box=0, use_sky=1), dict(use_bilinear=0, gamma_correction=0), dict(use_anti_alias=0, vector_bias_length=0.001),
+                dict(air_reduced_scattering_coef=[0.05, 0.05, 0.05], air_absorption_coef=[0.01, 0.02, 0.03])]
+    json_keys = {"use_sky_box": "Skybox", "use_sky": "Sky", "use_bilinear": "BilinearSample", "gamma_correction": "GammaCorrection",
+                 "use_anti_alias": "AntiAlias", "vector_bias_length": "BiasLength"}
+    for i, v in enumerate(variants):
+        c = cfg.copy()
+        over = {}
+        for k, val in v.items():
+            c[k] = val
+            if k in json_keys:
+                over[json_keys[k]] = bool(val) if isinstance(val, int) else val
+            elif k == "air_reduced_scattering_coef":
+                over["AirReducedScatteringCoef"] = " ".join(str(x) for x in val)
+            elif k == "air_absorption_coef":
+                over["AirAbsorptionCoef"] = " ".join(str(x) for x in val)
+        r.set_config(c)
+        assert r.pass_counter() == 0
+        r.render(2)
+        got, got8 = r.image_f32().copy(), r.image_u8().copy()
+        assert not np.array_equal(got, base), v
+        path = pr.write_config(str(tmp_path / ("v%d.json" % i)), Width=96, Height=72, MaxDepth=w["depth"], **over)
+        f = ptb.Renderer(path, device=0)
+        f.load_scene(w["scene"], root)
+        f.set_camera(cam)
+        f.render(2)
+        assert np.array_equal(got.view(np.uint32), f.image_f32().view(np.uint32)), v
+        assert np.array_equal(got8, f.image_u8()), v
+    bad = cfg.copy()
+    bad["max_tracer_depth"] = 3
+    with pytest.raises(ptb.PtbError):
+        r.set_config(bad)
