@@ -221,10 +221,17 @@ int ptb_scene_texture(ptb_renderer* r, int index, int* width, int* height, uint8
 int ptb_scene_cubemap_face(ptb_renderer* r, int face, uint8_t* out_rgba);
 /* image_loader::load_image (Others/image_loader.cpp:31-95: FreeImage_Load + ConvertTo24Bits, alpha forced to 255,
  * row 0 = top) on one file.  Decoded natively: BMP (24/32-bit), TGA, PNG (non-interlaced; grey / RGB / palette /
- * alpha dropped / 16-bit reduced to the high byte), baseline JPEG (1 or 3 components, 4:4:4 / 4:2:2 / 4:2:0; == libjpeg-turbo);
+ * alpha dropped / 16-bit reduced to the high byte), baseline JPEG (1 or 3 components, 4:4:4 / 4:2:2 / 4:2:0);
  * a "<file>.rgba8" side-car (u32 width, u32 height, RGBA8) takes precedence when present and serves every other format.
  * out_rgba may be NULL to query the size. */
 int ptb_decode_image(const char* path, int* width, int* height, uint8_t* out_rgba);
+/* JPEG decode parameters, process-wide, for every later load:
+ *   "reference" (default) what the reference gets from FreeImage_Load(fif, name, 0): flags 0 = JPEG_FAST
+ *               (lib/free_image/FreeImage.h:693-695) -> libjpeg 9a with the "ifast" IDCT and replicated chroma;
+ *   "fast"      libjpeg-turbo with dct_method=JDCT_IFAST, do_fancy_upsampling=FALSE (bit-identical; differs from "reference" by
+ *               one colour-table constant);
+ *   "accurate"  libjpeg-turbo's default decode (bit-identical to PIL). */
+int ptb_set_jpeg_decode(const char* mode);
 /* the parsed configuration as the reference's 96-byte `configuration` (Core/configuration.h:9-34) */
 int ptb_get_config(ptb_renderer* r, void* out96);
 

@@ -131,6 +131,7 @@ def load_library():
     L.ptb_get_config.argtypes = [vp, vp]
     L.ptb_set_config.argtypes = [vp, vp]
     L.ptb_decode_image.argtypes = [cp, ctypes.POINTER(ci), ctypes.POINTER(ci), vp]
+    L.ptb_set_jpeg_decode.argtypes = [cp]
     _lib = L
     return L
 
@@ -163,6 +164,13 @@ def decode_image(path):
     if L.ptb_decode_image(os.fsencode(path), ctypes.byref(w), ctypes.byref(h), _ptr(out)) != 0:
         raise PtbError(last_error())
     return out
+
+
+def set_jpeg_decode(mode):
+    """'reference' (default: FreeImage as the reference calls it — ifast IDCT, replicated chroma), 'fast' (libjpeg-turbo fast
+    decode) or 'accurate' (libjpeg-turbo default decode == PIL); process-wide, applies to later loads."""
+    if load_library().ptb_set_jpeg_decode(mode.encode()) != 0:
+        raise PtbError(last_error())
 
 
 def write_png(path, rgb_u8):

@@ -2,14 +2,22 @@
 //
 // The reference decodes images through FreeImage (Others/image_loader.cpp:31-95: FreeImage_Load + ConvertTo24Bits, a
 // binary-only library built on IJG libjpeg); its own assets are two cube maps of baseline 4:2:0 JPEGs
-// (res/texture/lycksele, maskonaive).  This file restates the published IJG algorithms those libraries share:
-//   * sequential Huffman decoding (ITU T.81 Annex F), 8-bit precision, 1 or 3 components, sampling factors 1 or 2;
-//   * the "islow" integer inverse DCT (jidctint.c: 13-bit constants, two passes, DESCALE rounding);
-//   * "fancy" triangle-filter chroma upsampling for 2h1v and 2h2v (jdsample.c) and plain replication otherwise;
-//   * the fixed-point YCbCr -> RGB tables (jdcolor.c, 16 fraction bits).
-// With those choices the output is bit-identical to libjpeg-turbo's default decode (what PIL uses; tests/test_image_out.py).
-// FreeImage 3.17 links IJG libjpeg 9, whose chroma upsampling differs by a few levels at edges; no source or binary of it
-// is available here, so that residual is unpinned (the harness feeds both sides the same decoded RGBA8 through side-cars).
+// (res/texture/lycksele, maskonaive).  It passes load flags 0 (image_loader.cpp:45), which FreeImage documents as
+// JPEG_DEFAULT = JPEG_FAST, "load the file as fast as possible, sacrificing some quality"
+// (lib/free_image/FreeImage.h:693-695): libjpeg then runs with dct_method = JDCT_IFAST and do_fancy_upsampling = FALSE.
+// Three modes (set_jpeg_mode / ptb_set_jpeg_decode), restating the published IJG algorithms:
+//   * kJpegReference (default) — what the reference gets: sequential Huffman decoding (ITU T.81 Annex F); the AAN "ifast"
+//     integer inverse DCT (jidctfst.c: 8-bit constants, multipliers pre-scaled by the AAN factors in jddctmgr.c, NO rounding in
+//     the descales, 10-bit wrapped range limit); chroma replicated (jdsample.c h2v1/h2v2_upsample == jdmerge.c); fixed-point
+//     YCbCr -> RGB with the constants of IJG libjpeg 9a (what FreeImage 3.17 bundles): G = Y - 0.344136286 Cb - 0.714136286 Cr;
+//   * kJpegFast — the same with libjpeg 6b's rounded constants 0.34414 / 0.71414 (one table entry differs by 1/65536):
+//     bit-identical to libjpeg-turbo run with dct_method=JDCT_IFAST, do_fancy_upsampling=FALSE (pinned through
+//     oracle/jpeg_lib_shim.c on the reference's own cube maps, committed golden vectors and live synthetic files,
+//     tests/test_image_out.py);
+//   * kJpegAccurate — "islow" IDCT (jidctint.c), triangle-filter chroma upsampling, 6b constants: bit-identical to
+//     libjpeg-turbo's default decode, i.e. PIL.
+// The IFAST + replication part of the reference mode is therefore pinned; its colour constant (22553 vs 22554 in one table)
+// follows the published libjpeg 9a source and is not pinned by a binary here.
 // Progressive / arithmetic-coded / 12-bit / CMYK files are rejected (side-car needed).
 #include "scene.h"
 
@@ -177,17 +185,95 @@ void idct_islow(const int16_t* coef, const uint16_t* quant, uint8_t* out, int st
 	}
 }
 
+// jidctfst.c ("ifast", AAN): multipliers = quant * AAN scale factors (jddctmgr.c: 14-bit table, DESCALE by 14 - IFAST_SCALE_BITS),
+// 8-bit constants, descales WITHOUT rounding, output through the 10-bit wrapped range-limit table.
+// kAanScales[8 i + j] = round(2^14 s_i s_j), s_0 = 1, s_k = sqrt(2) cos(k pi / 16).
+const int16_t kAanScales[64] = {
+	16384, 22725, 21407, 19266, 16384, 12873, 8867, 4520, 22725, 31521, 29692, 26722, 22725, 17855, 12299, 6270,
+	21407, 29692, 27969, 25172, 21407, 16819, 11585, 5906, 19266, 26722, 25172, 22654, 19266, 15137, 10426, 5315,
+	16384, 22725, 21407, 19266, 16384, 12873, 8867, 4520, 12873, 17855, 16819, 15137, 12873, 10114, 6967, 3552,
+	8867, 12299, 11585, 10426, 8867, 6967, 4799, 2446, 4520, 6270, 5906, 5315, 4520, 3552, 2446, 1247 };
+
+inline void ifast_multipliers(const uint16_t* quant, int* mult)
+{
+	for (int i = 0; i < 64; i++) mult[i] = (int)(((int64_t)quant[i] * kAanScales[i] + (1 << 11)) >> 12);
+}
+
+inline int fmul(int v, int c) { return (v * c) >> 8; }
+inline uint8_t range_limit_wrapped(int x)
+{
+	x &= 1023;                       // RANGE_MASK: values beyond +-512 wrap, as in the library's table
+	if (x >= 512) x -= 1024;
+	x += 128;
+	return (uint8_t)(x < 0 ? 0 : (x > 255 ? 255 : x));
+}
+
+void idct_ifast(const int16_t* coef, const int* mult, uint8_t* out, int stride)
+{
+	const int F1_082 = 277, F1_414 = 362, F1_847 = 473, F2_613 = 669;
+	int ws[64];
+	for (int c = 0; c < 8; c++)
+	{
+		const int16_t* in = coef + c;
+		const int* q = mult + c;
+		int* w = ws + c;
+		if (in[8] == 0 && in[16] == 0 && in[24] == 0 && in[32] == 0 && in[40] == 0 && in[48] == 0 && in[56] == 0)
+		{
+			const int dc = in[0] * q[0];
+			for (int r = 0; r < 8; r++) w[r * 8] = dc;
+			continue;
+		}
+		int tmp0 = in[0] * q[0], tmp1 = in[16] * q[16], tmp2 = in[32] * q[32], tmp3 = in[48] * q[48];
+		int tmp10 = tmp0 + tmp2, tmp11 = tmp0 - tmp2;
+		int tmp13 = tmp1 + tmp3;
+		int tmp12 = fmul(tmp1 - tmp3, F1_414) - tmp13;
+		tmp0 = tmp10 + tmp13; tmp3 = tmp10 - tmp13; tmp1 = tmp11 + tmp12; tmp2 = tmp11 - tmp12;
+		int tmp4 = in[8] * q[8], tmp5 = in[24] * q[24], tmp6 = in[40] * q[40], tmp7 = in[56] * q[56];
+		const int z13 = tmp6 + tmp5, z10 = tmp6 - tmp5, z11 = tmp4 + tmp7, z12 = tmp4 - tmp7;
+		tmp7 = z11 + z13;
+		tmp11 = fmul(z11 - z13, F1_414);
+		const int z5 = fmul(z10 + z12, F1_847);
+		tmp10 = fmul(z12, F1_082) - z5;
+		tmp12 = fmul(z10, -F2_613) + z5;
+		tmp6 = tmp12 - tmp7; tmp5 = tmp11 - tmp6; tmp4 = tmp10 + tmp5;
+		w[0] = tmp0 + tmp7; w[56] = tmp0 - tmp7;
+		w[8] = tmp1 + tmp6; w[48] = tmp1 - tmp6;
+		w[16] = tmp2 + tmp5; w[40] = tmp2 - tmp5;
+		w[32] = tmp3 + tmp4; w[24] = tmp3 - tmp4;
+	}
+	for (int r = 0; r < 8; r++)
+	{
+		const int* w = ws + r * 8;
+		uint8_t* o = out + (size_t)r * stride;
+		int tmp10 = w[0] + w[4], tmp11 = w[0] - w[4];
+		int tmp13 = w[2] + w[6];
+		int tmp12 = fmul(w[2] - w[6], F1_414) - tmp13;
+		const int tmp0 = tmp10 + tmp13, tmp3 = tmp10 - tmp13, tmp1 = tmp11 + tmp12, tmp2 = tmp11 - tmp12;
+		const int z13 = w[5] + w[3], z10 = w[5] - w[3], z11 = w[1] + w[7], z12 = w[1] - w[7];
+		const int tmp7 = z11 + z13;
+		tmp11 = fmul(z11 - z13, F1_414);
+		const int z5 = fmul(z10 + z12, F1_847);
+		tmp10 = fmul(z12, F1_082) - z5;
+		tmp12 = fmul(z10, -F2_613) + z5;
+		const int tmp6 = tmp12 - tmp7, tmp5 = tmp11 - tmp6, tmp4 = tmp10 + tmp5;
+		o[0] = range_limit_wrapped((tmp0 + tmp7) >> 5); o[7] = range_limit_wrapped((tmp0 - tmp7) >> 5);
+		o[1] = range_limit_wrapped((tmp1 + tmp6) >> 5); o[6] = range_limit_wrapped((tmp1 - tmp6) >> 5);
+		o[2] = range_limit_wrapped((tmp2 + tmp5) >> 5); o[5] = range_limit_wrapped((tmp2 - tmp5) >> 5);
+		o[4] = range_limit_wrapped((tmp3 + tmp4) >> 5); o[3] = range_limit_wrapped((tmp3 - tmp4) >> 5);
+	}
+}
+
 uint16_t be16(const uint8_t* p) { return (uint16_t)((p[0] << 8) | p[1]); }
 
 // one output row of a component at full resolution (jdsample.c)
-void upsample_row(const Component& c, int hmax, int vmax, int y, int out_width, std::vector<uint8_t>& row)
+void upsample_row(const Component& c, int hmax, int vmax, int y, int out_width, std::vector<uint8_t>& row, bool fancy)
 {
 	const int hs = hmax / c.h, vs = vmax / c.v;
 	row.resize((size_t)out_width + 2);
 	auto src_row = [&](int r) { r = r < 0 ? 0 : (r >= c.height ? c.height - 1 : r); return c.plane.data() + (size_t)r * c.stride; };
 	if (hs == 1 && vs == 1) { memcpy(row.data(), src_row(y), (size_t)out_width); return; }
 	const int n = c.width;
-	if (hs == 2 && vs == 1)
+	if (fancy && hs == 2 && vs == 1)
 	{
 		const uint8_t* in = src_row(y);
 		if (n <= 2) { for (int x = 0; x < out_width; x++) row[x] = in[(x / 2) < n ? x / 2 : n - 1]; return; }   // libjpeg: fancy only if width > 2
@@ -205,7 +291,7 @@ void upsample_row(const Component& c, int hmax, int vmax, int y, int out_width, 
 		memcpy(row.data(), tmp.data(), (size_t)out_width);
 		return;
 	}
-	if (hs == 2 && vs == 2)
+	if (fancy && hs == 2 && vs == 2)
 	{
 		const int r = y >> 1;
 		const uint8_t* in0 = src_row(r);
@@ -241,10 +327,18 @@ void upsample_row(const Component& c, int hmax, int vmax, int y, int out_width, 
 	for (int x = 0; x < out_width; x++) { int sx = x / hs; row[x] = in[sx < n ? sx : n - 1]; }
 }
 
+int g_jpeg_mode = kJpegReference;
+
 } // namespace
+
+void set_jpeg_mode(int mode) { g_jpeg_mode = mode; }
+int jpeg_mode() { return g_jpeg_mode; }
 
 bool decode_jpeg(const std::vector<uint8_t>& f, Texture& out)
 {
+	const int mode = g_jpeg_mode;
+	const bool fast = mode != kJpegAccurate;
+	int ifast_mult[4][64];
 	if (f.size() < 4 || f[0] != 0xff || f[1] != 0xd8) return false;
 	uint16_t quant[4][64];
 	bool quant_present[4] = { false, false, false, false };
@@ -278,6 +372,7 @@ bool decode_jpeg(const std::vector<uint8_t>& f, Texture& out)
 				for (int i = 0; i < 64; i++) { quant[tq][kZigzag[i]] = pq ? be16(&seg[o + 2 * i]) : seg[o + i]; }
 				o += pq ? 128 : 64;
 				quant_present[tq] = true;
+				ifast_multipliers(quant[tq], ifast_mult[tq]);
 			}
 		}
 		else if (marker == 0xc0 || marker == 0xc1)
@@ -394,7 +489,8 @@ bool decode_jpeg(const std::vector<uint8_t>& f, Texture& out)
 									k++;
 								}
 								uint8_t* dst = c.plane.data() + (size_t)(my * c.v + by) * 8 * c.stride + (size_t)(mx * c.h + bx) * 8;
-								idct_islow(block, quant[c.tq], dst, c.stride);
+								if (fast) idct_ifast(block, ifast_mult[c.tq], dst, c.stride);
+								else idct_islow(block, quant[c.tq], dst, c.stride);
 							}
 					}
 					if (restart_interval) restarts_left--;
@@ -402,32 +498,28 @@ bool decode_jpeg(const std::vector<uint8_t>& f, Texture& out)
 			// ---- upsample + colour conversion
 			out.width = width; out.height = height;
 			out.rgba.assign((size_t)width * height * 4, 255);
-			static int cr_r[256], cb_b[256], cr_g[256], cb_g[256];
-			static bool tables = false;
-			if (!tables)
+			int cr_r[256], cb_b[256], cr_g[256], cb_g[256];
+			const int fix_cb_g = mode == kJpegReference ? 22553 : 22554;   // FIX(0.344136286) in libjpeg 9a, FIX(0.34414) in 6b / turbo
+			for (int i = 0; i < 256; i++)
 			{
-				for (int i = 0; i < 256; i++)
-				{
-					const int x = i - 128;
-					cr_r[i] = (91881 * x + 32768) >> 16;        // FIX(1.40200)
-					cb_b[i] = (116130 * x + 32768) >> 16;       // FIX(1.77200)
-					cr_g[i] = -46802 * x;                       // FIX(0.71414)
-					cb_g[i] = -22554 * x + 32768;               // FIX(0.34414)
-				}
-				tables = true;
+				const int x = i - 128;
+				cr_r[i] = (91881 * x + 32768) >> 16;        // FIX(1.402)
+				cb_b[i] = (116130 * x + 32768) >> 16;       // FIX(1.772)
+				cr_g[i] = -46802 * x;                       // FIX(0.71414) == FIX(0.714136286)
+				cb_g[i] = -fix_cb_g * x + 32768;
 			}
 			std::vector<uint8_t> r0, r1, r2;
 			for (int y = 0; y < height; y++)
 			{
 				uint8_t* dst = &out.rgba[(size_t)y * width * 4];
-				upsample_row(comp[0], hmax, vmax, y, width, r0);
+				upsample_row(comp[0], hmax, vmax, y, width, r0, !fast);
 				if (n_comp == 1)
 				{
 					for (int x = 0; x < width; x++) { dst[4 * x] = dst[4 * x + 1] = dst[4 * x + 2] = r0[x]; }
 					continue;
 				}
-				upsample_row(comp[1], hmax, vmax, y, width, r1);
-				upsample_row(comp[2], hmax, vmax, y, width, r2);
+				upsample_row(comp[1], hmax, vmax, y, width, r1, !fast);
+				upsample_row(comp[2], hmax, vmax, y, width, r2, !fast);
 				for (int x = 0; x < width; x++)
 				{
 					const int yy = r0[x], cb = r1[x], cr = r2[x];

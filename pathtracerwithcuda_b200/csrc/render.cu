@@ -1596,6 +1596,17 @@ int ptb_decode_image(const char* path, int* width, int* height, uint8_t* out_rgb
 	return 0;
 }
 
+// which libjpeg parameters the JPEG decoder reproduces (process-wide; read by every later load)
+int ptb_set_jpeg_decode(const char* mode)
+{
+	const std::string m = mode ? mode : "";
+	if (m == "reference") set_jpeg_mode(kJpegReference);
+	else if (m == "fast") set_jpeg_mode(kJpegFast);
+	else if (m == "accurate") set_jpeg_mode(kJpegAccurate);
+	else { set_error("[Error]jpeg decode mode must be reference, fast or accurate"); return 1; }
+	return 0;
+}
+
 int ptb_scene_cubemap_face(ptb_renderer* r, int face, uint8_t* out_rgba)
 {
 	if (!r || !r->scene_loaded || face < 0 || face > 5) { set_error("[Error]bad cube face"); return 1; }

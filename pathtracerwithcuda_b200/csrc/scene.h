@@ -99,6 +99,11 @@ bool load_scene(const std::string& scene_json_path, const std::string& asset_roo
 bool load_image_rgba8(const std::string& path, Texture& out);
 // baseline JPEG (csrc/jpeg_decode.cpp); false for progressive / arithmetic / CMYK / corrupt files
 bool decode_jpeg(const std::vector<uint8_t>& file, Texture& out);
+// process-wide JPEG decode mode: reference = what FreeImage does for the reference's loads (IFAST IDCT, replicated chroma,
+// libjpeg 9a colour constants), fast = libjpeg-turbo's fast decode, accurate = libjpeg-turbo's default decode (PIL)
+enum { kJpegReference = 0, kJpegFast = 1, kJpegAccurate = 2 };
+void set_jpeg_mode(int mode);
+int jpeg_mode();
 // live edits with the reference's arithmetic: triangle_mesh::set_transform_device (triangle_mesh.cpp:271-328)
 // and set_rotate + apply_rotate (:330-426).  They rewrite `triangles` (and `local_triangles`) of one mesh.
 bool set_mesh_transform(HostScene& scene, int mesh, const Vec3& position, const Vec3& scale);

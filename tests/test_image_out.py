@@ -1,6 +1,7 @@
 """Output writers of the C ABI on host buffers (csrc/image_out.cpp; replaces Main/window.cpp:712-740's lodepng
 screenshot): the PNG must decode (zlib + CRC verified here by hand, and by PIL when present) to the RGBA8 image the
 reference would save; the PFM carries the scaled floats bottom-up."""
+import os
 import struct
 import zlib
 
@@ -148,7 +149,15 @@ def test_png_decode_filters_depths_and_errors(tmp_path):
             ptb.decode_image(p)
 
 
-# ---- native baseline JPEG decode (csrc/jpeg_decode.cpp): == libjpeg-turbo's default decode (PIL) bit for bit ----
+# ---- native baseline JPEG decode (csrc/jpeg_decode.cpp) ----
+# "accurate" mode == libjpeg-turbo's default decode (PIL) bit for bit; "fast" mode == libjpeg-turbo with the parameters FreeImage
+# sets for the reference's loads (ifast IDCT, replicated chroma); "reference" (default) = "fast" with libjpeg 9a's colour constant.
+@pytest.fixture
+def jpeg_mode():
+    yield ptb.set_jpeg_decode
+    ptb.set_jpeg_decode("reference")
+
+
 def _test_image(h, w, seed):
     rng = np.random.default_rng(seed)
     yy, xx = np.mgrid[0:h, 0:w]
@@ -158,8 +167,9 @@ def _test_image(h, w, seed):
 
 
 @pytest.mark.parametrize("shape", [(203, 157), (16, 16), (8, 8), (1, 1), (3, 2), (17, 33), (64, 250)])
-def test_jpeg_decode_matches_pil(tmp_path, shape):
+def test_jpeg_decode_matches_pil(tmp_path, shape, jpeg_mode):
     Image = pytest.importorskip("PIL.Image")
+    jpeg_mode("accurate")
     img = _test_image(shape[0], shape[1], shape[0] + shape[1])
     for sub in (0, 1, 2):                       # 4:4:4, 4:2:2, 4:2:0
         for kw in (dict(quality=30), dict(quality=75), dict(quality=95, optimize=True), dict(quality=60, restart_marker_blocks=3)):
@@ -198,13 +208,95 @@ def test_jpeg_progressive_needs_a_sidecar_and_corrupt_files_fail(tmp_path):
             ptb.decode_image(q)
 
 
-def test_reference_cube_maps_decode_like_pil():
+def test_jpeg_fast_mode_matches_golden(tmp_path, jpeg_mode):
+    """Committed vectors (tests/golden/make_jpeg_golden.py): libjpeg-turbo run with dct_method=JDCT_IFAST and
+    do_fancy_upsampling=FALSE — what FreeImage_Load(..., 0) selects for the reference (Others/image_loader.cpp:45)."""
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "jpeg_fast.npz"))
+    n = int(g["count"])
+    assert n >= 20
+    worst_ref = 0.0
+    for k in range(n):
+        p = str(tmp_path / ("g%02d.jpg" % k))
+        open(p, "wb").write(g["jpeg_%02d" % k].tobytes())
+        want = g["rgb_%02d" % k]
+        jpeg_mode("fast")
+        got = ptb.decode_image(p)
+        assert np.array_equal(got[..., :3], want), k
+        assert np.all(got[..., 3] == 255)
+        # the default mode differs only through one colour-table entry (libjpeg 9a's 0.344136286 vs 6b's 0.34414)
+        jpeg_mode("reference")
+        ref = ptb.decode_image(p)[..., :3].astype(int)
+        d = np.abs(ref - want.astype(int))
+        assert d.max() <= 1 and np.all(d[..., 0] == 0) and np.all(d[..., 2] == 0)
+        worst_ref = max(worst_ref, float((d > 0).mean()))
+    assert worst_ref < 0.01
+    with pytest.raises(ptb.PtbError):
+        ptb.set_jpeg_decode("best")
+
+
+def _libjpeg_shim():
+    """libjpeg-turbo from Pillow's wheel driven through oracle/jpeg_lib_shim.c; None where either is missing."""
+    import ctypes
+    import glob
+    repo = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    so = os.path.join(repo, "oracle", "_build", "libjpegshim.so")
+    try:
+        import PIL
+        found = glob.glob(os.path.join(os.path.dirname(PIL.__file__), "..", "pillow.libs", "libjpeg*.so.62*"))
+        lib = ctypes.CDLL(so)
+    except (ImportError, OSError):
+        return None
+    if not found:
+        return None
+    lib.jpegshim_decode.argtypes = [ctypes.c_char_p, ctypes.c_int, ctypes.c_char_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_int,
+                                    ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int), ctypes.c_void_p]
+    path = os.path.realpath(found[0]).encode()
+
+    def decode(data, dct_method, fancy):
+        w, h = ctypes.c_int(), ctypes.c_int()
+        assert lib.jpegshim_decode(path, 62, data, len(data), dct_method, fancy, ctypes.byref(w), ctypes.byref(h), None) == 0
+        out = np.zeros((h.value, w.value, 3), np.uint8)
+        assert lib.jpegshim_decode(path, 62, data, len(data), dct_method, fancy, ctypes.byref(w), ctypes.byref(h), out.ctypes.data) == 0
+        return out
+    return decode
+
+
+@pytest.mark.parametrize("shape", [(203, 157), (16, 16), (3, 2), (17, 33), (64, 250)])
+def test_jpeg_fast_mode_matches_libjpeg_live(tmp_path, shape, jpeg_mode):
+    Image = pytest.importorskip("PIL.Image")
+    decode = _libjpeg_shim()
+    if decode is None:
+        pytest.skip("libjpeg shim or Pillow's libjpeg not available")
+    img = _test_image(shape[0], shape[1], shape[0] * 3 + shape[1])
+    jpeg_mode("fast")
+    for sub in (0, 1, 2):
+        for kw in (dict(quality=20), dict(quality=75), dict(quality=100), dict(quality=60, restart_marker_blocks=3)):
+            p = str(tmp_path / ("f_%d_%d.jpg" % (sub, kw["quality"])))
+            try:
+                Image.fromarray(img).save(p, subsampling=sub, **kw)
+            except TypeError:
+                continue
+            data = open(p, "rb").read()
+            assert np.array_equal(decode(data, 0, 1), np.asarray(Image.open(p).convert("RGB")))      # the shim, with defaults, is PIL
+            assert np.array_equal(ptb.decode_image(p)[..., :3], decode(data, 1, 0)), (shape, sub, kw)
+
+
+def test_reference_cube_maps_decode_like_libjpeg(jpeg_mode):
     """The reference's own JPEG assets (two 2048^2 4:2:0 cube maps) — only where its checkout exists (this container)."""
     import glob
     Image = pytest.importorskip("PIL.Image")
     files = sorted(glob.glob("/root/reference/gpu_path_tracer/res/texture/*/*.jpg"))
     if not files:
         pytest.skip("reference checkout not present")
+    decode = _libjpeg_shim()
     for f in files[:4]:
-        want = np.asarray(Image.open(f).convert("RGB"))
-        assert np.array_equal(ptb.decode_image(f)[..., :3], want), f
+        jpeg_mode("accurate")
+        assert np.array_equal(ptb.decode_image(f)[..., :3], np.asarray(Image.open(f).convert("RGB"))), f
+        if decode is None:
+            continue
+        jpeg_mode("fast")
+        fast = ptb.decode_image(f)[..., :3]
+        assert np.array_equal(fast, decode(open(f, "rb").read(), 1, 0)), f
+        jpeg_mode("reference")
+        d = np.abs(ptb.decode_image(f)[..., :3].astype(int) - fast.astype(int))
+        assert d.max() <= 1 and (d > 0).mean() < 1e-3
