@@ -32,7 +32,23 @@ __device__ __forceinline__ float3 sample_texture(const DeviceTexture& tex, float
 #ifndef PTB_SHADE_MIN_BLOCKS
 #define PTB_SHADE_MIN_BLOCKS 10   // 48 registers: measured optimum (profiles/r01_experiments.md); the kernel is latency / HBM bound, occupancy pays
 #endif
-template <bool SORT, bool NEE>
+// Russian roulette (estimator option; absent in the reference): from bounce PTB_RR_START_DEPTH on a path
+// survives with probability p = clamp(max(throughput), 0.05, 1) and its throughput is divided by p — unbiased, fewer deep
+// segments.  Own random stream, so the surviving path is still the one the reference estimator follows.
+#ifndef PTB_RR_START_DEPTH
+#define PTB_RR_START_DEPTH 3
+#endif
+__device__ __forceinline__ bool russian_roulette(float3& not_absorbed, int seed, int pixel_index, int depth)
+{
+	Rng rr;
+	rr.seed((uint32_t)(hash_ref(seed) * hash_ref(pixel_index) * hash_ref(depth)) ^ 0x3c6ef372u, 0.0f, 1.0f);
+	const float p = fminf(fmaxf(fmaxf(not_absorbed.x, fmaxf(not_absorbed.y, not_absorbed.z)), 0.05f), 1.0f);
+	if (rr.next() >= p) return false;
+	not_absorbed = not_absorbed * (1.0f / p);
+	return true;
+}
+
+template <bool SORT, bool NEE, bool RR = false>
 __global__ void __launch_bounds__(128, PTB_SHADE_MIN_BLOCKS) k_shade(DeviceScene sc, PathState st, DeviceConfig cfg, int depth, int pixel_count, int first_pass, int pass_stride,
 	const int* __restrict__ queue_in, const int* __restrict__ count_in, int* __restrict__ queue_out, int* __restrict__ count_out, int* __restrict__ shadow_count,
 	int octant_order)
@@ -125,6 +141,11 @@ __global__ void __launch_bounds__(128, PTB_SHADE_MIN_BLOCKS) k_shade(DeviceScene
 					oct_key = (next_d.x < 0.0f ? 4 : 0) | (next_d.y < 0.0f ? 2 : 0) | (next_d.z < 0.0f ? 1 : 0);
 					st.throughput[id] = make_float4(not_absorbed.x, not_absorbed.y, not_absorbed.z, t4.w);
 					if (length(not_absorbed) <= cfg.energy_threshold) alive = false;
+					if (RR && alive && depth >= PTB_RR_START_DEPTH)
+					{
+						alive = russian_roulette(not_absorbed, seed, pixel_index, depth);
+						st.throughput[id] = make_float4(not_absorbed.x, not_absorbed.y, not_absorbed.z, t4.w);
+					}
 					done = true;
 				}
 				else
@@ -316,6 +337,7 @@ __global__ void __launch_bounds__(128, PTB_SHADE_MIN_BLOCKS) k_shade(DeviceScene
 							}
 						}
 					}
+					if (RR && alive && depth >= PTB_RR_START_DEPTH) alive = russian_roulette(not_absorbed, seed, pixel_index, depth);
 					st.ray_o[id] = make_float4(next_o.x, next_o.y, next_o.z, nee_flag);
 					st.throughput[id] = make_float4(not_absorbed.x, not_absorbed.y, not_absorbed.z, medium_bits);
 				}

@@ -67,6 +67,7 @@ struct ptb_renderer
 	int64_t bvh8_nodes = 0;
 	int bvh_max_leaf = 8;                  // binary layout; the wide layout holds <= 3 per leaf slot
 	float bvh_intersect_cost = 0.8f;       // SAH cost of a triangle test relative to a node visit (measured optimum on c2, profiles/r01_experiments.md)
+	int russian_roulette = 0;              // estimator option (absent in the reference): roulette from bounce 3 on, see kernels_shade.cuh
 	float pass_clamp = -1.0f;              // < 0: the reference's per-pass clamp 2 * MaxDepth (path_tracer_kernel.cu:644-651)
 	int nee = 0;                           // estimator: 0 = the reference's (default, parity mode), 1 = next-event estimation
 	int sort_by_material = 0;              // block-local material sort in k_shade (measured: profiles/r01_experiments.md)
@@ -693,18 +694,22 @@ int enqueue_batch(ptb_renderer* r, ptb_renderer::BatchContext& ctx, cudaEvent_t 
 		if (prof) cudaEventRecord(e1, stream);
 		int* shadow_count = ctx.counts + 2 * n_counts + depth;
 		const int sgrid = grid_for(r, total, 128, 16);
+#define PTB_SHADE_ARGS r->dscene, ctx.st, dc, depth, px, first_pass, stride, qin, ctx.counts + depth, qout, ctx.counts + depth + 1, shadow_count, r->octant_order
 		if (r->nee)
 		{
-			if (r->sort_by_material) k_shade<true, true><<<sgrid, 128, 0, stream>>>(r->dscene, ctx.st, dc, depth, px, first_pass, stride, qin, ctx.counts + depth, qout, ctx.counts + depth + 1, shadow_count, r->octant_order);
-			else k_shade<false, true><<<sgrid, 128, 0, stream>>>(r->dscene, ctx.st, dc, depth, px, first_pass, stride, qin, ctx.counts + depth, qout, ctx.counts + depth + 1, shadow_count, r->octant_order);
+			if (r->russian_roulette) k_shade<false, true, true><<<sgrid, 128, 0, stream>>>(PTB_SHADE_ARGS);
+			else if (r->sort_by_material) k_shade<true, true><<<sgrid, 128, 0, stream>>>(PTB_SHADE_ARGS);
+			else k_shade<false, true><<<sgrid, 128, 0, stream>>>(PTB_SHADE_ARGS);
 			if (depth + 1 < r->cfg.max_tracer_depth)
 			{
 				k_shadow<<<sgrid, 128, 0, stream>>>(r->dscene, ctx.st, shadow_count);
 				r->stats.kernel_launches++;
 			}
 		}
-		else if (r->sort_by_material) k_shade<true, false><<<sgrid, 128, 0, stream>>>(r->dscene, ctx.st, dc, depth, px, first_pass, stride, qin, ctx.counts + depth, qout, ctx.counts + depth + 1, shadow_count, r->octant_order);
-		else k_shade<false, false><<<sgrid, 128, 0, stream>>>(r->dscene, ctx.st, dc, depth, px, first_pass, stride, qin, ctx.counts + depth, qout, ctx.counts + depth + 1, shadow_count, r->octant_order);
+		else if (r->russian_roulette) k_shade<false, false, true><<<sgrid, 128, 0, stream>>>(PTB_SHADE_ARGS);
+		else if (r->sort_by_material) k_shade<true, false><<<sgrid, 128, 0, stream>>>(PTB_SHADE_ARGS);
+		else k_shade<false, false><<<sgrid, 128, 0, stream>>>(PTB_SHADE_ARGS);
+#undef PTB_SHADE_ARGS
 		r->stats.kernel_launches += 2;
 	}
 	if (prev_accumulated) PTB_CUDA(cudaStreamWaitEvent(stream, prev_accumulated, 0));
@@ -1500,6 +1505,7 @@ int ptb_set_option(ptb_renderer* r, const char* key, const char* value)
 	if (k == "tile_order") { r->tile_order = atoi(value); return 0; }
 	if (k == "octant_order") { r->octant_order = atoi(value); return 0; }
 	if (k == "sort_by_material") { r->sort_by_material = atoi(value); return 0; }
+	if (k == "russian_roulette") { r->russian_roulette = atoi(value) != 0; return ptb_clear(r); }
 	if (k == "pass_clamp") { r->pass_clamp = (float)atof(value); return 0; }   // diagnostic: per-pass clamp of the accumulation (default: the reference's)
 	if (k == "estimator")
 	{
