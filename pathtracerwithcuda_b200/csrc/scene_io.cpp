@@ -575,70 +575,91 @@ static bool decode_png(const std::vector<uint8_t>& f, Texture& out)
 		else if (!memcmp(type, "IEND", 4)) done = true;
 		pos += 12 + (size_t)n;
 	}
-	if (!have_ihdr || w == 0 || h == 0 || w > 65536 || h > 65536 || interlace != 0) return false;   // Adam7 files need a side-car
+	if (!have_ihdr || w == 0 || h == 0 || w > 65536 || h > 65536 || interlace > 1) return false;
 	int channels = ctype == 0 ? 1 : ctype == 2 ? 3 : ctype == 3 ? 1 : ctype == 4 ? 2 : ctype == 6 ? 4 : 0;
 	if (channels == 0) return false;
 	if (!(depth == 8 || depth == 16 || (depth < 8 && (ctype == 0 || ctype == 3) && (depth == 1 || depth == 2 || depth == 4)))) return false;
 	if (ctype == 3 && (depth > 8 || palette.empty())) return false;
 	const size_t bits_pp = (size_t)channels * depth;
-	const size_t row_bytes = (w * bits_pp + 7) / 8;
 	const size_t bpp = bits_pp >= 8 ? bits_pp / 8 : 1;
+	// one pass for plain files, the seven Adam7 passes (x0, y0, dx, dy) for interlaced ones: each pass is a reduced image with
+	// its own filter bytes; empty passes carry no data
+	static const int adam7[7][4] = { { 0, 0, 8, 8 }, { 4, 0, 8, 8 }, { 0, 4, 4, 8 }, { 2, 0, 4, 4 }, { 0, 2, 2, 4 }, { 1, 0, 2, 2 }, { 0, 1, 1, 2 } };
+	static const int whole[1][4] = { { 0, 0, 1, 1 } };
+	const int (*passes)[4] = interlace ? adam7 : whole;
+	const int n_passes = interlace ? 7 : 1;
+	size_t expected = 0;
+	for (int k = 0; k < n_passes; k++)
+	{
+		const size_t pw = (w - passes[k][0] + passes[k][2] - 1) / passes[k][2], ph = (h - passes[k][1] + passes[k][3] - 1) / passes[k][3];
+		if ((uint32_t)passes[k][0] >= w || (uint32_t)passes[k][1] >= h) continue;
+		expected += ((pw * bits_pp + 7) / 8 + 1) * ph;
+	}
 	std::vector<uint8_t> raw;
-	if (!inflate_zlib(idat, raw, (row_bytes + 1) * h) || raw.size() < (row_bytes + 1) * h) return false;
-	// unfilter in place
-	std::vector<uint8_t> prev(row_bytes, 0);
+	if (!inflate_zlib(idat, raw, expected) || raw.size() < expected) return false;
 	out.width = (int)w; out.height = (int)h;
 	out.rgba.assign((size_t)w * h * 4, 255);
-	for (uint32_t y = 0; y < h; y++)
+	size_t offset = 0;
+	for (int k = 0; k < n_passes; k++)
 	{
-		uint8_t* row = &raw[(row_bytes + 1) * y + 1];
-		const int filter = raw[(row_bytes + 1) * y];
-		for (size_t i = 0; i < row_bytes; i++)
+		if ((uint32_t)passes[k][0] >= w || (uint32_t)passes[k][1] >= h) continue;
+		const uint32_t pw = (w - passes[k][0] + passes[k][2] - 1) / passes[k][2], ph = (h - passes[k][1] + passes[k][3] - 1) / passes[k][3];
+		const size_t row_bytes = (pw * bits_pp + 7) / 8;
+		std::vector<uint8_t> prev(row_bytes, 0);
+		for (uint32_t py = 0; py < ph; py++)
 		{
-			const int a = i >= bpp ? row[i - bpp] : 0, b = prev[i], c = i >= bpp ? prev[i - bpp] : 0;
-			int x = row[i];
-			switch (filter)
+			uint8_t* row = &raw[offset + (row_bytes + 1) * py + 1];
+			const int filter = raw[offset + (row_bytes + 1) * py];
+			for (size_t i = 0; i < row_bytes; i++)
 			{
-			case 0: break;
-			case 1: x += a; break;
-			case 2: x += b; break;
-			case 3: x += (a + b) >> 1; break;
-			case 4: { int p = a + b - c, pa = abs(p - a), pb = abs(p - b), pc = abs(p - c); x += (pa <= pb && pa <= pc) ? a : (pb <= pc ? b : c); break; }
-			default: return false;
-			}
-			row[i] = (uint8_t)x;
-		}
-		memcpy(prev.data(), row, row_bytes);
-		uint8_t* dst = &out.rgba[(size_t)y * w * 4];
-		for (uint32_t x = 0; x < w; x++)
-		{
-			uint8_t r, g, b;
-			if (depth < 8)
-			{
-				const size_t bit = (size_t)x * depth;
-				const int v = (row[bit >> 3] >> (8 - depth - (bit & 7))) & ((1 << depth) - 1);
-				if (ctype == 3)
+				const int a = i >= bpp ? row[i - bpp] : 0, b = prev[i], c = i >= bpp ? prev[i - bpp] : 0;
+				int x = row[i];
+				switch (filter)
 				{
-					if ((size_t)v * 3 + 2 >= palette.size()) { r = g = b = 0; }
-					else { r = palette[v * 3]; g = palette[v * 3 + 1]; b = palette[v * 3 + 2]; }
+				case 0: break;
+				case 1: x += a; break;
+				case 2: x += b; break;
+				case 3: x += (a + b) >> 1; break;
+				case 4: { int p = a + b - c, pa = abs(p - a), pb = abs(p - b), pc = abs(p - c); x += (pa <= pb && pa <= pc) ? a : (pb <= pc ? b : c); break; }
+				default: return false;
 				}
-				else r = g = b = (uint8_t)(v * 255 / ((1 << depth) - 1));
+				row[i] = (uint8_t)x;
 			}
-			else
+			memcpy(prev.data(), row, row_bytes);
+			const uint32_t y = passes[k][1] + py * passes[k][3];
+			for (uint32_t px_i = 0; px_i < pw; px_i++)
 			{
-				const size_t step = depth / 8;
-				const uint8_t* px = row + (size_t)x * channels * step;
-				if (ctype == 3)
+				const uint32_t x = passes[k][0] + px_i * passes[k][2];
+				uint8_t* dst = &out.rgba[((size_t)y * w + x) * 4];
+				uint8_t r, g, b;
+				if (depth < 8)
 				{
-					const int v = px[0];
-					if ((size_t)v * 3 + 2 >= palette.size()) { r = g = b = 0; }
-					else { r = palette[v * 3]; g = palette[v * 3 + 1]; b = palette[v * 3 + 2]; }
+					const size_t bit = (size_t)px_i * depth;
+					const int v = (row[bit >> 3] >> (8 - depth - (bit & 7))) & ((1 << depth) - 1);
+					if (ctype == 3)
+					{
+						if ((size_t)v * 3 + 2 >= palette.size()) { r = g = b = 0; }
+						else { r = palette[v * 3]; g = palette[v * 3 + 1]; b = palette[v * 3 + 2]; }
+					}
+					else r = g = b = (uint8_t)(v * 255 / ((1 << depth) - 1));
 				}
-				else if (channels <= 2) r = g = b = px[0];
-				else { r = px[0]; g = px[step]; b = px[2 * step]; }
+				else
+				{
+					const size_t step = depth / 8;
+					const uint8_t* px = row + (size_t)px_i * channels * step;
+					if (ctype == 3)
+					{
+						const int v = px[0];
+						if ((size_t)v * 3 + 2 >= palette.size()) { r = g = b = 0; }
+						else { r = palette[v * 3]; g = palette[v * 3 + 1]; b = palette[v * 3 + 2]; }
+					}
+					else if (channels <= 2) r = g = b = px[0];
+					else { r = px[0]; g = px[step]; b = px[2 * step]; }
+				}
+				dst[0] = r; dst[1] = g; dst[2] = b;
 			}
-			dst[x * 4] = r; dst[x * 4 + 1] = g; dst[x * 4 + 2] = b;
 		}
+		offset += (row_bytes + 1) * ph;
 	}
 	return true;
 }
