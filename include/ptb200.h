@@ -221,7 +221,7 @@ int ptb_scene_texture(ptb_renderer* r, int index, int* width, int* height, uint8
 int ptb_scene_cubemap_face(ptb_renderer* r, int face, uint8_t* out_rgba);
 /* image_loader::load_image (Others/image_loader.cpp:31-95: FreeImage_Load + ConvertTo24Bits, alpha forced to 255,
  * row 0 = top) on one file.  Decoded natively: BMP (24/32-bit), TGA, PNG (plain or Adam7-interlaced; grey / RGB / palette /
- * alpha dropped / 16-bit reduced to the high byte), baseline JPEG (1 or 3 components, 4:4:4 / 4:2:2 / 4:2:0);
+ * alpha dropped / 16-bit reduced to the high byte), baseline and progressive JPEG (1 or 3 components, 4:4:4 / 4:2:2 / 4:2:0);
  * a "<file>.rgba8" side-car (u32 width, u32 height, RGBA8) takes precedence when present and serves every other format.
  * out_rgba may be NULL to query the size. */
 int ptb_decode_image(const char* path, int* width, int* height, uint8_t* out_rgba);

@@ -1,4 +1,4 @@
-// Baseline JPEG decoder for the scene front-end.
+// JPEG decoder (baseline and progressive Huffman) for the scene front-end.
 //
 // The reference decodes images through FreeImage (Others/image_loader.cpp:31-95: FreeImage_Load + ConvertTo24Bits, a
 // binary-only library built on IJG libjpeg); its own assets are two cube maps of baseline 4:2:0 JPEGs
@@ -18,7 +18,11 @@
 //     libjpeg-turbo's default decode, i.e. PIL.
 // The IFAST + replication part of the reference mode is therefore pinned; its colour constant (22553 vs 22554 in one table)
 // follows the published libjpeg 9a source and is not pinned by a binary here.
-// Progressive / arithmetic-coded / 12-bit / CMYK files are rejected (side-car needed).
+// Every scan goes into per-component coefficient arrays (non-interleaved scans walk the component's own block grid), so
+// multi-scan baseline files and progressive files (Annex G: DC/AC first + refinement scans, EOB runs) share one path; the
+// quantisation table is latched at a component's first scan as libjpeg does.  Complete progressive files need none of
+// libjpeg's block smoothing (all coefficients exact); a file cut short is rejected rather than approximated.
+// Arithmetic-coded / 12-bit / CMYK files are rejected (side-car needed).
 #include "scene.h"
 
 #include <cstring>
@@ -60,9 +64,16 @@ struct Component
 {
 	int id = 0, h = 1, v = 1, tq = 0, td = 0, ta = 0;
 	int width = 0, height = 0;          // real sample dimensions (ceil(image * h / hmax))
-	int stride = 0, rows = 0;           // allocated, padded to whole MCUs
+	int bw = 0, bh = 0;                 // blocks covering the real samples: the grid of a non-interleaved scan
+	int pbw = 0, pbh = 0;               // blocks padded to whole MCUs: the grid of interleaved scans and of `coefs`
+	int stride = 0, rows = 0;           // plane, padded to whole MCUs
 	std::vector<uint8_t> plane;
+	std::vector<int16_t> coefs;         // pbw * pbh blocks of 64, natural order
 	int dc_pred = 0;
+	bool seen = false;                  // appeared in a scan: quantisation table latched (as libjpeg does at a component's first scan)
+	uint16_t quant[64] = { 0 };
+	int ifast_mult[64] = { 0 };
+	int8_t known_al[64];                // progressive: successive-approximation bit still missing per coefficient (-1 = never coded)
 };
 
 struct BitSource
@@ -327,6 +338,175 @@ void upsample_row(const Component& c, int hmax, int vmax, int y, int out_width, 
 	for (int x = 0; x < out_width; x++) { int sx = x / hs; row[x] = in[sx < n ? sx : n - 1]; }
 }
 
+// One scan's entropy-coded segment (ITU T.81 Annex F sequential, Annex G progressive).  Blocks go to the coefficient
+// arrays; a non-interleaved scan walks the component's own block grid, an interleaved one the MCU grid.
+struct Scan
+{
+	int ns = 0;
+	Component* comp[3] = { nullptr, nullptr, nullptr };
+	int ss = 0, se = 63, ah = 0, al = 0;
+	bool progressive = false;
+};
+
+bool decode_scan(const std::vector<uint8_t>& f, size_t& pos, const Scan& sc, const HuffTable* dc_tab, const HuffTable* ac_tab,
+	int mcus_x, int mcus_y, int restart_interval)
+{
+	BitSource bs(f.data(), f.size(), pos);
+	int eobrun = 0;
+	const int total_x = sc.ns == 1 ? sc.comp[0]->bw : mcus_x, total_y = sc.ns == 1 ? sc.comp[0]->bh : mcus_y;
+	int restarts_left = restart_interval;
+	const int p1 = 1 << sc.al, m1 = -(1 << sc.al);
+	for (int i = 0; i < sc.ns; i++) sc.comp[i]->dc_pred = 0;
+
+	auto decode_block = [&](Component& c, int16_t* block) -> bool
+	{
+		if (!sc.progressive)
+		{
+			int s = huff_decode(bs, dc_tab[c.td]);
+			if (s < 0 || s > 15) return false;
+			c.dc_pred += s ? huff_extend(bs.get(s), s) : 0;
+			block[0] = (int16_t)c.dc_pred;
+			for (int k = 1; k < 64;)
+			{
+				const int rs = huff_decode(bs, ac_tab[c.ta]);
+				if (rs < 0) return false;
+				const int rr = rs >> 4, ss = rs & 15;
+				if (ss == 0)
+				{
+					if (rr != 15) break;
+					k += 16;
+					continue;
+				}
+				k += rr;
+				if (k > 63) return false;
+				block[kZigzag[k]] = (int16_t)huff_extend(bs.get(ss), ss);
+				k++;
+			}
+			return true;
+		}
+		if (sc.ss == 0)
+		{
+			if (sc.ah == 0)
+			{
+				const int s = huff_decode(bs, dc_tab[c.td]);
+				if (s < 0 || s > 15) return false;
+				c.dc_pred += s ? huff_extend(bs.get(s), s) : 0;
+				block[0] = (int16_t)(c.dc_pred * (1 << sc.al));
+			}
+			else if (bs.get(1)) block[0] |= (int16_t)p1;
+			return true;
+		}
+		if (sc.ah == 0)
+		{
+			if (eobrun > 0) { eobrun--; return true; }
+			for (int k = sc.ss; k <= sc.se; k++)
+			{
+				const int rs = huff_decode(bs, ac_tab[c.ta]);
+				if (rs < 0) return false;
+				const int r = rs >> 4, s = rs & 15;
+				if (s)
+				{
+					k += r;
+					if (k > 63) return false;
+					block[kZigzag[k]] = (int16_t)(huff_extend(bs.get(s), s) * (1 << sc.al));
+				}
+				else if (r == 15) k += 15;
+				else
+				{
+					eobrun = 1 << r;
+					if (r) eobrun += bs.get(r);
+					eobrun--;
+					break;
+				}
+			}
+			return true;
+		}
+		// AC refinement (G.1.2.3): correction bits for coefficients already non-zero, new +-1 coefficients after runs of zeros
+		int k = sc.ss;
+		if (eobrun == 0)
+		{
+			for (; k <= sc.se; k++)
+			{
+				const int rs = huff_decode(bs, ac_tab[c.ta]);
+				if (rs < 0) return false;
+				int r = rs >> 4, s = rs & 15;
+				if (s)
+				{
+					if (s != 1) return false;
+					s = bs.get(1) ? p1 : m1;
+				}
+				else if (r != 15)
+				{
+					eobrun = 1 << r;
+					if (r) eobrun += bs.get(r);
+					break;
+				}
+				do
+				{
+					int16_t& coef = block[kZigzag[k]];
+					if (coef != 0)
+					{
+						if (bs.get(1) && (coef & p1) == 0) coef = (int16_t)(coef + (coef >= 0 ? p1 : m1));
+					}
+					else if (--r < 0) break;
+					k++;
+				} while (k <= sc.se);
+				if (s)
+				{
+					if (k > 63) return false;
+					block[kZigzag[k]] = (int16_t)s;
+				}
+			}
+		}
+		if (eobrun > 0)
+		{
+			for (; k <= sc.se; k++)
+			{
+				int16_t& coef = block[kZigzag[k]];
+				if (coef != 0 && bs.get(1) && (coef & p1) == 0) coef = (int16_t)(coef + (coef >= 0 ? p1 : m1));
+			}
+			eobrun--;
+		}
+		return true;
+	};
+
+	for (int my = 0; my < total_y; my++)
+		for (int mx = 0; mx < total_x; mx++)
+		{
+			if (restart_interval && restarts_left == 0)
+			{
+				// byte-align, expect RSTn
+				bs.reset();
+				size_t p2 = bs.pos;
+				while (p2 + 1 < f.size() && !(f[p2] == 0xff && f[p2 + 1] >= 0xd0 && f[p2 + 1] <= 0xd7)) p2++;
+				if (p2 + 1 >= f.size()) return false;
+				bs.pos = p2 + 2;
+				for (int i = 0; i < sc.ns; i++) sc.comp[i]->dc_pred = 0;
+				eobrun = 0;
+				restarts_left = restart_interval;
+			}
+			if (sc.ns == 1)
+			{
+				Component& c = *sc.comp[0];
+				if (!decode_block(c, c.coefs.data() + ((size_t)my * c.pbw + mx) * 64)) return false;
+			}
+			else
+				for (int i = 0; i < sc.ns; i++)
+				{
+					Component& c = *sc.comp[i];
+					for (int by = 0; by < c.v; by++)
+						for (int bx = 0; bx < c.h; bx++)
+							if (!decode_block(c, c.coefs.data() + ((size_t)(my * c.v + by) * c.pbw + (mx * c.h + bx)) * 64)) return false;
+				}
+			if (restart_interval) restarts_left--;
+		}
+	// the next marker: entropy-coded data holds only stuffed 0xff00 and RSTn
+	size_t p2 = bs.pos;
+	while (p2 + 1 < f.size() && !(f[p2] == 0xff && f[p2 + 1] != 0x00 && f[p2 + 1] != 0xff && !(f[p2 + 1] >= 0xd0 && f[p2 + 1] <= 0xd7))) p2++;
+	pos = p2;
+	return true;
+}
+
 int g_jpeg_mode = kJpegReference;
 
 } // namespace
@@ -338,14 +518,13 @@ bool decode_jpeg(const std::vector<uint8_t>& f, Texture& out)
 {
 	const int mode = g_jpeg_mode;
 	const bool fast = mode != kJpegAccurate;
-	int ifast_mult[4][64];
 	if (f.size() < 4 || f[0] != 0xff || f[1] != 0xd8) return false;
 	uint16_t quant[4][64];
 	bool quant_present[4] = { false, false, false, false };
 	HuffTable dc_tab[4], ac_tab[4];
 	Component comp[3];
-	int n_comp = 0, width = 0, height = 0, hmax = 1, vmax = 1, restart_interval = 0;
-	bool have_sof = false, adobe = false;
+	int n_comp = 0, width = 0, height = 0, hmax = 1, vmax = 1, restart_interval = 0, mcus_x = 0, mcus_y = 0;
+	bool have_sof = false, progressive = false, adobe = false, saw_scan = false;
 	int adobe_transform = -1;
 	size_t pos = 2;
 	while (pos + 4 <= f.size())
@@ -372,12 +551,12 @@ bool decode_jpeg(const std::vector<uint8_t>& f, Texture& out)
 				for (int i = 0; i < 64; i++) { quant[tq][kZigzag[i]] = pq ? be16(&seg[o + 2 * i]) : seg[o + i]; }
 				o += pq ? 128 : 64;
 				quant_present[tq] = true;
-				ifast_multipliers(quant[tq], ifast_mult[tq]);
 			}
 		}
-		else if (marker == 0xc0 || marker == 0xc1)
+		else if (marker == 0xc0 || marker == 0xc1 || marker == 0xc2)
 		{
-			if (seg_len < 6 || seg[0] != 8) return false;
+			if (have_sof || seg_len < 6 || seg[0] != 8) return false;
+			progressive = marker == 0xc2;
 			height = be16(&seg[1]); width = be16(&seg[3]); n_comp = seg[5];
 			if (width <= 0 || height <= 0 || (n_comp != 1 && n_comp != 3) || seg_len < (size_t)(6 + 3 * n_comp)) return false;
 			for (int i = 0; i < n_comp; i++)
@@ -389,9 +568,23 @@ bool decode_jpeg(const std::vector<uint8_t>& f, Texture& out)
 				hmax = comp[i].h > hmax ? comp[i].h : hmax;
 				vmax = comp[i].v > vmax ? comp[i].v : vmax;
 			}
+			if (n_comp == 1) { comp[0].h = comp[0].v = 1; hmax = vmax = 1; }       // a single component is never interleaved
+			const int mcu_w = 8 * hmax, mcu_h = 8 * vmax;
+			mcus_x = (width + mcu_w - 1) / mcu_w; mcus_y = (height + mcu_h - 1) / mcu_h;
+			for (int i = 0; i < n_comp; i++)
+			{
+				Component& c = comp[i];
+				c.width = (width * c.h + hmax - 1) / hmax;
+				c.height = (height * c.v + vmax - 1) / vmax;
+				c.bw = (c.width + 7) / 8; c.bh = (c.height + 7) / 8;
+				c.pbw = mcus_x * c.h; c.pbh = mcus_y * c.v;
+				c.stride = c.pbw * 8; c.rows = c.pbh * 8;
+				c.coefs.assign((size_t)c.pbw * c.pbh * 64, 0);
+				memset(c.known_al, -1, sizeof(c.known_al));
+			}
 			have_sof = true;
 		}
-		else if (marker >= 0xc2 && marker <= 0xcf && marker != 0xc4 && marker != 0xc8 && marker != 0xcc) return false;   // progressive, lossless, arithmetic
+		else if (marker >= 0xc3 && marker <= 0xcf && marker != 0xc4 && marker != 0xc8 && marker != 0xcc) return false;   // lossless, hierarchical, arithmetic
 		else if (marker == 0xc4)
 		{
 			size_t o = 0;
@@ -416,124 +609,113 @@ bool decode_jpeg(const std::vector<uint8_t>& f, Texture& out)
 		else if (marker == 0xda)
 		{
 			if (!have_sof || seg_len < 1) return false;
-			const int ns = seg[0];
-			if (ns != n_comp || seg_len < (size_t)(1 + 2 * ns + 3)) return false;    // baseline files here are single-scan, interleaved
-			for (int i = 0; i < ns; i++)
+			Scan sc;
+			sc.ns = seg[0];
+			sc.progressive = progressive;
+			if (sc.ns < 1 || sc.ns > n_comp || seg_len < (size_t)(1 + 2 * sc.ns + 3)) return false;
+			for (int i = 0; i < sc.ns; i++)
 			{
 				const int cid = seg[1 + 2 * i];
 				int k = -1;
 				for (int j = 0; j < n_comp; j++) if (comp[j].id == cid) k = j;
 				if (k < 0) return false;
+				for (int j = 0; j < i; j++) if (sc.comp[j] == &comp[k]) return false;
 				comp[k].td = seg[2 + 2 * i] >> 4; comp[k].ta = seg[2 + 2 * i] & 15;
-				if (comp[k].td > 3 || comp[k].ta > 3 || !dc_tab[comp[k].td].present || !ac_tab[comp[k].ta].present || !quant_present[comp[k].tq]) return false;
+				if (comp[k].td > 3 || comp[k].ta > 3) return false;
+				sc.comp[i] = &comp[k];
+			}
+			sc.ss = seg[1 + 2 * sc.ns]; sc.se = seg[2 + 2 * sc.ns];
+			sc.ah = seg[3 + 2 * sc.ns] >> 4; sc.al = seg[3 + 2 * sc.ns] & 15;
+			if (!progressive) { if (sc.ss != 0 || sc.se != 63 || sc.ah != 0 || sc.al != 0) return false; }
+			else
+			{
+				if (sc.ss > sc.se || sc.se > 63 || sc.al > 13 || (sc.ah != 0 && sc.ah != sc.al + 1)) return false;
+				if (sc.ss == 0 ? sc.se != 0 : sc.ns != 1) return false;
+			}
+			for (int i = 0; i < sc.ns; i++)
+			{
+				Component& c = *sc.comp[i];
+				const bool need_dc = sc.ss == 0 && sc.ah == 0, need_ac = sc.se > 0;
+				if ((need_dc && !dc_tab[c.td].present) || (need_ac && !ac_tab[c.ta].present)) return false;
+				if (!c.seen)
+				{
+					if (!quant_present[c.tq]) return false;
+					memcpy(c.quant, quant[c.tq], sizeof(c.quant));
+					ifast_multipliers(c.quant, c.ifast_mult);
+					c.seen = true;
+				}
+				// successive-approximation bookkeeping: a band must be introduced before it is refined, one bit at a time
+				for (int k = sc.ss; k <= sc.se; k++)
+				{
+					if (progressive && (sc.ah == 0 ? c.known_al[k] >= 0 : c.known_al[k] != sc.ah)) return false;
+					c.known_al[k] = (int8_t)sc.al;
+				}
+				if (progressive && sc.ss > 0 && c.known_al[0] < 0) return false;
 			}
 			if (adobe && n_comp == 3 && adobe_transform == 0) return false;     // RGB-coded JPEG: not produced by the reference's assets
 			pos += len;
-			// ---- entropy-coded data
-			if (n_comp == 1) { comp[0].h = comp[0].v = 1; hmax = vmax = 1; }       // a single component is never interleaved
-			const int mcu_w = 8 * hmax, mcu_h = 8 * vmax;
-			const int mcus_x = (width + mcu_w - 1) / mcu_w, mcus_y = (height + mcu_h - 1) / mcu_h;
-			for (int i = 0; i < n_comp; i++)
-			{
-				Component& c = comp[i];
-				c.width = (width * c.h + hmax - 1) / hmax;
-				c.height = (height * c.v + vmax - 1) / vmax;
-				c.stride = mcus_x * c.h * 8;
-				c.rows = mcus_y * c.v * 8;
-				c.plane.assign((size_t)c.stride * c.rows, 0);
-				c.dc_pred = 0;
-			}
-			BitSource bs(f.data(), f.size(), pos);
-			int16_t block[64];
-			int restarts_left = restart_interval;
-			for (int my = 0; my < mcus_y; my++)
-				for (int mx = 0; mx < mcus_x; mx++)
-				{
-					if (restart_interval && restarts_left == 0)
-					{
-						// byte-align, expect RSTn
-						bs.reset();
-						size_t p2 = bs.pos;
-						while (p2 + 1 < f.size() && !(f[p2] == 0xff && f[p2 + 1] >= 0xd0 && f[p2 + 1] <= 0xd7)) p2++;
-						if (p2 + 1 >= f.size()) return false;
-						bs.pos = p2 + 2;
-						for (int i = 0; i < n_comp; i++) comp[i].dc_pred = 0;
-						restarts_left = restart_interval;
-					}
-					for (int i = 0; i < n_comp; i++)
-					{
-						Component& c = comp[i];
-						for (int by = 0; by < c.v; by++)
-							for (int bx = 0; bx < c.h; bx++)
-							{
-								memset(block, 0, sizeof(block));
-								int s = huff_decode(bs, dc_tab[c.td]);
-								if (s < 0 || s > 15) return false;
-								int diff = s ? huff_extend(bs.get(s), s) : 0;
-								c.dc_pred += diff;
-								block[0] = (int16_t)c.dc_pred;
-								for (int k = 1; k < 64;)
-								{
-									int rs = huff_decode(bs, ac_tab[c.ta]);
-									if (rs < 0) return false;
-									int rr = rs >> 4, ss = rs & 15;
-									if (ss == 0)
-									{
-										if (rr != 15) break;
-										k += 16;
-										continue;
-									}
-									k += rr;
-									if (k > 63) return false;
-									block[kZigzag[k]] = (int16_t)huff_extend(bs.get(ss), ss);
-									k++;
-								}
-								uint8_t* dst = c.plane.data() + (size_t)(my * c.v + by) * 8 * c.stride + (size_t)(mx * c.h + bx) * 8;
-								if (fast) idct_ifast(block, ifast_mult[c.tq], dst, c.stride);
-								else idct_islow(block, quant[c.tq], dst, c.stride);
-							}
-					}
-					if (restart_interval) restarts_left--;
-				}
-			// ---- upsample + colour conversion
-			out.width = width; out.height = height;
-			out.rgba.assign((size_t)width * height * 4, 255);
-			int cr_r[256], cb_b[256], cr_g[256], cb_g[256];
-			const int fix_cb_g = mode == kJpegReference ? 22553 : 22554;   // FIX(0.344136286) in libjpeg 9a, FIX(0.34414) in 6b / turbo
-			for (int i = 0; i < 256; i++)
-			{
-				const int x = i - 128;
-				cr_r[i] = (91881 * x + 32768) >> 16;        // FIX(1.402)
-				cb_b[i] = (116130 * x + 32768) >> 16;       // FIX(1.772)
-				cr_g[i] = -46802 * x;                       // FIX(0.71414) == FIX(0.714136286)
-				cb_g[i] = -fix_cb_g * x + 32768;
-			}
-			std::vector<uint8_t> r0, r1, r2;
-			for (int y = 0; y < height; y++)
-			{
-				uint8_t* dst = &out.rgba[(size_t)y * width * 4];
-				upsample_row(comp[0], hmax, vmax, y, width, r0, !fast);
-				if (n_comp == 1)
-				{
-					for (int x = 0; x < width; x++) { dst[4 * x] = dst[4 * x + 1] = dst[4 * x + 2] = r0[x]; }
-					continue;
-				}
-				upsample_row(comp[1], hmax, vmax, y, width, r1, !fast);
-				upsample_row(comp[2], hmax, vmax, y, width, r2, !fast);
-				for (int x = 0; x < width; x++)
-				{
-					const int yy = r0[x], cb = r1[x], cr = r2[x];
-					int rr = yy + cr_r[cr], gg = yy + ((cb_g[cb] + cr_g[cr]) >> 16), bb = yy + cb_b[cb];
-					dst[4 * x] = (uint8_t)(rr < 0 ? 0 : (rr > 255 ? 255 : rr));
-					dst[4 * x + 1] = (uint8_t)(gg < 0 ? 0 : (gg > 255 ? 255 : gg));
-					dst[4 * x + 2] = (uint8_t)(bb < 0 ? 0 : (bb > 255 ? 255 : bb));
-				}
-			}
-			return true;
+			if (!decode_scan(f, pos, sc, dc_tab, ac_tab, mcus_x, mcus_y, restart_interval)) return false;
+			saw_scan = true;
+			continue;
 		}
 		pos += len;
 	}
-	return false;
+	if (!have_sof || !saw_scan) return false;
+	// every coefficient of every component fully coded (a progressive file cut short would need libjpeg's block smoothing)
+	for (int i = 0; i < n_comp; i++)
+		for (int k = 0; k < 64; k++)
+			if (!comp[i].seen || comp[i].known_al[k] != 0) return false;
+
+	// ---- inverse DCT of every block
+	for (int i = 0; i < n_comp; i++)
+	{
+		Component& c = comp[i];
+		c.plane.assign((size_t)c.stride * c.rows, 0);
+		for (int by = 0; by < c.pbh; by++)
+			for (int bx = 0; bx < c.pbw; bx++)
+			{
+				const int16_t* block = c.coefs.data() + ((size_t)by * c.pbw + bx) * 64;
+				uint8_t* dst = c.plane.data() + (size_t)by * 8 * c.stride + (size_t)bx * 8;
+				if (fast) idct_ifast(block, c.ifast_mult, dst, c.stride);
+				else idct_islow(block, c.quant, dst, c.stride);
+			}
+		c.coefs.clear(); c.coefs.shrink_to_fit();
+	}
+	// ---- upsample + colour conversion
+	out.width = width; out.height = height;
+	out.rgba.assign((size_t)width * height * 4, 255);
+	int cr_r[256], cb_b[256], cr_g[256], cb_g[256];
+	const int fix_cb_g = mode == kJpegReference ? 22553 : 22554;   // FIX(0.344136286) in libjpeg 9a, FIX(0.34414) in 6b / turbo
+	for (int i = 0; i < 256; i++)
+	{
+		const int x = i - 128;
+		cr_r[i] = (91881 * x + 32768) >> 16;        // FIX(1.402)
+		cb_b[i] = (116130 * x + 32768) >> 16;       // FIX(1.772)
+		cr_g[i] = -46802 * x;                       // FIX(0.71414) == FIX(0.714136286)
+		cb_g[i] = -fix_cb_g * x + 32768;
+	}
+	std::vector<uint8_t> r0, r1, r2;
+	for (int y = 0; y < height; y++)
+	{
+		uint8_t* dst = &out.rgba[(size_t)y * width * 4];
+		upsample_row(comp[0], hmax, vmax, y, width, r0, !fast);
+		if (n_comp == 1)
+		{
+			for (int x = 0; x < width; x++) { dst[4 * x] = dst[4 * x + 1] = dst[4 * x + 2] = r0[x]; }
+			continue;
+		}
+		upsample_row(comp[1], hmax, vmax, y, width, r1, !fast);
+		upsample_row(comp[2], hmax, vmax, y, width, r2, !fast);
+		for (int x = 0; x < width; x++)
+		{
+			const int yy = r0[x], cb = r1[x], cr = r2[x];
+			int rr = yy + cr_r[cr], gg = yy + ((cb_g[cb] + cr_g[cr]) >> 16), bb = yy + cb_b[cb];
+			dst[4 * x] = (uint8_t)(rr < 0 ? 0 : (rr > 255 ? 255 : rr));
+			dst[4 * x + 1] = (uint8_t)(gg < 0 ? 0 : (gg > 255 ? 255 : gg));
+			dst[4 * x + 2] = (uint8_t)(bb < 0 ? 0 : (bb > 255 ? 255 : bb));
+		}
+	}
+	return true;
 }
 
 } // namespace ptb

@@ -97,7 +97,7 @@ void set_error(const std::string& msg);
 bool load_config(const std::string& path, Config& out);
 bool load_scene(const std::string& scene_json_path, const std::string& asset_root, HostScene& out);
 bool load_image_rgba8(const std::string& path, Texture& out);
-// baseline JPEG (csrc/jpeg_decode.cpp); false for progressive / arithmetic / CMYK / corrupt files
+// baseline / progressive JPEG (csrc/jpeg_decode.cpp); false for arithmetic / CMYK / corrupt / incomplete files
 bool decode_jpeg(const std::vector<uint8_t>& file, Texture& out);
 // process-wide JPEG decode mode: reference = what FreeImage does for the reference's loads (IFAST IDCT, replicated chroma,
 // libjpeg 9a colour constants), fast = libjpeg-turbo's fast decode, accurate = libjpeg-turbo's default decode (PIL)

@@ -687,7 +687,7 @@ bool load_image_rgba8(const std::string& path_in, Texture& out)
 	std::string lower = path;
 	std::transform(lower.begin(), lower.end(), lower.begin(), [](unsigned char ch) { return (char)tolower(ch); });
 	if (lower.size() > 4 && lower.substr(lower.size() - 4) == ".tga" && decode_tga(bytes, out)) return true;
-	set_error("[Error]Unsupported image file format (BMP, TGA, PNG and baseline JPEG are decoded natively; provide a .rgba8 side-car): " + path);
+	set_error("[Error]Unsupported image file format (BMP, TGA, PNG and Huffman-coded JPEG are decoded natively; provide a .rgba8 side-car): " + path);
 	return false;
 }
 

@@ -235,13 +235,43 @@ def test_jpeg_decode_matches_pil(tmp_path, shape, jpeg_mode):
     assert np.array_equal(ptb.decode_image(p)[..., :3], np.asarray(Image.open(p).convert("RGB")))
 
 
-def test_jpeg_progressive_needs_a_sidecar_and_corrupt_files_fail(tmp_path):
+@pytest.mark.parametrize("shape", [(203, 157), (16, 16), (1, 1), (17, 33), (64, 250)])
+def test_jpeg_progressive_matches_libjpeg(tmp_path, shape, jpeg_mode):
+    """Progressive files (spectral selection + successive approximation, ITU T.81 Annex G): PIL writes libjpeg's standard
+    10-scan script; decoded here they must equal PIL (accurate mode) and libjpeg-turbo's fast decode (fast mode)."""
+    Image = pytest.importorskip("PIL.Image")
+    decode = _libjpeg_shim()
+    img = _test_image(shape[0], shape[1], 7 * shape[0] + shape[1])
+    for sub in (0, 1, 2):
+        for kw in (dict(quality=30), dict(quality=85, optimize=True), dict(quality=100), dict(quality=60, restart_marker_blocks=2)):
+            p = str(tmp_path / ("p_%d_%d.jpg" % (sub, kw["quality"])))
+            try:
+                Image.fromarray(img).save(p, subsampling=sub, progressive=True, **kw)
+            except TypeError:
+                continue
+            assert Image.open(p).info.get("progressive")
+            jpeg_mode("accurate")
+            assert np.array_equal(ptb.decode_image(p)[..., :3], np.asarray(Image.open(p).convert("RGB"))), (shape, sub, kw)
+            if decode is not None:
+                jpeg_mode("fast")
+                assert np.array_equal(ptb.decode_image(p)[..., :3], decode(open(p, "rb").read(), 1, 0)), (shape, sub, kw)
+    p = str(tmp_path / "pgrey.jpg")
+    Image.fromarray(img[..., 0]).save(p, quality=70, progressive=True)
+    jpeg_mode("accurate")
+    assert np.array_equal(ptb.decode_image(p)[..., :3], np.asarray(Image.open(p).convert("RGB")))
+
+
+def test_jpeg_sidecar_and_corrupt_files(tmp_path, jpeg_mode):
     Image = pytest.importorskip("PIL.Image")
     img = _test_image(40, 56, 3)
     p = str(tmp_path / "prog.jpg")
     Image.fromarray(img).save(p, quality=80, progressive=True)
+    data = open(p, "rb").read()
+    # a progressive file cut before its last scans is incomplete (libjpeg would smooth it): rejected, not half-decoded
+    last_sos = data.rfind(b"\xff\xda")
+    open(p, "wb").write(data[:last_sos] + b"\xff\xd9")
     with pytest.raises(ptb.PtbError):
-        ptb.decode_image(p)                     # progressive scans are not decoded natively
+        ptb.decode_image(p)
     with open(p + ".rgba8", "wb") as f:         # ... the documented side-car is picked up instead
         rgba = np.concatenate([img, np.full(img.shape[:2] + (1,), 255, np.uint8)], 2)
         f.write(struct.pack("<II", img.shape[1], img.shape[0]) + rgba.tobytes())
