@@ -38,9 +38,9 @@ PASSES_PER_STEP = 64
 PASSES_IN_FLIGHT = 16     # passes traced as one wavefront batch (tools/sweep_batching.py: 16 x 4 streams +1.4 % over 8 x 4 at 11.7 GB of path state)
 STREAMS_IN_FLIGHT = 4     # batches overlapped on separate CUDA streams
 METRIC = "path samples/sec (Mspp*px/s), 1080p"
-# dram__bytes_read.sum + dram__bytes_write.sum per k_extend_persistent launch (ncu --set full, workload c2, 8 passes in flight),
-# averaged over the 8 depth launches of one batch — profiles/r01b_extend_shade_ncu_summary.md
-NCU_DRAM_BYTES_PER_EXTEND_LAUNCH = 197.2e6
+# dram__bytes_read.sum + dram__bytes_write.sum per closest-hit launch (ncu --set full, workload c2, 16 passes in flight as benchmarked),
+# averaged over the 8 depth launches of one batch — profiles/r01i_extend_ncu_summary.md (the 8-pass capture of r01b gave 197.2 MB)
+NCU_DRAM_BYTES_PER_EXTEND_LAUNCH = 378.9e6
 UNIT = "Msamples/s"
 
 
@@ -347,7 +347,7 @@ def run_ptb200(args, w, root, rank, local_rank, world):
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 64, "d2h_bytes_per_step": int(u8.nbytes)},
                 "roofline": {"bound": "hbm", "kernel": "k_extend", "achieved": achieved, "peak": peaks.get("hbm_gbs"), "unit": "GB/s",
                              "frac": (achieved / peaks["hbm_gbs"]) if achieved else None, "traffic": NCU_DRAM_BYTES_PER_EXTEND_LAUNCH,
-                             "traffic_source": "profiles/r01b_extend_shade_ncu_summary.md: dram__bytes_read.sum + dram__bytes_write.sum averaged over the 8 k_extend_persistent launches of one 8-pass batch of c2 (ncu --set full)",
+                             "traffic_source": "profiles/r01i_extend_ncu_summary.md: dram__bytes_read.sum + dram__bytes_write.sum averaged over the 8 closest-hit launches (k_extend_persistent d0-d1, k_extend_persistent8 d2-d7) of one 16-pass batch of c2 (ncu --set full)",
                              "peak_source": peak_kind,
                              "bytes_per_segment": bytes_per_seg, "nodes_per_segment": nodes_per_seg, "wide_nodes_per_segment": wide_per_seg, "tris_per_segment": tris_per_seg,
                              "segments_per_launch": seg_per_launch, "avg_launch_ms": avg_launch_ms,
