@@ -354,6 +354,13 @@ def run_ptb200(args, w, root, rank, local_rank, world):
                              "how": "per-launch CUDA events on the launching stream with ONE stream in flight, immediately before the timed region "
                                     "(the timed region overlaps %d streams, so launches there are not exclusive); achieved counts cache-served "
                                     "bytes: nodes/triangles are L1/L2-resident, see DESIGN.md" % STREAMS_IN_FLIGHT,
+                             # what actually crosses the HBM interface (ncu dram bytes per launch / the live launch duration), and what
+                             # the ncu capture names as the limiter instead: issue slots busy and the stall per issued instruction
+                             "dram_achieved": NCU_DRAM_BYTES_PER_EXTEND_LAUNCH / (avg_launch_ms / 1e3) / 1e9 if avg_launch_ms > 0 else None,
+                             "dram_frac": (NCU_DRAM_BYTES_PER_EXTEND_LAUNCH / (avg_launch_ms / 1e3) / 1e9 / peaks["hbm_gbs"]) if avg_launch_ms > 0 and peaks.get("hbm_gbs") else None,
+                             "ncu_limiters": {"source": "profiles/r01i_extend_ncu_summary.md (d0 / d1, binary-tree kernel)", "issue_active_pct": [68.2, 61.9],
+                                              "active_lanes_per_instruction": [22.1, 18.9], "stall_long_scoreboard_per_issue": [4.2, 5.85],
+                                              "l1_hit_pct": [71.7, 64.8], "lsu_wavefronts_pct_of_peak": [74.7, 65.5], "alu_pipe_pct": [61.4, 53.2]},
                              "extend_share_of_serial_step": serial_extend_ms / serial_step_ms if serial_step_ms else None,
                              "Mrays_s_extend_serial": serial_segments / (serial_extend_ms / 1e3) / 1e6 if serial_extend_ms else None,
                              "Mrays_s_whole_step": seg_total / world / (ms_max / 1e3) / 1e6},
