@@ -159,7 +159,8 @@ def run_reference(args, w, root, rank, world):
         median_ms = float(np.median(step_ms))
         value = px_step / (median_ms / 1e3) / 1e6
         mean_value = px_step * args.steps / secs / 1e6
-        line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+        # n_gpus echoes the launch (the driver pairs the arms by N); the reference itself is single-GPU code: gpus_used says so
+        line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": max(1, args.gpus), "gpus_used": 1, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": median_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
                 "data": "synthetic", "config": dict(config, note="unmodified reference CUDA kernels rebuilt headless for sm_100a, managed memory prefetched"),
                 "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "reference",
@@ -172,7 +173,7 @@ def run_reference(args, w, root, rank, world):
         return line
     cb = cpu_baseline(w, root, budget_s=20.0)
     cb["kind"] = "port"
-    return {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+    return {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": max(1, args.gpus), "gpus_used": 0, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": None, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": dict(config, note="oracle/_ref not on this box: C oracle port on the host cores"), "cpu_baseline": cb,
             "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
