@@ -558,7 +558,7 @@ bool decode_jpeg(const std::vector<uint8_t>& f, Texture& out)
 			if (have_sof || seg_len < 6 || seg[0] != 8) return false;
 			progressive = marker == 0xc2;
 			height = be16(&seg[1]); width = be16(&seg[3]); n_comp = seg[5];
-			if (width <= 0 || height <= 0 || (n_comp != 1 && n_comp != 3) || seg_len < (size_t)(6 + 3 * n_comp)) return false;
+			if (width <= 0 || height <= 0 || (uint64_t)width * height > kMaxImagePixels || (n_comp != 1 && n_comp != 3) || seg_len < (size_t)(6 + 3 * n_comp)) return false;
 			for (int i = 0; i < n_comp; i++)
 			{
 				comp[i].id = seg[6 + 3 * i];

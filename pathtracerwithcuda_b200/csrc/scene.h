@@ -97,6 +97,8 @@ void set_error(const std::string& msg);
 bool load_config(const std::string& path, Config& out);
 bool load_scene(const std::string& scene_json_path, const std::string& asset_root, HostScene& out);
 bool load_image_rgba8(const std::string& path, Texture& out);
+// decoders refuse headers announcing more than this many pixels (1 GiB of RGBA8) before allocating anything
+const uint64_t kMaxImagePixels = 1ull << 28;
 // baseline / progressive JPEG (csrc/jpeg_decode.cpp); false for arithmetic / CMYK / corrupt / incomplete files
 bool decode_jpeg(const std::vector<uint8_t>& file, Texture& out);
 // process-wide JPEG decode mode: reference = what FreeImage does for the reference's loads (IFAST IDCT, replicated chroma,

@@ -18,7 +18,10 @@
 #include "json_min.h"
 
 #include <algorithm>
+#include <climits>
 #include <cmath>
+#include <cstdint>
+#include <new>
 #include <cstdio>
 #include <cstring>
 #include <fstream>
@@ -319,7 +322,7 @@ static bool decode_bmp(const std::vector<uint8_t>& f, Texture& out)
 	int32_t h = (int32_t)le32(&f[22]);
 	uint32_t bits = le16(&f[28]);
 	uint32_t compression = le32(&f[30]);
-	if (w <= 0 || h == 0 || (bits != 24 && bits != 32) || (compression != 0 && compression != 3)) return false;
+	if (w <= 0 || h == 0 || h == INT32_MIN || (bits != 24 && bits != 32) || (compression != 0 && compression != 3)) return false;
 	bool bottom_up = h > 0;
 	uint32_t rows = (uint32_t)(h > 0 ? h : -h);
 	uint32_t bpp = bits / 8;
@@ -349,7 +352,7 @@ static bool decode_tga(const std::vector<uint8_t>& f, Texture& out)
 	if (f.size() < 18) return false;
 	uint32_t id_len = f[0], cmap_type = f[1], type = f[2];
 	uint32_t w = le16(&f[12]), h = le16(&f[14]), bits = f[16], desc = f[17];
-	if (cmap_type != 0 || (type != 2 && type != 3 && type != 10 && type != 11) || w == 0 || h == 0) return false;
+	if (cmap_type != 0 || (type != 2 && type != 3 && type != 10 && type != 11) || w == 0 || h == 0 || (uint64_t)w * h > kMaxImagePixels) return false;
 	uint32_t bpp = bits / 8;
 	if (bpp != 1 && bpp != 3 && bpp != 4) return false;
 	size_t pos = 18 + id_len;
@@ -575,7 +578,7 @@ static bool decode_png(const std::vector<uint8_t>& f, Texture& out)
 		else if (!memcmp(type, "IEND", 4)) done = true;
 		pos += 12 + (size_t)n;
 	}
-	if (!have_ihdr || w == 0 || h == 0 || w > 65536 || h > 65536 || interlace > 1) return false;
+	if (!have_ihdr || w == 0 || h == 0 || w > 65536 || h > 65536 || (uint64_t)w * h > kMaxImagePixels || interlace > 1) return false;
 	int channels = ctype == 0 ? 1 : ctype == 2 ? 3 : ctype == 3 ? 1 : ctype == 4 ? 2 : ctype == 6 ? 4 : 0;
 	if (channels == 0) return false;
 	if (!(depth == 8 || depth == 16 || (depth < 8 && (ctype == 0 || ctype == 3) && (depth == 1 || depth == 2 || depth == 4)))) return false;
@@ -681,12 +684,21 @@ bool load_image_rgba8(const std::string& path_in, Texture& out)
 	std::vector<uint8_t> bytes;
 	if (read_binary_file(path + ".rgba8", bytes) && decode_sidecar(bytes, out)) return true;
 	if (!read_binary_file(path, bytes)) { set_error("[Error]Failed to load image file " + path); return false; }
-	if (decode_bmp(bytes, out)) return true;
-	if (decode_png(bytes, out)) return true;
-	if (decode_jpeg(bytes, out)) return true;
-	std::string lower = path;
-	std::transform(lower.begin(), lower.end(), lower.begin(), [](unsigned char ch) { return (char)tolower(ch); });
-	if (lower.size() > 4 && lower.substr(lower.size() - 4) == ".tga" && decode_tga(bytes, out)) return true;
+	try
+	{
+		if (decode_bmp(bytes, out)) return true;
+		if (decode_png(bytes, out)) return true;
+		if (decode_jpeg(bytes, out)) return true;
+		std::string lower = path;
+		std::transform(lower.begin(), lower.end(), lower.begin(), [](unsigned char ch) { return (char)tolower(ch); });
+		if (lower.size() > 4 && lower.substr(lower.size() - 4) == ".tga" && decode_tga(bytes, out)) return true;
+	}
+	catch (const std::bad_alloc&)
+	{
+		// a header announcing more pixels than memory holds (corrupt or hostile file): fail like any other undecodable file
+		set_error("[Error]Image too large to decode: " + path);
+		return false;
+	}
 	set_error("[Error]Unsupported image file format (BMP, TGA, PNG and Huffman-coded JPEG are decoded natively; provide a .rgba8 side-car): " + path);
 	return false;
 }

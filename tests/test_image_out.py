@@ -285,6 +285,27 @@ def test_jpeg_sidecar_and_corrupt_files(tmp_path, jpeg_mode):
             ptb.decode_image(q)
 
 
+def test_oversized_headers_fail_before_allocating(tmp_path):
+    """A header announcing more pixels than any decoder should allocate (corrupt or hostile file) is an error, not a crash."""
+    Image = pytest.importorskip("PIL.Image")
+    p = str(tmp_path / "huge.png")
+    open(p, "wb").write(_png_bytes(60000, 60000, 8, 2, [(0, bytes(30))]))
+    with pytest.raises(ptb.PtbError):
+        ptb.decode_image(p)
+    q = str(tmp_path / "huge.jpg")
+    Image.fromarray(_test_image(16, 16, 1)).save(q, quality=80)
+    data = bytearray(open(q, "rb").read())
+    sof = data.find(b"\xff\xc0")
+    data[sof + 5:sof + 9] = b"\xff\xff\xff\xff"           # 65535 x 65535
+    open(q, "wb").write(bytes(data))
+    with pytest.raises(ptb.PtbError):
+        ptb.decode_image(q)
+    t = str(tmp_path / "huge.tga")
+    open(t, "wb").write(bytes([0, 0, 2, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0xff, 0xff, 0xff, 0xff, 24, 0]) + bytes(64))
+    with pytest.raises(ptb.PtbError):
+        ptb.decode_image(t)
+
+
 def test_jpeg_fast_mode_matches_golden(tmp_path, jpeg_mode):
     """Committed vectors (tests/golden/make_jpeg_golden.py): libjpeg-turbo run with dct_method=JDCT_IFAST and
     do_fancy_upsampling=FALSE — what FreeImage_Load(..., 0) selects for the reference (Others/image_loader.cpp:45)."""
