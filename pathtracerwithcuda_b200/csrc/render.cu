@@ -865,7 +865,12 @@ ptb_renderer* ptb_create(const char* config_json_path, int cuda_device)
 	memset(&r->stats, 0, sizeof(r->stats));
 	memset(&r->dscene, 0, sizeof(r->dscene));
 	memset(&r->st, 0, sizeof(r->st));
-	if (!config_json_path || !load_config(config_json_path, r->cfg)) { delete r; return nullptr; }
+	bool config_ok = false;
+	// no exception may cross the C boundary: a parser running out of memory is a load error like any other
+	try { config_ok = config_json_path && load_config(config_json_path, r->cfg); }
+	catch (const std::exception& e) { set_error(std::string("[Error]") + e.what()); }
+	catch (...) { set_error("[Error]unknown failure while reading the configuration"); }
+	if (!config_ok) { delete r; return nullptr; }
 	default_camera((float)r->cfg.width, (float)r->cfg.height, -1.0f, -1.0f, r->cam);
 	r->device = cuda_device;
 	if (cuda_device < 0)
@@ -933,7 +938,12 @@ int ptb_load_scene(ptb_renderer* r, const char* scene_json_path, const char* ass
 {
 	if (!r) { set_error("[Error]null renderer"); return 1; }
 	ptb_release_scene(r);
-	if (!load_scene(scene_json_path ? scene_json_path : "", asset_root ? asset_root : "", r->scene))
+	bool loaded = false;
+	// no exception may cross the C boundary (see ptb_create)
+	try { loaded = load_scene(scene_json_path ? scene_json_path : "", asset_root ? asset_root : "", r->scene); }
+	catch (const std::exception& e) { set_error(std::string("[Error]") + e.what()); }
+	catch (...) { set_error("[Error]unknown failure while reading the scene"); }
+	if (!loaded)
 	{
 		r->scene = HostScene();
 		return 1;
