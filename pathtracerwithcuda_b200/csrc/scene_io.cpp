@@ -996,8 +996,12 @@ int point_in_polygon(int nvert, const float* vertx, const float* verty, float te
 
 // tiny_obj_loader.h:985-1175 with triangulate=true: project on the dominant plane of the first
 // non-degenerate corner, then clip ears; a triangle passes through untouched.
-void emit_face(ObjShape& shape, const std::vector<ObjIndex>& face, const std::vector<float>& v)
+bool emit_face(ObjShape& shape, const std::vector<ObjIndex>& face, const std::vector<float>& v)
 {
+	// tinyobj triangulates with the vertices read so far and does not check the indices; a face pointing outside them
+	// (corrupt file, forward reference) is an error here instead of a wild read
+	for (const ObjIndex& ix : face)
+		if (ix.v < 0 || (size_t)ix.v >= v.size() / 3) { set_error("[Error]OBJ face references a vertex that is not defined"); return false; }
 	size_t npolys = face.size();
 	size_t axes[2] = { 1, 2 };
 	for (size_t k = 0; k < npolys; ++k)
@@ -1069,12 +1073,14 @@ void emit_face(ObjShape& shape, const std::vector<ObjIndex>& face, const std::ve
 	{
 		shape.indices.push_back(remaining[0]); shape.indices.push_back(remaining[1]); shape.indices.push_back(remaining[2]);
 	}
+	return true;
 }
 
-void flush_group(ObjShape& shape, std::vector<std::vector<ObjIndex>>& group, const std::vector<float>& v)
+bool flush_group(ObjShape& shape, std::vector<std::vector<ObjIndex>>& group, const std::vector<float>& v)
 {
-	for (auto& face : group) emit_face(shape, face, v);
+	for (auto& face : group) if (!emit_face(shape, face, v)) { group.clear(); return false; }
 	group.clear();
+	return true;
 }
 
 bool parse_obj(const std::string& path, ObjData& out)
@@ -1143,7 +1149,7 @@ bool parse_obj(const std::string& path, ObjData& out)
 		// never changes and the statement is a no-op (tiny_obj_loader.h:1779-1803).
 		if (token[0] == 'g' && is_space(token[1]))
 		{
-			flush_group(shape, group, out.v);
+			if (!flush_group(shape, group, out.v)) return false;
 			if (!shape.indices.empty()) out.shapes.push_back(shape);
 			shape = ObjShape();
 			continue;
@@ -1151,14 +1157,14 @@ bool parse_obj(const std::string& path, ObjData& out)
 		if (token[0] == 'o' && is_space(token[1]))
 		{
 			bool had_faces = !group.empty();
-			flush_group(shape, group, out.v);
+			if (!flush_group(shape, group, out.v)) return false;
 			if (had_faces) out.shapes.push_back(shape);
 			shape = ObjShape();
 			continue;
 		}
 	}
 	bool had_faces = !group.empty();
-	flush_group(shape, group, out.v);
+	if (!flush_group(shape, group, out.v)) return false;
 	if (had_faces || !shape.indices.empty()) out.shapes.push_back(shape);
 	return true;
 }

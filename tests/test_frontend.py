@@ -154,6 +154,13 @@ def test_scene_errors(workload_root, tmp_path):
         f.write("v 0 0 0\nv 1 0 0\nv 0 1 0\nf 1 2 3\n")
     with pytest.raises(ptb.PtbError, match="does not have normal"):
         load({"Background": bg, "Mesh": [{"Material": ["light"], "Path": "res\\obj\\novn.obj", "Position": "0 0 0", "Scale": "1 1 1", "Rotate": "0 0 0"}]})
+    # faces pointing outside the vertices read so far (corrupt file, forward reference): tinyobj would read wild memory while
+    # triangulating; here it is a load error (found by fuzzing the loader under AddressSanitizer)
+    for k, body in enumerate(("f 1//1 2//1 9999//1\n", "f 1//1 2//1 3//1 77//1\n", "f -1//1 -2//1 -50//1\n")):
+        with open(os.path.join(root, "res", "obj", "wild%d.obj" % k), "w") as f:
+            f.write("v 0 0 0\nv 1 0 0\nv 0 1 0\nvn 0 0 1\n" + body)
+        with pytest.raises(ptb.PtbError):
+            load({"Background": bg, "Mesh": [{"Material": ["light"], "Path": "res\\obj\\wild%d.obj" % k, "Position": "0 0 0", "Scale": "1 1 1", "Rotate": "0 0 0"}]})
     # empty scene (background only) is valid
     load({"Background": bg})
     assert r.scene_counts()["triangles"] == 0 and r.scene_counts()["cube_length"] == 64
