@@ -117,14 +117,16 @@ bool write_pfm_rgb(const std::string& path, const float* rgb, int width, int hei
 	return ok;
 }
 
-static const char kMagic[8] = { 'P', 'T', 'B', '2', '0', '0', 'C', '1' };
+static const char kMagic[8] = { 'P', 'T', 'B', '2', '0', '0', 'C', '2' };
 
 bool write_checkpoint(const std::string& path, const CheckpointHeader& h, const float* sum_rgb, std::string& err)
 {
 	FILE* f = fopen(path.c_str(), "wb");
 	if (!f) { err = "[Error]checkpoint: cannot open " + path; return false; }
 	const size_t n = (size_t)h.width * h.height * 3;
-	uint32_t crc = crc32(0, (const uint8_t*)sum_rgb, n * sizeof(float));
+	// the checksum covers the header too: a flipped pass counter or camera would resume a different render
+	uint32_t crc = crc32(0, (const uint8_t*)&h, sizeof(h));
+	crc = crc32(crc, (const uint8_t*)sum_rgb, n * sizeof(float));
 	bool ok = fwrite(kMagic, 1, 8, f) == 8 && fwrite(&h, sizeof(h), 1, f) == 1 && fwrite(&crc, 4, 1, f) == 1 && fwrite(sum_rgb, sizeof(float), n, f) == n;
 	ok = (fclose(f) == 0) && ok;
 	if (!ok) err = "[Error]checkpoint: short write to " + path;
@@ -141,9 +143,16 @@ bool read_checkpoint(const std::string& path, CheckpointHeader& h, std::vector<f
 	if (ok && (h.width <= 0 || h.height <= 0 || h.width > 65536 || h.height > 65536 || h.pass_counter < 0)) ok = false;
 	if (ok)
 	{
+		// the file must hold exactly the announced pixels: checked BEFORE allocating them
 		const size_t n = (size_t)h.width * h.height * 3;
-		sum_rgb.resize(n);
-		ok = fread(sum_rgb.data(), sizeof(float), n, f) == n && crc32(0, (const uint8_t*)sum_rgb.data(), n * sizeof(float)) == crc;
+		const long here = ftell(f);
+		ok = here >= 0 && fseek(f, 0, SEEK_END) == 0 && ftell(f) >= here && (size_t)(ftell(f) - here) == n * sizeof(float) && fseek(f, here, SEEK_SET) == 0;
+		if (ok)
+		{
+			sum_rgb.resize(n);
+			uint32_t want = crc32(0, (const uint8_t*)&h, sizeof(h));
+			ok = fread(sum_rgb.data(), sizeof(float), n, f) == n && crc32(want, (const uint8_t*)sum_rgb.data(), n * sizeof(float)) == crc;
+		}
 	}
 	fclose(f);
 	if (!ok) err = "[Error]checkpoint: " + path + " is not a valid ptb200 checkpoint (bad magic, size or checksum)";

@@ -59,11 +59,17 @@ def test_checkpoint_rejects_mismatch_and_corruption(workload_root, tmp_path):
     other.load_scene(w2["scene"], root2)
     with pytest.raises(ptb.PtbError):
         other.load_checkpoint(ck)               # resolution / depth differ
-    blob = bytearray(open(ck, "rb").read())
-    blob[len(blob) // 2] ^= 0x40
-    open(ck, "wb").write(bytes(blob))
-    with pytest.raises(ptb.PtbError):
-        r.load_checkpoint(ck)                   # checksum
+    good = open(ck, "rb").read()
+    # a flipped pixel byte, a flipped header byte (pass counter at offset 16, camera from offset 24: the checksum covers the
+    # header too), a truncated file and trailing bytes are all rejected
+    for bad in (good[:len(good) // 2] + bytes([good[len(good) // 2] ^ 0x40]) + good[len(good) // 2 + 1:],
+                good[:16] + bytes([good[16] ^ 1]) + good[17:], good[:30] + bytes([good[30] ^ 0x10]) + good[31:],
+                good[:-8], good + b"\0\0\0\0"):
+        open(ck, "wb").write(bad)
+        with pytest.raises(ptb.PtbError):
+            r.load_checkpoint(ck)
+    open(ck, "wb").write(good)
+    r.load_checkpoint(ck)                       # the untouched file still loads
     with pytest.raises(ptb.PtbError):
         r.load_checkpoint(str(tmp_path / "missing.ptbck"))
     assert r.pass_counter() == 2                # a failed load leaves the render untouched
