@@ -357,7 +357,7 @@ struct WideBuilder
 				for (int s = 0; s < 8; s++)
 				{
 					if (slot_done[s]) continue;
-					if (cost[c][s] > best) { best = cost[c][s]; bc = c; bs = s; }
+					if (cost[c][s] > best || bc < 0) { best = cost[c][s]; bc = c; bs = s; }     // bc < 0: a pair is always chosen, whatever the values (same rule as k_collapse8)
 				}
 			}
 			child_done[bc] = true; slot_done[bs] = true;

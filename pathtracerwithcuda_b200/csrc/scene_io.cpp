@@ -1172,6 +1172,8 @@ bool parse_obj(const std::string& path, ObjData& out)
 } // namespace
 
 // triangle_mesh::load_obj + create_mesh_device_data for one mesh (triangle_mesh.cpp:8-213,558-655)
+static bool mesh_in_range(const HostScene& scene, const MeshInfo& m);
+
 static bool append_mesh(HostScene& scene, const std::string& path, const Vec3& position, const Vec3& scale_v, const Vec3& rotate_v,
 	std::vector<ptb_material> mats)
 {
@@ -1244,7 +1246,23 @@ static bool append_mesh(HostScene& scene, const std::string& path, const Vec3& p
 	info.first_triangle = triangle_base; info.triangle_count = mesh_triangles;
 	info.first_material = material_base; info.material_count = mat_num;
 	info.position = position; info.scale = scale_v; info.rotate = rotate_v; info.rotate_applied = rotate_v;
+	if (!mesh_in_range(scene, info)) { set_error("[Error]Mesh " + path + " has vertices outside the supported range (non-finite or beyond 1e18)"); return false; }
 	scene.meshes.push_back(info);
+	return true;
+}
+
+// World-space positions must be finite and small enough that box extents and surface areas stay finite in float: the tree
+// builders (host and device) bin by centroid and compare areas, and neither defines a result for NaN / inf input.  The reference
+// builds garbage from such a mesh; here it is an error.
+static bool mesh_in_range(const HostScene& scene, const MeshInfo& m)
+{
+	const float limit = 1e18f;
+	for (int i = m.first_triangle; i < m.first_triangle + m.triangle_count; i++)
+	{
+		const Triangle& t = scene.triangles[i];
+		const float c[9] = { t.v0.x, t.v0.y, t.v0.z, t.v1.x, t.v1.y, t.v1.z, t.v2.x, t.v2.y, t.v2.z };
+		for (float x : c) if (!(std::fabs(x) <= limit)) return false;     // also false for NaN
+	}
 	return true;
 }
 
@@ -1278,9 +1296,17 @@ bool set_mesh_transform(HostScene& scene, int mesh, const Vec3& position, const 
 {
 	if (mesh < 0 || mesh >= (int)scene.meshes.size()) { set_error("[Error]mesh index out of range"); return false; }
 	MeshInfo& m = scene.meshes[mesh];
+	const Vec3 old_position = m.position, old_scale = m.scale;
 	m.position = position;
 	m.scale = scale_v;
 	place_mesh(scene, m);
+	if (!mesh_in_range(scene, m))
+	{
+		m.position = old_position; m.scale = old_scale;
+		place_mesh(scene, m);
+		set_error("[Error]mesh transform puts vertices outside the supported range (non-finite or beyond 1e18)");
+		return false;
+	}
 	return true;
 }
 
@@ -1288,6 +1314,7 @@ bool apply_mesh_rotate(HostScene& scene, int mesh, const Vec3& rotate_v)
 {
 	if (mesh < 0 || mesh >= (int)scene.meshes.size()) { set_error("[Error]mesh index out of range"); return false; }
 	MeshInfo& m = scene.meshes[mesh];
+	if (!std::isfinite(rotate_v.x) || !std::isfinite(rotate_v.y) || !std::isfinite(rotate_v.z)) { set_error("[Error]mesh rotation is not finite"); return false; }
 	m.rotate = rotate_v;
 	// the rotation still to apply, about z, then y, then x (triangle_mesh.cpp:364-368)
 	const float deg2rad = (float)0.01745329251994329576923690768489;

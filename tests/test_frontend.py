@@ -161,6 +161,19 @@ def test_scene_errors(workload_root, tmp_path):
             f.write("v 0 0 0\nv 1 0 0\nv 0 1 0\nvn 0 0 1\n" + body)
         with pytest.raises(ptb.PtbError):
             load({"Background": bg, "Mesh": [{"Material": ["light"], "Path": "res\\obj\\wild%d.obj" % k, "Position": "0 0 0", "Scale": "1 1 1", "Rotate": "0 0 0"}]})
+    # non-finite or astronomically large vertices: the tree builders define no result for them; a load error, as is an edit
+    # that would move a mesh there (the mesh keeps its previous placement)
+    with open(os.path.join(root, "res", "obj", "inf.obj"), "w") as f:
+        f.write("v 0 0 0\nv 1e39 0 0\nv 0 1 0\nvn 0 0 1\nf 1//1 2//1 3//1\n")
+    with pytest.raises(ptb.PtbError, match="outside the supported range"):
+        load({"Background": bg, "Mesh": [{"Material": ["light"], "Path": "res\\obj\\inf.obj", "Position": "0 0 0", "Scale": "1 1 1", "Rotate": "0 0 0"}]})
+    r.load_scene(w["scene"], root)
+    before = r.scene_triangles()[0].copy()
+    with pytest.raises(ptb.PtbError, match="outside the supported range"):
+        r.set_mesh_transform(0, (0.0, 0.0, 0.0), (1e30, 1e30, 1e30))
+    with pytest.raises(ptb.PtbError):
+        r.set_mesh_transform(0, (float("nan"), 0.0, 0.0), (1.0, 1.0, 1.0))
+    assert np.array_equal(r.scene_triangles()[0].view(np.uint32), before.view(np.uint32))
     # empty scene (background only) is valid
     load({"Background": bg})
     assert r.scene_counts()["triangles"] == 0 and r.scene_counts()["cube_length"] == 64

@@ -12,10 +12,12 @@ $CXX $FLAGS "$HERE/fuzz_images.cpp" "$SRC/scene_io.cpp" "$SRC/jpeg_decode.cpp" -
 $CXX $FLAGS "$HERE/fuzz_scene.cpp" "$SRC/scene_io.cpp" "$SRC/jpeg_decode.cpp" -o "$WORK/bin/scene"
 $CXX $FLAGS "$HERE/fuzz_config.cpp" "$SRC/scene_io.cpp" "$SRC/jpeg_decode.cpp" -o "$WORK/bin/config"
 $CXX $FLAGS "$HERE/fuzz_checkpoint.cpp" "$SRC/image_out.cpp" -o "$WORK/bin/checkpoint"
+$CXX $FLAGS -fopenmp -pthread "$HERE/fuzz_bvh.cpp" "$SRC/scene_io.cpp" "$SRC/jpeg_decode.cpp" "$SRC/bvh_host.cpp" -o "$WORK/bin/bvh"
 python "$HERE/make_corpus.py" "$WORK/corpus" "$SEED" "$COUNT"
 LOG="$WORK/log.txt"; : > "$LOG"
 (cd "$WORK/corpus/images" && ls | xargs -n 1000 "$WORK/bin/images") >> "$LOG" 2>&1 || true
 (ls "$WORK/corpus/scene_root/fz" | sed "s#^#$WORK/corpus/scene_root/fz/#" | xargs -n 500 "$WORK/bin/scene" "$WORK/corpus/scene_root") >> "$LOG" 2>&1 || true
+(ls "$WORK/corpus/scene_root/fz" | grep "^o" | sed "s#^#$WORK/corpus/scene_root/fz/#" | xargs -n 300 "$WORK/bin/bvh" "$WORK/corpus/scene_root") >> "$LOG" 2>&1 || true   # host SAH builder, flatten, 8-wide collapse
 (cd "$WORK/corpus/configs" && ls | xargs -n 1000 "$WORK/bin/config") >> "$LOG" 2>&1 || true
 "$WORK/bin/checkpoint" >> "$LOG" 2>&1 || true
 grep "^ok" "$LOG"
