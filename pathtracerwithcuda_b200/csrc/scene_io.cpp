@@ -27,6 +27,8 @@
 #include <fstream>
 #include <map>
 #include <sstream>
+#include <thread>
+#include <atomic>
 #include <dirent.h>
 
 namespace ptb
@@ -63,12 +65,19 @@ static std::string join_path(const std::string& root, const std::string& rel)
 
 static bool read_text_file(const std::string& path, std::string& out)
 {
-	std::ifstream f(path, std::ios::in | std::ios::binary);
+	// one sized read (mesh files run to hundreds of MB; a stringstream copies them twice)
+	FILE* f = fopen(path.c_str(), "rb");
 	if (!f) return false;
-	std::ostringstream ss;
-	ss << f.rdbuf();
-	out = ss.str();
-	return true;
+	bool ok = fseek(f, 0, SEEK_END) == 0;
+	const long size = ok ? ftell(f) : -1;
+	ok = ok && size >= 0 && fseek(f, 0, SEEK_SET) == 0;
+	if (ok)
+	{
+		out.resize((size_t)size);
+		ok = size == 0 || fread(&out[0], 1, (size_t)size, f) == (size_t)size;
+	}
+	fclose(f);
+	return ok;
 }
 
 // `istringstream >> float` (config_parser.cpp:189-195): leading blanks skipped, 0 on failure.
@@ -996,12 +1005,30 @@ int point_in_polygon(int nvert, const float* vertx, const float* verty, float te
 
 // tiny_obj_loader.h:985-1175 with triangulate=true: project on the dominant plane of the first
 // non-degenerate corner, then clip ears; a triangle passes through untouched.
-bool emit_face(ObjShape& shape, const std::vector<ObjIndex>& face, const std::vector<float>& v)
+// Faces of the current group, flat: indices back to back, `start` marks where each face begins (one allocation per group,
+// not one per face — a 1 M-triangle mesh is 1 M faces).
+struct FaceGroup
+{
+	std::vector<ObjIndex> idx;
+	std::vector<size_t> start;
+	bool empty() const { return start.empty(); }
+	void clear() { idx.clear(); start.clear(); }
+};
+
+bool emit_face(ObjShape& shape, const ObjIndex* face_begin, size_t face_size, const std::vector<float>& v)
 {
 	// tinyobj triangulates with the vertices read so far and does not check the indices; a face pointing outside them
 	// (corrupt file, forward reference) is an error here instead of a wild read
-	for (const ObjIndex& ix : face)
-		if (ix.v < 0 || (size_t)ix.v >= v.size() / 3) { set_error("[Error]OBJ face references a vertex that is not defined"); return false; }
+	const size_t n_vertices = v.size() / 3;
+	for (size_t k = 0; k < face_size; k++)
+		if (face_begin[k].v < 0 || (size_t)face_begin[k].v >= n_vertices) { set_error("[Error]OBJ face references a vertex that is not defined"); return false; }
+	if (face_size == 3)
+	{
+		// a triangle passes through the ear clipper untouched (nothing below has a side effect for three vertices)
+		shape.indices.push_back(face_begin[0]); shape.indices.push_back(face_begin[1]); shape.indices.push_back(face_begin[2]);
+		return true;
+	}
+	const std::vector<ObjIndex> face(face_begin, face_begin + face_size);
 	size_t npolys = face.size();
 	size_t axes[2] = { 1, 2 };
 	for (size_t k = 0; k < npolys; ++k)
@@ -1076,9 +1103,13 @@ bool emit_face(ObjShape& shape, const std::vector<ObjIndex>& face, const std::ve
 	return true;
 }
 
-bool flush_group(ObjShape& shape, std::vector<std::vector<ObjIndex>>& group, const std::vector<float>& v)
+bool flush_group(ObjShape& shape, FaceGroup& group, const std::vector<float>& v)
 {
-	for (auto& face : group) if (!emit_face(shape, face, v)) { group.clear(); return false; }
+	for (size_t f = 0; f < group.start.size(); f++)
+	{
+		const size_t b = group.start[f], e = f + 1 < group.start.size() ? group.start[f + 1] : group.idx.size();
+		if (!emit_face(shape, group.idx.data() + b, e - b, v)) { group.clear(); return false; }
+	}
 	group.clear();
 	return true;
 }
@@ -1087,20 +1118,23 @@ bool parse_obj(const std::string& path, ObjData& out)
 {
 	std::string text;
 	if (!read_text_file(path, text)) { set_error("[Info]Load file " + path + " failed: Cannot open file"); return false; }
-	std::vector<std::vector<ObjIndex>> group;
+	FaceGroup group;
 	ObjShape shape;
 	size_t pos = 0;
-	std::string line;
-	while (pos < text.size())
+	text.push_back('\0');             // the last line is terminated like every other (lines are parsed in place)
+	const size_t text_size = text.size() - 1;
+	while (pos < text_size)
 	{
-		// safeGetline: lines end at \n, \r\n or a lone \r
+		// safeGetline: lines end at \n, \r\n or a lone \r.  The line is parsed where it lies: its terminator becomes a NUL
+		// (an embedded NUL simply ends the line early, as it did for the copied string's c_str()).
 		size_t e = pos;
-		while (e < text.size() && text[e] != '\n' && text[e] != '\r') e++;
-		line.assign(text, pos, e - pos);
-		if (e < text.size() && text[e] == '\r' && e + 1 < text.size() && text[e + 1] == '\n') e++;
-		pos = e + 1;
-		if (line.empty()) continue;
-		const char* token = line.c_str();
+		while (e < text_size && text[e] != '\n' && text[e] != '\r') e++;
+		const size_t line_begin = pos, line_len = e - pos;
+		const bool crlf = e < text_size && text[e] == '\r' && e + 1 < text_size && text[e + 1] == '\n';
+		text[e] = '\0';
+		pos = e + (crlf ? 2 : 1);
+		if (line_len == 0) continue;
+		const char* token = text.data() + line_begin;
 		token += strspn(token, " \t");
 		if (token[0] == '\0' || token[0] == '#') continue;
 
@@ -1129,7 +1163,7 @@ bool parse_obj(const std::string& path, ObjData& out)
 		{
 			token += 2;
 			token += strspn(token, " \t");
-			std::vector<ObjIndex> face;
+			const size_t face_begin = group.idx.size();
 			while (!is_new_line(token[0]))
 			{
 				ObjIndex vi;
@@ -1138,11 +1172,12 @@ bool parse_obj(const std::string& path, ObjData& out)
 					set_error("[TinyObj]Failed parse `f' line(e.g. zero value for face index).");
 					return false;
 				}
-				face.push_back(vi);
+				group.idx.push_back(vi);
 				token += strspn(token, " \t\r");
 			}
-			if (face.size() >= 3) group.push_back(face);
-			else if (!face.empty()) { set_error("[Error]" + path + " has a face with fewer than 3 vertices"); return false; }
+			const size_t face_size = group.idx.size() - face_begin;
+			if (face_size >= 3) group.start.push_back(face_begin);
+			else if (face_size != 0) { set_error("[Error]" + path + " has a face with fewer than 3 vertices"); return false; }
 			continue;
 		}
 		// `usemtl`: no .mtl files ship, every name maps to material id -1, so the per-face material
@@ -1200,12 +1235,23 @@ static bool append_mesh(HostScene& scene, const std::string& path, const Vec3& p
 	const int triangle_base = (int)scene.triangles.size();
 	int mesh_triangles = 0;
 	const size_t nv = obj.v.size() / 3, nn = obj.vn.size() / 3, nt = obj.vt.size() / 2;
-	for (size_t si = 0; si < obj.shapes.size(); si++)
+	// every triangle is independent: sized once, filled by a few host threads (same arithmetic, same order of results)
+	std::vector<size_t> shape_base(obj.shapes.size() + 1, 0);
+	for (size_t si = 0; si < obj.shapes.size(); si++) shape_base[si + 1] = shape_base[si] + obj.shapes[si].indices.size() / 3;
+	const size_t total = shape_base.back();
+	scene.triangles.resize((size_t)triangle_base + total);
+	scene.local_triangles.resize((size_t)triangle_base + total);
+	scene.triangle_material.resize((size_t)triangle_base + total);
+	std::atomic<bool> bad_index(false);
+	auto fill = [&](size_t t_begin, size_t t_end)
 	{
-		const ObjShape& sh = obj.shapes[si];
-		int mat_index = (int)si < mat_num ? (int)si : mat_num - 1;
-		for (size_t f = 0; f + 2 < sh.indices.size(); f += 3)
+		size_t si = 0;
+		for (size_t t = t_begin; t < t_end; t++)
 		{
+			while (t >= shape_base[si + 1]) si++;
+			const ObjShape& sh = obj.shapes[si];
+			const size_t f = (t - shape_base[si]) * 3;
+			const int mat_index = (int)si < mat_num ? (int)si : mat_num - 1;
 			Triangle tri, local;
 			Vec3* vv[3] = { &tri.v0, &tri.v1, &tri.v2 };
 			Vec3* nn3[3] = { &tri.n0, &tri.n1, &tri.n2 };
@@ -1218,8 +1264,8 @@ static bool append_mesh(HostScene& scene, const std::string& path, const Vec3& p
 				const ObjIndex& ix = sh.indices[f + k];
 				if (ix.v < 0 || (size_t)ix.v >= nv || ix.vn < 0 || (size_t)ix.vn >= nn || (has_uv && (ix.vt < 0 || (size_t)ix.vt >= nt)))
 				{
-					set_error("[Error]" + path + ": face index out of range / missing normal or texcoord index");
-					return false;
+					bad_index = true;
+					return;
 				}
 				V4 p = transform(rot, v4(obj.v[ix.v * 3], obj.v[ix.v * 3 + 1], obj.v[ix.v * 3 + 2], 1.0f));
 				V4 n = transform(rot_it, v4(obj.vn[ix.vn * 3], obj.vn[ix.vn * 3 + 1], obj.vn[ix.vn * 3 + 2], 0.0f));
@@ -1232,13 +1278,30 @@ static bool append_mesh(HostScene& scene, const std::string& path, const Vec3& p
 				*uu[k] = has_uv ? Vec2{ obj.vt[ix.vt * 2], obj.vt[ix.vt * 2 + 1] } : Vec2{ 0.0f, 0.0f };
 				*lv[k] = Vec3{ p.x, p.y, p.z }; *ln[k] = n1; *lu[k] = *uu[k];
 			}
-			if (!has_uv) mats[mat_index].diffuse_texture_id = -1; // triangle_mesh.cpp:131-137
-			scene.triangles.push_back(tri);
-			scene.local_triangles.push_back(local);
-			scene.triangle_material.push_back(material_base + mat_index);
-			mesh_triangles++;
+			scene.triangles[(size_t)triangle_base + t] = tri;
+			scene.local_triangles[(size_t)triangle_base + t] = local;
+			scene.triangle_material[(size_t)triangle_base + t] = material_base + mat_index;
 		}
+	};
+	{
+		const size_t hw = std::max(1u, std::thread::hardware_concurrency());
+		const size_t n_threads = total < 65536 ? 1 : std::min<size_t>(16, hw);
+		std::vector<std::thread> workers;
+		for (size_t w = 1; w < n_threads; w++) workers.emplace_back(fill, total * w / n_threads, total * (w + 1) / n_threads);
+		fill(0, total / n_threads);
+		for (auto& th : workers) th.join();
 	}
+	if (bad_index)
+	{
+		scene.triangles.resize((size_t)triangle_base); scene.local_triangles.resize((size_t)triangle_base); scene.triangle_material.resize((size_t)triangle_base);
+		set_error("[Error]" + path + ": face index out of range / missing normal or texcoord index");
+		return false;
+	}
+	// a mesh without texture coordinates cannot carry a diffuse texture (triangle_mesh.cpp:131-137): applies to every material a triangle uses
+	if (!has_uv)
+		for (size_t si = 0; si < obj.shapes.size(); si++)
+			if (shape_base[si + 1] > shape_base[si]) mats[(int)si < mat_num ? (int)si : mat_num - 1].diffuse_texture_id = -1;
+	mesh_triangles = (int)total;
 	scene.materials.insert(scene.materials.end(), mats.begin(), mats.end());
 	scene.mesh_triangle_count.push_back(mesh_triangles);
 	scene.mesh_material_count.push_back(mat_num);
