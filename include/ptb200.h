@@ -173,7 +173,8 @@ int ptb_bvh_download(ptb_renderer* r, float* out_nodes16, int32_t* out_leaf_orde
  * floor(log2(visits + 1)) == k (binary-tree kernel) */
 int ptb_get_traversal_histogram(ptb_renderer* r, int64_t* out25);
 /* string options: "bvh_builder" = "gpu_sah" (default) | "host_sah"; "passes_in_flight" = "1".."64";
- * "profile_stages" = "0"|"1"; "count_traversal" = "0"|"1"; "sort_by_material" = "0"|"1". */
+ * "profile_stages" = "0"|"1"; "count_traversal" = "0"|"1"; "sort_by_material" = "0"|"1";
+ * "loader_threads" = "0".."64" (process-wide: slices an OBJ file is parsed in; 0 = by file size and host cores). */
 int ptb_set_option(ptb_renderer* r, const char* key, const char* value);
 
 /* ---- output side -----------------------------------------------------------------------------

@@ -1015,11 +1015,10 @@ struct FaceGroup
 	void clear() { idx.clear(); start.clear(); }
 };
 
-bool emit_face(ObjShape& shape, const ObjIndex* face_begin, size_t face_size, const std::vector<float>& v)
+bool emit_face(ObjShape& shape, const ObjIndex* face_begin, size_t face_size, const std::vector<float>& v, size_t n_vertices)
 {
-	// tinyobj triangulates with the vertices read so far and does not check the indices; a face pointing outside them
-	// (corrupt file, forward reference) is an error here instead of a wild read
-	const size_t n_vertices = v.size() / 3;
+	// tinyobj triangulates with the vertices read so far (n_vertices of them) and does not check the indices; a face pointing
+	// outside them (corrupt file, forward reference) is an error here instead of a wild read
 	for (size_t k = 0; k < face_size; k++)
 		if (face_begin[k].v < 0 || (size_t)face_begin[k].v >= n_vertices) { set_error("[Error]OBJ face references a vertex that is not defined"); return false; }
 	if (face_size == 3)
@@ -1103,103 +1102,222 @@ bool emit_face(ObjShape& shape, const ObjIndex* face_begin, size_t face_size, co
 	return true;
 }
 
-bool flush_group(ObjShape& shape, FaceGroup& group, const std::vector<float>& v)
+bool flush_group(ObjShape& shape, FaceGroup& group, const std::vector<float>& v, size_t n_vertices)
 {
 	for (size_t f = 0; f < group.start.size(); f++)
 	{
 		const size_t b = group.start[f], e = f + 1 < group.start.size() ? group.start[f + 1] : group.idx.size();
-		if (!emit_face(shape, group.idx.data() + b, e - b, v)) { group.clear(); return false; }
+		if (!emit_face(shape, group.idx.data() + b, e - b, v, n_vertices)) { group.clear(); return false; }
 	}
 	group.clear();
 	return true;
 }
 
-bool parse_obj(const std::string& path, ObjData& out)
-{
-	std::string text;
-	if (!read_text_file(path, text)) { set_error("[Info]Load file " + path + " failed: Cannot open file"); return false; }
-	FaceGroup group;
-	ObjShape shape;
-	size_t pos = 0;
-	text.push_back('\0');             // the last line is terminated like every other (lines are parsed in place)
-	const size_t text_size = text.size() - 1;
-	while (pos < text_size)
-	{
-		// safeGetline: lines end at \n, \r\n or a lone \r.  The line is parsed where it lies: its terminator becomes a NUL
-		// (an embedded NUL simply ends the line early, as it did for the copied string's c_str()).
-		size_t e = pos;
-		while (e < text_size && text[e] != '\n' && text[e] != '\r') e++;
-		const size_t line_begin = pos, line_len = e - pos;
-		const bool crlf = e < text_size && text[e] == '\r' && e + 1 < text_size && text[e + 1] == '\n';
-		text[e] = '\0';
-		pos = e + (crlf ? 2 : 1);
-		if (line_len == 0) continue;
-		const char* token = text.data() + line_begin;
-		token += strspn(token, " \t");
-		if (token[0] == '\0' || token[0] == '#') continue;
+int g_loader_threads = 0;   // 0: by file size and host cores (set_loader_threads / option "loader_threads")
 
+// One slice of the file (whole lines), parsed by one host thread.  Negative (relative) face indices need the number of
+// v / vn / vt lines before the face, so a first pass counts them per slice and a prefix sum gives every slice its base.
+struct ObjEvent
+{
+	int kind;              // 0 face, 1 `g`, 2 `o`, 3 parse error (message in the slice)
+	size_t begin, size;    // face: range in the slice's idx
+	size_t n_vertices;     // vertices read before this line (what tinyobj's triangulation would see)
+};
+
+struct ObjSlice
+{
+	size_t begin = 0, end = 0;
+	size_t count_v = 0, count_vn = 0, count_vt = 0;     // pass 1
+	size_t base_v = 0, base_vn = 0, base_vt = 0;
+	std::vector<float> v, vn, vt;
+	std::vector<ObjIndex> idx;
+	std::vector<ObjEvent> events;
+	std::string error;
+};
+
+// safeGetline: lines end at \n, \r\n or a lone \r.  A line is parsed where it lies: its terminator becomes a NUL (an embedded NUL
+// simply ends the line early, as it did for a copied string's c_str()).  Returns the start of the line's first token or nullptr.
+inline const char* next_line(std::string& text, size_t& pos, size_t end)
+{
+	size_t e = pos;
+	while (e < end && text[e] != '\n' && text[e] != '\r') e++;
+	const size_t line_begin = pos, line_len = e - pos;
+	const bool crlf = e < end && text[e] == '\r' && e + 1 < end && text[e + 1] == '\n';
+	text[e] = '\0';
+	pos = e + (crlf ? 2 : 1);
+	if (line_len == 0) return nullptr;
+	const char* token = text.data() + line_begin;
+	token += strspn(token, " \t");
+	if (token[0] == '\0' || token[0] == '#') return nullptr;
+	return token;
+}
+
+void count_slice(const std::string& text, ObjSlice& sl)
+{
+	// the same classification as parse_slice, without touching the text
+	size_t pos = sl.begin;
+	while (pos < sl.end)
+	{
+		size_t e = pos;
+		while (e < sl.end && text[e] != '\n' && text[e] != '\r') e++;
+		size_t t = pos;
+		while (t < e && (text[t] == ' ' || text[t] == '\t')) t++;
+		if (t + 1 < e + 1 && text[t] == 'v' && t < e)
+		{
+			const char c1 = t + 1 < e ? text[t + 1] : '\0', c2 = t + 2 < e ? text[t + 2] : '\0';
+			if (is_space(c1)) sl.count_v++;
+			else if (c1 == 'n' && is_space(c2)) sl.count_vn++;
+			else if (c1 == 't' && is_space(c2)) sl.count_vt++;
+		}
+		const bool crlf = e < sl.end && text[e] == '\r' && e + 1 < sl.end && text[e + 1] == '\n';
+		pos = e + (crlf ? 2 : 1);
+	}
+}
+
+void parse_slice(std::string& text, ObjSlice& sl, const std::string& path)
+{
+	size_t pos = sl.begin;
+	sl.v.reserve(sl.count_v * 3); sl.vn.reserve(sl.count_vn * 3); sl.vt.reserve(sl.count_vt * 2);
+	while (pos < sl.end)
+	{
+		const char* token = next_line(text, pos, sl.end);
+		if (!token) continue;
 		if (token[0] == 'v' && is_space(token[1]))
 		{
 			token += 2;
 			float x = parse_real(&token), y = parse_real(&token), z = parse_real(&token);
-			out.v.push_back(x); out.v.push_back(y); out.v.push_back(z);
+			sl.v.push_back(x); sl.v.push_back(y); sl.v.push_back(z);
 			continue;
 		}
 		if (token[0] == 'v' && token[1] == 'n' && is_space(token[2]))
 		{
 			token += 3;
 			float x = parse_real(&token), y = parse_real(&token), z = parse_real(&token);
-			out.vn.push_back(x); out.vn.push_back(y); out.vn.push_back(z);
+			sl.vn.push_back(x); sl.vn.push_back(y); sl.vn.push_back(z);
 			continue;
 		}
 		if (token[0] == 'v' && token[1] == 't' && is_space(token[2]))
 		{
 			token += 3;
 			float x = parse_real(&token), y = parse_real(&token);
-			out.vt.push_back(x); out.vt.push_back(y);
+			sl.vt.push_back(x); sl.vt.push_back(y);
 			continue;
 		}
+		const size_t n_vertices = sl.base_v + sl.v.size() / 3;
 		if (token[0] == 'f' && is_space(token[1]))
 		{
 			token += 2;
 			token += strspn(token, " \t");
-			const size_t face_begin = group.idx.size();
+			const size_t face_begin = sl.idx.size();
 			while (!is_new_line(token[0]))
 			{
 				ObjIndex vi;
-				if (!parse_triple(&token, (int)(out.v.size() / 3), (int)(out.vn.size() / 3), (int)(out.vt.size() / 2), &vi))
+				if (!parse_triple(&token, (int)n_vertices, (int)(sl.base_vn + sl.vn.size() / 3), (int)(sl.base_vt + sl.vt.size() / 2), &vi))
 				{
-					set_error("[TinyObj]Failed parse `f' line(e.g. zero value for face index).");
-					return false;
+					sl.error = "[TinyObj]Failed parse `f' line(e.g. zero value for face index).";
+					sl.events.push_back(ObjEvent{ 3, 0, 0, n_vertices });
+					return;
 				}
-				group.idx.push_back(vi);
+				sl.idx.push_back(vi);
 				token += strspn(token, " \t\r");
 			}
-			const size_t face_size = group.idx.size() - face_begin;
-			if (face_size >= 3) group.start.push_back(face_begin);
-			else if (face_size != 0) { set_error("[Error]" + path + " has a face with fewer than 3 vertices"); return false; }
+			const size_t face_size = sl.idx.size() - face_begin;
+			if (face_size >= 3) sl.events.push_back(ObjEvent{ 0, face_begin, face_size, n_vertices });
+			else if (face_size != 0)
+			{
+				sl.error = "[Error]" + path + " has a face with fewer than 3 vertices";
+				sl.events.push_back(ObjEvent{ 3, 0, 0, n_vertices });
+				return;
+			}
 			continue;
 		}
 		// `usemtl`: no .mtl files ship, every name maps to material id -1, so the per-face material
 		// never changes and the statement is a no-op (tiny_obj_loader.h:1779-1803).
-		if (token[0] == 'g' && is_space(token[1]))
+		if (token[0] == 'g' && is_space(token[1])) { sl.events.push_back(ObjEvent{ 1, 0, 0, n_vertices }); continue; }
+		if (token[0] == 'o' && is_space(token[1])) { sl.events.push_back(ObjEvent{ 2, 0, 0, n_vertices }); continue; }
+	}
+}
+
+bool parse_obj(const std::string& path, ObjData& out)
+{
+	std::string text;
+	if (!read_text_file(path, text)) { set_error("[Info]Load file " + path + " failed: Cannot open file"); return false; }
+	text.push_back('\0');             // the last line is terminated like every other (lines are parsed in place)
+	const size_t text_size = text.size() - 1;
+
+	// slices of whole lines, cut after a '\n' (a file of lone-'\r' line ends stays one slice)
+	const size_t hw = std::max(1u, std::thread::hardware_concurrency());
+	const size_t want = g_loader_threads > 0 ? (size_t)g_loader_threads : text_size < (4u << 20) ? 1 : std::min<size_t>(16, hw);
+	std::vector<ObjSlice> slices;
+	size_t cut = 0;
+	for (size_t k = 1; k <= want && cut < text_size; k++)
+	{
+		size_t end = k == want ? text_size : text_size * k / want;
+		if (end < cut) end = cut;
+		while (end < text_size && text[end > 0 ? end - 1 : 0] != '\n') end++;
+		if (end <= cut) continue;
+		ObjSlice sl;
+		sl.begin = cut; sl.end = end;
+		slices.push_back(std::move(sl));
+		cut = end;
+	}
+	auto run = [&](auto&& fn)
+	{
+		std::vector<std::thread> workers;
+		for (size_t k = 1; k < slices.size(); k++) workers.emplace_back([&, k] { fn(slices[k]); });
+		if (!slices.empty()) fn(slices[0]);
+		for (auto& th : workers) th.join();
+	};
+	run([&](ObjSlice& sl) { count_slice(text, sl); });
+	for (size_t k = 1; k < slices.size(); k++)
+	{
+		slices[k].base_v = slices[k - 1].base_v + slices[k - 1].count_v;
+		slices[k].base_vn = slices[k - 1].base_vn + slices[k - 1].count_vn;
+		slices[k].base_vt = slices[k - 1].base_vt + slices[k - 1].count_vt;
+	}
+	run([&](ObjSlice& sl) { parse_slice(text, sl, path); });
+
+	// a slice that stopped at a parse error read fewer v / vn / vt lines than counted; everything after it is discarded anyway
+	for (const ObjSlice& sl : slices)
+	{
+		out.v.insert(out.v.end(), sl.v.begin(), sl.v.end());
+		out.vn.insert(out.vn.end(), sl.vn.begin(), sl.vn.end());
+		out.vt.insert(out.vt.end(), sl.vt.begin(), sl.vt.end());
+		if (!sl.error.empty()) break;
+	}
+	// groups, shapes and triangulation in file order
+	FaceGroup group;
+	ObjShape shape;
+	size_t n_vertices = 0;
+	for (const ObjSlice& sl : slices)
+	{
+		for (const ObjEvent& ev : sl.events)
 		{
-			if (!flush_group(shape, group, out.v)) return false;
-			if (!shape.indices.empty()) out.shapes.push_back(shape);
-			shape = ObjShape();
-			continue;
+			n_vertices = ev.n_vertices;
+			if (ev.kind == 0)
+			{
+				group.start.push_back(group.idx.size());
+				group.idx.insert(group.idx.end(), sl.idx.begin() + ev.begin, sl.idx.begin() + ev.begin + ev.size);
+			}
+			else if (ev.kind == 1)
+			{
+				if (!flush_group(shape, group, out.v, n_vertices)) return false;
+				if (!shape.indices.empty()) out.shapes.push_back(shape);
+				shape = ObjShape();
+			}
+			else if (ev.kind == 2)
+			{
+				bool had_faces = !group.empty();
+				if (!flush_group(shape, group, out.v, n_vertices)) return false;
+				if (had_faces) out.shapes.push_back(shape);
+				shape = ObjShape();
+			}
+			else { set_error(sl.error); return false; }
 		}
-		if (token[0] == 'o' && is_space(token[1]))
-		{
-			bool had_faces = !group.empty();
-			if (!flush_group(shape, group, out.v)) return false;
-			if (had_faces) out.shapes.push_back(shape);
-			shape = ObjShape();
-			continue;
-		}
+		n_vertices = sl.base_v + sl.v.size() / 3;
 	}
 	bool had_faces = !group.empty();
-	if (!flush_group(shape, group, out.v)) return false;
+	if (!flush_group(shape, group, out.v, n_vertices)) return false;
 	if (had_faces || !shape.indices.empty()) out.shapes.push_back(shape);
 	return true;
 }
@@ -1420,6 +1538,8 @@ bool apply_mesh_rotate(HostScene& scene, int mesh, const Vec3& rotate_v)
 // ------------------------------------------------------------------------------------------
 // scene JSON
 // ------------------------------------------------------------------------------------------
+
+void set_loader_threads(int n) { g_loader_threads = n < 0 ? 0 : n > 64 ? 64 : n; }
 
 bool load_scene(const std::string& scene_json_path, const std::string& asset_root, HostScene& scene)
 {

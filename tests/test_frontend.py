@@ -66,6 +66,77 @@ def test_awkward_obj_matches_reference(workload_root):
     assert np.all(m["diffuse_texture_id"][:3] == -1)
 
 
+def _random_obj(seed, n_blocks):
+    """Relative and absolute v/vt/vn indices, polygons up to hexagons, g / o / usemtl / blank / comment lines, mixed line ends."""
+    import random
+    rnd = random.Random(seed)
+    lines, nv, nvt, nvn = ["# sliced"], 0, 0, 0
+    for b in range(n_blocks):
+        for i in range(rnd.randint(3, 12)):
+            lines.append("v %.6f %.6g %e" % (rnd.uniform(-3, 3), rnd.uniform(-3, 3), rnd.uniform(-3, 3))); nv += 1
+            if i == 0 or rnd.random() < 0.5:
+                lines.append("vt %.4f %.4f" % (rnd.random(), rnd.random())); nvt += 1
+            if i == 0 or rnd.random() < 0.5:
+                lines.append("  vn %.4f %.4f %.4f" % (rnd.uniform(-1, 1), rnd.uniform(-1, 1), rnd.uniform(-1, 1))); nvn += 1
+        r = rnd.random()
+        if r < 0.2: lines.append("g grp%d" % b)
+        elif r < 0.3: lines.append("o obj%d" % b)
+        elif r < 0.35: lines.append("usemtl m%d" % b)
+        elif r < 0.4: lines.append("")
+        elif r < 0.45: lines.append("\t# comment f 1 2 3")
+        for f in range(rnd.randint(1, 6)):
+            toks = []
+            for j in range(rnd.choice([3, 3, 3, 4, 4, 5, 6])):
+                vi = -rnd.randint(1, min(nv, 30)) if rnd.random() < 0.5 else rnd.randint(max(1, nv - 40), nv)
+                if rnd.random() < 0.5: toks.append("%d/%d/%d" % (vi, rnd.randint(max(1, nvt - 9), nvt), -rnd.randint(1, min(nvn, 9))))
+                else: toks.append("%d/%d/%d" % (vi, -rnd.randint(1, min(nvt, 9)), rnd.randint(max(1, nvn - 9), nvn)))
+            lines.append("f " + " ".join(toks))
+    return "".join(l + rnd.choice(["\n", "\r\n", "\n", "\r"]) for l in lines)
+
+
+def test_obj_parsed_in_slices_is_identical(workload_root):
+    """Large OBJ files are cut into slices of whole lines parsed by host threads (scene_io.cpp parse_obj); relative indices,
+    groups and the triangulation's vertex count must come out as in one sequential pass (tiny_obj_loader.h:1700-1830)."""
+    sys.path.insert(0, GOLDEN)
+    import objedge
+    root, w = workload_root("mix", width=96, height=72)
+    scene = objedge.write(root)
+    g = np.load(os.path.join(GOLDEN, "scene_objedge.npz"))
+    r = ptb.Renderer(w["config"], device=-1)
+    try:
+        for n in (1, 2, 3, 7, 64):                                    # 64 slices of a 44-line file: most hold one line or none
+            r.set_option("loader_threads", n)
+            r.load_scene(scene, root)
+            tri, mat = r.scene_triangles()
+            assert np.array_equal(tri.view(np.uint32), g["triangles"]) and np.array_equal(mat, g["triangle_material"]), n
+        obj = os.path.join(root, "res", "obj", "objedge.obj")
+        for seed in (1, 2):
+            with open(obj, "w", newline="") as f:
+                f.write(_random_obj(seed, 300))
+            want = None
+            for n in (1, 2, 5, 16, 61):
+                r.set_option("loader_threads", n)
+                r.load_scene(scene, root)
+                tri, mat = r.scene_triangles()
+                if want is None:
+                    want = (tri.copy(), mat.copy())
+                    assert tri.shape[0] > 2000
+                assert np.array_equal(tri.view(np.uint32), want[0].view(np.uint32)) and np.array_equal(mat, want[1]), (seed, n)
+        # the first error in file order wins, whichever slice a later one falls in
+        with open(obj, "w", newline="") as f:
+            f.write("v 0 0 0\nv 1 0 0\nv 0 1 0\nvt 0 0\nvn 0 0 1\nf 1/1/1 2/1/1 3/1/1\nf 1/1/1 2/1/1\n" + "v 1 1 1\n" * 50 + "f 0/1/1 1/1/1 2/1/1\n")
+        msgs = set()
+        for n in (1, 4, 32):
+            r.set_option("loader_threads", n)
+            with pytest.raises(RuntimeError) as e:
+                r.load_scene(scene, root)
+            msgs.add(str(e.value))
+        assert len(msgs) == 1 and "fewer than 3 vertices" in msgs.pop()
+    finally:
+        r.set_option("loader_threads", 0)
+        r.close()
+
+
 def test_builtin_materials_and_default_camera():
     with open(os.path.join(GOLDEN, "kat_host.json")) as f:
         kat = json.load(f)
