@@ -9,7 +9,7 @@ CXX=/usr/bin/g++; [ -x $CXX ] || CXX=g++
 FLAGS="-std=c++17 -O1 -g -fsanitize=address,undefined -fno-omit-frame-pointer -I$SRC -I$REPO/include"
 mkdir -p "$WORK/bin"
 $CXX $FLAGS "$HERE/fuzz_images.cpp" "$SRC/scene_io.cpp" "$SRC/jpeg_decode.cpp" -o "$WORK/bin/images"
-$CXX $FLAGS "$HERE/fuzz_scene.cpp" "$SRC/scene_io.cpp" "$SRC/jpeg_decode.cpp" -o "$WORK/bin/scene"
+$CXX $FLAGS -pthread "$HERE/fuzz_scene.cpp" "$SRC/scene_io.cpp" "$SRC/jpeg_decode.cpp" -o "$WORK/bin/scene"
 $CXX $FLAGS "$HERE/fuzz_config.cpp" "$SRC/scene_io.cpp" "$SRC/jpeg_decode.cpp" -o "$WORK/bin/config"
 $CXX $FLAGS "$HERE/fuzz_checkpoint.cpp" "$SRC/image_out.cpp" -o "$WORK/bin/checkpoint"
 $CXX $FLAGS -fopenmp -pthread "$HERE/fuzz_bvh.cpp" "$SRC/scene_io.cpp" "$SRC/jpeg_decode.cpp" "$SRC/bvh_host.cpp" -o "$WORK/bin/bvh"
