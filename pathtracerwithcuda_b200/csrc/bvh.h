@@ -33,7 +33,7 @@ struct Bvh2
 };
 
 // Top-down binned surface-area-heuristic build (host, multi-threaded).
-void build_bvh2_sah(const std::vector<Triangle>& tris, int max_leaf_size, Bvh2& out, float intersect_cost = 1.5f);
+void build_bvh2_sah(const TriangleArray& tris, int max_leaf_size, Bvh2& out, float intersect_cost = 1.5f);
 
 // GPU layout #1: binary nodes holding BOTH children's boxes (64 bytes = 4 x 16-byte loads).
 //   n[0] = c0.lo.x c0.hi.x c0.lo.y c0.hi.y
@@ -50,7 +50,7 @@ struct GpuBvh2
 	int root_ref = 0;
 };
 
-void flatten_bvh2(const Bvh2& bvh, const std::vector<Triangle>& tris, GpuBvh2& out);
+void flatten_bvh2(const Bvh2& bvh, const TriangleArray& tris, GpuBvh2& out);
 
 // GPU layout #2 (default): compressed 8-wide BVH, 80-byte nodes = 5 x 16-byte loads, after
 // Ylitie, Karras & Laine 2017.  Child boxes are quantised to 8 bits per plane on a per-node grid
@@ -72,6 +72,6 @@ struct GpuBvh8
 	int max_depth = 0;
 };
 
-void build_bvh8(const Bvh2& bvh, const std::vector<Triangle>& tris, GpuBvh8& out);
+void build_bvh8(const Bvh2& bvh, const TriangleArray& tris, GpuBvh8& out);
 
 } // namespace ptb

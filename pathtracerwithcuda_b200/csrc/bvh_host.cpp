@@ -154,7 +154,7 @@ struct Builder
 
 } // namespace
 
-void build_bvh2_sah(const std::vector<Triangle>& tris, int max_leaf_size, Bvh2& out, float intersect_cost)
+void build_bvh2_sah(const TriangleArray& tris, int max_leaf_size, Bvh2& out, float intersect_cost)
 {
 	const float kIntersectCost = intersect_cost;
 	out.nodes.clear();
@@ -209,7 +209,7 @@ static inline float pad_up(float v)
 	return v + m;
 }
 
-void flatten_bvh2(const Bvh2& bvh, const std::vector<Triangle>& tris, GpuBvh2& out)
+void flatten_bvh2(const Bvh2& bvh, const TriangleArray& tris, GpuBvh2& out)
 {
 	out.nodes.clear();
 	out.tris.clear();
@@ -298,11 +298,11 @@ struct WideChild
 struct WideBuilder
 {
 	const Bvh2& bvh;
-	const std::vector<Triangle>& tris;
+	const TriangleArray& tris;
 	GpuBvh8& out;
 	int max_depth = 0;
 
-	WideBuilder(const Bvh2& b, const std::vector<Triangle>& t, GpuBvh8& o) : bvh(b), tris(t), out(o) {}
+	WideBuilder(const Bvh2& b, const TriangleArray& t, GpuBvh8& o) : bvh(b), tris(t), out(o) {}
 
 	// open the inner child with the largest surface area until 8 children (or only leaves remain)
 	void gather_children(int node2, std::vector<int>& children) const
@@ -483,7 +483,7 @@ struct WideBuilder
 
 } // namespace
 
-void build_bvh8(const Bvh2& bvh, const std::vector<Triangle>& tris, GpuBvh8& out)
+void build_bvh8(const Bvh2& bvh, const TriangleArray& tris, GpuBvh8& out)
 {
 	WideBuilder b(bvh, tris, out);
 	b.build();

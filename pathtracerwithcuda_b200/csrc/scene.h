@@ -52,6 +52,19 @@ struct Triangle
 };
 static_assert(sizeof(Triangle) == 96, "24 floats");
 
+// Triangle arrays run to hundreds of MB: resize() must not zero-fill them on one thread before the loader's host threads
+// write every element anyway (default-initialising allocator: `resize(n)` leaves new elements uninitialised, `resize(n, x)`,
+// push_back and copies behave as usual).
+template <class T>
+struct DefaultInitAllocator : std::allocator<T>
+{
+	template <class U> struct rebind { using other = DefaultInitAllocator<U>; };
+	using std::allocator<T>::allocator;
+	template <class U> void construct(U* p) noexcept(std::is_nothrow_default_constructible<U>::value) { ::new (static_cast<void*>(p)) U; }
+	template <class U, class... Args> void construct(U* p, Args&&... args) { ::new (static_cast<void*>(p)) U(std::forward<Args>(args)...); }
+};
+using TriangleArray = std::vector<Triangle, DefaultInitAllocator<Triangle>>;
+
 struct Sphere
 {
 	Vec3 center;
@@ -77,8 +90,8 @@ struct MeshInfo
 
 struct HostScene
 {
-	std::vector<Triangle> triangles;       // global order: meshes in JSON order, shapes, faces
-	std::vector<Triangle> local_triangles; // the reference's m_triangles: rotation applied, translate/scale not (triangle_mesh.cpp:150-185)
+	TriangleArray triangles;               // global order: meshes in JSON order, shapes, faces
+	TriangleArray local_triangles;         // the reference's m_triangles: rotation applied, translate/scale not (triangle_mesh.cpp:150-185)
 	std::vector<MeshInfo> meshes;
 	std::vector<int32_t> triangle_material; // index into `materials`
 	std::vector<ptb_material> materials;    // per-mesh private copies, concatenated

@@ -29,7 +29,14 @@
 #include <sstream>
 #include <thread>
 #include <atomic>
+#include <chrono>
 #include <dirent.h>
+#include <fcntl.h>
+#include <memory>
+#include <type_traits>
+#include <sys/stat.h>
+#include <unistd.h>
+#include <cerrno>
 
 namespace ptb
 {
@@ -1005,16 +1012,6 @@ int point_in_polygon(int nvert, const float* vertx, const float* verty, float te
 
 // tiny_obj_loader.h:985-1175 with triangulate=true: project on the dominant plane of the first
 // non-degenerate corner, then clip ears; a triangle passes through untouched.
-// Faces of the current group, flat: indices back to back, `start` marks where each face begins (one allocation per group,
-// not one per face — a 1 M-triangle mesh is 1 M faces).
-struct FaceGroup
-{
-	std::vector<ObjIndex> idx;
-	std::vector<size_t> start;
-	bool empty() const { return start.empty(); }
-	void clear() { idx.clear(); start.clear(); }
-};
-
 bool emit_face(ObjShape& shape, const ObjIndex* face_begin, size_t face_size, const std::vector<float>& v, size_t n_vertices)
 {
 	// tinyobj triangulates with the vertices read so far (n_vertices of them) and does not check the indices; a face pointing
@@ -1102,26 +1099,33 @@ bool emit_face(ObjShape& shape, const ObjIndex* face_begin, size_t face_size, co
 	return true;
 }
 
-bool flush_group(ObjShape& shape, FaceGroup& group, const std::vector<float>& v, size_t n_vertices)
+#ifdef PTB_LOAD_TRACE   // phase timings of the loader on stderr (diagnostic builds only: tools/load_time.py notes)
+struct LoadTrace
 {
-	for (size_t f = 0; f < group.start.size(); f++)
+	std::chrono::steady_clock::time_point t = std::chrono::steady_clock::now();
+	void mark(const char* what)
 	{
-		const size_t b = group.start[f], e = f + 1 < group.start.size() ? group.start[f + 1] : group.idx.size();
-		if (!emit_face(shape, group.idx.data() + b, e - b, v, n_vertices)) { group.clear(); return false; }
+		auto n = std::chrono::steady_clock::now();
+		fprintf(stderr, "[load] %-28s %.3f s\n", what, std::chrono::duration<double>(n - t).count());
+		t = n;
 	}
-	group.clear();
-	return true;
-}
+};
+#define PTB_TRACE_BEGIN LoadTrace load_trace
+#define PTB_TRACE(what) load_trace.mark(what)
+#else
+#define PTB_TRACE_BEGIN
+#define PTB_TRACE(what)
+#endif
 
 int g_loader_threads = 0;   // 0: by file size and host cores (set_loader_threads / option "loader_threads")
 
 // One slice of the file (whole lines), parsed by one host thread.  Negative (relative) face indices need the number of
 // v / vn / vt lines before the face, so a first pass counts them per slice and a prefix sum gives every slice its base.
-struct ObjEvent
+struct ObjMark
 {
-	int kind;              // 0 face, 1 `g`, 2 `o`, 3 parse error (message in the slice)
-	size_t begin, size;    // face: range in the slice's idx
-	size_t n_vertices;     // vertices read before this line (what tinyobj's triangulation would see)
+	int kind;              // 1 `g`, 2 `o`, 3 parse error (message in the slice)
+	size_t face_index;     // faces of this slice recorded before the line
+	size_t n_vertices;     // vertices read before the line: what tinyobj's triangulation sees when the line flushes the group
 };
 
 struct ObjSlice
@@ -1131,13 +1135,57 @@ struct ObjSlice
 	size_t base_v = 0, base_vn = 0, base_vt = 0;
 	std::vector<float> v, vn, vt;
 	std::vector<ObjIndex> idx;
-	std::vector<ObjEvent> events;
+	std::vector<size_t> face_start;                     // face f = idx[face_start[f] .. face_start[f + 1]) (idx.size() after the last)
+	std::vector<ObjMark> marks;
 	std::string error;
 };
 
 // safeGetline: lines end at \n, \r\n or a lone \r.  A line is parsed where it lies: its terminator becomes a NUL (an embedded NUL
 // simply ends the line early, as it did for a copied string's c_str()).  Returns the start of the line's first token or nullptr.
-inline const char* next_line(std::string& text, size_t& pos, size_t end)
+// The OBJ text: one uninitialised allocation of file size + 1 (terminating NUL), filled by pread from a few host threads — a 190 MB
+// mesh file otherwise spends more time in the zero-fill of a std::string and its page faults than in the read itself.
+struct TextBuffer
+{
+	std::unique_ptr<char[]> buf;
+	size_t size = 0;      // bytes of the file; buf[size] = NUL
+	char* data() { return buf.get(); }
+	const char* data() const { return buf.get(); }
+	char& operator[](size_t i) { return buf[i]; }
+	const char& operator[](size_t i) const { return buf[i]; }
+};
+
+bool read_text_buffer(const std::string& path, TextBuffer& out)
+{
+	const int fd = open(path.c_str(), O_RDONLY);
+	if (fd < 0) return false;
+	struct stat st;
+	if (fstat(fd, &st) != 0 || !S_ISREG(st.st_mode) || st.st_size < 0) { close(fd); return false; }
+	const size_t size = (size_t)st.st_size;
+	out.buf.reset(new (std::nothrow) char[size + 1]);
+	if (!out.buf) { close(fd); return false; }
+	out.size = size;
+	out.buf[size] = '\0';
+	const size_t hw = std::max(1u, std::thread::hardware_concurrency());
+	const size_t n_threads = size < (16u << 20) ? 1 : std::min<size_t>(8, hw);
+	std::atomic<bool> ok(true);
+	auto read_range = [&](size_t begin, size_t end)
+	{
+		while (begin < end)
+		{
+			const ssize_t got = pread(fd, out.buf.get() + begin, end - begin, (off_t)begin);
+			if (got <= 0) { if (got < 0 && errno == EINTR) continue; ok = false; return; }     // 0: the file shrank under us
+			begin += (size_t)got;
+		}
+	};
+	std::vector<std::thread> workers;
+	for (size_t k = 1; k < n_threads; k++) workers.emplace_back(read_range, size * k / n_threads, size * (k + 1) / n_threads);
+	read_range(0, size / n_threads);
+	for (auto& th : workers) th.join();
+	close(fd);
+	return ok;
+}
+
+inline const char* next_line(TextBuffer& text, size_t& pos, size_t end)
 {
 	size_t e = pos;
 	while (e < end && text[e] != '\n' && text[e] != '\r') e++;
@@ -1152,7 +1200,7 @@ inline const char* next_line(std::string& text, size_t& pos, size_t end)
 	return token;
 }
 
-void count_slice(const std::string& text, ObjSlice& sl)
+void count_slice(const TextBuffer& text, ObjSlice& sl)
 {
 	// the same classification as parse_slice, without touching the text
 	size_t pos = sl.begin;
@@ -1174,7 +1222,7 @@ void count_slice(const std::string& text, ObjSlice& sl)
 	}
 }
 
-void parse_slice(std::string& text, ObjSlice& sl, const std::string& path)
+void parse_slice(TextBuffer& text, ObjSlice& sl, const std::string& path)
 {
 	size_t pos = sl.begin;
 	sl.v.reserve(sl.count_v * 3); sl.vn.reserve(sl.count_vn * 3); sl.vt.reserve(sl.count_vt * 2);
@@ -1215,35 +1263,38 @@ void parse_slice(std::string& text, ObjSlice& sl, const std::string& path)
 				if (!parse_triple(&token, (int)n_vertices, (int)(sl.base_vn + sl.vn.size() / 3), (int)(sl.base_vt + sl.vt.size() / 2), &vi))
 				{
 					sl.error = "[TinyObj]Failed parse `f' line(e.g. zero value for face index).";
-					sl.events.push_back(ObjEvent{ 3, 0, 0, n_vertices });
+					sl.idx.resize(face_begin);     // the last recorded face ends where the failed one began
+					sl.marks.push_back(ObjMark{ 3, sl.face_start.size(), n_vertices });
 					return;
 				}
 				sl.idx.push_back(vi);
 				token += strspn(token, " \t\r");
 			}
 			const size_t face_size = sl.idx.size() - face_begin;
-			if (face_size >= 3) sl.events.push_back(ObjEvent{ 0, face_begin, face_size, n_vertices });
+			if (face_size >= 3) sl.face_start.push_back(face_begin);
 			else if (face_size != 0)
 			{
 				sl.error = "[Error]" + path + " has a face with fewer than 3 vertices";
-				sl.events.push_back(ObjEvent{ 3, 0, 0, n_vertices });
+				sl.idx.resize(face_begin);
+				sl.marks.push_back(ObjMark{ 3, sl.face_start.size(), n_vertices });
 				return;
 			}
 			continue;
 		}
 		// `usemtl`: no .mtl files ship, every name maps to material id -1, so the per-face material
 		// never changes and the statement is a no-op (tiny_obj_loader.h:1779-1803).
-		if (token[0] == 'g' && is_space(token[1])) { sl.events.push_back(ObjEvent{ 1, 0, 0, n_vertices }); continue; }
-		if (token[0] == 'o' && is_space(token[1])) { sl.events.push_back(ObjEvent{ 2, 0, 0, n_vertices }); continue; }
+		if (token[0] == 'g' && is_space(token[1])) { sl.marks.push_back(ObjMark{ 1, sl.face_start.size(), n_vertices }); continue; }
+		if (token[0] == 'o' && is_space(token[1])) { sl.marks.push_back(ObjMark{ 2, sl.face_start.size(), n_vertices }); continue; }
 	}
 }
 
 bool parse_obj(const std::string& path, ObjData& out)
 {
-	std::string text;
-	if (!read_text_file(path, text)) { set_error("[Info]Load file " + path + " failed: Cannot open file"); return false; }
-	text.push_back('\0');             // the last line is terminated like every other (lines are parsed in place)
-	const size_t text_size = text.size() - 1;
+	PTB_TRACE_BEGIN;
+	TextBuffer text;                  // NUL-terminated: the last line is terminated like every other (lines are parsed in place)
+	if (!read_text_buffer(path, text)) { set_error("[Info]Load file " + path + " failed: Cannot open file"); return false; }
+	const size_t text_size = text.size;
+	PTB_TRACE("obj read");
 
 	// slices of whole lines, cut after a '\n' (a file of lone-'\r' line ends stays one slice)
 	const size_t hw = std::max(1u, std::thread::hardware_concurrency());
@@ -1269,6 +1320,7 @@ bool parse_obj(const std::string& path, ObjData& out)
 		for (auto& th : workers) th.join();
 	};
 	run([&](ObjSlice& sl) { count_slice(text, sl); });
+	PTB_TRACE("obj count");
 	for (size_t k = 1; k < slices.size(); k++)
 	{
 		slices[k].base_v = slices[k - 1].base_v + slices[k - 1].count_v;
@@ -1276,6 +1328,7 @@ bool parse_obj(const std::string& path, ObjData& out)
 		slices[k].base_vt = slices[k - 1].base_vt + slices[k - 1].count_vt;
 	}
 	run([&](ObjSlice& sl) { parse_slice(text, sl, path); });
+	PTB_TRACE("obj parse slices");
 
 	// a slice that stopped at a parse error read fewer v / vn / vt lines than counted; everything after it is discarded anyway
 	for (const ObjSlice& sl : slices)
@@ -1285,40 +1338,81 @@ bool parse_obj(const std::string& path, ObjData& out)
 		out.vt.insert(out.vt.end(), sl.vt.begin(), sl.vt.end());
 		if (!sl.error.empty()) break;
 	}
-	// groups, shapes and triangulation in file order
-	FaceGroup group;
-	ObjShape shape;
-	size_t n_vertices = 0;
-	for (const ObjSlice& sl : slices)
+	PTB_TRACE("obj merge vertices");
+	// Groups, shapes and triangulation in file order.  A group is flushed by the next `g` / `o` line or the end of the file and
+	// is triangulated with the vertices read up to there; its faces may lie in several slices: one run per slice.  The runs are
+	// triangulated by host threads (each face is independent), then appended to their shapes in order.
+	struct Run { size_t slice, f0, f1, n_vertices; ObjShape tris; bool failed = false; std::string error; };
+	struct Group { size_t run0 = 0, run1 = 0; int kind = 0; };     // kind: the mark that flushed it (1 `g`, 2 `o`), 0 = end of file
+	std::vector<Run> runs;
+	std::vector<Group> groups;
+	const std::string* parse_error = nullptr;     // a slice that stopped at a parse error ends the file there (the open group is never flushed)
 	{
-		for (const ObjEvent& ev : sl.events)
+		Group g;
+		size_t n_vertices = 0;
+		for (size_t k = 0; k < slices.size() && !parse_error; k++)
 		{
-			n_vertices = ev.n_vertices;
-			if (ev.kind == 0)
+			const ObjSlice& sl = slices[k];
+			size_t f_cur = 0;
+			for (const ObjMark& m : sl.marks)
 			{
-				group.start.push_back(group.idx.size());
-				group.idx.insert(group.idx.end(), sl.idx.begin() + ev.begin, sl.idx.begin() + ev.begin + ev.size);
+				if (m.face_index > f_cur) { Run r; r.slice = k; r.f0 = f_cur; r.f1 = m.face_index; r.n_vertices = 0; runs.push_back(std::move(r)); f_cur = m.face_index; }
+				if (m.kind == 3) { parse_error = &sl.error; break; }
+				g.run1 = runs.size(); g.kind = m.kind;
+				for (size_t r = g.run0; r < g.run1; r++) runs[r].n_vertices = m.n_vertices;
+				groups.push_back(g);
+				g = Group(); g.run0 = g.run1 = runs.size();
 			}
-			else if (ev.kind == 1)
-			{
-				if (!flush_group(shape, group, out.v, n_vertices)) return false;
-				if (!shape.indices.empty()) out.shapes.push_back(shape);
-				shape = ObjShape();
-			}
-			else if (ev.kind == 2)
-			{
-				bool had_faces = !group.empty();
-				if (!flush_group(shape, group, out.v, n_vertices)) return false;
-				if (had_faces) out.shapes.push_back(shape);
-				shape = ObjShape();
-			}
-			else { set_error(sl.error); return false; }
+			if (parse_error) break;
+			if (sl.face_start.size() > f_cur) { Run r; r.slice = k; r.f0 = f_cur; r.f1 = sl.face_start.size(); r.n_vertices = 0; runs.push_back(std::move(r)); }
+			n_vertices = sl.base_v + sl.v.size() / 3;
 		}
-		n_vertices = sl.base_v + sl.v.size() / 3;
+		if (!parse_error)
+		{
+			g.run1 = runs.size(); g.kind = 0;
+			for (size_t r = g.run0; r < g.run1; r++) runs[r].n_vertices = n_vertices;
+			groups.push_back(g);
+		}
 	}
-	bool had_faces = !group.empty();
-	if (!flush_group(shape, group, out.v, n_vertices)) return false;
-	if (had_faces || !shape.indices.empty()) out.shapes.push_back(shape);
+	const size_t flushed_runs = groups.empty() ? 0 : groups.back().run1;
+	{
+		std::atomic<size_t> next(0);
+		auto work = [&]
+		{
+			for (size_t i = next++; i < flushed_runs; i = next++)
+			{
+				Run& r = runs[i];
+				const ObjSlice& sl = slices[r.slice];
+				r.tris.indices.reserve((sl.face_start[r.f1 - 1] - sl.face_start[r.f0]) + 3);     // exact for triangles; polygons grow it
+				for (size_t f = r.f0; f < r.f1; f++)
+				{
+					const size_t b = sl.face_start[f], e = f + 1 < sl.face_start.size() ? sl.face_start[f + 1] : sl.idx.size();
+					if (!emit_face(r.tris, sl.idx.data() + b, e - b, out.v, r.n_vertices)) { r.failed = true; r.error = last_error(); break; }
+				}
+			}
+		};
+		std::vector<std::thread> workers;
+		for (size_t k = 1; k < slices.size() && k < flushed_runs; k++) workers.emplace_back(work);
+		work();
+		for (auto& th : workers) th.join();
+	}
+	ObjShape shape;
+	for (const Group& g : groups)
+	{
+		for (size_t r = g.run0; r < g.run1; r++)
+		{
+			if (runs[r].failed) { set_error(runs[r].error); return false; }
+			if (shape.indices.empty()) shape.indices = std::move(runs[r].tris.indices);
+			else shape.indices.insert(shape.indices.end(), runs[r].tris.indices.begin(), runs[r].tris.indices.end());
+			runs[r].tris = ObjShape();
+		}
+		const bool had_faces = g.run1 > g.run0;
+		if (g.kind == 1) { if (!shape.indices.empty()) out.shapes.push_back(std::move(shape)); shape = ObjShape(); }
+		else if (g.kind == 2) { if (had_faces) out.shapes.push_back(std::move(shape)); shape = ObjShape(); }
+		else if (had_faces || !shape.indices.empty()) out.shapes.push_back(std::move(shape));
+	}
+	if (parse_error) { set_error(*parse_error); return false; }
+	PTB_TRACE("obj groups + triangulation");
 	return true;
 }
 
@@ -1327,12 +1421,32 @@ bool parse_obj(const std::string& path, ObjData& out)
 // triangle_mesh::load_obj + create_mesh_device_data for one mesh (triangle_mesh.cpp:8-213,558-655)
 static bool mesh_in_range(const HostScene& scene, const MeshInfo& m);
 
-static bool append_mesh(HostScene& scene, const std::string& path, const Vec3& position, const Vec3& scale_v, const Vec3& rotate_v,
-	std::vector<ptb_material> mats)
+// A mesh between its two load steps: the OBJ text parsed (read_mesh), triangles not yet appended to the scene (append_mesh).
+// load_scene reads every mesh first so the scene's triangle arrays are allocated once, at their final size.
+struct PendingMesh
 {
-	if (mats.empty()) { set_error("[Error]Mesh has no material"); return false; }
 	ObjData obj;
-	if (!parse_obj(path, obj)) return false;
+	bool ok = false;
+	std::string error;       // of the failed step; reported when the meshes before this one have been appended
+	size_t triangle_count() const { size_t n = 0; for (const ObjShape& sh : obj.shapes) n += sh.indices.size() / 3; return n; }
+};
+
+static void read_mesh(const std::string& path, size_t mat_num, PendingMesh& out)
+{
+	out.ok = false;
+	if (mat_num == 0) { out.error = "[Error]Mesh has no material"; return; }
+	PTB_TRACE_BEGIN;
+	if (!parse_obj(path, out.obj)) { out.error = last_error(); return; }
+	PTB_TRACE("parse_obj total");
+	out.ok = true;
+}
+
+static bool append_mesh(HostScene& scene, const std::string& path, const Vec3& position, const Vec3& scale_v, const Vec3& rotate_v,
+	std::vector<ptb_material> mats, const PendingMesh& pending)
+{
+	if (!pending.ok) { set_error(pending.error); return false; }
+	const ObjData& obj = pending.obj;
+	PTB_TRACE_BEGIN;
 	if (obj.vn.empty()) { set_error("[Error]Mesh does not have normal! (" + path + ")"); return false; }
 	const int mat_num = (int)mats.size();
 	const bool has_uv = !obj.vt.empty();
@@ -1360,6 +1474,7 @@ static bool append_mesh(HostScene& scene, const std::string& path, const Vec3& p
 	scene.triangles.resize((size_t)triangle_base + total);
 	scene.local_triangles.resize((size_t)triangle_base + total);
 	scene.triangle_material.resize((size_t)triangle_base + total);
+	PTB_TRACE("mesh resize");
 	std::atomic<bool> bad_index(false);
 	auto fill = [&](size_t t_begin, size_t t_end)
 	{
@@ -1409,6 +1524,7 @@ static bool append_mesh(HostScene& scene, const std::string& path, const Vec3& p
 		fill(0, total / n_threads);
 		for (auto& th : workers) th.join();
 	}
+	PTB_TRACE("mesh fill world triangles");
 	if (bad_index)
 	{
 		scene.triangles.resize((size_t)triangle_base); scene.local_triangles.resize((size_t)triangle_base); scene.triangle_material.resize((size_t)triangle_base);
@@ -1429,6 +1545,7 @@ static bool append_mesh(HostScene& scene, const std::string& path, const Vec3& p
 	info.position = position; info.scale = scale_v; info.rotate = rotate_v; info.rotate_applied = rotate_v;
 	if (!mesh_in_range(scene, info)) { set_error("[Error]Mesh " + path + " has vertices outside the supported range (non-finite or beyond 1e18)"); return false; }
 	scene.meshes.push_back(info);
+	PTB_TRACE("mesh range check");
 	return true;
 }
 
@@ -1706,11 +1823,24 @@ bool load_scene(const std::string& scene_json_path, const std::string& asset_roo
 	for (auto& m : meshes) for (auto& n : m.mats) if (!materials.count(n)) { missing = true; missing_names += " <" + n + ">"; }
 	if (missing) { set_error("[Error]Material" + missing_names + " not found!"); return false; }
 
-	for (auto& m : meshes)
+	// every mesh file is parsed first (stopping at the first that fails), then the triangle arrays are sized once and the meshes
+	// appended in order: results and the error reported are those of loading the meshes one after the other
+	std::vector<PendingMesh> pending(meshes.size());
+	size_t total_triangles = 0;
+	for (size_t i = 0; i < meshes.size(); i++)
 	{
+		read_mesh(join_path(asset_root, meshes[i].path), meshes[i].mats.size(), pending[i]);
+		if (!pending[i].ok) break;
+		total_triangles += pending[i].triangle_count();
+	}
+	scene.triangles.reserve(total_triangles); scene.local_triangles.reserve(total_triangles); scene.triangle_material.reserve(total_triangles);
+	for (size_t i = 0; i < meshes.size(); i++)
+	{
+		auto& m = meshes[i];
 		std::vector<ptb_material> mesh_mats;
 		for (auto& n : m.mats) mesh_mats.push_back(materials[n]);
-		if (!append_mesh(scene, join_path(asset_root, m.path), m.position, m.scale, m.rotate, mesh_mats)) return false;
+		if (!append_mesh(scene, join_path(asset_root, m.path), m.position, m.scale, m.rotate, mesh_mats, pending[i])) return false;
+		pending[i].obj = ObjData();     // the parsed text of a 2.5 M-triangle mesh holds ~150 MB
 	}
 	for (size_t i = 0; i < scene.spheres.size(); i++) scene.spheres[i].mat = materials[sphere_materials[i]];
 	return true;
