@@ -67,3 +67,69 @@ def test_reference_host_code_drives_our_kernel_symbol(name):
     # bit-equality of the 3-pass sum is informative only (ptxas fuses mul+add differently as register limits change);
     # the contract is the 1e-3 relative tolerance asserted above
     assert rep["u8_max"] <= 1 and rep["bit_equal"] >= 0.95, rep
+
+
+LOOKAHEAD_WORKER = r'''
+import ctypes, json, os, sys, tempfile
+import numpy as np
+sys.path.insert(0, %(repo)r)
+from oracle import refharness as rh
+from pathtracerwithcuda_b200 import procedural as pr, api
+out_path = sys.argv[1]
+root = tempfile.mkdtemp(prefix="ptb_compat_la_")
+w = pr.make_workload(root, "mix", width=96, height=72)
+rh.link_backslash_names(root)
+ref = rh.RefLib(host_only=False)
+ref.open(root, config_rel=w["config_rel"], scene=w["scene_name"])
+cam = ref.default_camera(w["width"], w["height"], w["aperture"], w["focal"])
+ref.set_camera(cam)
+L = api.load_library()
+vp, ci = ctypes.c_void_p, ctypes.c_int
+L.path_tracer_kernel.argtypes = [ci, vp, vp, ci, vp, ci, vp, vp, ci, vp, vp, vp, vp, vp, vp, vp, vp, vp]
+L.path_tracer_kernel.restype = None
+def call(p):
+    args = (ctypes.c_void_p * 18)()
+    ref.lib.ref_kernel_args(args)
+    iv = lambda k: int(args[k] or 0)
+    L.path_tracer_kernel(iv(0), args[1], args[2], iv(3), args[4], iv(5), args[6], args[7], p, args[9], args[10], args[11], args[12],
+                         args[13], args[14], args[15], args[16], args[17])
+snaps = {}
+def snap(tag):
+    snaps[tag + "_sum"] = ref.image_f32().copy(); snaps[tag + "_u8"] = ref.image_u8().copy(); snaps[tag + "_last"] = ref.last_pass_f32().copy()
+ref.clear()
+for p in range(1, 12): call(p)                      # crosses a batch boundary of the default look-ahead (8)
+snap("p11")
+cam2 = np.array(cam, np.float32).copy(); cam2[0] += 0.5     # the eye moves, the accumulation carries on (no clear)
+ref.set_camera(cam2)
+for p in range(12, 22): call(p)
+snap("moved_p21")
+call(23); call(24)                                   # a skipped pass number
+snap("skipped_p24")
+ref.set_camera(cam)
+ref.clear()
+for p in range(1, 20): call(p)                       # restart: pass 1 overwrites
+snap("restart_p19")
+np.savez(out_path, **snaps)
+'''
+
+
+@pytest.mark.skipif(not os.path.exists(REF_LIB), reason="oracle/_ref/libptref.so not present on this box")
+def test_lookahead_leaves_what_one_pass_per_call_leaves(tmp_path):
+    """csrc/compat.inc renders passes ahead of the calls that ask for them; after every call the caller's buffers must hold
+    exactly what the one-pass-per-call path (PTB_COMPAT_LOOKAHEAD=1) leaves — also across a camera move without clear(),
+    a skipped pass number and a restart."""
+    script = str(tmp_path / "worker.py")
+    with open(script, "w") as f:
+        f.write(LOOKAHEAD_WORKER % {"repo": REPO})
+    results = {}
+    for la in ("1", "8", "3"):
+        out_path = str(tmp_path / ("la%s.npz" % la))
+        env = dict(os.environ, PTB_COMPAT_LOOKAHEAD=la)
+        out = subprocess.run([sys.executable, script, out_path], capture_output=True, text=True, env=env)
+        assert out.returncode == 0, out.stderr[-3000:]
+        results[la] = np.load(out_path)
+    base = results["1"]
+    assert float(base["p11_sum"].mean()) > 0 and not np.array_equal(base["p11_sum"], base["moved_p21_sum"])
+    for la in ("8", "3"):
+        for key in base.files:
+            assert np.array_equal(base[key].view(np.uint8), results[la][key].view(np.uint8)), (la, key)

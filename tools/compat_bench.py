@@ -2,7 +2,8 @@
 """Drop-in timing (GPU box): the UNMODIFIED reference host code (oracle/_ref/libptref.so: scene_parser, triangle_mesh, BVH build,
 image, config_parser) builds its managed AoS scene once; then the SAME 18 arguments of Core/path_tracer.cpp:48-67 are handed,
 one synchronous call per pass, first to the reference's own `path_tracer_kernel` and then to libptb200.so's symbol of that name.
-    python tools/compat_bench.py [workload=c2] [passes=64] [steps=4]
+    python tools/compat_bench.py [workload=c2] [passes=64] [steps=4] [reference_steps=steps]
+PTB_COMPAT_LOOKAHEAD=1 switches the look-ahead of the drop-in symbol off (csrc/compat.inc).
 Prints one JSON line: Msamples/s of both and their ratio."""
 import ctypes, json, os, sys, tempfile, time
 import numpy as np
@@ -24,8 +25,11 @@ ref.set_camera(ref.default_camera(w["width"], w["height"], w["aperture"], w["foc
 px = w["width"] * w["height"]
 
 # (a) the reference's kernel, managed memory prefetched (its most favourable condition, as in bench.py --impl reference)
-ref.clear(); ref.render(2); ref.prefetch(); ref.render(passes); ref.prefetch()
-ref_ms = [ref.render(passes) * 1e3 for _ in range(steps)]
+ref_steps = int(sys.argv[4]) if len(sys.argv) > 4 else steps      # 0: skip the reference's timing (its image is still rendered for the comparison)
+ref.clear(); ref.render(2); ref.prefetch()
+if ref_steps:
+    ref.render(passes); ref.prefetch()
+ref_ms = [ref.render(passes) * 1e3 for _ in range(ref_steps)] or [float("nan")]
 ref.clear(); ref.render(passes)
 a_sum = ref.image_f32().copy()
 
@@ -59,7 +63,7 @@ for _ in range(steps):
     ours_ms.append((time.perf_counter() - t0) * 1e3)
 sys.stdout.flush(); os.dup2(saved, 1)
 rate = lambda ms: px * passes / (ms / 1e3) / 1e6
-print(json.dumps({"workload": name, "resolution": [w["width"], w["height"]], "passes_per_step": passes, "steps": steps,
+print(json.dumps({"workload": name, "lookahead": os.environ.get("PTB_COMPAT_LOOKAHEAD", "default (8)"), "resolution": [w["width"], w["height"]], "passes_per_step": passes, "steps": steps,
                   "reference_kernel_Msamples_s": {"median": rate(float(np.median(ref_ms))), "best": rate(min(ref_ms)), "step_ms": ref_ms},
                   "ptb200_symbol_Msamples_s": {"median": rate(float(np.median(ours_ms))), "best": rate(min(ours_ms)), "step_ms": ours_ms,
                                                "first_call_ms_ingest_build_pass": first_ms},
