@@ -51,21 +51,38 @@ def call(p):
 ref.clear()
 t0 = time.perf_counter(); call(1); first_ms = (time.perf_counter() - t0) * 1e3        # ingest + BVH build + first pass
 p = 1
-for _ in range(passes - 1):
-    p += 1; call(p)
-b_sum = ref.image_f32().copy()
-rel = np.abs(a_sum.astype(np.float64) - b_sum) / np.maximum(np.abs(a_sum), 1e-3)
+for _ in range(passes - 1):                    # warm-up, then straight into the timed steps: the look-ahead is in steady state at
+    p += 1; call(p)                            # both ends of the timed region (a host pause before it would hand it finished batches)
 ours_ms = []
 for _ in range(steps):
     t0 = time.perf_counter()
     for _ in range(passes):
         p += 1; call(p)
     ours_ms.append((time.perf_counter() - t0) * 1e3)
+ref.clear()
+for q in range(1, passes + 1):
+    call(q)
+b_sum = ref.image_f32().copy()
+rel = np.abs(a_sum.astype(np.float64) - b_sum) / np.maximum(np.abs(a_sum), 1e-3)
+# (c) for scale: the native C ABI on the same workload in the same process (8 passes x 3 streams in flight, like the look-ahead)
+import pathtracerwithcuda_b200 as ptb
+nr = ptb.Renderer(w["config"], device=0)
+nr.set_option("passes_in_flight", 8); nr.set_option("streams_in_flight", 3)
+nr.load_scene(w["scene"], root)
+if w["aperture"] >= 0 or w["focal"] >= 0:
+    nr.set_camera(ptb.default_camera(w["width"], w["height"], w["aperture"], w["focal"]))
+nr.render(passes)
+native_ms = []
+for _ in range(steps):
+    t0 = time.perf_counter(); nr.render(passes); native_ms.append((time.perf_counter() - t0) * 1e3)
+native_segments = nr.stats()["ray_segments"]
+nr.close()
 sys.stdout.flush(); os.dup2(saved, 1)
 rate = lambda ms: px * passes / (ms / 1e3) / 1e6
 print(json.dumps({"workload": name, "lookahead": os.environ.get("PTB_COMPAT_LOOKAHEAD", "default (8)"), "resolution": [w["width"], w["height"]], "passes_per_step": passes, "steps": steps,
                   "reference_kernel_Msamples_s": {"median": rate(float(np.median(ref_ms))), "best": rate(min(ref_ms)), "step_ms": ref_ms},
                   "ptb200_symbol_Msamples_s": {"median": rate(float(np.median(ours_ms))), "best": rate(min(ours_ms)), "step_ms": ours_ms,
                                                "first_call_ms_ingest_build_pass": first_ms},
+                  "ptb200_native_abi_Msamples_s": {"median": rate(float(np.median(native_ms))), "step_ms": native_ms, "ray_segments_per_step": native_segments},
                   "ratio_median": rate(float(np.median(ours_ms))) / rate(float(np.median(ref_ms))), "ratio_best_vs_best": rate(min(ours_ms)) / rate(min(ref_ms)),
                   "image_after_%d_passes" % passes: {"outliers_1e-3": float((rel > 1e-3).mean()), "p999_rel": float(np.quantile(rel, 0.999))}}))
