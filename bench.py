@@ -336,6 +336,12 @@ def run_ptb200(args, w, root, rank, local_rank, world):
         seg_per_launch = serial_segments / max(serial_launches, 1)
         avg_launch_ms = serial_extend_ms / max(serial_launches, 1)
         achieved = seg_per_launch * bytes_per_seg / (avg_launch_ms / 1e3) / 1e9 if avg_launch_ms > 0 else None
+        # the co-bound SURVEY.md 8d names: algorithmic FP32 work of the same kernel — 25 flop per box tested (2 per binary node, 8 per wide
+        # node), 51 per triangle test — against the non-tensor FP32 peak at the SM clock held during the timed region (148 SMs x 128 lanes x 2)
+        flop_per_seg = nodes_per_seg * 2 * 25.0 + wide_per_seg * 8 * 25.0 + tris_per_seg * 51.0
+        sm_mhz = (clocks or {}).get("sm_mhz") or (clocks or {}).get("sm_max_mhz")
+        fp32_peak = 148 * 128 * 2 * sm_mhz * 1e6 / 1e12 if sm_mhz else None
+        fp32_achieved = seg_per_launch * flop_per_seg / (avg_launch_ms / 1e3) / 1e12 if avg_launch_ms > 0 else None
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
                 "data": "synthetic",
@@ -362,6 +368,9 @@ def run_ptb200(args, w, root, rank, local_rank, world):
                              "ncu_limiters": {"source": "profiles/r01i_extend_ncu_summary.md (d0 / d1, binary-tree kernel)", "issue_active_pct": [68.2, 61.9],
                                               "active_lanes_per_instruction": [22.1, 18.9], "stall_long_scoreboard_per_issue": [4.2, 5.85],
                                               "l1_hit_pct": [71.7, 64.8], "lsu_wavefronts_pct_of_peak": [74.7, 65.5], "alu_pipe_pct": [61.4, 53.2]},
+                             "fp32": {"flop_per_segment": flop_per_seg, "achieved_TFLOPs": fp32_achieved, "peak_TFLOPs": fp32_peak,
+                                      "frac": (fp32_achieved / fp32_peak) if fp32_achieved and fp32_peak else None,
+                                      "note": "algorithmic slab + Moller-Trumbore flops only; the kernel's instruction mix is min/max/select/compare-heavy (ALU pipe 61 %, FMA pipe 21 % in ncu)"},
                              "extend_share_of_serial_step": serial_extend_ms / serial_step_ms if serial_step_ms else None,
                              "Mrays_s_extend_serial": serial_segments / (serial_extend_ms / 1e3) / 1e6 if serial_extend_ms else None,
                              "Mrays_s_whole_step": seg_total / world / (ms_max / 1e3) / 1e6},
