@@ -246,7 +246,7 @@ int ptb_get_config(ptb_renderer* r, void* out96);
  * 1, "+=" otherwise), image_pixels_256 and accumulated_colors are written like
  * pixel_256_transform_gamma_corrected_kernel does.  Synchronous for the pass asked for; logs in the
  * reference's "[Cuda]Error ..." format and returns on failure.  Passes are rendered ahead of the calls
- * (environment variable PTB_COMPAT_LOOKAHEAD = passes per batch, default 8, 1 = off): a call for the
+ * (environment variables PTB_COMPAT_LOOKAHEAD = passes per batch, default 8, 1 = off; PTB_COMPAT_CONTEXTS = batches in flight, default 4): a call for the
  * next pass number with unchanged camera / configuration / scene is answered from a finished batch
  * while later ones render; any other call starts over from the caller's image_pixels, so every call
  * leaves what one pass per call would have left (csrc/compat.inc).  Declared with opaque pointers here. */
