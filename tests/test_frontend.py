@@ -232,6 +232,19 @@ def test_scene_errors(workload_root, tmp_path):
             f.write("v 0 0 0\nv 1 0 0\nv 0 1 0\nvn 0 0 1\n" + body)
         with pytest.raises(ptb.PtbError):
             load({"Background": bg, "Mesh": [{"Material": ["light"], "Path": "res\\obj\\wild%d.obj" % k, "Position": "0 0 0", "Scale": "1 1 1", "Rotate": "0 0 0"}]})
+    # several meshes: all files are parsed before any is appended (one allocation of the triangle arrays), but the error reported
+    # is still the first in mesh order — a mesh-level error of mesh 1 wins over a parse error of mesh 2, and the other way round
+    mesh = lambda path: {"Material": ["light"], "Path": path, "Position": "0 0 0", "Scale": "1 1 1", "Rotate": "0 0 0"}
+    with open(os.path.join(root, "res", "obj", "badface.obj"), "w") as f:
+        f.write("v 0 0 0\nv 1 0 0\nv 0 1 0\nvn 0 0 1\nf 1//1 2//1\n")
+    with pytest.raises(ptb.PtbError, match="does not have normal"):
+        load({"Background": bg, "Mesh": [mesh("res\\obj\\novn.obj"), mesh("res\\obj\\badface.obj")]})
+    with pytest.raises(ptb.PtbError, match="fewer than 3 vertices"):
+        load({"Background": bg, "Mesh": [mesh("res\\obj\\badface.obj"), mesh("res\\obj\\novn.obj")]})
+    with pytest.raises(ptb.PtbError, match="fewer than 3 vertices"):
+        load({"Background": bg, "Mesh": [mesh("res\\obj\\ptb_light.obj"), mesh("res\\obj\\badface.obj"), mesh("res\\obj\\missing.obj")]})
+    with pytest.raises(ptb.PtbError, match="Cannot open file"):
+        load({"Background": bg, "Mesh": [mesh("res\\obj\\ptb_light.obj"), mesh("res\\obj\\missing.obj"), mesh("res\\obj\\badface.obj")]})
     # non-finite or astronomically large vertices: the tree builders define no result for them; a load error, as is an edit
     # that would move a mesh there (the mesh keeps its previous placement)
     with open(os.path.join(root, "res", "obj", "inf.obj"), "w") as f:
