@@ -29,6 +29,8 @@
 #include <sstream>
 #include <thread>
 #include <atomic>
+#include <exception>
+#include <mutex>
 #include <chrono>
 #include <dirent.h>
 #include <fcntl.h>
@@ -69,6 +71,31 @@ static std::string join_path(const std::string& root, const std::string& rel)
 	if (root.back() == '/') return root + r;
 	return root + "/" + r;
 }
+
+// Host threads of the loader.  An exception in a worker (bad_alloc on a huge mesh) must reach the calling thread and, through it,
+// the C boundary as a load error — never std::terminate; and no thread may be left joinable when one cannot be started.
+class WorkerGroup
+{
+public:
+	~WorkerGroup() { join(); }
+	template <class F> void spawn(F body)
+	{
+		threads_.emplace_back([this, body]() mutable { try { body(); } catch (...) { capture(); } });
+	}
+	template <class F> void run_here(F body) { try { body(); } catch (...) { capture(); } }
+	// joins the workers; rethrows the first exception any of them (or run_here) met
+	void finish()
+	{
+		join();
+		if (error_) { std::exception_ptr e = error_; error_ = nullptr; std::rethrow_exception(e); }
+	}
+private:
+	void join() { for (auto& t : threads_) if (t.joinable()) t.join(); threads_.clear(); }
+	void capture() { std::lock_guard<std::mutex> lock(mutex_); if (!error_) error_ = std::current_exception(); }
+	std::vector<std::thread> threads_;
+	std::mutex mutex_;
+	std::exception_ptr error_;
+};
 
 static bool read_text_file(const std::string& path, std::string& out)
 {
@@ -1161,8 +1188,8 @@ bool read_text_buffer(const std::string& path, TextBuffer& out)
 	struct stat st;
 	if (fstat(fd, &st) != 0 || !S_ISREG(st.st_mode) || st.st_size < 0) { close(fd); return false; }
 	const size_t size = (size_t)st.st_size;
-	out.buf.reset(new (std::nothrow) char[size + 1]);
-	if (!out.buf) { close(fd); return false; }
+	try { out.buf.reset(new char[size + 1]); }
+	catch (...) { close(fd); throw; }      // out of memory is reported as such at the C boundary, not as an unreadable file
 	out.size = size;
 	out.buf[size] = '\0';
 	const size_t hw = std::max(1u, std::thread::hardware_concurrency());
@@ -1177,10 +1204,16 @@ bool read_text_buffer(const std::string& path, TextBuffer& out)
 			begin += (size_t)got;
 		}
 	};
-	std::vector<std::thread> workers;
-	for (size_t k = 1; k < n_threads; k++) workers.emplace_back(read_range, size * k / n_threads, size * (k + 1) / n_threads);
-	read_range(0, size / n_threads);
-	for (auto& th : workers) th.join();
+	{
+		WorkerGroup group;
+		for (size_t k = 1; k < n_threads; k++)
+		{
+			const size_t b = size * k / n_threads, e = size * (k + 1) / n_threads;
+			group.spawn([&read_range, b, e] { read_range(b, e); });
+		}
+		group.run_here([&] { read_range(0, size / n_threads); });
+		try { group.finish(); } catch (...) { close(fd); throw; }
+	}
 	close(fd);
 	return ok;
 }
@@ -1314,10 +1347,10 @@ bool parse_obj(const std::string& path, ObjData& out)
 	}
 	auto run = [&](auto&& fn)
 	{
-		std::vector<std::thread> workers;
-		for (size_t k = 1; k < slices.size(); k++) workers.emplace_back([&, k] { fn(slices[k]); });
-		if (!slices.empty()) fn(slices[0]);
-		for (auto& th : workers) th.join();
+		WorkerGroup group;
+		for (size_t k = 1; k < slices.size(); k++) group.spawn([&, k] { fn(slices[k]); });
+		if (!slices.empty()) group.run_here([&] { fn(slices[0]); });
+		group.finish();
 	};
 	run([&](ObjSlice& sl) { count_slice(text, sl); });
 	PTB_TRACE("obj count");
@@ -1391,10 +1424,10 @@ bool parse_obj(const std::string& path, ObjData& out)
 				}
 			}
 		};
-		std::vector<std::thread> workers;
-		for (size_t k = 1; k < slices.size() && k < flushed_runs; k++) workers.emplace_back(work);
-		work();
-		for (auto& th : workers) th.join();
+		WorkerGroup group;
+		for (size_t k = 1; k < slices.size() && k < flushed_runs; k++) group.spawn([&work] { work(); });
+		group.run_here([&work] { work(); });
+		group.finish();
 	}
 	ObjShape shape;
 	for (const Group& g : groups)
@@ -1519,10 +1552,14 @@ static bool append_mesh(HostScene& scene, const std::string& path, const Vec3& p
 	{
 		const size_t hw = std::max(1u, std::thread::hardware_concurrency());
 		const size_t n_threads = total < 65536 ? 1 : std::min<size_t>(16, hw);
-		std::vector<std::thread> workers;
-		for (size_t w = 1; w < n_threads; w++) workers.emplace_back(fill, total * w / n_threads, total * (w + 1) / n_threads);
-		fill(0, total / n_threads);
-		for (auto& th : workers) th.join();
+		WorkerGroup group;
+		for (size_t w = 1; w < n_threads; w++)
+		{
+			const size_t b = total * w / n_threads, e = total * (w + 1) / n_threads;
+			group.spawn([&fill, b, e] { fill(b, e); });
+		}
+		group.run_here([&] { fill(0, total / n_threads); });
+		group.finish();
 	}
 	PTB_TRACE("mesh fill world triangles");
 	if (bad_index)
@@ -1815,10 +1852,10 @@ bool load_scene(const std::string& scene_json_path, const std::string& asset_roo
 		};
 		const size_t hw = std::max(1u, std::thread::hardware_concurrency());
 		const size_t n_threads = g_loader_threads > 0 ? (size_t)g_loader_threads : std::min<size_t>(8, hw);
-		std::vector<std::thread> workers;
-		for (size_t k = 1; k < n_threads && k < image_paths.size(); k++) workers.emplace_back(work);
-		work();
-		for (auto& th : workers) th.join();
+		WorkerGroup group;
+		for (size_t k = 1; k < n_threads && k < image_paths.size(); k++) group.spawn([&work] { work(); });
+		group.run_here([&work] { work(); });
+		group.finish();
 	}
 	PTB_TRACE("images decoded");
 	for (int f = 0; f < 6; f++)

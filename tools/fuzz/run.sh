@@ -20,6 +20,7 @@ LOG="$WORK/log.txt"; : > "$LOG"
 (ls "$WORK/corpus/scene_root/fz" | grep "^o" | sed "s#^#$WORK/corpus/scene_root/fz/#" | xargs -n 300 "$WORK/bin/bvh" "$WORK/corpus/scene_root") >> "$LOG" 2>&1 || true   # host SAH builder, flatten, 8-wide collapse
 (cd "$WORK/corpus/configs" && ls | xargs -n 1000 "$WORK/bin/config") >> "$LOG" 2>&1 || true
 "$WORK/bin/checkpoint" >> "$LOG" 2>&1 || true
+python "$HERE/oom_sweep.py" "$WORK/oom" >> "$LOG" 2>&1 || echo "exception oom sweep found abnormal exits" >> "$LOG"   # allocation / thread-start failures inside the threaded scene loader
 grep "^ok" "$LOG"
 if grep -q "runtime error\|AddressSanitizer\|exception" "$LOG"; then grep "runtime error\|SUMMARY\|exception" "$LOG" | sort | uniq -c | head -20; exit 1; fi
 echo "no findings"
