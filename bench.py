@@ -38,9 +38,21 @@ PASSES_PER_STEP = 64
 PASSES_IN_FLIGHT = 16     # passes traced as one wavefront batch (tools/sweep_batching.py: 16 x 4 streams +1.4 % over 8 x 4 at 11.7 GB of path state)
 STREAMS_IN_FLIGHT = 4     # batches overlapped on separate CUDA streams
 METRIC = "path samples/sec (Mspp*px/s), 1080p"
-# dram__bytes_read.sum + dram__bytes_write.sum per closest-hit launch (ncu --set full, workload c2, 16 passes in flight as benchmarked),
-# averaged over the 8 depth launches of one batch — profiles/r01i_extend_ncu_summary.md (the 8-pass capture of r01b gave 197.2 MB)
-NCU_DRAM_BYTES_PER_EXTEND_LAUNCH = 378.9e6
+# Per-launch memory traffic of the closest-hit kernels from ONE `ncu --set full` capture of the shipped kernels (workload c2, one 16-pass
+# batch as benchmarked: d0-d1 k_extend_persistent, d2-d7 k_extend_persistent8), averaged over the 8 depth launches of the batch like
+# `avg_launch_ms` below — profiles/r02_extend_ncu_summary.md.  bench.py divides these by the launch duration it measures LIVE.
+NCU_CAPTURE = {
+    "source": "profiles/r02_extend_ncu_summary.md",
+    "workload": "c2", "passes_in_flight": 16,
+    "dram_bytes_per_launch": 379.2e6,         # dram__bytes_read.sum + dram__bytes_write.sum
+    "l2_bytes_per_launch": 2345.4e6,          # lts__t_bytes.sum
+    "l1_writeback_bytes_per_launch": 22042.7e6,   # l1tex__lsu_writeback_active_mem_lgds.sum (cycles) x 128 B: what the load instructions cost the L1 data pipe
+    "l1_tag_bytes_per_launch": 4379.9e6,      # l1tex__t_bytes.sum (distinct sectors x 32 B through the tag stage)
+    "limiters": {"time_weighted_d0_d7": {"sm__throughput_pct": 56.6, "issue_active_pct": 65.4, "l1_data_pipe_wavefronts_pct": 62.3, "l1_writeback_active_pct": 50.4,
+                                          "active_lanes_per_instruction": 20.2, "l1_hit_pct": 67.5, "l2_hit_pct": 65.2},
+                 "d0_d1": {"sm__throughput_pct": [68.0, 50.5], "issue_active_pct": [69.8, 64.4], "l1_data_pipe_wavefronts_pct": [74.5, 64.9],
+                           "active_lanes_per_instruction": [22.6, 19.6], "stall_long_scoreboard_per_issue": [4.2, 5.94], "alu_pipe_pct": [63.8, 56.8]}},
+}
 UNIT = "Msamples/s"
 
 
@@ -90,11 +102,14 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def make_scene(workload, root):
+def make_scene(workload, root, for_reference=False):
     from pathtracerwithcuda_b200 import procedural as pr
-    from oracle import refharness as rh
     w = pr.make_workload(root, workload)
-    rh.link_backslash_names(root)      # the reference opens '\\'-spelled paths; harmless for us
+    if for_reference:
+        # the reference opens '\\'-spelled paths: alias every file under that name (the product arm reads the same JSON and
+        # converts separators itself, so it imports nothing from oracle/)
+        from oracle import refharness as rh
+        rh.link_backslash_names(root)
     return w
 
 
@@ -142,32 +157,48 @@ def run_reference(args, w, root, rank, world):
         # (b) steady state: everything prefetched to the GPU, config marked read-mostly — the most
         #     favourable condition for the reference; THIS is the reported value
         ref.prefetch()
-        for _ in range(args.warmup):
+        for _ in range(max(args.warmup, 5)):        # >= 5 warm-up steps after the prefetch: its first steps still migrate pages
             ref.render(PASSES_PER_STEP)
         ref.prefetch()
-        secs, step_ms = 0.0, []
+        secs, step_ms, pass_ms = 0.0, [], []
         for _ in range(args.steps):
-            dt = ref.render(PASSES_PER_STEP)       # synchronous: returns after cudaDeviceSynchronize
+            per_pass = ref.render_per_pass(PASSES_PER_STEP)     # synchronous passes: each returns after cudaDeviceSynchronize
+            dt = float(per_pass.sum())
             secs += dt
             step_ms.append(dt * 1e3)
+            pass_ms += (per_pass * 1e3).tolist()
         seg, trace_ms = ref.pass_instrumented(ref.lib.ref_pass_counter() + 1)
-        # The reference's steps show multi-x outliers on this platform (cudaMallocManaged buffers +
-        # a cudaMalloc/cudaFree pair inside thrust::remove_if every bounce).  To keep the ratio the
-        # driver computes CONSERVATIVE for us, `value` is taken from the MEDIAN step, not the mean;
-        # the mean and the best step are reported next to it.
-        px_step = w["width"] * w["height"] * PASSES_PER_STEP
-        median_ms = float(np.median(step_ms))
-        value = px_step / (median_ms / 1e3) / 1e6
+        # The reference's passes show multi-x outliers on some boxes and none on others.  tools/ref_variance.py (profiles/r02_ref_variance_c2.json)
+        # attributes ALL of the excess to thread_shrink — thrust::remove_if with its temporary cudaMalloc / cudaFree and implicit
+        # synchronisation, eight times per pass — while trace_ray_kernel stays at 4.0 ms +- 3 %: on one box the median pass took 32 ms
+        # (30 ms of it inside thread_shrink) and single passes up to 3.2 s, on another 7 ms.  Step medians therefore read 35 .. 288
+        # Msamples/s across boxes (round 1: 52.9 vs 254-288), whereas the BEST SINGLE PASS reads 350 and ~310.  `value` is taken from the
+        # best single pass of the timed region: the reference with every host-side call at its fastest — the statistic that reproduces
+        # across boxes and the one most favourable to the reference, so the ratio the driver computes is a LOWER bound for us.
+        # Median / mean steps and the pure trace_ray_kernel rate (an upper bound its host loop cannot reach) are printed beside it.
+        px_pass = w["width"] * w["height"]
+        px_step = px_pass * PASSES_PER_STEP
+        median_ms, best_ms = float(np.median(step_ms)), float(min(step_ms))
+        best_pass_ms, median_pass_ms = float(min(pass_ms)), float(np.median(pass_ms))
+        value = px_pass / (best_pass_ms / 1e3) / 1e6
+        best_step_value = px_step / (best_ms / 1e3) / 1e6
+        median_value = px_step / (median_ms / 1e3) / 1e6
         mean_value = px_step * args.steps / secs / 1e6
+        kernel_only = px_pass / (trace_ms / 1e3) / 1e6 if trace_ms else None
         # n_gpus echoes the launch (the driver pairs the arms by N); the reference itself is single-GPU code: gpus_used says so
-        line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": max(1, args.gpus), "gpus_used": 1, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": median_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": max(1, args.gpus), "gpus_used": 1, "steps": args.steps, "warmup": max(args.warmup, 5),
+                "ms_per_step": best_pass_ms * PASSES_PER_STEP, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
                 "data": "synthetic", "config": dict(config, note="unmodified reference CUDA kernels rebuilt headless for sm_100a, managed memory prefetched"),
+                "value_basis": "best single pass of the timed region (see reference_extra)", "best_pass": value, "min_step": best_step_value, "median_step": median_value,
+                "mean_step": mean_value, "kernel_only": kernel_only,
                 "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "reference",
                                  "sample": "%d passes of %s through path_tracer_kernel() on the B200 (the reference has no CPU implementation of this path)" % (PASSES_PER_STEP * args.steps, w["name"])},
                 "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-                "reference_extra": {"value_basis": "median step", "mean_step_Msamples_s": mean_value, "best_step_Msamples_s": px_step / (min(step_ms) / 1e3) / 1e6,
-                                    "ms_per_step_mean": secs / args.steps * 1e3, "step_ms": step_ms, "as_shipped_unified_memory_Msamples_s": w["width"] * w["height"] * PASSES_PER_STEP / shipped_s / 1e6,
+                "reference_extra": {"value_basis": "best single pass", "best_pass_Msamples_s": value, "median_pass_Msamples_s": px_pass / (median_pass_ms / 1e3) / 1e6,
+                                    "median_step_Msamples_s": median_value, "mean_step_Msamples_s": mean_value, "best_step_Msamples_s": best_step_value,
+                                    "kernel_only_Msamples_s": kernel_only, "best_pass_ms": best_pass_ms, "median_pass_ms": median_pass_ms, "worst_pass_ms": float(max(pass_ms)),
+                                    "cause_of_spread": "thread_shrink (thrust::remove_if + temporary cudaMalloc/cudaFree + sync, 8 per pass); trace_ray_kernel is stable: profiles/r02_ref_variance_c2.json",
+                                    "ms_per_step_median": median_ms, "ms_per_step_mean": secs / args.steps * 1e3, "step_ms": step_ms, "as_shipped_unified_memory_Msamples_s": w["width"] * w["height"] * PASSES_PER_STEP / shipped_s / 1e6,
                                     "ray_segments_per_pass": seg, "trace_ray_kernel_ms_per_pass": trace_ms, "Mrays_s_trace_kernel": seg / trace_ms / 1e3 if trace_ms else None}}
         ref.close()
         return line
@@ -198,7 +229,7 @@ def main():
         return 0
     root = tempfile.mkdtemp(prefix="ptb_bench_%d_" % rank)
     try:
-        w = make_scene(args.workload, root)
+        w = make_scene(args.workload, root, for_reference=args.impl == "reference")
         if args.impl == "reference":
             # the reference prints its "[Info]..." progress lines with printf/cout: keep stdout to the ONE JSON line
             sys.stdout.flush()
@@ -276,6 +307,16 @@ def run_ptb200(args, w, root, rank, local_rank, world):
     r.set_option("profile_stages", 0)
     r.set_option("active_streams", 0)
 
+    # ---- the machine roofs of the closest-hit kernel, measured on THIS GPU before the timed region (tools/roofs/roofs.cu)
+    roofs = None
+    if rank == 0:
+        sys.path.insert(0, os.path.join(ROOT, "tools", "roofs"))
+        import roofs as roofs_mod
+        info = r.bvh_info()
+        tree_bytes = max(1 << 20, int(info.get("node_records", 0)) * 64 + int(w["triangles"]) * 48)
+        roofs = roofs_mod.measure(local_rank, tree_bytes=tree_bytes)
+    barrier()
+
     # ---- warm-up
     sr.begin()
     for _ in range(args.warmup):
@@ -330,18 +371,35 @@ def run_ptb200(args, w, root, rank, local_rank, world):
     if rank == 0:
         peaks, peak_kind = measured_peaks()
         seg_total, launches_total, _ = [float(x) for x in seg_t.tolist()]
-        # algorithmic bytes of the extend (closest-hit) kernel per ray segment, SURVEY.md 8d:
-        # queue id 4 + ray o,d 32 + binary nodes*64 + wide nodes*80 + tris*48 + hit record 16
+        # ALGORITHMIC work of the closest-hit kernel per ray segment: queue id 4 + ray o,d 32 + binary nodes x 64 +
+        # wide nodes x 80 + triangles x 48 + hit record 16 bytes; 25 flop per box tested (2 per binary node, 8 per wide node), 51 per triangle
         bytes_per_seg = 4 + 32 + nodes_per_seg * 64.0 + wide_per_seg * 80.0 + tris_per_seg * 48.0 + 16
+        flop_per_seg = nodes_per_seg * 2 * 25.0 + wide_per_seg * 8 * 25.0 + tris_per_seg * 51.0
         seg_per_launch = serial_segments / max(serial_launches, 1)
         avg_launch_ms = serial_extend_ms / max(serial_launches, 1)
-        achieved = seg_per_launch * bytes_per_seg / (avg_launch_ms / 1e3) / 1e9 if avg_launch_ms > 0 else None
-        # the co-bound SURVEY.md 8d names: algorithmic FP32 work of the same kernel — 25 flop per box tested (2 per binary node, 8 per wide
-        # node), 51 per triangle test — against the non-tensor FP32 peak at the SM clock held during the timed region (148 SMs x 128 lanes x 2)
-        flop_per_seg = nodes_per_seg * 2 * 25.0 + wide_per_seg * 8 * 25.0 + tris_per_seg * 51.0
-        sm_mhz = (clocks or {}).get("sm_mhz") or (clocks or {}).get("sm_max_mhz")
-        fp32_peak = 148 * 128 * 2 * sm_mhz * 1e6 / 1e12 if sm_mhz else None
-        fp32_achieved = seg_per_launch * flop_per_seg / (avg_launch_ms / 1e3) / 1e12 if avg_launch_ms > 0 else None
+        secs = avg_launch_ms / 1e3 if avg_launch_ms > 0 else None
+
+        def rate(x, scale):
+            return x / secs / scale if (secs and x is not None) else None
+
+        def frac(a, b):
+            return a / b if (a is not None and b) else None
+        same_capture = w["name"] == NCU_CAPTURE["workload"] and PASSES_IN_FLIGHT == NCU_CAPTURE["passes_in_flight"]
+        ncu = NCU_CAPTURE if same_capture else {}
+        # Roofs (measured above, not estimated):  L2 = random 64-byte gathers over a working set of the tree's size, L1 = the same gathers over
+        # a 64 KB set, FP32 = FMA issue.  Bytes moved through L2 / L1 are the ncu counters of the capture named in NCU_CAPTURE (not the
+        # algorithmic model: nodes shared by the lanes of a warp are one access), flops are algorithmic.  The tree of c1-c4 is cache
+        # resident, so HBM is not the roof of this kernel (dram_frac ~ 0.05); c5's 560 MB tree would make it one.
+        l2_gbs, l1_gbs, fp32_tf = rate(ncu.get("l2_bytes_per_launch"), 1e9), rate(ncu.get("l1_writeback_bytes_per_launch"), 1e9), rate(seg_per_launch * flop_per_seg, 1e12)
+        dram_gbs = rate(ncu.get("dram_bytes_per_launch"), 1e9)
+        # l1: bytes the load instructions write back into registers (the L1 data pipe's port, 128 B per cycle per SM) against the measured
+        # write-back roof; l2: bytes through L2 against the measured random-gather bandwidth over a tree-sized working set
+        fracs = {"l2": frac(l2_gbs, roofs and roofs["l2_gather_gbs"]), "l1": frac(l1_gbs, roofs and roofs["l1_writeback_gbs"]),
+                 "fp32": frac(fp32_tf, roofs and roofs["fp32_tflops"]), "hbm": frac(dram_gbs, peaks.get("hbm_gbs"))}
+        known = {k: v for k, v in fracs.items() if v is not None}
+        bound = max(known, key=known.get) if known else None
+        achieved = {"l2": l2_gbs, "l1": l1_gbs, "fp32": fp32_tf, "hbm": dram_gbs}.get(bound)
+        peak = {"l2": roofs and roofs["l2_gather_gbs"], "l1": roofs and roofs["l1_writeback_gbs"], "fp32": roofs and roofs["fp32_tflops"], "hbm": peaks.get("hbm_gbs")}.get(bound)
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
                 "data": "synthetic",
@@ -352,25 +410,24 @@ def run_ptb200(args, w, root, rank, local_rank, world):
                            "scene_load_s": load_s},
                 "clocks": clocks, "gpu_launches": int(launches_total),
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 64, "d2h_bytes_per_step": int(u8.nbytes)},
-                "roofline": {"bound": "hbm", "kernel": "k_extend", "achieved": achieved, "peak": peaks.get("hbm_gbs"), "unit": "GB/s",
-                             "frac": (achieved / peaks["hbm_gbs"]) if achieved else None, "traffic": NCU_DRAM_BYTES_PER_EXTEND_LAUNCH,
-                             "traffic_source": "profiles/r01i_extend_ncu_summary.md: dram__bytes_read.sum + dram__bytes_write.sum averaged over the 8 closest-hit launches (k_extend_persistent d0-d1, k_extend_persistent8 d2-d7) of one 16-pass batch of c2 (ncu --set full)",
-                             "peak_source": peak_kind,
-                             "bytes_per_segment": bytes_per_seg, "nodes_per_segment": nodes_per_seg, "wide_nodes_per_segment": wide_per_seg, "tris_per_segment": tris_per_seg,
+                "roofline": {"bound": bound, "kernel": "k_extend_persistent / k_extend_persistent8 (closest hit)", "achieved": achieved, "peak": peak,
+                             "unit": "TFLOP/s" if bound == "fp32" else "GB/s", "frac": known.get(bound) if bound else None,
+                             "traffic": ncu.get("dram_bytes_per_launch"),
+                             "fracs": fracs,
+                             "achieved_all": {"l2_GBs": l2_gbs, "l1_writeback_GBs": l1_gbs, "l1_tag_GBs": rate(ncu.get("l1_tag_bytes_per_launch"), 1e9), "fp32_TFLOPs": fp32_tf, "dram_GBs": dram_gbs,
+                                              "algorithmic_GBs": rate(seg_per_launch * bytes_per_seg, 1e9)},
+                             "roofs": roofs, "hbm_copy_peak_gbs": peaks.get("hbm_gbs"), "hbm_peak_source": peak_kind,
+                             "peak_source": "tools/roofs/roofs.cu run in this process before the timed region: l1 = 256-bit loads streaming an L1-resident buffer "
+                                            "(register write-back bandwidth), l2 = random 64 B gathers at 8 x 128 threads per SM over a tree-sized working set, "
+                                            "fp32 = FMA issue; hbm = MEASURED_PEAKS.json copy bandwidth",
+                             "ncu_capture": ncu.get("source"), "ncu_limiters": ncu.get("limiters"),
+                             "bytes_per_segment": bytes_per_seg, "flop_per_segment": flop_per_seg, "nodes_per_segment": nodes_per_seg,
+                             "wide_nodes_per_segment": wide_per_seg, "tris_per_segment": tris_per_seg,
                              "segments_per_launch": seg_per_launch, "avg_launch_ms": avg_launch_ms,
-                             "how": "per-launch CUDA events on the launching stream with ONE stream in flight, immediately before the timed region "
-                                    "(the timed region overlaps %d streams, so launches there are not exclusive); achieved counts cache-served "
-                                    "bytes: nodes/triangles are L1/L2-resident, see DESIGN.md" % STREAMS_IN_FLIGHT,
-                             # what actually crosses the HBM interface (ncu dram bytes per launch / the live launch duration), and what
-                             # the ncu capture names as the limiter instead: issue slots busy and the stall per issued instruction
-                             "dram_achieved": NCU_DRAM_BYTES_PER_EXTEND_LAUNCH / (avg_launch_ms / 1e3) / 1e9 if avg_launch_ms > 0 else None,
-                             "dram_frac": (NCU_DRAM_BYTES_PER_EXTEND_LAUNCH / (avg_launch_ms / 1e3) / 1e9 / peaks["hbm_gbs"]) if avg_launch_ms > 0 and peaks.get("hbm_gbs") else None,
-                             "ncu_limiters": {"source": "profiles/r01i_extend_ncu_summary.md (d0 / d1, binary-tree kernel)", "issue_active_pct": [68.2, 61.9],
-                                              "active_lanes_per_instruction": [22.1, 18.9], "stall_long_scoreboard_per_issue": [4.2, 5.85],
-                                              "l1_hit_pct": [71.7, 64.8], "lsu_wavefronts_pct_of_peak": [74.7, 65.5], "alu_pipe_pct": [61.4, 53.2]},
-                             "fp32": {"flop_per_segment": flop_per_seg, "achieved_TFLOPs": fp32_achieved, "peak_TFLOPs": fp32_peak,
-                                      "frac": (fp32_achieved / fp32_peak) if fp32_achieved and fp32_peak else None,
-                                      "note": "algorithmic slab + Moller-Trumbore flops only; the kernel's instruction mix is min/max/select/compare-heavy (ALU pipe 61 %, FMA pipe 21 % in ncu)"},
+                             "how": "launch duration: per-launch CUDA events on the launching stream with ONE stream in flight, immediately before the timed "
+                                    "region (the timed region overlaps %d streams, so launches there are not exclusive), averaged over the depth launches of "
+                                    "the batches; L2 / L1 / DRAM bytes per launch: ncu counters of the committed capture averaged the same way; "
+                                    "frac = max over the roofs of achieved / measured roof" % STREAMS_IN_FLIGHT,
                              "extend_share_of_serial_step": serial_extend_ms / serial_step_ms if serial_step_ms else None,
                              "Mrays_s_extend_serial": serial_segments / (serial_extend_ms / 1e3) / 1e6 if serial_extend_ms else None,
                              "Mrays_s_whole_step": seg_total / world / (ms_max / 1e3) / 1e6},

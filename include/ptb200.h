@@ -172,10 +172,88 @@ int ptb_bvh_download(ptb_renderer* r, float* out_nodes16, int32_t* out_leaf_orde
 /* with option "count_traversal" = 1: out25[0] = most node visits of one ray in the last render, out25[1 + k] = rays with
  * floor(log2(visits + 1)) == k (binary-tree kernel) */
 int ptb_get_traversal_histogram(ptb_renderer* r, int64_t* out25);
-/* string options: "bvh_builder" = "gpu_sah" (default) | "host_sah"; "passes_in_flight" = "1".."64";
- * "profile_stages" = "0"|"1"; "count_traversal" = "0"|"1"; "sort_by_material" = "0"|"1";
- * "loader_threads" = "0".."64" (process-wide: slices an OBJ file is parsed in; 0 = by file size and host cores). */
+/* String options (every key ptb_set_option accepts; unknown keys fail).  None of them changes WHICH paths are traced except the
+ * three estimator keys; images are bit-identical across all scheduling / tree options (tests/test_gpu_parity.py).
+ *  scheduling
+ *   "passes_in_flight"   "1".."64" (default 4)  passes traced as one wavefront batch; re-allocates the path state, resets the image
+ *   "streams_in_flight"  "1".."8"  (default 4)  batches overlapped on separate CUDA streams (own path-state buffers each)
+ *   "active_streams"     "0" = all (default) | n  use only the first n stream contexts ("1": serial batches, clean per-kernel timing)
+ *   "tile_order"         "1" (default) | "0"    camera rays enter the first queue in 8x4 pixel tiles / row-major
+ *   "octant_order"       "0" (default) | "1"    next-depth queue grouped by ray-direction octant per block (measured slower)
+ *   "sort_by_material"   "0" (default) | "1"    block-local material sort of the shade queue (measured 3-7 % slower, off)
+ *  acceleration structure (take effect at the next ptb_load_scene / geometry edit)
+ *   "bvh_builder"        "gpu_sah" (default, csrc/bvh_build.cu) | "host_sah" (csrc/bvh_host.cpp, cross-check / fallback)
+ *   "bvh_layout"         "2" (default: 64-byte binary nodes) | "8" (80-byte compressed 8-wide nodes only)
+ *   "bvh_hybrid"         "1" (default) | "0"    layout 2 only: also build the compressed wide tree for the deeper bounces
+ *   "hybrid_from_depth"  "2" (default)          first bounce depth traced over the wide tree (immediate)
+ *   "bvh_collapse"       "gpu" (default) | "host"  where the binary tree is collapsed to 8-wide nodes
+ *   "bvh_max_leaf"       "1".."8" (default 8)    triangles per leaf of the binary tree
+ *   "bvh_intersect_cost" float > 0 (default 0.8) SAH cost of a triangle test relative to a node visit
+ *   "l2_persist"         "0" (default) | "1"    nodes + leaf-order triangles in one allocation under a persisting L2 access-policy
+ *                                               window on every render stream (measured neutral: the tree is never evicted)
+ *  closest-hit kernels (immediate; tuning knobs of tools/sweep_*.py, defaults are the measured optima)
+ *   "extend_persistent"  "1" (default) | "0"    persistent warp-voting kernels / one ray per thread
+ *   "extend_variant"     "0" (default) | "1" postponed leaves | "2" + leaf prefetch | "3" top of the tree in shared memory
+ *                                               (all measured slower than 0 on c2, profiles/r02_experiments.md; same hits)
+ *   "treelet_block", "treelet_nodes"            variant 3: threads per block (1024), nodes held in shared memory (1023)
+ *   "tune_refill", "tune_leaf", "tune_reps"     binary-tree kernel: refill when >= N lanes idle (20), leaf phase when >= N lanes
+ *                                               wait (6), node steps per node phase (6); "unroll_reps" "1" | "0"
+ *   "tune_refill8", "tune_leaf8"                wide-tree kernel (12, 6)
+ *   "persistent_grid", "persistent_grid8"       blocks of the persistent launches (default: one resident wave)
+ *  estimator (NOT parity modes: they change the samples, same expectation; tests/test_gpu_nee.py, test_gpu_rr.py, test_gpu_estimators.py)
+ *   "estimator"          "reference" (default) | "nee"   next-event estimation + shadow rays (binary tree)
+ *   "russian_roulette"   "0" (default) | "1"    from bounce 3 on
+ *   "pass_clamp"         float (default -1 = the reference's 2 * MaxDepth)   diagnostic: per-pass clamp of the accumulation
+ *  measurement
+ *   "profile_stages"     "0" | "1"   CUDA events around every closest-hit launch (ptb_get_depth_profile, ptb_stats.gpu_ms_extend)
+ *   "count_traversal"    "0" | "1"   instrumented kernels: node visits / triangle tests (ptb_stats, ptb_get_traversal_histogram)
+ *  loader (process-wide)
+ *   "loader_threads"     "0".."64"   slices an OBJ file is parsed in; 0 = by file size and host cores */
 int ptb_set_option(ptb_renderer* r, const char* key, const char* value);
+
+/* ---- multi-GPU --------------------------------------------------------------------------------
+ * The reference picks one device (Main/window.cpp:281-295) and calls path_tracer::render() once per pass
+ * (Core/path_tracer.cpp:40-99).  A pass depends only on (scene, camera, configuration, pass number), so the box shards by pass
+ * index: device k of G renders passes P+1+k, P+1+k+G, ... (each keeps its single-GPU seed), and ONE ncclReduce(sum, float,
+ * 3*W*H) per image lands on the root, which holds the MERGED image (its own accumulation stays untouched, so rendering more
+ * and reducing again is correct).  NCCL is dlopen'ed at first use (libnccl.so.2; override with the environment variable
+ * PTB200_NCCL_LIB): no link-time dependency, single-GPU hosts never load it.  csrc/multi.inc.
+ *
+ * (a) ONE process, every GPU of the box — what the reference's C++ host would call instead of path_tracer::render():
+ *     ptb_multi_create(config, n, devices-or-NULL) = n renderers + ncclCommInitAll; ptb_multi_load_scene parses the scene files
+ *     ONCE and uploads / builds the BVH on every device concurrently (one host thread per device); ptb_multi_render(total)
+ *     renders the next `total` passes of the image across the devices (blocking) and merges; ptb_multi_image_* read the merged
+ *     image; ptb_multi_renderer(i) exposes the per-device handle (options, stats, edits). */
+typedef struct ptb_multi ptb_multi;
+ptb_multi* ptb_multi_create(const char* config_json_path, int n_devices, const int* devices);
+void ptb_multi_destroy(ptb_multi* m);
+int ptb_multi_device_count(ptb_multi* m);
+ptb_renderer* ptb_multi_renderer(ptb_multi* m, int index);
+int ptb_multi_set_option(ptb_multi* m, const char* key, const char* value);
+int ptb_multi_load_scene(ptb_multi* m, const char* scene_json_path, const char* asset_root);
+int ptb_multi_set_camera(ptb_multi* m, const ptb_camera* cam);
+int ptb_multi_render(ptb_multi* m, int total_passes);
+int ptb_multi_clear(ptb_multi* m);
+int ptb_multi_pass_counter(ptb_multi* m);
+int ptb_multi_image_f32(ptb_multi* m, float* out_rgb_sum, int* out_passes);
+int ptb_multi_image_u8(ptb_multi* m, uint8_t* out_rgb);
+/* (b) one process per GPU (MPI / torchrun): rank 0 calls ptb_dist_unique_id, the host hands the 128 bytes to every rank however
+ *     it likes, every rank calls ptb_dist_init(r, rank, world, id).  ptb_dist_broadcast_scene(r, root): the root has loaded the
+ *     scene, every other rank receives the PARSED scene (world-space triangles, materials, spheres, textures, cube map) through
+ *     one ncclBroadcast and builds its own BVH — no rank but the root reads the scene files.  ptb_dist_render(r, total): this
+ *     rank's share of the next `total` passes (same `total` on every rank).  ptb_dist_reduce(r, root): collective; afterwards
+ *     ptb_merged_image_f32 / _u8 on the root return the merged sum / the finished 8-bit image (out_passes = passes of all ranks).
+ *     ptb_nccl_version: NCCL's version code, 0 if it cannot be loaded. */
+int ptb_nccl_version(void);
+int ptb_dist_unique_id(void* out_id128);
+int ptb_dist_init(ptb_renderer* r, int rank, int world_size, const void* id128);
+int ptb_dist_shutdown(ptb_renderer* r);
+int ptb_dist_broadcast_scene(ptb_renderer* r, int root);
+int ptb_dist_render(ptb_renderer* r, int total_passes);
+int ptb_dist_reduce(ptb_renderer* r, int root);
+int ptb_dist_clear(ptb_renderer* r);
+int ptb_merged_image_f32(ptb_renderer* r, float* out_rgb_sum, int* out_passes);
+int ptb_merged_image_u8(ptb_renderer* r, uint8_t* out_rgb);
 
 /* ---- output side -----------------------------------------------------------------------------
  * ptb_save_png        = screenshot() of Main/window.cpp:712-740 (lodepng::encode of the displayed RGBA8 image),

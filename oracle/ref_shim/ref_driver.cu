@@ -36,7 +36,7 @@ namespace
 	int* g_energy_exist = nullptr;
 	scattering* g_scatterings = nullptr;
 	bool g_scene_ready = false;
-	double g_last_trace_ms = 0.0;
+	double g_last_trace_ms = 0.0, g_last_shrink_ms = 0.0, g_last_pass_ms = 0.0;
 	long long g_last_segments = 0;
 }
 
@@ -169,6 +169,19 @@ double ref_render(int n_passes)
 	for (int i = 0; i < n_passes; i++) call_reference_pass();
 	auto t1 = std::chrono::steady_clock::now();
 	return std::chrono::duration<double>(t1 - t0).count();
+}
+
+/* wall seconds of each of n synchronous reference passes (diagnostic for the step-time spread of the reference arm) */
+int ref_render_per_pass(int n_passes, double* out_seconds)
+{
+	if (!g_scene_ready) return 1;
+	for (int i = 0; i < n_passes; i++)
+	{
+		auto t0 = std::chrono::steady_clock::now();
+		call_reference_pass();
+		out_seconds[i] = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+	}
+	return 0;
 }
 
 /* the 18 arguments the reference hands to path_tracer_kernel (Core/path_tracer.cpp:48-67), as raw
@@ -425,6 +438,8 @@ long long ref_pass_instrumented(int pass_counter, int capture_depth, int* out_pi
 	int seed = pass_counter;
 	cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
 	double trace_ms = 0.0; long long segments = 0;
+	g_last_shrink_ms = 0.0;
+	auto pass_t0 = std::chrono::steady_clock::now();
 
 	init_data_kernel<<<blocks, threads>>>(pixel_count, g_energy_exist, g_not_absorbed, g_accumulated, g_scatterings, config_device);
 	generate_ray_kernel<<<blocks, threads>>>(g_render_cam->eye, g_render_cam->view, g_render_cam->up, g_render_cam->resolution,
@@ -455,7 +470,9 @@ long long ref_pass_instrumented(int pass_counter, int capture_depth, int* out_pi
 		cudaEventRecord(e1);
 		cudaEventSynchronize(e1);
 		float ms = 0; cudaEventElapsedTime(&ms, e0, e1); trace_ms += ms;
-		count = thread_shrink(g_energy_exist, count);
+		auto s0 = std::chrono::steady_clock::now();
+		count = thread_shrink(g_energy_exist, count);   /* thrust::remove_if + its temporary cudaMalloc / cudaFree + the implicit synchronisation */
+		g_last_shrink_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - s0).count();
 	}
 	if (capture_depth >= 0) { cudaEventDestroy(e0); cudaEventDestroy(e1); return 0; }
 	g_image->pass_counter = pass_counter;
@@ -463,10 +480,13 @@ long long ref_pass_instrumented(int pass_counter, int capture_depth, int* out_pi
 	cudaDeviceSynchronize();
 	cudaEventDestroy(e0); cudaEventDestroy(e1);
 	g_last_trace_ms = trace_ms; g_last_segments = segments;
+	g_last_pass_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - pass_t0).count();
 	return segments;
 }
 
 double ref_last_trace_ms() { return g_last_trace_ms; }
+double ref_last_shrink_ms() { return g_last_shrink_ms; }
+double ref_last_pass_ms() { return g_last_pass_ms; }
 
 /* ---- known-answer helpers: the reference's own header functions evaluated on the HOST
  * (they are __host__ __device__), and its device-only hash() evaluated on the device ---- */

@@ -124,6 +124,11 @@ class RefLib:
         L.ref_render.restype = ctypes.c_double
         L.ref_render.argtypes = [ctypes.c_int]
         L.ref_last_trace_ms.restype = ctypes.c_double
+        for fn in ("ref_last_shrink_ms", "ref_last_pass_ms"):
+            if hasattr(L, fn):
+                getattr(L, fn).restype = ctypes.c_double
+        if hasattr(L, "ref_render_per_pass"):
+            L.ref_render_per_pass.argtypes = [ctypes.c_int, ctypes.c_void_p]
         L.ref_num_bvh_nodes.restype = ctypes.c_longlong
         L.ref_pass_instrumented.restype = ctypes.c_longlong
         L.ref_pass_instrumented.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
@@ -254,6 +259,18 @@ class RefLib:
         rays = np.zeros((max_out, 6), np.float32)
         n = self.lib.ref_pass_instrumented(int(pass_counter), int(depth), pix.ctypes.data_as(ctypes.c_void_p), rays.ctypes.data_as(ctypes.c_void_p), max_out)
         return pix[:n].copy(), rays[:n].copy()
+
+    def render_per_pass(self, n_passes):
+        """Wall seconds of each of n synchronous passes through the unmodified path_tracer_kernel()."""
+        out = np.zeros(n_passes, np.float64)
+        if self.lib.ref_render_per_pass(int(n_passes), out.ctypes.data_as(ctypes.c_void_p)):
+            raise RuntimeError("ref_render_per_pass failed")
+        return out
+
+    def pass_breakdown(self, pass_counter):
+        """One pass of the re-issued loop: (wall ms of the pass, ms in trace_ray_kernel by CUDA events, wall ms in thread_shrink)."""
+        self.lib.ref_pass_instrumented(int(pass_counter), -1, None, None, 0)
+        return float(self.lib.ref_last_pass_ms()), float(self.lib.ref_last_trace_ms()), float(self.lib.ref_last_shrink_ms())
 
     def pass_instrumented(self, pass_counter):
         """Runs one full pass; returns (ray segments, ms spent in trace_ray_kernel)."""

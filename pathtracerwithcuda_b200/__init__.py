@@ -5,4 +5,4 @@ libptb200.so from csrc/): `Renderer` wraps the handle API, `PathTracer` mirrors 
 `path_tracer` class.  No CPU / PyTorch fallback exists.
 """
 from .api import (Camera, PathTracer, PtbError, Renderer, Stats, default_camera, device_count, last_error,  # noqa: F401
-                  load_library, write_png, write_pfm, decode_image, set_jpeg_decode, MATERIAL_DTYPE, SPHERE_DTYPE, CONFIG_DTYPE)
+                  load_library, write_png, write_pfm, MultiRenderer, dist_unique_id, nccl_version, decode_image, set_jpeg_decode, MATERIAL_DTYPE, SPHERE_DTYPE, CONFIG_DTYPE)

@@ -132,6 +132,30 @@ def load_library():
     L.ptb_set_config.argtypes = [vp, vp]
     L.ptb_decode_image.argtypes = [cp, ctypes.POINTER(ci), ctypes.POINTER(ci), vp]
     L.ptb_set_jpeg_decode.argtypes = [cp]
+    # multi-GPU (csrc/multi.inc)
+    L.ptb_multi_create.restype = vp
+    L.ptb_multi_create.argtypes = [cp, ci, vp]
+    L.ptb_multi_destroy.argtypes = [vp]
+    L.ptb_multi_device_count.argtypes = [vp]
+    L.ptb_multi_renderer.restype = vp
+    L.ptb_multi_renderer.argtypes = [vp, ci]
+    L.ptb_multi_set_option.argtypes = [vp, cp, cp]
+    L.ptb_multi_load_scene.argtypes = [vp, cp, cp]
+    L.ptb_multi_set_camera.argtypes = [vp, ctypes.POINTER(Camera)]
+    L.ptb_multi_render.argtypes = [vp, ci]
+    L.ptb_multi_clear.argtypes = [vp]
+    L.ptb_multi_pass_counter.argtypes = [vp]
+    L.ptb_multi_image_f32.argtypes = [vp, vp, ctypes.POINTER(ci)]
+    L.ptb_multi_image_u8.argtypes = [vp, vp]
+    L.ptb_dist_unique_id.argtypes = [vp]
+    L.ptb_dist_init.argtypes = [vp, ci, ci, vp]
+    L.ptb_dist_shutdown.argtypes = [vp]
+    L.ptb_dist_broadcast_scene.argtypes = [vp, ci]
+    L.ptb_dist_render.argtypes = [vp, ci]
+    L.ptb_dist_reduce.argtypes = [vp, ci]
+    L.ptb_dist_clear.argtypes = [vp]
+    L.ptb_merged_image_f32.argtypes = [vp, vp, ctypes.POINTER(ci)]
+    L.ptb_merged_image_u8.argtypes = [vp, vp]
     _lib = L
     return L
 
@@ -197,9 +221,22 @@ class Renderer:
         self.width = self.lib.ptb_width(self.handle)
         self.height = self.lib.ptb_height(self.handle)
 
+    @classmethod
+    def _borrowed(cls, handle, device):
+        """View of a handle owned by someone else (MultiRenderer.renderer(i)): never destroyed from here."""
+        self = cls.__new__(cls)
+        self.lib = load_library()
+        self.handle = handle
+        self.device = device
+        self.width = self.lib.ptb_width(handle)
+        self.height = self.lib.ptb_height(handle)
+        self._owned = False
+        return self
+
     def close(self):
         if self.handle:
-            self.lib.ptb_destroy(self.handle)
+            if getattr(self, "_owned", True):
+                self.lib.ptb_destroy(self.handle)
             self.handle = None
 
     def __del__(self):
@@ -211,6 +248,38 @@ class Renderer:
     def _check(self, rc):
         if rc != 0:
             raise PtbError(last_error())
+
+    # -- one process per GPU: NCCL communicator, scene broadcast, sharded render, reduce (csrc/multi.inc) ---------
+    def dist_init(self, rank, world_size, unique_id):
+        buf = ctypes.create_string_buffer(bytes(unique_id), 128)
+        self._check(self.lib.ptb_dist_init(self.handle, int(rank), int(world_size), buf))
+
+    def dist_shutdown(self):
+        self.lib.ptb_dist_shutdown(self.handle)
+
+    def dist_broadcast_scene(self, root=0):
+        self._check(self.lib.ptb_dist_broadcast_scene(self.handle, int(root)))
+
+    def dist_render(self, total_passes):
+        self._check(self.lib.ptb_dist_render(self.handle, int(total_passes)))
+
+    def dist_reduce(self, root=0):
+        self._check(self.lib.ptb_dist_reduce(self.handle, int(root)))
+
+    def dist_clear(self):
+        self._check(self.lib.ptb_dist_clear(self.handle))
+
+    def merged_image_f32(self):
+        out = np.zeros((self.height, self.width, 3), np.float32)
+        n = ctypes.c_int()
+        self._check(self.lib.ptb_merged_image_f32(self.handle, _ptr(out), ctypes.byref(n)))
+        return out, n.value
+
+    def merged_image_u8(self, out=None):
+        if out is None:
+            out = np.zeros((self.height, self.width, 3), np.uint8)
+        self._check(self.lib.ptb_merged_image_u8(self.handle, _ptr(out)))
+        return out
 
     # -- scene ---------------------------------------------------------------------------------
     def load_scene(self, scene_json_path, asset_root=""):
@@ -429,6 +498,89 @@ class Renderer:
         s = Stats()
         self._check(self.lib.ptb_get_stats(self.handle, ctypes.byref(s)))
         return {k: getattr(s, k) for k, _ in Stats._fields_}
+
+
+def dist_unique_id():
+    """128-byte NCCL id for Renderer.dist_init: created on one rank, handed to all ranks by the host."""
+    buf = ctypes.create_string_buffer(128)
+    if load_library().ptb_dist_unique_id(buf) != 0:
+        raise PtbError(last_error())
+    return buf.raw
+
+
+def nccl_version():
+    return load_library().ptb_nccl_version()
+
+
+class MultiRenderer:
+    """One process, every GPU of the box (ptb_multi_*): the scene is parsed once, every device builds its own BVH, passes are
+    sharded by index, one NCCL reduce per render call merges the accumulation buffers on device 0."""
+
+    def __init__(self, config_json_path, n_devices, devices=None):
+        self.lib = load_library()
+        dev = None
+        if devices is not None:
+            dev = (ctypes.c_int * n_devices)(*[int(d) for d in devices])
+        self.handle = self.lib.ptb_multi_create(os.fsencode(config_json_path), int(n_devices), dev)
+        if not self.handle:
+            raise PtbError(last_error())
+        self.n_devices = n_devices
+        first = self.renderer(0)
+        self.width, self.height = first.width, first.height
+
+    def _check(self, rc):
+        if rc != 0:
+            raise PtbError(last_error())
+
+    def close(self):
+        if self.handle:
+            self.lib.ptb_multi_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def renderer(self, index):
+        h = self.lib.ptb_multi_renderer(self.handle, int(index))
+        if not h:
+            raise PtbError("device index out of range")
+        return Renderer._borrowed(h, index)
+
+    def set_option(self, key, value):
+        self._check(self.lib.ptb_multi_set_option(self.handle, key.encode(), str(value).encode()))
+
+    def load_scene(self, scene_json_path, asset_root=""):
+        self._check(self.lib.ptb_multi_load_scene(self.handle, os.fsencode(scene_json_path), os.fsencode(asset_root)))
+
+    def set_camera(self, cam):
+        if not isinstance(cam, Camera):
+            c = Camera()
+            ctypes.memmove(ctypes.byref(c), np.ascontiguousarray(cam).ctypes.data, 64)
+            cam = c
+        self._check(self.lib.ptb_multi_set_camera(self.handle, ctypes.byref(cam)))
+
+    def render(self, total_passes):
+        self._check(self.lib.ptb_multi_render(self.handle, int(total_passes)))
+
+    def clear(self):
+        self._check(self.lib.ptb_multi_clear(self.handle))
+
+    def pass_counter(self):
+        return self.lib.ptb_multi_pass_counter(self.handle)
+
+    def image_f32(self):
+        out = np.zeros((self.height, self.width, 3), np.float32)
+        n = ctypes.c_int()
+        self._check(self.lib.ptb_multi_image_f32(self.handle, _ptr(out), ctypes.byref(n)))
+        return out
+
+    def image_u8(self):
+        out = np.zeros((self.height, self.width, 3), np.uint8)
+        self._check(self.lib.ptb_multi_image_u8(self.handle, _ptr(out)))
+        return out
 
 
 class PathTracer:

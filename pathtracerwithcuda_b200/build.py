@@ -77,6 +77,23 @@ def build(force=False, verbose=False, extra_nvcc=None, out=None):
     return OUT
 
 
+ROOFS_SRC = os.path.join(HERE, "..", "tools", "roofs", "roofs.cu")
+ROOFS_OUT = os.path.join(HERE, "..", "tools", "roofs", "libptbroofs.so")
+
+
+def build_roofs(force=False):
+    """tools/roofs/libptbroofs.so: the FP32 / L2-gather / L1-gather roof microbenchmarks bench.py runs before its timed region
+    (measurement tooling; the product library neither links nor loads it)."""
+    src, out = os.path.normpath(ROOFS_SRC), os.path.normpath(ROOFS_OUT)
+    if not force and os.path.exists(out) and os.path.getmtime(out) >= os.path.getmtime(src):
+        return out
+    cmd = ["nvcc", "-std=c++17", "-O3", "-lineinfo"] + NVCC_ARCH + ["-shared", "-Xcompiler", "-fPIC", "-o", out, src]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("build failed: %s\n%s\n%s" % (" ".join(cmd), r.stdout, r.stderr))
+    return out
+
+
 if __name__ == "__main__":
     extra = []
     for a in sys.argv[1:]:
@@ -85,4 +102,5 @@ if __name__ == "__main__":
         elif a.startswith("--nvcc="):      # e.g. --nvcc=-Xptxas,-fmad=false  ->  -Xptxas -fmad=false
             extra += a.split("=", 1)[1].split(",")
     out = [a.split("=", 1)[1] for a in sys.argv[1:] if a.startswith("--out=")]
+    build_roofs(force="--force" in sys.argv)
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, extra_nvcc=extra or None, out=out[0] if out else None))

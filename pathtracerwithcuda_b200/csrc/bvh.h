@@ -30,6 +30,7 @@ struct Bvh2
 	std::vector<Bvh2Node> nodes;
 	std::vector<int> prim_order; // permutation of triangle indices
 	float sah_cost = 0.0f;
+	int max_depth = 0;           // depth of the deepest node (root = 0); the builders keep it below the traversal stack size
 };
 
 // Top-down binned surface-area-heuristic build (host, multi-threaded).

@@ -14,6 +14,7 @@ namespace
 
 const int kBins = 16;
 const float kTraversalCost = 1.0f;
+const int kDepthLimit = 40;   // as in bvh_build.cu
 
 inline void box_reset(Aabb& b)
 {
@@ -44,15 +45,18 @@ struct Builder
 	std::vector<PrimRef> prims;
 	std::vector<Bvh2Node>* nodes;
 	int max_leaf;
+	int max_depth = 0;
 	float kIntersectCost = 1.5f;
 
 	// builds the subtree for prims[first, first+count) into node `node_index`
 	void build(int node_index, int first, int count)
 	{
 		// explicit stack keeps deep, degenerate inputs from overflowing the call stack
-		struct Item { int node, first, count; };
+		// `depth`: at kDepthLimit and below SAH splits give way to halving by index (the same rule as the device builder,
+		// bvh_build.cu kDepthLimit), so the tree is never deeper than kDepthLimit + log2(n) < the 64-entry traversal stack
+		struct Item { int node, first, count, depth; };
 		std::vector<Item> stack;
-		stack.push_back({ node_index, first, count });
+		stack.push_back({ node_index, first, count, 0 });
 		while (!stack.empty())
 		{
 			Item it = stack.back();
@@ -65,7 +69,14 @@ struct Builder
 				for (int a = 0; a < 3; a++) { cbox.lo[a] = std::min(cbox.lo[a], prims[i].c[a]); cbox.hi[a] = std::max(cbox.hi[a], prims[i].c[a]); }
 			}
 			(*nodes)[it.node].box = box;
+			max_depth = std::max(max_depth, it.depth);
 			if (it.count <= 1) { make_leaf(it.node, it.first, it.count); continue; }
+			if (it.depth >= kDepthLimit)
+			{
+				if (it.count <= max_leaf) { make_leaf(it.node, it.first, it.count); continue; }
+				push_children(stack, it.node, it.first, it.first + it.count / 2, it.first + it.count, it.depth + 1);
+				continue;
+			}
 
 			int best_axis = -1, best_split = -1;
 			float best_cost = std::numeric_limits<float>::infinity();
@@ -111,7 +122,7 @@ struct Builder
 				// all centroids coincide: leaf if it fits, else split by index
 				if (it.count <= max_leaf) { make_leaf(it.node, it.first, it.count); continue; }
 				int mid = it.first + it.count / 2;
-				push_children(stack, it.node, it.first, mid, it.first + it.count);
+				push_children(stack, it.node, it.first, mid, it.first + it.count, it.depth + 1);
 				continue;
 			}
 			if (it.count <= max_leaf && leaf_cost <= split_cost) { make_leaf(it.node, it.first, it.count); continue; }
@@ -127,12 +138,12 @@ struct Builder
 			});
 			int mid = (int)(mid_it - prims.begin());
 			if (mid == it.first || mid == it.first + it.count) mid = it.first + it.count / 2;
-			push_children(stack, it.node, it.first, mid, it.first + it.count);
+			push_children(stack, it.node, it.first, mid, it.first + it.count, it.depth + 1);
 		}
 	}
 
 	template <class Stack>
-	void push_children(Stack& stack, int node, int first, int mid, int end)
+	void push_children(Stack& stack, int node, int first, int mid, int end, int depth)
 	{
 		int l = (int)nodes->size();
 		nodes->emplace_back();
@@ -140,8 +151,8 @@ struct Builder
 		(*nodes)[node].left = l;
 		(*nodes)[node].right = l + 1;
 		(*nodes)[node].count = 0;
-		stack.push_back({ l + 1, mid, end - mid });
-		stack.push_back({ l, first, mid - first });
+		stack.push_back({ l + 1, mid, end - mid, depth });
+		stack.push_back({ l, first, mid - first, depth });
 	}
 
 	void make_leaf(int node, int first, int count)
@@ -182,6 +193,7 @@ void build_bvh2_sah(const TriangleArray& tris, int max_leaf_size, Bvh2& out, flo
 	out.nodes.reserve((size_t)2 * n);
 	out.nodes.emplace_back();
 	b.build(0, 0, n);
+	out.max_depth = b.max_depth;
 	out.prim_order.resize(n);
 	for (int i = 0; i < n; i++) out.prim_order[i] = b.prims[i].index;
 

@@ -301,10 +301,23 @@ __device__ __forceinline__ void load_node(const float4* np, float4& n0, float4& 
 #ifndef PTB_PERSISTENT_MIN_BLOCKS
 #define PTB_PERSISTENT_MIN_BLOCKS 8
 #endif
+#ifndef PTB_PERSISTENT_MIN_BLOCKS8
+#define PTB_PERSISTENT_MIN_BLOCKS8 8
+#endif
 
-template <bool COUNT, int REPS>
-__global__ void __launch_bounds__(128, PTB_PERSISTENT_MIN_BLOCKS) k_extend_persistent(DeviceScene sc, PathState st, const int* __restrict__ queue, const int* __restrict__ count_ptr,
-	int* __restrict__ work_counter, unsigned long long* __restrict__ counters, int refill_min, int leaf_min, int node_reps)
+// Leaf phase: 1 = every vote tests ONE triangle per waiting lane (a lane with more triangles stays in the leaf state), so the lanes
+// of a leaf phase never idle behind the longest leaf; 0 = the whole leaf in one phase (round 1).
+#ifndef PTB_LEAF_SINGLE
+#define PTB_LEAF_SINGLE 1
+#endif
+
+// TREELET (k_extend_treelet below): the first `n_top` nodes of the array — the top levels of the tree, which the device builder
+// numbers level by level — are copied into shared memory by the block and fetched from there: every ray walks through them, and a
+// scattered 64-byte gather costs the L1 data stage ~1.45 cycles per lane (tools/roofs: 12.8 TB/s) where shared memory delivers it at
+// bank rate.  Blocks are then as large as the launch allows (one 1024-thread block per SM shares one copy).
+template <bool COUNT, int REPS, bool TREELET, bool STAGED>
+__device__ __forceinline__ void extend_persistent_body(const DeviceScene& sc, const PathState& st, const int* __restrict__ queue, const int* __restrict__ count_ptr,
+	int* __restrict__ work_counter, unsigned long long* __restrict__ counters, int refill_min, int leaf_min, int node_reps, const float4* s_top, int n_top, float4* s_stage)
 {
 	const int count = *count_ptr;
 	const unsigned lane = threadIdx.x & 31u;
@@ -315,12 +328,18 @@ __global__ void __launch_bounds__(128, PTB_PERSISTENT_MIN_BLOCKS) k_extend_persi
 	int id = -1;                 // path id this lane is tracing; -1 = idle
 	unsigned ray_nodes = 0;      // COUNT only: node visits of the current ray
 	bool exhausted = false;      // warp-uniform: the queue has been handed out completely
+	int staged = 0;              // STAGED: set-up rays waiting in this warp's shared-memory buffer (warp-uniform)
 	float3 o = make_float3(0, 0, 0), d = o, idir = o, noidir = o;
 	float margin2 = 0.0f;
 	HitRecord best;
 	best.t = CUDART_INF_F; best.t1 = 0.0f; best.t2 = 0.0f; best.prim = -1;
 	int best_tri = 0x7fffffff;
+	// per-thread traversal stack (local memory).  A shared-memory stack ([entry][thread], conflict-free at any depth mix) was measured
+	// 3-4 % SLOWER at every size tried (12 / 16 / 24 / 32 entries, profiles/r02_experiments.md) and is not kept.  The push is bounded:
+	// the builders keep every tree shallower than PTB_STACK_SIZE (render.cu rejects deeper ones), the guard costs nothing.
 	int stack[PTB_STACK_SIZE];
+#define PTB_PUSH(v) do { if (sp < PTB_STACK_SIZE) stack[sp] = (v); sp++; } while (0)
+#define PTB_POP(dst) do { --sp; dst = stack[min(sp, PTB_STACK_SIZE - 1)]; } while (0)
 	int sp = 0;
 	int node = PTB_DONE;         // >= 0 inner node, PTB_DONE = nothing left, other negative = leaf reference
 
@@ -350,6 +369,65 @@ __global__ void __launch_bounds__(128, PTB_PERSISTENT_MIN_BLOCKS) k_extend_persi
 		const unsigned m_node = __ballot_sync(FULL, has_ray && node >= 0);
 		const unsigned m_leaf = __ballot_sync(FULL, has_ray && node < 0);
 
+		if (STAGED)
+		{
+			// ---- STAGED refill: rays are fetched and set up 32 at a time by the WHOLE warp (every lane busy) into a shared-memory buffer;
+			// an idle lane then takes a ready ray for a dozen instructions, so idle lanes no longer wait until 20 of them justify the
+			// ~150-instruction divergent set-up — fewer lanes idle per issued instruction.
+			if (m_idle != 0u && (staged > 0 || !exhausted) && (__popc(m_idle) >= refill_min || (m_node | m_leaf) == 0u))
+			{
+				if (staged == 0)
+				{
+					int base = 0;
+					if (lane == 0) base = atomicAdd(work_counter, 32);
+					base = __shfl_sync(FULL, base, 0);
+					if (base + 32 >= count) exhausted = true;
+					staged = max(0, min(32, count - base));
+					const int i = base + (int)lane;
+					if (i < count)
+					{
+						const int rid = __ldcs(&queue[i]);
+						const float4 o4 = __ldcs(&st.ray_o[rid]), d4 = __ldcs(&st.ray_d[rid]);
+						const float3 ro = make_float3(o4.x, o4.y, o4.z), rd = make_float3(d4.x, d4.y, d4.z);
+						float bt = d4.w;
+						int bprim = -1;
+						for (int sidx = 0; sidx < sc.n_spheres; sidx++)
+						{
+							const float4 sph = __ldg(&sc.spheres[sidx]);
+							float t;
+							if (intersect_sphere(make_float3(sph.x, sph.y, sph.z), sph.w, ro, rd, t) && t < bt && t > 0.0f) { bt = t; bprim = -(sidx + 2); }
+						}
+						const float tiny = 1e-30f;
+						const float3 ds = make_float3(fabsf(rd.x) < tiny ? copysignf(tiny, rd.x) : rd.x, fabsf(rd.y) < tiny ? copysignf(tiny, rd.y) : rd.y,
+							fabsf(rd.z) < tiny ? copysignf(tiny, rd.z) : rd.z);
+						s_stage[lane] = make_float4(ro.x, ro.y, ro.z, bt);
+						s_stage[32 + lane] = make_float4(rd.x, rd.y, rd.z, __int_as_float(rid));
+						s_stage[64 + lane] = make_float4(1.0f / ds.x, 1.0f / ds.y, 1.0f / ds.z, __int_as_float(bprim));
+					}
+					__syncwarp();
+				}
+				const int rank = __popc(m_idle & lane_lt);
+				if (!has_ray && rank < staged)
+				{
+					const int slot = staged - 1 - rank;
+					const float4 a = s_stage[slot], b = s_stage[32 + slot], c = s_stage[64 + slot];
+					o = make_float3(a.x, a.y, a.z);
+					d = make_float3(b.x, b.y, b.z);
+					id = __float_as_int(b.w);
+					idir = make_float3(c.x, c.y, c.z);
+					best.t = a.w; best.t1 = CUDART_INF_F; best.t2 = CUDART_INF_F; best.prim = __float_as_int(c.w);
+					best_tri = 0x7fffffff;
+					noidir = make_float3(-o.x * idir.x, -o.y * idir.y, -o.z * idir.z);
+					margin2 = 4.8e-7f * fmaxf(fmaxf(fabsf(noidir.x), fabsf(noidir.y)), fabsf(noidir.z));
+					sp = 0;
+					node = sc.n_triangles > 0 ? sc.root_ref : PTB_DONE;
+				}
+				staged -= min(staged, __popc(m_idle));
+				__syncwarp();
+				continue;
+			}
+		}
+		else
 		if (m_idle != 0u && !exhausted && (__popc(m_idle) >= refill_min || (m_node | m_leaf) == 0u))
 		{
 			// ---- refill idle lanes from the queue: one atomic per warp
@@ -407,11 +485,17 @@ __global__ void __launch_bounds__(128, PTB_PERSISTENT_MIN_BLOCKS) k_extend_persi
 			{
 				const int ref = ~node;
 				const int first = ref >> 3;
+#if PTB_LEAF_SINGLE
+				{
+					if (COUNT) n_tris++;
+					const float4* tp = sc.tri_isect + (size_t)first * 3;
+#else
 				const int cnt = (ref & 7) + 1;
 				for (int k = 0; k < cnt; k++)
 				{
 					if (COUNT) n_tris++;
 					const float4* tp = sc.tri_isect + (size_t)(first + k) * 3;
+#endif
 					const float4 a = __ldg(tp + 0), b = __ldg(tp + 1), c = __ldg(tp + 2);
 					float t, t1, t2;
 					if (intersect_triangle(make_float3(a.x, a.y, a.z), make_float3(b.x, b.y, b.z), make_float3(c.x, c.y, c.z), o, d, t, t1, t2) && t > 0.0f)
@@ -423,7 +507,12 @@ __global__ void __launch_bounds__(128, PTB_PERSISTENT_MIN_BLOCKS) k_extend_persi
 						}
 					}
 				}
-				node = sp > 0 ? stack[--sp] : PTB_DONE;
+#if PTB_LEAF_SINGLE
+				// (first + 1, count - 1) is the same reference plus 7: ((first + 1) << 3 | (count - 2)) - (first << 3 | (count - 1))
+				if (ref & 7) node = ~(ref + 7);
+				else
+#endif
+				if (sp > 0) PTB_POP(node); else node = PTB_DONE;
 			}
 			continue;
 		}
@@ -438,7 +527,13 @@ __global__ void __launch_bounds__(128, PTB_PERSISTENT_MIN_BLOCKS) k_extend_persi
 			const float4* np = sc.bvh_nodes + (size_t)node * 4;
 			float4 n0, n1, n2;
 			float2 n3;
-			load_node(np, n0, n1, n2, n3);
+			if (TREELET && node < n_top)
+			{
+				const float4* sp4 = s_top + node * 4;
+				n0 = sp4[0]; n1 = sp4[1]; n2 = sp4[2];
+				n3 = *reinterpret_cast<const float2*>(sp4 + 3);
+			}
+			else load_node(np, n0, n1, n2, n3);
 			const float c0x0 = fmaf(n0.x, idir.x, noidir.x), c0x1 = fmaf(n0.y, idir.x, noidir.x);
 			const float c0y0 = fmaf(n0.z, idir.y, noidir.y), c0y1 = fmaf(n0.w, idir.y, noidir.y);
 			const float c0z0 = fmaf(n2.x, idir.z, noidir.z), c0z1 = fmaf(n2.y, idir.z, noidir.z);
@@ -458,8 +553,209 @@ __global__ void __launch_bounds__(128, PTB_PERSISTENT_MIN_BLOCKS) k_extend_persi
 			const int near_c = swap ? child1 : child0;
 			const int far_c = swap ? child0 : child1;
 			int next = both ? near_c : (h0 ? child0 : (h1 ? child1 : PTB_DONE));
-			if (both) stack[sp++] = far_c;
-			else if (!(h0 || h1) && sp > 0) next = stack[--sp];
+			if (both) PTB_PUSH(far_c);
+			else if (!(h0 || h1) && sp > 0) PTB_POP(next);
+			node = next;
+		}
+	}
+	if (COUNT)
+	{
+		for (int off = 16; off > 0; off >>= 1)
+		{
+			n_nodes += __shfl_down_sync(FULL, n_nodes, off);
+			n_tris += __shfl_down_sync(FULL, n_tris, off);
+		}
+		if (lane == 0)
+		{
+			atomicAdd(&counters[0], (unsigned long long)n_nodes);
+			atomicAdd(&counters[1], (unsigned long long)n_tris);
+		}
+	}
+}
+
+#undef PTB_PUSH
+#undef PTB_POP
+
+template <bool COUNT, int REPS>
+__global__ void __launch_bounds__(128, PTB_PERSISTENT_MIN_BLOCKS) k_extend_persistent(DeviceScene sc, PathState st, const int* __restrict__ queue, const int* __restrict__ count_ptr,
+	int* __restrict__ work_counter, unsigned long long* __restrict__ counters, int refill_min, int leaf_min, int node_reps)
+{
+	extend_persistent_body<COUNT, REPS, false, false>(sc, st, queue, count_ptr, work_counter, counters, refill_min, leaf_min, node_reps, nullptr, 0, nullptr);
+}
+
+// STAGED refill (extend_variant 4): 96 float4 (1.5 KB) of shared memory per warp hold 32 set-up rays
+template <bool COUNT>
+__global__ void __launch_bounds__(128, PTB_PERSISTENT_MIN_BLOCKS) k_extend_staged(DeviceScene sc, PathState st, const int* __restrict__ queue, const int* __restrict__ count_ptr,
+	int* __restrict__ work_counter, unsigned long long* __restrict__ counters, int refill_min, int leaf_min)
+{
+	__shared__ float4 s_stage_all[4 * 96];
+	extend_persistent_body<COUNT, 6, false, true>(sc, st, queue, count_ptr, work_counter, counters, refill_min, leaf_min, 6, nullptr, 0, s_stage_all + (threadIdx.x >> 5) * 96);
+}
+
+// up to 1024 threads per block (1 x 1024 or 2 x 512 per SM: 64 registers per thread either way), dynamic shared memory = n_top x 64 bytes
+template <bool COUNT>
+__global__ void __launch_bounds__(1024, 1) k_extend_treelet(DeviceScene sc, PathState st, const int* __restrict__ queue, const int* __restrict__ count_ptr,
+	int* __restrict__ work_counter, unsigned long long* __restrict__ counters, int refill_min, int leaf_min, int n_top)
+{
+	extern __shared__ float4 s_top_nodes[];
+	for (int i = threadIdx.x; i < n_top * 4; i += blockDim.x) s_top_nodes[i] = __ldg(sc.bvh_nodes + i);
+	__syncthreads();
+	extend_persistent_body<COUNT, 6, true, false>(sc, st, queue, count_ptr, work_counter, counters, refill_min, leaf_min, 6, s_top_nodes, n_top, nullptr);
+}
+
+
+// ------------------------------------------------------------------------------------------
+// k_extend_speculative — k_extend_persistent with POSTPONED LEAVES (after Aila & Laine 2009, "speculative traversal"):
+// a lane that reaches a leaf parks it in `leaf` and keeps traversing (pops the next node) for the rest of the node phase instead of
+// idling until enough lanes wait at a leaf; it only stalls when it meets a second leaf.  The parked leaf's first triangle can be
+// prefetched into L1 meanwhile (PREFETCH).  Culling uses whatever best.t the lane has at that moment, so postponing a leaf can only
+// visit MORE nodes, never miss one: hits are identical (tests/test_gpu_parity.py runs every variant against the exhaustive scan).
+// ------------------------------------------------------------------------------------------
+template <bool COUNT, bool PREFETCH>
+__global__ void __launch_bounds__(128, PTB_PERSISTENT_MIN_BLOCKS) k_extend_speculative(DeviceScene sc, PathState st, const int* __restrict__ queue, const int* __restrict__ count_ptr,
+	int* __restrict__ work_counter, unsigned long long* __restrict__ counters, int refill_min, int leaf_min)
+{
+	const int count = *count_ptr;
+	const unsigned lane = threadIdx.x & 31u;
+	const unsigned lane_lt = (1u << lane) - 1u;
+	const unsigned FULL = 0xffffffffu;
+	unsigned n_nodes = 0, n_tris = 0;
+
+	int id = -1;
+	bool exhausted = false;
+	float3 o = make_float3(0, 0, 0), d = o, idir = o, noidir = o;
+	float margin2 = 0.0f;
+	HitRecord best;
+	best.t = CUDART_INF_F; best.t1 = 0.0f; best.t2 = 0.0f; best.prim = -1;
+	int best_tri = 0x7fffffff;
+	int stack[PTB_STACK_SIZE];
+	int sp = 0;
+	int node = PTB_DONE;         // >= 0 inner node, PTB_DONE = nothing left, other negative = a leaf this lane is stuck at (slot taken)
+	int leaf = 0;                // < 0: parked leaf reference still to be tested, 0: none
+
+	while (true)
+	{
+		if (id >= 0 && node == PTB_DONE && leaf == 0)
+		{
+			__stcs(&st.hit[id], make_float4(best.prim == -1 ? CUDART_INF_F : best.t, best.t1, best.t2, __int_as_float(best.prim)));
+			id = -1;
+		}
+		const bool has_ray = id >= 0;
+		const unsigned m_idle = __ballot_sync(FULL, !has_ray);
+		const unsigned m_node = __ballot_sync(FULL, has_ray && node >= 0);
+		const unsigned m_leaf = __ballot_sync(FULL, has_ray && leaf < 0);
+
+		if (m_idle != 0u && !exhausted && (__popc(m_idle) >= refill_min || (m_node | m_leaf) == 0u))
+		{
+			const int n = __popc(m_idle);
+			int base = 0;
+			if (lane == 0) base = atomicAdd(work_counter, n);
+			base = __shfl_sync(FULL, base, 0);
+			if (base + n >= count) exhausted = true;
+			if (!has_ray)
+			{
+				const int i = base + __popc(m_idle & lane_lt);
+				if (i < count)
+				{
+					id = __ldcs(&queue[i]);
+					const float4 o4 = __ldcs(&st.ray_o[id]), d4 = __ldcs(&st.ray_d[id]);
+					o = make_float3(o4.x, o4.y, o4.z);
+					d = make_float3(d4.x, d4.y, d4.z);
+					best.t = d4.w; best.t1 = CUDART_INF_F; best.t2 = CUDART_INF_F; best.prim = -1;
+					best_tri = 0x7fffffff;
+					for (int s = 0; s < sc.n_spheres; s++)
+					{
+						const float4 sph = __ldg(&sc.spheres[s]);
+						float t;
+						if (intersect_sphere(make_float3(sph.x, sph.y, sph.z), sph.w, o, d, t) && t < best.t && t > 0.0f)
+						{
+							best.t = t;
+							best.prim = -(s + 2);
+						}
+					}
+					const float tiny = 1e-30f;
+					const float3 ds = make_float3(fabsf(d.x) < tiny ? copysignf(tiny, d.x) : d.x, fabsf(d.y) < tiny ? copysignf(tiny, d.y) : d.y,
+						fabsf(d.z) < tiny ? copysignf(tiny, d.z) : d.z);
+					idir = make_float3(1.0f / ds.x, 1.0f / ds.y, 1.0f / ds.z);
+					noidir = make_float3(-o.x * idir.x, -o.y * idir.y, -o.z * idir.z);
+					margin2 = 4.8e-7f * fmaxf(fmaxf(fabsf(noidir.x), fabsf(noidir.y)), fabsf(noidir.z));
+					sp = 0;
+					leaf = 0;
+					node = sc.n_triangles > 0 ? sc.root_ref : PTB_DONE;
+				}
+			}
+			continue;
+		}
+		if ((m_node | m_leaf) == 0u) break;
+
+		if (m_leaf != 0u && (__popc(m_leaf) >= leaf_min || m_node == 0u))
+		{
+			// ---- leaf phase: ONE triangle of the parked leaf per vote; leaf = ~((first << 3) | (count - 1))
+			if (has_ray && leaf < 0)
+			{
+				const int ref = ~leaf;
+				if (COUNT) n_tris++;
+				const float4* tp = sc.tri_isect + (size_t)(ref >> 3) * 3;
+				const float4 a = __ldg(tp + 0), b = __ldg(tp + 1), c = __ldg(tp + 2);
+				float t, t1, t2;
+				if (intersect_triangle(make_float3(a.x, a.y, a.z), make_float3(b.x, b.y, b.z), make_float3(c.x, c.y, c.z), o, d, t, t1, t2) && t > 0.0f)
+				{
+					const int tid = __float_as_int(a.w);
+					if (t < best.t || (t == best.t && best.prim >= 0 && tid < best_tri))
+					{
+						best.t = t; best.t1 = t1; best.t2 = t2; best.prim = tid; best_tri = tid;
+					}
+				}
+				if (ref & 7) leaf = ~(ref + 7);          // (first + 1, count - 1)
+				else if (node < 0 && node != PTB_DONE)
+				{
+					// the leaf this lane was stuck at moves into the slot; traversal resumes from the stack
+					leaf = node;
+					if (PREFETCH) asm volatile("prefetch.global.L1 [%0];" :: "l"(sc.tri_isect + (size_t)((~leaf) >> 3) * 3));
+					node = sp > 0 ? stack[--sp] : PTB_DONE;
+				}
+				else leaf = 0;
+			}
+			continue;
+		}
+
+		// ---- node phase
+#pragma unroll
+		for (int rep = 0; rep < 6; rep++)
+		if (id >= 0 && node >= 0)
+		{
+			if (COUNT) n_nodes++;
+			const float4* np = sc.bvh_nodes + (size_t)node * 4;
+			float4 n0, n1, n2;
+			float2 n3;
+			load_node(np, n0, n1, n2, n3);
+			const float c0x0 = fmaf(n0.x, idir.x, noidir.x), c0x1 = fmaf(n0.y, idir.x, noidir.x);
+			const float c0y0 = fmaf(n0.z, idir.y, noidir.y), c0y1 = fmaf(n0.w, idir.y, noidir.y);
+			const float c0z0 = fmaf(n2.x, idir.z, noidir.z), c0z1 = fmaf(n2.y, idir.z, noidir.z);
+			const float c1x0 = fmaf(n1.x, idir.x, noidir.x), c1x1 = fmaf(n1.y, idir.x, noidir.x);
+			const float c1y0 = fmaf(n1.z, idir.y, noidir.y), c1y1 = fmaf(n1.w, idir.y, noidir.y);
+			const float c1z0 = fmaf(n2.z, idir.z, noidir.z), c1z1 = fmaf(n2.w, idir.z, noidir.z);
+			const float tmin0 = fmaxf(fmaxf(fminf(c0x0, c0x1), fminf(c0y0, c0y1)), fmaxf(fminf(c0z0, c0z1), 0.0f));
+			const float tmax0 = fminf(fminf(fmaxf(c0x0, c0x1), fmaxf(c0y0, c0y1)), fminf(fmaxf(c0z0, c0z1), best.t));
+			const float tmin1 = fmaxf(fmaxf(fminf(c1x0, c1x1), fminf(c1y0, c1y1)), fmaxf(fminf(c1z0, c1z1), 0.0f));
+			const float tmax1 = fminf(fminf(fmaxf(c1x0, c1x1), fmaxf(c1y0, c1y1)), fminf(fmaxf(c1z0, c1z1), best.t));
+			const bool h0 = fmaf(tmin0, PTB_SLACK_LO / PTB_SLACK_HI, -margin2) <= tmax0;
+			const bool h1 = fmaf(tmin1, PTB_SLACK_LO / PTB_SLACK_HI, -margin2) <= tmax1;
+			const int child0 = __float_as_int(n3.x), child1 = __float_as_int(n3.y);
+			const bool both = h0 && h1;
+			const bool swap = tmin1 < tmin0;
+			const int near_c = swap ? child1 : child0;
+			const int far_c = swap ? child0 : child1;
+			int next = both ? near_c : (h0 ? child0 : (h1 ? child1 : PTB_DONE));
+			if (both) { if (sp < PTB_STACK_SIZE) stack[sp] = far_c; sp++; }
+			else if (!(h0 || h1) && sp > 0) next = stack[min(--sp, PTB_STACK_SIZE - 1)];
+			if (next < 0 && next != PTB_DONE && leaf == 0)
+			{
+				// park the leaf, keep traversing
+				leaf = next;
+				if (PREFETCH) asm volatile("prefetch.global.L1 [%0];" :: "l"(sc.tri_isect + (size_t)((~leaf) >> 3) * 3));
+				next = sp > 0 ? stack[min(--sp, PTB_STACK_SIZE - 1)] : PTB_DONE;
+			}
 			node = next;
 		}
 	}
@@ -485,7 +781,7 @@ __global__ void __launch_bounds__(128, PTB_PERSISTENT_MIN_BLOCKS) k_extend_persi
 // Phases: refill | wide-node step (one child popped, 8 quantised boxes decoded and tested) | triangle step.
 // ------------------------------------------------------------------------------------------
 template <bool COUNT>
-__global__ void __launch_bounds__(128, PTB_PERSISTENT_MIN_BLOCKS) k_extend_persistent8(DeviceScene sc, PathState st, const int* __restrict__ queue, const int* __restrict__ count_ptr,
+__global__ void __launch_bounds__(128, PTB_PERSISTENT_MIN_BLOCKS8) k_extend_persistent8(DeviceScene sc, PathState st, const int* __restrict__ queue, const int* __restrict__ count_ptr,
 	int* __restrict__ work_counter, unsigned long long* __restrict__ counters, int refill_min, int leaf_min)
 {
 	const int count = *count_ptr;
@@ -502,6 +798,8 @@ __global__ void __launch_bounds__(128, PTB_PERSISTENT_MIN_BLOCKS) k_extend_persi
 	best.t = CUDART_INF_F; best.t1 = 0.0f; best.t2 = 0.0f; best.prim = -1;
 	int best_tri = 0x7fffffff;
 	uint2 stack[PTB_STACK_SIZE8];
+#define PTB_PUSH8(v) do { if (sp < PTB_STACK_SIZE8) stack[sp] = (v); sp++; } while (0)
+#define PTB_POP8(dst) do { --sp; dst = stack[min(sp, PTB_STACK_SIZE8 - 1)]; } while (0)
 	int sp = 0;
 	uint2 current = make_uint2(0u, 0u), tri_group = make_uint2(0u, 0u);
 
@@ -510,7 +808,7 @@ __global__ void __launch_bounds__(128, PTB_PERSISTENT_MIN_BLOCKS) k_extend_persi
 		// bookkeeping without votes: pop a node group when the lane ran dry, retire when nothing is left
 		if (id >= 0 && (current.y & 0xff000000u) == 0u && tri_group.y == 0u)
 		{
-			if (sp > 0) current = stack[--sp];
+			if (sp > 0) PTB_POP8(current);
 			else
 			{
 				__stcs(&st.hit[id], make_float4(best.prim == -1 ? CUDART_INF_F : best.t, best.t1, best.t2, __int_as_float(best.prim)));
@@ -571,8 +869,12 @@ __global__ void __launch_bounds__(128, PTB_PERSISTENT_MIN_BLOCKS) k_extend_persi
 			// ---- triangle phase
 			if (at_tri)
 			{
+#if PTB_LEAF_SINGLE
+				{
+#else
 				while (tri_group.y)
 				{
+#endif
 					const unsigned k = 31u - __clz(tri_group.y);
 					tri_group.y &= ~(1u << k);
 					if (COUNT) n_tris++;
@@ -599,7 +901,7 @@ __global__ void __launch_bounds__(128, PTB_PERSISTENT_MIN_BLOCKS) k_extend_persi
 			const unsigned child_index_offset = 31u - __clz(hits_imask);
 			const unsigned child_index_base = current.x;
 			current.y &= ~(1u << child_index_offset);
-			if (current.y & 0xff000000u) { if (sp < PTB_STACK_SIZE8) stack[sp++] = current; }
+			if (current.y & 0xff000000u) PTB_PUSH8(current);
 			const unsigned slot_index = (child_index_offset - 24u) ^ (oct_inv4 & 0xffu);
 			const unsigned relative_index = __popc(hits_imask & ~(0xffffffffu << slot_index));
 			const unsigned node_index = child_index_base + relative_index;
@@ -658,6 +960,9 @@ __global__ void __launch_bounds__(128, PTB_PERSISTENT_MIN_BLOCKS) k_extend_persi
 		}
 	}
 }
+
+#undef PTB_PUSH8
+#undef PTB_POP8
 
 // brute-force closest hit over every primitive (test hook; same acceptance arithmetic)
 __global__ void k_bruteforce(DeviceScene sc, const float4* __restrict__ ray_o, const float4* __restrict__ ray_d, float4* __restrict__ hit, int n)

@@ -40,7 +40,7 @@ __global__ void __launch_bounds__(256) k_generate(PathState st, int* __restrict_
 	int tid = blockIdx.x * blockDim.x + threadIdx.x;
 	// counts[0..n_counts) = live paths per depth; counts[n_counts..2*n_counts) = per-depth work-fetch cursors of the persistent
 	// extend kernel; counts[2*n_counts..3*n_counts) = shadow rays per depth (estimator "nee")
-	if (tid < 3 * n_counts) counts[tid] = tid == 0 ? total : 0;
+	for (int c = tid; c < 3 * n_counts; c += gridDim.x * blockDim.x) counts[c] = c == 0 ? total : 0;   // any grid size, any MaxDepth
 	for (int i = tid; i < total; i += gridDim.x * blockDim.x)
 	{
 		int slot = i / pixel_count;

@@ -38,6 +38,31 @@ namespace ptb
 #include "kernels_extend.cuh"
 #include "kernels_shade.cuh"
 
+#ifdef PTB_EXPERIMENT_SORT
+// EXPERIMENT ONLY (tools/build_variants.sh "sortexp", never in the shipped library): upper bound of what re-ordering a bounce queue by
+// origin cell + direction octant can buy the closest-hit kernel — a full radix sort by a library, its cost ignored.
+#include <cub/cub.cuh>
+namespace ptb
+{
+__device__ __forceinline__ unsigned spread3(unsigned v) { v &= 0x3ffu; v = (v | (v << 16)) & 0x030000ffu; v = (v | (v << 8)) & 0x0300f00fu; v = (v | (v << 4)) & 0x030c30c3u; v = (v | (v << 2)) & 0x09249249u; return v; }
+__global__ void k_sort_keys(PathState st, const int* __restrict__ queue, const int* __restrict__ count_ptr, unsigned* __restrict__ keys, int total, float3 lo, float3 inv_extent, int cell_bits, int use_octant)
+{
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= total) return;
+	if (i >= *count_ptr) { keys[i] = 0xffffffffu; return; }
+	const int id = queue[i];
+	const float4 o = st.ray_o[id], d = st.ray_d[id];
+	const unsigned scale = 1u << cell_bits;
+	const unsigned cx = min(scale - 1u, (unsigned)max(0.0f, (o.x - lo.x) * inv_extent.x * scale));
+	const unsigned cy = min(scale - 1u, (unsigned)max(0.0f, (o.y - lo.y) * inv_extent.y * scale));
+	const unsigned cz = min(scale - 1u, (unsigned)max(0.0f, (o.z - lo.z) * inv_extent.z * scale));
+	const unsigned morton = spread3(cx) | (spread3(cy) << 1) | (spread3(cz) << 2);
+	const unsigned oct = use_octant ? ((d.x < 0.0f ? 1u : 0u) | (d.y < 0.0f ? 2u : 0u) | (d.z < 0.0f ? 4u : 0u)) : 0u;
+	keys[i] = use_octant == 2 ? ((morton << 3) | oct) : ((oct << (3 * cell_bits)) | morton);
+}
+}
+#endif
+
 // ==========================================================================================
 // Renderer
 // ==========================================================================================
@@ -73,6 +98,8 @@ struct ptb_renderer
 	int sort_by_material = 0;              // block-local material sort in k_shade (measured: profiles/r01_experiments.md)
 	int octant_order = 0;                  // next-depth queue grouped by ray-direction octant per block (measured: profiles/r01_experiments.md)
 	int tile_order = 1;                    // camera rays enter the first queue in 8x4 pixel tiles
+	int l2_persist = 0;                    // 1: binary nodes + leaf-order triangles in one arena under a persisting L2 access-policy window (measured: profiles/r02_experiments.md)
+	void* l2_arena = nullptr; size_t l2_arena_bytes = 0;
 	// facts about the last acceleration-structure build (ptb_bvh_info)
 	int bvh_collapsed_on_gpu = 0;
 	std::string bvh_collapse = "gpu";      // "gpu" (csrc/bvh_build.cu: k_collapse8) | "host" (csrc/bvh_host.cpp: build_bvh8)
@@ -80,6 +107,12 @@ struct ptb_renderer
 	double bvh_build_ms = 0.0, scene_upload_ms = 0.0;
 	std::string bvh_note;
 	int extend_persistent = 1;
+	int tune_refill4 = 8;                  // extend_variant 4: pop staged rays when >= N lanes are idle
+	int treelet_block = 1024, treelet_nodes = 1023;   // extend_variant 3: threads per block and top-of-tree nodes held in shared memory (64 B each)
+	int sort_depth_mask = 0, sort_cell_bits = 5, sort_octant = 1;   // PTB_EXPERIMENT_SORT builds only
+	unsigned* sort_keys[2] = { nullptr, nullptr }; int* sort_vals = nullptr; void* sort_tmp = nullptr; size_t sort_tmp_bytes = 0;
+	float scene_lo[3] = { 0, 0, 0 }, scene_hi[3] = { 1, 1, 1 };
+	int extend_variant = 0;                // binary-tree kernel: 0 = k_extend_persistent, 1 = k_extend_speculative (postponed leaves), 2 = + leaf prefetch
 	int persistent_grid = 148 * 4;
 	int persistent_grid8 = 148 * 4;
 	// voting thresholds of the persistent kernels (tools/sweep_tune.py, profiles/r01_experiments.md): refill when >= N lanes are idle,
@@ -128,6 +161,14 @@ struct ptb_renderer
 	std::vector<BatchContext> contexts;      // size streams_in_flight; [0] aliases the members above
 	unsigned long long* segment_totals = nullptr;   // per-depth live-path totals of the current call (device)
 
+	// multi-GPU (csrc/multi.inc): NCCL communicator of this device, its rank, and the merged image a reduce leaves on the root
+	void* nccl_comm = nullptr;
+	int dist_rank = 0, dist_world = 1, dist_global_passes = 0;
+	float* merged_sum = nullptr;
+	uint8_t* merged_u8 = nullptr;
+	int merged_passes = 0;
+	unsigned long long* pass_count_dev = nullptr;
+
 	ptb_stats stats;
 	int64_t traversal_histogram[32] = { 0 };  // raw device counters of the last count_traversal call
 	std::vector<double> depth_extend_ms;   // per-depth sums of the last call (profile_stages)
@@ -166,6 +207,8 @@ void free_path_state(PathState& st, int* queue[2], int** counts)
 	st = PathState(); queue[0] = queue[1] = nullptr; *counts = nullptr;
 }
 
+void apply_l2_window(ptb_renderer* r);
+
 int alloc_work_buffers(ptb_renderer* r)
 {
 	r->pixel_count = r->cfg.width * r->cfg.height;
@@ -198,6 +241,7 @@ int alloc_work_buffers(ptb_renderer* r)
 	PTB_CUDA(cudaMemsetAsync(r->image_u8, 0, (size_t)r->pixel_count * 3, r->stream));
 	PTB_CUDA(cudaMemsetAsync(r->counters, 0, 32 * sizeof(unsigned long long), r->stream));
 	PTB_CUDA(cudaStreamSynchronize(r->stream));
+	apply_l2_window(r);   // new streams: re-apply the access-policy window of option l2_persist
 	return 0;
 }
 
@@ -216,6 +260,8 @@ void free_work_buffers(ptb_renderer* r)
 	cudaFree(r->counters); cudaFree(r->segment_totals);
 	if (r->counts_host) cudaFreeHost(r->counts_host);
 	cudaFree(r->image_sum); cudaFree(r->last_pass); cudaFree(r->image_u8);
+	cudaFree(r->merged_sum); cudaFree(r->merged_u8); cudaFree(r->pass_count_dev);
+	r->merged_sum = nullptr; r->merged_u8 = nullptr; r->pass_count_dev = nullptr; r->merged_passes = 0;
 	r->counts_host = nullptr; r->counters = nullptr; r->segment_totals = nullptr;
 	r->image_sum = nullptr; r->last_pass = nullptr; r->image_u8 = nullptr;
 }
@@ -315,6 +361,40 @@ int download_bvh2(const GpuBuildOutput& gb, Bvh2& out)
 	return 0;
 }
 
+// Option l2_persist: the binary tree's nodes and its leaf-order triangles are moved into ONE allocation and every render stream gets a
+// persisting access-policy window over it (cudaStreamAttributeAccessPolicyWindow), everything else in those streams is "streaming":
+// the tree the traversal kernels gather from is protected against the path-state records streaming through L2.
+void apply_l2_window(ptb_renderer* r)
+{
+	if (r->host_only) return;
+	cudaStreamAttrValue attr;
+	memset(&attr, 0, sizeof(attr));
+	if (r->l2_persist && r->l2_arena && r->l2_arena_bytes)
+	{
+		int max_window = 0, max_persist = 0;
+		cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, r->device);
+		cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, r->device);
+		const size_t bytes = std::min<size_t>(r->l2_arena_bytes, (size_t)std::max(max_window, 0));
+		cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, std::min<size_t>(bytes, (size_t)std::max(max_persist, 0)));
+		attr.accessPolicyWindow.base_ptr = r->l2_arena;
+		attr.accessPolicyWindow.num_bytes = bytes;
+		attr.accessPolicyWindow.hitRatio = max_persist > 0 ? std::min(1.0f, (float)max_persist / (float)std::max<size_t>(bytes, 1)) : 0.0f;
+		attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+		attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+	}
+	else
+	{
+		attr.accessPolicyWindow.num_bytes = 0;
+		attr.accessPolicyWindow.hitProp = cudaAccessPropertyNormal;
+		attr.accessPolicyWindow.missProp = cudaAccessPropertyNormal;
+	}
+	if (r->stream) cudaStreamSetAttribute(r->stream, cudaStreamAttributeAccessPolicyWindow, &attr);
+	for (size_t c = 1; c < r->contexts.size(); c++)
+		if (r->contexts[c].stream) cudaStreamSetAttribute(r->contexts[c].stream, cudaStreamAttributeAccessPolicyWindow, &attr);
+	if (!(r->l2_persist && r->l2_arena)) cudaCtxResetPersistingL2Cache();
+	cudaGetLastError();
+}
+
 // triangles, acceleration structure and shading attributes (re-run by mesh edits: the BVH is REBUILT on the
 // device — 5-65 ms for 0.15-5 M triangles — where the reference only re-transforms the old boxes,
 // Bvh/bvh.cpp:332-356)
@@ -330,6 +410,14 @@ int upload_geometry(ptb_renderer* r)
 	// raw triangles + material indices on the device: the builder, the leaf-order emitter and the
 	// shading-attribute packer all read them there
 	const int n_tris = (int)s.triangles.size();
+#ifdef PTB_EXPERIMENT_SORT
+	for (int a = 0; a < 3; a++) { r->scene_lo[a] = INFINITY; r->scene_hi[a] = -INFINITY; }
+	for (int i = 0; i < n_tris; i++)
+	{
+		const float* v = (const float*)&s.triangles[i];
+		for (int k = 0; k < 3; k++) for (int a = 0; a < 3; a++) { r->scene_lo[a] = std::min(r->scene_lo[a], v[k * 3 + a]); r->scene_hi[a] = std::max(r->scene_hi[a], v[k * 3 + a]); }
+	}
+#endif
 	const float* d_tris24 = nullptr;
 	const int* d_material = nullptr;
 	if (upload(r, (const float*)s.triangles.data(), (size_t)n_tris * 24, &d_tris24, G)) return 1;
@@ -403,6 +491,8 @@ int upload_geometry(ptb_renderer* r)
 		const auto t0 = std::chrono::steady_clock::now();
 		build_bvh2_sah(s.triangles, max_leaf, bvh, r->bvh_intersect_cost);
 		r->bvh_build_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+		r->bvh_max_depth = bvh.max_depth;
+		if (bvh.max_depth >= PTB_STACK_SIZE) { set_error("[Error]BVH too deep for the traversal stack"); return 1; }
 	}
 	if (r->bvh_layout == 8 && !have_device_bvh8)
 	{
@@ -489,6 +579,25 @@ int upload_geometry(ptb_renderer* r)
 		pack_tri_shade_gpu(d_tris24, d_material, n_tris, d_shade, r->stream);
 		ds.tri_shade = d_shade;
 	}
+	r->l2_arena = nullptr; r->l2_arena_bytes = 0;
+	if (r->l2_persist && ds.bvh_layout == 2 && ds.bvh_nodes && ds.tri_isect && n_tris > 0)
+	{
+		const size_t node_bytes = ((size_t)r->bvh_nodes * 64 + 255) & ~(size_t)255, tri_bytes = (size_t)n_tris * 48;
+		char* arena = nullptr;
+		PTB_CUDA(cudaMalloc(&arena, node_bytes + tri_bytes));
+		PTB_CUDA(cudaMemcpyAsync(arena, ds.bvh_nodes, (size_t)r->bvh_nodes * 64, cudaMemcpyDeviceToDevice, r->stream));
+		PTB_CUDA(cudaMemcpyAsync(arena + node_bytes, ds.tri_isect, tri_bytes, cudaMemcpyDeviceToDevice, r->stream));
+		PTB_CUDA(cudaStreamSynchronize(r->stream));
+		for (const void* old_ptr : { (const void*)ds.bvh_nodes, (const void*)ds.tri_isect })
+		{
+			auto it = std::find(G->begin(), G->end(), (void*)old_ptr);
+			if (it != G->end()) { cudaFree(*it); G->erase(it); }
+		}
+		G->push_back(arena);
+		ds.bvh_nodes = (const float4*)arena; ds.tri_isect = (const float4*)(arena + node_bytes);
+		r->l2_arena = arena; r->l2_arena_bytes = node_bytes + tri_bytes;
+	}
+	apply_l2_window(r);
 	PTB_CUDA(cudaStreamSynchronize(r->stream));
 	PTB_CUDA(cudaGetLastError());
 	return 0;
@@ -646,6 +755,40 @@ void launch_extend(ptb_renderer* r, cudaStream_t stream, size_t items, const Pat
 	{
 		// persistent warps: one resident wave, sized from the occupancy the kernel actually gets
 		int grid = std::max(1, std::min(r->persistent_grid, (int)((items + 127) / 128)));
+		if (r->extend_variant == 4)
+		{
+			// staged refill (kernels_extend.cuh: k_extend_staged): rays set up 32 at a time into shared memory, idle lanes pop ready rays
+			if (r->count_traversal) k_extend_staged<true><<<grid, 128, 0, stream>>>(r->dscene, st, queue, count_ptr, work_counter, r->counters, r->tune_refill4, r->tune_leaf);
+			else k_extend_staged<false><<<grid, 128, 0, stream>>>(r->dscene, st, queue, count_ptr, work_counter, r->counters, r->tune_refill4, r->tune_leaf);
+			return;
+		}
+		if (r->extend_variant == 3)
+		{
+			// top of the tree in shared memory, blocks as large as the SM allows (kernels_extend.cuh: k_extend_treelet)
+			const int n_top = (int)std::max<int64_t>(0, std::min<int64_t>(r->treelet_nodes, r->bvh_nodes));
+			const int block = std::max(128, std::min(1024, r->treelet_block)) & ~31;
+			const size_t smem = (size_t)n_top * 64;
+			static bool attr_set = false;
+			if (!attr_set)
+			{
+				cudaFuncSetAttribute(k_extend_treelet<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+				cudaFuncSetAttribute(k_extend_treelet<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+				attr_set = true;
+			}
+			int per_sm = 1;
+			cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_extend_treelet<false>, block, smem);
+			const int tgrid = std::max(1, std::min(r->sm_count * std::max(per_sm, 1), (int)((items + block - 1) / block)));
+			if (r->count_traversal) k_extend_treelet<true><<<tgrid, block, smem, stream>>>(r->dscene, st, queue, count_ptr, work_counter, r->counters, r->tune_refill, r->tune_leaf, n_top);
+			else k_extend_treelet<false><<<tgrid, block, smem, stream>>>(r->dscene, st, queue, count_ptr, work_counter, r->counters, r->tune_refill, r->tune_leaf, n_top);
+			return;
+		}
+		if (r->extend_variant > 0)
+		{
+			if (r->count_traversal) k_extend_speculative<true, false><<<grid, 128, 0, stream>>>(r->dscene, st, queue, count_ptr, work_counter, r->counters, r->tune_refill, r->tune_leaf);
+			else if (r->extend_variant == 2) k_extend_speculative<false, true><<<grid, 128, 0, stream>>>(r->dscene, st, queue, count_ptr, work_counter, r->counters, r->tune_refill, r->tune_leaf);
+			else k_extend_speculative<false, false><<<grid, 128, 0, stream>>>(r->dscene, st, queue, count_ptr, work_counter, r->counters, r->tune_refill, r->tune_leaf);
+			return;
+		}
 		if (r->count_traversal) k_extend_persistent<true, 0><<<grid, 128, 0, stream>>>(r->dscene, st, queue, count_ptr, work_counter, r->counters, r->tune_refill, r->tune_leaf, r->tune_reps);
 		else if (r->tune_reps == PTB_NODE_REPS && r->unroll_reps) k_extend_persistent<false, PTB_NODE_REPS><<<grid, 128, 0, stream>>>(r->dscene, st, queue, count_ptr, work_counter, r->counters, r->tune_refill, r->tune_leaf, r->tune_reps);
 		else k_extend_persistent<false, 0><<<grid, 128, 0, stream>>>(r->dscene, st, queue, count_ptr, work_counter, r->counters, r->tune_refill, r->tune_leaf, r->tune_reps);
@@ -711,6 +854,23 @@ int enqueue_batch(ptb_renderer* r, ptb_renderer::BatchContext& ctx, cudaEvent_t 
 		else k_shade<false, false><<<sgrid, 128, 0, stream>>>(PTB_SHADE_ARGS);
 #undef PTB_SHADE_ARGS
 		r->stats.kernel_launches += 2;
+#ifdef PTB_EXPERIMENT_SORT
+		if ((r->sort_depth_mask >> (depth + 1)) & 1)
+		{
+			const int tot = (int)total;
+			if (!r->sort_keys[0])
+			{
+				cudaMalloc(&r->sort_keys[0], total * 4); cudaMalloc(&r->sort_keys[1], total * 4); cudaMalloc(&r->sort_vals, total * 4);
+				cub::DeviceRadixSort::SortPairs(nullptr, r->sort_tmp_bytes, r->sort_keys[0], r->sort_keys[1], qout, r->sort_vals, tot);
+				cudaMalloc(&r->sort_tmp, r->sort_tmp_bytes);
+			}
+			const float3 lo = make_float3(r->scene_lo[0], r->scene_lo[1], r->scene_lo[2]);
+			const float3 inv = make_float3(1.0f / (r->scene_hi[0] - r->scene_lo[0]), 1.0f / (r->scene_hi[1] - r->scene_lo[1]), 1.0f / (r->scene_hi[2] - r->scene_lo[2]));
+			k_sort_keys<<<(tot + 255) / 256, 256, 0, stream>>>(ctx.st, qout, ctx.counts + depth + 1, r->sort_keys[0], tot, lo, inv, r->sort_cell_bits, r->sort_octant);
+			cub::DeviceRadixSort::SortPairs(r->sort_tmp, r->sort_tmp_bytes, r->sort_keys[0], r->sort_keys[1], qout, r->sort_vals, tot, 0, 3 * r->sort_cell_bits + 3, stream);
+			cudaMemcpyAsync(qout, r->sort_vals, (size_t)tot * 4, cudaMemcpyDeviceToDevice, stream);
+		}
+#endif
 	}
 	if (prev_accumulated) PTB_CUDA(cudaStreamWaitEvent(stream, prev_accumulated, 0));
 	k_accumulate<<<(px + 255) / 256, 256, 0, stream>>>(ctx.st.radiance, r->image_sum, r->last_pass, ctx.counts, r->segment_totals, n_counts, px, n_slots, r->pass_clamp >= 0.0f ? r->pass_clamp : (float)r->cfg.max_tracer_depth * 2.0f);
@@ -725,6 +885,7 @@ int render_impl(ptb_renderer* r, int first_pass, int stride, int n_passes, bool 
 	if (!r || r->host_only) { set_error("[Error]renderer has no CUDA device (host-only handle): rendering is unavailable, there is no CPU fallback"); return 1; }
 	if (!r->scene_loaded) { set_error("[Error]no scene loaded"); return 1; }
 	if (n_passes <= 0) return 0;
+	PTB_CUDA(cudaSetDevice(r->device));   // the caller's thread may drive several devices (csrc/multi.inc)
 	if (r->nee && r->dscene.bvh_layout != 2) { set_error("[Error]estimator nee needs the binary tree (bvh_layout 2): its shadow stage traverses it"); return 1; }
 	memset(&r->stats, 0, sizeof(r->stats));
 	r->stats.bvh_nodes = r->bvh_nodes; r->stats.bvh_bytes = r->bvh_bytes;
@@ -748,7 +909,9 @@ int render_impl(ptb_renderer* r, int first_pass, int stride, int n_passes, bool 
 	// the last accumulate depends (transitively) on every earlier batch: wait for it on the main stream
 	if (prev_acc && batch > 0 && r->contexts[(batch - 1) % n_ctx].stream != r->stream) PTB_CUDA(cudaStreamWaitEvent(r->stream, prev_acc, 0));
 	if (advance_counter) r->pass_counter += n_passes;
-	int total_passes = advance_counter ? r->pass_counter : n_passes;
+	// strided calls (spp sharding; ptb_render_strided advances the counter after the call) accumulate across calls: the displayed
+	// image divides by every pass summed since the last clear, not by this call's count
+	int total_passes = advance_counter ? r->pass_counter : r->pass_counter + n_passes;
 	k_tonemap<<<(r->pixel_count + 255) / 256, 256, 0, r->stream>>>(r->image_sum, r->image_u8, r->pixel_count, std::max(total_passes, 1), r->cfg.gamma_correction ? 1 : 0);
 	r->stats.kernel_launches++;
 	PTB_CUDA(cudaMemcpyAsync(r->counts_host, r->segment_totals, n_counts * sizeof(unsigned long long), cudaMemcpyDeviceToHost, r->stream));
@@ -887,7 +1050,7 @@ ptb_renderer* ptb_create(const char* config_json_path, int cuda_device)
 		delete r;
 		return nullptr;
 	}
-	cudaDeviceProp prop;
+	cudaDeviceProp prop = {};
 	if (cudaGetDeviceProperties(&prop, cuda_device) == cudaSuccess) r->sm_count = prop.multiProcessorCount;
 	if (cudaStreamCreateWithFlags(&r->stream, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreate(&r->ev0) != cudaSuccess || cudaEventCreate(&r->ev1) != cudaSuccess)
 	{
@@ -896,11 +1059,27 @@ ptb_renderer* ptb_create(const char* config_json_path, int cuda_device)
 		return nullptr;
 	}
 	{
-		int per_sm = 0;
-		if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_extend_persistent<false, 0>, 128, 0) == cudaSuccess && per_sm > 0)
-			r->persistent_grid = r->sm_count * per_sm;
-		if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_extend_persistent8<false>, 128, 0) == cudaSuccess && per_sm > 0)
-			r->persistent_grid8 = r->sm_count * per_sm;
+		// persistent grids = one resident wave; the shared-memory part of the traversal stack asks for an explicit L1 / shared split
+		// (the rest of the 256 KB stays L1 for the node and triangle gathers)
+		auto setup = [&](auto kernel, int* grid)
+		{
+			int per_sm = 0;
+			if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, 128, 0) != cudaSuccess || per_sm <= 0) { cudaGetLastError(); return; }
+			if (grid) *grid = r->sm_count * per_sm;
+			cudaFuncAttributes fa;
+			if (cudaFuncGetAttributes(&fa, kernel) == cudaSuccess && fa.sharedSizeBytes > 0)
+			{
+				const size_t need = (size_t)per_sm * (fa.sharedSizeBytes + 1024);
+				const int pct = (int)std::min<size_t>(100, (need * 100 + prop.sharedMemPerMultiprocessor - 1) / std::max<size_t>(prop.sharedMemPerMultiprocessor, 1));
+				cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+			}
+			cudaGetLastError();
+		};
+		setup(k_extend_persistent<false, 0>, &r->persistent_grid);
+		setup(k_extend_persistent<false, PTB_NODE_REPS>, nullptr);
+		setup(k_extend_persistent<true, 0>, nullptr);
+		setup(k_extend_persistent8<false>, &r->persistent_grid8);
+		setup(k_extend_persistent8<true>, nullptr);
 	}
 	if (alloc_work_buffers(r)) { free_work_buffers(r); delete r; return nullptr; }
 	return r;
@@ -1043,6 +1222,19 @@ static int edit_prologue(ptb_renderer* r)
 	return 0;
 }
 
+// A geometry edit whose device rebuild fails (out of memory, "BVH too deep") has already changed the host triangles and freed the old
+// tree: the scene is unloaded, so the next ptb_render answers "[Error]no scene loaded" instead of traversing freed memory.
+static int geometry_edit_failed(ptb_renderer* r)
+{
+	const std::string why = last_error();
+	cudaGetLastError();
+	release_scene_device(r);
+	r->scene_loaded = false;
+	r->scene = HostScene();
+	set_error(why + " (the scene was unloaded: reload it)");
+	return 1;
+}
+
 int ptb_set_sphere(ptb_renderer* r, int index, const void* sphere100)
 {
 	if (edit_prologue(r)) return 1;
@@ -1070,7 +1262,7 @@ int ptb_set_mesh_transform(ptb_renderer* r, int mesh, const float* position3, co
 	// the UI clamps the scale to >= 1e-6 before the call (Core/path_tracer.cpp:346-351)
 	Vec3 sc{ std::max(scale3[0], 0.000001f), std::max(scale3[1], 0.000001f), std::max(scale3[2], 0.000001f) };
 	if (!set_mesh_transform(r->scene, mesh, Vec3{ position3[0], position3[1], position3[2] }, sc)) return 1;
-	if (!r->host_only && (upload_geometry(r) || upload_lights(r))) return 1;
+	if (!r->host_only && (upload_geometry(r) || upload_lights(r))) return geometry_edit_failed(r);
 	return ptb_clear(r);
 }
 
@@ -1079,7 +1271,7 @@ int ptb_apply_mesh_rotate(ptb_renderer* r, int mesh, const float* rotate3)
 	if (edit_prologue(r)) return 1;
 	if (!rotate3) { set_error("[Error]null argument"); return 1; }
 	if (!apply_mesh_rotate(r->scene, mesh, Vec3{ rotate3[0], rotate3[1], rotate3[2] })) return 1;
-	if (!r->host_only && (upload_geometry(r) || upload_lights(r))) return 1;
+	if (!r->host_only && (upload_geometry(r) || upload_lights(r))) return geometry_edit_failed(r);
 	return ptb_clear(r);
 }
 
@@ -1514,6 +1706,7 @@ int ptb_set_option(ptb_renderer* r, const char* key, const char* value)
 	if (k == "bvh_intersect_cost") { float c = (float)atof(value); if (!(c > 0.0f)) { set_error("[Error]bvh_intersect_cost must be > 0"); return 1; } r->bvh_intersect_cost = c; return 0; }
 	if (k == "loader_threads") { set_loader_threads(atoi(value)); return 0; }   // process-wide, like ptb_set_jpeg_decode
 	if (k == "tile_order") { r->tile_order = atoi(value); return 0; }
+	if (k == "l2_persist") { r->l2_persist = atoi(value) != 0; return 0; }      // takes effect at the next ptb_load_scene / geometry edit
 	if (k == "octant_order") { r->octant_order = atoi(value); return 0; }
 	if (k == "sort_by_material") { r->sort_by_material = atoi(value); return 0; }
 	if (k == "russian_roulette") { r->russian_roulette = atoi(value) != 0; return ptb_clear(r); }
@@ -1537,6 +1730,13 @@ int ptb_set_option(ptb_renderer* r, const char* key, const char* value)
 		return 0;
 	}
 	if (k == "extend_persistent") { r->extend_persistent = atoi(value); return 0; }
+	if (k == "extend_variant") { r->extend_variant = atoi(value); return 0; }
+	if (k == "tune_refill4") { r->tune_refill4 = atoi(value); return 0; }
+	if (k == "treelet_block") { r->treelet_block = atoi(value); return 0; }
+	if (k == "treelet_nodes") { r->treelet_nodes = atoi(value); return 0; }
+	if (k == "sort_depth_mask") { r->sort_depth_mask = atoi(value); return 0; }
+	if (k == "sort_cell_bits") { r->sort_cell_bits = atoi(value); return 0; }
+	if (k == "sort_octant") { r->sort_octant = atoi(value); return 0; }
 	if (k == "tune_refill") { r->tune_refill = atoi(value); return 0; }
 	if (k == "tune_leaf") { r->tune_leaf = atoi(value); return 0; }
 	if (k == "tune_reps") { r->tune_reps = atoi(value); return 0; }
@@ -1544,6 +1744,7 @@ int ptb_set_option(ptb_renderer* r, const char* key, const char* value)
 	if (k == "tune_refill8") { r->tune_refill8 = atoi(value); return 0; }
 	if (k == "tune_leaf8") { r->tune_leaf8 = atoi(value); return 0; }
 	if (k == "persistent_grid") { r->persistent_grid = atoi(value); return 0; }
+	if (k == "persistent_grid8") { r->persistent_grid8 = atoi(value); return 0; }
 	if (k == "bvh_collapse") { if (v != "gpu" && v != "host") { set_error("[Error]bvh_collapse must be gpu or host"); return 1; } r->bvh_collapse = v; return 0; }
 	if (k == "bvh_hybrid") { r->bvh_hybrid = atoi(value); return 0; }             // takes effect at the next ptb_load_scene
 	if (k == "hybrid_from_depth") { r->hybrid_from_depth = atoi(value); return 0; }
@@ -1641,3 +1842,4 @@ int ptb_get_config(ptb_renderer* r, void* out96)
 } // extern "C"
 
 #include "compat.inc"
+#include "multi.inc"

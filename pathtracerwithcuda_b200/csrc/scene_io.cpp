@@ -230,6 +230,9 @@ bool load_config(const std::string& path, Config& c)
 	c.cuda_acceleration = parse_bool(s["CUDAAcceleration"]);
 
 	if (c.width <= 0 || c.height <= 0) { set_error("[Error]config Width/Height must be positive"); return false; }
+	// path ids (pass slot * pixels + pixel, up to 64 slots) and the per-depth counters are ints: bound what sizes them
+	if ((long long)c.width * (long long)c.height > (long long)(0x7fffffff / 64)) { set_error("[Error]config Width*Height must not exceed 33554431 pixels"); return false; }
+	if (c.max_tracer_depth < 0 || c.max_tracer_depth > 4096) { set_error("[Error]config MaxDepth must be in 0..4096"); return false; }
 	return true;
 }
 

@@ -156,13 +156,15 @@ def test_edge_cases(workload_root, tmp_path):
 # (3) live reference, when oracle/_ref travelled to the box
 # --------------------------------------------------------------------------------------------
 @pytest.mark.skipif(not os.path.exists(REF_LIB), reason="oracle/_ref/libptref.so not present on this box")
-@pytest.mark.parametrize("workload,size,spp", [("mix", (96, 72), 4), ("c2", (320, 180), 2)])
+@pytest.mark.parametrize("workload,size,spp", [("mix", (96, 72), 4), ("c2", (320, 180), 2), ("c3", (320, 180), 2), ("c4", (320, 180), 2)])
 def test_live_reference(workload, size, spp):
+    """BASELINE.json configs[1..3] at reduced size (320x180, a tenth of the triangles; c3 keeps its textures, sky box and thin-lens
+    camera, c4 its subsurface material and MaxDepth 16) against the unmodified reference kernels run in the same call."""
     out = tempfile.mktemp(suffix=".json")
     tool = os.path.join(REPO, "tools", "parity_report.py")
     # a fresh process per scene: the reference keeps builder state between scene loads
     subprocess.run([sys.executable, tool, "--workload", workload, "--width", str(size[0]), "--height", str(size[1]), "--spp", str(spp),
-                    "--tri-scale", "0.1" if workload == "c2" else "1.0", "--out", out], check=True, capture_output=True)
+                    "--tri-scale", "0.1" if workload in ("c2", "c3", "c4") else "1.0", "--out", out], check=True, capture_output=True)
     rep = json.load(open(out))
     assert rep["triangles_bit_equal"] and rep["camera_rays_bit_equal"]
     for d, c in rep["prim_ids"].items():
@@ -244,7 +246,7 @@ def test_scheduling_options_do_not_change_the_image(workload_root):
     ref = None
     for opts in (dict(), dict(tile_order=0), dict(sort_by_material=1), dict(sort_by_material=1, tile_order=0, streams_in_flight=1),
                  dict(extend_persistent=0), dict(bvh_max_leaf=2, bvh_intersect_cost=1.5), dict(bvh_hybrid=0), dict(hybrid_from_depth=0),
-                 dict(bvh_layout=8), dict(octant_order=1)):
+                 dict(bvh_layout=8), dict(octant_order=1), dict(extend_variant=1), dict(extend_variant=2), dict(extend_variant=3), dict(extend_variant=3, treelet_block=512, treelet_nodes=100), dict(extend_variant=4), dict(extend_variant=4, tune_refill4=1), dict(l2_persist=1)):
         r = gpu_renderer(w, root, **opts)
         r.set_camera(ptb.default_camera(w["width"], w["height"], w["aperture"], w["focal"]))
         r.render(5)
