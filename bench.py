@@ -210,6 +210,27 @@ def run_reference(args, w, root, rank, world):
             "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
 
 
+def other_workloads(impl, names=("c1", "c3", "c4"), steps=3):
+    """BASELINE.json configs[0], [2], [3] through this same script in --quick mode, one fresh process each (the reference cannot load a
+    second scene in one process: its Morton builder keeps state).  Returns {name: record subset or {"error": ...}}."""
+    out = {}
+    for name in names:
+        cmd = [sys.executable, os.path.abspath(__file__), "--workload", name, "--steps", str(steps), "--warmup", "3", "--quick"]
+        if impl == "reference":
+            cmd += ["--impl", "reference"]
+        try:
+            env = {k: v for k, v in os.environ.items() if k not in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT")}
+            p = subprocess.run(cmd, capture_output=True, text=True, timeout=420, env=env)
+            rec = json.loads([l for l in p.stdout.splitlines() if l.startswith("{")][-1])
+            keep = ("value", "unit", "ms_per_step", "config", "e2e", "value_basis", "best_pass", "median_step", "mean_step", "kernel_only", "gpu_launches", "ray_segments")
+            out[name] = {k: rec[k] for k in keep if k in rec}
+            if "roofline" in rec:
+                out[name]["Mrays_s_whole_step"] = rec["roofline"].get("Mrays_s_whole_step")
+        except Exception as e:      # an extra record must never take the headline line down
+            out[name] = {"error": "%s: %s" % (type(e).__name__, str(e)[:300])}
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -218,7 +239,11 @@ def main():
     ap.add_argument("--impl", default="ptb200")
     ap.add_argument("--workload", default="c2")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--quick", action="store_true", help="headline record only: no cpu_baseline, no other_workloads, no strong-scaling record")
+    ap.add_argument("--strong-passes", type=int, default=4096, help="total passes of the c5 strong-scaling record (BASELINE.json configs[4]: 4096 spp)")
     args = ap.parse_args()
+    if args.quick:
+        args.no_cpu_baseline = True
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else max(args.warmup, 1)
 
     rank = int(os.environ.get("RANK", "0"))
@@ -237,6 +262,8 @@ def main():
             os.dup2(2, 1)
             try:
                 line = run_reference(args, w, root, rank, world)
+                if not args.quick and line is not None:
+                    line["other_workloads"] = other_workloads("reference", steps=2)
             finally:
                 sys.stdout.flush()
                 os.dup2(saved, 1)
@@ -251,7 +278,7 @@ def main():
 def run_ptb200(args, w, root, rank, local_rank, world):
     import torch
     import pathtracerwithcuda_b200 as ptb
-    from pathtracerwithcuda_b200.distributed import CudaBackend, ShardedRenderer
+    from pathtracerwithcuda_b200.distributed import DistRenderer, torch_exchange
 
     dist = None
     saved_stdout_fd = None
@@ -271,12 +298,14 @@ def run_ptb200(args, w, root, rank, local_rank, world):
     r = ptb.Renderer(w["config"], device=local_rank)
     r.set_option("passes_in_flight", PASSES_IN_FLIGHT)
     r.set_option("streams_in_flight", STREAMS_IN_FLIGHT)
+    # N > 1: everything multi-GPU goes through the C ABI (ptb_dist_*, csrc/multi.inc): the library's own NCCL communicator (torch.distributed
+    # only hands the 128-byte id around), rank 0 parses the scene and broadcasts the PARSED scene, the reduce runs on the render stream
+    sr = DistRenderer(r, rank, world, torch_exchange(dist) if dist is not None else None)
     t0 = time.perf_counter()
-    r.load_scene(w["scene"], root)
+    sr.load_scene(w["scene"], root)
     load_s = time.perf_counter() - t0
     if w["aperture"] >= 0 or w["focal"] >= 0:
         r.set_camera(ptb.default_camera(w["width"], w["height"], w["aperture"], w["focal"]))
-    sr = ShardedRenderer(CudaBackend(r), rank, world, dist)
     px = w["width"] * w["height"]
     stream = torch.cuda.ExternalStream(r.stream(), device=torch.device("cuda", local_rank))
 
@@ -321,6 +350,7 @@ def run_ptb200(args, w, root, rank, local_rank, world):
     sr.begin()
     for _ in range(args.warmup):
         sr.render_local(PASSES_PER_STEP)
+    sr.reduce()                                     # the first collective sets NCCL's channels up: not part of a steady-state step
     sr.begin()
 
     # ---- timed region: K steps, device-timed on the render stream (4 batches overlap on 4 streams)
@@ -335,7 +365,8 @@ def run_ptb200(args, w, root, rank, local_rank, world):
         sr.render_local(PASSES_PER_STEP)
         s = r.stats()
         segments += s["ray_segments"]; launches += s["kernel_launches"]; extend_ms += s["gpu_ms_extend"]
-    total_passes = sr.reduce()                      # one sum-reduce per image (no-op at N=1) + tonemap on rank 0
+    sr.reduce()                                     # one ncclReduce per image onto rank 0's merged image + tonemap there (no-op at N=1)
+    total_passes = PASSES_PER_STEP * args.steps * world
     e1.record(stream)
     barrier()
     clocks = sampler.stop()
@@ -360,7 +391,8 @@ def run_ptb200(args, w, root, rank, local_rank, world):
         sr.render_local(PASSES_PER_STEP)             # synchronous C-ABI call
         r.image_u8(u8)                               # D2H of the displayed image (the reference's per-frame cudaMemcpy)
     sr.reduce()
-    r.image_f32()
+    if rank == 0:
+        sr.image_f32()                               # the merged float image of the job, device -> host
     barrier()
     e2e_s = time.perf_counter() - t0
     te = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
@@ -434,6 +466,31 @@ def run_ptb200(args, w, root, rank, local_rank, world):
                 "ray_segments": int(seg_total), "total_passes": int(total_passes)}
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(w, root)
+    else:
+        line = None
+    # ---- records beside the headline (never inside its timed region)
+    sr.close()
+    r.close()
+    r = None
+    if not args.quick:
+        # (1) STRONG scaling on BASELINE.json configs[4]: a fixed number of passes of c5 (4K, ~5 M triangles) sharded over the N ranks, timed
+        #     from ptb_load_scene (rank 0 parses, the others receive the parsed scene by ncclBroadcast) to the merged image on rank 0
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "tools"))
+            import scale_render
+            rec = scale_render.run("c5", args.strong_passes, rank, local_rank, world, dist, passes_in_flight=8, warm=True)
+        except Exception as e:
+            rec = {"error": "%s: %s" % (type(e).__name__, str(e)[:300])}
+        if rank == 0:
+            line["strong_scaling"] = rec
+            if isinstance(rec, dict) and "error" not in rec:
+                rec["note"] = ("fixed total work: efficiency(N) = time(1) / (N * time(N)); `ms` = device time of render + reduce (max over ranks), "
+                               "`time_to_image_s` adds the load: rank 0 reads and parses 374 MB of OBJ text, broadcasts the parsed scene (NCCL), every rank "
+                               "uploads and builds its own BVH")
+        # (2) the other single-GPU BASELINE configs, so every config has a driver-run number
+        if rank == 0 and world == 1:
+            line["other_workloads"] = other_workloads("ptb200")
+    if rank == 0:
         if saved_stdout_fd is not None:
             sys.stdout.flush()
             os.dup2(saved_stdout_fd, 1)
@@ -441,7 +498,6 @@ def run_ptb200(args, w, root, rank, local_rank, world):
         sys.stdout.flush()
         if saved_stdout_fd is not None:
             os.dup2(2, 1)
-    r.close()
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()

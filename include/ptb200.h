@@ -249,11 +249,15 @@ int ptb_dist_unique_id(void* out_id128);
 int ptb_dist_init(ptb_renderer* r, int rank, int world_size, const void* id128);
 int ptb_dist_shutdown(ptb_renderer* r);
 int ptb_dist_broadcast_scene(ptb_renderer* r, int root);
+/* wall ms of the last broadcast on this rank: staging on the root, ncclBroadcast, device->host unpack, upload + BVH build, whole call; out6[5] = bytes */
+int ptb_dist_broadcast_timing(ptb_renderer* r, double* out6);
 int ptb_dist_render(ptb_renderer* r, int total_passes);
 int ptb_dist_reduce(ptb_renderer* r, int root);
 int ptb_dist_clear(ptb_renderer* r);
 int ptb_merged_image_f32(ptb_renderer* r, float* out_rgb_sum, int* out_passes);
 int ptb_merged_image_u8(ptb_renderer* r, uint8_t* out_rgb);
+/* test hook: the loaded scene through the broadcast format and back on this device; 0 = byte-identical */
+int ptb_test_scene_blob_roundtrip(ptb_renderer* r);
 
 /* ---- output side -----------------------------------------------------------------------------
  * ptb_save_png        = screenshot() of Main/window.cpp:712-740 (lodepng::encode of the displayed RGBA8 image),

@@ -72,6 +72,19 @@ def load_library():
     if not os.path.exists(_LIB_PATH):
         from . import build as _build
         _build.build()
+    if "PTB200_NCCL_LIB" not in os.environ:
+        # multi-GPU entry points dlopen NCCL lazily (csrc/multi.inc).  In a Python process torch may be imported later and needs ITS libnccl.so.2
+        # (pip package nvidia-nccl); a different copy loaded first under the same soname would break that import, so point the library at it.
+        try:
+            import importlib.util
+            spec = importlib.util.find_spec("nvidia.nccl")
+            for loc in (spec.submodule_search_locations if spec else []):
+                cand = os.path.join(loc, "lib", "libnccl.so.2")
+                if os.path.exists(cand):
+                    os.environ["PTB200_NCCL_LIB"] = cand
+                    break
+        except Exception:
+            pass
     L = ctypes.CDLL(_LIB_PATH)
     vp, ci, cf, cp = ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_char_p
     L.ptb_last_error.restype = cp
@@ -152,10 +165,12 @@ def load_library():
     L.ptb_dist_shutdown.argtypes = [vp]
     L.ptb_dist_broadcast_scene.argtypes = [vp, ci]
     L.ptb_dist_render.argtypes = [vp, ci]
+    L.ptb_dist_broadcast_timing.argtypes = [vp, vp]
     L.ptb_dist_reduce.argtypes = [vp, ci]
     L.ptb_dist_clear.argtypes = [vp]
     L.ptb_merged_image_f32.argtypes = [vp, vp, ctypes.POINTER(ci)]
     L.ptb_merged_image_u8.argtypes = [vp, vp]
+    L.ptb_test_scene_blob_roundtrip.argtypes = [vp]
     _lib = L
     return L
 
@@ -260,11 +275,19 @@ class Renderer:
     def dist_broadcast_scene(self, root=0):
         self._check(self.lib.ptb_dist_broadcast_scene(self.handle, int(root)))
 
+    def dist_broadcast_timing(self):
+        out = np.zeros(6, np.float64)
+        self._check(self.lib.ptb_dist_broadcast_timing(self.handle, _ptr(out)))
+        return dict(zip(["stage_ms", "broadcast_ms", "unpack_ms", "upload_build_ms", "total_ms", "bytes"], out.tolist()))
+
     def dist_render(self, total_passes):
         self._check(self.lib.ptb_dist_render(self.handle, int(total_passes)))
 
     def dist_reduce(self, root=0):
         self._check(self.lib.ptb_dist_reduce(self.handle, int(root)))
+
+    def scene_blob_roundtrip(self):
+        self._check(self.lib.ptb_test_scene_blob_roundtrip(self.handle))
 
     def dist_clear(self):
         self._check(self.lib.ptb_dist_clear(self.handle))

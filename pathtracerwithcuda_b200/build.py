@@ -94,6 +94,18 @@ def build_roofs(force=False):
     return out
 
 
+def build_fastobj(force=False):
+    """tools/fastobj/libfastobj.so: C stdio writer for the procedural OBJ fixtures (byte-identical to the numpy writer, much faster)."""
+    src = os.path.normpath(os.path.join(HERE, "..", "tools", "fastobj", "fastobj.c"))
+    out = os.path.normpath(os.path.join(HERE, "..", "tools", "fastobj", "libfastobj.so"))
+    if not force and os.path.exists(out) and os.path.getmtime(out) >= os.path.getmtime(src):
+        return out
+    r = subprocess.run(["gcc", "-O2", "-shared", "-fPIC", "-o", out, src], capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("build failed: fastobj\n%s\n%s" % (r.stdout, r.stderr))
+    return out
+
+
 if __name__ == "__main__":
     extra = []
     for a in sys.argv[1:]:
@@ -103,4 +115,5 @@ if __name__ == "__main__":
             extra += a.split("=", 1)[1].split(",")
     out = [a.split("=", 1)[1] for a in sys.argv[1:] if a.startswith("--out=")]
     build_roofs(force="--force" in sys.argv)
+    build_fastobj(force="--force" in sys.argv)
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, extra_nvcc=extra or None, out=out[0] if out else None))

@@ -14,6 +14,7 @@
 #include <cmath>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #define PTB200_BUILDING_LIBRARY 1
@@ -168,6 +169,8 @@ struct ptb_renderer
 	uint8_t* merged_u8 = nullptr;
 	int merged_passes = 0;
 	unsigned long long* pass_count_dev = nullptr;
+	const float* staged_tris24 = nullptr; size_t staged_tris_count = 0;   // device copy of the world-space triangles upload_geometry may adopt
+	double bcast_ms[5] = { 0, 0, 0, 0, 0 }, bcast_bytes = 0.0;   // timing of the last ptb_dist_broadcast_scene on this rank
 
 	ptb_stats stats;
 	int64_t traversal_histogram[32] = { 0 };  // raw device counters of the last count_traversal call
@@ -266,6 +269,98 @@ void free_work_buffers(ptb_renderer* r)
 	r->image_sum = nullptr; r->last_pass = nullptr; r->image_u8 = nullptr;
 }
 
+// Large host <-> device copies of PAGEABLE memory (the parsed scene lives in std::vectors).  The driver stages such copies through
+// its own small pinned buffer on one thread (measured on the B200 boxes: 0.6-1 GB/s for the 480 MB triangle array of c5); here the copy
+// is cut into 32 MB chunks that host threads memcpy into / out of two pinned buffers while the previous chunk's DMA runs.
+struct PinnedStager
+{
+	static const size_t kChunk = 32u << 20;
+	char* buf[2] = { nullptr, nullptr };
+	cudaEvent_t ev[2] = { nullptr, nullptr };
+	bool ok = false;
+	bool init()
+	{
+		if (ok) return true;
+		for (int i = 0; i < 2; i++)
+		{
+			if (cudaMallocHost(&buf[i], kChunk) != cudaSuccess || cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming) != cudaSuccess) { release(); cudaGetLastError(); return false; }
+		}
+		ok = true;
+		return true;
+	}
+	void release()
+	{
+		for (int i = 0; i < 2; i++) { if (buf[i]) cudaFreeHost(buf[i]); if (ev[i]) cudaEventDestroy(ev[i]); buf[i] = nullptr; ev[i] = nullptr; }
+		ok = false;
+	}
+	~PinnedStager() { release(); }
+};
+
+void parallel_memcpy(char* dst, const char* src, size_t bytes)
+{
+	const size_t hw = std::max(1u, std::thread::hardware_concurrency());
+	const size_t n = std::max<size_t>(1, std::min<size_t>(std::min<size_t>(8, hw), bytes / (4u << 20)));
+	if (n == 1) { memcpy(dst, src, bytes); return; }
+	std::vector<std::thread> th;
+	const size_t part = ((bytes + n - 1) / n + 4095) & ~(size_t)4095;
+	for (size_t k = 1; k < n; k++)
+	{
+		const size_t a = std::min(bytes, k * part), b = std::min(bytes, (k + 1) * part);
+		if (b > a) th.emplace_back([=] { memcpy(dst + a, src + a, b - a); });
+	}
+	memcpy(dst, src, std::min(bytes, part));
+	for (auto& t : th) t.join();
+}
+
+// to_device: host (pageable) -> device; else device -> host (pageable).  Synchronous with respect to the host buffer; ordered on `stream`.
+int staged_copy(void* dst, const void* src, size_t bytes, bool to_device, cudaStream_t stream)
+{
+	static thread_local PinnedStager stager;
+	if (bytes < (8u << 20) || !stager.init())
+	{
+		PTB_CUDA(cudaMemcpyAsync(dst, src, bytes, to_device ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost, stream));
+		PTB_CUDA(cudaStreamSynchronize(stream));
+		return 0;
+	}
+	const size_t chunk = PinnedStager::kChunk;
+	const size_t n_chunks = (bytes + chunk - 1) / chunk;
+	if (to_device)
+	{
+		for (size_t c = 0; c < n_chunks; c++)
+		{
+			const int b = (int)(c & 1);
+			const size_t off = c * chunk, n = std::min(chunk, bytes - off);
+			if (c >= 2) PTB_CUDA(cudaEventSynchronize(stager.ev[b]));      // the DMA that last read this buffer is done
+			parallel_memcpy(stager.buf[b], (const char*)src + off, n);
+			PTB_CUDA(cudaMemcpyAsync((char*)dst + off, stager.buf[b], n, cudaMemcpyHostToDevice, stream));
+			PTB_CUDA(cudaEventRecord(stager.ev[b], stream));
+		}
+		PTB_CUDA(cudaStreamSynchronize(stream));
+	}
+	else
+	{
+		// chunk c + 1 is in flight on the copy engine while the host threads drain chunk c
+		for (size_t c = 0; c <= n_chunks; c++)
+		{
+			if (c < n_chunks)
+			{
+				const int b = (int)(c & 1);
+				const size_t off = c * chunk, n = std::min(chunk, bytes - off);
+				PTB_CUDA(cudaMemcpyAsync(stager.buf[b], (const char*)src + off, n, cudaMemcpyDeviceToHost, stream));
+				PTB_CUDA(cudaEventRecord(stager.ev[b], stream));
+			}
+			if (c >= 1)
+			{
+				const int b = (int)((c - 1) & 1);
+				const size_t off = (c - 1) * chunk, n = std::min(chunk, bytes - off);
+				PTB_CUDA(cudaEventSynchronize(stager.ev[b]));
+				parallel_memcpy((char*)dst + off, stager.buf[b], n);
+			}
+		}
+	}
+	return 0;
+}
+
 template <class T>
 int upload(ptb_renderer* r, const T* host, size_t count, const T** out, std::vector<void*>* group = nullptr)
 {
@@ -273,7 +368,8 @@ int upload(ptb_renderer* r, const T* host, size_t count, const T** out, std::vec
 	size_t bytes = std::max<size_t>(count * sizeof(T), 16);
 	PTB_CUDA(cudaMalloc(&d, bytes));
 	(group ? *group : r->scene_allocs).push_back(d);
-	if (count) PTB_CUDA(cudaMemcpyAsync(d, host, count * sizeof(T), cudaMemcpyHostToDevice, r->stream));
+	if (count * sizeof(T) >= (8u << 20)) { if (staged_copy(d, host, count * sizeof(T), true, r->stream)) return 1; }
+	else if (count) PTB_CUDA(cudaMemcpyAsync(d, host, count * sizeof(T), cudaMemcpyHostToDevice, r->stream));
 	*out = (const T*)d;
 	return 0;
 }
@@ -420,10 +516,27 @@ int upload_geometry(ptb_renderer* r)
 #endif
 	const float* d_tris24 = nullptr;
 	const int* d_material = nullptr;
-	if (upload(r, (const float*)s.triangles.data(), (size_t)n_tris * 24, &d_tris24, G)) return 1;
+	if (r->staged_tris24 && r->staged_tris_count == (size_t)n_tris && n_tris > 0)
+	{
+		// the triangles are already on this device (a scene received by ptb_dist_broadcast_scene): device -> device instead of host -> device
+		float* d = nullptr;
+		PTB_CUDA(cudaMalloc(&d, (size_t)n_tris * 96));
+		G->push_back(d);
+		PTB_CUDA(cudaMemcpyAsync(d, r->staged_tris24, (size_t)n_tris * 96, cudaMemcpyDeviceToDevice, r->stream));
+		d_tris24 = d;
+	}
+	else if (upload(r, (const float*)s.triangles.data(), (size_t)n_tris * 24, &d_tris24, G)) return 1;
 	if (upload(r, s.triangle_material.data(), (size_t)n_tris, &d_material, G)) return 1;
 	ds.tris24 = d_tris24;
 	r->bvh_built_on_gpu = 0; r->bvh_levels = 0; r->bvh_small_tasks = 0; r->bvh_max_depth = 0; r->bvh_build_ms = 0.0; r->bvh_note.clear();
+	// the host builders / fallbacks read the HOST triangles: a scene that arrived on the device first (staged_tris24, csrc/multi.inc) is
+	// drained to the host before the first of them runs
+	bool host_triangles_ready = r->staged_tris24 == nullptr;
+	auto host_triangles = [&]() -> int {
+		if (host_triangles_ready || n_tris == 0) return 0;
+		host_triangles_ready = true;
+		return staged_copy(r->scene.triangles.data(), r->staged_tris24, (size_t)n_tris * 96, false, r->stream);
+	};
 
 	// acceleration structure over all meshes' world-space triangles
 	const int max_leaf = r->bvh_layout == 8 ? 3 : r->bvh_max_leaf;   // <= 3 triangles per leaf slot of a wide node
@@ -488,6 +601,7 @@ int upload_geometry(ptb_renderer* r)
 	}
 	if (!have_device_bvh2 && !(r->bvh_built_on_gpu && r->bvh_layout == 8))
 	{
+		if (host_triangles()) return 1;
 		const auto t0 = std::chrono::steady_clock::now();
 		build_bvh2_sah(s.triangles, max_leaf, bvh, r->bvh_intersect_cost);
 		r->bvh_build_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
@@ -497,6 +611,7 @@ int upload_geometry(ptb_renderer* r)
 	if (r->bvh_layout == 8 && !have_device_bvh8)
 	{
 		GpuBvh8 wide;
+		if (host_triangles()) return 1;
 		build_bvh8(bvh, s.triangles, wide);
 		if (wide.max_depth > PTB_STACK_SIZE8) { set_error("[Error]BVH8 too deep for the traversal stack"); return 1; }
 		if (upload(r, (const float4*)wide.nodes.data(), wide.nodes.size() / 4, &ds.bvh_nodes, G)) return 1;
@@ -507,6 +622,7 @@ int upload_geometry(ptb_renderer* r)
 	else if (r->bvh_layout != 8 && !have_device_bvh2)
 	{
 		GpuBvh2 flat;
+		if (host_triangles()) return 1;
 		flatten_bvh2(bvh, s.triangles, flat);
 		if (upload(r, (const float4*)flat.nodes.data(), flat.nodes.size() / 4, &ds.bvh_nodes, G)) return 1;
 		if (upload(r, (const float4*)flat.tris.data(), flat.tris.size() / 4, &ds.tri_isect, G)) return 1;
@@ -558,8 +674,14 @@ int upload_geometry(ptb_renderer* r)
 		}
 		if (!done)
 		{
-			if (!have_tree) { cudaGetLastError(); build_bvh2_sah(s.triangles, 3, tree3, r->bvh_intersect_cost); }
+			if (!have_tree)
+			{
+				cudaGetLastError();
+				if (host_triangles()) return 1;
+				build_bvh2_sah(s.triangles, 3, tree3, r->bvh_intersect_cost);
+			}
 			GpuBvh8 wide;
+			if (host_triangles()) return 1;
 			build_bvh8(tree3, s.triangles, wide);
 			if (wide.max_depth <= PTB_STACK_SIZE8)
 			{

@@ -2,8 +2,15 @@
 rank r of G renders passes r+1, r+1+G, ... (each pass keeps the seed it has in a single-GPU run,
 Kernel/path_tracer_kernel.cu:712), accumulates locally, and ONE sum-reduce of the float
 accumulation buffer per image lands on rank 0, which then runs the mean / gamma / 8-bit step.
-No data-path collective exists besides that reduce; torch.distributed (NCCL over NVLink on the
-GPU box, gloo in the CPU tests) is plumbing only.
+No data-path collective exists besides that reduce (and the one-off broadcast of the parsed scene).
+
+Two drivers:
+* `DistRenderer` — the product path, a THIN caller of the C ABI (include/ptb200.h, csrc/multi.inc): the library owns the NCCL
+  communicator, broadcasts the parsed scene from rank 0, shards the passes and reduces on its own render stream; the host only
+  hands the 128-byte NCCL id around (torch.distributed / gloo / MPI / a file — `torch_exchange` below uses torch.distributed).
+  In ONE process with all GPUs use `pathtracerwithcuda_b200.MultiRenderer` (ptb_multi_*) instead.
+* `ShardedRenderer` — the same sharding logic over an abstract backend and torch.distributed collectives; it is what the CPU
+  tests drive with gloo (the oracle as stand-in compute) and what tests emulate two ranks with on one GPU.
 """
 import numpy as np
 
@@ -66,6 +73,91 @@ class CudaBackend:
         return self.r.image_f32()
 
 
+def torch_exchange(dist):
+    """unique-id exchange for DistRenderer over an initialised torch.distributed group (plumbing only)."""
+    def exchange(payload):
+        box = [payload]
+        dist.broadcast_object_list(box, src=0)
+        return box[0]
+    return exchange
+
+
+class DistRenderer:
+    """One process per GPU through the C ABI.  exchange(bytes-or-None) -> bytes must return rank 0's argument on every rank."""
+
+    def __init__(self, renderer, rank=0, world_size=1, exchange=None):
+        from . import api
+        self.r = renderer
+        self.rank, self.world_size = rank, world_size
+        self.local_passes = 0
+        self.timing = {}
+        if world_size > 1:
+            if exchange is None:
+                raise ValueError("DistRenderer: world_size > 1 needs an exchange callable for the NCCL id")
+            uid = exchange(api.dist_unique_id() if rank == 0 else None)
+            renderer.dist_init(rank, world_size, uid)
+
+    def load_scene(self, scene_json_path, asset_root="", root=0):
+        """rank `root` reads and parses the scene files; every other rank receives the parsed scene over NCCL."""
+        if self.world_size == 1:
+            self.r.load_scene(scene_json_path, asset_root)
+            return
+        import time
+        err = None
+        t0 = time.perf_counter()
+        if self.rank == root:
+            try:
+                self.r.load_scene(scene_json_path, asset_root)
+            except Exception as e:      # still take part in the broadcast: the others fail with us instead of hanging
+                err = e
+        self.timing = {"root_load_s": time.perf_counter() - t0 if self.rank == root else None}
+        try:
+            self.r.dist_broadcast_scene(root)
+        except Exception:
+            if err is None:
+                raise
+        if err is not None:
+            raise err
+        self.timing["broadcast"] = self.r.dist_broadcast_timing()
+
+    def begin(self):
+        self.local_passes = 0
+        if self.world_size > 1:
+            self.r.dist_clear()
+        else:
+            self.r.clear()
+
+    def render(self, total_passes):
+        """the next total_passes passes of the image, sharded over the ranks (same argument on every rank)"""
+        if self.world_size > 1:
+            self.r.dist_render(total_passes)
+        else:
+            self.r.render(total_passes)
+
+    def render_local(self, n_local_passes):
+        self.render(n_local_passes * self.world_size)
+        self.local_passes += n_local_passes
+
+    def reduce(self, root=0):
+        if self.world_size > 1:
+            self.r.dist_reduce(root)
+
+    def image_f32(self):
+        """(sum image, passes) of the whole job — valid on the root after reduce()"""
+        if self.world_size > 1:
+            return self.r.merged_image_f32()
+        return self.r.image_f32(), self.r.pass_counter()
+
+    def image_u8(self, out=None):
+        if self.world_size > 1:
+            return self.r.merged_image_u8(out)
+        return self.r.image_u8(out)
+
+    def close(self):
+        if self.world_size > 1:
+            self.r.dist_shutdown()
+
+
 class ShardedRenderer:
     """Drives one backend per process; `dist` is torch.distributed (already initialised) or None."""
 
@@ -75,13 +167,18 @@ class ShardedRenderer:
         self.world_size = world_size
         self.dist = dist
         self.local_passes = 0
+        self._reduced = False
 
     def begin(self):
         self.backend.clear()
         self.local_passes = 0
+        self._reduced = False
 
     def render_local(self, n_local_passes):
         """Renders this rank's next n_local_passes passes (global indices rank+1 + k*world)."""
+        if self._reduced:
+            raise RuntimeError("ShardedRenderer: reduce() summed IN PLACE into rank 0's accumulation buffer; call begin() before rendering more "
+                               "(DistRenderer / MultiRenderer reduce into a separate merged image and may continue)")
         first = self.rank + 1 + self.local_passes * self.world_size
         self.backend.render_strided(first, self.world_size, n_local_passes)
         self.local_passes += n_local_passes
@@ -96,6 +193,9 @@ class ShardedRenderer:
         """Sum the per-rank accumulation buffers onto rank 0 and finish the image there."""
         if total_passes is None:
             total_passes = self.local_passes * self.world_size
+        if self._reduced:
+            raise RuntimeError("ShardedRenderer: reduce() is one-shot per begin() — a second in-place reduce would count the other ranks' passes twice")
+        self._reduced = True
         if self.dist is not None and self.world_size > 1:
             t = self.backend.accumulation_tensor()
             self.backend.synchronize()

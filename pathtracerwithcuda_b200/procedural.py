@@ -10,6 +10,7 @@ Workloads (SURVEY.md §8d / BASELINE.md §3.3):
   c4  ~1M-tri blob with a random-walk subsurface material                   1920x1080, depth 16
   c5  ~5M tris in two meshes                                                3840x2160, depth 8
 """
+import ctypes
 import json
 import os
 import struct
@@ -153,12 +154,49 @@ def box_mesh(half=(0.8, 0.8, 0.8)):
     return corners, quads
 
 
+_FASTOBJ = [False]
+
+
+def _fastobj():
+    """tools/fastobj/libfastobj.so if it has been built (pathtracerwithcuda_b200.build.build_fastobj), else None (numpy writer)."""
+    if _FASTOBJ[0] is False:
+        lib = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools", "fastobj", "libfastobj.so")
+        _FASTOBJ[0] = None
+        if os.path.exists(lib) and not os.environ.get("PTB_NO_FASTOBJ"):
+            try:
+                L = ctypes.CDLL(lib)
+                dp = ctypes.POINTER(ctypes.c_double)
+                L.fastobj_vertices.argtypes = [ctypes.c_char_p, dp, dp, dp, ctypes.c_int64, ctypes.c_int64]
+                L.fastobj_group.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.POINTER(ctypes.c_int64), ctypes.c_int64, ctypes.c_int]
+                _FASTOBJ[0] = L
+            except OSError:
+                pass
+    return _FASTOBJ[0]
+
+
 def write_obj(path, groups, verts, normals=None, uvs=None):
     """groups: list of (name, faces[int, 3]) with 0-based indices shared by v / vn / vt."""
     os.makedirs(os.path.dirname(path), exist_ok=True)
     if normals is None:
         allf = np.concatenate([f for _, f in groups], 0)
         normals = vertex_normals(verts, allf)
+    fast = _fastobj()
+    if fast is not None:
+        # same bytes as the numpy writer below, written by C stdio (tools/fastobj/fastobj.c)
+        with open(path, "w") as f:
+            f.write("# generated by pathtracerwithcuda_b200.procedural\n")
+        v = np.ascontiguousarray(verts, np.float64)
+        nrm = np.ascontiguousarray(normals, np.float64)
+        uv = np.ascontiguousarray(uvs, np.float64) if uvs is not None else None
+        dp = ctypes.POINTER(ctypes.c_double)
+        rc = fast.fastobj_vertices(os.fsencode(path), v.ctypes.data_as(dp), uv.ctypes.data_as(dp) if uv is not None else None, nrm.ctypes.data_as(dp),
+                                   v.shape[0], uv.shape[0] if uv is not None else 0)
+        for name, faces in groups:
+            i = np.ascontiguousarray(faces + 1, np.int64)
+            rc |= fast.fastobj_group(os.fsencode(path), name.encode(), i.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)), i.shape[0], 1 if uvs is not None else 0)
+        if rc:
+            raise IOError("fastobj: cannot write " + path)
+        return path
     with open(path, "w") as f:
         f.write("# generated by pathtracerwithcuda_b200.procedural\n")
         np.savetxt(f, verts, fmt="v %.6f %.6f %.6f")

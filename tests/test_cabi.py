@@ -55,9 +55,16 @@ def test_no_cpu_fallback(workload_root):
         with pytest.raises(ptb.PtbError):
             call()
     assert r.image_device_ptr() is None
+    # the multi-GPU entry points refuse a host-only handle as loudly
+    for call in (lambda: r.dist_init(0, 1, b"\0" * 128), lambda: r.dist_render(1), lambda: r.dist_reduce(0), lambda: r.dist_broadcast_scene(0),
+                 lambda: r.merged_image_f32(), lambda: r.scene_blob_roundtrip()):
+        with pytest.raises(ptb.PtbError):
+            call()
     if ptb.device_count() == 0:
         with pytest.raises(ptb.PtbError, match="no CPU fallback"):
             ptb.Renderer(w["config"], device=0)
+        with pytest.raises(ptb.PtbError, match="no CPU fallback"):
+            ptb.MultiRenderer(w["config"], 2)
 
 
 def test_path_tracer_class_mirror(workload_root):
