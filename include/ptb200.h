@@ -204,6 +204,12 @@ int ptb_get_traversal_histogram(ptb_renderer* r, int64_t* out25);
  *   "estimator"          "reference" (default) | "nee"   next-event estimation + shadow rays (binary tree)
  *   "russian_roulette"   "0" (default) | "1"    from bounce 3 on
  *   "pass_clamp"         float (default -1 = the reference's 2 * MaxDepth)   diagnostic: per-pass clamp of the accumulation
+ *   "sampler"            "reference" (default: hash-product seeds + minstd, Kernel/path_tracer_kernel.cu:35-44,324-325,415-416) | "pcg"
+ *   "sss"                "reference" (default: free flight from sigma_s'.x only, :456-464) | "per_channel" (uniform channel pick +
+ *                                               single-sample MIS over sigma_s'.xyz; equals the reference mode when the channels agree)
+ *  filtering (takes effect at the next ptb_load_scene)
+ *   "texture_filter"     "software" (default: the reference's filter, Core/texture.h:15-79, bit-compatible) | "hardware" (bilinear lookups
+ *                                               of textures and cube-map faces by the texture unit on cudaArray copies; 9-bit weights)
  *  measurement
  *   "profile_stages"     "0" | "1"   CUDA events around every closest-hit launch (ptb_get_depth_profile, ptb_stats.gpu_ms_extend)
  *   "count_traversal"    "0" | "1"   instrumented kernels: node visits / triangle tests (ptb_stats, ptb_get_traversal_histogram)
@@ -249,6 +255,9 @@ int ptb_dist_unique_id(void* out_id128);
 int ptb_dist_init(ptb_renderer* r, int rank, int world_size, const void* id128);
 int ptb_dist_shutdown(ptb_renderer* r);
 int ptb_dist_broadcast_scene(ptb_renderer* r, int root);
+/* collective load: `root` reads and parses the files (the other ranks' path arguments are ignored), then every rank — the root included —
+ * uploads and builds its BVH from the broadcast device copy at the same time */
+int ptb_dist_load_scene(ptb_renderer* r, const char* scene_json_path, const char* asset_root, int root);
 /* wall ms of the last broadcast on this rank: staging on the root, ncclBroadcast, device->host unpack, upload + BVH build, whole call; out6[5] = bytes */
 int ptb_dist_broadcast_timing(ptb_renderer* r, double* out6);
 int ptb_dist_render(ptb_renderer* r, int total_passes);

@@ -165,6 +165,7 @@ def load_library():
     L.ptb_dist_shutdown.argtypes = [vp]
     L.ptb_dist_broadcast_scene.argtypes = [vp, ci]
     L.ptb_dist_render.argtypes = [vp, ci]
+    L.ptb_dist_load_scene.argtypes = [vp, cp, cp, ci]
     L.ptb_dist_broadcast_timing.argtypes = [vp, vp]
     L.ptb_dist_reduce.argtypes = [vp, ci]
     L.ptb_dist_clear.argtypes = [vp]
@@ -274,6 +275,9 @@ class Renderer:
 
     def dist_broadcast_scene(self, root=0):
         self._check(self.lib.ptb_dist_broadcast_scene(self.handle, int(root)))
+
+    def dist_load_scene(self, scene_json_path, asset_root="", root=0):
+        self._check(self.lib.ptb_dist_load_scene(self.handle, os.fsencode(scene_json_path or ""), os.fsencode(asset_root or ""), int(root)))
 
     def dist_broadcast_timing(self):
         out = np.zeros(6, np.float64)

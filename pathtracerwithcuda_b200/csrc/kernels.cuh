@@ -21,6 +21,7 @@ struct DeviceTexture
 {
 	const uint8_t* pixels;
 	int width, height;
+	cudaTextureObject_t tex;      // option texture_filter=hardware: the same RGBA8 image as a cudaArray texture (bilinear by the texture unit), else 0
 };
 
 struct DeviceScene
@@ -62,6 +63,9 @@ struct DeviceConfig
 	float air_n;
 	float3 air_sigma_a;
 	float3 air_sigma_s;
+	// estimator options (0 = the reference's behaviour)
+	int sampler;        // 1: pcg streams instead of hash-product + minstd (pt_device.cuh)
+	int sss_mode;       // 1: per-channel subsurface scattering (kernels_shade.cuh: spectral MIS over sigma_s'.xyz instead of sigma_s'.x only)
 };
 
 // SoA path state, indexed by path id = slot * pixel_count + pixel.

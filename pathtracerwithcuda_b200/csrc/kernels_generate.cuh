@@ -16,12 +16,30 @@ using namespace ptbdev;
 // The RNG stream of a bounce depends only on (pass, pixel, depth), so d is known before the ray is
 // traced: the closest-hit search can stop at d.  Subsurface random walks (mean free path << object
 // size) then cost a handful of node visits instead of a full traversal, with identical results.
+// Per-channel subsurface scattering (option sss=per_channel; the reference's TODO at path_tracer_kernel.cu:456-464,
+// which samples the free flight from sigma_s'.x alone): the channel the free-flight distance is drawn from, one uniform pick per bounce from
+// its own stream.  Used by next_bounce_bound (which bounds the NEXT closest-hit search by that distance) and by k_shade — same pick.
+__device__ __forceinline__ float sss_sampling_sigma(const DeviceConfig& cfg, float3 sigma_s, int seed, int pixel_index, int depth)
+{
+	if (cfg.sss_mode == 0) return sigma_s.x;
+	Rng pick;
+	pick.seed3(cfg.sampler, seed, pixel_index, depth, 0x51ed270bu, 0.0f, 1.0f);
+	const float u = pick.next();
+	return u < (1.0f / 3.0f) ? sigma_s.x : (u < (2.0f / 3.0f) ? sigma_s.y : sigma_s.z);
+}
+
+__device__ __forceinline__ bool medium_participates(const DeviceConfig& cfg, float3 sigma_a, float3 sigma_s)
+{
+	if (cfg.sss_mode == 0) return sigma_s.x > 0.0f || length(sigma_a) > cfg.sss_threshold;
+	return fmaxf(sigma_s.x, fmaxf(sigma_s.y, sigma_s.z)) > 0.0f || length(sigma_a) > cfg.sss_threshold;
+}
+
 __device__ __forceinline__ float next_bounce_bound(const DeviceConfig& cfg, float3 sigma_a, float3 sigma_s, int seed, int pixel_index, int depth)
 {
-	if (!(sigma_s.x > 0.0f || length(sigma_a) > cfg.sss_threshold)) return CUDART_INF_F;
+	if (!medium_participates(cfg, sigma_a, sigma_s)) return CUDART_INF_F;
 	Rng rng;
-	rng.seed((uint32_t)(hash_ref(seed) * hash_ref(pixel_index) * hash_ref(depth)), 0.0f, 1.0f);
-	const float scattering_distance = -__logf(rng.next()) / sigma_s.x;
+	rng.seed3(cfg.sampler, seed, pixel_index, depth, 0u, 0.0f, 1.0f);
+	const float scattering_distance = -__logf(rng.next()) / sss_sampling_sigma(cfg, sigma_s, seed, pixel_index, depth);
 	// hits with t <= d are still needed (the test is d < t_hit): bound = next float above d.
 	// NaN (0/0) never compares less than t_hit -> no clipping.
 	if (!(scattering_distance == scattering_distance)) return CUDART_INF_F;
@@ -33,9 +51,11 @@ __device__ __forceinline__ float next_bounce_bound(const DeviceConfig& cfg, floa
 // ------------------------------------------------------------------------------------------
 // k_generate — init_data_kernel + generate_ray_kernel fused (path_tracer_kernel.cu:275-379)
 // ------------------------------------------------------------------------------------------
+template <bool ALT = false>
 __global__ void __launch_bounds__(256) k_generate(PathState st, int* __restrict__ queue, int* __restrict__ counts, int n_counts,
 	CameraParams cam, DeviceConfig cfg, int pixel_count, int n_slots, int first_pass, int pass_stride, int tiles_x)
 {
+	if (!ALT) { cfg.sampler = 0; cfg.sss_mode = 0; }   // the default instantiation is the reference's sampler, folded at compile time
 	const int total = pixel_count * n_slots;
 	int tid = blockIdx.x * blockDim.x + threadIdx.x;
 	// counts[0..n_counts) = live paths per depth; counts[n_counts..2*n_counts) = per-depth work-fetch cursors of the persistent
@@ -56,7 +76,7 @@ __global__ void __launch_bounds__(256) k_generate(PathState st, int* __restrict_
 		const int id = slot * pixel_count + pixel;
 		int seed = first_pass + slot * pass_stride;
 		float3 o, d;
-		generate_camera_ray(cam, pixel, seed, cfg.use_anti_alias != 0, o, d);
+		generate_camera_ray(cam, pixel, seed, cfg.use_anti_alias != 0, o, d, cfg.sampler);
 		st.ray_o[id] = make_float4(o.x, o.y, o.z, 0.0f);
 		st.ray_d[id] = make_float4(d.x, d.y, d.z, next_bounce_bound(cfg, cfg.air_sigma_a, cfg.air_sigma_s, seed, pixel, 0));
 		st.radiance[id] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);

@@ -17,6 +17,10 @@ __device__ __forceinline__ float3 sample_texture(const DeviceTexture& tex, float
 {
 	float ux = uv.x - floorf(uv.x);
 	float uy = uv.y - floorf(uv.y);
+	// option texture_filter=hardware: the bilinear filter of texture.h:22-67 done by the texture unit on a cudaArray copy
+	// of the same RGBA8 image — texel i sits at i + 0.5 in unnormalised texture coordinates, clamp addressing like the software filter's
+	// clamped floor / ceil indices.  9-bit filter weights: NOT bit-identical to the software filter, which stays the parity mode (default).
+	if (use_bilinear && tex.tex) return sample_image_hw(tex.tex, tex.width, tex.height, ux, 1.0f - uy);
 	return sample_image(tex.pixels, tex.width, tex.height, ux, 1.0f - uy, use_bilinear);
 }
 
@@ -38,21 +42,40 @@ __device__ __forceinline__ float3 sample_texture(const DeviceTexture& tex, float
 #ifndef PTB_RR_START_DEPTH
 #define PTB_RR_START_DEPTH 3
 #endif
-__device__ __forceinline__ bool russian_roulette(float3& not_absorbed, int seed, int pixel_index, int depth)
+__device__ __forceinline__ bool russian_roulette(float3& not_absorbed, int seed, int pixel_index, int depth, int sampler)
 {
 	Rng rr;
-	rr.seed((uint32_t)(hash_ref(seed) * hash_ref(pixel_index) * hash_ref(depth)) ^ 0x3c6ef372u, 0.0f, 1.0f);
+	rr.seed3(sampler, seed, pixel_index, depth, 0x3c6ef372u, 0.0f, 1.0f);
 	const float p = fminf(fmaxf(fmaxf(not_absorbed.x, fmaxf(not_absorbed.y, not_absorbed.z)), 0.05f), 1.0f);
 	if (rr.next() >= p) return false;
 	not_absorbed = not_absorbed * (1.0f / p);
 	return true;
 }
 
-template <bool SORT, bool NEE, bool RR = false>
+// spectral single-sample MIS weights of option sss=per_channel (balance heuristic over the uniformly picked channel)
+__device__ __forceinline__ float3 sss_scatter_weight(float3 sigma_s, float d)
+{
+	const float3 p = make_float3(sigma_s.x * __expf(-sigma_s.x * d), sigma_s.y * __expf(-sigma_s.y * d), sigma_s.z * __expf(-sigma_s.z * d));
+	const float mean = (p.x + p.y + p.z) * (1.0f / 3.0f);
+	return mean > 0.0f ? make_float3(p.x / mean, p.y / mean, p.z / mean) : make_float3(0.0f, 0.0f, 0.0f);
+}
+__device__ __forceinline__ float3 sss_survive_weight(float3 sigma_s, float t)
+{
+	// sigma = 0: the channel never scatters (and 0 * inf must not appear when the ray misses everything, t = inf)
+	const float3 p = make_float3(sigma_s.x > 0.0f ? __expf(-sigma_s.x * t) : 1.0f, sigma_s.y > 0.0f ? __expf(-sigma_s.y * t) : 1.0f,
+		sigma_s.z > 0.0f ? __expf(-sigma_s.z * t) : 1.0f);
+	const float mean = (p.x + p.y + p.z) * (1.0f / 3.0f);
+	return mean > 0.0f ? make_float3(p.x / mean, p.y / mean, p.z / mean) : make_float3(0.0f, 0.0f, 0.0f);
+}
+
+// ALT: the instantiation that honours the estimator options sampler / sss; the default instantiations fold both to the reference's
+// behaviour at compile time, so the parity path carries none of their branches (measured: a run-time switch cost k_shade 2.4 % on c2).
+template <bool SORT, bool NEE, bool RR = false, bool ALT = false>
 __global__ void __launch_bounds__(128, PTB_SHADE_MIN_BLOCKS) k_shade(DeviceScene sc, PathState st, DeviceConfig cfg, int depth, int pixel_count, int first_pass, int pass_stride,
 	const int* __restrict__ queue_in, const int* __restrict__ count_in, int* __restrict__ queue_out, int* __restrict__ count_out, int* __restrict__ shadow_count,
 	int octant_order)
 {
+	if (!ALT) { cfg.sampler = 0; cfg.sss_mode = 0; }
 	__shared__ int s_oct[10];
 	__shared__ int s_ids[SORT ? 128 : 1];
 	__shared__ int s_hist[SORT ? 16 : 1];
@@ -113,7 +136,7 @@ __global__ void __launch_bounds__(128, PTB_SHADE_MIN_BLOCKS) k_shade(DeviceScene
 			int prim = __float_as_int(h4.w);
 
 			Rng rng;
-			rng.seed((uint32_t)(hash_ref(seed) * hash_ref(pixel_index) * hash_ref(depth)), 0.0f, 1.0f);
+			rng.seed3(cfg.sampler, seed, pixel_index, depth, 0u, 0.0f, 1.0f);
 
 			float3 sigma_a = cfg.air_sigma_a, sigma_s = cfg.air_sigma_s;
 			if (medium_index >= 0)
@@ -125,10 +148,10 @@ __global__ void __launch_bounds__(128, PTB_SHADE_MIN_BLOCKS) k_shade(DeviceScene
 
 			bool done = false;
 			alive = true;
-			if (sigma_s.x > 0.0f || length(sigma_a) > cfg.sss_threshold)
+			if (medium_participates(cfg, sigma_a, sigma_s))
 			{
 				float rand = rng.next();
-				float scattering_distance = -__logf(rand) / sigma_s.x;
+				float scattering_distance = -__logf(rand) / sss_sampling_sigma(cfg, sigma_s, seed, pixel_index, depth);
 				if (scattering_distance < min_t)
 				{
 					float rand1 = rng.next();
@@ -136,6 +159,9 @@ __global__ void __launch_bounds__(128, PTB_SHADE_MIN_BLOCKS) k_shade(DeviceScene
 					float3 next_o = ray_o + ray_d * scattering_distance;
 					float3 next_d = sample_on_sphere(rand1, rand2);
 					not_absorbed = not_absorbed * absorption_through_medium(sigma_a, scattering_distance);
+					// per-channel mode: the distance came from ONE channel's sigma_s' picked uniformly; single-sample MIS over the three
+					// channels weights channel c by sigma_c exp(-sigma_c d) / mean_j(sigma_j exp(-sigma_j d)) (1 when the three are equal)
+					if (cfg.sss_mode) not_absorbed = not_absorbed * sss_scatter_weight(sigma_s, scattering_distance);
 					st.ray_o[id] = make_float4(next_o.x, next_o.y, next_o.z, 0.0f);
 					st.ray_d[id] = make_float4(next_d.x, next_d.y, next_d.z, next_bounce_bound(cfg, sigma_a, sigma_s, seed, pixel_index, depth + 1));
 					oct_key = (next_d.x < 0.0f ? 4 : 0) | (next_d.y < 0.0f ? 2 : 0) | (next_d.z < 0.0f ? 1 : 0);
@@ -143,7 +169,7 @@ __global__ void __launch_bounds__(128, PTB_SHADE_MIN_BLOCKS) k_shade(DeviceScene
 					if (length(not_absorbed) <= cfg.energy_threshold) alive = false;
 					if (RR && alive && depth >= PTB_RR_START_DEPTH)
 					{
-						alive = russian_roulette(not_absorbed, seed, pixel_index, depth);
+						alive = russian_roulette(not_absorbed, seed, pixel_index, depth, cfg.sampler);
 						st.throughput[id] = make_float4(not_absorbed.x, not_absorbed.y, not_absorbed.z, t4.w);
 					}
 					done = true;
@@ -151,6 +177,8 @@ __global__ void __launch_bounds__(128, PTB_SHADE_MIN_BLOCKS) k_shade(DeviceScene
 				else
 				{
 					not_absorbed = not_absorbed * absorption_through_medium(sigma_a, min_t);
+					// per-channel mode: reaching the surface unscattered has probability mean_j exp(-sigma_j t) under the channel pick
+					if (cfg.sss_mode) not_absorbed = not_absorbed * sss_survive_weight(sigma_s, min_t);
 				}
 			}
 
@@ -295,7 +323,7 @@ __global__ void __launch_bounds__(128, PTB_SHADE_MIN_BLOCKS) k_shade(DeviceScene
 						nee_flag = 1.0f;
 						// own random stream: the path itself is the one the reference estimator follows
 						Rng lrng;
-						lrng.seed((uint32_t)(hash_ref(seed) * hash_ref(pixel_index) * hash_ref(depth)) ^ 0x68bc21ebu, 0.0f, 1.0f);
+						lrng.seed3(cfg.sampler, seed, pixel_index, depth, 0x68bc21ebu, 0.0f, 1.0f);
 						const float u0 = lrng.next(), u1 = lrng.next(), u2 = lrng.next();
 						int lo = 0, hi = sc.n_lights - 1;
 						while (lo < hi) { const int mid = (lo + hi) >> 1; if (__ldg(&sc.light_cdf[mid]) < u0) lo = mid + 1; else hi = mid; }
@@ -337,7 +365,7 @@ __global__ void __launch_bounds__(128, PTB_SHADE_MIN_BLOCKS) k_shade(DeviceScene
 							}
 						}
 					}
-					if (RR && alive && depth >= PTB_RR_START_DEPTH) alive = russian_roulette(not_absorbed, seed, pixel_index, depth);
+					if (RR && alive && depth >= PTB_RR_START_DEPTH) alive = russian_roulette(not_absorbed, seed, pixel_index, depth, cfg.sampler);
 					st.ray_o[id] = make_float4(next_o.x, next_o.y, next_o.z, nee_flag);
 					st.throughput[id] = make_float4(not_absorbed.x, not_absorbed.y, not_absorbed.z, medium_bits);
 				}

@@ -63,18 +63,43 @@ __device__ __forceinline__ int hash_ref(int a_in)
 	return (int)a;
 }
 
+// Sampler option "pcg" (estimator upgrade, SURVEY.md 8f rank 4 — NOT a parity mode): the reference keys its streams by the PRODUCT
+// hash(seed) * hash(pixel) * hash(depth), which collides whenever two factors swap or one hash is 0 / even-heavy; the pcg sampler keys a
+// 32-bit PCG (Jarzynski & Olano 2020 output permutation over an LCG) by a nested hash of the three coordinates and a stream salt.
+__device__ __forceinline__ uint32_t pcg_permute(uint32_t state)
+{
+	const uint32_t word = ((state >> ((state >> 28u) + 4u)) ^ state) * 277803737u;
+	return (word >> 22u) ^ word;
+}
+__device__ __forceinline__ uint32_t pcg_hash(uint32_t v) { return pcg_permute(v * 747796405u + 2891336453u); }
+
 struct Rng
 {
 	uint32_t x;
 	float lo, span;
+	bool pcg;
 	__device__ __forceinline__ void seed(uint32_t s, float a, float b)
 	{
 		x = s % 2147483647u;
 		if (x == 0u) x = 1u;
 		lo = a; span = b - a;
+		pcg = false;
+	}
+	// stream keyed by three coordinates: sampler 0 = the reference's product of hashes (xor salt), sampler 1 = pcg
+	__device__ __forceinline__ void seed3(int sampler, int c0, int c1, int c2, uint32_t salt, float a, float b)
+	{
+		if (sampler == 0) { seed((uint32_t)(hash_ref(c0) * hash_ref(c1) * hash_ref(c2)) ^ salt, a, b); return; }
+		x = pcg_hash((uint32_t)c2 + pcg_hash((uint32_t)c1 + pcg_hash((uint32_t)c0 ^ salt ^ 0x9e3779b9u)));
+		lo = a; span = b - a;
+		pcg = true;
 	}
 	__device__ __forceinline__ float next()
 	{
+		if (pcg)
+		{
+			x = x * 747796405u + 2891336453u;
+			return (float)(pcg_permute(x) >> 8) * (1.0f / 16777216.0f) * span + lo;
+		}
 		x = (uint32_t)(((uint64_t)x * 48271ull) % 2147483647ull);
 		float r = (float)(x - 1u);
 		r /= 2147483648.0f;
@@ -91,14 +116,14 @@ struct CameraParams
 };
 
 __device__ __forceinline__ void generate_camera_ray(const CameraParams& cam, int pixel_index, int seed, bool use_anti_alias,
-	float3& origin, float3& direction)
+	float3& origin, float3& direction, int sampler = 0)
 {
 	float2 resolution = cam.resolution;
 	int image_y = (int)(pixel_index / resolution.x);
 	int image_x = pixel_index - (image_y * resolution.x);
 
 	Rng rng;
-	rng.seed((uint32_t)(hash_ref(seed) * hash_ref(seed) * hash_ref(pixel_index)), -0.5f, 0.5f);
+	rng.seed3(sampler, seed, seed, pixel_index, sampler ? 0x243f6a88u : 0u, -0.5f, 0.5f);
 
 	float jitter_x = 0.0f;
 	float jitter_y = 0.0f;
@@ -319,6 +344,12 @@ __device__ __forceinline__ float3 sample_image(const uint8_t* __restrict__ pixel
 	return texel_rgb(pixels, width, x_image, y_image);
 }
 
+__device__ __forceinline__ float3 sample_image_hw(cudaTextureObject_t tex, int width, int height, float u, float v_flipped)
+{
+	const float4 c = tex2D<float4>(tex, u * (float)(width - 1) + 0.5f, v_flipped * (float)(height - 1) + 0.5f);
+	return make_float3(c.x, c.y, c.z);
+}
+
 __device__ __forceinline__ void cube_uv(float x, float y, float z, int& index, float& u, float& v)
 {
 	float ax = fabsf(x), ay = fabsf(y), az = fabsf(z);
@@ -341,6 +372,7 @@ struct SkyParams
 	const uint8_t* faces[6];
 	int length;
 	int use_sky_box, use_sky, use_bilinear;
+	cudaTextureObject_t face_tex[6];   // option texture_filter=hardware, else 0
 };
 
 __device__ __forceinline__ float3 background_color(const SkyParams& sky, float3 direction)
@@ -350,6 +382,7 @@ __device__ __forceinline__ float3 background_color(const SkyParams& sky, float3 
 		float u, v;
 		int index;
 		cube_uv(direction.x, direction.y, direction.z, index, u, v);
+		if (sky.use_bilinear && sky.face_tex[index]) return sample_image_hw(sky.face_tex[index], sky.length, sky.length, u, 1.0f - v);
 		return sample_image(sky.faces[index], sky.length, sky.length, u, 1.0f - v, sky.use_bilinear != 0);
 	}
 	if (sky.use_sky)

@@ -99,6 +99,10 @@ struct ptb_renderer
 	int sort_by_material = 0;              // block-local material sort in k_shade (measured: profiles/r01_experiments.md)
 	int octant_order = 0;                  // next-depth queue grouped by ray-direction octant per block (measured: profiles/r01_experiments.md)
 	int tile_order = 1;                    // camera rays enter the first queue in 8x4 pixel tiles
+	int sampler = 0;                       // estimator option: 0 = the reference's hash-product + minstd streams, 1 = pcg (pt_device.cuh)
+	int sss_mode = 0;                      // estimator option: 1 = per-channel subsurface scattering (kernels_shade.cuh)
+	int hw_textures = 0;                   // texture_filter=hardware: bilinear lookups by the texture unit on cudaArray copies (takes effect at load)
+	std::vector<cudaArray_t> texture_arrays; std::vector<cudaTextureObject_t> texture_objects;
 	int l2_persist = 0;                    // 1: binary nodes + leaf-order triangles in one arena under a persisting L2 access-policy window (measured: profiles/r02_experiments.md)
 	void* l2_arena = nullptr; size_t l2_arena_bytes = 0;
 	// facts about the last acceleration-structure build (ptb_bvh_info)
@@ -170,6 +174,7 @@ struct ptb_renderer
 	int merged_passes = 0;
 	unsigned long long* pass_count_dev = nullptr;
 	const float* staged_tris24 = nullptr; size_t staged_tris_count = 0;   // device copy of the world-space triangles upload_geometry may adopt
+	bool root_parse_ok = false;            // ptb_dist_load_scene: this rank parsed the scene files and has not uploaded them yet
 	double bcast_ms[5] = { 0, 0, 0, 0, 0 }, bcast_bytes = 0.0;   // timing of the last ptb_dist_broadcast_scene on this rank
 
 	ptb_stats stats;
@@ -380,6 +385,9 @@ void release_scene_device(ptb_renderer* r)
 	for (void* p : r->geometry_allocs) cudaFree(p);
 	for (void* p : r->material_allocs) cudaFree(p);
 	for (void* p : r->light_allocs) cudaFree(p);
+	for (cudaTextureObject_t t : r->texture_objects) cudaDestroyTextureObject(t);
+	for (cudaArray_t a : r->texture_arrays) cudaFreeArray(a);
+	r->texture_objects.clear(); r->texture_arrays.clear();
 	r->scene_allocs.clear(); r->geometry_allocs.clear(); r->material_allocs.clear(); r->light_allocs.clear();
 	memset(&r->dscene, 0, sizeof(r->dscene));
 	r->bvh_nodes = r->bvh_bytes = 0;
@@ -783,6 +791,34 @@ int upload_materials(ptb_renderer* r)
 	return 0;
 }
 
+// texture_filter=hardware: an RGBA8 image as a cudaArray + texture object (unnormalised coordinates, clamp, linear filter, bytes read as
+// normalised floats) — the reference filters in software (Core/texture.h:15-79, Core/cube_map.h:20-119); this is the optional fast path
+int make_texture_object(ptb_renderer* r, const Texture& t, cudaTextureObject_t* out)
+{
+	*out = 0;
+	if (t.width <= 0 || t.height <= 0 || t.rgba.size() < (size_t)t.width * t.height * 4) return 0;
+	cudaChannelFormatDesc desc = cudaCreateChannelDesc<uchar4>();
+	cudaArray_t arr = nullptr;
+	PTB_CUDA(cudaMallocArray(&arr, &desc, (size_t)t.width, (size_t)t.height));
+	r->texture_arrays.push_back(arr);
+	PTB_CUDA(cudaMemcpy2DToArray(arr, 0, 0, t.rgba.data(), (size_t)t.width * 4, (size_t)t.width * 4, (size_t)t.height, cudaMemcpyHostToDevice));
+	cudaResourceDesc res;
+	memset(&res, 0, sizeof(res));
+	res.resType = cudaResourceTypeArray;
+	res.res.array.array = arr;
+	cudaTextureDesc td;
+	memset(&td, 0, sizeof(td));
+	td.addressMode[0] = cudaAddressModeClamp; td.addressMode[1] = cudaAddressModeClamp;
+	td.filterMode = cudaFilterModeLinear;
+	td.readMode = cudaReadModeNormalizedFloat;
+	td.normalizedCoords = 0;
+	cudaTextureObject_t obj = 0;
+	PTB_CUDA(cudaCreateTextureObject(&obj, &res, &td, nullptr));
+	r->texture_objects.push_back(obj);
+	*out = obj;
+	return 0;
+}
+
 int upload_scene(ptb_renderer* r)
 {
 	release_scene_device(r);
@@ -800,13 +836,19 @@ int upload_scene(ptb_renderer* r)
 		DeviceTexture dt;
 		if (upload(r, t.rgba.data(), t.rgba.size(), &dt.pixels)) return 1;
 		dt.width = t.width; dt.height = t.height;
+		dt.tex = 0;
+		if (r->hw_textures && make_texture_object(r, t, &dt.tex)) return 1;
 		textures.push_back(dt);
 	}
 	if (upload(r, textures.data(), textures.size(), &ds.textures)) return 1;
 	ds.n_textures = (int)textures.size();
 
 	for (int f = 0; f < 6; f++)
+	{
 		if (upload(r, s.cube_faces[f].rgba.data(), s.cube_faces[f].rgba.size(), &ds.sky.faces[f])) return 1;
+		ds.sky.face_tex[f] = 0;
+		if (r->hw_textures && make_texture_object(r, s.cube_faces[f], &ds.sky.face_tex[f])) return 1;
+	}
 	ds.sky.length = s.cube_length;
 	ds.sky.use_sky_box = r->cfg.use_sky_box ? 1 : 0;
 	ds.sky.use_sky = r->cfg.use_sky ? 1 : 0;
@@ -830,6 +872,8 @@ DeviceConfig device_config(const ptb_renderer* r)
 	c.air_n = r->cfg.air_refraction_index;
 	c.air_sigma_a = make_float3(r->cfg.air_absorption_coef.x, r->cfg.air_absorption_coef.y, r->cfg.air_absorption_coef.z);
 	c.air_sigma_s = make_float3(r->cfg.air_reduced_scattering_coef.x, r->cfg.air_reduced_scattering_coef.y, r->cfg.air_reduced_scattering_coef.z);
+	c.sampler = r->sampler;
+	c.sss_mode = r->sss_mode;
 	return c;
 }
 
@@ -942,7 +986,9 @@ int enqueue_batch(ptb_renderer* r, ptb_renderer::BatchContext& ctx, cudaEvent_t 
 	const bool prof = r->profile_stages != 0;
 	cudaStream_t stream = ctx.stream;
 	const int tiles_x = (r->tile_order && r->cfg.width % 8 == 0 && r->cfg.height % 4 == 0) ? r->cfg.width / 8 : 0;
-	k_generate<<<grid_for(r, total, 256, 8), 256, 0, stream>>>(ctx.st, ctx.queue[0], ctx.counts, n_counts, cp, dc, px, n_slots, first_pass, stride, tiles_x);
+	const bool alt = r->sampler != 0 || r->sss_mode != 0;   // estimator options: the ALT instantiations of k_generate / k_shade
+	if (alt) k_generate<true><<<grid_for(r, total, 256, 8), 256, 0, stream>>>(ctx.st, ctx.queue[0], ctx.counts, n_counts, cp, dc, px, n_slots, first_pass, stride, tiles_x);
+	else k_generate<false><<<grid_for(r, total, 256, 8), 256, 0, stream>>>(ctx.st, ctx.queue[0], ctx.counts, n_counts, cp, dc, px, n_slots, first_pass, stride, tiles_x);
 	r->stats.kernel_launches++;
 	for (int depth = 0; depth < r->cfg.max_tracer_depth; depth++)
 	{
@@ -962,7 +1008,9 @@ int enqueue_batch(ptb_renderer* r, ptb_renderer::BatchContext& ctx, cudaEvent_t 
 #define PTB_SHADE_ARGS r->dscene, ctx.st, dc, depth, px, first_pass, stride, qin, ctx.counts + depth, qout, ctx.counts + depth + 1, shadow_count, r->octant_order
 		if (r->nee)
 		{
-			if (r->russian_roulette) k_shade<false, true, true><<<sgrid, 128, 0, stream>>>(PTB_SHADE_ARGS);
+			if (alt && r->russian_roulette) k_shade<false, true, true, true><<<sgrid, 128, 0, stream>>>(PTB_SHADE_ARGS);
+			else if (alt) k_shade<false, true, false, true><<<sgrid, 128, 0, stream>>>(PTB_SHADE_ARGS);
+			else if (r->russian_roulette) k_shade<false, true, true><<<sgrid, 128, 0, stream>>>(PTB_SHADE_ARGS);
 			else if (r->sort_by_material) k_shade<true, true><<<sgrid, 128, 0, stream>>>(PTB_SHADE_ARGS);
 			else k_shade<false, true><<<sgrid, 128, 0, stream>>>(PTB_SHADE_ARGS);
 			if (depth + 1 < r->cfg.max_tracer_depth)
@@ -971,6 +1019,8 @@ int enqueue_batch(ptb_renderer* r, ptb_renderer::BatchContext& ctx, cudaEvent_t 
 				r->stats.kernel_launches++;
 			}
 		}
+		else if (alt && r->russian_roulette) k_shade<false, false, true, true><<<sgrid, 128, 0, stream>>>(PTB_SHADE_ARGS);
+		else if (alt) k_shade<false, false, false, true><<<sgrid, 128, 0, stream>>>(PTB_SHADE_ARGS);
 		else if (r->russian_roulette) k_shade<false, false, true><<<sgrid, 128, 0, stream>>>(PTB_SHADE_ARGS);
 		else if (r->sort_by_material) k_shade<true, false><<<sgrid, 128, 0, stream>>>(PTB_SHADE_ARGS);
 		else k_shade<false, false><<<sgrid, 128, 0, stream>>>(PTB_SHADE_ARGS);
@@ -1558,7 +1608,7 @@ int ptb_generate_rays(ptb_renderer* r, int pass, float* out_rays6)
 {
 	if (!r || r->host_only) { set_error("[Error]no CUDA device"); return 1; }
 	const int px = r->pixel_count;
-	k_generate<<<grid_for(r, px, 256, 8), 256, 0, r->stream>>>(r->st, r->queue[0], r->counts, r->cfg.max_tracer_depth + 2, camera_params(r->cam), device_config(r), px, 1, pass, 1, 0);
+	k_generate<false><<<grid_for(r, px, 256, 8), 256, 0, r->stream>>>(r->st, r->queue[0], r->counts, r->cfg.max_tracer_depth + 2, camera_params(r->cam), device_config(r), px, 1, pass, 1, 0);
 	std::vector<float4> o(px), d(px);
 	PTB_CUDA(cudaMemcpyAsync(o.data(), r->st.ray_o, (size_t)px * sizeof(float4), cudaMemcpyDeviceToHost, r->stream));
 	PTB_CUDA(cudaMemcpyAsync(d.data(), r->st.ray_d, (size_t)px * sizeof(float4), cudaMemcpyDeviceToHost, r->stream));
@@ -1577,7 +1627,7 @@ int ptb_capture_rays(ptb_renderer* r, int pass, int depth, int32_t* out_pixels, 
 	if (!r->scene_loaded) { set_error("[Error]no scene loaded"); return -1; }
 	const int px = r->pixel_count;
 	DeviceConfig dc = device_config(r);
-	k_generate<<<grid_for(r, px, 256, 8), 256, 0, r->stream>>>(r->st, r->queue[0], r->counts, r->cfg.max_tracer_depth + 2, camera_params(r->cam), dc, px, 1, pass, 1, 0);
+	k_generate<false><<<grid_for(r, px, 256, 8), 256, 0, r->stream>>>(r->st, r->queue[0], r->counts, r->cfg.max_tracer_depth + 2, camera_params(r->cam), dc, px, 1, pass, 1, 0);
 	int d = 0;
 	for (; d < depth && d < r->cfg.max_tracer_depth; d++)
 	{
@@ -1832,6 +1882,24 @@ int ptb_set_option(ptb_renderer* r, const char* key, const char* value)
 	if (k == "octant_order") { r->octant_order = atoi(value); return 0; }
 	if (k == "sort_by_material") { r->sort_by_material = atoi(value); return 0; }
 	if (k == "russian_roulette") { r->russian_roulette = atoi(value) != 0; return ptb_clear(r); }
+	if (k == "sampler")
+	{
+		if (v != "reference" && v != "pcg") { set_error("[Error]sampler must be reference or pcg"); return 1; }
+		r->sampler = v == "pcg" ? 1 : 0;
+		return ptb_clear(r);
+	}
+	if (k == "sss")
+	{
+		if (v != "reference" && v != "per_channel") { set_error("[Error]sss must be reference or per_channel"); return 1; }
+		r->sss_mode = v == "per_channel" ? 1 : 0;
+		return ptb_clear(r);
+	}
+	if (k == "texture_filter")
+	{
+		if (v != "software" && v != "hardware") { set_error("[Error]texture_filter must be software or hardware"); return 1; }
+		r->hw_textures = v == "hardware" ? 1 : 0;   // takes effect at the next ptb_load_scene
+		return 0;
+	}
 	if (k == "pass_clamp") { r->pass_clamp = (float)atof(value); return 0; }   // diagnostic: per-pass clamp of the accumulation (default: the reference's)
 	if (k == "estimator")
 	{

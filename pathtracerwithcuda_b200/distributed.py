@@ -103,22 +103,11 @@ class DistRenderer:
             self.r.load_scene(scene_json_path, asset_root)
             return
         import time
-        err = None
         t0 = time.perf_counter()
-        if self.rank == root:
-            try:
-                self.r.load_scene(scene_json_path, asset_root)
-            except Exception as e:      # still take part in the broadcast: the others fail with us instead of hanging
-                err = e
-        self.timing = {"root_load_s": time.perf_counter() - t0 if self.rank == root else None}
         try:
-            self.r.dist_broadcast_scene(root)
-        except Exception:
-            if err is None:
-                raise
-        if err is not None:
-            raise err
-        self.timing["broadcast"] = self.r.dist_broadcast_timing()
+            self.r.dist_load_scene(scene_json_path if self.rank == root else "", asset_root if self.rank == root else "", root)
+        finally:
+            self.timing = {"load_s": time.perf_counter() - t0, "broadcast": self.r.dist_broadcast_timing()}
 
     def begin(self):
         self.local_passes = 0

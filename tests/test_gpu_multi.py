@@ -77,6 +77,18 @@ def test_dist_world_of_one_runs_the_nccl_path(workload_root):
     assert passes == 5
     assert np.array_equal(img.view(np.uint32), single.image_f32().view(np.uint32))
     assert np.array_equal(r.merged_image_u8(), single.image_u8())
+    # the collective load: parse on the root (host only), broadcast, build from the DEVICE copy of the triangles
+    r.dist_load_scene(w["scene"], root, 0)
+    tri_a, mat_a = r.scene_triangles()
+    tri_b, mat_b = single.scene_triangles()
+    assert np.array_equal(tri_a.view(np.uint32), tri_b.view(np.uint32)) and np.array_equal(mat_a, mat_b)
+    r.dist_clear()
+    r.dist_render(5)
+    r.dist_reduce(0)
+    img, passes = r.merged_image_f32()
+    assert passes == 5 and np.array_equal(img.view(np.uint32), single.image_f32().view(np.uint32))
+    with pytest.raises(ptb.PtbError):
+        r.dist_load_scene("/nonexistent/scene.json", root, 0)      # a root that cannot parse fails every rank, nobody hangs
     r.dist_shutdown()
     with pytest.raises(ptb.PtbError):
         r.dist_render(1)                # no communicator any more: fails loudly
