@@ -68,6 +68,9 @@ struct DeviceConfig
 	int sss_mode;       // 1: per-channel subsurface scattering (kernels_shade.cuh: spectral MIS over sigma_s'.xyz instead of sigma_s'.x only)
 };
 
+// hit.w of a path that ended inside the closest-hit kernel (option inline_scatter): neither a triangle (>= 0), a miss (-1) nor a sphere (<= -2 small)
+#define PTB_PRIM_DEAD ((int)0x80000001)
+
 // SoA path state, indexed by path id = slot * pixel_count + pixel.
 struct PathState
 {

@@ -780,9 +780,26 @@ __global__ void __launch_bounds__(128, PTB_PERSISTENT_MIN_BLOCKS) k_extend_specu
 // (child base + hit bits), `tri_group` = leaf triangles still to test; stack entries are node groups.
 // Phases: refill | wide-node step (one child popped, 8 quantised boxes decoded and tested) | triangle step.
 // ------------------------------------------------------------------------------------------
-template <bool COUNT>
+// FUSED (option inline_scatter, default on in parity mode): in a scattering medium most bounces are scatter events — the free flight ends
+// before any surface (k_shade: d < t_hit), the path gets an isotropic direction, its throughput is attenuated, nothing else happens
+// (path_tracer_kernel.cu:460-486).  The bounded search already knows it (no hit below the free-flight bound), so the lane performs the
+// event here with the reference's arithmetic and random stream of that depth and goes on tracing the SAME path, instead of a round trip
+// through hit record, queue, k_shade and the next launch per event.  The path runs ahead of the wavefront's loop depth by `lead`
+// bounces (kept in ray_o.w for k_shade<.., FUSED>); scatter events are executed as a voted phase like node and triangle steps.
+struct FusedArgs
+{
+	DeviceConfig cfg;
+	int loop_depth, pixel_count, first_pass, pass_stride, scatter_min;
+	// ray segments per ACTUAL depth (the call totals ptb_get_depth_profile reports): with paths ahead of the loop depth the queue sizes no longer
+	// say at which depth a search ran, so this kernel tallies its own searches (block histogram in shared memory, flushed once per block)
+	unsigned long long* depth_segments;
+	int n_depth_slots;
+};
+#define PTB_FUSED_HIST 66
+
+template <bool COUNT, bool FUSED = false>
 __global__ void __launch_bounds__(128, PTB_PERSISTENT_MIN_BLOCKS8) k_extend_persistent8(DeviceScene sc, PathState st, const int* __restrict__ queue, const int* __restrict__ count_ptr,
-	int* __restrict__ work_counter, unsigned long long* __restrict__ counters, int refill_min, int leaf_min)
+	int* __restrict__ work_counter, unsigned long long* __restrict__ counters, int refill_min, int leaf_min, FusedArgs fa = FusedArgs())
 {
 	const int count = *count_ptr;
 	const unsigned lane = threadIdx.x & 31u;
@@ -802,24 +819,40 @@ __global__ void __launch_bounds__(128, PTB_PERSISTENT_MIN_BLOCKS8) k_extend_pers
 #define PTB_POP8(dst) do { --sp; dst = stack[min(sp, PTB_STACK_SIZE8 - 1)]; } while (0)
 	int sp = 0;
 	uint2 current = make_uint2(0u, 0u), tri_group = make_uint2(0u, 0u);
+	int lead = 0;                // FUSED: bounces this path is ahead of the loop depth
+	bool at_scatter = false;     // FUSED: the search ended below the free-flight bound without a hit: a scatter event is due
+	__shared__ int s_hist[FUSED ? PTB_FUSED_HIST : 1];
+	if (FUSED)
+	{
+		if (threadIdx.x < PTB_FUSED_HIST) s_hist[threadIdx.x] = 0;
+		__syncthreads();
+	}
 
 	while (true)
 	{
 		// bookkeeping without votes: pop a node group when the lane ran dry, retire when nothing is left
-		if (id >= 0 && (current.y & 0xff000000u) == 0u && tri_group.y == 0u)
+		if (id >= 0 && !at_scatter && (current.y & 0xff000000u) == 0u && tri_group.y == 0u)
 		{
 			if (sp > 0) PTB_POP8(current);
+			else if (FUSED && best.prim == -1 && best.t < CUDART_INF_F) at_scatter = true;
 			else
 			{
 				__stcs(&st.hit[id], make_float4(best.prim == -1 ? CUDART_INF_F : best.t, best.t1, best.t2, __int_as_float(best.prim)));
+				if (FUSED && lead > 0)
+				{
+					// the ray in memory is the one the path had when it entered: k_shade needs the segment that found the surface
+					st.ray_o[id] = make_float4(o.x, o.y, o.z, __int_as_float(lead));
+					st.ray_d[id] = make_float4(d.x, d.y, d.z, 0.0f);
+				}
 				id = -1;
 			}
 		}
 		const bool has_ray = id >= 0;
 		const bool at_tri = has_ray && tri_group.y != 0u;
-		const bool at_node = has_ray && !at_tri && (current.y & 0xff000000u) != 0u;
+		const bool at_node = has_ray && !at_tri && !at_scatter && (current.y & 0xff000000u) != 0u;
 		const unsigned m_idle = __ballot_sync(FULL, !has_ray);
-		const unsigned m_node = __ballot_sync(FULL, at_node);
+		const unsigned m_scat = FUSED ? __ballot_sync(FULL, has_ray && at_scatter) : 0u;
+		const unsigned m_node = __ballot_sync(FULL, at_node) | m_scat;   // "work in flight" for the refill / exit tests below
 		const unsigned m_tri = __ballot_sync(FULL, at_tri);
 
 		if (m_idle != 0u && !exhausted && (__popc(m_idle) >= refill_min || (m_node | m_tri) == 0u))
@@ -840,6 +873,7 @@ __global__ void __launch_bounds__(128, PTB_PERSISTENT_MIN_BLOCKS8) k_extend_pers
 					d = make_float3(d4.x, d4.y, d4.z);
 					best.t = d4.w; best.t1 = CUDART_INF_F; best.t2 = CUDART_INF_F; best.prim = -1;
 					best_tri = 0x7fffffff;
+					if (FUSED) { lead = __float_as_int(o4.w); at_scatter = false; atomicAdd(&s_hist[min(fa.loop_depth + lead, PTB_FUSED_HIST - 1)], 1); }
 					for (int s = 0; s < sc.n_spheres; s++)
 					{
 						const float4 sph = __ldg(&sc.spheres[s]);
@@ -864,7 +898,74 @@ __global__ void __launch_bounds__(128, PTB_PERSISTENT_MIN_BLOCKS8) k_extend_pers
 		}
 		if ((m_node | m_tri) == 0u) break;
 
-		if (m_tri != 0u && (__popc(m_tri) >= leaf_min || m_node == 0u))
+		if (FUSED && m_scat != 0u && (__popc(m_scat) >= fa.scatter_min || ((m_node & ~m_scat) | m_tri) == 0u))
+		{
+			// ---- scatter phase: the medium event of k_shade (kernels_shade.cuh) for the lanes whose search ended below the free-flight bound
+			if (has_ray && at_scatter)
+			{
+				const DeviceConfig& cfg = fa.cfg;
+				const int slot = id / fa.pixel_count;
+				const int pixel_index = id - slot * fa.pixel_count;
+				const int seed = fa.first_pass + slot * fa.pass_stride;
+				const int depth = fa.loop_depth + lead;
+				const float4 t4 = depth == 0 ? make_float4(1.0f, 1.0f, 1.0f, __int_as_float(-1)) : st.throughput[id];
+				float3 not_absorbed = make_float3(t4.x, t4.y, t4.z);
+				const int medium_index = __float_as_int(t4.w);
+				float3 sigma_a = cfg.air_sigma_a, sigma_s = cfg.air_sigma_s;
+				if (medium_index >= 0)
+				{
+					const float4 md = __ldg(&sc.materials[medium_index].d), me = __ldg(&sc.materials[medium_index].e);
+					sigma_a = make_float3(md.x, md.y, md.z);
+					sigma_s = make_float3(md.w, me.x, me.y);
+				}
+				Rng rng;
+				rng.seed3(0, seed, pixel_index, depth, 0u, 0.0f, 1.0f);
+				const float rand = rng.next();
+				const float scattering_distance = -__logf(rand) / sigma_s.x;
+				const float rand1 = rng.next();
+				const float rand2 = rng.next();
+				const float3 next_o = o + d * scattering_distance;
+				const float3 next_d = sample_on_sphere(rand1, rand2);
+				not_absorbed = not_absorbed * absorption_through_medium(sigma_a, scattering_distance);
+				at_scatter = false;
+				if (length(not_absorbed) <= cfg.energy_threshold || depth + 1 >= cfg.max_depth)
+				{
+					// the path ends here: energy cut (:480-483) or the bounce limit of the reference's depth loop
+					__stcs(&st.hit[id], make_float4(CUDART_INF_F, 0.0f, 0.0f, __int_as_float(PTB_PRIM_DEAD)));
+					id = -1;
+				}
+				else
+				{
+					st.throughput[id] = make_float4(not_absorbed.x, not_absorbed.y, not_absorbed.z, t4.w);
+					lead++;
+					atomicAdd(&s_hist[min(depth + 1, PTB_FUSED_HIST - 1)], 1);     // the search of the next bounce starts here
+					o = next_o; d = next_d;
+					best.t = next_bounce_bound(cfg, sigma_a, sigma_s, seed, pixel_index, depth + 1);
+					best.t1 = CUDART_INF_F; best.t2 = CUDART_INF_F; best.prim = -1;
+					best_tri = 0x7fffffff;
+					for (int sidx = 0; sidx < sc.n_spheres; sidx++)
+					{
+						const float4 sph = __ldg(&sc.spheres[sidx]);
+						float t;
+						if (intersect_sphere(make_float3(sph.x, sph.y, sph.z), sph.w, o, d, t) && t < best.t && t > 0.0f)
+						{
+							best.t = t;
+							best.prim = -(sidx + 2);
+						}
+					}
+					const float tiny = 1e-30f;
+					const float3 ds = make_float3(fabsf(d.x) < tiny ? copysignf(tiny, d.x) : d.x, fabsf(d.y) < tiny ? copysignf(tiny, d.y) : d.y,
+						fabsf(d.z) < tiny ? copysignf(tiny, d.z) : d.z);
+					idir = make_float3(1.0f / ds.x, 1.0f / ds.y, 1.0f / ds.z);
+					oct_inv4 = (d.x < 0.0f ? 0u : 0x04040404u) | (d.y < 0.0f ? 0u : 0x02020202u) | (d.z < 0.0f ? 0u : 0x01010101u);
+					sp = 0;
+					tri_group = make_uint2(0u, 0u);
+					current = sc.n_triangles > 0 ? make_uint2(0u, 0x80000000u) : make_uint2(0u, 0u);
+				}
+			}
+			continue;
+		}
+		if (m_tri != 0u && (__popc(m_tri) >= leaf_min || (m_node & ~m_scat) == 0u))
 		{
 			// ---- triangle phase
 			if (at_tri)
@@ -945,6 +1046,12 @@ __global__ void __launch_bounds__(128, PTB_PERSISTENT_MIN_BLOCKS8) k_extend_pers
 			current.y = (hit_mask & 0xff000000u) | (e_imask >> 24);
 			tri_group.y = hit_mask & 0x00ffffffu;
 		}
+	}
+	if (FUSED)
+	{
+		__syncthreads();
+		if (threadIdx.x < PTB_FUSED_HIST && s_hist[threadIdx.x])
+			atomicAdd(&fa.depth_segments[min((int)threadIdx.x, fa.n_depth_slots - 1)], (unsigned long long)s_hist[threadIdx.x]);
 	}
 	if (COUNT)
 	{

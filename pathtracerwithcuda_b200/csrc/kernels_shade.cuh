@@ -70,8 +70,12 @@ __device__ __forceinline__ float3 sss_survive_weight(float3 sigma_s, float t)
 
 // ALT: the instantiation that honours the estimator options sampler / sss; the default instantiations fold both to the reference's
 // behaviour at compile time, so the parity path carries none of their branches (measured: a run-time switch cost k_shade 2.4 % on c2).
-template <bool SORT, bool NEE, bool RR = false, bool ALT = false>
-__global__ void __launch_bounds__(128, PTB_SHADE_MIN_BLOCKS) k_shade(DeviceScene sc, PathState st, DeviceConfig cfg, int depth, int pixel_count, int first_pass, int pass_stride,
+// FUSED (option inline_scatter): the closest-hit kernel of the deeper bounces performs the medium's scatter events itself
+// (k_extend_persistent8<.., true>, kernels_extend.cuh), so a path may be several bounces AHEAD of the wavefront's loop depth when it
+// arrives here: ray_o.w carries that lead (an int), every depth-keyed quantity uses loop depth + lead, a path the extend stage
+// finished off carries the primitive PTB_PRIM_DEAD, and the bounce limit is checked per path.
+template <bool SORT, bool NEE, bool RR = false, bool ALT = false, bool FUSED = false>
+__global__ void __launch_bounds__(128, PTB_SHADE_MIN_BLOCKS) k_shade(DeviceScene sc, PathState st, DeviceConfig cfg, int loop_depth, int pixel_count, int first_pass, int pass_stride,
 	const int* __restrict__ queue_in, const int* __restrict__ count_in, int* __restrict__ queue_out, int* __restrict__ count_out, int* __restrict__ shadow_count,
 	int octant_order)
 {
@@ -90,6 +94,7 @@ __global__ void __launch_bounds__(128, PTB_SHADE_MIN_BLOCKS) k_shade(DeviceScene
 		bool want_shadow = false;
 		int oct_key = 0;
 		int id = 0;
+		int path_lead = 0;
 		if (SORT)
 		{
 			int key = 15;
@@ -127,6 +132,9 @@ __global__ void __launch_bounds__(128, PTB_SHADE_MIN_BLOCKS) k_shade(DeviceScene
 			// at depth 0 the throughput is (1, 1, 1) in air by construction (init_data_kernel :275-297): k_generate does not
 			// write it and it is not read here
 			float4 o4 = st.ray_o[id], d4 = st.ray_d[id], h4 = st.hit[id];
+			const int lead = FUSED ? __float_as_int(o4.w) : 0;
+			path_lead = lead;
+			const int depth = loop_depth + lead;
 			float4 t4 = depth == 0 ? make_float4(1.0f, 1.0f, 1.0f, __int_as_float(-1)) : st.throughput[id];
 			float3 ray_o = make_float3(o4.x, o4.y, o4.z);
 			float3 ray_d = make_float3(d4.x, d4.y, d4.z);
@@ -148,7 +156,8 @@ __global__ void __launch_bounds__(128, PTB_SHADE_MIN_BLOCKS) k_shade(DeviceScene
 
 			bool done = false;
 			alive = true;
-			if (medium_participates(cfg, sigma_a, sigma_s))
+			if (FUSED && prim == PTB_PRIM_DEAD) { done = true; alive = false; }   // ended inside the closest-hit kernel (energy cut or bounce limit)
+			else if (medium_participates(cfg, sigma_a, sigma_s))
 			{
 				float rand = rng.next();
 				float scattering_distance = -__logf(rand) / sss_sampling_sigma(cfg, sigma_s, seed, pixel_index, depth);
@@ -162,7 +171,7 @@ __global__ void __launch_bounds__(128, PTB_SHADE_MIN_BLOCKS) k_shade(DeviceScene
 					// per-channel mode: the distance came from ONE channel's sigma_s' picked uniformly; single-sample MIS over the three
 					// channels weights channel c by sigma_c exp(-sigma_c d) / mean_j(sigma_j exp(-sigma_j d)) (1 when the three are equal)
 					if (cfg.sss_mode) not_absorbed = not_absorbed * sss_scatter_weight(sigma_s, scattering_distance);
-					st.ray_o[id] = make_float4(next_o.x, next_o.y, next_o.z, 0.0f);
+					st.ray_o[id] = make_float4(next_o.x, next_o.y, next_o.z, FUSED ? __int_as_float(lead) : 0.0f);
 					st.ray_d[id] = make_float4(next_d.x, next_d.y, next_d.z, next_bounce_bound(cfg, sigma_a, sigma_s, seed, pixel_index, depth + 1));
 					oct_key = (next_d.x < 0.0f ? 4 : 0) | (next_d.y < 0.0f ? 2 : 0) | (next_d.z < 0.0f ? 1 : 0);
 					st.throughput[id] = make_float4(not_absorbed.x, not_absorbed.y, not_absorbed.z, t4.w);
@@ -366,7 +375,7 @@ __global__ void __launch_bounds__(128, PTB_SHADE_MIN_BLOCKS) k_shade(DeviceScene
 						}
 					}
 					if (RR && alive && depth >= PTB_RR_START_DEPTH) alive = russian_roulette(not_absorbed, seed, pixel_index, depth, cfg.sampler);
-					st.ray_o[id] = make_float4(next_o.x, next_o.y, next_o.z, nee_flag);
+					st.ray_o[id] = make_float4(next_o.x, next_o.y, next_o.z, FUSED ? __int_as_float(lead) : nee_flag);
 					st.throughput[id] = make_float4(not_absorbed.x, not_absorbed.y, not_absorbed.z, medium_bits);
 				}
 				else
@@ -379,6 +388,8 @@ __global__ void __launch_bounds__(128, PTB_SHADE_MIN_BLOCKS) k_shade(DeviceScene
 				}
 			}
 		}
+		// a path ahead of the loop runs out of bounces before the loop does (the reference's depth loop ends at MaxDepth for every path)
+		if (FUSED && alive && loop_depth + path_lead + 1 >= cfg.max_depth) alive = false;
 		if (octant_order)
 		{
 			// block-level compaction grouped by the direction octant of the next ray: the 32 rays an extend warp
@@ -523,7 +534,8 @@ __global__ void __launch_bounds__(256) k_accumulate(const float4* __restrict__ r
 	int pixel_count, int n_slots, float clamp_hi)
 {
 	int p = blockIdx.x * blockDim.x + threadIdx.x;
-	// tally this batch's live-path counters (ray segments per depth) into the call totals
+	// tally this batch's live-path counters (ray segments per depth) into the call totals; n_counts stops at the first loop depth whose
+	// closest-hit kernel tallies its own searches (option inline_scatter)
 	if (p < n_counts && counts != nullptr) atomicAdd(&segment_totals[p], (unsigned long long)counts[p]);
 	if (p >= pixel_count) return;
 	float sx = image_sum[p * 3 + 0], sy = image_sum[p * 3 + 1], sz = image_sum[p * 3 + 2];

@@ -99,6 +99,9 @@ struct ptb_renderer
 	int sort_by_material = 0;              // block-local material sort in k_shade (measured: profiles/r01_experiments.md)
 	int octant_order = 0;                  // next-depth queue grouped by ray-direction octant per block (measured: profiles/r01_experiments.md)
 	int tile_order = 1;                    // camera rays enter the first queue in 8x4 pixel tiles
+	int inline_scatter = 1;                // medium scatter events performed inside the wide-tree closest-hit kernel (bit-identical images; off: one wavefront round trip per event)
+	int tune_scatter = 8;                  // ... as a voted phase once >= N lanes wait for one
+	bool scene_has_medium = false;         // some material (or the air) scatters: sigma_s'.x > 0
 	int sampler = 0;                       // estimator option: 0 = the reference's hash-product + minstd streams, 1 = pcg (pt_device.cuh)
 	int sss_mode = 0;                      // estimator option: 1 = per-channel subsurface scattering (kernels_shade.cuh)
 	int hw_textures = 0;                   // texture_filter=hardware: bilinear lookups by the texture unit on cudaArray copies (takes effect at load)
@@ -777,6 +780,9 @@ int upload_materials(ptb_renderer* r)
 	DeviceScene& ds = r->dscene;
 	std::vector<DeviceMaterial> mats;
 	for (auto& m : s.materials) mats.push_back(pack_material(m));
+	r->scene_has_medium = false;
+	for (auto& m : s.materials) if (m.reduced_scattering_coefficient[0] > 0.0f) r->scene_has_medium = true;
+	for (auto& sp : s.spheres) if (sp.mat.reduced_scattering_coefficient[0] > 0.0f) r->scene_has_medium = true;
 	ds.sphere_material_base = (int)mats.size();
 	std::vector<float4> spheres;
 	for (auto& sp : s.spheres)
@@ -897,7 +903,7 @@ int grid_for(const ptb_renderer* r, size_t items, int block, int blocks_per_sm)
 	return (int)std::max<size_t>(1, std::min(need, cap));
 }
 
-void launch_extend(ptb_renderer* r, cudaStream_t stream, size_t items, const PathState& st, const int* queue, const int* count_ptr, int* work_counter, int depth = 0)
+void launch_extend(ptb_renderer* r, cudaStream_t stream, size_t items, const PathState& st, const int* queue, const int* count_ptr, int* work_counter, int depth = 0, const FusedArgs* fused = nullptr)
 {
 	bool wide = r->dscene.bvh_layout == 8;
 	if (r->dscene.bvh_layout == 2 && r->dscene.bvh8_nodes && r->extend_persistent && depth >= r->hybrid_from_depth)
@@ -906,14 +912,24 @@ void launch_extend(ptb_renderer* r, cudaStream_t stream, size_t items, const Pat
 		DeviceScene sc8 = r->dscene;
 		sc8.bvh_nodes = r->dscene.bvh8_nodes; sc8.tri_isect = r->dscene.tri_isect8; sc8.bvh_layout = 8;
 		int grid = std::max(1, std::min(r->persistent_grid8, (int)((items + 127) / 128)));
-		if (r->count_traversal) k_extend_persistent8<true><<<grid, 128, 0, stream>>>(sc8, st, queue, count_ptr, work_counter, r->counters, r->tune_refill8, r->tune_leaf8);
+		if (fused)
+		{
+			if (r->count_traversal) k_extend_persistent8<true, true><<<grid, 128, 0, stream>>>(sc8, st, queue, count_ptr, work_counter, r->counters, r->tune_refill8, r->tune_leaf8, *fused);
+			else k_extend_persistent8<false, true><<<grid, 128, 0, stream>>>(sc8, st, queue, count_ptr, work_counter, r->counters, r->tune_refill8, r->tune_leaf8, *fused);
+		}
+		else if (r->count_traversal) k_extend_persistent8<true><<<grid, 128, 0, stream>>>(sc8, st, queue, count_ptr, work_counter, r->counters, r->tune_refill8, r->tune_leaf8);
 		else k_extend_persistent8<false><<<grid, 128, 0, stream>>>(sc8, st, queue, count_ptr, work_counter, r->counters, r->tune_refill8, r->tune_leaf8);
 		return;
 	}
 	if (wide && r->extend_persistent)
 	{
 		int grid = std::max(1, std::min(r->persistent_grid8, (int)((items + 127) / 128)));
-		if (r->count_traversal) k_extend_persistent8<true><<<grid, 128, 0, stream>>>(r->dscene, st, queue, count_ptr, work_counter, r->counters, r->tune_refill8, r->tune_leaf8);
+		if (fused)
+		{
+			if (r->count_traversal) k_extend_persistent8<true, true><<<grid, 128, 0, stream>>>(r->dscene, st, queue, count_ptr, work_counter, r->counters, r->tune_refill8, r->tune_leaf8, *fused);
+			else k_extend_persistent8<false, true><<<grid, 128, 0, stream>>>(r->dscene, st, queue, count_ptr, work_counter, r->counters, r->tune_refill8, r->tune_leaf8, *fused);
+		}
+		else if (r->count_traversal) k_extend_persistent8<true><<<grid, 128, 0, stream>>>(r->dscene, st, queue, count_ptr, work_counter, r->counters, r->tune_refill8, r->tune_leaf8);
 		else k_extend_persistent8<false><<<grid, 128, 0, stream>>>(r->dscene, st, queue, count_ptr, work_counter, r->counters, r->tune_refill8, r->tune_leaf8);
 		return;
 	}
@@ -987,6 +1003,14 @@ int enqueue_batch(ptb_renderer* r, ptb_renderer::BatchContext& ctx, cudaEvent_t 
 	cudaStream_t stream = ctx.stream;
 	const int tiles_x = (r->tile_order && r->cfg.width % 8 == 0 && r->cfg.height % 4 == 0) ? r->cfg.width / 8 : 0;
 	const bool alt = r->sampler != 0 || r->sss_mode != 0;   // estimator options: the ALT instantiations of k_generate / k_shade
+	// inline scatter events (kernels_extend.cuh: k_extend_persistent8<.., FUSED>): the reference's estimator only, and only where a medium exists
+	const bool fused = r->inline_scatter && (r->scene_has_medium || r->cfg.air_reduced_scattering_coef.x > 0.0f) && !alt && !r->nee && !r->russian_roulette && !r->sort_by_material && r->extend_persistent &&
+		(r->dscene.bvh_layout == 8 || (r->dscene.bvh_layout == 2 && r->dscene.bvh8_nodes));
+	FusedArgs fa;
+	fa.cfg = dc; fa.pixel_count = px; fa.first_pass = first_pass; fa.pass_stride = stride; fa.scatter_min = r->tune_scatter;
+	fa.depth_segments = r->segment_totals; fa.n_depth_slots = n_counts;
+	// loop depths traced by the fused kernel tally their own searches per actual depth; the queue sizes only count below that
+	const int tally_counts = fused ? (r->dscene.bvh_layout == 8 ? 0 : std::min(std::max(r->hybrid_from_depth, 0), n_counts)) : n_counts;
 	if (alt) k_generate<true><<<grid_for(r, total, 256, 8), 256, 0, stream>>>(ctx.st, ctx.queue[0], ctx.counts, n_counts, cp, dc, px, n_slots, first_pass, stride, tiles_x);
 	else k_generate<false><<<grid_for(r, total, 256, 8), 256, 0, stream>>>(ctx.st, ctx.queue[0], ctx.counts, n_counts, cp, dc, px, n_slots, first_pass, stride, tiles_x);
 	r->stats.kernel_launches++;
@@ -1001,7 +1025,8 @@ int enqueue_batch(ptb_renderer* r, ptb_renderer::BatchContext& ctx, cudaEvent_t 
 			r->stage_events.push_back(e0); r->stage_events.push_back(e1);
 			cudaEventRecord(e0, stream);
 		}
-		launch_extend(r, stream, total, ctx.st, qin, ctx.counts + depth, ctx.counts + n_counts + depth, depth);
+		fa.loop_depth = depth;
+		launch_extend(r, stream, total, ctx.st, qin, ctx.counts + depth, ctx.counts + n_counts + depth, depth, fused ? &fa : nullptr);
 		if (prof) cudaEventRecord(e1, stream);
 		int* shadow_count = ctx.counts + 2 * n_counts + depth;
 		const int sgrid = grid_for(r, total, 128, 16);
@@ -1019,6 +1044,7 @@ int enqueue_batch(ptb_renderer* r, ptb_renderer::BatchContext& ctx, cudaEvent_t 
 				r->stats.kernel_launches++;
 			}
 		}
+		else if (fused) k_shade<false, false, false, false, true><<<sgrid, 128, 0, stream>>>(PTB_SHADE_ARGS);
 		else if (alt && r->russian_roulette) k_shade<false, false, true, true><<<sgrid, 128, 0, stream>>>(PTB_SHADE_ARGS);
 		else if (alt) k_shade<false, false, false, true><<<sgrid, 128, 0, stream>>>(PTB_SHADE_ARGS);
 		else if (r->russian_roulette) k_shade<false, false, true><<<sgrid, 128, 0, stream>>>(PTB_SHADE_ARGS);
@@ -1045,7 +1071,7 @@ int enqueue_batch(ptb_renderer* r, ptb_renderer::BatchContext& ctx, cudaEvent_t 
 #endif
 	}
 	if (prev_accumulated) PTB_CUDA(cudaStreamWaitEvent(stream, prev_accumulated, 0));
-	k_accumulate<<<(px + 255) / 256, 256, 0, stream>>>(ctx.st.radiance, r->image_sum, r->last_pass, ctx.counts, r->segment_totals, n_counts, px, n_slots, r->pass_clamp >= 0.0f ? r->pass_clamp : (float)r->cfg.max_tracer_depth * 2.0f);
+	k_accumulate<<<(px + 255) / 256, 256, 0, stream>>>(ctx.st.radiance, r->image_sum, r->last_pass, ctx.counts, r->segment_totals, tally_counts, px, n_slots, r->pass_clamp >= 0.0f ? r->pass_clamp : (float)r->cfg.max_tracer_depth * 2.0f);
 	r->stats.kernel_launches++;
 	PTB_CUDA(cudaEventRecord(ctx.accumulated, stream));
 	PTB_CUDA(cudaGetLastError());
@@ -1099,6 +1125,7 @@ int render_impl(ptb_renderer* r, int first_pass, int stride, int n_passes, bool 
 			r->stats.ray_segments += (int64_t)r->counts_host[d];
 			r->depth_segments[d] = (int64_t)r->counts_host[d];
 		}
+
 		float ms = 0.0f;
 		cudaEventElapsedTime(&ms, r->ev0, r->ev1);
 		r->stats.gpu_ms_total = ms;
@@ -1882,6 +1909,8 @@ int ptb_set_option(ptb_renderer* r, const char* key, const char* value)
 	if (k == "octant_order") { r->octant_order = atoi(value); return 0; }
 	if (k == "sort_by_material") { r->sort_by_material = atoi(value); return 0; }
 	if (k == "russian_roulette") { r->russian_roulette = atoi(value) != 0; return ptb_clear(r); }
+	if (k == "inline_scatter") { r->inline_scatter = atoi(value) != 0; return 0; }
+	if (k == "tune_scatter") { r->tune_scatter = atoi(value); return 0; }
 	if (k == "sampler")
 	{
 		if (v != "reference" && v != "pcg") { set_error("[Error]sampler must be reference or pcg"); return 1; }

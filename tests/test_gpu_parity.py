@@ -239,6 +239,29 @@ def test_bvh_layouts_agree(workload_root):
     assert res[8][4]["nodes_visited"] == 0 and res[2][4]["wide_nodes_visited"] > 0      # layout 2 is hybrid: deep bounces use the wide tree
 
 
+def test_c5_layout_at_reduced_size_equals_exhaustive_scan(workload_root):
+    """BASELINE.json configs[4] (two large meshes + light, 4K) at a fiftieth of the triangles and 480x270: both trees of the hybrid return
+    the exhaustive scan's hits on camera and bounce rays, and the image does not depend on the batching."""
+    root, w = workload_root("c5", width=480, height=270, tri_scale=0.02)
+    r = gpu_renderer(w, root, passes_in_flight=2)
+    assert r.scene_counts()["meshes"] == 3 and r.scene_counts()["triangles"] > 90000
+    for opts in (dict(), dict(hybrid_from_depth=0)):          # binary tree / compressed wide tree
+        for k, v in opts.items():
+            r.set_option(k, v)
+        rays = np.concatenate([r.generate_rays(1)[::7], r.capture_rays(1, 1)[1][::5], r.capture_rays(1, 3)[1][::3]], 0)
+        prim, t = r.trace_batch(rays)
+        bp, bt = r.trace_batch(rays, bruteforce=True)
+        assert np.array_equal(prim, bp) and np.array_equal(t.view(np.uint32), bt.view(np.uint32))
+    r.set_option("hybrid_from_depth", 2)
+    r.clear()
+    r.render(4)
+    a = r.image_f32().copy()
+    r.clear()
+    for _ in range(4):
+        r.render(1)
+    assert np.array_equal(a.view(np.uint32), r.image_f32().view(np.uint32))
+
+
 def test_scheduling_options_do_not_change_the_image(workload_root):
     """Queue order (8x4 pixel tiles), the block-local material sort of k_shade and the number of overlapped
     streams only reorder independent paths: the accumulated image must be bit-identical."""
@@ -246,7 +269,7 @@ def test_scheduling_options_do_not_change_the_image(workload_root):
     ref = None
     for opts in (dict(), dict(tile_order=0), dict(sort_by_material=1), dict(sort_by_material=1, tile_order=0, streams_in_flight=1),
                  dict(extend_persistent=0), dict(bvh_max_leaf=2, bvh_intersect_cost=1.5), dict(bvh_hybrid=0), dict(hybrid_from_depth=0),
-                 dict(bvh_layout=8), dict(octant_order=1), dict(extend_variant=1), dict(extend_variant=2), dict(extend_variant=3), dict(extend_variant=3, treelet_block=512, treelet_nodes=100), dict(extend_variant=4), dict(extend_variant=4, tune_refill4=1), dict(l2_persist=1)):
+                 dict(bvh_layout=8), dict(octant_order=1), dict(extend_variant=1), dict(extend_variant=2), dict(extend_variant=3), dict(extend_variant=3, treelet_block=512, treelet_nodes=100), dict(extend_variant=4), dict(extend_variant=4, tune_refill4=1), dict(l2_persist=1), dict(inline_scatter=0), dict(inline_scatter=0, hybrid_from_depth=0), dict(tune_scatter=1), dict(tune_scatter=32, hybrid_from_depth=1)):
         r = gpu_renderer(w, root, **opts)
         r.set_camera(ptb.default_camera(w["width"], w["height"], w["aperture"], w["focal"]))
         r.render(5)
