@@ -311,13 +311,77 @@ __device__ __forceinline__ void load_node(const float4* np, float4& n0, float4& 
 #define PTB_LEAF_SINGLE 1
 #endif
 
+// FUSED (option inline_scatter, default on in parity mode): in a scattering medium most bounces are scatter events — the free flight ends
+// before any surface (k_shade: d < t_hit), the path gets an isotropic direction, its throughput is attenuated, nothing else happens
+// (path_tracer_kernel.cu:460-486).  The bounded search already knows it (no hit below the free-flight bound), so the lane performs the
+// event here with the reference's arithmetic and random stream of that depth and goes on tracing the SAME path, instead of a round trip
+// through hit record, queue, k_shade and the next launch per event.  The path runs ahead of the wavefront's loop depth by `lead`
+// bounces (kept in ray_o.w for k_shade<.., FUSED>); scatter events are executed as a voted phase like node and triangle steps.
+struct FusedArgs
+{
+	DeviceConfig cfg;
+	int loop_depth, pixel_count, first_pass, pass_stride, scatter_min;
+	// ray segments per ACTUAL depth (the call totals ptb_get_depth_profile reports): with paths ahead of the loop depth the queue sizes no longer
+	// say at which depth a search ran, so this kernel tallies its own searches (block histogram in shared memory, flushed once per block)
+	unsigned long long* depth_segments;
+	int n_depth_slots;
+};
+#define PTB_FUSED_HIST 66
+
+
+// One scatter event of the lane's path at bounce `depth` (= loop depth + lead): k_shade's medium branch (kernels_shade.cuh) with the
+// reference's arithmetic and random stream.  Returns false when the path ends (energy cut or bounce limit; its hit record then carries
+// PTB_PRIM_DEAD); otherwise o / d / bound describe the next segment, the throughput is in s_thr, and the caller restarts its search.
+__device__ __forceinline__ bool fused_scatter_event(const DeviceScene& sc, const PathState& st, const FusedArgs& fa, int id, int depth,
+	bool& thr_cached, float4* s_thr_slot, int* s_hist, float3& o, float3& d, float& bound)
+{
+	const DeviceConfig& cfg = fa.cfg;
+	const int slot = id / fa.pixel_count;
+	const int pixel_index = id - slot * fa.pixel_count;
+	const int seed = fa.first_pass + slot * fa.pass_stride;
+	const float4 t4 = thr_cached ? *s_thr_slot : (depth == 0 ? make_float4(1.0f, 1.0f, 1.0f, __int_as_float(-1)) : st.throughput[id]);
+	float3 not_absorbed = make_float3(t4.x, t4.y, t4.z);
+	const int medium_index = __float_as_int(t4.w);
+	float3 sigma_a = cfg.air_sigma_a, sigma_s = cfg.air_sigma_s;
+	if (medium_index >= 0)
+	{
+		const float4 md = __ldg(&sc.materials[medium_index].d), me = __ldg(&sc.materials[medium_index].e);
+		sigma_a = make_float3(md.x, md.y, md.z);
+		sigma_s = make_float3(md.w, me.x, me.y);
+	}
+	// streams of this bounce and the next: (hash(seed) * hash(pixel)) * hash(depth) — the product the reference seeds with, the
+	// first two factors shared (integer multiplication is associative mod 2^32)
+	const int hsp = hash_ref(seed) * hash_ref(pixel_index);
+	Rng rng;
+	rng.seed((uint32_t)(hsp * hash_ref(depth)), 0.0f, 1.0f);
+	const float rand = rng.next();
+	const float scattering_distance = -__logf(rand) / sigma_s.x;
+	const float rand1 = rng.next();
+	const float rand2 = rng.next();
+	const float3 next_o = o + d * scattering_distance;
+	const float3 next_d = sample_on_sphere(rand1, rand2);
+	not_absorbed = not_absorbed * absorption_through_medium(sigma_a, scattering_distance);
+	if (length(not_absorbed) <= cfg.energy_threshold || depth + 1 >= cfg.max_depth)
+	{
+		// the path ends here: energy cut (:480-483) or the bounce limit of the reference's depth loop
+		__stcs(&st.hit[id], make_float4(CUDART_INF_F, 0.0f, 0.0f, __int_as_float(PTB_PRIM_DEAD)));
+		return false;
+	}
+	*s_thr_slot = make_float4(not_absorbed.x, not_absorbed.y, not_absorbed.z, t4.w);
+	thr_cached = true;
+	atomicAdd(&s_hist[min(depth + 1, PTB_FUSED_HIST - 1)], 1);     // the search of the next bounce starts here
+	o = next_o; d = next_d;
+	bound = next_bounce_bound_hashed(cfg, sigma_a, sigma_s, hsp, depth + 1);
+	return true;
+}
+
 // TREELET (k_extend_treelet below): the first `n_top` nodes of the array — the top levels of the tree, which the device builder
 // numbers level by level — are copied into shared memory by the block and fetched from there: every ray walks through them, and a
 // scattered 64-byte gather costs the L1 data stage ~1.45 cycles per lane (tools/roofs: 12.8 TB/s) where shared memory delivers it at
 // bank rate.  Blocks are then as large as the launch allows (one 1024-thread block per SM shares one copy).
-template <bool COUNT, int REPS, bool TREELET, bool STAGED>
+template <bool COUNT, int REPS, bool TREELET, bool STAGED, bool FUSED = false>
 __device__ __forceinline__ void extend_persistent_body(const DeviceScene& sc, const PathState& st, const int* __restrict__ queue, const int* __restrict__ count_ptr,
-	int* __restrict__ work_counter, unsigned long long* __restrict__ counters, int refill_min, int leaf_min, int node_reps, const float4* s_top, int n_top, float4* s_stage)
+	int* __restrict__ work_counter, unsigned long long* __restrict__ counters, int refill_min, int leaf_min, int node_reps, const float4* s_top, int n_top, float4* s_stage, const FusedArgs* fa = nullptr, float4* s_thr = nullptr, int* s_hist = nullptr)
 {
 	const int count = *count_ptr;
 	const unsigned lane = threadIdx.x & 31u;
@@ -342,14 +406,24 @@ __device__ __forceinline__ void extend_persistent_body(const DeviceScene& sc, co
 #define PTB_POP(dst) do { --sp; dst = stack[min(sp, PTB_STACK_SIZE - 1)]; } while (0)
 	int sp = 0;
 	int node = PTB_DONE;         // >= 0 inner node, PTB_DONE = nothing left, other negative = leaf reference
+	// FUSED (see FusedArgs above): scatter events of the medium performed here, the path runs `lead` bounces ahead of the loop depth
+	int lead = 0;
+	bool at_scatter = false, thr_cached = false;
 
 	// Every iteration starts with full-mask votes, so all 32 lanes are converged when a phase
 	// begins; a phase is executed by the lanes in that state, the others are predicated off.
 	while (true)
 	{
 		// retire finished rays (no vote needed: a plain predicated store)
-		if (id >= 0 && node == PTB_DONE)
+		if (FUSED && id >= 0 && node == PTB_DONE && !at_scatter && best.prim == -1 && best.t < CUDART_INF_F) at_scatter = true;
+		if (id >= 0 && node == PTB_DONE && !at_scatter)
 		{
+			if (FUSED && thr_cached)
+			{
+				st.ray_o[id] = make_float4(o.x, o.y, o.z, __int_as_float(lead));
+				st.ray_d[id] = make_float4(d.x, d.y, d.z, 0.0f);
+				st.throughput[id] = s_thr[threadIdx.x];
+			}
 #ifndef PTB_NO_STREAMING_HINTS
 			__stcs(&st.hit[id], make_float4(best.prim == -1 ? CUDART_INF_F : best.t, best.t1, best.t2, __int_as_float(best.prim)));
 #else
@@ -366,8 +440,9 @@ __device__ __forceinline__ void extend_persistent_body(const DeviceScene& sc, co
 		}
 		const bool has_ray = id >= 0;
 		const unsigned m_idle = __ballot_sync(FULL, !has_ray);
-		const unsigned m_node = __ballot_sync(FULL, has_ray && node >= 0);
-		const unsigned m_leaf = __ballot_sync(FULL, has_ray && node < 0);
+		const unsigned m_scat = FUSED ? __ballot_sync(FULL, has_ray && at_scatter) : 0u;
+		const unsigned m_node = __ballot_sync(FULL, has_ray && node >= 0) | m_scat;   // "work in flight" for the refill / exit tests
+		const unsigned m_leaf = __ballot_sync(FULL, has_ray && node < 0 && !at_scatter);
 
 		if (STAGED)
 		{
@@ -452,6 +527,7 @@ __device__ __forceinline__ void extend_persistent_body(const DeviceScene& sc, co
 					d = make_float3(d4.x, d4.y, d4.z);
 					best.t = d4.w; best.t1 = CUDART_INF_F; best.t2 = CUDART_INF_F; best.prim = -1;   // d4.w: free-flight bound (next_bounce_bound)
 					best_tri = 0x7fffffff;
+					if (FUSED) { lead = __float_as_int(o4.w); at_scatter = false; thr_cached = false; atomicAdd(&s_hist[min(fa->loop_depth + lead, PTB_FUSED_HIST - 1)], 1); }
 					for (int s = 0; s < sc.n_spheres; s++)
 					{
 						const float4 sph = __ldg(&sc.spheres[s]);
@@ -478,10 +554,45 @@ __device__ __forceinline__ void extend_persistent_body(const DeviceScene& sc, co
 		}
 		if ((m_node | m_leaf) == 0u) break;   // nothing in flight and nothing left to fetch
 
-		if (m_leaf != 0u && (__popc(m_leaf) >= leaf_min || m_node == 0u))
+		if (FUSED && m_scat != 0u && (__popc(m_scat) >= fa->scatter_min || ((m_node & ~m_scat) | m_leaf) == 0u))
+		{
+			// ---- scatter phase (fused_scatter_event): the lanes whose search ended below the free-flight bound without a hit
+			if (has_ray && at_scatter)
+			{
+				at_scatter = false;
+				if (!fused_scatter_event(sc, st, *fa, id, fa->loop_depth + lead, thr_cached, &s_thr[threadIdx.x], s_hist, o, d, best.t)) id = -1;
+				else
+				{
+					lead++;
+					best.t1 = CUDART_INF_F; best.t2 = CUDART_INF_F; best.prim = -1;
+					best_tri = 0x7fffffff;
+					for (int s = 0; s < sc.n_spheres; s++)
+					{
+						const float4 sph = __ldg(&sc.spheres[s]);
+						float t;
+						if (intersect_sphere(make_float3(sph.x, sph.y, sph.z), sph.w, o, d, t) && t < best.t && t > 0.0f)
+						{
+							best.t = t;
+							best.prim = -(s + 2);
+						}
+					}
+					const float tiny = 1e-30f;
+					const float3 ds = make_float3(fabsf(d.x) < tiny ? copysignf(tiny, d.x) : d.x, fabsf(d.y) < tiny ? copysignf(tiny, d.y) : d.y,
+						fabsf(d.z) < tiny ? copysignf(tiny, d.z) : d.z);
+					idir = make_float3(1.0f / ds.x, 1.0f / ds.y, 1.0f / ds.z);
+					noidir = make_float3(-o.x * idir.x, -o.y * idir.y, -o.z * idir.z);
+					margin2 = 4.8e-7f * fmaxf(fmaxf(fabsf(noidir.x), fabsf(noidir.y)), fabsf(noidir.z));
+					sp = 0;
+					node = sc.n_triangles > 0 ? sc.root_ref : PTB_DONE;
+				}
+			}
+			continue;
+		}
+
+		if (m_leaf != 0u && (__popc(m_leaf) >= leaf_min || (m_node & ~m_scat) == 0u))
 		{
 			// ---- leaf phase: node = ~((first << 3) | (count - 1))
-			if (has_ray && node < 0)
+			if (has_ray && node < 0 && !(FUSED && at_scatter))   // a lane waiting for its scatter event sits at PTB_DONE, which is negative too
 			{
 				const int ref = ~node;
 				const int first = ref >> 3;
@@ -581,6 +692,21 @@ __global__ void __launch_bounds__(128, PTB_PERSISTENT_MIN_BLOCKS) k_extend_persi
 	int* __restrict__ work_counter, unsigned long long* __restrict__ counters, int refill_min, int leaf_min, int node_reps)
 {
 	extend_persistent_body<COUNT, REPS, false, false>(sc, st, queue, count_ptr, work_counter, counters, refill_min, leaf_min, node_reps, nullptr, 0, nullptr);
+}
+
+// the binary-tree kernel with inline scatter events (option inline_scatter with fused_tree=2: the whole subsurface walk over the binary tree)
+template <bool COUNT>
+__global__ void __launch_bounds__(128, PTB_PERSISTENT_MIN_BLOCKS) k_extend_persistent_fused(DeviceScene sc, PathState st, const int* __restrict__ queue, const int* __restrict__ count_ptr,
+	int* __restrict__ work_counter, unsigned long long* __restrict__ counters, int refill_min, int leaf_min, FusedArgs fa)
+{
+	__shared__ int s_hist[PTB_FUSED_HIST];
+	__shared__ float4 s_thr[128];
+	if (threadIdx.x < PTB_FUSED_HIST) s_hist[threadIdx.x] = 0;
+	__syncthreads();
+	extend_persistent_body<COUNT, 6, false, false, true>(sc, st, queue, count_ptr, work_counter, counters, refill_min, leaf_min, 6, nullptr, 0, nullptr, &fa, s_thr, s_hist);
+	__syncthreads();
+	if (threadIdx.x < PTB_FUSED_HIST && s_hist[threadIdx.x])
+		atomicAdd(&fa.depth_segments[min((int)threadIdx.x, fa.n_depth_slots - 1)], (unsigned long long)s_hist[threadIdx.x]);
 }
 
 // STAGED refill (extend_variant 4): 96 float4 (1.5 KB) of shared memory per warp hold 32 set-up rays
@@ -780,23 +906,6 @@ __global__ void __launch_bounds__(128, PTB_PERSISTENT_MIN_BLOCKS) k_extend_specu
 // (child base + hit bits), `tri_group` = leaf triangles still to test; stack entries are node groups.
 // Phases: refill | wide-node step (one child popped, 8 quantised boxes decoded and tested) | triangle step.
 // ------------------------------------------------------------------------------------------
-// FUSED (option inline_scatter, default on in parity mode): in a scattering medium most bounces are scatter events — the free flight ends
-// before any surface (k_shade: d < t_hit), the path gets an isotropic direction, its throughput is attenuated, nothing else happens
-// (path_tracer_kernel.cu:460-486).  The bounded search already knows it (no hit below the free-flight bound), so the lane performs the
-// event here with the reference's arithmetic and random stream of that depth and goes on tracing the SAME path, instead of a round trip
-// through hit record, queue, k_shade and the next launch per event.  The path runs ahead of the wavefront's loop depth by `lead`
-// bounces (kept in ray_o.w for k_shade<.., FUSED>); scatter events are executed as a voted phase like node and triangle steps.
-struct FusedArgs
-{
-	DeviceConfig cfg;
-	int loop_depth, pixel_count, first_pass, pass_stride, scatter_min;
-	// ray segments per ACTUAL depth (the call totals ptb_get_depth_profile reports): with paths ahead of the loop depth the queue sizes no longer
-	// say at which depth a search ran, so this kernel tallies its own searches (block histogram in shared memory, flushed once per block)
-	unsigned long long* depth_segments;
-	int n_depth_slots;
-};
-#define PTB_FUSED_HIST 66
-
 template <bool COUNT, bool FUSED = false>
 __global__ void __launch_bounds__(128, PTB_PERSISTENT_MIN_BLOCKS8) k_extend_persistent8(DeviceScene sc, PathState st, const int* __restrict__ queue, const int* __restrict__ count_ptr,
 	int* __restrict__ work_counter, unsigned long long* __restrict__ counters, int refill_min, int leaf_min, FusedArgs fa = FusedArgs())
@@ -822,6 +931,10 @@ __global__ void __launch_bounds__(128, PTB_PERSISTENT_MIN_BLOCKS8) k_extend_pers
 	int lead = 0;                // FUSED: bounces this path is ahead of the loop depth
 	bool at_scatter = false;     // FUSED: the search ended below the free-flight bound without a hit: a scatter event is due
 	__shared__ int s_hist[FUSED ? PTB_FUSED_HIST : 1];
+	// FUSED: throughput + medium index of the lane's path while it scatters (loaded at its first event here, written back when the path
+	// leaves the kernel alive): every later event costs shared-memory latency instead of a scattered 16-byte global load and store
+	__shared__ float4 s_thr[FUSED ? 128 : 1];
+	bool thr_cached = false;
 	if (FUSED)
 	{
 		if (threadIdx.x < PTB_FUSED_HIST) s_hist[threadIdx.x] = 0;
@@ -838,11 +951,13 @@ __global__ void __launch_bounds__(128, PTB_PERSISTENT_MIN_BLOCKS8) k_extend_pers
 			else
 			{
 				__stcs(&st.hit[id], make_float4(best.prim == -1 ? CUDART_INF_F : best.t, best.t1, best.t2, __int_as_float(best.prim)));
-				if (FUSED && lead > 0)
+				if (FUSED && thr_cached)
 				{
-					// the ray in memory is the one the path had when it entered: k_shade needs the segment that found the surface
+					// the path scattered here: the ray in memory is the one it had when it entered (k_shade needs the segment that found the
+					// surface) and its throughput lives in shared memory
 					st.ray_o[id] = make_float4(o.x, o.y, o.z, __int_as_float(lead));
 					st.ray_d[id] = make_float4(d.x, d.y, d.z, 0.0f);
+					st.throughput[id] = s_thr[threadIdx.x];
 				}
 				id = -1;
 			}
@@ -873,7 +988,7 @@ __global__ void __launch_bounds__(128, PTB_PERSISTENT_MIN_BLOCKS8) k_extend_pers
 					d = make_float3(d4.x, d4.y, d4.z);
 					best.t = d4.w; best.t1 = CUDART_INF_F; best.t2 = CUDART_INF_F; best.prim = -1;
 					best_tri = 0x7fffffff;
-					if (FUSED) { lead = __float_as_int(o4.w); at_scatter = false; atomicAdd(&s_hist[min(fa.loop_depth + lead, PTB_FUSED_HIST - 1)], 1); }
+					if (FUSED) { lead = __float_as_int(o4.w); at_scatter = false; thr_cached = false; atomicAdd(&s_hist[min(fa.loop_depth + lead, PTB_FUSED_HIST - 1)], 1); }
 					for (int s = 0; s < sc.n_spheres; s++)
 					{
 						const float4 sph = __ldg(&sc.spheres[s]);
@@ -903,44 +1018,11 @@ __global__ void __launch_bounds__(128, PTB_PERSISTENT_MIN_BLOCKS8) k_extend_pers
 			// ---- scatter phase: the medium event of k_shade (kernels_shade.cuh) for the lanes whose search ended below the free-flight bound
 			if (has_ray && at_scatter)
 			{
-				const DeviceConfig& cfg = fa.cfg;
-				const int slot = id / fa.pixel_count;
-				const int pixel_index = id - slot * fa.pixel_count;
-				const int seed = fa.first_pass + slot * fa.pass_stride;
-				const int depth = fa.loop_depth + lead;
-				const float4 t4 = depth == 0 ? make_float4(1.0f, 1.0f, 1.0f, __int_as_float(-1)) : st.throughput[id];
-				float3 not_absorbed = make_float3(t4.x, t4.y, t4.z);
-				const int medium_index = __float_as_int(t4.w);
-				float3 sigma_a = cfg.air_sigma_a, sigma_s = cfg.air_sigma_s;
-				if (medium_index >= 0)
-				{
-					const float4 md = __ldg(&sc.materials[medium_index].d), me = __ldg(&sc.materials[medium_index].e);
-					sigma_a = make_float3(md.x, md.y, md.z);
-					sigma_s = make_float3(md.w, me.x, me.y);
-				}
-				Rng rng;
-				rng.seed3(0, seed, pixel_index, depth, 0u, 0.0f, 1.0f);
-				const float rand = rng.next();
-				const float scattering_distance = -__logf(rand) / sigma_s.x;
-				const float rand1 = rng.next();
-				const float rand2 = rng.next();
-				const float3 next_o = o + d * scattering_distance;
-				const float3 next_d = sample_on_sphere(rand1, rand2);
-				not_absorbed = not_absorbed * absorption_through_medium(sigma_a, scattering_distance);
 				at_scatter = false;
-				if (length(not_absorbed) <= cfg.energy_threshold || depth + 1 >= cfg.max_depth)
-				{
-					// the path ends here: energy cut (:480-483) or the bounce limit of the reference's depth loop
-					__stcs(&st.hit[id], make_float4(CUDART_INF_F, 0.0f, 0.0f, __int_as_float(PTB_PRIM_DEAD)));
-					id = -1;
-				}
+				if (!fused_scatter_event(sc, st, fa, id, fa.loop_depth + lead, thr_cached, &s_thr[threadIdx.x], s_hist, o, d, best.t)) id = -1;
 				else
 				{
-					st.throughput[id] = make_float4(not_absorbed.x, not_absorbed.y, not_absorbed.z, t4.w);
 					lead++;
-					atomicAdd(&s_hist[min(depth + 1, PTB_FUSED_HIST - 1)], 1);     // the search of the next bounce starts here
-					o = next_o; d = next_d;
-					best.t = next_bounce_bound(cfg, sigma_a, sigma_s, seed, pixel_index, depth + 1);
 					best.t1 = CUDART_INF_F; best.t2 = CUDART_INF_F; best.prim = -1;
 					best_tri = 0x7fffffff;
 					for (int sidx = 0; sidx < sc.n_spheres; sidx++)

@@ -48,6 +48,20 @@ __device__ __forceinline__ float next_bounce_bound(const DeviceConfig& cfg, floa
 	return __uint_as_float(__float_as_uint(scattering_distance) + 1u);
 }
 
+// the same bound for the reference's sampler with hash(seed) * hash(pixel) already multiplied (k_extend_persistent8<.., FUSED> computes
+// it once per scatter event for this bounce's stream and the next one's)
+__device__ __forceinline__ float next_bounce_bound_hashed(const DeviceConfig& cfg, float3 sigma_a, float3 sigma_s, int hash_seed_pixel, int depth)
+{
+	if (!(sigma_s.x > 0.0f || length(sigma_a) > cfg.sss_threshold)) return CUDART_INF_F;
+	Rng rng;
+	rng.seed((uint32_t)(hash_seed_pixel * hash_ref(depth)), 0.0f, 1.0f);
+	const float scattering_distance = -__logf(rng.next()) / sigma_s.x;
+	if (!(scattering_distance == scattering_distance)) return CUDART_INF_F;
+	if (scattering_distance < 0.0f || scattering_distance == 0.0f) return 1e-37f;
+	if (scattering_distance >= 3.0e38f) return CUDART_INF_F;
+	return __uint_as_float(__float_as_uint(scattering_distance) + 1u);
+}
+
 // ------------------------------------------------------------------------------------------
 // k_generate — init_data_kernel + generate_ray_kernel fused (path_tracer_kernel.cu:275-379)
 // ------------------------------------------------------------------------------------------

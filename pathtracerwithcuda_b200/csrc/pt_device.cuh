@@ -78,9 +78,17 @@ struct Rng
 	uint32_t x;
 	float lo, span;
 	bool pcg;
+	// x mod (2^31 - 1) without a division: 2^31 = 1 (mod m), so fold the high bits onto the low 31 and subtract m at most once —
+	// exactly thrust::minstd_rand's arithmetic (linear_congruential_engine.h), a third of the instructions of the 64-bit '%'
+	__device__ __forceinline__ static uint32_t mod_m31(uint64_t v)
+	{
+		uint32_t t = (uint32_t)(v & 0x7fffffffull) + (uint32_t)(v >> 31);   // v < 2^47: the sum stays below 2^32
+		t = (t & 0x7fffffffu) + (t >> 31);                                    // fold once more: now t <= 2^31 - 1 + 1
+		return t >= 2147483647u ? t - 2147483647u : t;
+	}
 	__device__ __forceinline__ void seed(uint32_t s, float a, float b)
 	{
-		x = s % 2147483647u;
+		x = mod_m31((uint64_t)s);
 		if (x == 0u) x = 1u;
 		lo = a; span = b - a;
 		pcg = false;
@@ -100,7 +108,7 @@ struct Rng
 			x = x * 747796405u + 2891336453u;
 			return (float)(pcg_permute(x) >> 8) * (1.0f / 16777216.0f) * span + lo;
 		}
-		x = (uint32_t)(((uint64_t)x * 48271ull) % 2147483647ull);
+		x = mod_m31((uint64_t)x * 48271ull);
 		float r = (float)(x - 1u);
 		r /= 2147483648.0f;
 		return (r * span) + lo;

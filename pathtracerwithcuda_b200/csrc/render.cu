@@ -100,6 +100,7 @@ struct ptb_renderer
 	int octant_order = 0;                  // next-depth queue grouped by ray-direction octant per block (measured: profiles/r01_experiments.md)
 	int tile_order = 1;                    // camera rays enter the first queue in 8x4 pixel tiles
 	int inline_scatter = 1;                // medium scatter events performed inside the wide-tree closest-hit kernel (bit-identical images; off: one wavefront round trip per event)
+	int fused_from_depth = -1;             // first loop depth with inline scatter events (-1: where the wide tree takes over)
 	int tune_scatter = 8;                  // ... as a voted phase once >= N lanes wait for one
 	bool scene_has_medium = false;         // some material (or the air) scatters: sigma_s'.x > 0
 	int sampler = 0;                       // estimator option: 0 = the reference's hash-product + minstd streams, 1 = pcg (pt_device.cuh)
@@ -937,6 +938,13 @@ void launch_extend(ptb_renderer* r, cudaStream_t stream, size_t items, const Pat
 	{
 		// persistent warps: one resident wave, sized from the occupancy the kernel actually gets
 		int grid = std::max(1, std::min(r->persistent_grid, (int)((items + 127) / 128)));
+		if (fused)
+		{
+			// inline scatter events over the binary tree (fused_from_depth <= depth < hybrid_from_depth)
+			if (r->count_traversal) k_extend_persistent_fused<true><<<grid, 128, 0, stream>>>(r->dscene, st, queue, count_ptr, work_counter, r->counters, r->tune_refill, r->tune_leaf, *fused);
+			else k_extend_persistent_fused<false><<<grid, 128, 0, stream>>>(r->dscene, st, queue, count_ptr, work_counter, r->counters, r->tune_refill, r->tune_leaf, *fused);
+			return;
+		}
 		if (r->extend_variant == 4)
 		{
 			// staged refill (kernels_extend.cuh: k_extend_staged): rays set up 32 at a time into shared memory, idle lanes pop ready rays
@@ -1004,13 +1012,15 @@ int enqueue_batch(ptb_renderer* r, ptb_renderer::BatchContext& ctx, cudaEvent_t 
 	const int tiles_x = (r->tile_order && r->cfg.width % 8 == 0 && r->cfg.height % 4 == 0) ? r->cfg.width / 8 : 0;
 	const bool alt = r->sampler != 0 || r->sss_mode != 0;   // estimator options: the ALT instantiations of k_generate / k_shade
 	// inline scatter events (kernels_extend.cuh: k_extend_persistent8<.., FUSED>): the reference's estimator only, and only where a medium exists
-	const bool fused = r->inline_scatter && (r->scene_has_medium || r->cfg.air_reduced_scattering_coef.x > 0.0f) && !alt && !r->nee && !r->russian_roulette && !r->sort_by_material && r->extend_persistent &&
-		(r->dscene.bvh_layout == 8 || (r->dscene.bvh_layout == 2 && r->dscene.bvh8_nodes));
+	const bool fused = r->inline_scatter && (r->scene_has_medium || r->cfg.air_reduced_scattering_coef.x > 0.0f) && !alt && !r->nee && !r->russian_roulette && !r->sort_by_material && r->extend_persistent && r->extend_variant == 0;
 	FusedArgs fa;
 	fa.cfg = dc; fa.pixel_count = px; fa.first_pass = first_pass; fa.pass_stride = stride; fa.scatter_min = r->tune_scatter;
 	fa.depth_segments = r->segment_totals; fa.n_depth_slots = n_counts;
 	// loop depths traced by the fused kernel tally their own searches per actual depth; the queue sizes only count below that
-	const int tally_counts = fused ? (r->dscene.bvh_layout == 8 ? 0 : std::min(std::max(r->hybrid_from_depth, 0), n_counts)) : n_counts;
+	// first loop depth whose closest-hit launch scatters inline: fused_from_depth (default: where the wide tree takes over; lower values run
+	// the walk on the binary-tree kernel until then)
+	const int fused_from = r->fused_from_depth >= 0 ? r->fused_from_depth : (r->dscene.bvh_layout == 8 ? 0 : std::max(r->hybrid_from_depth, 0));
+	const int tally_counts = fused ? std::min(fused_from, n_counts) : n_counts;
 	if (alt) k_generate<true><<<grid_for(r, total, 256, 8), 256, 0, stream>>>(ctx.st, ctx.queue[0], ctx.counts, n_counts, cp, dc, px, n_slots, first_pass, stride, tiles_x);
 	else k_generate<false><<<grid_for(r, total, 256, 8), 256, 0, stream>>>(ctx.st, ctx.queue[0], ctx.counts, n_counts, cp, dc, px, n_slots, first_pass, stride, tiles_x);
 	r->stats.kernel_launches++;
@@ -1026,7 +1036,7 @@ int enqueue_batch(ptb_renderer* r, ptb_renderer::BatchContext& ctx, cudaEvent_t 
 			cudaEventRecord(e0, stream);
 		}
 		fa.loop_depth = depth;
-		launch_extend(r, stream, total, ctx.st, qin, ctx.counts + depth, ctx.counts + n_counts + depth, depth, fused ? &fa : nullptr);
+		launch_extend(r, stream, total, ctx.st, qin, ctx.counts + depth, ctx.counts + n_counts + depth, depth, (fused && depth >= fused_from) ? &fa : nullptr);
 		if (prof) cudaEventRecord(e1, stream);
 		int* shadow_count = ctx.counts + 2 * n_counts + depth;
 		const int sgrid = grid_for(r, total, 128, 16);
@@ -1910,6 +1920,7 @@ int ptb_set_option(ptb_renderer* r, const char* key, const char* value)
 	if (k == "sort_by_material") { r->sort_by_material = atoi(value); return 0; }
 	if (k == "russian_roulette") { r->russian_roulette = atoi(value) != 0; return ptb_clear(r); }
 	if (k == "inline_scatter") { r->inline_scatter = atoi(value) != 0; return 0; }
+	if (k == "fused_from_depth") { r->fused_from_depth = atoi(value); return 0; }
 	if (k == "tune_scatter") { r->tune_scatter = atoi(value); return 0; }
 	if (k == "sampler")
 	{

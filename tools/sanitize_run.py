@@ -11,7 +11,9 @@ import make_golden as mg
 root = tempfile.mkdtemp(prefix="ptb_san_")
 for name, kw in (("mix", dict(width=96, height=72)), ("c2", dict(width=64, height=36, tri_scale=0.2))):
     w = pr.make_workload(root, name, **kw)
-    for opts in (dict(), dict(bvh_layout=8), dict(estimator="nee"), dict(sort_by_material=1, octant_order=1, extend_persistent=0)):
+    for opts in (dict(), dict(bvh_layout=8), dict(estimator="nee"), dict(sort_by_material=1, octant_order=1, extend_persistent=0),
+                 dict(fused_from_depth=0), dict(fused_from_depth=1, hybrid_from_depth=99), dict(inline_scatter=0), dict(sampler="pcg", sss="per_channel"),
+                 dict(texture_filter="hardware"), dict(extend_variant=1), dict(extend_variant=3), dict(extend_variant=4)):
         r = ptb.Renderer(w["config"], device=0)
         for k, v in opts.items():
             r.set_option(k, v)
