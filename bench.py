@@ -33,6 +33,9 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# the C oracle (cpu_baseline) runs under OpenMP: idle workers that keep SPINNING after it returned took the host threads of the scene
+# loader's staged copies from 0.12 s to 2.2 s on the box — let them sleep (must be set before libgomp is loaded)
+os.environ.setdefault("OMP_WAIT_POLICY", "passive")
 
 PASSES_PER_STEP = 64
 PASSES_IN_FLIGHT = 16     # passes traced as one wavefront batch (tools/sweep_batching.py: 16 x 4 streams +1.4 % over 8 x 4 at 11.7 GB of path state)
@@ -44,13 +47,13 @@ METRIC = "path samples/sec (Mspp*px/s), 1080p"
 NCU_CAPTURE = {
     "source": "profiles/r02_extend_ncu_summary.md",
     "workload": "c2", "passes_in_flight": 16,
-    "dram_bytes_per_launch": 379.2e6,         # dram__bytes_read.sum + dram__bytes_write.sum
-    "l2_bytes_per_launch": 2345.4e6,          # lts__t_bytes.sum
-    "l1_writeback_bytes_per_launch": 22042.7e6,   # l1tex__lsu_writeback_active_mem_lgds.sum (cycles) x 128 B: what the load instructions cost the L1 data pipe
-    "l1_tag_bytes_per_launch": 4379.9e6,      # l1tex__t_bytes.sum (distinct sectors x 32 B through the tag stage)
-    "limiters": {"time_weighted_d0_d7": {"sm__throughput_pct": 56.6, "issue_active_pct": 65.4, "l1_data_pipe_wavefronts_pct": 62.3, "l1_writeback_active_pct": 50.4,
-                                          "active_lanes_per_instruction": 20.2, "l1_hit_pct": 67.5, "l2_hit_pct": 65.2},
-                 "d0_d1": {"sm__throughput_pct": [68.0, 50.5], "issue_active_pct": [69.8, 64.4], "l1_data_pipe_wavefronts_pct": [74.5, 64.9],
+    "dram_bytes_per_launch": 379.1e6,         # dram__bytes_read.sum + dram__bytes_write.sum
+    "l2_bytes_per_launch": 2335.5e6,          # lts__t_bytes.sum
+    "l1_writeback_bytes_per_launch": 22039.5e6,   # l1tex__lsu_writeback_active_mem_lgds.sum (cycles) x 128 B: what the load instructions cost the L1 data pipe
+    "l1_tag_bytes_per_launch": 4379.7e6,      # l1tex__t_bytes.sum (distinct sectors x 32 B through the tag stage)
+    "limiters": {"time_weighted_d0_d7": {"sm__throughput_pct": 56.8, "issue_active_pct": 65.4, "l1_data_pipe_wavefronts_pct": 62.8, "l1_writeback_active_pct": 50.8,
+                                          "active_lanes_per_instruction": 20.3, "l1_hit_pct": 67.5, "l2_hit_pct": 65.4},
+                 "d0_d1": {"sm__throughput_pct": [67.9, 51.3], "issue_active_pct": [69.8, 64.4], "l1_data_pipe_wavefronts_pct": [74.5, 64.9],
                            "active_lanes_per_instruction": [22.6, 19.6], "stall_long_scoreboard_per_issue": [4.2, 5.94], "alu_pipe_pct": [63.8, 56.8]}},
 }
 UNIT = "Msamples/s"
@@ -86,12 +89,19 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append([c.strip() for c in line.split(",")])
 
-    def stop(self):
+    def mark(self):
+        """index of the next sample: brackets the timed region (the sampler is started well before it, nvidia-smi needs a moment)"""
+        return len(self.rows)
+
+    def stop(self, first=0, last=None):
         if self.proc:
             time.sleep(0.15)
             self.proc.terminate()
+        rows = self.rows[first:last] if last is not None else self.rows[first:]
+        if not rows:                      # a timed region shorter than the sampling period: the samples around it
+            rows = self.rows[max(0, first - 2):(last + 2) if last is not None else None]
         sm, mx, reasons = [], [], set()
-        for r in self.rows:
+        for r in rows:
             try:
                 sm.append(float(r[0])); mx.append(float(r[1]))
                 for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], r[3:7]):
@@ -346,7 +356,9 @@ def run_ptb200(args, w, root, rank, local_rank, world):
         roofs = roofs_mod.measure(local_rank, tree_bytes=tree_bytes)
     barrier()
 
-    # ---- warm-up
+    # ---- warm-up (the clock sampler starts here so that it is delivering samples when the timed region begins)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     sr.begin()
     for _ in range(args.warmup):
         sr.render_local(PASSES_PER_STEP)
@@ -354,9 +366,8 @@ def run_ptb200(args, w, root, rank, local_rank, world):
     sr.begin()
 
     # ---- timed region: K steps, device-timed on the render stream (4 batches overlap on 4 streams)
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     barrier()
+    clock_first = sampler.mark()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
     segments = launches = 0
@@ -369,7 +380,7 @@ def run_ptb200(args, w, root, rank, local_rank, world):
     total_passes = PASSES_PER_STEP * args.steps * world
     e1.record(stream)
     barrier()
-    clocks = sampler.stop()
+    clocks = sampler.stop(clock_first, sampler.mark() + 1)
     ms = e0.elapsed_time(e1)
     t = torch.tensor([ms], dtype=torch.float64, device="cuda")
     seg_t = torch.tensor([float(segments), float(launches), extend_ms], dtype=torch.float64, device="cuda")
