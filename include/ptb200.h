@@ -267,6 +267,8 @@ int ptb_merged_image_f32(ptb_renderer* r, float* out_rgb_sum, int* out_passes);
 int ptb_merged_image_u8(ptb_renderer* r, uint8_t* out_rgb);
 /* test hook: the loaded scene through the broadcast format and back on this device; 0 = byte-identical */
 int ptb_test_scene_blob_roundtrip(ptb_renderer* r);
+/* test hook (host only): first pass index and pass count of rank `rank` of `world` for the next `total` passes after `global_done` */
+int ptb_test_shard(int global_done, int total, int rank, int world, int* out_first, int* out_count);
 
 /* ---- output side -----------------------------------------------------------------------------
  * ptb_save_png        = screenshot() of Main/window.cpp:712-740 (lodepng::encode of the displayed RGBA8 image),

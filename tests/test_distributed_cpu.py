@@ -21,6 +21,25 @@ def test_shard_passes_partition():
             assert sorted(seen) == list(range(1, total + 1)), (total, world)
 
 
+def test_c_abi_shards_partition_the_passes():
+    """csrc/multi.inc: the shard arithmetic behind ptb_multi_render / ptb_dist_render (host-only hook), incl. progressive calls."""
+    import ctypes
+    import pathtracerwithcuda_b200 as ptb
+    L = ptb.load_library()
+    L.ptb_test_shard.argtypes = [ctypes.c_int] * 4 + [ctypes.POINTER(ctypes.c_int)] * 2
+    for world in (1, 2, 3, 8):
+        done, seen = 0, []
+        for total in (0, 1, 5, 8, 64, 7):
+            for r in range(world):
+                first, count = ctypes.c_int(), ctypes.c_int()
+                assert L.ptb_test_shard(done, total, r, world, ctypes.byref(first), ctypes.byref(count)) == 0
+                seen += [first.value + k * world for k in range(count.value)]
+                assert (first.value, world, count.value) == tuple(x + (done if i == 0 else 0) for i, x in enumerate(shard_passes(total, r, world)))
+            done += total
+        assert sorted(seen) == list(range(1, done + 1)), world      # every pass exactly once, seeds as on one GPU
+    assert L.ptb_test_shard(0, 4, 2, 2, ctypes.byref(ctypes.c_int()), ctypes.byref(ctypes.c_int())) == 1
+
+
 class OracleBackend:
     def __init__(self, scene):
         import torch
