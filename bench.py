@@ -70,36 +70,77 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    """SM clock / throttle reasons sampled DURING the timed region: NVML in this process every 10 ms (a 0.3 s timed region still gets ~30
+    samples); `nvidia-smi -lms 100` in a child process only when NVML cannot be loaded."""
     Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self.nvml, self.running, self.source = index, [], None, None, False, None
+
+    def _nvml_handle(self):
+        import pynvml as nv
+        nv.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+        ids = [v.strip() for v in vis.split(",") if v.strip()]
+        if self.index < len(ids):
+            v = ids[self.index]
+            h = nv.nvmlDeviceGetHandleByIndex(int(v)) if v.isdigit() else nv.nvmlDeviceGetHandleByUUID(v.encode() if hasattr(v, "encode") else v)
+        else:
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+        return nv, h
 
     def start(self):
         try:
+            nv, h = self._nvml_handle()
+            nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+            self.nvml, self.running, self.source = (nv, h), True, "nvml"
+            threading.Thread(target=self._poll, daemon=True).start()
+            return
+        except Exception:
+            self.nvml = None
+        try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.source = "nvidia-smi"
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
             self.proc = None
+
+    def _poll(self):
+        nv, h = self.nvml
+        mx = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+        get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        bits = [("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4)]
+        while self.running:
+            try:
+                sm = float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                rs = int(get_reasons(h))
+                self.rows.append([str(sm), str(mx), ""] + ["Active" if rs & b else "Not Active" for _, b in bits])
+            except Exception:
+                pass
+            time.sleep(0.01)
 
     def _read(self):
         for line in self.proc.stdout:
             self.rows.append([c.strip() for c in line.split(",")])
 
     def mark(self):
-        """index of the next sample: brackets the timed region (the sampler is started well before it, nvidia-smi needs a moment)"""
+        """index of the next sample: brackets the timed region (the sampler is started well before it)"""
         return len(self.rows)
 
     def stop(self, first=0, last=None):
+        if self.nvml:
+            time.sleep(0.02)
+            self.running = False
         if self.proc:
             time.sleep(0.15)
             self.proc.terminate()
         rows = self.rows[first:last] if last is not None else self.rows[first:]
         if not rows:                      # a timed region shorter than the sampling period: the samples around it
             rows = self.rows[max(0, first - 2):(last + 2) if last is not None else None]
+        if not rows:
+            rows = self.rows[-3:]
         sm, mx, reasons = [], [], set()
         for r in rows:
             try:
@@ -109,7 +150,8 @@ class ClockSampler:
                         reasons.add(name)
             except Exception:
                 pass
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm),
+                "source": self.source}
 
 
 def make_scene(workload, root, for_reference=False):

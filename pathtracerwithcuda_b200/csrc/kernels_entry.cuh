@@ -1,0 +1,177 @@
+// ptb200 wavefront integrator: entry cuts for camera rays (round 2).
+//
+// Every camera ray of an 8x4 pixel tile lies inside one thin shaft: the pyramid from the eye through the tile's rectangle on the canvas
+// plane (generate_camera_ray, pt_device.cuh; path_tracer_kernel.cu:299-379), widened by the lens disc when the camera has an aperture.
+// The closest-hit search of such a ray spends most of its node visits walking from the root down to the few leaves its shaft touches —
+// the same walk for all 32 pixels of the tile and for every pass, because the shaft only depends on the camera.  k_entry_cut does that
+// walk ONCE per tile: starting at the root it replaces a node by those of its children whose boxes overlap the shaft (one child
+// overlapping = a free descent; both = the list grows by one) until the list holds `k_max` sub-trees, and stores them sorted by a lower
+// bound on the hit distance.  k_extend_entry (kernels_extend.cuh, ENTRY) then starts each camera ray at its tile's list instead of at
+// the root and stops walking the list at the first sub-tree that begins beyond its current hit.
+//
+// Correctness: every state of the list covers all triangles whose boxes overlap the shaft, the overlap test and the distance bound are
+// conservative (margins below), so the rays find exactly the hits a search from the root finds (closest hit with the same acceptance
+// arithmetic; tests/test_gpu_entry.py compares hit records bit for bit).  Included by render.cu only.
+#pragma once
+#include <cuda_runtime.h>
+#include <math_constants.h>
+#include "kernels.cuh"
+
+namespace ptb
+{
+
+using namespace ptbdev;
+
+#define PTB_ENTRY_STRIDE 16          // int2 slots per tile: <= 15 sub-trees + terminator
+#define PTB_ENTRY_TILE_W 8
+#define PTB_ENTRY_TILE_H 4
+#define PTB_ENTRY_END ((int)0x80000000)   // == PTB_DONE of kernels_extend.cuh
+
+// distances to the shaft's planes / eye of one box, relative to the eye
+struct EntryShaft
+{
+	float3 eye, w;          // eye, unit view direction
+	float3 n[4];            // inward unit normals of the four side planes of the pinhole pyramid
+	float lens;             // aperture radius (0 = pinhole)
+	float focal_lo;         // lower bound on dot(F - eye, w) over the tile's focal points F
+	float focal_hi;         // upper bound (= focal distance)
+};
+
+// Conservative: false only when no camera ray of the tile can touch the box.  A ray from lens point eye + delta (|delta| <= lens,
+// delta perpendicular to w) through focal point F is P(u) = [eye + u (F - eye)] + (1 - u) delta, u >= 0: the pinhole ray's point at
+// depth fraction u displaced by at most |1 - u| * lens.  So P is at most |1 - u| * lens outside any side plane of the pinhole pyramid,
+// with u = dot(P - eye, w) / dot(F - eye, w).
+__device__ __forceinline__ bool entry_box_overlaps(const EntryShaft& s, float3 lo, float3 hi, float& t_lower)
+{
+	const float3 a = lo - s.eye, b = hi - s.eye;
+	// depth range of the box along the view direction
+	const float z_hi = fmaxf(a.x * s.w.x, b.x * s.w.x) + fmaxf(a.y * s.w.y, b.y * s.w.y) + fmaxf(a.z * s.w.z, b.z * s.w.z);
+	const float z_lo = fminf(a.x * s.w.x, b.x * s.w.x) + fminf(a.y * s.w.y, b.y * s.w.y) + fminf(a.z * s.w.z, b.z * s.w.z);
+	const float scale = fabsf(a.x) + fabsf(a.y) + fabsf(a.z) + fabsf(b.x) + fabsf(b.y) + fabsf(b.z);
+	const float eps = 4e-6f * scale + 1e-30f;
+	if (z_hi < -eps) return false;                           // behind the lens plane
+	float widen = 0.0f;
+	if (s.lens > 0.0f)
+	{
+		const float u_lo = fmaxf(z_lo, 0.0f) / s.focal_hi, u_hi = fmaxf(z_hi, 0.0f) / s.focal_lo;
+		widen = s.lens * fmaxf(fabsf(1.0f - u_lo), fabsf(1.0f - u_hi)) * 1.0001f;
+	}
+#pragma unroll
+	for (int k = 0; k < 4; k++)
+	{
+		const float3 n = s.n[k];
+		const float m = fmaxf(a.x * n.x, b.x * n.x) + fmaxf(a.y * n.y, b.y * n.y) + fmaxf(a.z * n.z, b.z * n.z);   // most-inside corner
+		if (m < -(widen + eps)) return false;
+	}
+	// lower bound on the ray parameter of any point in the box: |P - o| >= |P - eye| - lens (unit directions)
+	const float dx = fmaxf(fmaxf(a.x, -b.x), 0.0f), dy = fmaxf(fmaxf(a.y, -b.y), 0.0f), dz = fmaxf(fmaxf(a.z, -b.z), 0.0f);
+	t_lower = fmaxf(0.0f, (sqrtf(dx * dx + dy * dy + dz * dz) - s.lens) * 0.99999f - eps);
+	return true;
+}
+
+// One thread per tile.  cuts[tile * PTB_ENTRY_STRIDE + i] = (node reference, lower bound on t as float bits), ascending in t,
+// terminated by (PTB_ENTRY_END, +inf).
+__global__ void __launch_bounds__(128) k_entry_cut(DeviceScene sc, CameraParams cam, int width, int height, int tiles_x, int n_tiles, int k_max,
+	int2* __restrict__ cuts)
+{
+	const int tile = blockIdx.x * blockDim.x + threadIdx.x;
+	if (tile >= n_tiles) return;
+	const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
+	int2* out = cuts + (size_t)tile * PTB_ENTRY_STRIDE;
+
+	// the camera frame of generate_camera_ray, same expressions
+	const float distance = length(cam.view);
+	const float3 horizontal = normalize(cross(cam.view, cam.up));
+	const float3 vertical = normalize(cross(horizontal, cam.view));
+	const float3 x_axis = horizontal * (distance * __tanf(cam.fov.x * 0.5f * (PTB_PI / 180.0f)));
+	const float3 y_axis = vertical * (distance * __tanf(-cam.fov.y * 0.5f * (PTB_PI / 180.0f)));
+	// the tile's rectangle on the canvas plane: pixel centres +- 0.5 of jitter, + 1/16 pixel of slack for the rounding of the
+	// generator's own arithmetic
+	const float slack = 0.5f + 0.0625f;
+	const float px0 = (float)(tx * PTB_ENTRY_TILE_W) - slack, px1 = (float)min(tx * PTB_ENTRY_TILE_W + PTB_ENTRY_TILE_W - 1, width - 1) + slack;
+	const float py0 = (float)(ty * PTB_ENTRY_TILE_H) - slack, py1 = (float)min(ty * PTB_ENTRY_TILE_H + PTB_ENTRY_TILE_H - 1, height - 1) + slack;
+	const float nx0 = (px0 / (cam.resolution.x - 1.0f)) * 2.0f - 1.0f, nx1 = (px1 / (cam.resolution.x - 1.0f)) * 2.0f - 1.0f;
+	const float ny0 = (py0 / (cam.resolution.y - 1.0f)) * 2.0f - 1.0f, ny1 = (py1 / (cam.resolution.y - 1.0f)) * 2.0f - 1.0f;
+	float3 c[4];
+	c[0] = cam.view + nx0 * x_axis + ny0 * y_axis;
+	c[1] = cam.view + nx1 * x_axis + ny0 * y_axis;
+	c[2] = cam.view + nx1 * x_axis + ny1 * y_axis;
+	c[3] = cam.view + nx0 * x_axis + ny1 * y_axis;
+	const float3 centre = cam.view + (0.5f * (nx0 + nx1)) * x_axis + (0.5f * (ny0 + ny1)) * y_axis;
+
+	EntryShaft s;
+	s.eye = cam.eye;
+	s.w = cam.view * (1.0f / distance);
+	s.lens = cam.aperture_radius > 0.00001f ? cam.aperture_radius : 0.0f;
+	float cos_min = 1.0f;
+#pragma unroll
+	for (int k = 0; k < 4; k++)
+	{
+		float3 n = normalize(cross(c[k], c[(k + 1) & 3]));
+		if (dot(n, centre) < 0.0f) n = n * -1.0f;
+		s.n[k] = n;
+		cos_min = fminf(cos_min, dot(normalize(c[k]), s.w));
+	}
+	s.focal_hi = fmaxf(cam.focal_distance, 1e-20f) * 1.0001f;
+	s.focal_lo = fmaxf(cam.focal_distance * cos_min * 0.9999f, 1e-20f);
+
+	int ref[PTB_ENTRY_STRIDE];
+	float tn[PTB_ENTRY_STRIDE];
+	unsigned frozen = 0u;      // bit i: entry i is final
+	int n = 0;
+	k_max = max(1, min(k_max, PTB_ENTRY_STRIDE - 1));
+	// a degenerate frame (zero view / up parallel to view) makes every test pass: the list stays at the root, which is always valid
+	if (sc.n_triangles > 0)
+	{
+		ref[0] = sc.root_ref; tn[0] = 0.0f; n = 1;
+		if (sc.root_ref < 0) frozen = 1u;
+	}
+	for (int iter = 0; iter < 160; iter++)
+	{
+		// the front-most sub-tree that may still be opened
+		int pick = -1;
+		float front = CUDART_INF_F;
+		for (int i = 0; i < n; i++)
+			if (!((frozen >> i) & 1u) && tn[i] < front) { front = tn[i]; pick = i; }
+		if (pick < 0) break;
+		const float4* np = sc.bvh_nodes + (size_t)ref[pick] * 4;
+		const float4 n0 = __ldg(np + 0), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3);
+		const int child0 = __float_as_int(n3.x), child1 = __float_as_int(n3.y);
+		float t0 = 0.0f, t1 = 0.0f;
+		const bool ok0 = entry_box_overlaps(s, make_float3(n0.x, n0.z, n2.x), make_float3(n0.y, n0.w, n2.y), t0);
+		const bool ok1 = entry_box_overlaps(s, make_float3(n1.x, n1.z, n2.z), make_float3(n1.y, n1.w, n2.w), t1);
+		if (!ok0 && !ok1)
+		{
+			// nothing of this sub-tree is inside the shaft: drop it (last entry moves into the hole)
+			n--;
+			ref[pick] = ref[n]; tn[pick] = tn[n];
+			frozen = (frozen & ~(1u << pick)) | (((frozen >> n) & 1u) << pick);
+			frozen &= ~(1u << n);
+			continue;
+		}
+		// a leaf never becomes an entry: the box test that lets a ray skip it sits in its parent
+		if ((ok0 && child0 < 0) || (ok1 && child1 < 0)) { frozen |= 1u << pick; continue; }
+		if (ok0 != ok1)
+		{
+			ref[pick] = ok0 ? child0 : child1; tn[pick] = fmaxf(tn[pick], ok0 ? t0 : t1);   // free descent
+			continue;
+		}
+		if (n >= k_max) { frozen |= 1u << pick; continue; }
+		const float parent_t = tn[pick];
+		ref[pick] = child0; tn[pick] = fmaxf(parent_t, t0);
+		ref[n] = child1; tn[n] = fmaxf(parent_t, t1);
+		n++;
+	}
+	// ascending lower bounds: a ray stops at the first entry beyond its current hit
+	for (int i = 1; i < n; i++)
+	{
+		const int r_i = ref[i]; const float t_i = tn[i];
+		int j = i - 1;
+		while (j >= 0 && tn[j] > t_i) { ref[j + 1] = ref[j]; tn[j + 1] = tn[j]; j--; }
+		ref[j + 1] = r_i; tn[j + 1] = t_i;
+	}
+	for (int i = 0; i < n; i++) out[i] = make_int2(ref[i], __float_as_int(tn[i]));
+	out[n] = make_int2(PTB_ENTRY_END, __float_as_int(CUDART_INF_F));
+}
+
+} // namespace ptb

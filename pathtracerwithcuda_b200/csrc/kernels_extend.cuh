@@ -379,9 +379,19 @@ __device__ __forceinline__ bool fused_scatter_event(const DeviceScene& sc, const
 // numbers level by level — are copied into shared memory by the block and fetched from there: every ray walks through them, and a
 // scattered 64-byte gather costs the L1 data stage ~1.45 cycles per lane (tools/roofs: 12.8 TB/s) where shared memory delivers it at
 // bank rate.  Blocks are then as large as the launch allows (one 1024-thread block per SM shares one copy).
-template <bool COUNT, int REPS, bool TREELET, bool STAGED, bool FUSED = false>
+// ENTRY (k_extend_entry below; camera rays only): a ray starts at its 8x4 pixel tile's entry cut (kernels_entry.cuh: the sub-trees its
+// shaft touches, ascending in a lower bound on the hit distance) instead of at the root, and stops walking the list at the first
+// sub-tree that begins beyond its current hit.
+struct EntryArgs
+{
+	const int2* cuts;
+	int pixel_count, width, tiles_x;
+};
+
+template <bool COUNT, int REPS, bool TREELET, bool STAGED, bool FUSED = false, bool ENTRY = false>
 __device__ __forceinline__ void extend_persistent_body(const DeviceScene& sc, const PathState& st, const int* __restrict__ queue, const int* __restrict__ count_ptr,
-	int* __restrict__ work_counter, unsigned long long* __restrict__ counters, int refill_min, int leaf_min, int node_reps, const float4* s_top, int n_top, float4* s_stage, const FusedArgs* fa = nullptr, float4* s_thr = nullptr, int* s_hist = nullptr)
+	int* __restrict__ work_counter, unsigned long long* __restrict__ counters, int refill_min, int leaf_min, int node_reps, const float4* s_top, int n_top, float4* s_stage, const FusedArgs* fa = nullptr, float4* s_thr = nullptr, int* s_hist = nullptr,
+	const EntryArgs* ea = nullptr)
 {
 	const int count = *count_ptr;
 	const unsigned lane = threadIdx.x & 31u;
@@ -409,11 +419,18 @@ __device__ __forceinline__ void extend_persistent_body(const DeviceScene& sc, co
 	// FUSED (see FusedArgs above): scatter events of the medium performed here, the path runs `lead` bounces ahead of the loop depth
 	int lead = 0;
 	bool at_scatter = false, thr_cached = false;
+	int cut = 0;                 // ENTRY: index of the next entry of the lane's tile list
 
 	// Every iteration starts with full-mask votes, so all 32 lanes are converged when a phase
 	// begins; a phase is executed by the lanes in that state, the others are predicated off.
 	while (true)
 	{
+		if (ENTRY && id >= 0 && node == PTB_DONE)
+		{
+			// the sub-tree is finished (or the ray is new): next entry of the tile's list, unless it begins beyond the current hit
+			const int2 e = __ldg(ea->cuts + cut);
+			if (e.x != PTB_DONE && __int_as_float(e.y) <= best.t) { node = e.x; cut++; }
+		}
 		// retire finished rays (no vote needed: a plain predicated store)
 		if (FUSED && id >= 0 && node == PTB_DONE && !at_scatter && best.prim == -1 && best.t < CUDART_INF_F) at_scatter = true;
 		if (id >= 0 && node == PTB_DONE && !at_scatter)
@@ -548,6 +565,15 @@ __device__ __forceinline__ void extend_persistent_body(const DeviceScene& sc, co
 					margin2 = 4.8e-7f * fmaxf(fmaxf(fabsf(noidir.x), fabsf(noidir.y)), fabsf(noidir.z));
 					sp = 0;
 					node = sc.n_triangles > 0 ? sc.root_ref : PTB_DONE;
+					if (ENTRY)
+					{
+						const int pixel = id % ea->pixel_count;
+						const int py = pixel / ea->width, px = pixel - py * ea->width;
+						cut = ((py >> 2) * ea->tiles_x + (px >> 3)) * 16;
+						const int2 e = __ldg(ea->cuts + cut);
+						node = PTB_DONE;
+						if (e.x != PTB_DONE && __int_as_float(e.y) <= best.t) { node = e.x; cut++; }
+					}
 				}
 			}
 			continue;
@@ -692,6 +718,14 @@ __global__ void __launch_bounds__(128, PTB_PERSISTENT_MIN_BLOCKS) k_extend_persi
 	int* __restrict__ work_counter, unsigned long long* __restrict__ counters, int refill_min, int leaf_min, int node_reps)
 {
 	extend_persistent_body<COUNT, REPS, false, false>(sc, st, queue, count_ptr, work_counter, counters, refill_min, leaf_min, node_reps, nullptr, 0, nullptr);
+}
+
+// camera rays (depth 0) started at their tile's entry cut (kernels_entry.cuh)
+template <bool COUNT>
+__global__ void __launch_bounds__(128, PTB_PERSISTENT_MIN_BLOCKS) k_extend_entry(DeviceScene sc, PathState st, const int* __restrict__ queue, const int* __restrict__ count_ptr,
+	int* __restrict__ work_counter, unsigned long long* __restrict__ counters, int refill_min, int leaf_min, EntryArgs ea)
+{
+	extend_persistent_body<COUNT, 6, false, false, false, true>(sc, st, queue, count_ptr, work_counter, counters, refill_min, leaf_min, 6, nullptr, 0, nullptr, nullptr, nullptr, nullptr, &ea);
 }
 
 // the binary-tree kernel with inline scatter events (option inline_scatter with fused_tree=2: the whole subsurface walk over the binary tree)

@@ -36,6 +36,7 @@ namespace ptb
 } // namespace ptb
 
 #include "kernels_generate.cuh"
+#include "kernels_entry.cuh"
 #include "kernels_extend.cuh"
 #include "kernels_shade.cuh"
 
@@ -116,6 +117,14 @@ struct ptb_renderer
 	double bvh_build_ms = 0.0, scene_upload_ms = 0.0;
 	std::string bvh_note;
 	int extend_persistent = 1;
+	// entry cuts (kernels_entry.cuh): camera rays start at the sub-trees their 8x4 pixel tile's shaft touches instead of at the root.
+	// Same hits bit for bit; the lists depend on camera + geometry only and are rebuilt when either changes.
+	int entry_cuts = 1;
+	int entry_k = 8;                       // sub-trees per tile (<= PTB_ENTRY_STRIDE - 1)
+	int2* entry_buf = nullptr; size_t entry_buf_tiles = 0;
+	bool entry_valid = false;
+	unsigned char entry_key[96] = { 0 };   // camera, resolution, k and geometry version the lists were built for
+	uint64_t geometry_version = 0;
 	int tune_refill4 = 8;                  // extend_variant 4: pop staged rays when >= N lanes are idle
 	int treelet_block = 1024, treelet_nodes = 1023;   // extend_variant 3: threads per block and top-of-tree nodes held in shared memory (64 B each)
 	int sort_depth_mask = 0, sort_cell_bits = 5, sort_octant = 1;   // PTB_EXPERIMENT_SORT builds only
@@ -272,6 +281,7 @@ void free_work_buffers(ptb_renderer* r)
 	cudaFree(r->counters); cudaFree(r->segment_totals);
 	if (r->counts_host) cudaFreeHost(r->counts_host);
 	cudaFree(r->image_sum); cudaFree(r->last_pass); cudaFree(r->image_u8);
+	cudaFree(r->entry_buf); r->entry_buf = nullptr; r->entry_buf_tiles = 0; r->entry_valid = false;
 	cudaFree(r->merged_sum); cudaFree(r->merged_u8); cudaFree(r->pass_count_dev);
 	r->merged_sum = nullptr; r->merged_u8 = nullptr; r->pass_count_dev = nullptr; r->merged_passes = 0;
 	r->counts_host = nullptr; r->counters = nullptr; r->segment_totals = nullptr;
@@ -395,6 +405,7 @@ void release_scene_device(ptb_renderer* r)
 	r->scene_allocs.clear(); r->geometry_allocs.clear(); r->material_allocs.clear(); r->light_allocs.clear();
 	memset(&r->dscene, 0, sizeof(r->dscene));
 	r->bvh_nodes = r->bvh_bytes = 0;
+	r->entry_valid = false;
 }
 
 DeviceMaterial pack_material(const ptb_material& m)
@@ -508,6 +519,8 @@ void apply_l2_window(ptb_renderer* r)
 // Bvh/bvh.cpp:332-356)
 int upload_geometry(ptb_renderer* r)
 {
+	r->geometry_version++;        // entry cuts of the camera rays refer to the old tree
+	r->entry_valid = false;
 	for (void* p : r->geometry_allocs) cudaFree(p);
 	r->geometry_allocs.clear();
 	const HostScene& s = r->scene;
@@ -904,9 +917,65 @@ int grid_for(const ptb_renderer* r, size_t items, int block, int blocks_per_sm)
 	return (int)std::max<size_t>(1, std::min(need, cap));
 }
 
-void launch_extend(ptb_renderer* r, cudaStream_t stream, size_t items, const PathState& st, const int* queue, const int* count_ptr, int* work_counter, int depth = 0, const FusedArgs* fused = nullptr)
+// Entry cuts of the camera rays (kernels_entry.cuh): true when this render can use them (binary tree traced by the persistent kernel,
+// a camera whose rays the shaft construction covers).
+bool entry_cuts_usable(const ptb_renderer* r)
+{
+	if (!r->entry_cuts || r->dscene.bvh_layout != 2 || !r->extend_persistent || r->extend_variant != 0 || r->dscene.n_triangles <= 0) return false;
+	const ptb_camera& c = r->cam;
+	const float vl = std::sqrt(c.view[0] * c.view[0] + c.view[1] * c.view[1] + c.view[2] * c.view[2]);
+	if (!(vl > 1e-20f) || !std::isfinite(vl)) return false;
+	if (!(c.focal_distance > 1e-6f) || !std::isfinite(c.focal_distance)) return false;     // a non-positive focal distance flips the rays
+	if (!(c.fov[0] > 0.01f && c.fov[0] < 175.0f && c.fov[1] > 0.01f && c.fov[1] < 175.0f)) return false;
+	if (c.resolution[0] != (float)r->cfg.width || c.resolution[1] != (float)r->cfg.height || r->cfg.width < 2 || r->cfg.height < 2) return false;
+	if (!(c.aperture_radius < 0.25f * c.focal_distance)) return false;                      // (also rejects NaN)
+	for (int k = 0; k < 3; k++) if (!std::isfinite(c.eye[k]) || !std::isfinite(c.up[k])) return false;
+	return true;
+}
+
+// (Re)builds the lists when camera, resolution, k or geometry changed since the last build.  Rare (a camera move, a scene edit): waits
+// for every stream that may still read the old lists, builds on `stream`, and makes the other streams wait for the build.
+int ensure_entry_cuts(ptb_renderer* r, cudaStream_t stream)
+{
+	unsigned char key[sizeof(r->entry_key)];
+	memset(key, 0, sizeof(key));
+	static_assert(sizeof(ptb_camera) + 4 * sizeof(int) + sizeof(uint64_t) <= sizeof(key), "entry key too small");
+	memcpy(key, &r->cam, sizeof(ptb_camera));
+	const int ints[4] = { r->cfg.width, r->cfg.height, r->entry_k, 0 };
+	memcpy(key + sizeof(ptb_camera), ints, sizeof(ints));
+	memcpy(key + sizeof(ptb_camera) + sizeof(ints), &r->geometry_version, sizeof(uint64_t));
+	if (r->entry_valid && memcmp(key, r->entry_key, sizeof(key)) == 0) return 0;
+	const int tiles_x = (r->cfg.width + PTB_ENTRY_TILE_W - 1) / PTB_ENTRY_TILE_W, tiles_y = (r->cfg.height + PTB_ENTRY_TILE_H - 1) / PTB_ENTRY_TILE_H;
+	const size_t n_tiles = (size_t)tiles_x * tiles_y;
+	PTB_CUDA(cudaDeviceSynchronize());
+	if (n_tiles > r->entry_buf_tiles)
+	{
+		cudaFree(r->entry_buf); r->entry_buf = nullptr; r->entry_buf_tiles = 0;
+		PTB_CUDA(cudaMalloc(&r->entry_buf, n_tiles * PTB_ENTRY_STRIDE * sizeof(int2)));
+		r->entry_buf_tiles = n_tiles;
+	}
+	k_entry_cut<<<(int)((n_tiles + 127) / 128), 128, 0, stream>>>(r->dscene, camera_params(r->cam), r->cfg.width, r->cfg.height, tiles_x, (int)n_tiles, r->entry_k, r->entry_buf);
+	r->stats.kernel_launches++;
+	PTB_CUDA(cudaGetLastError());
+	PTB_CUDA(cudaStreamSynchronize(stream));
+	memcpy(r->entry_key, key, sizeof(key));
+	r->entry_valid = true;
+	return 0;
+}
+
+void launch_extend(ptb_renderer* r, cudaStream_t stream, size_t items, const PathState& st, const int* queue, const int* count_ptr, int* work_counter, int depth = 0, const FusedArgs* fused = nullptr, bool entry = false)
 {
 	bool wide = r->dscene.bvh_layout == 8;
+	if (entry && !fused && r->entry_valid)
+	{
+		// camera rays: every ray starts at its tile's entry cut
+		EntryArgs ea;
+		ea.cuts = r->entry_buf; ea.pixel_count = r->pixel_count; ea.width = r->cfg.width; ea.tiles_x = (r->cfg.width + PTB_ENTRY_TILE_W - 1) / PTB_ENTRY_TILE_W;
+		int grid = std::max(1, std::min(r->persistent_grid, (int)((items + 127) / 128)));
+		if (r->count_traversal) k_extend_entry<true><<<grid, 128, 0, stream>>>(r->dscene, st, queue, count_ptr, work_counter, r->counters, r->tune_refill, r->tune_leaf, ea);
+		else k_extend_entry<false><<<grid, 128, 0, stream>>>(r->dscene, st, queue, count_ptr, work_counter, r->counters, r->tune_refill, r->tune_leaf, ea);
+		return;
+	}
 	if (r->dscene.bvh_layout == 2 && r->dscene.bvh8_nodes && r->extend_persistent && depth >= r->hybrid_from_depth)
 	{
 		// hybrid: bounce rays over the compressed wide tree
@@ -1021,6 +1090,8 @@ int enqueue_batch(ptb_renderer* r, ptb_renderer::BatchContext& ctx, cudaEvent_t 
 	// the walk on the binary-tree kernel until then)
 	const int fused_from = r->fused_from_depth >= 0 ? r->fused_from_depth : (r->dscene.bvh_layout == 8 ? 0 : std::max(r->hybrid_from_depth, 0));
 	const int tally_counts = fused ? std::min(fused_from, n_counts) : n_counts;
+	const bool entry = entry_cuts_usable(r) && r->hybrid_from_depth > 0 && !(fused && fused_from <= 0);
+	if (entry && ensure_entry_cuts(r, stream)) return 1;
 	if (alt) k_generate<true><<<grid_for(r, total, 256, 8), 256, 0, stream>>>(ctx.st, ctx.queue[0], ctx.counts, n_counts, cp, dc, px, n_slots, first_pass, stride, tiles_x);
 	else k_generate<false><<<grid_for(r, total, 256, 8), 256, 0, stream>>>(ctx.st, ctx.queue[0], ctx.counts, n_counts, cp, dc, px, n_slots, first_pass, stride, tiles_x);
 	r->stats.kernel_launches++;
@@ -1036,7 +1107,7 @@ int enqueue_batch(ptb_renderer* r, ptb_renderer::BatchContext& ctx, cudaEvent_t 
 			cudaEventRecord(e0, stream);
 		}
 		fa.loop_depth = depth;
-		launch_extend(r, stream, total, ctx.st, qin, ctx.counts + depth, ctx.counts + n_counts + depth, depth, (fused && depth >= fused_from) ? &fa : nullptr);
+		launch_extend(r, stream, total, ctx.st, qin, ctx.counts + depth, ctx.counts + n_counts + depth, depth, (fused && depth >= fused_from) ? &fa : nullptr, entry && depth == 0);
 		if (prof) cudaEventRecord(e1, stream);
 		int* shadow_count = ctx.counts + 2 * n_counts + depth;
 		const int sgrid = grid_for(r, total, 128, 16);
@@ -1287,6 +1358,8 @@ ptb_renderer* ptb_create(const char* config_json_path, int cuda_device)
 		setup(k_extend_persistent<false, 0>, &r->persistent_grid);
 		setup(k_extend_persistent<false, PTB_NODE_REPS>, nullptr);
 		setup(k_extend_persistent<true, 0>, nullptr);
+		setup(k_extend_entry<false>, nullptr);
+		setup(k_extend_entry<true>, nullptr);
 		setup(k_extend_persistent8<false>, &r->persistent_grid8);
 		setup(k_extend_persistent8<true>, nullptr);
 	}
@@ -1961,6 +2034,8 @@ int ptb_set_option(ptb_renderer* r, const char* key, const char* value)
 	}
 	if (k == "extend_persistent") { r->extend_persistent = atoi(value); return 0; }
 	if (k == "extend_variant") { r->extend_variant = atoi(value); return 0; }
+	if (k == "entry_cuts") { r->entry_cuts = atoi(value) != 0; return 0; }
+	if (k == "entry_k") { r->entry_k = std::max(1, std::min(atoi(value), PTB_ENTRY_STRIDE - 1)); return 0; }
 	if (k == "tune_refill4") { r->tune_refill4 = atoi(value); return 0; }
 	if (k == "treelet_block") { r->treelet_block = atoi(value); return 0; }
 	if (k == "treelet_nodes") { r->treelet_nodes = atoi(value); return 0; }

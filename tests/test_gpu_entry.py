@@ -1,0 +1,120 @@
+"""Entry cuts of the camera rays (csrc/kernels_entry.cuh, k_extend_entry): starting every camera ray at the sub-trees its 8x4 pixel
+tile's shaft touches must find exactly the hits a search from the root finds — the accumulated image and the per-depth segment counts
+are compared BIT FOR BIT against the same render with entry_cuts=0, over cameras that stress the shaft construction (thin lens, eye
+inside the geometry's bounds, grazing views, resolutions that are no multiple of the tile, anti-aliasing jitter on and off)."""
+import numpy as np
+import pytest
+
+import pathtracerwithcuda_b200 as ptb
+
+pytestmark = pytest.mark.gpu
+
+
+def render(w, root, cam, passes, **options):
+    r = ptb.Renderer(w["config"], device=0)
+    for k, v in options.items():
+        r.set_option(k, v)
+    r.load_scene(w["scene"], root)
+    r.set_camera(cam)
+    r.render(passes)
+    img = r.image_f32().copy()
+    seg, _ = r.depth_profile()
+    r.close()
+    return img, list(seg)
+
+
+def camera(w, eye=None, view=None, up=None, aperture=None, focal=None, fov_scale=1.0):
+    cam = ptb.default_camera(w["width"], w["height"], w["aperture"] if aperture is None else aperture, w["focal"] if focal is None else focal)
+    if eye is not None:
+        for k in range(3):
+            cam.eye[k] = eye[k]
+    if view is not None:
+        for k in range(3):
+            cam.view[k] = view[k]
+    if up is not None:
+        for k in range(3):
+            cam.up[k] = up[k]
+    cam.fov[0] *= fov_scale
+    cam.fov[1] *= fov_scale
+    return cam
+
+
+CAMERAS = [
+    ("default", dict()),
+    ("pinhole", dict(aperture=0.0)),
+    ("wide_lens_near_focus", dict(aperture=0.6, focal=3.0)),
+    ("lens_far_focus", dict(aperture=0.3, focal=27.0)),
+    ("inside_looking_out", dict(eye=(0.3, 0.4, 0.2), view=(0.7, -0.1, -0.7))),
+    ("grazing_from_below", dict(eye=(6.0, -1.5, 6.0), view=(-3.0, 0.45, -3.0), aperture=0.0)),
+    ("long_view_vector_rolled", dict(eye=(-9.0, 5.0, 4.0), view=(18.0, -9.0, -8.5), up=(0.3, 1.0, 0.1))),
+    ("narrow_fov", dict(fov_scale=0.2, aperture=0.0)),
+    ("wide_fov", dict(fov_scale=2.6, aperture=0.05)),
+]
+
+
+@pytest.mark.parametrize("label,kw", CAMERAS)
+def test_entry_cuts_find_the_same_hits_mix(workload_root, label, kw):
+    root, w = workload_root("mix", width=100, height=70)      # neither a multiple of 8 nor of 4: partial tiles on both edges
+    cam = camera(w, **kw)
+    ref, seg0 = render(w, root, cam, 3, entry_cuts=0)
+    for k in (1, 4, 8, 15):
+        img, seg = render(w, root, cam, 3, entry_cuts=1, entry_k=k)
+        assert np.array_equal(ref.view(np.uint32), img.view(np.uint32)), (label, k)
+        assert seg == seg0, (label, k)
+
+
+@pytest.mark.parametrize("name,size,scale", [("c2", (320, 180), 0.1), ("c3", (256, 144), 0.05), ("c4", (192, 108), 0.03), ("c1", (96, 96), 1.0)])
+def test_entry_cuts_find_the_same_hits_baseline_configs(workload_root, name, size, scale):
+    root, w = workload_root(name, width=size[0], height=size[1], tri_scale=scale)
+    cam = camera(w)
+    ref, seg0 = render(w, root, cam, 2, entry_cuts=0)
+    img, seg = render(w, root, cam, 2, entry_cuts=1)
+    assert np.array_equal(ref.view(np.uint32), img.view(np.uint32))
+    assert seg == seg0
+    # anti-aliasing off: every ray goes through its pixel centre (the shaft's slack still covers it)
+    r0 = ptb.Renderer(w["config"], device=0); r1 = ptb.Renderer(w["config"], device=0)
+    for r, on in ((r0, 0), (r1, 1)):
+        r.set_option("entry_cuts", on)
+        r.load_scene(w["scene"], root)
+        r.set_camera(cam)
+        c = r.config().copy()
+        c["use_anti_alias"] = 0
+        r.set_config(c)
+        r.render(2)
+    assert np.array_equal(r0.image_f32().view(np.uint32), r1.image_f32().view(np.uint32))
+    r0.close(); r1.close()
+
+
+def test_entry_cuts_follow_camera_and_geometry_edits(workload_root):
+    """The lists are rebuilt when the camera or the geometry changes between calls on ONE renderer."""
+    root, w = workload_root("mix", width=96, height=72)
+    rs = []
+    for on in (0, 1):
+        r = ptb.Renderer(w["config"], device=0)
+        r.set_option("entry_cuts", on)
+        r.load_scene(w["scene"], root)
+        rs.append(r)
+    steps = [camera(w), camera(w, eye=(5.0, 2.0, -9.0), view=(-0.45, -0.15, 0.88)), camera(w, aperture=0.0, fov_scale=0.5)]
+    for i, cam in enumerate(steps):
+        imgs = []
+        for r in rs:
+            r.set_camera(cam)
+            r.clear()
+            r.render(2)
+            imgs.append(r.image_f32().copy())
+        assert np.array_equal(imgs[0].view(np.uint32), imgs[1].view(np.uint32)), i
+        if i == 1:
+            for r in rs:      # move a mesh: the tree is rebuilt, the old lists refer to nodes that no longer exist
+                r.set_mesh_transform(1, position=(-0.6, 0.9, 0.8), scale=(1.2, 1.0, 1.4))
+    for r in rs:
+        r.close()
+
+
+def test_unusable_cameras_fall_back_to_the_root(workload_root):
+    """A camera the shaft construction does not cover (non-positive focal distance: the generator flips the rays) is traced from the root."""
+    root, w = workload_root("mix", width=64, height=48)
+    cam = camera(w, aperture=0.0)
+    cam.focal_distance = -2.0
+    a, _ = render(w, root, cam, 2, entry_cuts=0)
+    b, _ = render(w, root, cam, 2, entry_cuts=1)
+    assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
