@@ -22,9 +22,8 @@ namespace ptb
 
 using namespace ptbdev;
 
-#define PTB_ENTRY_STRIDE 16          // int2 slots per tile: <= 15 sub-trees + terminator
-#define PTB_ENTRY_TILE_W 8
-#define PTB_ENTRY_TILE_H 4
+#define PTB_ENTRY_STRIDE 32          // most int2 slots per tile: <= 31 sub-trees + terminator (the lists are stored with a stride of
+                                     // the next power of two above k_max)
 #define PTB_ENTRY_END ((int)0x80000000)   // == PTB_DONE of kernels_extend.cuh
 
 // distances to the shaft's planes / eye of one box, relative to the eye
@@ -69,15 +68,15 @@ __device__ __forceinline__ bool entry_box_overlaps(const EntryShaft& s, float3 l
 	return true;
 }
 
-// One thread per tile.  cuts[tile * PTB_ENTRY_STRIDE + i] = (node reference, lower bound on t as float bits), ascending in t,
+// One thread per tile.  cuts[tile * stride + i] = (node reference, lower bound on t as float bits), ascending in t,
 // terminated by (PTB_ENTRY_END, +inf).
 __global__ void __launch_bounds__(128) k_entry_cut(DeviceScene sc, CameraParams cam, int width, int height, int tiles_x, int n_tiles, int k_max,
-	int2* __restrict__ cuts)
+	int tile_w, int tile_h, int stride, int2* __restrict__ cuts)
 {
 	const int tile = blockIdx.x * blockDim.x + threadIdx.x;
 	if (tile >= n_tiles) return;
 	const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
-	int2* out = cuts + (size_t)tile * PTB_ENTRY_STRIDE;
+	int2* out = cuts + (size_t)tile * stride;
 
 	// the camera frame of generate_camera_ray, same expressions
 	const float distance = length(cam.view);
@@ -88,8 +87,8 @@ __global__ void __launch_bounds__(128) k_entry_cut(DeviceScene sc, CameraParams 
 	// the tile's rectangle on the canvas plane: pixel centres +- 0.5 of jitter, + 1/16 pixel of slack for the rounding of the
 	// generator's own arithmetic
 	const float slack = 0.5f + 0.0625f;
-	const float px0 = (float)(tx * PTB_ENTRY_TILE_W) - slack, px1 = (float)min(tx * PTB_ENTRY_TILE_W + PTB_ENTRY_TILE_W - 1, width - 1) + slack;
-	const float py0 = (float)(ty * PTB_ENTRY_TILE_H) - slack, py1 = (float)min(ty * PTB_ENTRY_TILE_H + PTB_ENTRY_TILE_H - 1, height - 1) + slack;
+	const float px0 = (float)(tx * tile_w) - slack, px1 = (float)min(tx * tile_w + tile_w - 1, width - 1) + slack;
+	const float py0 = (float)(ty * tile_h) - slack, py1 = (float)min(ty * tile_h + tile_h - 1, height - 1) + slack;
 	const float nx0 = (px0 / (cam.resolution.x - 1.0f)) * 2.0f - 1.0f, nx1 = (px1 / (cam.resolution.x - 1.0f)) * 2.0f - 1.0f;
 	const float ny0 = (py0 / (cam.resolution.y - 1.0f)) * 2.0f - 1.0f, ny1 = (py1 / (cam.resolution.y - 1.0f)) * 2.0f - 1.0f;
 	float3 c[4];
@@ -119,14 +118,14 @@ __global__ void __launch_bounds__(128) k_entry_cut(DeviceScene sc, CameraParams 
 	float tn[PTB_ENTRY_STRIDE];
 	unsigned frozen = 0u;      // bit i: entry i is final
 	int n = 0;
-	k_max = max(1, min(k_max, PTB_ENTRY_STRIDE - 1));
+	k_max = max(1, min(k_max, min(stride, PTB_ENTRY_STRIDE) - 1));
 	// a degenerate frame (zero view / up parallel to view) makes every test pass: the list stays at the root, which is always valid
 	if (sc.n_triangles > 0)
 	{
 		ref[0] = sc.root_ref; tn[0] = 0.0f; n = 1;
 		if (sc.root_ref < 0) frozen = 1u;
 	}
-	for (int iter = 0; iter < 160; iter++)
+	for (int iter = 0; iter < 256; iter++)
 	{
 		// the front-most sub-tree that may still be opened
 		int pick = -1;
@@ -172,6 +171,53 @@ __global__ void __launch_bounds__(128) k_entry_cut(DeviceScene sc, CameraParams 
 	}
 	for (int i = 0; i < n; i++) out[i] = make_int2(ref[i], __float_as_int(tn[i]));
 	out[n] = make_int2(PTB_ENTRY_END, __float_as_int(CUDART_INF_F));
+}
+
+// ------------------------------------------------------------------------------------------
+// Leaf starts for bounce rays (k_extend_persistent<.., UPWALK>, kernels_extend.cuh).
+// A ray that leaves a triangle spends ~18 of its ~22 node visits walking from the root down to the leaf it starts in: at every level
+// the child that contains the origin is "hit" trivially and the only question is whether the SIBLING is hit too.  With one record per
+// child slot — the sibling's box, the sibling's reference and the slot of the node in its own parent — the ray walks UP from its leaf
+// instead: one 32-byte record and one box test per level (a top-down step loads 64 bytes and tests two boxes), the siblings it hits
+// go on the traversal stack (deepest = nearest first) and the search proceeds as usual from the leaf's own triangles.  Every sub-tree
+// of the scene is either the start leaf or the sibling of one of its ancestors, so the search is as exhaustive as one from the root.
+// k_up_level builds the records top-down, one launch per tree level (unused pool slots of the node array are never touched).
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_up_level(const float4* __restrict__ nodes, const float4* __restrict__ tri_isect, const int2* __restrict__ frontier_in,
+	int2* __restrict__ frontier_out, int* __restrict__ level_counts, int level, int capacity, float4* __restrict__ up, int* __restrict__ tri_slot, int n_tris)
+{
+	const int count = min(level_counts[level], capacity);
+	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x)
+	{
+		const int2 f = frontier_in[i];         // node index, the node's slot in its parent
+		const int n = f.x;
+		const float4* np = nodes + (size_t)n * 4;
+		const float4 n0 = np[0], n1 = np[1], n2 = np[2], n3 = np[3];
+		const int child[2] = { __float_as_int(n3.x), __float_as_int(n3.y) };
+		// slot of child 0: its sibling is child 1, and vice versa
+		up[((size_t)n * 2 + 0) * 2 + 0] = make_float4(n1.x, n1.z, n2.z, __int_as_float(child[1]));
+		up[((size_t)n * 2 + 0) * 2 + 1] = make_float4(n1.y, n1.w, n2.w, __int_as_float(f.y));
+		up[((size_t)n * 2 + 1) * 2 + 0] = make_float4(n0.x, n0.z, n2.x, __int_as_float(child[0]));
+		up[((size_t)n * 2 + 1) * 2 + 1] = make_float4(n0.y, n0.w, n2.y, __int_as_float(f.y));
+		for (int s = 0; s < 2; s++)
+		{
+			const int c = child[s];
+			if (c >= 0)
+			{
+				const int pos = atomicAdd(&level_counts[level + 1], 1);
+				if (pos < capacity) frontier_out[pos] = make_int2(c, n * 2 + s);
+			}
+			else if (c != PTB_ENTRY_END)
+			{
+				const int ref = ~c, first = ref >> 3, cnt = (ref & 7) + 1;
+				for (int k = 0; k < cnt; k++)
+				{
+					const int gid = __float_as_int(tri_isect[(size_t)(first + k) * 3].w);
+					if (gid >= 0 && gid < n_tris) tri_slot[gid] = n * 2 + s;
+				}
+			}
+		}
+	}
 }
 
 } // namespace ptb

@@ -385,10 +385,13 @@ __device__ __forceinline__ bool fused_scatter_event(const DeviceScene& sc, const
 struct EntryArgs
 {
 	const int2* cuts;
-	int pixel_count, width, tiles_x;
+	int pixel_count, width, tiles_x, tile_w_shift, tile_h_shift, stride_shift;
 };
 
-template <bool COUNT, int REPS, bool TREELET, bool STAGED, bool FUSED = false, bool ENTRY = false>
+// UPWALK (k_extend_upwalk below; bounce rays): a ray that leaves a triangle (k_shade left its id in ray_o.w) starts at that triangle's
+// leaf and collects the siblings of the leaf's ancestors it hits by walking UP the tree (kernels_entry.cuh: k_up_level) instead of
+// descending from the root.
+template <bool COUNT, int REPS, bool TREELET, bool STAGED, bool FUSED = false, bool ENTRY = false, bool UPWALK = false>
 __device__ __forceinline__ void extend_persistent_body(const DeviceScene& sc, const PathState& st, const int* __restrict__ queue, const int* __restrict__ count_ptr,
 	int* __restrict__ work_counter, unsigned long long* __restrict__ counters, int refill_min, int leaf_min, int node_reps, const float4* s_top, int n_top, float4* s_stage, const FusedArgs* fa = nullptr, float4* s_thr = nullptr, int* s_hist = nullptr,
 	const EntryArgs* ea = nullptr)
@@ -565,11 +568,38 @@ __device__ __forceinline__ void extend_persistent_body(const DeviceScene& sc, co
 					margin2 = 4.8e-7f * fmaxf(fmaxf(fabsf(noidir.x), fabsf(noidir.y)), fabsf(noidir.z));
 					sp = 0;
 					node = sc.n_triangles > 0 ? sc.root_ref : PTB_DONE;
+					if (UPWALK)
+					{
+						const int from = __float_as_int(o4.w);
+						int slot = (from >= 0 && from < sc.n_triangles) ? __ldg(&sc.tri_slot[from]) : -1;
+						if (slot >= 0)
+						{
+							// the leaf itself first, then the siblings of its ancestors, deepest (= nearest) first
+							const float2 ch = __ldg(reinterpret_cast<const float2*>(sc.bvh_nodes + (size_t)(slot >> 1) * 4 + 3));
+							node = __float_as_int((slot & 1) ? ch.y : ch.x);
+							int n = 0;
+							do
+							{
+								const float4 lo = __ldg(sc.up_records + (size_t)slot * 2), hi = __ldg(sc.up_records + (size_t)slot * 2 + 1);
+								if (COUNT) { n_nodes++; ray_nodes++; }
+								const float x0 = fmaf(lo.x, idir.x, noidir.x), x1 = fmaf(hi.x, idir.x, noidir.x);
+								const float y0 = fmaf(lo.y, idir.y, noidir.y), y1 = fmaf(hi.y, idir.y, noidir.y);
+								const float z0 = fmaf(lo.z, idir.z, noidir.z), z1 = fmaf(hi.z, idir.z, noidir.z);
+								const float tmin = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fmaxf(fminf(z0, z1), 0.0f));
+								const float tmax = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fminf(fmaxf(z0, z1), best.t));
+								if (fmaf(tmin, PTB_SLACK_LO / PTB_SLACK_HI, -margin2) <= tmax) { if (n < PTB_STACK_SIZE) stack[n] = __float_as_int(lo.w); n++; }
+								slot = __float_as_int(hi.w);
+							} while (slot >= 0);
+							n = min(n, PTB_STACK_SIZE);
+							for (int a = 0, b = n - 1; a < b; a++, b--) { const int t = stack[a]; stack[a] = stack[b]; stack[b] = t; }
+							sp = n;
+						}
+					}
 					if (ENTRY)
 					{
 						const int pixel = id % ea->pixel_count;
 						const int py = pixel / ea->width, px = pixel - py * ea->width;
-						cut = ((py >> 2) * ea->tiles_x + (px >> 3)) * 16;
+						cut = ((py >> ea->tile_h_shift) * ea->tiles_x + (px >> ea->tile_w_shift)) << ea->stride_shift;
 						const int2 e = __ldg(ea->cuts + cut);
 						node = PTB_DONE;
 						if (e.x != PTB_DONE && __int_as_float(e.y) <= best.t) { node = e.x; cut++; }
@@ -692,6 +722,12 @@ __device__ __forceinline__ void extend_persistent_body(const DeviceScene& sc, co
 			int next = both ? near_c : (h0 ? child0 : (h1 ? child1 : PTB_DONE));
 			if (both) PTB_PUSH(far_c);
 			else if (!(h0 || h1) && sp > 0) PTB_POP(next);
+			if (ENTRY && next == PTB_DONE)
+			{
+				// sub-tree finished inside the phase: go on with the tile's next entry instead of idling until the next vote
+				const int2 e = __ldg(ea->cuts + cut);
+				if (e.x != PTB_DONE && __int_as_float(e.y) <= best.t) { next = e.x; cut++; }
+			}
 			node = next;
 		}
 	}
@@ -720,12 +756,20 @@ __global__ void __launch_bounds__(128, PTB_PERSISTENT_MIN_BLOCKS) k_extend_persi
 	extend_persistent_body<COUNT, REPS, false, false>(sc, st, queue, count_ptr, work_counter, counters, refill_min, leaf_min, node_reps, nullptr, 0, nullptr);
 }
 
-// camera rays (depth 0) started at their tile's entry cut (kernels_entry.cuh)
-template <bool COUNT>
-__global__ void __launch_bounds__(128, PTB_PERSISTENT_MIN_BLOCKS) k_extend_entry(DeviceScene sc, PathState st, const int* __restrict__ queue, const int* __restrict__ count_ptr,
-	int* __restrict__ work_counter, unsigned long long* __restrict__ counters, int refill_min, int leaf_min, EntryArgs ea)
+// bounce rays on the binary tree started at the leaf of the triangle they leave (kernels_entry.cuh: k_up_level)
+template <bool COUNT, int REPS>
+__global__ void __launch_bounds__(128, PTB_PERSISTENT_MIN_BLOCKS) k_extend_upwalk(DeviceScene sc, PathState st, const int* __restrict__ queue, const int* __restrict__ count_ptr,
+	int* __restrict__ work_counter, unsigned long long* __restrict__ counters, int refill_min, int leaf_min, int node_reps)
 {
-	extend_persistent_body<COUNT, 6, false, false, false, true>(sc, st, queue, count_ptr, work_counter, counters, refill_min, leaf_min, 6, nullptr, 0, nullptr, nullptr, nullptr, nullptr, &ea);
+	extend_persistent_body<COUNT, REPS, false, false, false, false, true>(sc, st, queue, count_ptr, work_counter, counters, refill_min, leaf_min, node_reps, nullptr, 0, nullptr);
+}
+
+// camera rays (depth 0) started at their tile's entry cut (kernels_entry.cuh); REPS as in k_extend_persistent
+template <bool COUNT, int REPS>
+__global__ void __launch_bounds__(128, PTB_PERSISTENT_MIN_BLOCKS) k_extend_entry(DeviceScene sc, PathState st, const int* __restrict__ queue, const int* __restrict__ count_ptr,
+	int* __restrict__ work_counter, unsigned long long* __restrict__ counters, int refill_min, int leaf_min, int node_reps, EntryArgs ea)
+{
+	extend_persistent_body<COUNT, REPS, false, false, false, true>(sc, st, queue, count_ptr, work_counter, counters, refill_min, leaf_min, node_reps, nullptr, 0, nullptr, nullptr, nullptr, nullptr, &ea);
 }
 
 // the binary-tree kernel with inline scatter events (option inline_scatter with fused_tree=2: the whole subsurface walk over the binary tree)

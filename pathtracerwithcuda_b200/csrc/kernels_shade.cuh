@@ -171,7 +171,7 @@ __global__ void __launch_bounds__(128, PTB_SHADE_MIN_BLOCKS) k_shade(DeviceScene
 					// per-channel mode: the distance came from ONE channel's sigma_s' picked uniformly; single-sample MIS over the three
 					// channels weights channel c by sigma_c exp(-sigma_c d) / mean_j(sigma_j exp(-sigma_j d)) (1 when the three are equal)
 					if (cfg.sss_mode) not_absorbed = not_absorbed * sss_scatter_weight(sigma_s, scattering_distance);
-					st.ray_o[id] = make_float4(next_o.x, next_o.y, next_o.z, FUSED ? __int_as_float(lead) : 0.0f);
+					st.ray_o[id] = make_float4(next_o.x, next_o.y, next_o.z, FUSED ? __int_as_float(lead) : (NEE ? 0.0f : __int_as_float(-1)));   // not on a surface: the next search starts at the root
 					st.ray_d[id] = make_float4(next_d.x, next_d.y, next_d.z, next_bounce_bound(cfg, sigma_a, sigma_s, seed, pixel_index, depth + 1));
 					oct_key = (next_d.x < 0.0f ? 4 : 0) | (next_d.y < 0.0f ? 2 : 0) | (next_d.z < 0.0f ? 1 : 0);
 					st.throughput[id] = make_float4(not_absorbed.x, not_absorbed.y, not_absorbed.z, t4.w);
@@ -375,7 +375,9 @@ __global__ void __launch_bounds__(128, PTB_SHADE_MIN_BLOCKS) k_shade(DeviceScene
 						}
 					}
 					if (RR && alive && depth >= PTB_RR_START_DEPTH) alive = russian_roulette(not_absorbed, seed, pixel_index, depth, cfg.sampler);
-					st.ray_o[id] = make_float4(next_o.x, next_o.y, next_o.z, FUSED ? __int_as_float(lead) : nee_flag);
+					// ray_o.w: the lead of a path ahead of the loop (FUSED), the NEE flag, or the triangle this segment leaves (the bounce-ray kernel
+					// k_extend_upwalk starts its search at that triangle's leaf; -1 = a sphere)
+					st.ray_o[id] = make_float4(next_o.x, next_o.y, next_o.z, FUSED ? __int_as_float(lead) : (NEE ? nee_flag : __int_as_float(prim >= 0 ? prim : -1)));
 					st.throughput[id] = make_float4(not_absorbed.x, not_absorbed.y, not_absorbed.z, medium_bits);
 				}
 				else

@@ -119,9 +119,13 @@ struct ptb_renderer
 	int extend_persistent = 1;
 	// entry cuts (kernels_entry.cuh): camera rays start at the sub-trees their 8x4 pixel tile's shaft touches instead of at the root.
 	// Same hits bit for bit; the lists depend on camera + geometry only and are rebuilt when either changes.
+	int upwalk = 1;                        // bounce rays on the binary tree start at the leaf of the triangle they leave (kernels_entry.cuh: k_up_level); same hits
 	int entry_cuts = 1;
-	int entry_k = 8;                       // sub-trees per tile (<= PTB_ENTRY_STRIDE - 1)
-	int2* entry_buf = nullptr; size_t entry_buf_tiles = 0;
+	int entry_k = 15;                      // sub-trees per tile (<= PTB_ENTRY_STRIDE - 1)
+	int entry_tile_w = 8, entry_tile_h = 4; // pixels per tile (powers of two); 8x4 = the 32 lanes of a warp under tile_order
+	int tune_refill_u = 20, tune_leaf_u = 6, tune_reps_u = 6;   // voting thresholds of k_extend_upwalk
+	int tune_refill_e = 28, tune_leaf_e = 6, tune_reps_e = 6;   // voting thresholds of k_extend_entry (short searches: refills batched harder than in the other kernels; swept in profiles/r02_experiments.md)
+	int2* entry_buf = nullptr; size_t entry_buf_slots = 0; int entry_stride = 16;
 	bool entry_valid = false;
 	unsigned char entry_key[96] = { 0 };   // camera, resolution, k and geometry version the lists were built for
 	uint64_t geometry_version = 0;
@@ -281,7 +285,7 @@ void free_work_buffers(ptb_renderer* r)
 	cudaFree(r->counters); cudaFree(r->segment_totals);
 	if (r->counts_host) cudaFreeHost(r->counts_host);
 	cudaFree(r->image_sum); cudaFree(r->last_pass); cudaFree(r->image_u8);
-	cudaFree(r->entry_buf); r->entry_buf = nullptr; r->entry_buf_tiles = 0; r->entry_valid = false;
+	cudaFree(r->entry_buf); r->entry_buf = nullptr; r->entry_buf_slots = 0; r->entry_valid = false;
 	cudaFree(r->merged_sum); cudaFree(r->merged_u8); cudaFree(r->pass_count_dev);
 	r->merged_sum = nullptr; r->merged_u8 = nullptr; r->pass_count_dev = nullptr; r->merged_passes = 0;
 	r->counts_host = nullptr; r->counters = nullptr; r->segment_totals = nullptr;
@@ -745,6 +749,36 @@ int upload_geometry(ptb_renderer* r)
 		r->l2_arena = arena; r->l2_arena_bytes = node_bytes + tri_bytes;
 	}
 	apply_l2_window(r);
+	ds.up_records = nullptr; ds.tri_slot = nullptr;
+	if (r->upwalk && ds.bvh_layout == 2 && ds.bvh_nodes && ds.tri_isect && n_tris > 0 && r->bvh_nodes > 0)
+	{
+		// leaf starts of the bounce rays: sibling records per child slot + the slot of every triangle's leaf, built top-down from the root
+		const int n_nodes = (int)r->bvh_nodes;
+		float4* up = nullptr; int* tri_slot = nullptr; int2* frontier[2] = { nullptr, nullptr }; int* level_counts = nullptr;
+		const int levels = PTB_STACK_SIZE + 2;
+		PTB_CUDA(cudaMalloc(&up, (size_t)n_nodes * 64));
+		G->push_back(up);
+		PTB_CUDA(cudaMalloc(&tri_slot, (size_t)n_tris * sizeof(int)));
+		G->push_back(tri_slot);
+		PTB_CUDA(cudaMalloc(&frontier[0], (size_t)n_nodes * sizeof(int2)));
+		PTB_CUDA(cudaMalloc(&frontier[1], (size_t)n_nodes * sizeof(int2)));
+		PTB_CUDA(cudaMalloc(&level_counts, (levels + 1) * sizeof(int)));
+		PTB_CUDA(cudaMemsetAsync(tri_slot, 0xff, (size_t)n_tris * sizeof(int), r->stream));
+		PTB_CUDA(cudaMemsetAsync(level_counts, 0, (levels + 1) * sizeof(int), r->stream));
+		const int2 root_entry = make_int2(ds.root_ref, -1);
+		const int one = 1;
+		PTB_CUDA(cudaMemcpyAsync(frontier[0], &root_entry, sizeof(int2), cudaMemcpyHostToDevice, r->stream));
+		PTB_CUDA(cudaMemcpyAsync(level_counts, &one, sizeof(int), cudaMemcpyHostToDevice, r->stream));
+		PTB_CUDA(cudaStreamSynchronize(r->stream));   // the two host words above are stack variables
+		const int grid = std::max(1, std::min((n_nodes + 127) / 128, r->sm_count * 8));
+		for (int level = 0; level < levels; level++)
+			k_up_level<<<grid, 128, 0, r->stream>>>(ds.bvh_nodes, ds.tri_isect, frontier[level & 1], frontier[(level + 1) & 1], level_counts, level, n_nodes, up, tri_slot, n_tris);
+		PTB_CUDA(cudaStreamSynchronize(r->stream));
+		cudaFree(frontier[0]); cudaFree(frontier[1]); cudaFree(level_counts);
+		PTB_CUDA(cudaGetLastError());
+		ds.up_records = up; ds.tri_slot = tri_slot;
+		r->bvh_bytes += (int64_t)n_nodes * 64 + (int64_t)n_tris * 4;
+	}
 	PTB_CUDA(cudaStreamSynchronize(r->stream));
 	PTB_CUDA(cudaGetLastError());
 	return 0;
@@ -941,20 +975,22 @@ int ensure_entry_cuts(ptb_renderer* r, cudaStream_t stream)
 	memset(key, 0, sizeof(key));
 	static_assert(sizeof(ptb_camera) + 4 * sizeof(int) + sizeof(uint64_t) <= sizeof(key), "entry key too small");
 	memcpy(key, &r->cam, sizeof(ptb_camera));
-	const int ints[4] = { r->cfg.width, r->cfg.height, r->entry_k, 0 };
+	const int ints[4] = { r->cfg.width, r->cfg.height, r->entry_k, r->entry_tile_w * 256 + r->entry_tile_h };
 	memcpy(key + sizeof(ptb_camera), ints, sizeof(ints));
 	memcpy(key + sizeof(ptb_camera) + sizeof(ints), &r->geometry_version, sizeof(uint64_t));
 	if (r->entry_valid && memcmp(key, r->entry_key, sizeof(key)) == 0) return 0;
-	const int tiles_x = (r->cfg.width + PTB_ENTRY_TILE_W - 1) / PTB_ENTRY_TILE_W, tiles_y = (r->cfg.height + PTB_ENTRY_TILE_H - 1) / PTB_ENTRY_TILE_H;
+	const int tiles_x = (r->cfg.width + r->entry_tile_w - 1) / r->entry_tile_w, tiles_y = (r->cfg.height + r->entry_tile_h - 1) / r->entry_tile_h;
 	const size_t n_tiles = (size_t)tiles_x * tiles_y;
 	PTB_CUDA(cudaDeviceSynchronize());
-	if (n_tiles > r->entry_buf_tiles)
+	r->entry_stride = 2;
+	while (r->entry_stride < r->entry_k + 1) r->entry_stride *= 2;
+	if (n_tiles * r->entry_stride > r->entry_buf_slots)
 	{
-		cudaFree(r->entry_buf); r->entry_buf = nullptr; r->entry_buf_tiles = 0;
-		PTB_CUDA(cudaMalloc(&r->entry_buf, n_tiles * PTB_ENTRY_STRIDE * sizeof(int2)));
-		r->entry_buf_tiles = n_tiles;
+		cudaFree(r->entry_buf); r->entry_buf = nullptr; r->entry_buf_slots = 0;
+		PTB_CUDA(cudaMalloc(&r->entry_buf, n_tiles * r->entry_stride * sizeof(int2)));
+		r->entry_buf_slots = n_tiles * r->entry_stride;
 	}
-	k_entry_cut<<<(int)((n_tiles + 127) / 128), 128, 0, stream>>>(r->dscene, camera_params(r->cam), r->cfg.width, r->cfg.height, tiles_x, (int)n_tiles, r->entry_k, r->entry_buf);
+	k_entry_cut<<<(int)((n_tiles + 127) / 128), 128, 0, stream>>>(r->dscene, camera_params(r->cam), r->cfg.width, r->cfg.height, tiles_x, (int)n_tiles, r->entry_k, r->entry_tile_w, r->entry_tile_h, r->entry_stride, r->entry_buf);
 	r->stats.kernel_launches++;
 	PTB_CUDA(cudaGetLastError());
 	PTB_CUDA(cudaStreamSynchronize(stream));
@@ -963,17 +999,22 @@ int ensure_entry_cuts(ptb_renderer* r, cudaStream_t stream)
 	return 0;
 }
 
-void launch_extend(ptb_renderer* r, cudaStream_t stream, size_t items, const PathState& st, const int* queue, const int* count_ptr, int* work_counter, int depth = 0, const FusedArgs* fused = nullptr, bool entry = false)
+void launch_extend(ptb_renderer* r, cudaStream_t stream, size_t items, const PathState& st, const int* queue, const int* count_ptr, int* work_counter, int depth = 0, const FusedArgs* fused = nullptr, bool entry = false, bool upwalk = false)
 {
 	bool wide = r->dscene.bvh_layout == 8;
 	if (entry && !fused && r->entry_valid)
 	{
 		// camera rays: every ray starts at its tile's entry cut
 		EntryArgs ea;
-		ea.cuts = r->entry_buf; ea.pixel_count = r->pixel_count; ea.width = r->cfg.width; ea.tiles_x = (r->cfg.width + PTB_ENTRY_TILE_W - 1) / PTB_ENTRY_TILE_W;
+		ea.cuts = r->entry_buf; ea.pixel_count = r->pixel_count; ea.width = r->cfg.width; ea.tiles_x = (r->cfg.width + r->entry_tile_w - 1) / r->entry_tile_w;
+		ea.tile_w_shift = 0; ea.tile_h_shift = 0; ea.stride_shift = 0;
+		while ((1 << ea.stride_shift) < r->entry_stride) ea.stride_shift++;
+		while ((1 << ea.tile_w_shift) < r->entry_tile_w) ea.tile_w_shift++;
+		while ((1 << ea.tile_h_shift) < r->entry_tile_h) ea.tile_h_shift++;
 		int grid = std::max(1, std::min(r->persistent_grid, (int)((items + 127) / 128)));
-		if (r->count_traversal) k_extend_entry<true><<<grid, 128, 0, stream>>>(r->dscene, st, queue, count_ptr, work_counter, r->counters, r->tune_refill, r->tune_leaf, ea);
-		else k_extend_entry<false><<<grid, 128, 0, stream>>>(r->dscene, st, queue, count_ptr, work_counter, r->counters, r->tune_refill, r->tune_leaf, ea);
+		if (r->count_traversal) k_extend_entry<true, 0><<<grid, 128, 0, stream>>>(r->dscene, st, queue, count_ptr, work_counter, r->counters, r->tune_refill_e, r->tune_leaf_e, r->tune_reps_e, ea);
+		else if (r->tune_reps_e == PTB_NODE_REPS && r->unroll_reps) k_extend_entry<false, PTB_NODE_REPS><<<grid, 128, 0, stream>>>(r->dscene, st, queue, count_ptr, work_counter, r->counters, r->tune_refill_e, r->tune_leaf_e, r->tune_reps_e, ea);
+		else k_extend_entry<false, 0><<<grid, 128, 0, stream>>>(r->dscene, st, queue, count_ptr, work_counter, r->counters, r->tune_refill_e, r->tune_leaf_e, r->tune_reps_e, ea);
 		return;
 	}
 	if (r->dscene.bvh_layout == 2 && r->dscene.bvh8_nodes && r->extend_persistent && depth >= r->hybrid_from_depth)
@@ -1048,6 +1089,14 @@ void launch_extend(ptb_renderer* r, cudaStream_t stream, size_t items, const Pat
 			else k_extend_speculative<false, false><<<grid, 128, 0, stream>>>(r->dscene, st, queue, count_ptr, work_counter, r->counters, r->tune_refill, r->tune_leaf);
 			return;
 		}
+		if (upwalk && r->dscene.up_records)
+		{
+			// bounce rays: start at the leaf of the triangle the ray leaves
+			if (r->count_traversal) k_extend_upwalk<true, 0><<<grid, 128, 0, stream>>>(r->dscene, st, queue, count_ptr, work_counter, r->counters, r->tune_refill_u, r->tune_leaf_u, r->tune_reps_u);
+			else if (r->tune_reps_u == PTB_NODE_REPS && r->unroll_reps) k_extend_upwalk<false, PTB_NODE_REPS><<<grid, 128, 0, stream>>>(r->dscene, st, queue, count_ptr, work_counter, r->counters, r->tune_refill_u, r->tune_leaf_u, r->tune_reps_u);
+			else k_extend_upwalk<false, 0><<<grid, 128, 0, stream>>>(r->dscene, st, queue, count_ptr, work_counter, r->counters, r->tune_refill_u, r->tune_leaf_u, r->tune_reps_u);
+			return;
+		}
 		if (r->count_traversal) k_extend_persistent<true, 0><<<grid, 128, 0, stream>>>(r->dscene, st, queue, count_ptr, work_counter, r->counters, r->tune_refill, r->tune_leaf, r->tune_reps);
 		else if (r->tune_reps == PTB_NODE_REPS && r->unroll_reps) k_extend_persistent<false, PTB_NODE_REPS><<<grid, 128, 0, stream>>>(r->dscene, st, queue, count_ptr, work_counter, r->counters, r->tune_refill, r->tune_leaf, r->tune_reps);
 		else k_extend_persistent<false, 0><<<grid, 128, 0, stream>>>(r->dscene, st, queue, count_ptr, work_counter, r->counters, r->tune_refill, r->tune_leaf, r->tune_reps);
@@ -1092,6 +1141,8 @@ int enqueue_batch(ptb_renderer* r, ptb_renderer::BatchContext& ctx, cudaEvent_t 
 	const int tally_counts = fused ? std::min(fused_from, n_counts) : n_counts;
 	const bool entry = entry_cuts_usable(r) && r->hybrid_from_depth > 0 && !(fused && fused_from <= 0);
 	if (entry && ensure_entry_cuts(r, stream)) return 1;
+	// bounce rays start at the leaf they leave: k_shade<no NEE, not FUSED> leaves the triangle in ray_o.w
+	const bool upwalk = r->upwalk && !fused && !r->nee && r->dscene.bvh_layout == 2 && r->extend_persistent && r->extend_variant == 0 && r->dscene.up_records != nullptr;
 	if (alt) k_generate<true><<<grid_for(r, total, 256, 8), 256, 0, stream>>>(ctx.st, ctx.queue[0], ctx.counts, n_counts, cp, dc, px, n_slots, first_pass, stride, tiles_x);
 	else k_generate<false><<<grid_for(r, total, 256, 8), 256, 0, stream>>>(ctx.st, ctx.queue[0], ctx.counts, n_counts, cp, dc, px, n_slots, first_pass, stride, tiles_x);
 	r->stats.kernel_launches++;
@@ -1107,7 +1158,7 @@ int enqueue_batch(ptb_renderer* r, ptb_renderer::BatchContext& ctx, cudaEvent_t 
 			cudaEventRecord(e0, stream);
 		}
 		fa.loop_depth = depth;
-		launch_extend(r, stream, total, ctx.st, qin, ctx.counts + depth, ctx.counts + n_counts + depth, depth, (fused && depth >= fused_from) ? &fa : nullptr, entry && depth == 0);
+		launch_extend(r, stream, total, ctx.st, qin, ctx.counts + depth, ctx.counts + n_counts + depth, depth, (fused && depth >= fused_from) ? &fa : nullptr, entry && depth == 0, upwalk && depth >= 1);
 		if (prof) cudaEventRecord(e1, stream);
 		int* shadow_count = ctx.counts + 2 * n_counts + depth;
 		const int sgrid = grid_for(r, total, 128, 16);
@@ -1358,8 +1409,12 @@ ptb_renderer* ptb_create(const char* config_json_path, int cuda_device)
 		setup(k_extend_persistent<false, 0>, &r->persistent_grid);
 		setup(k_extend_persistent<false, PTB_NODE_REPS>, nullptr);
 		setup(k_extend_persistent<true, 0>, nullptr);
-		setup(k_extend_entry<false>, nullptr);
-		setup(k_extend_entry<true>, nullptr);
+		setup(k_extend_upwalk<false, PTB_NODE_REPS>, nullptr);
+		setup(k_extend_upwalk<false, 0>, nullptr);
+		setup(k_extend_upwalk<true, 0>, nullptr);
+		setup(k_extend_entry<false, PTB_NODE_REPS>, nullptr);
+		setup(k_extend_entry<false, 0>, nullptr);
+		setup(k_extend_entry<true, 0>, nullptr);
 		setup(k_extend_persistent8<false>, &r->persistent_grid8);
 		setup(k_extend_persistent8<true>, nullptr);
 	}
@@ -2034,8 +2089,23 @@ int ptb_set_option(ptb_renderer* r, const char* key, const char* value)
 	}
 	if (k == "extend_persistent") { r->extend_persistent = atoi(value); return 0; }
 	if (k == "extend_variant") { r->extend_variant = atoi(value); return 0; }
+	if (k == "upwalk") { r->upwalk = atoi(value) != 0; return 0; }      // takes effect at the next scene load / geometry edit
+	if (k == "tune_refill_u") { r->tune_refill_u = atoi(value); return 0; }
+	if (k == "tune_leaf_u") { r->tune_leaf_u = atoi(value); return 0; }
+	if (k == "tune_reps_u") { r->tune_reps_u = std::max(1, atoi(value)); return 0; }
 	if (k == "entry_cuts") { r->entry_cuts = atoi(value) != 0; return 0; }
 	if (k == "entry_k") { r->entry_k = std::max(1, std::min(atoi(value), PTB_ENTRY_STRIDE - 1)); return 0; }
+	if (k == "entry_tile")
+	{
+		// "WxH", powers of two
+		int tw = 0, th = 0;
+		if (sscanf(value, "%dx%d", &tw, &th) != 2 || tw < 1 || th < 1 || tw > 64 || th > 64 || (tw & (tw - 1)) || (th & (th - 1))) { set_error("[Error]entry_tile: WxH with powers of two up to 64"); return 1; }
+		r->entry_tile_w = tw; r->entry_tile_h = th;
+		return 0;
+	}
+	if (k == "tune_refill_e") { r->tune_refill_e = atoi(value); return 0; }
+	if (k == "tune_leaf_e") { r->tune_leaf_e = atoi(value); return 0; }
+	if (k == "tune_reps_e") { r->tune_reps_e = std::max(1, atoi(value)); return 0; }
 	if (k == "tune_refill4") { r->tune_refill4 = atoi(value); return 0; }
 	if (k == "treelet_block") { r->treelet_block = atoi(value); return 0; }
 	if (k == "treelet_nodes") { r->treelet_nodes = atoi(value); return 0; }

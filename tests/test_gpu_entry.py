@@ -57,10 +57,10 @@ def test_entry_cuts_find_the_same_hits_mix(workload_root, label, kw):
     root, w = workload_root("mix", width=100, height=70)      # neither a multiple of 8 nor of 4: partial tiles on both edges
     cam = camera(w, **kw)
     ref, seg0 = render(w, root, cam, 3, entry_cuts=0)
-    for k in (1, 4, 8, 15):
-        img, seg = render(w, root, cam, 3, entry_cuts=1, entry_k=k)
-        assert np.array_equal(ref.view(np.uint32), img.view(np.uint32)), (label, k)
-        assert seg == seg0, (label, k)
+    for k, tile in ((1, "8x4"), (4, "8x4"), (15, "8x4"), (31, "8x4"), (8, "4x4"), (31, "2x2"), (6, "16x8"), (15, "64x1")):
+        img, seg = render(w, root, cam, 3, entry_cuts=1, entry_k=k, entry_tile=tile)
+        assert np.array_equal(ref.view(np.uint32), img.view(np.uint32)), (label, k, tile)
+        assert seg == seg0, (label, k, tile)
 
 
 @pytest.mark.parametrize("name,size,scale", [("c2", (320, 180), 0.1), ("c3", (256, 144), 0.05), ("c4", (192, 108), 0.03), ("c1", (96, 96), 1.0)])
@@ -83,6 +83,24 @@ def test_entry_cuts_find_the_same_hits_baseline_configs(workload_root, name, siz
         r.render(2)
     assert np.array_equal(r0.image_f32().view(np.uint32), r1.image_f32().view(np.uint32))
     r0.close(); r1.close()
+
+
+@pytest.mark.parametrize("name,size,scale", [("c2", (320, 180), 0.1), ("c3", (256, 144), 0.05), ("c1", (96, 96), 1.0), ("mix", (100, 70), 1.0)])
+def test_leaf_starts_of_bounce_rays_find_the_same_hits(workload_root, name, size, scale):
+    """upwalk (k_extend_upwalk): a bounce ray that leaves a triangle starts its search at that triangle's leaf and walks UP through the
+    siblings of the leaf's ancestors; images and per-depth segment counts must equal a search from the root bit for bit — with the binary
+    tree used for the first bounce only (the default hybrid) and for every bounce (hybrid_from_depth=99)."""
+    kw = dict(width=size[0], height=size[1])
+    if scale != 1.0:
+        kw["tri_scale"] = scale
+    root, w = workload_root(name, **kw)
+    cam = camera(w)
+    ref, seg0 = render(w, root, cam, 3, upwalk=0, entry_cuts=0)
+    for opts in (dict(upwalk=1, entry_cuts=0), dict(upwalk=1), dict(upwalk=1, hybrid_from_depth=99), dict(upwalk=1, hybrid_from_depth=99, bvh_builder="host_sah"),
+                 dict(upwalk=1, bvh_max_leaf=1), dict(upwalk=1, hybrid_from_depth=99, tune_refill_u=1, tune_leaf_u=1)):
+        img, seg = render(w, root, cam, 3, **opts)
+        assert np.array_equal(ref.view(np.uint32), img.view(np.uint32)), opts
+        assert seg == seg0, opts
 
 
 def test_entry_cuts_follow_camera_and_geometry_edits(workload_root):

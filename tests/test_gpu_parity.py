@@ -234,8 +234,8 @@ def test_bvh_layouts_agree(workload_root):
     assert np.array_equal(res[2][1].view(np.uint32), res[8][1].view(np.uint32))
     assert np.array_equal(res[2][2].view(np.uint32), res[8][2].view(np.uint32))
     assert np.array_equal(res[2][3].view(np.uint32), res[8][3].view(np.uint32))
-    # the wide tree visits far fewer nodes per ray
-    assert res[8][4]["all_nodes"] < 0.6 * res[2][4]["all_nodes"]
+    # the wide tree visits fewer nodes per ray (the binary side already starts camera rays at their tile's entry cut)
+    assert res[8][4]["all_nodes"] < 0.8 * res[2][4]["all_nodes"]
     assert res[8][4]["nodes_visited"] == 0 and res[2][4]["wide_nodes_visited"] > 0      # layout 2 is hybrid: deep bounces use the wide tree
 
 
@@ -270,6 +270,7 @@ def test_scheduling_options_do_not_change_the_image(workload_root):
     for opts in (dict(), dict(tile_order=0), dict(sort_by_material=1), dict(sort_by_material=1, tile_order=0, streams_in_flight=1),
                  dict(extend_persistent=0), dict(bvh_max_leaf=2, bvh_intersect_cost=1.5), dict(bvh_hybrid=0), dict(hybrid_from_depth=0),
                  dict(bvh_layout=8), dict(octant_order=1), dict(extend_variant=1), dict(extend_variant=2), dict(extend_variant=3), dict(extend_variant=3, treelet_block=512, treelet_nodes=100), dict(extend_variant=4), dict(extend_variant=4, tune_refill4=1), dict(l2_persist=1), dict(inline_scatter=0), dict(inline_scatter=0, hybrid_from_depth=0), dict(tune_scatter=1), dict(tune_scatter=32, hybrid_from_depth=1), dict(fused_from_depth=0), dict(fused_from_depth=1, hybrid_from_depth=99), dict(fused_from_depth=3),
+                 dict(upwalk=0), dict(upwalk=0, hybrid_from_depth=99), dict(upwalk=1, hybrid_from_depth=99), dict(upwalk=1, hybrid_from_depth=99, inline_scatter=0), dict(upwalk=1, hybrid_from_depth=3, tile_order=0),
                  dict(entry_cuts=0), dict(entry_k=1), dict(entry_k=15), dict(entry_cuts=0, tile_order=0), dict(entry_k=3, tile_order=0)):
         r = gpu_renderer(w, root, **opts)
         r.set_camera(ptb.default_camera(w["width"], w["height"], w["aperture"], w["focal"]))
