@@ -74,6 +74,14 @@ struct DeviceConfig
 // hit.w of a path that ended inside the closest-hit kernel (option inline_scatter): neither a triangle (>= 0), a miss (-1) nor a sphere (<= -2 small)
 #define PTB_PRIM_DEAD ((int)0x80000001)
 
+// ray_o.w (every estimator but "nee", which keeps a flag there): bits 0-7 = bounces the path is ahead of the loop depth (its lead; FUSED
+// instantiations, option inline_scatter, else 0), bits 8-31 = 1 + the triangle the segment leaves / the current walk entered through
+// (0 = none): the bounce-ray kernels start their searches at that triangle's leaf (k_extend_upwalk, k_extend_persistent_fused<.., UPWALK>).
+// Needs MaxDepth <= 255 for FUSED; triangles beyond 2^23 - 2 read "none".
+#define PTB_LEAD_OF(w) ((w) & 0xff)
+#define PTB_FROM_BITS_OF(w) ((w) & ~0xff)
+#define PTB_FROM_BITS(prim) (((prim) >= 0 && (prim) < (1 << 23) - 2 ? (prim) + 1 : 0) << 8)
+
 // SoA path state, indexed by path id = slot * pixel_count + pixel.
 struct PathState
 {

@@ -388,13 +388,41 @@ struct EntryArgs
 	int pixel_count, width, tiles_x, tile_w_shift, tile_h_shift, stride_shift;
 };
 
+// The leaf start of a bounce ray (UPWALK): `slot` = child slot (node * 2 + side) of the leaf the search starts at.  Sets `node` to that
+// leaf and leaves on the stack the siblings of the leaf's ancestors the ray's box test accepts, deepest (= nearest) on top.  Every
+// sub-tree of the scene is the start leaf or one of those siblings, so the search is exhaustive whatever leaf it starts at; a leaf near
+// the ray's origin makes it cheap (one 32-byte record and one box test per level instead of a 64-byte node and two).
+template <bool COUNT>
+__device__ __forceinline__ void upwalk_start(const DeviceScene& sc, int slot, float3 idir, float3 noidir, float margin2, float t_max,
+	int* stack, int& sp, int& node, unsigned& n_nodes, unsigned& ray_nodes)
+{
+	const float2 ch = __ldg(reinterpret_cast<const float2*>(sc.bvh_nodes + (size_t)(slot >> 1) * 4 + 3));
+	node = __float_as_int((slot & 1) ? ch.y : ch.x);
+	int n = 0;
+	do
+	{
+		const float4 lo = __ldg(sc.up_records + (size_t)slot * 2), hi = __ldg(sc.up_records + (size_t)slot * 2 + 1);
+		if (COUNT) { n_nodes++; ray_nodes++; }
+		const float x0 = fmaf(lo.x, idir.x, noidir.x), x1 = fmaf(hi.x, idir.x, noidir.x);
+		const float y0 = fmaf(lo.y, idir.y, noidir.y), y1 = fmaf(hi.y, idir.y, noidir.y);
+		const float z0 = fmaf(lo.z, idir.z, noidir.z), z1 = fmaf(hi.z, idir.z, noidir.z);
+		const float tmin = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fmaxf(fminf(z0, z1), 0.0f));
+		const float tmax = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fminf(fmaxf(z0, z1), t_max));
+		if (fmaf(tmin, PTB_SLACK_LO / PTB_SLACK_HI, -margin2) <= tmax) { if (n < PTB_STACK_SIZE) stack[n] = __float_as_int(lo.w); n++; }
+		slot = __float_as_int(hi.w);
+	} while (slot >= 0);
+	n = min(n, PTB_STACK_SIZE);
+	for (int a = 0, b = n - 1; a < b; a++, b--) { const int t = stack[a]; stack[a] = stack[b]; stack[b] = t; }
+	sp = n;
+}
+
 // UPWALK (k_extend_upwalk below; bounce rays): a ray that leaves a triangle (k_shade left its id in ray_o.w) starts at that triangle's
 // leaf and collects the siblings of the leaf's ancestors it hits by walking UP the tree (kernels_entry.cuh: k_up_level) instead of
 // descending from the root.
 template <bool COUNT, int REPS, bool TREELET, bool STAGED, bool FUSED = false, bool ENTRY = false, bool UPWALK = false>
 __device__ __forceinline__ void extend_persistent_body(const DeviceScene& sc, const PathState& st, const int* __restrict__ queue, const int* __restrict__ count_ptr,
 	int* __restrict__ work_counter, unsigned long long* __restrict__ counters, int refill_min, int leaf_min, int node_reps, const float4* s_top, int n_top, float4* s_stage, const FusedArgs* fa = nullptr, float4* s_thr = nullptr, int* s_hist = nullptr,
-	const EntryArgs* ea = nullptr)
+	const EntryArgs* ea = nullptr, int* s_from = nullptr)
 {
 	const int count = *count_ptr;
 	const unsigned lane = threadIdx.x & 31u;
@@ -423,6 +451,7 @@ __device__ __forceinline__ void extend_persistent_body(const DeviceScene& sc, co
 	int lead = 0;
 	bool at_scatter = false, thr_cached = false;
 	int cut = 0;                 // ENTRY: index of the next entry of the lane's tile list
+	int start_slot = -1;         // UPWALK: child slot of the leaf the lane's searches start at (FUSED: kept across the path's scatter events)
 
 	// Every iteration starts with full-mask votes, so all 32 lanes are converged when a phase
 	// begins; a phase is executed by the lanes in that state, the others are predicated off.
@@ -440,7 +469,7 @@ __device__ __forceinline__ void extend_persistent_body(const DeviceScene& sc, co
 		{
 			if (FUSED && thr_cached)
 			{
-				st.ray_o[id] = make_float4(o.x, o.y, o.z, __int_as_float(lead));
+				st.ray_o[id] = make_float4(o.x, o.y, o.z, __int_as_float(lead | s_from[threadIdx.x]));
 				st.ray_d[id] = make_float4(d.x, d.y, d.z, 0.0f);
 				st.throughput[id] = s_thr[threadIdx.x];
 			}
@@ -547,7 +576,7 @@ __device__ __forceinline__ void extend_persistent_body(const DeviceScene& sc, co
 					d = make_float3(d4.x, d4.y, d4.z);
 					best.t = d4.w; best.t1 = CUDART_INF_F; best.t2 = CUDART_INF_F; best.prim = -1;   // d4.w: free-flight bound (next_bounce_bound)
 					best_tri = 0x7fffffff;
-					if (FUSED) { lead = __float_as_int(o4.w); at_scatter = false; thr_cached = false; atomicAdd(&s_hist[min(fa->loop_depth + lead, PTB_FUSED_HIST - 1)], 1); }
+					if (FUSED) { lead = PTB_LEAD_OF(__float_as_int(o4.w)); s_from[threadIdx.x] = PTB_FROM_BITS_OF(__float_as_int(o4.w)); at_scatter = false; thr_cached = false; atomicAdd(&s_hist[min(fa->loop_depth + lead, PTB_FUSED_HIST - 1)], 1); }
 					for (int s = 0; s < sc.n_spheres; s++)
 					{
 						const float4 sph = __ldg(&sc.spheres[s]);
@@ -570,30 +599,10 @@ __device__ __forceinline__ void extend_persistent_body(const DeviceScene& sc, co
 					node = sc.n_triangles > 0 ? sc.root_ref : PTB_DONE;
 					if (UPWALK)
 					{
-						const int from = __float_as_int(o4.w);
-						int slot = (from >= 0 && from < sc.n_triangles) ? __ldg(&sc.tri_slot[from]) : -1;
-						if (slot >= 0)
-						{
-							// the leaf itself first, then the siblings of its ancestors, deepest (= nearest) first
-							const float2 ch = __ldg(reinterpret_cast<const float2*>(sc.bvh_nodes + (size_t)(slot >> 1) * 4 + 3));
-							node = __float_as_int((slot & 1) ? ch.y : ch.x);
-							int n = 0;
-							do
-							{
-								const float4 lo = __ldg(sc.up_records + (size_t)slot * 2), hi = __ldg(sc.up_records + (size_t)slot * 2 + 1);
-								if (COUNT) { n_nodes++; ray_nodes++; }
-								const float x0 = fmaf(lo.x, idir.x, noidir.x), x1 = fmaf(hi.x, idir.x, noidir.x);
-								const float y0 = fmaf(lo.y, idir.y, noidir.y), y1 = fmaf(hi.y, idir.y, noidir.y);
-								const float z0 = fmaf(lo.z, idir.z, noidir.z), z1 = fmaf(hi.z, idir.z, noidir.z);
-								const float tmin = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fmaxf(fminf(z0, z1), 0.0f));
-								const float tmax = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fminf(fmaxf(z0, z1), best.t));
-								if (fmaf(tmin, PTB_SLACK_LO / PTB_SLACK_HI, -margin2) <= tmax) { if (n < PTB_STACK_SIZE) stack[n] = __float_as_int(lo.w); n++; }
-								slot = __float_as_int(hi.w);
-							} while (slot >= 0);
-							n = min(n, PTB_STACK_SIZE);
-							for (int a = 0, b = n - 1; a < b; a++, b--) { const int t = stack[a]; stack[a] = stack[b]; stack[b] = t; }
-							sp = n;
-						}
+						// the triangle this segment leaves (k_shade: ray_o.w, kernels.cuh: PTB_FROM_BITS)
+						const int from = (PTB_FROM_BITS_OF(__float_as_int(o4.w)) >> 8) - 1;
+						start_slot = (from >= 0 && from < sc.n_triangles) ? __ldg(&sc.tri_slot[from]) : -1;
+						if (start_slot >= 0) upwalk_start<COUNT>(sc, start_slot, idir, noidir, margin2, best.t, stack, sp, node, n_nodes, ray_nodes);
 					}
 					if (ENTRY)
 					{
@@ -640,6 +649,8 @@ __device__ __forceinline__ void extend_persistent_body(const DeviceScene& sc, co
 					margin2 = 4.8e-7f * fmaxf(fmaxf(fabsf(noidir.x), fabsf(noidir.y)), fabsf(noidir.z));
 					sp = 0;
 					node = sc.n_triangles > 0 ? sc.root_ref : PTB_DONE;
+					// the walk stays near the surface it entered through: the next search starts at the same leaf
+					if (UPWALK && start_slot >= 0) upwalk_start<COUNT>(sc, start_slot, idir, noidir, margin2, best.t, stack, sp, node, n_nodes, ray_nodes);
 				}
 			}
 			continue;
@@ -773,15 +784,16 @@ __global__ void __launch_bounds__(128, PTB_PERSISTENT_MIN_BLOCKS) k_extend_entry
 }
 
 // the binary-tree kernel with inline scatter events (option inline_scatter with fused_tree=2: the whole subsurface walk over the binary tree)
-template <bool COUNT>
+template <bool COUNT, bool UPWALK = false>
 __global__ void __launch_bounds__(128, PTB_PERSISTENT_MIN_BLOCKS) k_extend_persistent_fused(DeviceScene sc, PathState st, const int* __restrict__ queue, const int* __restrict__ count_ptr,
 	int* __restrict__ work_counter, unsigned long long* __restrict__ counters, int refill_min, int leaf_min, FusedArgs fa)
 {
 	__shared__ int s_hist[PTB_FUSED_HIST];
 	__shared__ float4 s_thr[128];
+	__shared__ int s_from[128];
 	if (threadIdx.x < PTB_FUSED_HIST) s_hist[threadIdx.x] = 0;
 	__syncthreads();
-	extend_persistent_body<COUNT, 6, false, false, true>(sc, st, queue, count_ptr, work_counter, counters, refill_min, leaf_min, 6, nullptr, 0, nullptr, &fa, s_thr, s_hist);
+	extend_persistent_body<COUNT, 6, false, false, true, false, UPWALK>(sc, st, queue, count_ptr, work_counter, counters, refill_min, leaf_min, 6, nullptr, 0, nullptr, &fa, s_thr, s_hist, nullptr, s_from);
 	__syncthreads();
 	if (threadIdx.x < PTB_FUSED_HIST && s_hist[threadIdx.x])
 		atomicAdd(&fa.depth_segments[min((int)threadIdx.x, fa.n_depth_slots - 1)], (unsigned long long)s_hist[threadIdx.x]);
@@ -1012,6 +1024,7 @@ __global__ void __launch_bounds__(128, PTB_PERSISTENT_MIN_BLOCKS8) k_extend_pers
 	// FUSED: throughput + medium index of the lane's path while it scatters (loaded at its first event here, written back when the path
 	// leaves the kernel alive): every later event costs shared-memory latency instead of a scattered 16-byte global load and store
 	__shared__ float4 s_thr[FUSED ? 128 : 1];
+	__shared__ int s_from[FUSED ? 128 : 1];     // the "segment leaves triangle" bits of ray_o.w (kernels.cuh: PTB_FROM_BITS_OF), carried through unchanged
 	bool thr_cached = false;
 	if (FUSED)
 	{
@@ -1033,7 +1046,7 @@ __global__ void __launch_bounds__(128, PTB_PERSISTENT_MIN_BLOCKS8) k_extend_pers
 				{
 					// the path scattered here: the ray in memory is the one it had when it entered (k_shade needs the segment that found the
 					// surface) and its throughput lives in shared memory
-					st.ray_o[id] = make_float4(o.x, o.y, o.z, __int_as_float(lead));
+					st.ray_o[id] = make_float4(o.x, o.y, o.z, __int_as_float(lead | s_from[threadIdx.x]));
 					st.ray_d[id] = make_float4(d.x, d.y, d.z, 0.0f);
 					st.throughput[id] = s_thr[threadIdx.x];
 				}
@@ -1066,7 +1079,7 @@ __global__ void __launch_bounds__(128, PTB_PERSISTENT_MIN_BLOCKS8) k_extend_pers
 					d = make_float3(d4.x, d4.y, d4.z);
 					best.t = d4.w; best.t1 = CUDART_INF_F; best.t2 = CUDART_INF_F; best.prim = -1;
 					best_tri = 0x7fffffff;
-					if (FUSED) { lead = __float_as_int(o4.w); at_scatter = false; thr_cached = false; atomicAdd(&s_hist[min(fa.loop_depth + lead, PTB_FUSED_HIST - 1)], 1); }
+					if (FUSED) { lead = PTB_LEAD_OF(__float_as_int(o4.w)); s_from[threadIdx.x] = PTB_FROM_BITS_OF(__float_as_int(o4.w)); at_scatter = false; thr_cached = false; atomicAdd(&s_hist[min(fa.loop_depth + lead, PTB_FUSED_HIST - 1)], 1); }
 					for (int s = 0; s < sc.n_spheres; s++)
 					{
 						const float4 sph = __ldg(&sc.spheres[s]);

@@ -132,7 +132,7 @@ __global__ void __launch_bounds__(128, PTB_SHADE_MIN_BLOCKS) k_shade(DeviceScene
 			// at depth 0 the throughput is (1, 1, 1) in air by construction (init_data_kernel :275-297): k_generate does not
 			// write it and it is not read here
 			float4 o4 = st.ray_o[id], d4 = st.ray_d[id], h4 = st.hit[id];
-			const int lead = FUSED ? __float_as_int(o4.w) : 0;
+			const int lead = FUSED ? PTB_LEAD_OF(__float_as_int(o4.w)) : 0;
 			path_lead = lead;
 			const int depth = loop_depth + lead;
 			float4 t4 = depth == 0 ? make_float4(1.0f, 1.0f, 1.0f, __int_as_float(-1)) : st.throughput[id];
@@ -171,7 +171,7 @@ __global__ void __launch_bounds__(128, PTB_SHADE_MIN_BLOCKS) k_shade(DeviceScene
 					// per-channel mode: the distance came from ONE channel's sigma_s' picked uniformly; single-sample MIS over the three
 					// channels weights channel c by sigma_c exp(-sigma_c d) / mean_j(sigma_j exp(-sigma_j d)) (1 when the three are equal)
 					if (cfg.sss_mode) not_absorbed = not_absorbed * sss_scatter_weight(sigma_s, scattering_distance);
-					st.ray_o[id] = make_float4(next_o.x, next_o.y, next_o.z, FUSED ? __int_as_float(lead) : (NEE ? 0.0f : __int_as_float(-1)));   // not on a surface: the next search starts at the root
+					st.ray_o[id] = make_float4(next_o.x, next_o.y, next_o.z, NEE ? 0.0f : __int_as_float(lead | PTB_FROM_BITS_OF(__float_as_int(o4.w))));   // not on a surface: the walk keeps the triangle it entered through as the start of its searches
 					st.ray_d[id] = make_float4(next_d.x, next_d.y, next_d.z, next_bounce_bound(cfg, sigma_a, sigma_s, seed, pixel_index, depth + 1));
 					oct_key = (next_d.x < 0.0f ? 4 : 0) | (next_d.y < 0.0f ? 2 : 0) | (next_d.z < 0.0f ? 1 : 0);
 					st.throughput[id] = make_float4(not_absorbed.x, not_absorbed.y, not_absorbed.z, t4.w);
@@ -375,9 +375,9 @@ __global__ void __launch_bounds__(128, PTB_SHADE_MIN_BLOCKS) k_shade(DeviceScene
 						}
 					}
 					if (RR && alive && depth >= PTB_RR_START_DEPTH) alive = russian_roulette(not_absorbed, seed, pixel_index, depth, cfg.sampler);
-					// ray_o.w: the lead of a path ahead of the loop (FUSED), the NEE flag, or the triangle this segment leaves (the bounce-ray kernel
-					// k_extend_upwalk starts its search at that triangle's leaf; -1 = a sphere)
-					st.ray_o[id] = make_float4(next_o.x, next_o.y, next_o.z, FUSED ? __int_as_float(lead) : (NEE ? nee_flag : __int_as_float(prim >= 0 ? prim : -1)));
+					// ray_o.w: the NEE flag, or (kernels.cuh: PTB_FROM_BITS) the lead of a path ahead of the loop (FUSED only) + the triangle this
+					// segment leaves — the bounce-ray kernels start their search at that triangle's leaf (none for a sphere)
+					st.ray_o[id] = make_float4(next_o.x, next_o.y, next_o.z, NEE ? nee_flag : __int_as_float(lead | PTB_FROM_BITS(prim)));
 					st.throughput[id] = make_float4(not_absorbed.x, not_absorbed.y, not_absorbed.z, medium_bits);
 				}
 				else

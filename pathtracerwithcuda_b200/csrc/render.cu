@@ -119,10 +119,13 @@ struct ptb_renderer
 	int extend_persistent = 1;
 	// entry cuts (kernels_entry.cuh): camera rays start at the sub-trees their 8x4 pixel tile's shaft touches instead of at the root.
 	// Same hits bit for bit; the lists depend on camera + geometry only and are rebuilt when either changes.
+	int upwalk_min_nodes = 64;
 	int upwalk = 1;                        // bounce rays on the binary tree start at the leaf of the triangle they leave (kernels_entry.cuh: k_up_level); same hits
 	int entry_cuts = 1;
 	int entry_k = 15;                      // sub-trees per tile (<= PTB_ENTRY_STRIDE - 1)
 	int entry_tile_w = 8, entry_tile_h = 4; // pixels per tile (powers of two); 8x4 = the 32 lanes of a warp under tile_order
+	int fused_upwalk = 0;                  // scattering media: the whole walk on the binary tree, every search started at the leaf of the triangle the path entered through (measured SLOWER than the wide tree from the root: c4 807 -> 716-746 Msamples/s, profiles/r02_experiments.md)
+	int tune_refill_f = 20, tune_leaf_f = 6;   // voting thresholds of k_extend_persistent_fused<.., UPWALK>
 	int tune_refill_u = 20, tune_leaf_u = 6, tune_reps_u = 6;   // voting thresholds of k_extend_upwalk
 	int tune_refill_e = 28, tune_leaf_e = 6, tune_reps_e = 6;   // voting thresholds of k_extend_entry (short searches: refills batched harder than in the other kernels; swept in profiles/r02_experiments.md)
 	int2* entry_buf = nullptr; size_t entry_buf_slots = 0; int entry_stride = 16;
@@ -750,7 +753,7 @@ int upload_geometry(ptb_renderer* r)
 	}
 	apply_l2_window(r);
 	ds.up_records = nullptr; ds.tri_slot = nullptr;
-	if (r->upwalk && ds.bvh_layout == 2 && ds.bvh_nodes && ds.tri_isect && n_tris > 0 && r->bvh_nodes > 0)
+	if (r->upwalk && ds.bvh_layout == 2 && ds.bvh_nodes && ds.tri_isect && n_tris > 0 && r->bvh_nodes >= r->upwalk_min_nodes)   // a tree of a few nodes is as quick from the root (c1: -1 %)
 	{
 		// leaf starts of the bounce rays: sibling records per child slot + the slot of every triangle's leaf, built top-down from the root
 		const int n_nodes = (int)r->bvh_nodes;
@@ -999,9 +1002,10 @@ int ensure_entry_cuts(ptb_renderer* r, cudaStream_t stream)
 	return 0;
 }
 
-void launch_extend(ptb_renderer* r, cudaStream_t stream, size_t items, const PathState& st, const int* queue, const int* count_ptr, int* work_counter, int depth = 0, const FusedArgs* fused = nullptr, bool entry = false, bool upwalk = false)
+void launch_extend(ptb_renderer* r, cudaStream_t stream, size_t items, const PathState& st, const int* queue, const int* count_ptr, int* work_counter, int depth = 0, const FusedArgs* fused = nullptr, bool entry = false, bool upwalk = false, int hybrid_from = -1)
 {
 	bool wide = r->dscene.bvh_layout == 8;
+	if (hybrid_from < 0) hybrid_from = r->hybrid_from_depth;
 	if (entry && !fused && r->entry_valid)
 	{
 		// camera rays: every ray starts at its tile's entry cut
@@ -1017,7 +1021,7 @@ void launch_extend(ptb_renderer* r, cudaStream_t stream, size_t items, const Pat
 		else k_extend_entry<false, 0><<<grid, 128, 0, stream>>>(r->dscene, st, queue, count_ptr, work_counter, r->counters, r->tune_refill_e, r->tune_leaf_e, r->tune_reps_e, ea);
 		return;
 	}
-	if (r->dscene.bvh_layout == 2 && r->dscene.bvh8_nodes && r->extend_persistent && depth >= r->hybrid_from_depth)
+	if (r->dscene.bvh_layout == 2 && r->dscene.bvh8_nodes && r->extend_persistent && depth >= hybrid_from)
 	{
 		// hybrid: bounce rays over the compressed wide tree
 		DeviceScene sc8 = r->dscene;
@@ -1051,7 +1055,13 @@ void launch_extend(ptb_renderer* r, cudaStream_t stream, size_t items, const Pat
 		if (fused)
 		{
 			// inline scatter events over the binary tree (fused_from_depth <= depth < hybrid_from_depth)
-			if (r->count_traversal) k_extend_persistent_fused<true><<<grid, 128, 0, stream>>>(r->dscene, st, queue, count_ptr, work_counter, r->counters, r->tune_refill, r->tune_leaf, *fused);
+			if (upwalk && r->dscene.up_records)
+			{
+				// ... every search of the walk started at the leaf of the triangle the path entered the medium through
+				if (r->count_traversal) k_extend_persistent_fused<true, true><<<grid, 128, 0, stream>>>(r->dscene, st, queue, count_ptr, work_counter, r->counters, r->tune_refill_f, r->tune_leaf_f, *fused);
+				else k_extend_persistent_fused<false, true><<<grid, 128, 0, stream>>>(r->dscene, st, queue, count_ptr, work_counter, r->counters, r->tune_refill_f, r->tune_leaf_f, *fused);
+			}
+			else if (r->count_traversal) k_extend_persistent_fused<true><<<grid, 128, 0, stream>>>(r->dscene, st, queue, count_ptr, work_counter, r->counters, r->tune_refill, r->tune_leaf, *fused);
 			else k_extend_persistent_fused<false><<<grid, 128, 0, stream>>>(r->dscene, st, queue, count_ptr, work_counter, r->counters, r->tune_refill, r->tune_leaf, *fused);
 			return;
 		}
@@ -1130,19 +1140,25 @@ int enqueue_batch(ptb_renderer* r, ptb_renderer::BatchContext& ctx, cudaEvent_t 
 	const int tiles_x = (r->tile_order && r->cfg.width % 8 == 0 && r->cfg.height % 4 == 0) ? r->cfg.width / 8 : 0;
 	const bool alt = r->sampler != 0 || r->sss_mode != 0;   // estimator options: the ALT instantiations of k_generate / k_shade
 	// inline scatter events (kernels_extend.cuh: k_extend_persistent8<.., FUSED>): the reference's estimator only, and only where a medium exists
-	const bool fused = r->inline_scatter && (r->scene_has_medium || r->cfg.air_reduced_scattering_coef.x > 0.0f) && !alt && !r->nee && !r->russian_roulette && !r->sort_by_material && r->extend_persistent && r->extend_variant == 0;
+	const bool fused = r->inline_scatter && r->cfg.max_tracer_depth <= 255 && (r->scene_has_medium || r->cfg.air_reduced_scattering_coef.x > 0.0f) && !alt && !r->nee && !r->russian_roulette && !r->sort_by_material && r->extend_persistent && r->extend_variant == 0;
 	FusedArgs fa;
 	fa.cfg = dc; fa.pixel_count = px; fa.first_pass = first_pass; fa.pass_stride = stride; fa.scatter_min = r->tune_scatter;
 	fa.depth_segments = r->segment_totals; fa.n_depth_slots = n_counts;
 	// loop depths traced by the fused kernel tally their own searches per actual depth; the queue sizes only count below that
 	// first loop depth whose closest-hit launch scatters inline: fused_from_depth (default: where the wide tree takes over; lower values run
 	// the walk on the binary-tree kernel until then)
-	const int fused_from = r->fused_from_depth >= 0 ? r->fused_from_depth : (r->dscene.bvh_layout == 8 ? 0 : std::max(r->hybrid_from_depth, 0));
+	// scattering media with leaf starts (fused_upwalk): every bounce stays on the binary tree — a search that starts at the leaf of the
+	// triangle the walk entered through costs one 32-byte record per tree level and few node visits, less than descending the wide tree
+	// from the root for a segment one mean free path long
+	const bool have_up = r->upwalk && !r->nee && r->dscene.bvh_layout == 2 && r->extend_persistent && r->extend_variant == 0 && r->dscene.up_records != nullptr;
+	const bool fused_up = fused && have_up && r->fused_upwalk;
+	const int hybrid_from = fused_up ? 0x7fffffff : r->hybrid_from_depth;
+	const int fused_from = r->fused_from_depth >= 0 ? r->fused_from_depth : (fused_up ? (r->cfg.air_reduced_scattering_coef.x > 0.0f ? 0 : 1) : (r->dscene.bvh_layout == 8 ? 0 : std::max(r->hybrid_from_depth, 0)));
 	const int tally_counts = fused ? std::min(fused_from, n_counts) : n_counts;
-	const bool entry = entry_cuts_usable(r) && r->hybrid_from_depth > 0 && !(fused && fused_from <= 0);
+	const bool entry = entry_cuts_usable(r) && hybrid_from > 0 && !(fused && fused_from <= 0);
 	if (entry && ensure_entry_cuts(r, stream)) return 1;
-	// bounce rays start at the leaf they leave: k_shade<no NEE, not FUSED> leaves the triangle in ray_o.w
-	const bool upwalk = r->upwalk && !fused && !r->nee && r->dscene.bvh_layout == 2 && r->extend_persistent && r->extend_variant == 0 && r->dscene.up_records != nullptr;
+	// bounce rays start at the leaf they leave: k_shade leaves the triangle in ray_o.w (kernels.cuh: PTB_FROM_BITS)
+	const bool upwalk = have_up;
 	if (alt) k_generate<true><<<grid_for(r, total, 256, 8), 256, 0, stream>>>(ctx.st, ctx.queue[0], ctx.counts, n_counts, cp, dc, px, n_slots, first_pass, stride, tiles_x);
 	else k_generate<false><<<grid_for(r, total, 256, 8), 256, 0, stream>>>(ctx.st, ctx.queue[0], ctx.counts, n_counts, cp, dc, px, n_slots, first_pass, stride, tiles_x);
 	r->stats.kernel_launches++;
@@ -1158,7 +1174,7 @@ int enqueue_batch(ptb_renderer* r, ptb_renderer::BatchContext& ctx, cudaEvent_t 
 			cudaEventRecord(e0, stream);
 		}
 		fa.loop_depth = depth;
-		launch_extend(r, stream, total, ctx.st, qin, ctx.counts + depth, ctx.counts + n_counts + depth, depth, (fused && depth >= fused_from) ? &fa : nullptr, entry && depth == 0, upwalk && depth >= 1);
+		launch_extend(r, stream, total, ctx.st, qin, ctx.counts + depth, ctx.counts + n_counts + depth, depth, (fused && depth >= fused_from) ? &fa : nullptr, entry && depth == 0, upwalk && depth >= 1 && (!(fused && depth >= fused_from) || fused_up), hybrid_from);
 		if (prof) cudaEventRecord(e1, stream);
 		int* shadow_count = ctx.counts + 2 * n_counts + depth;
 		const int sgrid = grid_for(r, total, 128, 16);
@@ -1409,6 +1425,8 @@ ptb_renderer* ptb_create(const char* config_json_path, int cuda_device)
 		setup(k_extend_persistent<false, 0>, &r->persistent_grid);
 		setup(k_extend_persistent<false, PTB_NODE_REPS>, nullptr);
 		setup(k_extend_persistent<true, 0>, nullptr);
+		setup(k_extend_persistent_fused<false, true>, nullptr);
+		setup(k_extend_persistent_fused<true, true>, nullptr);
 		setup(k_extend_upwalk<false, PTB_NODE_REPS>, nullptr);
 		setup(k_extend_upwalk<false, 0>, nullptr);
 		setup(k_extend_upwalk<true, 0>, nullptr);
@@ -2089,6 +2107,10 @@ int ptb_set_option(ptb_renderer* r, const char* key, const char* value)
 	}
 	if (k == "extend_persistent") { r->extend_persistent = atoi(value); return 0; }
 	if (k == "extend_variant") { r->extend_variant = atoi(value); return 0; }
+	if (k == "fused_upwalk") { r->fused_upwalk = atoi(value) != 0; return 0; }
+	if (k == "tune_refill_f") { r->tune_refill_f = atoi(value); return 0; }
+	if (k == "tune_leaf_f") { r->tune_leaf_f = atoi(value); return 0; }
+	if (k == "upwalk_min_nodes") { r->upwalk_min_nodes = std::max(1, atoi(value)); return 0; }
 	if (k == "upwalk") { r->upwalk = atoi(value) != 0; return 0; }      // takes effect at the next scene load / geometry edit
 	if (k == "tune_refill_u") { r->tune_refill_u = atoi(value); return 0; }
 	if (k == "tune_leaf_u") { r->tune_leaf_u = atoi(value); return 0; }

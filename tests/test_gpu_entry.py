@@ -85,19 +85,21 @@ def test_entry_cuts_find_the_same_hits_baseline_configs(workload_root, name, siz
     r0.close(); r1.close()
 
 
-@pytest.mark.parametrize("name,size,scale", [("c2", (320, 180), 0.1), ("c3", (256, 144), 0.05), ("c1", (96, 96), 1.0), ("mix", (100, 70), 1.0)])
+@pytest.mark.parametrize("name,size,scale", [("c2", (320, 180), 0.1), ("c3", (256, 144), 0.05), ("c1", (96, 96), 1.0), ("mix", (100, 70), 1.0), ("c4", (192, 108), 0.03)])
 def test_leaf_starts_of_bounce_rays_find_the_same_hits(workload_root, name, size, scale):
     """upwalk (k_extend_upwalk): a bounce ray that leaves a triangle starts its search at that triangle's leaf and walks UP through the
     siblings of the leaf's ancestors; images and per-depth segment counts must equal a search from the root bit for bit — with the binary
-    tree used for the first bounce only (the default hybrid) and for every bounce (hybrid_from_depth=99)."""
+    tree used for the first bounce only (the default hybrid) and for every bounce (hybrid_from_depth=99), and, in scattering media (mix,
+    c4), with every search of a subsurface walk started at the leaf of the triangle the path entered through (fused_upwalk)."""
     kw = dict(width=size[0], height=size[1])
     if scale != 1.0:
         kw["tri_scale"] = scale
     root, w = workload_root(name, **kw)
     cam = camera(w)
     ref, seg0 = render(w, root, cam, 3, upwalk=0, entry_cuts=0)
-    for opts in (dict(upwalk=1, entry_cuts=0), dict(upwalk=1), dict(upwalk=1, hybrid_from_depth=99), dict(upwalk=1, hybrid_from_depth=99, bvh_builder="host_sah"),
-                 dict(upwalk=1, bvh_max_leaf=1), dict(upwalk=1, hybrid_from_depth=99, tune_refill_u=1, tune_leaf_u=1)):
+    for opts in (dict(upwalk=1, entry_cuts=0), dict(upwalk=1), dict(upwalk=1, upwalk_min_nodes=1), dict(upwalk=1, upwalk_min_nodes=1, hybrid_from_depth=99), dict(upwalk=1, hybrid_from_depth=99), dict(upwalk=1, hybrid_from_depth=99, bvh_builder="host_sah"),
+                 dict(upwalk=1, bvh_max_leaf=1), dict(upwalk=1, hybrid_from_depth=99, tune_refill_u=1, tune_leaf_u=1),
+                 dict(upwalk=1, fused_upwalk=0), dict(upwalk=1, fused_upwalk=1, fused_from_depth=0), dict(upwalk=1, inline_scatter=0)):
         img, seg = render(w, root, cam, 3, **opts)
         assert np.array_equal(ref.view(np.uint32), img.view(np.uint32)), opts
         assert seg == seg0, opts
