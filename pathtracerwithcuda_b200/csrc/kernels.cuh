@@ -42,7 +42,7 @@ struct DeviceScene
 	int n_textures;
 	int root_ref;                 // node index (>= 0) or leaf ref (< 0)
 	// bounce rays that leave a triangle start their search AT that triangle's leaf (kernels_entry.cuh: k_up_level; layout 2 only, else nullptr):
-	const float4* up_records;     // per child slot (node * 2 + side) of the binary tree: sibling box lo.xyz + sibling ref | hi.xyz + the node's own slot in ITS parent (-1 at the root)
+	const float4* up_records;     // per child slot (node * 2 + side) of the binary tree, 4 x float4: the sibling's box + reference, the parent's sibling's box + reference, the slot two levels up (kernels_entry.cuh: k_up_pair)
 	const int* tri_slot;          // child slot holding the leaf of triangle (global id), -1 = unknown
 	// next-event estimation (estimator "nee", off by default): emissive, non-transparent triangles
 	const float* tris24;          // raw triangles by global id (v0 v1 v2 ...), 24 floats each

@@ -220,4 +220,28 @@ __global__ void __launch_bounds__(128) k_up_level(const float4* __restrict__ nod
 	}
 }
 
+// Two levels per record: up2[slot] = { A.lo.xyz, A.ref | A.hi.xyz, B.ref | B.lo.xyz, slot two levels up | B.hi.xyz, - } with A the sibling of
+// `slot` and B the sibling of its parent (B.ref = PTB_ENTRY_END when `slot` hangs off the root).  Halves the chain of dependent loads of
+// the walk.  `up` must have been filled with 0xff before k_up_level ran, so unused pool slots read "no parent".
+__global__ void __launch_bounds__(128) k_up_pair(const float4* __restrict__ up, float4* __restrict__ up2, int n_slots)
+{
+	const int s = blockIdx.x * blockDim.x + threadIdx.x;
+	if (s >= n_slots) return;
+	const float4 a_lo = up[(size_t)s * 2], a_hi = up[(size_t)s * 2 + 1];
+	const int p = __float_as_int(a_hi.w);
+	float4 b_lo = make_float4(1.0f, 1.0f, 1.0f, __int_as_float(-1)), b_hi = make_float4(-1.0f, -1.0f, -1.0f, 0.0f);
+	int b_ref = PTB_ENTRY_END;
+	if (p >= 0 && p < n_slots)
+	{
+		const float4 q_lo = up[(size_t)p * 2], q_hi = up[(size_t)p * 2 + 1];
+		b_ref = __float_as_int(q_lo.w);
+		b_lo = make_float4(q_lo.x, q_lo.y, q_lo.z, q_hi.w);      // .w: the slot two levels up
+		b_hi = make_float4(q_hi.x, q_hi.y, q_hi.z, 0.0f);
+	}
+	up2[(size_t)s * 4 + 0] = a_lo;
+	up2[(size_t)s * 4 + 1] = make_float4(a_hi.x, a_hi.y, a_hi.z, __int_as_float(b_ref));
+	up2[(size_t)s * 4 + 2] = b_lo;
+	up2[(size_t)s * 4 + 3] = b_hi;
+}
+
 } // namespace ptb

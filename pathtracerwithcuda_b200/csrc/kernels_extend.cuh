@@ -391,7 +391,7 @@ struct EntryArgs
 // The leaf start of a bounce ray (UPWALK): `slot` = child slot (node * 2 + side) of the leaf the search starts at.  Sets `node` to that
 // leaf and leaves on the stack the siblings of the leaf's ancestors the ray's box test accepts, deepest (= nearest) on top.  Every
 // sub-tree of the scene is the start leaf or one of those siblings, so the search is exhaustive whatever leaf it starts at; a leaf near
-// the ray's origin makes it cheap (one 32-byte record and one box test per level instead of a 64-byte node and two).
+// the ray's origin makes it cheap (32 bytes and one box test per level instead of a 64-byte node and two; records hold two levels).
 template <bool COUNT>
 __device__ __forceinline__ void upwalk_start(const DeviceScene& sc, int slot, float3 idir, float3 noidir, float margin2, float t_max,
 	int* stack, int& sp, int& node, unsigned& n_nodes, unsigned& ray_nodes)
@@ -401,15 +401,38 @@ __device__ __forceinline__ void upwalk_start(const DeviceScene& sc, int slot, fl
 	int n = 0;
 	do
 	{
-		const float4 lo = __ldg(sc.up_records + (size_t)slot * 2), hi = __ldg(sc.up_records + (size_t)slot * 2 + 1);
+		// two levels per 64-byte record (kernels_entry.cuh: k_up_pair): the sibling of `slot`, then the sibling of its parent
+		const float4* rp = sc.up_records + (size_t)slot * 4;
+		float4 a_lo, a_hi, b_lo;
+		float2 b_hi_xy; float b_hi_z;
+		{
+			float pad;
+			asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+				: "=f"(a_lo.x), "=f"(a_lo.y), "=f"(a_lo.z), "=f"(a_lo.w), "=f"(a_hi.x), "=f"(a_hi.y), "=f"(a_hi.z), "=f"(a_hi.w) : "l"(rp));
+			asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+				: "=f"(b_lo.x), "=f"(b_lo.y), "=f"(b_lo.z), "=f"(b_lo.w), "=f"(b_hi_xy.x), "=f"(b_hi_xy.y), "=f"(b_hi_z), "=f"(pad) : "l"(rp + 2));
+		}
 		if (COUNT) { n_nodes++; ray_nodes++; }
-		const float x0 = fmaf(lo.x, idir.x, noidir.x), x1 = fmaf(hi.x, idir.x, noidir.x);
-		const float y0 = fmaf(lo.y, idir.y, noidir.y), y1 = fmaf(hi.y, idir.y, noidir.y);
-		const float z0 = fmaf(lo.z, idir.z, noidir.z), z1 = fmaf(hi.z, idir.z, noidir.z);
-		const float tmin = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fmaxf(fminf(z0, z1), 0.0f));
-		const float tmax = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fminf(fmaxf(z0, z1), t_max));
-		if (fmaf(tmin, PTB_SLACK_LO / PTB_SLACK_HI, -margin2) <= tmax) { if (n < PTB_STACK_SIZE) stack[n] = __float_as_int(lo.w); n++; }
-		slot = __float_as_int(hi.w);
+		{
+			const float x0 = fmaf(a_lo.x, idir.x, noidir.x), x1 = fmaf(a_hi.x, idir.x, noidir.x);
+			const float y0 = fmaf(a_lo.y, idir.y, noidir.y), y1 = fmaf(a_hi.y, idir.y, noidir.y);
+			const float z0 = fmaf(a_lo.z, idir.z, noidir.z), z1 = fmaf(a_hi.z, idir.z, noidir.z);
+			const float tmin = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fmaxf(fminf(z0, z1), 0.0f));
+			const float tmax = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fminf(fmaxf(z0, z1), t_max));
+			if (fmaf(tmin, PTB_SLACK_LO / PTB_SLACK_HI, -margin2) <= tmax) { if (n < PTB_STACK_SIZE) stack[n] = __float_as_int(a_lo.w); n++; }
+		}
+		const int b_ref = __float_as_int(a_hi.w);
+		if (b_ref != PTB_DONE)
+		{
+			if (COUNT) { n_nodes++; ray_nodes++; }
+			const float x0 = fmaf(b_lo.x, idir.x, noidir.x), x1 = fmaf(b_hi_xy.x, idir.x, noidir.x);
+			const float y0 = fmaf(b_lo.y, idir.y, noidir.y), y1 = fmaf(b_hi_xy.y, idir.y, noidir.y);
+			const float z0 = fmaf(b_lo.z, idir.z, noidir.z), z1 = fmaf(b_hi_z, idir.z, noidir.z);
+			const float tmin = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fmaxf(fminf(z0, z1), 0.0f));
+			const float tmax = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fminf(fmaxf(z0, z1), t_max));
+			if (fmaf(tmin, PTB_SLACK_LO / PTB_SLACK_HI, -margin2) <= tmax) { if (n < PTB_STACK_SIZE) stack[n] = b_ref; n++; }
+		}
+		slot = __float_as_int(b_lo.w);
 	} while (slot >= 0);
 	n = min(n, PTB_STACK_SIZE);
 	for (int a = 0, b = n - 1; a < b; a++, b--) { const int t = stack[a]; stack[a] = stack[b]; stack[b] = t; }

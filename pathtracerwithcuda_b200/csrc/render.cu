@@ -759,7 +759,10 @@ int upload_geometry(ptb_renderer* r)
 		const int n_nodes = (int)r->bvh_nodes;
 		float4* up = nullptr; int* tri_slot = nullptr; int2* frontier[2] = { nullptr, nullptr }; int* level_counts = nullptr;
 		const int levels = PTB_STACK_SIZE + 2;
-		PTB_CUDA(cudaMalloc(&up, (size_t)n_nodes * 64));
+		float4* up1 = nullptr;      // one level per record (k_up_level), paired into `up` below
+		PTB_CUDA(cudaMalloc(&up1, (size_t)n_nodes * 64));
+		PTB_CUDA(cudaMemsetAsync(up1, 0xff, (size_t)n_nodes * 64, r->stream));      // unused pool slots of the node array read "no parent"
+		PTB_CUDA(cudaMalloc(&up, (size_t)n_nodes * 128));
 		G->push_back(up);
 		PTB_CUDA(cudaMalloc(&tri_slot, (size_t)n_tris * sizeof(int)));
 		G->push_back(tri_slot);
@@ -775,12 +778,13 @@ int upload_geometry(ptb_renderer* r)
 		PTB_CUDA(cudaStreamSynchronize(r->stream));   // the two host words above are stack variables
 		const int grid = std::max(1, std::min((n_nodes + 127) / 128, r->sm_count * 8));
 		for (int level = 0; level < levels; level++)
-			k_up_level<<<grid, 128, 0, r->stream>>>(ds.bvh_nodes, ds.tri_isect, frontier[level & 1], frontier[(level + 1) & 1], level_counts, level, n_nodes, up, tri_slot, n_tris);
+			k_up_level<<<grid, 128, 0, r->stream>>>(ds.bvh_nodes, ds.tri_isect, frontier[level & 1], frontier[(level + 1) & 1], level_counts, level, n_nodes, up1, tri_slot, n_tris);
+		k_up_pair<<<(n_nodes * 2 + 127) / 128, 128, 0, r->stream>>>(up1, up, n_nodes * 2);
 		PTB_CUDA(cudaStreamSynchronize(r->stream));
-		cudaFree(frontier[0]); cudaFree(frontier[1]); cudaFree(level_counts);
+		cudaFree(frontier[0]); cudaFree(frontier[1]); cudaFree(level_counts); cudaFree(up1);
 		PTB_CUDA(cudaGetLastError());
 		ds.up_records = up; ds.tri_slot = tri_slot;
-		r->bvh_bytes += (int64_t)n_nodes * 64 + (int64_t)n_tris * 4;
+		r->bvh_bytes += (int64_t)n_nodes * 128 + (int64_t)n_tris * 4;
 	}
 	PTB_CUDA(cudaStreamSynchronize(r->stream));
 	PTB_CUDA(cudaGetLastError());
