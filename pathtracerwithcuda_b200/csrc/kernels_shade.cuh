@@ -85,6 +85,7 @@ __global__ void __launch_bounds__(128, PTB_SHADE_MIN_BLOCKS) k_shade(DeviceScene
 	__shared__ int s_hist[SORT ? 16 : 1];
 	const int count = *count_in;
 	const unsigned lane = threadIdx.x & 31;
+	const float pixel_count_inv = 1.0f / (float)pixel_count;
 	// block-uniform trip count (barriers in the SORT path), hence warp-uniform: the ballots below are convergent
 	for (int block_base = blockIdx.x * blockDim.x; block_base < count; block_base += gridDim.x * blockDim.x)
 	{
@@ -125,8 +126,11 @@ __global__ void __launch_bounds__(128, PTB_SHADE_MIN_BLOCKS) k_shade(DeviceScene
 		else if (valid) id = queue_in[i];
 		if (valid)
 		{
-			int slot = id / pixel_count;
+			// id / pixel_count with a float estimate and one correction (the quotient is a batch slot, < 2^10; exact for every id)
+			int slot = (int)((float)id * pixel_count_inv);
 			int pixel_index = id - slot * pixel_count;
+			if (pixel_index < 0) { slot--; pixel_index += pixel_count; }
+			else if (pixel_index >= pixel_count) { slot++; pixel_index -= pixel_count; }
 			int seed = first_pass + slot * pass_stride;
 
 			// at depth 0 the throughput is (1, 1, 1) in air by construction (init_data_kernel :275-297): k_generate does not

@@ -155,3 +155,20 @@ def test_background(kat):
         out = np.zeros(3, np.float32)
         L.ptbo_background(ctypes.byref(scene), p(cfg), p(d), p(out))
         assert close(out, f32(s["rgb"]), rel=1e-6, abs_=1e-6)
+
+
+def test_byte_over_255_is_the_ieee_division():
+    """csrc/pt_device.cuh: byte_over_255 replaces the texel normalisation v / 255.0f (Core/texture.h) by v * RN(1/255) plus one Newton
+    correction in fused multiply-adds; it must be the correctly rounded quotient for all 256 bytes (libm's fmaf is correctly rounded)."""
+    import ctypes
+    import ctypes.util
+    libm = ctypes.CDLL(ctypes.util.find_library("m") or "libm.so.6")
+    libm.fmaf.restype = ctypes.c_float
+    libm.fmaf.argtypes = [ctypes.c_float, ctypes.c_float, ctypes.c_float]
+    r = np.float32(float.fromhex("0x1.010102p-8"))
+    assert r == np.float32(1.0) / np.float32(255.0)
+    for v in range(256):
+        fv = np.float32(v)
+        q = np.float32(fv * r)
+        got = libm.fmaf(libm.fmaf(-255.0, float(q), float(fv)), float(r), float(q))
+        assert np.float32(got) == fv / np.float32(255.0), v
