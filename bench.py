@@ -42,19 +42,22 @@ PASSES_IN_FLIGHT = 16     # passes traced as one wavefront batch (tools/sweep_ba
 STREAMS_IN_FLIGHT = 4     # batches overlapped on separate CUDA streams
 METRIC = "path samples/sec (Mspp*px/s), 1080p"
 # Per-launch memory traffic of the closest-hit kernels from ONE `ncu --set full` capture of the shipped kernels (workload c2, one 16-pass
-# batch as benchmarked: d0-d1 k_extend_persistent, d2-d7 k_extend_persistent8), averaged over the 8 depth launches of the batch like
-# `avg_launch_ms` below — profiles/r02_extend_ncu_summary.md.  bench.py divides these by the launch duration it measures LIVE.
+# batch as benchmarked: d0 k_extend_entry, d1 k_extend_upwalk, d2-d7 k_extend_persistent8), averaged over the 8 depth launches of the batch
+# like `avg_launch_ms` below — profiles/r02_extend_ncu_summary.md.  bench.py divides these by the launch duration it measures LIVE.
 NCU_CAPTURE = {
     "source": "profiles/r02_extend_ncu_summary.md",
     "workload": "c2", "passes_in_flight": 16,
-    "dram_bytes_per_launch": 379.1e6,         # dram__bytes_read.sum + dram__bytes_write.sum
-    "l2_bytes_per_launch": 2335.5e6,          # lts__t_bytes.sum
-    "l1_writeback_bytes_per_launch": 22039.5e6,   # l1tex__lsu_writeback_active_mem_lgds.sum (cycles) x 128 B: what the load instructions cost the L1 data pipe
-    "l1_tag_bytes_per_launch": 4379.7e6,      # l1tex__t_bytes.sum (distinct sectors x 32 B through the tag stage)
-    "limiters": {"time_weighted_d0_d7": {"sm__throughput_pct": 56.8, "issue_active_pct": 65.4, "l1_data_pipe_wavefronts_pct": 62.8, "l1_writeback_active_pct": 50.8,
-                                          "active_lanes_per_instruction": 20.3, "l1_hit_pct": 67.5, "l2_hit_pct": 65.4},
-                 "d0_d1": {"sm__throughput_pct": [67.9, 51.3], "issue_active_pct": [69.8, 64.4], "l1_data_pipe_wavefronts_pct": [74.5, 64.9],
-                           "active_lanes_per_instruction": [22.6, 19.6], "stall_long_scoreboard_per_issue": [4.2, 5.94], "alu_pipe_pct": [63.8, 56.8]}},
+    "dram_bytes_per_launch": 380.2e6,         # dram__bytes_read.sum + dram__bytes_write.sum
+    "l2_bytes_per_launch": 2300.4e6,          # lts__t_bytes.sum
+    "l1_writeback_bytes_per_launch": 13788.8e6,   # l1tex__lsu_writeback_active_mem_lgds.sum (cycles) x 128 B: what the load instructions cost the L1 data pipe
+    "l1_tag_bytes_per_launch": 3609.7e6,      # l1tex__t_bytes.sum (distinct sectors x 32 B through the tag stage)
+    "limiters": {"time_weighted_d0_d7": {"sm__throughput_pct": 50.4, "issue_active_pct": 62.1, "l1_data_pipe_wavefronts_pct": 50.7, "l1_writeback_active_pct": 40.3,
+                                          "active_lanes_per_instruction": 18.9, "l1_hit_pct": 58.5, "l2_hit_pct": 65.4},
+                 "d0_d1": {"sm__throughput_pct": [62.9, 45.1], "issue_active_pct": [66.6, 61.2], "l1_data_pipe_wavefronts_pct": [41.1, 63.3],
+                           "active_lanes_per_instruction": [21.9, 18.2], "stall_long_scoreboard_per_issue": [4.94, 7.0], "alu_pipe_pct": [51.5, 50.6],
+                           "warp_instructions": [1.29e9, 2.07e9], "ms": [1.80, 3.98]},
+                 "same_batch_with_root_starts": {"source": "profiles/r02_extend_ncu_summary_root_start.md", "d0_d1_ms": [3.41, 4.47], "d0_d1_warp_instructions": [2.64e9, 2.56e9],
+                                                 "sm__throughput_pct_time_weighted": 56.8, "l1_writeback_bytes_per_launch": 22039.5e6}},
 }
 UNIT = "Msamples/s"
 
@@ -212,6 +215,10 @@ def run_reference(args, w, root, rank, world):
         for _ in range(max(args.warmup, 5)):        # >= 5 warm-up steps after the prefetch: its first steps still migrate pages
             ref.render(PASSES_PER_STEP)
         ref.prefetch()
+        sampler = ClockSampler(int(os.environ.get("LOCAL_RANK", "0")))
+        sampler.start()
+        time.sleep(0.05)
+        clock_first = sampler.mark()
         secs, step_ms, pass_ms = 0.0, [], []
         for _ in range(args.steps):
             per_pass = ref.render_per_pass(PASSES_PER_STEP)     # synchronous passes: each returns after cudaDeviceSynchronize
@@ -219,6 +226,7 @@ def run_reference(args, w, root, rank, world):
             secs += dt
             step_ms.append(dt * 1e3)
             pass_ms += (per_pass * 1e3).tolist()
+        clocks = sampler.stop(clock_first, sampler.mark() + 1)
         seg, trace_ms = ref.pass_instrumented(ref.lib.ref_pass_counter() + 1)
         # The reference's passes show multi-x outliers on some boxes and none on others.  tools/ref_variance.py (profiles/r02_ref_variance_c2.json)
         # attributes ALL of the excess to thread_shrink — thrust::remove_if with its temporary cudaMalloc / cudaFree and implicit
@@ -242,7 +250,7 @@ def run_reference(args, w, root, rank, world):
                 "ms_per_step": best_pass_ms * PASSES_PER_STEP, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
                 "data": "synthetic", "config": dict(config, note="unmodified reference CUDA kernels rebuilt headless for sm_100a, managed memory prefetched"),
                 "value_basis": "best single pass of the timed region (see reference_extra)", "best_pass": value, "min_step": best_step_value, "median_step": median_value,
-                "mean_step": mean_value, "kernel_only": kernel_only,
+                "mean_step": mean_value, "kernel_only": kernel_only, "clocks": clocks,
                 "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "reference",
                                  "sample": "%d passes of %s through path_tracer_kernel() on the B200 (the reference has no CPU implementation of this path)" % (PASSES_PER_STEP * args.steps, w["name"])},
                 "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -495,7 +503,7 @@ def run_ptb200(args, w, root, rank, local_rank, world):
                            "scene_load_s": load_s},
                 "clocks": clocks, "gpu_launches": int(launches_total),
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 64, "d2h_bytes_per_step": int(u8.nbytes)},
-                "roofline": {"bound": bound, "kernel": "k_extend_persistent / k_extend_persistent8 (closest hit)", "achieved": achieved, "peak": peak,
+                "roofline": {"bound": bound, "kernel": "k_extend_entry (d0) / k_extend_upwalk (d1) / k_extend_persistent8 (d2+): closest hit", "achieved": achieved, "peak": peak,
                              "unit": "TFLOP/s" if bound == "fp32" else "GB/s", "frac": known.get(bound) if bound else None,
                              "traffic": ncu.get("dram_bytes_per_launch"),
                              "fracs": fracs,
