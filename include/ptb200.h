@@ -191,6 +191,17 @@ int ptb_get_traversal_histogram(ptb_renderer* r, int64_t* out25);
  *   "bvh_intersect_cost" float > 0 (default 0.8) SAH cost of a triangle test relative to a node visit
  *   "l2_persist"         "0" (default) | "1"    nodes + leaf-order triangles in one allocation under a persisting L2 access-policy
  *                                               window on every render stream (measured neutral: the tree is never evicted)
+ *  where a closest-hit search starts (same hits bit for bit, tests/test_gpu_entry.py; binary tree + persistent kernels only)
+ *   "entry_cuts"         "1" (default) | "0"    camera rays start at the sub-trees their pixel tile's shaft touches instead of at the
+ *                                               root (csrc/kernels_entry.cuh: k_entry_cut, rebuilt when camera / geometry change;
+ *                                               cameras it does not cover — focal distance <= 0, fov >= 175 degrees — use the root)
+ *   "entry_k"            "1".."31" (default 15) sub-trees per tile; "entry_tile" "WxH" powers of two (default "8x4")
+ *   "upwalk"             "1" (default) | "0"    a bounce ray that leaves a triangle starts at that triangle's leaf and collects the
+ *                                               siblings of the leaf's ancestors it hits walking UP (k_up_level / k_up_pair records;
+ *                                               takes effect at the next ptb_load_scene / geometry edit); "upwalk_min_nodes" (64):
+ *                                               smaller trees are searched from the root
+ *   "fused_upwalk"       "0" (default) | "1"    scattering media: the whole subsurface walk on the binary tree with every search
+ *                                               started at the leaf the path entered through (measured slower than the wide tree)
  *  closest-hit kernels (immediate; tuning knobs of tools/sweep_*.py, defaults are the measured optima)
  *   "extend_persistent"  "1" (default) | "0"    persistent warp-voting kernels / one ray per thread
  *   "extend_variant"     "0" (default) | "1" postponed leaves | "2" + leaf prefetch | "3" top of the tree in shared memory
@@ -199,6 +210,10 @@ int ptb_get_traversal_histogram(ptb_renderer* r, int64_t* out25);
  *   "tune_refill", "tune_leaf", "tune_reps"     binary-tree kernel: refill when >= N lanes idle (20), leaf phase when >= N lanes
  *                                               wait (6), node steps per node phase (6); "unroll_reps" "1" | "0"
  *   "tune_refill8", "tune_leaf8"                wide-tree kernel (12, 6)
+ *   "tune_refill_e", "tune_leaf_e", "tune_reps_e"  camera-ray kernel k_extend_entry (28, 6, 6)
+ *   "tune_refill_u", "tune_leaf_u", "tune_reps_u"  bounce-ray kernel k_extend_upwalk (20, 6, 6); "tune_refill_f", "tune_leaf_f": with fused_upwalk
+ *   "inline_scatter"     "1" (default) | "0"    medium scatter events performed inside the closest-hit kernel of the deeper bounces;
+ *                                               "fused_from_depth" (-1 = where the wide tree takes over), "tune_scatter" (8 lanes)
  *   "persistent_grid", "persistent_grid8"       blocks of the persistent launches (default: one resident wave)
  *  estimator (NOT parity modes: they change the samples, same expectation; tests/test_gpu_nee.py, test_gpu_rr.py, test_gpu_estimators.py)
  *   "estimator"          "reference" (default) | "nee"   next-event estimation + shadow rays (binary tree)

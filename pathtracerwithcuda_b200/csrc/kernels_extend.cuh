@@ -310,6 +310,9 @@ __device__ __forceinline__ void load_node(const float4* np, float4& n0, float4& 
 #ifndef PTB_LEAF_SINGLE
 #define PTB_LEAF_SINGLE 1
 #endif
+#ifndef PTB_LEAF_FALLTHROUGH
+#define PTB_LEAF_FALLTHROUGH 0
+#endif
 
 // FUSED (option inline_scatter, default on in parity mode): in a scattering medium most bounces are scatter events — the free flight ends
 // before any surface (k_shade: d < t_hit), the path gets an isotropic direction, its throughput is attenuated, nothing else happens
@@ -715,7 +718,13 @@ __device__ __forceinline__ void extend_persistent_body(const DeviceScene& sc, co
 #endif
 				if (sp > 0) PTB_POP(node); else node = PTB_DONE;
 			}
+#if PTB_LEAF_FALLTHROUGH
+			// lanes at an inner node take their node steps in the SAME iteration (one round of votes for both phases); a lane whose leaf
+			// just ended joins them with the node it popped
+			if ((m_node & ~m_scat) == 0u) continue;
+#else
 			continue;
+#endif
 		}
 
 		// ---- node phase (node_reps steps for every lane sitting at an inner node)
