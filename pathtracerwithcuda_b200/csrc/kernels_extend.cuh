@@ -126,6 +126,15 @@ __device__ __forceinline__ unsigned sign_extend_s8x4(unsigned x)
 
 __device__ __forceinline__ unsigned extract_byte(unsigned x, unsigned i) { return (x >> (i * 8)) & 0xffu; }
 
+// (float)byte j of x.  The int -> float conversion issues on the quarter-rate XU pipe, the busiest pipe of the wide-tree kernels under ncu
+// (63 %, 48 conversions per node); replacing it by PRMT into the mantissa of 2^23 + FADD (build flag PTB_BYTE_NO_I2F, exact) was measured
+// SLOWER — c2 d2 1.47 -> 1.56 ms, c4 807 -> 761 Msamples/s (profiles/r02_experiments.md): the kernel is bound by issue slots, not by that pipe.
+#ifdef PTB_BYTE_NO_I2F
+__device__ __forceinline__ float byte_to_float(unsigned x, int j) { return __uint_as_float(__byte_perm(x, 0x4B000000u, 0x7650u + (unsigned)j)) - 8388608.0f; }
+#else
+__device__ __forceinline__ float byte_to_float(unsigned x, int j) { return (float)extract_byte(x, j); }
+#endif
+
 template <bool COUNT>
 __device__ __forceinline__ HitRecord closest_hit_bvh8(const DeviceScene& sc, float3 o, float3 d, float t_bound, unsigned& n_nodes, unsigned& n_tris)
 {
@@ -196,9 +205,9 @@ __device__ __forceinline__ HitRecord closest_hit_bvh8(const DeviceScene& sc, flo
 #pragma unroll
 				for (int j = 0; j < 4; j++)
 				{
-					const float tx0 = fmaf((float)extract_byte(x_min, j), adir.x, aorg.x), tx1 = fmaf((float)extract_byte(x_max, j), adir.x, aorg.x);
-					const float ty0 = fmaf((float)extract_byte(y_min, j), adir.y, aorg.y), ty1 = fmaf((float)extract_byte(y_max, j), adir.y, aorg.y);
-					const float tz0 = fmaf((float)extract_byte(z_min, j), adir.z, aorg.z), tz1 = fmaf((float)extract_byte(z_max, j), adir.z, aorg.z);
+					const float tx0 = fmaf(byte_to_float(x_min, j), adir.x, aorg.x), tx1 = fmaf(byte_to_float(x_max, j), adir.x, aorg.x);
+					const float ty0 = fmaf(byte_to_float(y_min, j), adir.y, aorg.y), ty1 = fmaf(byte_to_float(y_max, j), adir.y, aorg.y);
+					const float tz0 = fmaf(byte_to_float(z_min, j), adir.z, aorg.z), tz1 = fmaf(byte_to_float(z_max, j), adir.z, aorg.z);
 					const float tmin = fmaxf(fmaxf(tx0, ty0), fmaxf(tz0, 0.0f));
 					const float tmax = fminf(fminf(tx1, ty1), fminf(tz1, best.t));
 					if (tmin * PTB_SLACK_LO <= tmax * PTB_SLACK_HI)
@@ -1237,9 +1246,9 @@ __global__ void __launch_bounds__(128, PTB_PERSISTENT_MIN_BLOCKS8) k_extend_pers
 #pragma unroll
 				for (int j = 0; j < 4; j++)
 				{
-					const float tx0 = fmaf((float)extract_byte(x_min, j), adir.x, aorg.x), tx1 = fmaf((float)extract_byte(x_max, j), adir.x, aorg.x);
-					const float ty0 = fmaf((float)extract_byte(y_min, j), adir.y, aorg.y), ty1 = fmaf((float)extract_byte(y_max, j), adir.y, aorg.y);
-					const float tz0 = fmaf((float)extract_byte(z_min, j), adir.z, aorg.z), tz1 = fmaf((float)extract_byte(z_max, j), adir.z, aorg.z);
+					const float tx0 = fmaf(byte_to_float(x_min, j), adir.x, aorg.x), tx1 = fmaf(byte_to_float(x_max, j), adir.x, aorg.x);
+					const float ty0 = fmaf(byte_to_float(y_min, j), adir.y, aorg.y), ty1 = fmaf(byte_to_float(y_max, j), adir.y, aorg.y);
+					const float tz0 = fmaf(byte_to_float(z_min, j), adir.z, aorg.z), tz1 = fmaf(byte_to_float(z_max, j), adir.z, aorg.z);
 					const float tmin = fmaxf(fmaxf(tx0, ty0), fmaxf(tz0, 0.0f));
 					const float tmax = fminf(fminf(tx1, ty1), fminf(tz1, best.t));
 					if (tmin * PTB_SLACK_LO <= tmax * PTB_SLACK_HI)
