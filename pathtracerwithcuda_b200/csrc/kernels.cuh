@@ -82,6 +82,9 @@ struct DeviceConfig
 #define PTB_FROM_BITS_OF(w) ((w) & ~0xff)
 #define PTB_FROM_BITS(prim) (((prim) >= 0 && (prim) < (1 << 23) - 2 ? (prim) + 1 : 0) << 8)
 
+// terminator of a tile's entry cut (kernels_entry.cuh) == PTB_DONE of kernels_extend.cuh
+#define PTB_ENTRY_END ((int)0x80000000)
+
 // SoA path state, indexed by path id = slot * pixel_count + pixel.
 struct PathState
 {

@@ -24,7 +24,6 @@ using namespace ptbdev;
 
 #define PTB_ENTRY_STRIDE 32          // most int2 slots per tile: <= 31 sub-trees + terminator (the lists are stored with a stride of
                                      // the next power of two above k_max)
-#define PTB_ENTRY_END ((int)0x80000000)   // == PTB_DONE of kernels_extend.cuh
 
 // distances to the shaft's planes / eye of one box, relative to the eye
 struct EntryShaft
@@ -171,6 +170,30 @@ __global__ void __launch_bounds__(128) k_entry_cut(DeviceScene sc, CameraParams 
 	}
 	for (int i = 0; i < n; i++) out[i] = make_int2(ref[i], __float_as_int(tn[i]));
 	out[n] = make_int2(PTB_ENTRY_END, __float_as_int(CUDART_INF_F));
+}
+
+// Numbers the tiles whose entry cut is not empty, in tile (= queue) order: rank[t] = index among them, -1 for an empty cut; *n_nonempty =
+// how many.  One block; k_generate<.., SKY> (kernels_generate.cuh) queues only their rays and keeps the queue in tile order without atomics.
+__global__ void __launch_bounds__(1024) k_tile_rank(const int2* __restrict__ cuts, int stride, int n_tiles, int* __restrict__ rank, int* __restrict__ n_nonempty)
+{
+	__shared__ int s_sum[1024];
+	const int per = (n_tiles + 1023) / 1024;
+	const int begin = min(n_tiles, (int)threadIdx.x * per), end = min(n_tiles, begin + per);
+	int mine = 0;
+	for (int t = begin; t < end; t++) mine += cuts[(size_t)t * stride].x != PTB_ENTRY_END ? 1 : 0;
+	s_sum[threadIdx.x] = mine;
+	__syncthreads();
+	// inclusive scan over the 1024 partial sums
+	for (int off = 1; off < 1024; off <<= 1)
+	{
+		const int v = threadIdx.x >= off ? s_sum[threadIdx.x - off] : 0;
+		__syncthreads();
+		s_sum[threadIdx.x] += v;
+		__syncthreads();
+	}
+	int next = s_sum[threadIdx.x] - mine;
+	for (int t = begin; t < end; t++) rank[t] = cuts[(size_t)t * stride].x != PTB_ENTRY_END ? next++ : -1;
+	if (threadIdx.x == 1023) *n_nonempty = s_sum[1023];
 }
 
 // ------------------------------------------------------------------------------------------

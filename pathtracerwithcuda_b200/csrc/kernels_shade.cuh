@@ -537,9 +537,12 @@ __global__ void __launch_bounds__(128) k_shadow(DeviceScene sc, PathState st, co
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_accumulate(const float4* __restrict__ radiance, float* __restrict__ image_sum, float* __restrict__ last_pass,
 	const int* __restrict__ counts, unsigned long long* __restrict__ segment_totals, int n_counts,
-	int pixel_count, int n_slots, float clamp_hi)
+	int pixel_count, int n_slots, float clamp_hi, int generated = 0)
 {
 	int p = blockIdx.x * blockDim.x + threadIdx.x;
+	// generated > 0: k_generate<.., SKY> finished the camera rays of empty tiles itself (background colour) and queued only counts[0] of the
+	// `generated` rays; the others are depth-0 segments like the queued ones
+	if (p == 0 && generated > 0 && n_counts > 0 && counts != nullptr) atomicAdd(&segment_totals[0], (unsigned long long)(generated - counts[0]));
 	// tally this batch's live-path counters (ray segments per depth) into the call totals; n_counts stops at the first loop depth whose
 	// closest-hit kernel tallies its own searches (option inline_scatter)
 	if (p < n_counts && counts != nullptr) atomicAdd(&segment_totals[p], (unsigned long long)counts[p]);

@@ -122,6 +122,7 @@ struct ptb_renderer
 	int upwalk_min_nodes = 64;
 	int upwalk = 1;                        // bounce rays on the binary tree start at the leaf of the triangle they leave (kernels_entry.cuh: k_up_level); same hits
 	int entry_cuts = 1;
+	int sky_fast = 1;                      // camera rays of tiles with an empty entry cut are finished by k_generate (background colour), never queued
 	int entry_k = 15;                      // sub-trees per tile (<= PTB_ENTRY_STRIDE - 1)
 	int entry_tile_w = 8, entry_tile_h = 4; // pixels per tile (powers of two); 8x4 = the 32 lanes of a warp under tile_order
 	int fused_upwalk = 0;                  // scattering media: the whole walk on the binary tree, every search started at the leaf of the triangle the path entered through (measured SLOWER than the wide tree from the root: c4 807 -> 716-746 Msamples/s, profiles/r02_experiments.md)
@@ -129,7 +130,9 @@ struct ptb_renderer
 	int tune_refill_u = 20, tune_leaf_u = 6, tune_reps_u = 6;   // voting thresholds of k_extend_upwalk
 	int tune_refill_e = 28, tune_leaf_e = 6, tune_reps_e = 6;   // voting thresholds of k_extend_entry (short searches: refills batched harder than in the other kernels; swept in profiles/r02_experiments.md)
 	int2* entry_buf = nullptr; size_t entry_buf_slots = 0; int entry_stride = 16;
+	int* entry_rank = nullptr; size_t entry_rank_tiles = 0;   // k_tile_rank: [n_tiles] ranks + 1 int (non-empty tiles)
 	bool entry_valid = false;
+	size_t entry_n_tiles = 0;
 	unsigned char entry_key[96] = { 0 };   // camera, resolution, k and geometry version the lists were built for
 	uint64_t geometry_version = 0;
 	int tune_refill4 = 8;                  // extend_variant 4: pop staged rays when >= N lanes are idle
@@ -289,6 +292,7 @@ void free_work_buffers(ptb_renderer* r)
 	if (r->counts_host) cudaFreeHost(r->counts_host);
 	cudaFree(r->image_sum); cudaFree(r->last_pass); cudaFree(r->image_u8);
 	cudaFree(r->entry_buf); r->entry_buf = nullptr; r->entry_buf_slots = 0; r->entry_valid = false;
+	cudaFree(r->entry_rank); r->entry_rank = nullptr; r->entry_rank_tiles = 0;
 	cudaFree(r->merged_sum); cudaFree(r->merged_u8); cudaFree(r->pass_count_dev);
 	r->merged_sum = nullptr; r->merged_u8 = nullptr; r->pass_count_dev = nullptr; r->merged_passes = 0;
 	r->counts_host = nullptr; r->counters = nullptr; r->segment_totals = nullptr;
@@ -997,8 +1001,16 @@ int ensure_entry_cuts(ptb_renderer* r, cudaStream_t stream)
 		PTB_CUDA(cudaMalloc(&r->entry_buf, n_tiles * r->entry_stride * sizeof(int2)));
 		r->entry_buf_slots = n_tiles * r->entry_stride;
 	}
+	if (n_tiles > r->entry_rank_tiles)
+	{
+		cudaFree(r->entry_rank); r->entry_rank = nullptr; r->entry_rank_tiles = 0;
+		PTB_CUDA(cudaMalloc(&r->entry_rank, (n_tiles + 1) * sizeof(int)));
+		r->entry_rank_tiles = n_tiles;
+	}
 	k_entry_cut<<<(int)((n_tiles + 127) / 128), 128, 0, stream>>>(r->dscene, camera_params(r->cam), r->cfg.width, r->cfg.height, tiles_x, (int)n_tiles, r->entry_k, r->entry_tile_w, r->entry_tile_h, r->entry_stride, r->entry_buf);
-	r->stats.kernel_launches++;
+	k_tile_rank<<<1, 1024, 0, stream>>>(r->entry_buf, r->entry_stride, (int)n_tiles, r->entry_rank, r->entry_rank + n_tiles);
+	r->entry_n_tiles = n_tiles;
+	r->stats.kernel_launches += 2;
 	PTB_CUDA(cudaGetLastError());
 	PTB_CUDA(cudaStreamSynchronize(stream));
 	memcpy(r->entry_key, key, sizeof(key));
@@ -1163,7 +1175,20 @@ int enqueue_batch(ptb_renderer* r, ptb_renderer::BatchContext& ctx, cudaEvent_t 
 	if (entry && ensure_entry_cuts(r, stream)) return 1;
 	// bounce rays start at the leaf they leave: k_shade leaves the triangle in ray_o.w (kernels.cuh: PTB_FROM_BITS)
 	const bool upwalk = have_up;
-	if (alt) k_generate<true><<<grid_for(r, total, 256, 8), 256, 0, stream>>>(ctx.st, ctx.queue[0], ctx.counts, n_counts, cp, dc, px, n_slots, first_pass, stride, tiles_x);
+	// camera rays of tiles with an EMPTY entry cut end at the background: k_generate finishes them (kernels_generate.cuh, SKY) — valid when
+	// nothing but triangles can be hit and the air does not take part
+	const bool sky_fast = entry && r->entry_valid && r->sky_fast && tiles_x > 0 && r->entry_tile_w == 8 && r->entry_tile_h == 4 && r->dscene.n_spheres == 0 &&
+		r->cfg.max_tracer_depth >= 1 && !(fused && fused_from <= 0) &&
+		!(dc.air_sigma_s.x > 0.0f || dc.air_sigma_s.y > 0.0f || dc.air_sigma_s.z > 0.0f ||
+		  std::sqrt(dc.air_sigma_a.x * dc.air_sigma_a.x + dc.air_sigma_a.y * dc.air_sigma_a.y + dc.air_sigma_a.z * dc.air_sigma_a.z) > dc.sss_threshold);
+	if (sky_fast)
+	{
+		SkyArgs sa;
+		sa.sky = r->dscene.sky; sa.tile_rank = r->entry_rank; sa.n_nonempty = r->entry_rank + r->entry_n_tiles;
+		if (alt) k_generate<true, true><<<grid_for(r, total, 256, 8), 256, 0, stream>>>(ctx.st, ctx.queue[0], ctx.counts, n_counts, cp, dc, px, n_slots, first_pass, stride, tiles_x, sa);
+		else k_generate<false, true><<<grid_for(r, total, 256, 8), 256, 0, stream>>>(ctx.st, ctx.queue[0], ctx.counts, n_counts, cp, dc, px, n_slots, first_pass, stride, tiles_x, sa);
+	}
+	else if (alt) k_generate<true><<<grid_for(r, total, 256, 8), 256, 0, stream>>>(ctx.st, ctx.queue[0], ctx.counts, n_counts, cp, dc, px, n_slots, first_pass, stride, tiles_x);
 	else k_generate<false><<<grid_for(r, total, 256, 8), 256, 0, stream>>>(ctx.st, ctx.queue[0], ctx.counts, n_counts, cp, dc, px, n_slots, first_pass, stride, tiles_x);
 	r->stats.kernel_launches++;
 	for (int depth = 0; depth < r->cfg.max_tracer_depth; depth++)
@@ -1223,7 +1248,7 @@ int enqueue_batch(ptb_renderer* r, ptb_renderer::BatchContext& ctx, cudaEvent_t 
 #endif
 	}
 	if (prev_accumulated) PTB_CUDA(cudaStreamWaitEvent(stream, prev_accumulated, 0));
-	k_accumulate<<<(px + 255) / 256, 256, 0, stream>>>(ctx.st.radiance, r->image_sum, r->last_pass, ctx.counts, r->segment_totals, tally_counts, px, n_slots, r->pass_clamp >= 0.0f ? r->pass_clamp : (float)r->cfg.max_tracer_depth * 2.0f);
+	k_accumulate<<<(px + 255) / 256, 256, 0, stream>>>(ctx.st.radiance, r->image_sum, r->last_pass, ctx.counts, r->segment_totals, tally_counts, px, n_slots, r->pass_clamp >= 0.0f ? r->pass_clamp : (float)r->cfg.max_tracer_depth * 2.0f, sky_fast ? (int)total : 0);
 	r->stats.kernel_launches++;
 	PTB_CUDA(cudaEventRecord(ctx.accumulated, stream));
 	PTB_CUDA(cudaGetLastError());
@@ -2119,6 +2144,7 @@ int ptb_set_option(ptb_renderer* r, const char* key, const char* value)
 	if (k == "tune_refill_u") { r->tune_refill_u = atoi(value); return 0; }
 	if (k == "tune_leaf_u") { r->tune_leaf_u = atoi(value); return 0; }
 	if (k == "tune_reps_u") { r->tune_reps_u = std::max(1, atoi(value)); return 0; }
+	if (k == "sky_fast") { r->sky_fast = atoi(value) != 0; return 0; }
 	if (k == "entry_cuts") { r->entry_cuts = atoi(value) != 0; return 0; }
 	if (k == "entry_k") { r->entry_k = std::max(1, std::min(atoi(value), PTB_ENTRY_STRIDE - 1)); return 0; }
 	if (k == "entry_tile")
