@@ -42,20 +42,20 @@ PASSES_IN_FLIGHT = 16     # passes traced as one wavefront batch (tools/sweep_ba
 STREAMS_IN_FLIGHT = 4     # batches overlapped on separate CUDA streams
 METRIC = "path samples/sec (Mspp*px/s), 1080p"
 # Per-launch memory traffic of the closest-hit kernels from ONE `ncu --set full` capture of the shipped kernels (workload c2, one 16-pass
-# batch as benchmarked: d0 k_extend_entry, d1 k_extend_upwalk, d2-d7 k_extend_persistent8), averaged over the 8 depth launches of the batch
+# batch as benchmarked: d0 k_extend_entry over the camera rays k_generate did not finish itself, d1 k_extend_upwalk, d2-d7 k_extend_persistent8), averaged over the 8 depth launches of the batch
 # like `avg_launch_ms` below — profiles/r02_extend_ncu_summary.md.  bench.py divides these by the launch duration it measures LIVE.
 NCU_CAPTURE = {
     "source": "profiles/r02_extend_ncu_summary.md",
     "workload": "c2", "passes_in_flight": 16,
-    "dram_bytes_per_launch": 380.2e6,         # dram__bytes_read.sum + dram__bytes_write.sum
-    "l2_bytes_per_launch": 2300.4e6,          # lts__t_bytes.sum
-    "l1_writeback_bytes_per_launch": 13788.8e6,   # l1tex__lsu_writeback_active_mem_lgds.sum (cycles) x 128 B: what the load instructions cost the L1 data pipe
-    "l1_tag_bytes_per_launch": 3609.7e6,      # l1tex__t_bytes.sum (distinct sectors x 32 B through the tag stage)
-    "limiters": {"time_weighted_d0_d7": {"sm__throughput_pct": 50.4, "issue_active_pct": 62.1, "l1_data_pipe_wavefronts_pct": 50.7, "l1_writeback_active_pct": 40.3,
-                                          "active_lanes_per_instruction": 18.9, "l1_hit_pct": 58.5, "l2_hit_pct": 65.4},
-                 "d0_d1": {"sm__throughput_pct": [62.9, 45.1], "issue_active_pct": [66.6, 61.2], "l1_data_pipe_wavefronts_pct": [41.1, 63.3],
-                           "active_lanes_per_instruction": [21.9, 18.2], "stall_long_scoreboard_per_issue": [4.94, 7.0], "alu_pipe_pct": [51.5, 50.6],
-                           "warp_instructions": [1.29e9, 2.07e9], "ms": [1.80, 3.98]},
+    "dram_bytes_per_launch": 288.4e6,         # dram__bytes_read.sum + dram__bytes_write.sum
+    "l2_bytes_per_launch": 2046.8e6,          # lts__t_bytes.sum
+    "l1_writeback_bytes_per_launch": 13425.3e6,   # l1tex__lsu_writeback_active_mem_lgds.sum (cycles) x 128 B: what the load instructions cost the L1 data pipe
+    "l1_tag_bytes_per_launch": 3399.5e6,      # l1tex__t_bytes.sum (distinct sectors x 32 B through the tag stage)
+    "limiters": {"time_weighted_d0_d7": {"sm__throughput_pct": 49.2, "issue_active_pct": 63.0, "l1_data_pipe_wavefronts_pct": 49.9, "l1_writeback_active_pct": 39.7,
+                                          "active_lanes_per_instruction": 18.9, "l1_hit_pct": 61.7, "l2_hit_pct": 67.9},
+                 "d0_d1": {"sm__throughput_pct": [66.3, 42.4], "issue_active_pct": [70.7, 61.4], "l1_data_pipe_wavefronts_pct": [43.8, 59.6],
+                           "active_lanes_per_instruction": [21.4, 18.6], "stall_long_scoreboard_per_issue": [3.85, 6.91], "alu_pipe_pct": [55.3, 50.8],
+                           "warp_instructions": [1.19e9, 2.02e9], "ms": [1.60, 4.16]},
                  "same_batch_with_root_starts": {"source": "profiles/r02_extend_ncu_summary_root_start.md", "d0_d1_ms": [3.41, 4.47], "d0_d1_warp_instructions": [2.64e9, 2.56e9],
                                                  "sm__throughput_pct_time_weighted": 56.8, "l1_writeback_bytes_per_launch": 22039.5e6}},
 }

@@ -74,6 +74,11 @@ __device__ __forceinline__ float3 sss_survive_weight(float3 sigma_s, float t)
 // (k_extend_persistent8<.., true>, kernels_extend.cuh), so a path may be several bounces AHEAD of the wavefront's loop depth when it
 // arrives here: ray_o.w carries that lead (an int), every depth-keyed quantity uses loop depth + lead, a path the extend stage
 // finished off carries the primitive PTB_PRIM_DEAD, and the bounce limit is checked per path.
+// survivors are queued with one atomic per BLOCK and iteration (1) or per warp (0): c2 +1.1 %, c3 +1.7 % (profiles/r02_experiments.md) — fewer
+// same-address atomics, and 128 consecutive paths stay together in the next queue
+#ifndef PTB_SHADE_BLOCK_COMPACT
+#define PTB_SHADE_BLOCK_COMPACT 1
+#endif
 template <bool SORT, bool NEE, bool RR = false, bool ALT = false, bool FUSED = false>
 __global__ void __launch_bounds__(128, PTB_SHADE_MIN_BLOCKS) k_shade(DeviceScene sc, PathState st, DeviceConfig cfg, int loop_depth, int pixel_count, int first_pass, int pass_stride,
 	const int* __restrict__ queue_in, const int* __restrict__ count_in, int* __restrict__ queue_out, int* __restrict__ count_out, int* __restrict__ shadow_count,
@@ -81,6 +86,9 @@ __global__ void __launch_bounds__(128, PTB_SHADE_MIN_BLOCKS) k_shade(DeviceScene
 {
 	if (!ALT) { cfg.sampler = 0; cfg.sss_mode = 0; }
 	__shared__ int s_oct[10];
+#if PTB_SHADE_BLOCK_COMPACT
+	__shared__ int s_cmp[5];
+#endif
 	__shared__ int s_ids[SORT ? 128 : 1];
 	__shared__ int s_hist[SORT ? 16 : 1];
 	const int count = *count_in;
@@ -426,8 +434,26 @@ __global__ void __launch_bounds__(128, PTB_SHADE_MIN_BLOCKS) k_shade(DeviceScene
 		}
 		else
 		{
-		// stream compaction of survivors: one atomic per warp (replaces thrust::remove_if + host sync)
+		// stream compaction of survivors (replaces thrust::remove_if + host sync)
 		unsigned mask = __ballot_sync(0xffffffffu, alive);
+#if PTB_SHADE_BLOCK_COMPACT
+		// one atomic per BLOCK and iteration: the warps' counts meet in shared memory
+		{
+			const int warp = threadIdx.x >> 5;
+			if (lane == 0) s_cmp[warp] = __popc(mask);
+			__syncthreads();
+			if (threadIdx.x == 0)
+			{
+				int sum = 0;
+				for (int k = 0; k < 4; k++) { const int c = s_cmp[k]; s_cmp[k] = sum; sum += c; }
+				s_cmp[4] = sum ? atomicAdd(count_out, sum) : 0;
+			}
+			__syncthreads();
+			if (alive) queue_out[s_cmp[4] + s_cmp[warp] + __popc(mask & ((1u << lane) - 1u))] = id;
+			__syncthreads();
+		}
+#else
+		// one atomic per warp
 		if (mask)
 		{
 			int pos = 0;
@@ -435,6 +461,7 @@ __global__ void __launch_bounds__(128, PTB_SHADE_MIN_BLOCKS) k_shade(DeviceScene
 			pos = __shfl_sync(0xffffffffu, pos, 0);
 			if (alive) queue_out[pos + __popc(mask & ((1u << lane) - 1u))] = id;
 		}
+#endif
 		}
 		if (NEE)
 		{

@@ -63,7 +63,7 @@ def test_entry_cuts_find_the_same_hits_mix(workload_root, label, kw):
         assert seg == seg0, (label, k, tile)
 
 
-@pytest.mark.parametrize("name,size,scale", [("c2", (320, 180), 0.1), ("c3", (256, 144), 0.05), ("c4", (192, 108), 0.03), ("c1", (96, 96), 1.0)])
+@pytest.mark.parametrize("name,size,scale", [("c2", (320, 180), 0.1), ("c2", (300, 170), 0.1), ("c3", (256, 144), 0.05), ("c4", (192, 108), 0.03), ("c1", (96, 96), 1.0)])
 def test_entry_cuts_find_the_same_hits_baseline_configs(workload_root, name, size, scale):
     root, w = workload_root(name, width=size[0], height=size[1], tri_scale=scale)
     cam = camera(w)
