@@ -196,6 +196,9 @@ int ptb_get_traversal_histogram(ptb_renderer* r, int64_t* out25);
  *                                               root (csrc/kernels_entry.cuh: k_entry_cut, rebuilt when camera / geometry change;
  *                                               cameras it does not cover — focal distance <= 0, fov >= 175 degrees — use the root)
  *   "entry_k"            "1".."31" (default 15) sub-trees per tile; "entry_tile" "WxH" powers of two (default "8x4")
+ *   "sky_fast"           "1" (default) | "0"    with entry cuts: camera rays of tiles whose cut is EMPTY are finished by k_generate with the
+ *                                               background colour (never queued, searched or shaded); needs tile_order, 8x4 tiles, a
+ *                                               resolution that is a multiple of them, no spheres and air that does not participate
  *   "upwalk"             "1" (default) | "0"    a bounce ray that leaves a triangle starts at that triangle's leaf and collects the
  *                                               siblings of the leaf's ancestors it hits walking UP (k_up_level / k_up_pair records;
  *                                               takes effect at the next ptb_load_scene / geometry edit); "upwalk_min_nodes" (64):
