@@ -91,6 +91,9 @@ struct ptb_renderer
 	int bvh_layout = 2;
 	int bvh_hybrid = 1;                    // layout 2 only: also build the compressed 8-wide tree and trace depth >= hybrid_from_depth with it
 	int hybrid_from_depth = 2;             // measured: c2 -0.4 %, c3 +1.2 %, c4 +8.4 % against binary-only (from depth 1: c2 -2.8 %)
+	bool hybrid_from_user = false;         // hybrid_from_depth was set by the caller: small_tree_bytes does not override it
+	int64_t small_tree_bytes = 0;          // (off: 0) binary nodes + sibling records + triangles up to this size: EVERY bounce stays on the binary tree with leaf starts
+	                                       // (c2, 21 MB: +2 %; c3, 43 MB: +-0; c5, 720 MB: -7 % — the compact wide tree wins once the tree leaves the caches)
 	int64_t bvh8_nodes = 0;
 	int bvh_max_leaf = 8;                  // binary layout; the wide layout holds <= 3 per leaf slot
 	float bvh_intersect_cost = 0.8f;       // SAH cost of a triangle test relative to a node visit (measured optimum on c2, profiles/r01_experiments.md)
@@ -1168,7 +1171,9 @@ int enqueue_batch(ptb_renderer* r, ptb_renderer::BatchContext& ctx, cudaEvent_t 
 	// from the root for a segment one mean free path long
 	const bool have_up = r->upwalk && !r->nee && r->dscene.bvh_layout == 2 && r->extend_persistent && r->extend_variant == 0 && r->dscene.up_records != nullptr;
 	const bool fused_up = fused && have_up && r->fused_upwalk;
-	const int hybrid_from = fused_up ? 0x7fffffff : r->hybrid_from_depth;
+	const bool small_tree = have_up && !fused && !r->hybrid_from_user && r->small_tree_bytes > 0 &&
+		r->bvh_nodes * (int64_t)(64 + 128) + (int64_t)r->dscene.n_triangles * 48 <= r->small_tree_bytes;
+	const int hybrid_from = (fused_up || small_tree) ? 0x7fffffff : r->hybrid_from_depth;
 	const int fused_from = r->fused_from_depth >= 0 ? r->fused_from_depth : (fused_up ? (r->cfg.air_reduced_scattering_coef.x > 0.0f ? 0 : 1) : (r->dscene.bvh_layout == 8 ? 0 : std::max(r->hybrid_from_depth, 0)));
 	const int tally_counts = fused ? std::min(fused_from, n_counts) : n_counts;
 	const bool entry = entry_cuts_usable(r) && hybrid_from > 0 && !(fused && fused_from <= 0);
@@ -2174,7 +2179,8 @@ int ptb_set_option(ptb_renderer* r, const char* key, const char* value)
 	if (k == "persistent_grid8") { r->persistent_grid8 = atoi(value); return 0; }
 	if (k == "bvh_collapse") { if (v != "gpu" && v != "host") { set_error("[Error]bvh_collapse must be gpu or host"); return 1; } r->bvh_collapse = v; return 0; }
 	if (k == "bvh_hybrid") { r->bvh_hybrid = atoi(value); return 0; }             // takes effect at the next ptb_load_scene
-	if (k == "hybrid_from_depth") { r->hybrid_from_depth = atoi(value); return 0; }
+	if (k == "hybrid_from_depth") { r->hybrid_from_depth = atoi(value); r->hybrid_from_user = true; return 0; }
+	if (k == "small_tree_bytes") { r->small_tree_bytes = atoll(value); return 0; }
 	if (k == "bvh_layout")
 	{
 		int n = atoi(value);

@@ -221,7 +221,8 @@ def test_bvh_layouts_agree(workload_root):
     root, w = workload_root("c2", width=320, height=180, tri_scale=0.2)
     res = {}
     for layout in (2, 8):
-        r = gpu_renderer(w, root, bvh_layout=layout, count_traversal=1)
+        # hybrid_from_depth set explicitly: a tree this small would otherwise keep every bounce on the binary tree (small_tree_bytes)
+        r = gpu_renderer(w, root, bvh_layout=layout, count_traversal=1, hybrid_from_depth=2)
         rays = np.concatenate([r.generate_rays(1), r.capture_rays(1, 2)[1], r.capture_rays(2, 4)[1]], 0)
         prim, t, bary = r.trace_batch(rays, with_bary=True)
         r.render(2)
@@ -272,7 +273,7 @@ def test_scheduling_options_do_not_change_the_image(workload_root):
                  dict(bvh_layout=8), dict(octant_order=1), dict(extend_variant=1), dict(extend_variant=2), dict(extend_variant=3), dict(extend_variant=3, treelet_block=512, treelet_nodes=100), dict(extend_variant=4), dict(extend_variant=4, tune_refill4=1), dict(l2_persist=1), dict(inline_scatter=0), dict(inline_scatter=0, hybrid_from_depth=0), dict(tune_scatter=1), dict(tune_scatter=32, hybrid_from_depth=1), dict(fused_from_depth=0), dict(fused_from_depth=1, hybrid_from_depth=99), dict(fused_from_depth=3),
                  dict(fused_upwalk=0), dict(fused_upwalk=1, tune_scatter=1), dict(fused_upwalk=1, fused_from_depth=0), dict(fused_upwalk=1, fused_from_depth=3, tune_refill_f=1), dict(fused_upwalk=1, inline_scatter=0),
                  dict(upwalk=0), dict(upwalk=0, hybrid_from_depth=99), dict(upwalk=1, hybrid_from_depth=99), dict(upwalk=1, hybrid_from_depth=99, inline_scatter=0), dict(upwalk=1, hybrid_from_depth=3, tile_order=0),
-                 dict(sky_fast=0), dict(entry_cuts=0), dict(entry_k=1), dict(entry_k=15), dict(entry_cuts=0, tile_order=0), dict(entry_k=3, tile_order=0)):
+                 dict(small_tree_bytes=0), dict(small_tree_bytes=0, upwalk=0), dict(sky_fast=0), dict(entry_cuts=0), dict(entry_k=1), dict(entry_k=15), dict(entry_cuts=0, tile_order=0), dict(entry_k=3, tile_order=0)):
         r = gpu_renderer(w, root, **opts)
         r.set_camera(ptb.default_camera(w["width"], w["height"], w["aperture"], w["focal"]))
         r.render(5)
