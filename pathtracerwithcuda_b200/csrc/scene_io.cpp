@@ -1403,7 +1403,8 @@ bool parse_obj(const std::string& path, ObjData& out)
 	// Groups, shapes and triangulation in file order.  A group is flushed by the next `g` / `o` line or the end of the file and
 	// is triangulated with the vertices read up to there; its faces may lie in several slices: one run per slice.  The runs are
 	// triangulated by host threads (each face is independent), then appended to their shapes in order.
-	struct Run { size_t slice, f0, f1, n_vertices; ObjShape tris; bool failed = false; std::string error; };
+	// direct: every face of the run is a triangle, so its output IS the slice's index range [d0, d1) (checked, not copied)
+	struct Run { size_t slice, f0, f1, n_vertices; ObjShape tris; bool failed = false; std::string error; bool direct = false; size_t d0 = 0, d1 = 0; };
 	struct Group { size_t run0 = 0, run1 = 0; int kind = 0; };     // kind: the mark that flushed it (1 `g`, 2 `o`), 0 = end of file
 	std::vector<Run> runs;
 	std::vector<Group> groups;
@@ -1444,6 +1445,19 @@ bool parse_obj(const std::string& path, ObjData& out)
 			{
 				Run& r = runs[i];
 				const ObjSlice& sl = slices[r.slice];
+				{
+					// faces have >= 3 corners each: a run with exactly 3 per face on average holds triangles only, which the ear clipper
+					// passes through untouched — nothing to compute, only the vertex references to check
+					const size_t b0 = sl.face_start[r.f0], e1 = r.f1 < sl.face_start.size() ? sl.face_start[r.f1] : sl.idx.size();
+					if (e1 - b0 == 3 * (r.f1 - r.f0))
+					{
+						bool ok = true;
+						for (size_t k = b0; k < e1 && ok; k++) ok = sl.idx[k].v >= 0 && (size_t)sl.idx[k].v < r.n_vertices;
+						if (!ok) { r.failed = true; r.error = "[Error]OBJ face references a vertex that is not defined"; }
+						r.direct = true; r.d0 = b0; r.d1 = e1;
+						continue;
+					}
+				}
 				r.tris.indices.reserve((sl.face_start[r.f1 - 1] - sl.face_start[r.f0]) + 3);     // exact for triangles; polygons grow it
 				for (size_t f = r.f0; f < r.f1; f++)
 				{
@@ -1460,9 +1474,18 @@ bool parse_obj(const std::string& path, ObjData& out)
 	ObjShape shape;
 	for (const Group& g : groups)
 	{
+		size_t group_indices = 0;
+		for (size_t r = g.run0; r < g.run1; r++) group_indices += runs[r].direct ? runs[r].d1 - runs[r].d0 : runs[r].tris.indices.size();
 		for (size_t r = g.run0; r < g.run1; r++)
 		{
 			if (runs[r].failed) { set_error(runs[r].error); return false; }
+			if (runs[r].direct)
+			{
+				const std::vector<ObjIndex>& idx = slices[runs[r].slice].idx;
+				if (shape.indices.empty()) shape.indices.reserve(group_indices);
+				shape.indices.insert(shape.indices.end(), idx.begin() + (ptrdiff_t)runs[r].d0, idx.begin() + (ptrdiff_t)runs[r].d1);
+				continue;
+			}
 			if (shape.indices.empty()) shape.indices = std::move(runs[r].tris.indices);
 			else shape.indices.insert(shape.indices.end(), runs[r].tris.indices.begin(), runs[r].tris.indices.end());
 			runs[r].tris = ObjShape();
