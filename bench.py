@@ -42,20 +42,20 @@ PASSES_IN_FLIGHT = 16     # passes traced as one wavefront batch (tools/sweep_ba
 STREAMS_IN_FLIGHT = 4     # batches overlapped on separate CUDA streams
 METRIC = "path samples/sec (Mspp*px/s), 1080p"
 # Per-launch memory traffic of the closest-hit kernels from ONE `ncu --set full` capture of the shipped kernels (workload c2, one 16-pass
-# batch as benchmarked: d0 k_extend_entry over the camera rays k_generate did not finish itself, d1 k_extend_upwalk, d2-d7 k_extend_persistent8), averaged over the 8 depth launches of the batch
+# batch as benchmarked: d0 k_extend_entry over the camera rays k_generate did not finish itself, d1-d7 k_extend_upwalk — c2's tree is below small_tree_bytes), averaged over the 8 depth launches of the batch
 # like `avg_launch_ms` below — profiles/r02_extend_ncu_summary.md.  bench.py divides these by the launch duration it measures LIVE.
 NCU_CAPTURE = {
     "source": "profiles/r02_extend_ncu_summary.md",
     "workload": "c2", "passes_in_flight": 16,
-    "dram_bytes_per_launch": 288.4e6,         # dram__bytes_read.sum + dram__bytes_write.sum
-    "l2_bytes_per_launch": 2046.8e6,          # lts__t_bytes.sum
-    "l1_writeback_bytes_per_launch": 13425.3e6,   # l1tex__lsu_writeback_active_mem_lgds.sum (cycles) x 128 B: what the load instructions cost the L1 data pipe
-    "l1_tag_bytes_per_launch": 3399.5e6,      # l1tex__t_bytes.sum (distinct sectors x 32 B through the tag stage)
-    "limiters": {"time_weighted_d0_d7": {"sm__throughput_pct": 49.2, "issue_active_pct": 63.0, "l1_data_pipe_wavefronts_pct": 49.9, "l1_writeback_active_pct": 39.7,
-                                          "active_lanes_per_instruction": 18.9, "l1_hit_pct": 61.7, "l2_hit_pct": 67.9},
-                 "d0_d1": {"sm__throughput_pct": [66.3, 42.4], "issue_active_pct": [70.7, 61.4], "l1_data_pipe_wavefronts_pct": [43.8, 59.6],
-                           "active_lanes_per_instruction": [21.4, 18.6], "stall_long_scoreboard_per_issue": [3.85, 6.91], "alu_pipe_pct": [55.3, 50.8],
-                           "warp_instructions": [1.19e9, 2.02e9], "ms": [1.60, 4.16]},
+    "dram_bytes_per_launch": 291.1e6,         # dram__bytes_read.sum + dram__bytes_write.sum
+    "l2_bytes_per_launch": 2183.4e6,          # lts__t_bytes.sum
+    "l1_writeback_bytes_per_launch": 14001.7e6,   # l1tex__lsu_writeback_active_mem_lgds.sum (cycles) x 128 B: what the load instructions cost the L1 data pipe
+    "l1_tag_bytes_per_launch": 3324.1e6,      # l1tex__t_bytes.sum (distinct sectors x 32 B through the tag stage)
+    "limiters": {"time_weighted_d0_d7": {"sm__throughput_pct": 45.3, "issue_active_pct": 59.3, "l1_data_pipe_wavefronts_pct": 53.9, "l1_writeback_active_pct": 41.9,
+                                          "active_lanes_per_instruction": 18.4, "l1_hit_pct": 57.6, "l2_hit_pct": 68.9},
+                 "d0_d1": {"sm__throughput_pct": [66.0, 42.2], "issue_active_pct": [70.7, 61.4], "l1_data_pipe_wavefronts_pct": [43.6, 59.2],
+                           "active_lanes_per_instruction": [21.4, 18.6], "stall_long_scoreboard_per_issue": [3.84, 6.91], "alu_pipe_pct": [55.3, 50.8],
+                           "warp_instructions": [1.19e9, 2.02e9], "ms": [1.58, 4.17]},
                  "same_batch_with_root_starts": {"source": "profiles/r02_extend_ncu_summary_root_start.md", "d0_d1_ms": [3.41, 4.47], "d0_d1_warp_instructions": [2.64e9, 2.56e9],
                                                  "sm__throughput_pct_time_weighted": 56.8, "l1_writeback_bytes_per_launch": 22039.5e6}},
 }
@@ -503,7 +503,7 @@ def run_ptb200(args, w, root, rank, local_rank, world):
                            "scene_load_s": load_s},
                 "clocks": clocks, "gpu_launches": int(launches_total),
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 64, "d2h_bytes_per_step": int(u8.nbytes)},
-                "roofline": {"bound": bound, "kernel": "k_extend_entry (d0) / k_extend_upwalk (d1) / k_extend_persistent8 (d2+): closest hit", "achieved": achieved, "peak": peak,
+                "roofline": {"bound": bound, "kernel": "k_extend_entry (d0) / k_extend_upwalk (d1+; k_extend_persistent8 from d2 on trees above small_tree_bytes): closest hit", "achieved": achieved, "peak": peak,
                              "unit": "TFLOP/s" if bound == "fp32" else "GB/s", "frac": known.get(bound) if bound else None,
                              "traffic": ncu.get("dram_bytes_per_launch"),
                              "fracs": fracs,

@@ -186,6 +186,8 @@ int ptb_get_traversal_histogram(ptb_renderer* r, int64_t* out25);
  *   "bvh_layout"         "2" (default: 64-byte binary nodes) | "8" (80-byte compressed 8-wide nodes only)
  *   "bvh_hybrid"         "1" (default) | "0"    layout 2 only: also build the compressed wide tree for the deeper bounces
  *   "hybrid_from_depth"  "2" (default)          first bounce depth traced over the wide tree (immediate)
+ *   "small_tree_bytes"   bytes (default 64 MiB) binary nodes + sibling records + triangles up to this size: every bounce stays on the binary
+ *                                               tree with leaf starts ("upwalk"); an explicit hybrid_from_depth wins; "0" = off
  *   "bvh_collapse"       "gpu" (default) | "host"  where the binary tree is collapsed to 8-wide nodes
  *   "bvh_max_leaf"       "1".."8" (default 8)    triangles per leaf of the binary tree
  *   "bvh_intersect_cost" float > 0 (default 0.8) SAH cost of a triangle test relative to a node visit

@@ -92,8 +92,8 @@ struct ptb_renderer
 	int bvh_hybrid = 1;                    // layout 2 only: also build the compressed 8-wide tree and trace depth >= hybrid_from_depth with it
 	int hybrid_from_depth = 2;             // measured: c2 -0.4 %, c3 +1.2 %, c4 +8.4 % against binary-only (from depth 1: c2 -2.8 %)
 	bool hybrid_from_user = false;         // hybrid_from_depth was set by the caller: small_tree_bytes does not override it
-	int64_t small_tree_bytes = 0;          // (off: 0) binary nodes + sibling records + triangles up to this size: EVERY bounce stays on the binary tree with leaf starts
-	                                       // (c2, 21 MB: +2 %; c3, 43 MB: +-0; c5, 720 MB: -7 % — the compact wide tree wins once the tree leaves the caches)
+	int64_t small_tree_bytes = 64 << 20;   // binary nodes + sibling records + triangles up to this size: EVERY bounce stays on the binary tree with leaf starts
+	                                       // (c2, 21 MB: +1.8 %; c3, 43 MB: +1 %; c5, 720 MB: -7 % — the compact wide tree wins once the tree leaves the caches); 0 = off
 	int64_t bvh8_nodes = 0;
 	int bvh_max_leaf = 8;                  // binary layout; the wide layout holds <= 3 per leaf slot
 	float bvh_intersect_cost = 0.8f;       // SAH cost of a triangle test relative to a node visit (measured optimum on c2, profiles/r01_experiments.md)
