@@ -978,6 +978,15 @@ bool entry_cuts_usable(const ptb_renderer* r)
 	if (c.resolution[0] != (float)r->cfg.width || c.resolution[1] != (float)r->cfg.height || r->cfg.width < 2 || r->cfg.height < 2) return false;
 	if (!(c.aperture_radius < 0.25f * c.focal_distance)) return false;                      // (also rejects NaN)
 	for (int k = 0; k < 3; k++) if (!std::isfinite(c.eye[k]) || !std::isfinite(c.up[k])) return false;
+	// The generator forms eye + view + offsets and eye + direction * focal_distance in binary32 and subtracts the eye again
+	// (path_tracer_kernel.cu:299-379): a camera far from the origin relative to |view| / the focal distance loses direction bits there.  The
+	// shafts carry 1/16 pixel of slack for that; beyond 1/20 pixel of worst-case rounding the rays are searched from the root.
+	const float eye_max = std::max(std::fabs(c.eye[0]), std::max(std::fabs(c.eye[1]), std::fabs(c.eye[2])));
+	const float tan_x = std::tan(c.fov[0] * 0.5f * 3.14159265f / 180.0f), tan_y = std::tan(c.fov[1] * 0.5f * 3.14159265f / 180.0f);
+	const float pixel = std::min(2.0f * tan_x / (float)(r->cfg.width - 1), 2.0f * tan_y / (float)(r->cfg.height - 1));      // on a canvas at distance 1
+	const float ulp2 = 2.4e-7f;      // 2^-22
+	if (!(ulp2 * (eye_max + vl * (1.0f + tan_x + tan_y)) <= pixel * vl / 20.0f)) return false;
+	if (!(ulp2 * (eye_max + c.focal_distance) <= pixel * c.focal_distance / 20.0f)) return false;
 	return true;
 }
 

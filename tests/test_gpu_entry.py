@@ -143,3 +143,8 @@ def test_unusable_cameras_fall_back_to_the_root(workload_root):
     a, _ = render(w, root, cam, 2, entry_cuts=0)
     b, _ = render(w, root, cam, 2, entry_cuts=1)
     assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+    # a camera so far from the origin that the generator's binary32 sums lose direction bits beyond the shafts' slack: also from the root
+    far = camera(w, eye=(800.0, 300.0, 600.0), view=(-0.7619, -0.2857, -0.5714), aperture=0.0, fov_scale=0.02)
+    a, _ = render(w, root, far, 2, entry_cuts=0)
+    b, _ = render(w, root, far, 2, entry_cuts=1)
+    assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
