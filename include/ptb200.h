@@ -198,6 +198,9 @@ int ptb_get_traversal_histogram(ptb_renderer* r, int64_t* out25);
  *                                               root (csrc/kernels_entry.cuh: k_entry_cut, rebuilt when camera / geometry change;
  *                                               cameras it does not cover — focal distance <= 0, fov >= 175 degrees — use the root)
  *   "entry_k"            "1".."31" (default 15) sub-trees per tile; "entry_tile" "WxH" powers of two (default "8x4")
+ *   "entry_min_passes"   (default 4)            a batch of fewer passes builds the lists only for a camera the previous batch had too: a
+ *                                               host that moves the camera with every single-pass call is served from the root (building
+ *                                               the lists costs ~0.4 ms at 1080p, they save ~0.15 ms per pass)
  *   "sky_fast"           "1" (default) | "0"    with entry cuts: camera rays of tiles whose cut is EMPTY are finished by k_generate with the
  *                                               background colour (never queued, searched or shaded); needs tile_order, 8x4 tiles, a
  *                                               resolution that is a multiple of them, no spheres and air that does not participate

@@ -12,6 +12,7 @@ pytestmark = pytest.mark.gpu
 
 def render(w, root, cam, passes, **options):
     r = ptb.Renderer(w["config"], device=0)
+    r.set_option("entry_min_passes", 1)      # build the lists even for these 2-3 pass renders (default: from 4 passes per batch on, or for a camera seen before)
     for k, v in options.items():
         r.set_option(k, v)
     r.load_scene(w["scene"], root)
@@ -80,6 +81,7 @@ def test_entry_cuts_find_the_same_hits_baseline_configs(workload_root, name, siz
     r0 = ptb.Renderer(w["config"], device=0); r1 = ptb.Renderer(w["config"], device=0)
     for r, on in ((r0, 0), (r1, 1)):
         r.set_option("entry_cuts", on)
+        r.set_option("entry_min_passes", 1)
         r.load_scene(w["scene"], root)
         r.set_camera(cam)
         c = r.config().copy()
@@ -117,6 +119,7 @@ def test_entry_cuts_follow_camera_and_geometry_edits(workload_root):
     for on in (0, 1):
         r = ptb.Renderer(w["config"], device=0)
         r.set_option("entry_cuts", on)
+        r.set_option("entry_min_passes", 1)
         r.load_scene(w["scene"], root)
         rs.append(r)
     steps = [camera(w), camera(w, eye=(5.0, 2.0, -9.0), view=(-0.45, -0.15, 0.88)), camera(w, aperture=0.0, fov_scale=0.5)]
@@ -145,6 +148,7 @@ def test_entry_cuts_random_cameras(workload_root, name, kw):
     for on in (0, 1):
         r = ptb.Renderer(w["config"], device=0)
         r.set_option("entry_cuts", on)
+        r.set_option("entry_min_passes", 1)
         r.set_option("passes_in_flight", 2)
         r.load_scene(w["scene"], root)
         rs.append(r)
@@ -171,6 +175,27 @@ def test_entry_cuts_random_cameras(workload_root, name, kw):
         assert same, (i, eye.tolist(), view.tolist(), up.tolist(), cam.aperture_radius, cam.focal_distance, cam.fov[0])
     for r in rs:
         r.close()
+
+
+def test_lists_are_not_rebuilt_for_a_camera_that_moves_every_pass(workload_root):
+    """One pass per call with a new camera each time (a host dragging the view): the lists are not built (k_entry_cut would cost more than it
+    saves), the search starts at the root, the image is the same; the second call with an unchanged camera builds them."""
+    root, w = workload_root("c2", width=320, height=180, tri_scale=0.1)
+    r = ptb.Renderer(w["config"], device=0)
+    r.set_option("passes_in_flight", 1)
+    r.load_scene(w["scene"], root)
+    ref = ptb.Renderer(w["config"], device=0)
+    ref.set_option("passes_in_flight", 1); ref.set_option("entry_cuts", 0)
+    ref.load_scene(w["scene"], root)
+    launches = []
+    for i in range(6):
+        cam = camera(w, eye=(14.0 * np.sin(0.1 * i) , 4.0, 14.0 * np.cos(0.1 * i)), view=(-np.sin(0.1 * i), -0.28, -np.cos(0.1 * i))) if i < 4 else cam
+        for x in (r, ref):
+            x.set_camera(cam); x.clear(); x.render(1)
+        assert np.array_equal(r.image_f32().view(np.uint32), ref.image_f32().view(np.uint32)), i
+        launches.append(r.stats()["kernel_launches"])
+    # calls 0-3 (camera moved): no list build; call 4 is the second with the camera of call 3: + k_entry_cut + k_tile_rank; call 5: none again
+    assert launches[1] == launches[0] and launches[4] == launches[0] + 2 and launches[5] == launches[0], launches
 
 
 def test_unusable_cameras_fall_back_to_the_root(workload_root):
