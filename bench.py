@@ -47,15 +47,15 @@ METRIC = "path samples/sec (Mspp*px/s), 1080p"
 NCU_CAPTURE = {
     "source": "profiles/r02_extend_ncu_summary.md",
     "workload": "c2", "passes_in_flight": 16,
-    "dram_bytes_per_launch": 291.1e6,         # dram__bytes_read.sum + dram__bytes_write.sum
-    "l2_bytes_per_launch": 2183.4e6,          # lts__t_bytes.sum
-    "l1_writeback_bytes_per_launch": 14001.7e6,   # l1tex__lsu_writeback_active_mem_lgds.sum (cycles) x 128 B: what the load instructions cost the L1 data pipe
-    "l1_tag_bytes_per_launch": 3324.1e6,      # l1tex__t_bytes.sum (distinct sectors x 32 B through the tag stage)
-    "limiters": {"time_weighted_d0_d7": {"sm__throughput_pct": 45.3, "issue_active_pct": 59.3, "l1_data_pipe_wavefronts_pct": 53.9, "l1_writeback_active_pct": 41.9,
-                                          "active_lanes_per_instruction": 18.4, "l1_hit_pct": 57.6, "l2_hit_pct": 68.9},
-                 "d0_d1": {"sm__throughput_pct": [66.0, 42.2], "issue_active_pct": [70.7, 61.4], "l1_data_pipe_wavefronts_pct": [43.6, 59.2],
-                           "active_lanes_per_instruction": [21.4, 18.6], "stall_long_scoreboard_per_issue": [3.84, 6.91], "alu_pipe_pct": [55.3, 50.8],
-                           "warp_instructions": [1.19e9, 2.02e9], "ms": [1.58, 4.17]},
+    "dram_bytes_per_launch": 293.1e6,         # dram__bytes_read.sum + dram__bytes_write.sum
+    "l2_bytes_per_launch": 2443.4e6,          # lts__t_bytes.sum
+    "l1_writeback_bytes_per_launch": 14438.7e6,   # l1tex__lsu_writeback_active_mem_lgds.sum (cycles) x 128 B: what the load instructions cost the L1 data pipe
+    "l1_tag_bytes_per_launch": 3715.6e6,      # l1tex__t_bytes.sum (distinct sectors x 32 B through the tag stage)
+    "limiters": {"time_weighted_d0_d7": {"sm__throughput_pct": 46.9, "issue_active_pct": 61.4, "l1_data_pipe_wavefronts_pct": 57.2, "l1_writeback_active_pct": 44.1,
+                                          "active_lanes_per_instruction": 18.4, "l1_hit_pct": 59.7, "l2_hit_pct": 70.2},
+                 "d0_d1": {"sm__throughput_pct": [70.1, 43.3], "issue_active_pct": [75.3, 63.3], "l1_data_pipe_wavefronts_pct": [51.3, 61.7],
+                           "active_lanes_per_instruction": [21.3, 18.6], "stall_long_scoreboard_per_issue": [3.93, 8.01],
+                           "warp_instructions": [1.22e9, 2.04e9], "ms": [1.52, 4.12], "registers": 48, "resident_blocks_per_sm": 10},
                  "same_batch_with_root_starts": {"source": "profiles/r02_extend_ncu_summary_root_start.md", "d0_d1_ms": [3.41, 4.47], "d0_d1_warp_instructions": [2.64e9, 2.56e9],
                                                  "sm__throughput_pct_time_weighted": 56.8, "l1_writeback_bytes_per_launch": 22039.5e6}},
 }

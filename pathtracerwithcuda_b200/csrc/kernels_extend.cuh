@@ -307,8 +307,12 @@ __device__ __forceinline__ void load_node(const float4* np, float4& n0, float4& 
 	n3 = __ldg(reinterpret_cast<const float2*>(np + 3));
 #endif
 }
+// resident blocks per SM the binary-tree kernels are compiled for.  8 (<= 64 registers: 54-56 used, 9 blocks fit) was the optimum while the
+// searches started at the root and the kernels were issue-bound; with entry cuts and leaf starts they wait on dependent fetches, and 10
+// blocks (48 registers, 8-12 bytes of spills) read c2 4443 -> 4529, c5 3647 -> 3739 Msamples/s; 12 blocks (40 registers, 60-70 bytes of
+// spills) 4325 / 3663 (profiles/r02_experiments.md).  The wide-tree kernels stay at 8 (9 / 10: c4 830 -> 818 / 815).
 #ifndef PTB_PERSISTENT_MIN_BLOCKS
-#define PTB_PERSISTENT_MIN_BLOCKS 8
+#define PTB_PERSISTENT_MIN_BLOCKS 10
 #endif
 #ifndef PTB_PERSISTENT_MIN_BLOCKS8
 #define PTB_PERSISTENT_MIN_BLOCKS8 8
