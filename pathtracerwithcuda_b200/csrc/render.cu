@@ -768,32 +768,34 @@ int upload_geometry(ptb_renderer* r)
 		const int n_nodes = (int)r->bvh_nodes;
 		float4* up = nullptr; int* tri_slot = nullptr; int2* frontier[2] = { nullptr, nullptr }; int* level_counts = nullptr;
 		const int levels = PTB_STACK_SIZE + 2;
+		// (an accelerator, not a requirement: without memory for the records the bounce rays start at the root)
 		float4* up1 = nullptr;      // one level per record (k_up_level), paired into `up` below
-		PTB_CUDA(cudaMalloc(&up1, (size_t)n_nodes * 64));
-		PTB_CUDA(cudaMemsetAsync(up1, 0xff, (size_t)n_nodes * 64, r->stream));      // unused pool slots of the node array read "no parent"
-		PTB_CUDA(cudaMalloc(&up, (size_t)n_nodes * 128));
-		G->push_back(up);
-		PTB_CUDA(cudaMalloc(&tri_slot, (size_t)n_tris * sizeof(int)));
-		G->push_back(tri_slot);
-		PTB_CUDA(cudaMalloc(&frontier[0], (size_t)n_nodes * sizeof(int2)));
-		PTB_CUDA(cudaMalloc(&frontier[1], (size_t)n_nodes * sizeof(int2)));
-		PTB_CUDA(cudaMalloc(&level_counts, (levels + 1) * sizeof(int)));
-		PTB_CUDA(cudaMemsetAsync(tri_slot, 0xff, (size_t)n_tris * sizeof(int), r->stream));
-		PTB_CUDA(cudaMemsetAsync(level_counts, 0, (levels + 1) * sizeof(int), r->stream));
-		const int2 root_entry = make_int2(ds.root_ref, -1);
-		const int one = 1;
-		PTB_CUDA(cudaMemcpyAsync(frontier[0], &root_entry, sizeof(int2), cudaMemcpyHostToDevice, r->stream));
-		PTB_CUDA(cudaMemcpyAsync(level_counts, &one, sizeof(int), cudaMemcpyHostToDevice, r->stream));
-		PTB_CUDA(cudaStreamSynchronize(r->stream));   // the two host words above are stack variables
-		const int grid = std::max(1, std::min((n_nodes + 127) / 128, r->sm_count * 8));
-		for (int level = 0; level < levels; level++)
-			k_up_level<<<grid, 128, 0, r->stream>>>(ds.bvh_nodes, ds.tri_isect, frontier[level & 1], frontier[(level + 1) & 1], level_counts, level, n_nodes, up1, tri_slot, n_tris);
-		k_up_pair<<<(n_nodes * 2 + 127) / 128, 128, 0, r->stream>>>(up1, up, n_nodes * 2);
-		PTB_CUDA(cudaStreamSynchronize(r->stream));
+		bool have = cudaMalloc(&up1, (size_t)n_nodes * 64) == cudaSuccess && cudaMalloc(&up, (size_t)n_nodes * 128) == cudaSuccess &&
+			cudaMalloc(&tri_slot, (size_t)n_tris * sizeof(int)) == cudaSuccess && cudaMalloc(&frontier[0], (size_t)n_nodes * sizeof(int2)) == cudaSuccess &&
+			cudaMalloc(&frontier[1], (size_t)n_nodes * sizeof(int2)) == cudaSuccess && cudaMalloc(&level_counts, (levels + 1) * sizeof(int)) == cudaSuccess;
+		if (have)
+		{
+			PTB_CUDA(cudaMemsetAsync(up1, 0xff, (size_t)n_nodes * 64, r->stream));      // unused pool slots of the node array read "no parent"
+			PTB_CUDA(cudaMemsetAsync(tri_slot, 0xff, (size_t)n_tris * sizeof(int), r->stream));
+			PTB_CUDA(cudaMemsetAsync(level_counts, 0, (levels + 1) * sizeof(int), r->stream));
+			const int2 root_entry = make_int2(ds.root_ref, -1);
+			const int one = 1;
+			PTB_CUDA(cudaMemcpyAsync(frontier[0], &root_entry, sizeof(int2), cudaMemcpyHostToDevice, r->stream));
+			PTB_CUDA(cudaMemcpyAsync(level_counts, &one, sizeof(int), cudaMemcpyHostToDevice, r->stream));
+			PTB_CUDA(cudaStreamSynchronize(r->stream));   // the two host words above are stack variables
+			const int grid = std::max(1, std::min((n_nodes + 127) / 128, r->sm_count * 8));
+			for (int level = 0; level < levels; level++)
+				k_up_level<<<grid, 128, 0, r->stream>>>(ds.bvh_nodes, ds.tri_isect, frontier[level & 1], frontier[(level + 1) & 1], level_counts, level, n_nodes, up1, tri_slot, n_tris);
+			k_up_pair<<<(n_nodes * 2 + 127) / 128, 128, 0, r->stream>>>(up1, up, n_nodes * 2);
+			PTB_CUDA(cudaStreamSynchronize(r->stream));
+			PTB_CUDA(cudaGetLastError());
+		}
+		else cudaGetLastError();
 		cudaFree(frontier[0]); cudaFree(frontier[1]); cudaFree(level_counts); cudaFree(up1);
-		PTB_CUDA(cudaGetLastError());
+		if (!have) { cudaFree(up); cudaFree(tri_slot); up = nullptr; tri_slot = nullptr; }
+		else { G->push_back(up); G->push_back(tri_slot); }
 		ds.up_records = up; ds.tri_slot = tri_slot;
-		r->bvh_bytes += (int64_t)n_nodes * 128 + (int64_t)n_tris * 4;
+		if (have) r->bvh_bytes += (int64_t)n_nodes * 128 + (int64_t)n_tris * 4;
 	}
 	PTB_CUDA(cudaStreamSynchronize(r->stream));
 	PTB_CUDA(cudaGetLastError());
@@ -1022,16 +1024,17 @@ int ensure_entry_cuts(ptb_renderer* r, cudaStream_t stream, int n_slots)
 	PTB_CUDA(cudaDeviceSynchronize());
 	r->entry_stride = 2;
 	while (r->entry_stride < r->entry_k + 1) r->entry_stride *= 2;
+	// the lists are an accelerator, not a requirement: without memory for them the searches start at the root
 	if (n_tiles * r->entry_stride > r->entry_buf_slots)
 	{
 		cudaFree(r->entry_buf); r->entry_buf = nullptr; r->entry_buf_slots = 0;
-		PTB_CUDA(cudaMalloc(&r->entry_buf, n_tiles * r->entry_stride * sizeof(int2)));
+		if (cudaMalloc(&r->entry_buf, n_tiles * r->entry_stride * sizeof(int2)) != cudaSuccess) { cudaGetLastError(); r->entry_buf = nullptr; r->entry_valid = false; return 0; }
 		r->entry_buf_slots = n_tiles * r->entry_stride;
 	}
 	if (n_tiles > r->entry_rank_tiles)
 	{
 		cudaFree(r->entry_rank); r->entry_rank = nullptr; r->entry_rank_tiles = 0;
-		PTB_CUDA(cudaMalloc(&r->entry_rank, (n_tiles + 1) * sizeof(int)));
+		if (cudaMalloc(&r->entry_rank, (n_tiles + 1) * sizeof(int)) != cudaSuccess) { cudaGetLastError(); r->entry_rank = nullptr; r->entry_valid = false; return 0; }
 		r->entry_rank_tiles = n_tiles;
 	}
 	k_entry_cut<<<(int)((n_tiles + 127) / 128), 128, 0, stream>>>(r->dscene, camera_params(r->cam), r->cfg.width, r->cfg.height, tiles_x, (int)n_tiles, r->entry_k, r->entry_tile_w, r->entry_tile_h, r->entry_stride, r->entry_buf);
