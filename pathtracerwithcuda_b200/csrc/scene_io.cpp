@@ -1560,8 +1560,10 @@ static bool append_mesh(HostScene& scene, const std::string& path, const Vec3& p
 	scene.triangle_material.resize((size_t)triangle_base + total);
 	PTB_TRACE("mesh resize");
 	std::atomic<bool> bad_index(false);
+	std::atomic<bool> out_of_range(false);      // mesh_in_range's test, made while the triangle is at hand instead of in a second, single-threaded pass
 	auto fill = [&](size_t t_begin, size_t t_end)
 	{
+		bool range_ok = true;
 		size_t si = 0;
 		for (size_t t = t_begin; t < t_end; t++)
 		{
@@ -1595,10 +1597,15 @@ static bool append_mesh(HostScene& scene, const std::string& path, const Vec3& p
 				*uu[k] = has_uv ? Vec2{ obj.vt[ix.vt * 2], obj.vt[ix.vt * 2 + 1] } : Vec2{ 0.0f, 0.0f };
 				*lv[k] = Vec3{ p.x, p.y, p.z }; *ln[k] = n1; *lu[k] = *uu[k];
 			}
+			{
+				const float c[9] = { tri.v0.x, tri.v0.y, tri.v0.z, tri.v1.x, tri.v1.y, tri.v1.z, tri.v2.x, tri.v2.y, tri.v2.z };
+				for (float x : c) if (!(std::fabs(x) <= 1e18f)) range_ok = false;     // also false for NaN
+			}
 			scene.triangles[(size_t)triangle_base + t] = tri;
 			scene.local_triangles[(size_t)triangle_base + t] = local;
 			scene.triangle_material[(size_t)triangle_base + t] = material_base + mat_index;
 		}
+		if (!range_ok) out_of_range = true;
 	};
 	{
 		const size_t hw = std::max(1u, std::thread::hardware_concurrency());
@@ -1631,7 +1638,7 @@ static bool append_mesh(HostScene& scene, const std::string& path, const Vec3& p
 	info.first_triangle = triangle_base; info.triangle_count = mesh_triangles;
 	info.first_material = material_base; info.material_count = mat_num;
 	info.position = position; info.scale = scale_v; info.rotate = rotate_v; info.rotate_applied = rotate_v;
-	if (!mesh_in_range(scene, info)) { set_error("[Error]Mesh " + path + " has vertices outside the supported range (non-finite or beyond 1e18)"); return false; }
+	if (out_of_range) { set_error("[Error]Mesh " + path + " has vertices outside the supported range (non-finite or beyond 1e18)"); return false; }
 	scene.meshes.push_back(info);
 	PTB_TRACE("mesh range check");
 	return true;
