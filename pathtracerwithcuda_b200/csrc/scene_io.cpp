@@ -1174,6 +1174,7 @@ struct LoadTrace
 #endif
 
 int g_loader_threads = 0;   // 0: by file size and host cores (set_loader_threads / option "loader_threads")
+int g_loader_per_vertex = 1;   // append_mesh transforms every position / normal once instead of once per triangle corner (option "loader_per_vertex"; same output)
 
 // One slice of the file (whole lines), parsed by one host thread.  Negative (relative) face indices need the number of
 // v / vn / vt lines before the face, so a first pass counts them per slice and a prefix sum gives every slice its base.
@@ -1560,6 +1561,41 @@ static bool append_mesh(HostScene& scene, const std::string& path, const Vec3& p
 	scene.triangle_material.resize((size_t)triangle_base + total);
 	PTB_TRACE("mesh resize");
 	std::atomic<bool> bad_index(false);
+	// A vertex is shared by about six triangles of a closed mesh: when the file has fewer positions + normals than triangle corners, every
+	// position and normal is transformed ONCE (same arithmetic per element, so the triangles are bit-identical to transforming per corner)
+	// and the triangles only gather.
+	const bool per_vertex = g_loader_per_vertex > 0 && (total >= 65536 || g_loader_per_vertex > 1) && nv + nn <= total * 2;      // 2: also for small meshes (tests)
+	std::vector<Vec3, DefaultInitAllocator<Vec3>> local_p, world_p, local_n, world_n;
+	if (per_vertex)
+	{
+		local_p.resize(nv); world_p.resize(nv); local_n.resize(nn); world_n.resize(nn);
+		auto xform = [&](size_t b, size_t e, bool normals)
+		{
+			for (size_t i = b; i < e; i++)
+			{
+				if (!normals)
+				{
+					V4 p = transform(rot, v4(obj.v[i * 3], obj.v[i * 3 + 1], obj.v[i * 3 + 2], 1.0f));
+					V4 pw = transform(xf, v4(p.x, p.y, p.z, 1.0f));
+					local_p[i] = Vec3{ p.x, p.y, p.z }; world_p[i] = Vec3{ pw.x, pw.y, pw.z };
+				}
+				else
+				{
+					V4 n = transform(rot_it, v4(obj.vn[i * 3], obj.vn[i * 3 + 1], obj.vn[i * 3 + 2], 0.0f));
+					Vec3 n1 = normalize_host(n.x, n.y, n.z);
+					V4 nw = transform(xf_it, v4(n1.x, n1.y, n1.z, 0.0f));
+					local_n[i] = n1; world_n[i] = normalize_host(nw.x, nw.y, nw.z);
+				}
+			}
+		};
+		const size_t hw = std::max(1u, std::thread::hardware_concurrency());
+		const size_t n_threads = std::min<size_t>(16, hw);
+		WorkerGroup group;
+		for (size_t w = 1; w < n_threads; w++)
+			group.spawn([&xform, w, n_threads, nv, nn] { xform(nv * w / n_threads, nv * (w + 1) / n_threads, false); xform(nn * w / n_threads, nn * (w + 1) / n_threads, true); });
+		group.run_here([&] { xform(0, nv / n_threads, false); xform(0, nn / n_threads, true); });
+		group.finish();
+	}
 	std::atomic<bool> out_of_range(false);      // mesh_in_range's test, made while the triangle is at hand instead of in a second, single-threaded pass
 	auto fill = [&](size_t t_begin, size_t t_end)
 	{
@@ -1585,6 +1621,13 @@ static bool append_mesh(HostScene& scene, const std::string& path, const Vec3& p
 				{
 					bad_index = true;
 					return;
+				}
+				if (per_vertex)
+				{
+					*vv[k] = world_p[ix.v]; *nn3[k] = world_n[ix.vn];
+					*uu[k] = has_uv ? Vec2{ obj.vt[ix.vt * 2], obj.vt[ix.vt * 2 + 1] } : Vec2{ 0.0f, 0.0f };
+					*lv[k] = local_p[ix.v]; *ln[k] = local_n[ix.vn]; *lu[k] = *uu[k];
+					continue;
 				}
 				V4 p = transform(rot, v4(obj.v[ix.v * 3], obj.v[ix.v * 3 + 1], obj.v[ix.v * 3 + 2], 1.0f));
 				V4 n = transform(rot_it, v4(obj.vn[ix.vn * 3], obj.vn[ix.vn * 3 + 1], obj.vn[ix.vn * 3 + 2], 0.0f));
@@ -1752,6 +1795,7 @@ bool apply_mesh_rotate(HostScene& scene, int mesh, const Vec3& rotate_v)
 // ------------------------------------------------------------------------------------------
 
 void set_loader_threads(int n) { g_loader_threads = n < 0 ? 0 : n > 64 ? 64 : n; }
+void set_loader_per_vertex(int mode) { g_loader_per_vertex = mode < 0 ? 0 : mode > 2 ? 2 : mode; }
 
 bool load_scene(const std::string& scene_json_path, const std::string& asset_root, HostScene& scene)
 {

@@ -94,6 +94,32 @@ def _random_obj(seed, n_blocks):
     return "".join(l + rnd.choice(["\n", "\r\n", "\n", "\r"]) for l in lines)
 
 
+def test_world_triangles_per_vertex_equal_per_corner(workload_root):
+    """append_mesh transforms every position / normal of a large mesh once per VERTEX instead of once per triangle corner (scene_io.cpp,
+    loader_per_vertex); the world-space triangles — and the object-space copies a later transform edit starts from — must be the same bits.
+    Checked on the golden scenes' own files (mode 2 forces the per-vertex path for small meshes) and on a 75 k-triangle blob (mode 1)."""
+    cases = [workload_root("mix", width=96, height=72), workload_root("c2", width=64, height=36, tri_scale=1.0)]
+    r = ptb.Renderer(cases[0][1]["config"], device=-1)
+    try:
+        for root, w in cases:
+            got = {}
+            for mode in (0, 1, 2):
+                r.set_option("loader_per_vertex", mode)
+                r.load_scene(w["scene"], root)
+                tri, mat = r.scene_triangles()
+                r.set_mesh_transform(1, position=(0.3, -0.2, 0.1), scale=(1.1, 0.9, 1.3))      # re-transforms the object-space copies
+                r.apply_mesh_rotate(1, (10.0, 20.0, 5.0))
+                tri2, _ = r.scene_triangles()
+                got[mode] = (tri.copy(), mat.copy(), tri2.copy())
+            for mode in (1, 2):
+                for a, b in zip(got[0], got[mode]):
+                    assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), (w["scene"], mode)
+            assert got[0][0].shape[0] == w["triangles"]
+    finally:
+        r.set_option("loader_per_vertex", 1)
+        r.close()
+
+
 def test_obj_parsed_in_slices_is_identical(workload_root):
     """Large OBJ files are cut into slices of whole lines parsed by host threads (scene_io.cpp parse_obj); relative indices,
     groups and the triangulation's vertex count must come out as in one sequential pass (tiny_obj_loader.h:1700-1830)."""
