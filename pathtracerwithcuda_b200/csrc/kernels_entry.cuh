@@ -11,7 +11,11 @@
 //
 // Correctness: every state of the list covers all triangles whose boxes overlap the shaft, the overlap test and the distance bound are
 // conservative (margins below), so the rays find exactly the hits a search from the root finds (closest hit with the same acceptance
-// arithmetic; tests/test_gpu_entry.py compares hit records bit for bit).  Included by render.cu only.
+// arithmetic; tests/test_gpu_entry.py compares the accumulated images and the per-depth segment counts bit for bit over hand-picked and
+// random cameras; tests/test_entry_shaft_math.py pins the lens derivation).  render.cu only builds the lists for cameras whose generator
+// arithmetic stays within the shafts' slack (entry_cuts_usable) and for batches that amortise the build (ensure_entry_cuts).
+// The same file holds k_tile_rank (queue positions of the non-empty tiles, for k_generate's sky fast path) and the sibling records of
+// the bounce rays' leaf starts (k_up_level, k_up_pair).  Included by render.cu only.
 #pragma once
 #include <cuda_runtime.h>
 #include <math_constants.h>
