@@ -238,6 +238,7 @@ int ptb_get_traversal_histogram(ptb_renderer* r, int64_t* out25);
  *   "count_traversal"    "0" | "1"   instrumented kernels: node visits / triangle tests (ptb_stats, ptb_get_traversal_histogram)
  *  loader (process-wide)
  *   "loader_threads"     "0".."64"   slices an OBJ file is parsed in; 0 = by file size and host cores
+ *   "loader_mesh_lanes"  "0".."8"    mesh files parsed at the same time; 0 = max(2, host cores / threads per file)
  *   "loader_per_vertex"  "1" (default) | "0" | "2"   world-space triangles from positions / normals transformed once per VERTEX (meshes of
  *                                    >= 65536 triangles; "2": every mesh) or once per triangle corner ("0"); the output is the same bit for bit */
 int ptb_set_option(ptb_renderer* r, const char* key, const char* value);

@@ -2121,6 +2121,7 @@ int ptb_set_option(ptb_renderer* r, const char* key, const char* value)
 	if (k == "bvh_max_leaf") { int n = atoi(value); if (n < 1 || n > 8) { set_error("[Error]bvh_max_leaf must be in 1..8"); return 1; } r->bvh_max_leaf = n; return 0; }
 	if (k == "bvh_intersect_cost") { float c = (float)atof(value); if (!(c > 0.0f)) { set_error("[Error]bvh_intersect_cost must be > 0"); return 1; } r->bvh_intersect_cost = c; return 0; }
 	if (k == "loader_threads") { set_loader_threads(atoi(value)); return 0; }   // process-wide, like ptb_set_jpeg_decode
+	if (k == "loader_mesh_lanes") { set_loader_mesh_lanes(atoi(value)); return 0; }   // process-wide
 	if (k == "loader_per_vertex") { set_loader_per_vertex(atoi(value)); return 0; }   // process-wide
 	if (k == "tile_order") { r->tile_order = atoi(value); return 0; }
 	if (k == "l2_persist") { r->l2_persist = atoi(value) != 0; return 0; }      // takes effect at the next ptb_load_scene / geometry edit

@@ -121,6 +121,7 @@ void set_jpeg_mode(int mode);
 int jpeg_mode();
 // OBJ text is parsed in this many slices by host threads (0 = chosen from the file size and the host's cores)
 void set_loader_threads(int n);
+void set_loader_mesh_lanes(int n);      // mesh files parsed at the same time (0: by host cores)
 void set_loader_per_vertex(int mode);   // 0: per triangle corner, 1 (default): per vertex for meshes of >= 65536 triangles, 2: per vertex always
 // live edits with the reference's arithmetic: triangle_mesh::set_transform_device (triangle_mesh.cpp:271-328)
 // and set_rotate + apply_rotate (:330-426).  They rewrite `triangles` (and `local_triangles`) of one mesh.

@@ -289,6 +289,25 @@ def test_scene_errors(workload_root, tmp_path):
     assert r.scene_counts()["triangles"] == 0 and r.scene_counts()["cube_length"] == 64
 
 
+def test_mesh_files_parsed_side_by_side(workload_root, tmp_path):
+    """A host with more cores than one file's parser threads reads several mesh FILES at the same time (scene_io.cpp load_scene; option
+    loader_mesh_lanes, 0 = by host cores).  Forced to 3 lanes here (and to a single slice per file, so that the lanes are the only
+    concurrency): the golden scenes load bit-identically and a failing mesh is reported exactly as when the files are read in order."""
+    root, w = workload_root("mix", width=96, height=72)
+    r = ptb.Renderer(w["config"], device=-1)
+    try:
+        for lanes, threads in ((3, 0), (8, 1), (2, 4)):
+            r.set_option("loader_mesh_lanes", lanes)
+            r.set_option("loader_threads", threads)
+            test_scene_bit_exact_vs_reference_loader(workload_root, "mix", dict(width=96, height=72))
+            test_scene_bit_exact_vs_reference_loader(workload_root, "c1", dict(width=64, height=64))
+            test_scene_errors(workload_root, tmp_path)
+    finally:
+        r.set_option("loader_mesh_lanes", 0)
+        r.set_option("loader_threads", 0)
+        r.close()
+
+
 def test_images_bmp_and_tga(tmp_path):
     # BMP written bottom-up and a TGA (top-left origin, RLE) decode to the same top-down RGBA8
     rgb = (np.arange(5 * 7 * 3) * 7 % 256).astype(np.uint8).reshape(5, 7, 3)
