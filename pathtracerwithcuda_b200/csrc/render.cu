@@ -403,7 +403,9 @@ int upload(ptb_renderer* r, const T* host, size_t count, const T** out, std::vec
 	size_t bytes = std::max<size_t>(count * sizeof(T), 16);
 	PTB_CUDA(cudaMalloc(&d, bytes));
 	(group ? *group : r->scene_allocs).push_back(d);
-	if (count * sizeof(T) >= (8u << 20)) { if (staged_copy(d, host, count * sizeof(T), true, r->stream)) return 1; }
+	// staged through pinned chunks from 48 MB on: below that the driver's own pageable copy takes a few milliseconds, while pinning this
+	// thread's 64 MB of staging memory for the first time took 0.1-0.8 s on some boxes (c2's 14 MB of triangles: load 0.09 -> 0.9 s there)
+	if (count * sizeof(T) >= (48u << 20)) { if (staged_copy(d, host, count * sizeof(T), true, r->stream)) return 1; }
 	else if (count) PTB_CUDA(cudaMemcpyAsync(d, host, count * sizeof(T), cudaMemcpyHostToDevice, r->stream));
 	*out = (const T*)d;
 	return 0;
